@@ -1,0 +1,305 @@
+"""Host-side mirror of Candela's ``RayIntersector<T>`` (Source/Core/BVH/Intersector.h:60-124) over
+the C ABI in include/candela_b200.h.  Method names and argument meaning follow the reference;
+where the reference throws a string literal this raises ``CandelaError`` with the same text.
+
+This is ctypes glue only: every query runs in libcandela_b200.so on the GPU.  There is no CPU
+path; importing on a machine without the compiled library or without a B200 fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import _build
+
+STACKLESS, STACK = 0, 1  # BVH::StacklessTraversalNode / BVH::StackTraversalNode (Intersector.h:39-40)
+BUILDER_SAH_EXACT, BUILDER_LBVH = 0, 1
+SWAP_NONE, SWAP_HASHED = 0, 1
+IGNORE_TRANSPARENT = 1
+
+VERTEX_DT = np.dtype([("position", "<f4", 4), ("normal_tangent", "<u4", 3), ("texcoords", "<u4")])
+TRIANGLE_DT = np.dtype([("v", "<i4", 3), ("mesh", "<i4")])
+NODE_DT = np.dtype([("min", "<f4", 4), ("max", "<f4", 4)])
+STACK_NODE_DT = np.dtype([("lmin", "<f4", 4), ("lmax", "<f4", 4), ("rmin", "<f4", 4), ("rmax", "<f4", 4)])
+ENTITY_DT = np.dtype([("model", "<f4", 16), ("inverse", "<f4", 16), ("node_offset", "<i4"), ("node_count", "<i4"), ("data", "<i4", 14)])
+RAY_DT = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
+HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("w", "<f4"), ("mesh", "<i4"), ("tri", "<i4"), ("entity", "<i4"), ("iters", "<i4")])
+
+EXPORTS = [
+    "cndl_abi_version", "cndl_create", "cndl_destroy", "cndl_last_error", "cndl_add_object", "cndl_add_prebuilt_object",
+    "cndl_node_count", "cndl_triangle_count", "cndl_vertex_count", "cndl_get_object", "cndl_commit", "cndl_read_buffers",
+    "cndl_device_buffers", "cndl_push_entity", "cndl_push_entity_records", "cndl_buffer_entities", "cndl_entity_count",
+    "cndl_intersect_closest", "cndl_intersect_any", "cndl_intersect_closest_device", "cndl_intersect_any_device",
+    "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_host_alloc", "cndl_host_free",
+    "cndl_set_traversal_mode", "cndl_launch_count", "cndl_last_build_ms",
+]
+
+
+class CandelaError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+        self.message = message
+
+
+class BuildOpts(C.Structure):
+    _fields_ = [("builder", C.c_int32), ("swap_policy", C.c_int32), ("swap_seed", C.c_uint64)]
+
+
+_lib = None
+
+
+def library_path() -> Path:
+    return _build.LIB
+
+
+def load_library() -> C.CDLL:
+    """Loads libcandela_b200.so. Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _build.LIB.exists():
+        raise ImportError(f"{_build.LIB} is missing: run `python -m candela_b200._build` (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(str(_build.LIB))
+    vp, sz, i32p = C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)
+    L.cndl_abi_version.restype = C.c_int
+    L.cndl_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    L.cndl_destroy.argtypes = [vp]
+    L.cndl_destroy.restype = None
+    L.cndl_last_error.argtypes = [vp]
+    L.cndl_last_error.restype = C.c_char_p
+    L.cndl_add_object.argtypes = [vp, C.c_uint32, vp, sz, vp, sz, vp, C.POINTER(BuildOpts)]
+    L.cndl_add_prebuilt_object.argtypes = [vp, C.c_uint32, vp, sz, vp, sz, vp, sz]
+    for f in ("cndl_node_count", "cndl_triangle_count", "cndl_vertex_count", "cndl_entity_count"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = sz
+    L.cndl_get_object.argtypes = [vp, C.c_uint32, i32p, i32p, i32p, i32p]
+    L.cndl_commit.argtypes = [vp, C.c_int]
+    L.cndl_read_buffers.argtypes = [vp, vp, vp, vp]
+    L.cndl_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.cndl_push_entity.argtypes = [vp, C.c_uint32, vp, C.c_float, C.c_float]
+    L.cndl_push_entity_records.argtypes = [vp, vp, sz]
+    L.cndl_buffer_entities.argtypes = [vp]
+    L.cndl_intersect_closest.argtypes = [vp, vp, sz, C.c_int, vp]
+    L.cndl_intersect_any.argtypes = [vp, vp, sz, vp]
+    L.cndl_intersect_closest_device.argtypes = [vp, vp, sz, C.c_int, vp, vp]
+    L.cndl_intersect_any_device.argtypes = [vp, vp, sz, vp, vp]
+    L.cndl_intersect_primary.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
+    L.cndl_intersect_primary_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+    L.cndl_host_alloc.argtypes = [sz]
+    L.cndl_host_alloc.restype = vp
+    L.cndl_host_free.argtypes = [vp]
+    L.cndl_host_free.restype = None
+    L.cndl_set_traversal_mode.argtypes = [vp, C.c_int, C.c_int]
+    L.cndl_launch_count.argtypes = [vp]
+    L.cndl_launch_count.restype = C.c_uint64
+    L.cndl_last_build_ms.argtypes = [vp]
+    L.cndl_last_build_ms.restype = C.c_float
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _colmajor(m) -> np.ndarray:
+    """4x4 (row, column) matrix -> 16 floats column-major, glm's storage."""
+    return np.ascontiguousarray(np.asarray(m, dtype=np.float32).reshape(4, 4).T).ravel()
+
+
+def make_vertices(positions) -> np.ndarray:
+    """32-byte Vertex records (Utils/Vertex.h:7-12) with w = 1 and zero packed attributes."""
+    positions = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+    v = np.zeros(len(positions), dtype=VERTEX_DT)
+    v["position"][:, :3] = positions
+    v["position"][:, 3] = 1.0
+    return v
+
+
+def make_rays(origins, directions, tmax=0.0) -> np.ndarray:
+    o = np.asarray(origins, dtype=np.float32).reshape(-1, 3)
+    r = np.zeros(len(o), dtype=RAY_DT)
+    r["o"] = o
+    r["d"] = np.asarray(directions, dtype=np.float32).reshape(-1, 3)
+    r["tmax"] = tmax
+    return r
+
+
+class PinnedBuffer:
+    """cndl_host_alloc()'d memory viewed as a numpy array (for ray / hit batches)."""
+
+    def __init__(self, count: int, dtype):
+        self._lib = load_library()
+        self.dtype = np.dtype(dtype)
+        self.nbytes = max(1, count * self.dtype.itemsize)
+        self.ptr = self._lib.cndl_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("cndl_host_alloc failed")
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=count)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.cndl_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class RayIntersector:
+    """``Candela::RayIntersector<T>`` with ``T`` given by ``node_format``."""
+
+    def __init__(self, node_format: int = STACKLESS, device: int = 0):
+        self._lib = load_library()
+        if node_format not in (STACKLESS, STACK):
+            # Intersector.h:146-148
+            raise CandelaError(-1, "Template <T> Passed to RayIntersector can only be of type BVH::FlattenedStackNode or BVH::FlattenedNode>!")
+        h = C.c_void_p()
+        rc = self._lib.cndl_create(C.byref(h), node_format, device)
+        if rc != 0:
+            raise CandelaError(rc, "cndl_create failed: no usable sm_100 CUDA device (there is no CPU fallback)")
+        self._h = h
+        self.node_format = node_format
+        self.node_dtype = NODE_DT if node_format == STACKLESS else STACK_NODE_DT
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cndl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CandelaError(rc, self._lib.cndl_last_error(self._h).decode())
+
+    def Initialize(self):
+        """Intersector.h:154 loads the trace shader; kernels here are precompiled — nothing to do."""
+
+    # -- scene ----------------------------------------------------------------------------------
+    def AddObject(self, object_id: int, verts, indices, mesh_ids=None, builder: int = BUILDER_SAH_EXACT,
+                  swap_policy: int = SWAP_NONE, swap_seed: int = 0):
+        """Intersector.h:170-198 with the BVH built on the GPU. `indices`: object-local, per-mesh offset applied."""
+        verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+        indices = np.ascontiguousarray(indices, dtype=np.uint32).ravel()
+        if mesh_ids is not None:
+            mesh_ids = np.ascontiguousarray(mesh_ids, dtype=np.int32)
+        opts = BuildOpts(builder, swap_policy, swap_seed)
+        self._check(self._lib.cndl_add_object(self._h, object_id, _p(verts), len(verts), _p(indices), len(indices), _p(mesh_ids), C.byref(opts)))
+
+    def AddPrebuiltObject(self, object_id: int, nodes, tris, verts):
+        """AddObject for buffers the engine built with its own BVH::BuildBVH (object-local vertex indices)."""
+        nodes = np.ascontiguousarray(nodes)
+        assert nodes.dtype.itemsize == self.node_dtype.itemsize, "node records do not match the context's format"
+        tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
+        verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+        self._check(self._lib.cndl_add_prebuilt_object(self._h, object_id, _p(nodes), len(nodes), _p(tris), len(tris), _p(verts), len(verts)))
+
+    def BufferData(self, ClearCPUData: bool = True):
+        """Intersector.h:322-351."""
+        self._check(self._lib.cndl_commit(self._h, int(ClearCPUData)))
+
+    def PushEntity(self, object_id: int, model=None, emissive: float = 0.0, translucency: float = 0.0):
+        """Intersector.h:201-216. `model` is a 4x4 (row, column) matrix."""
+        m = _colmajor(np.eye(4, dtype=np.float32) if model is None else model)
+        self._check(self._lib.cndl_push_entity(self._h, object_id, _p(m), emissive, translucency))
+
+    def PushEntities(self, entities):
+        """Intersector.h:219-224. entities: iterable of (object_id, model, emissive, translucency)."""
+        for e in entities:
+            self.PushEntity(*e)
+
+    def PushEntityRecords(self, records):
+        records = np.ascontiguousarray(records, dtype=ENTITY_DT)
+        self._check(self._lib.cndl_push_entity_records(self._h, _p(records), len(records)))
+
+    def BufferEntities(self):
+        """Intersector.h:227-239."""
+        self._check(self._lib.cndl_buffer_entities(self._h))
+
+    def object_data(self, object_id: int) -> dict:
+        v = [C.c_int32() for _ in range(4)]
+        self._check(self._lib.cndl_get_object(self._h, object_id, *[C.byref(x) for x in v]))
+        return dict(node_offset=v[0].value, node_count=v[1].value, tri_offset=v[2].value, vert_offset=v[3].value)
+
+    @property
+    def node_count(self) -> int:
+        return int(self._lib.cndl_node_count(self._h))
+
+    @property
+    def triangle_count(self) -> int:
+        return int(self._lib.cndl_triangle_count(self._h))
+
+    @property
+    def vertex_count(self) -> int:
+        return int(self._lib.cndl_vertex_count(self._h))
+
+    @property
+    def entity_count(self) -> int:
+        return int(self._lib.cndl_entity_count(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.cndl_launch_count(self._h))
+
+    @property
+    def last_build_ms(self) -> float:
+        return float(self._lib.cndl_last_build_ms(self._h))
+
+    def read_buffers(self):
+        """m_BVHNodes, m_BVHTriangles, m_BVHVertices (Intersector.h:96-98) copied back from the device."""
+        nodes = np.zeros(self.node_count, dtype=self.node_dtype)
+        tris = np.zeros(self.triangle_count, dtype=TRIANGLE_DT)
+        verts = np.zeros(self.vertex_count, dtype=VERTEX_DT)
+        self._check(self._lib.cndl_read_buffers(self._h, _p(nodes), _p(tris), _p(verts)))
+        return nodes, tris, verts
+
+    def set_traversal_mode(self, mode: int, sort_rays: bool = False):
+        self._check(self._lib.cndl_set_traversal_mode(self._h, mode, int(sort_rays)))
+
+    # -- queries: host buffers --------------------------------------------------------------------
+    def IntersectRays(self, rays, ignore_transparent: bool = False, out=None) -> np.ndarray:
+        """IntersectRay / IntersectRayIgnoreTransparent for a host batch -> hit records."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DT)
+        hits = np.zeros(len(rays), dtype=HIT_DT) if out is None else out
+        self._check(self._lib.cndl_intersect_closest(self._h, _p(rays), len(rays), IGNORE_TRANSPARENT if ignore_transparent else 0, _p(hits)))
+        return hits
+
+    def IntersectRaysAny(self, rays, out=None) -> np.ndarray:
+        """float IntersectRay(o, d) for a host batch -> first accepted t or -1."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DT)
+        t = np.zeros(len(rays), dtype=np.float32) if out is None else out
+        self._check(self._lib.cndl_intersect_any(self._h, _p(rays), len(rays), _p(t)))
+        return t
+
+    def IntersectPrimary(self, inv_view, inv_proj, Width: int, Height: int, return_rays: bool = False):
+        """Intersector.h:241-266; matrices are 4x4 (row, column)."""
+        iv, ip = _colmajor(inv_view), _colmajor(inv_proj)
+        hits = np.zeros(Width * Height, dtype=HIT_DT)
+        rays = np.zeros(Width * Height, dtype=RAY_DT) if return_rays else None
+        self._check(self._lib.cndl_intersect_primary(self._h, _p(iv), _p(ip), Width, Height, _p(hits), _p(rays)))
+        return (hits, rays) if return_rays else hits
+
+    # -- queries: device buffers (raw pointers, e.g. torch tensors' data_ptr()) --------------------
+    def intersect_closest_device(self, d_rays: int, n_rays: int, d_hits: int, flags: int = 0, stream: int = 0):
+        self._check(self._lib.cndl_intersect_closest_device(self._h, d_rays, n_rays, flags, d_hits, stream or None))
+
+    def intersect_any_device(self, d_rays: int, n_rays: int, d_t: int, stream: int = 0):
+        self._check(self._lib.cndl_intersect_any_device(self._h, d_rays, n_rays, d_t, stream or None))
+
+    def intersect_primary_device(self, inv_view, inv_proj, Width: int, Height: int, d_hits: int, d_rays: int = 0, stream: int = 0):
+        iv, ip = _colmajor(inv_view), _colmajor(inv_proj)
+        self._check(self._lib.cndl_intersect_primary_device(self._h, _p(iv), _p(ip), Width, Height, d_hits, d_rays or None, stream or None))

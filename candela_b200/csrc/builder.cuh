@@ -1,0 +1,27 @@
+// GPU BVH construction for cndl_add_object (replaces the CPU BVH::BuildBVH,
+// Source/Core/BVH/BVHConstructor.cpp:951-1108).
+#pragma once
+#include <string>
+
+#include "kernels.cuh"
+
+namespace cndl {
+
+struct BuildRequest {
+    int format;                  // CNDL_STACKLESS / CNDL_STACK
+    cndl_build_opts opts;
+    const float4* d_verts;       // device, 2 float4 per 32-byte vertex, object-local
+    size_t V;
+    const uint32_t* h_indices;   // host, 3 per triangle, object-local
+    const int32_t* h_mesh_ids;   // host, one per triangle, may be null (-> 0)
+    size_t T;
+    int tri_offset;              // TriangleOffset_: triangles already in the intersector
+    void* d_nodes_out;           // device, room for 2T-1 nodes of the context's format
+    int4* d_tris_out;            // device, T records, vertex indices object-local
+    size_t n_nodes_out;          // result: LastNodeIndex + 1
+};
+
+// Returns CNDL_OK or a negative cndl_status with `err` set. Work is enqueued on `st` and complete on return.
+int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* build_ms, std::string& err);
+
+}  // namespace cndl

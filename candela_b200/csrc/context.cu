@@ -1,0 +1,497 @@
+// C ABI of libcandela_b200.so (include/candela_b200.h): the state RayIntersector<T> keeps
+// (Source/Core/BVH/Intersector.h:60-124) held in device memory, plus the query entry points.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "builder.cuh"
+#include "kernels.cuh"
+
+using namespace cndl;
+
+namespace {
+
+struct DeviceBuffer {
+    void* p = nullptr;
+    size_t bytes = 0, cap = 0;
+    ~DeviceBuffer() { if (p) cudaFree(p); }
+    // grows keeping the contents
+    cudaError_t reserve(size_t want, cudaStream_t st) {
+        if (want <= cap) return cudaSuccess;
+        size_t ncap = cap ? cap : 4096;
+        while (ncap < want) ncap *= 2;
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap);
+        if (e != cudaSuccess) return e;
+        if (bytes) e = cudaMemcpyAsync(q, p, bytes, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (p) cudaFree(p);
+        p = q;
+        cap = ncap;
+        return e;
+    }
+    // contents not preserved
+    cudaError_t ensure_scratch(size_t want) {
+        if (want <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+};
+
+struct ObjectData { int tri_offset, vert_offset, node_offset, node_count; };  // _ObjectData, Intersector.h:51-56
+
+}  // namespace
+
+struct cndl_ctx {
+    int format = CNDL_STACKLESS;
+    int device = 0;
+    int sm_count = 148;
+    size_t node_size = 32;
+    std::string err;
+
+    // m_BVHNodes / m_BVHTriangles / m_BVHVertices (device-resident) and their element counts
+    DeviceBuffer nodes, tris, verts, tri48, ents;
+    size_t n_nodes = 0, n_tris = 0, n_verts = 0;
+    size_t committed_nodes = 0, committed_tris = 0;  // m_NodeCountBuffered
+    bool committed = false;
+    std::unordered_map<uint32_t, ObjectData> objects;
+
+    std::vector<cndl_entity> staged;  // m_Entities
+    size_t n_ents = 0;                 // m_EntityPushed
+    bool ents_buffered = false;
+
+    // query scratch
+    DeviceBuffer d_rays, d_hits, d_order, d_keys, d_sort_tmp, d_counter;
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t main_stream = nullptr;
+    int mode = 1, sort_rays = 0;
+    LaunchCounter launches;
+    float last_build_ms = 0.0f;
+
+    int fail(int code, const std::string& msg) { err = msg; return code; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? CNDL_ERR_OOM : CNDL_ERR_CUDA;
+    }
+};
+
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return ctx->cuda_fail(e__, #call); \
+    } while (0)
+
+namespace {
+
+SceneView scene_view(const cndl_ctx* ctx) {
+    SceneView s;
+    s.nodes = static_cast<const float4*>(ctx->nodes.p);
+    s.tri48 = static_cast<const float4*>(ctx->tri48.p);
+    s.tris = static_cast<const int4*>(ctx->tris.p);
+    s.ents = static_cast<const cndl_entity*>(ctx->ents.p);
+    s.total_nodes = (int)ctx->committed_nodes;
+    s.n_ents = (int)ctx->n_ents;
+    return s;
+}
+
+int check_ready(cndl_ctx* ctx) {
+    if (!ctx->committed) return ctx->fail(CNDL_ERR_NOT_COMMITTED, "cndl_commit has not been called");
+    if (!ctx->ents_buffered) return ctx->fail(CNDL_ERR_NOT_COMMITTED, "cndl_buffer_entities has not been called");
+    return CNDL_OK;
+}
+
+// Enqueues one traversal batch on `st`.
+int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cndl_hit* d_hits, float* d_any, unsigned* d_counter,
+                  cudaStream_t st) {
+    if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 rays in one call");
+    const SceneView s = scene_view(ctx);
+    const bool stack = ctx->format == CNDL_STACK;
+    if (ctx->mode == 0 || stack) launch_trace_simple(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, st, ctx->launches);
+    else launch_trace_persistent(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, st, ctx->launches);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "traversal launch");
+    return CNDL_OK;
+}
+
+// glm 0.9.8.5 compute_inverse<tmat4x4> (glm/detail/func_matrix.inl:297-353), host side, used by
+// cndl_push_entity like Intersector.h:209.  Compiled without contraction (-ffp-contract=off).
+void glm_inverse(const float* m, float* out) {
+    auto M = [&](int c, int r) { return m[4 * c + r]; };
+    const float c00 = M(2,2) * M(3,3) - M(3,2) * M(2,3), c02 = M(1,2) * M(3,3) - M(3,2) * M(1,3), c03 = M(1,2) * M(2,3) - M(2,2) * M(1,3);
+    const float c04 = M(2,1) * M(3,3) - M(3,1) * M(2,3), c06 = M(1,1) * M(3,3) - M(3,1) * M(1,3), c07 = M(1,1) * M(2,3) - M(2,1) * M(1,3);
+    const float c08 = M(2,1) * M(3,2) - M(3,1) * M(2,2), c10 = M(1,1) * M(3,2) - M(3,1) * M(1,2), c11 = M(1,1) * M(2,2) - M(2,1) * M(1,2);
+    const float c12 = M(2,0) * M(3,3) - M(3,0) * M(2,3), c14 = M(1,0) * M(3,3) - M(3,0) * M(1,3), c15 = M(1,0) * M(2,3) - M(2,0) * M(1,3);
+    const float c16 = M(2,0) * M(3,2) - M(3,0) * M(2,2), c18 = M(1,0) * M(3,2) - M(3,0) * M(1,2), c19 = M(1,0) * M(2,2) - M(2,0) * M(1,2);
+    const float c20 = M(2,0) * M(3,1) - M(3,0) * M(2,1), c22 = M(1,0) * M(3,1) - M(3,0) * M(1,1), c23 = M(1,0) * M(2,1) - M(2,0) * M(1,1);
+    const float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+    const float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+    const float v0[4] = {M(1,0), M(0,0), M(0,0), M(0,0)}, v1[4] = {M(1,1), M(0,1), M(0,1), M(0,1)};
+    const float v2[4] = {M(1,2), M(0,2), M(0,2), M(0,2)}, v3[4] = {M(1,3), M(0,3), M(0,3), M(0,3)};
+    const float sa[4] = {1.0f, -1.0f, 1.0f, -1.0f}, sb[4] = {-1.0f, 1.0f, -1.0f, 1.0f};
+    float inv[16];
+    for (int k = 0; k < 4; ++k) {
+        inv[0 + k] = (v1[k] * f0[k] - v2[k] * f1[k] + v3[k] * f2[k]) * sa[k];
+        inv[4 + k] = (v0[k] * f0[k] - v2[k] * f3[k] + v3[k] * f4[k]) * sb[k];
+        inv[8 + k] = (v0[k] * f1[k] - v1[k] * f3[k] + v3[k] * f5[k]) * sa[k];
+        inv[12 + k] = (v0[k] * f2[k] - v1[k] * f4[k] + v2[k] * f5[k]) * sb[k];
+    }
+    const float d0 = M(0,0) * inv[0], d1 = M(0,1) * inv[4], d2 = M(0,2) * inv[8], d3 = M(0,3) * inv[12];
+    const float ood = 1.0f / ((d0 + d1) + (d2 + d3));
+    for (int k = 0; k < 16; ++k) out[k] = inv[k] * ood;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cndl_abi_version(void) { return CNDL_ABI_VERSION; }
+
+int cndl_create(cndl_ctx** out, int node_format, int device) {
+    if (!out) return CNDL_ERR_INVALID;
+    *out = nullptr;
+    if (node_format != CNDL_STACKLESS && node_format != CNDL_STACK) return CNDL_ERR_INVALID;  // Intersector.h:146-148
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) {
+        cudaGetLastError();
+        return CNDL_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CNDL_ERR_NO_DEVICE;
+    if (prop.major != 10) return CNDL_ERR_NO_DEVICE;  // built for sm_100a only
+    cndl_ctx* ctx = new (std::nothrow) cndl_ctx;
+    if (!ctx) return CNDL_ERR_OOM;
+    ctx->format = node_format;
+    ctx->node_size = node_format == CNDL_STACKLESS ? sizeof(cndl_node) : sizeof(cndl_stack_node);
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CNDL_ERR_CUDA; }
+    for (auto& s : ctx->streams)
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CNDL_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CNDL_ERR_CUDA; }
+    if (ctx->d_counter.ensure_scratch(256) != cudaSuccess) { delete ctx; return CNDL_ERR_CUDA; }
+    *out = ctx;
+    return CNDL_OK;
+}
+
+void cndl_destroy(cndl_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& s : ctx->streams) if (s) cudaStreamDestroy(s);
+    if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    delete ctx;
+}
+
+const char* cndl_last_error(const cndl_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+size_t cndl_node_count(const cndl_ctx* ctx) { return ctx ? ctx->n_nodes : 0; }
+size_t cndl_triangle_count(const cndl_ctx* ctx) { return ctx ? ctx->n_tris : 0; }
+size_t cndl_vertex_count(const cndl_ctx* ctx) { return ctx ? ctx->n_verts : 0; }
+size_t cndl_entity_count(const cndl_ctx* ctx) { return ctx ? ctx->n_ents : 0; }
+uint64_t cndl_launch_count(const cndl_ctx* ctx) { return ctx ? ctx->launches.n : 0; }
+float cndl_last_build_ms(const cndl_ctx* ctx) { return ctx ? ctx->last_build_ms : 0.0f; }
+
+int cndl_get_object(const cndl_ctx* ctx, uint32_t object_id, int32_t* node_offset, int32_t* node_count, int32_t* triangle_offset,
+                    int32_t* vertex_offset) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    auto it = ctx->objects.find(object_id);
+    if (it == ctx->objects.end()) return CNDL_ERR_UNKNOWN_OBJECT;
+    if (node_offset) *node_offset = it->second.node_offset;
+    if (node_count) *node_count = it->second.node_count;
+    if (triangle_offset) *triangle_offset = it->second.tri_offset;
+    if (vertex_offset) *vertex_offset = it->second.vert_offset;
+    return CNDL_OK;
+}
+
+int cndl_add_prebuilt_object(cndl_ctx* ctx, uint32_t object_id, const void* nodes, size_t N, const cndl_triangle* tris, size_t T,
+                             const cndl_vertex* verts, size_t V) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!nodes || !tris || !verts || N == 0 || T == 0 || V == 0) return ctx->fail(CNDL_ERR_INVALID, "null or empty buffer");
+    if (ctx->n_nodes + N > 0x7FFFFFF0ull || ctx->n_tris + T > (1ull << 27) || ctx->n_verts + V > 0x7FFFFFF0ull)
+        return ctx->fail(CNDL_ERR_INVALID, "scene exceeds the leaf-pack limits (2^27 triangles, BVHConstructor.cpp:794)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->main_stream;
+    const size_t ns = ctx->node_size;
+    // one spare zeroed node: the reference's bounds check admits Pointer == NodeStart+NodeCount (…Stackless.glsl:196)
+    CK(ctx->nodes.reserve((ctx->n_nodes + N + 1) * ns, st));
+    CK(ctx->tris.reserve((ctx->n_tris + T) * sizeof(cndl_triangle), st));
+    CK(ctx->verts.reserve((ctx->n_verts + V) * sizeof(cndl_vertex), st));
+    char* dn = static_cast<char*>(ctx->nodes.p) + ctx->n_nodes * ns;
+    char* dt = static_cast<char*>(ctx->tris.p) + ctx->n_tris * sizeof(cndl_triangle);
+    char* dv = static_cast<char*>(ctx->verts.p) + ctx->n_verts * sizeof(cndl_vertex);
+    CK(cudaMemcpyAsync(dn, nodes, N * ns, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dn + N * ns, 0, ns, st));
+    CK(cudaMemcpyAsync(dt, tris, T * sizeof(cndl_triangle), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv, verts, V * sizeof(cndl_vertex), cudaMemcpyHostToDevice, st));
+    launch_rebase_triangles(reinterpret_cast<int4*>(dt), T, (int)ctx->n_verts, st, ctx->launches);  // Intersector.h:190-197
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ObjectData od;  // Intersector.h:179-181,:188
+    od.node_offset = (int)ctx->n_nodes;
+    od.tri_offset = (int)ctx->n_tris;
+    od.vert_offset = (int)ctx->n_verts;
+    od.node_count = (int)N;
+    ctx->objects[object_id] = od;
+    ctx->n_nodes += N;
+    ctx->n_tris += T;
+    ctx->n_verts += V;
+    ctx->nodes.bytes = ctx->n_nodes * ns;
+    ctx->tris.bytes = ctx->n_tris * sizeof(cndl_triangle);
+    ctx->verts.bytes = ctx->n_verts * sizeof(cndl_vertex);
+    ctx->committed = false;
+    return CNDL_OK;
+}
+
+int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts, size_t V, const uint32_t* indices, size_t I,
+                    const int32_t* mesh_id_per_tri, const cndl_build_opts* opts) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!verts || !indices || V == 0 || I == 0 || I % 3 != 0) return ctx->fail(CNDL_ERR_INVALID, "null or empty geometry, or index count not a multiple of 3");
+    const size_t T = I / 3;
+    if (ctx->n_tris + T > (1ull << 27) || ctx->n_verts + V > 0x7FFFFFF0ull)
+        return ctx->fail(CNDL_ERR_INVALID, "scene exceeds the leaf-pack limits (2^27 triangles, BVHConstructor.cpp:794)");
+    cndl_build_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->main_stream;
+    const size_t ns = ctx->node_size;
+    const size_t n_max = 2 * T - 1;  // upper bound of LastNodeIndex + 1 (every leaf holds >= 1 triangle)
+    CK(ctx->nodes.reserve((ctx->n_nodes + n_max + 1) * ns, st));
+    CK(ctx->tris.reserve((ctx->n_tris + T) * sizeof(cndl_triangle), st));
+    CK(ctx->verts.reserve((ctx->n_verts + V) * sizeof(cndl_vertex), st));
+    char* dn = static_cast<char*>(ctx->nodes.p) + ctx->n_nodes * ns;
+    char* dt = static_cast<char*>(ctx->tris.p) + ctx->n_tris * sizeof(cndl_triangle);
+    char* dv = static_cast<char*>(ctx->verts.p) + ctx->n_verts * sizeof(cndl_vertex);
+    CK(cudaMemcpyAsync(dv, verts, V * sizeof(cndl_vertex), cudaMemcpyHostToDevice, st));
+    BuildRequest rq;
+    rq.format = ctx->format;
+    rq.opts = o;
+    rq.d_verts = reinterpret_cast<const float4*>(dv);
+    rq.V = V;
+    rq.h_indices = indices;
+    rq.h_mesh_ids = mesh_id_per_tri;
+    rq.T = T;
+    rq.tri_offset = (int)ctx->n_tris;
+    rq.d_nodes_out = dn;
+    rq.d_tris_out = reinterpret_cast<int4*>(dt);
+    rq.n_nodes_out = 0;
+    std::string berr;
+    float ms = 0.0f;
+    const int rc = build_object(rq, st, ctx->launches, &ms, berr);
+    if (rc != CNDL_OK) return ctx->fail(rc, berr);
+    ctx->last_build_ms = ms;
+    const size_t N = rq.n_nodes_out;
+    CK(cudaMemsetAsync(dn + N * ns, 0, ns, st));
+    launch_rebase_triangles(reinterpret_cast<int4*>(dt), T, (int)ctx->n_verts, st, ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ObjectData od;
+    od.node_offset = (int)ctx->n_nodes;
+    od.tri_offset = (int)ctx->n_tris;
+    od.vert_offset = (int)ctx->n_verts;
+    od.node_count = (int)N;
+    ctx->objects[object_id] = od;
+    ctx->n_nodes += N;
+    ctx->n_tris += T;
+    ctx->n_verts += V;
+    ctx->nodes.bytes = ctx->n_nodes * ns;
+    ctx->tris.bytes = ctx->n_tris * sizeof(cndl_triangle);
+    ctx->verts.bytes = ctx->n_verts * sizeof(cndl_vertex);
+    ctx->committed = false;
+    return CNDL_OK;
+}
+
+int cndl_commit(cndl_ctx* ctx, int clear_host) {
+    (void)clear_host;  // the host never keeps a copy: the device buffers are the only ones
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (ctx->n_tris == 0) return ctx->fail(CNDL_ERR_INVALID, "nothing to commit");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->main_stream;
+    CK(ctx->tri48.ensure_scratch(ctx->n_tris * 48));
+    launch_make_tri48(static_cast<const int4*>(ctx->tris.p), static_cast<const float4*>(ctx->verts.p), ctx->n_tris,
+                      static_cast<float4*>(ctx->tri48.p), st, ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ctx->committed_nodes = ctx->n_nodes;  // m_NodeCountBuffered, Intersector.h:345
+    ctx->committed_tris = ctx->n_tris;
+    ctx->committed = true;
+    return CNDL_OK;
+}
+
+int cndl_read_buffers(cndl_ctx* ctx, void* nodes, cndl_triangle* tris, cndl_vertex* verts) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (nodes && ctx->n_nodes) CK(cudaMemcpy(nodes, ctx->nodes.p, ctx->n_nodes * ctx->node_size, cudaMemcpyDeviceToHost));
+    if (tris && ctx->n_tris) CK(cudaMemcpy(tris, ctx->tris.p, ctx->n_tris * sizeof(cndl_triangle), cudaMemcpyDeviceToHost));
+    if (verts && ctx->n_verts) CK(cudaMemcpy(verts, ctx->verts.p, ctx->n_verts * sizeof(cndl_vertex), cudaMemcpyDeviceToHost));
+    return CNDL_OK;
+}
+
+int cndl_device_buffers(cndl_ctx* ctx, const void** nodes, const cndl_triangle** tris, const cndl_vertex** verts,
+                        const cndl_entity** entities) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (nodes) *nodes = ctx->nodes.p;
+    if (tris) *tris = static_cast<const cndl_triangle*>(ctx->tris.p);
+    if (verts) *verts = static_cast<const cndl_vertex*>(ctx->verts.p);
+    if (entities) *entities = static_cast<const cndl_entity*>(ctx->ents.p);
+    return CNDL_OK;
+}
+
+int cndl_push_entity(cndl_ctx* ctx, uint32_t object_id, const float model[16], float emissive, float translucency) {
+    if (!ctx || !model) return CNDL_ERR_INVALID;
+    auto it = ctx->objects.find(object_id);
+    if (it == ctx->objects.end())
+        return ctx->fail(CNDL_ERR_UNKNOWN_OBJECT, "Trying to push entity whose parent object hasn't been added to global BVH");
+    cndl_entity e;
+    std::memset(&e, 0, sizeof(e));
+    std::memcpy(e.model, model, 64);
+    glm_inverse(model, e.inverse);
+    e.node_offset = it->second.node_offset;
+    e.node_count = it->second.node_count;
+    const float alpha = 1.0f - translucency;
+    std::memcpy(&e.data[0], &emissive, 4);  // Intersector.h:212
+    std::memcpy(&e.data[1], &alpha, 4);     // Intersector.h:213
+    ctx->staged.push_back(e);
+    return CNDL_OK;
+}
+
+int cndl_push_entity_records(cndl_ctx* ctx, const cndl_entity* records, size_t E) {
+    if (!ctx || (!records && E)) return CNDL_ERR_INVALID;
+    ctx->staged.insert(ctx->staged.end(), records, records + E);
+    return CNDL_OK;
+}
+
+int cndl_buffer_entities(cndl_ctx* ctx) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const size_t E = ctx->staged.size();
+    CK(ctx->ents.ensure_scratch((E ? E : 1) * sizeof(cndl_entity)));
+    if (E) CK(cudaMemcpy(ctx->ents.p, ctx->staged.data(), E * sizeof(cndl_entity), cudaMemcpyHostToDevice));
+    ctx->n_ents = E;  // m_EntityPushed
+    ctx->staged.clear();
+    ctx->ents_buffered = true;
+    return CNDL_OK;
+}
+
+int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays) {
+    if (!ctx || mode < 0 || mode > 1) return CNDL_ERR_INVALID;
+    ctx->mode = mode;
+    ctx->sort_rays = sort_rays ? 1 : 0;
+    return CNDL_OK;
+}
+
+int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, int flags, cndl_hit* d_hits, void* stream) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (R && (!d_rays || !d_hits)) return ctx->fail(CNDL_ERR_INVALID, "null ray or hit buffer");
+    int rc = check_ready(ctx);
+    if (rc != CNDL_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int kind = (flags & CNDL_IGNORE_TRANSPARENT) ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST;
+    return enqueue_trace(ctx, kind, d_rays, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), static_cast<cudaStream_t>(stream));
+}
+
+int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, float* d_t_out, void* stream) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (R && (!d_rays || !d_t_out)) return ctx->fail(CNDL_ERR_INVALID, "null ray or output buffer");
+    int rc = check_ready(ctx);
+    if (rc != CNDL_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return enqueue_trace(ctx, Q_ANY, d_rays, R, nullptr, d_t_out, static_cast<unsigned*>(ctx->d_counter.p), static_cast<cudaStream_t>(stream));
+}
+
+// Host-buffer queries: the batch is cut into chunks that rotate over three streams, so the
+// host->device copy of chunk k+1, the traversal of chunk k and the device->host copy of chunk
+// k-1 overlap (two copy engines + SMs) when the host buffers are pinned.
+static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, cndl_hit* hits, float* any_t) {
+    int rc = check_ready(ctx);
+    if (rc != CNDL_OK) return rc;
+    if (R == 0) return CNDL_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t out_elt = kind == Q_ANY ? sizeof(float) : sizeof(cndl_hit);
+    CK(ctx->d_rays.ensure_scratch(R * sizeof(cndl_ray)));
+    CK(ctx->d_hits.ensure_scratch(R * out_elt));
+    size_t chunk = (R + 7) / 8;
+    if (chunk < (1u << 18)) chunk = 1u << 18;
+    size_t k = 0;
+    for (size_t lo = 0; lo < R; lo += chunk, ++k) {
+        const size_t n = R - lo < chunk ? R - lo : chunk;
+        cudaStream_t st = ctx->streams[k % 3];
+        cndl_ray* dr = static_cast<cndl_ray*>(ctx->d_rays.p) + lo;
+        char* dout = static_cast<char*>(ctx->d_hits.p) + lo * out_elt;
+        CK(cudaMemcpyAsync(dr, rays + lo, n * sizeof(cndl_ray), cudaMemcpyHostToDevice, st));
+        unsigned* counter = static_cast<unsigned*>(ctx->d_counter.p) + 16 * (k % 3);  // one counter per stream in flight
+        rc = enqueue_trace(ctx, kind, dr, n, kind == Q_ANY ? nullptr : reinterpret_cast<cndl_hit*>(dout),
+                           kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter, st);
+        if (rc != CNDL_OK) return rc;
+        char* hout = kind == Q_ANY ? reinterpret_cast<char*>(any_t + lo) : reinterpret_cast<char*>(hits + lo);
+        CK(cudaMemcpyAsync(hout, dout, n * out_elt, cudaMemcpyDeviceToHost, st));
+    }
+    for (auto& s : ctx->streams) CK(cudaStreamSynchronize(s));
+    return CNDL_OK;
+}
+
+int cndl_intersect_closest(cndl_ctx* ctx, const cndl_ray* rays, size_t R, int flags, cndl_hit* hits) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (R && (!rays || !hits)) return ctx->fail(CNDL_ERR_INVALID, "null ray or hit buffer");
+    return host_query(ctx, (flags & CNDL_IGNORE_TRANSPARENT) ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST, rays, R, hits, nullptr);
+}
+
+int cndl_intersect_any(cndl_ctx* ctx, const cndl_ray* rays, size_t R, float* t_out) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (R && (!rays || !t_out)) return ctx->fail(CNDL_ERR_INVALID, "null ray or output buffer");
+    return host_query(ctx, Q_ANY, rays, R, nullptr, t_out);
+}
+
+int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H, cndl_hit* d_hits,
+                                  cndl_ray* d_rays_out, void* stream) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!inv_view || !inv_proj || W <= 0 || H <= 0 || !d_hits) return ctx->fail(CNDL_ERR_INVALID, "bad primary-ray arguments");
+    int rc = check_ready(ctx);
+    if (rc != CNDL_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t R = (size_t)W * (size_t)H;
+    cndl_ray* dr = d_rays_out;
+    if (!dr) {
+        CK(ctx->d_rays.ensure_scratch(R * sizeof(cndl_ray)));
+        dr = static_cast<cndl_ray*>(ctx->d_rays.p);
+    }
+    launch_primary_rays(inv_view, inv_proj, W, H, dr, st, ctx->launches);
+    CK(cudaGetLastError());
+    return enqueue_trace(ctx, Q_CLOSEST, dr, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), st);
+}
+
+int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H, cndl_hit* hits,
+                           cndl_ray* rays_out) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!hits || W <= 0 || H <= 0) return ctx->fail(CNDL_ERR_INVALID, "bad primary-ray arguments");
+    const size_t R = (size_t)W * (size_t)H;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_rays.ensure_scratch(R * sizeof(cndl_ray)));
+    CK(ctx->d_hits.ensure_scratch(R * sizeof(cndl_hit)));
+    cudaStream_t st = ctx->main_stream;
+    int rc = cndl_intersect_primary_device(ctx, inv_view, inv_proj, W, H, static_cast<cndl_hit*>(ctx->d_hits.p),
+                                           static_cast<cndl_ray*>(ctx->d_rays.p), st);
+    if (rc != CNDL_OK) return rc;
+    CK(cudaMemcpyAsync(hits, ctx->d_hits.p, R * sizeof(cndl_hit), cudaMemcpyDeviceToHost, st));
+    if (rays_out) CK(cudaMemcpyAsync(rays_out, ctx->d_rays.p, R * sizeof(cndl_ray), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return CNDL_OK;
+}
+
+void* cndl_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void cndl_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

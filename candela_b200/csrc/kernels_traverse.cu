@@ -1,0 +1,291 @@
+// Traversal kernels for sm_100a.  See traverse.cuh for the arithmetic contract.
+#include "kernels.cuh"
+
+namespace cndl {
+
+namespace {
+
+__device__ __forceinline__ void load_ray(const cndl_ray* __restrict__ rays, size_t i, V3& o, V3& d, float& tmax) {
+    const float4* p = reinterpret_cast<const float4*>(rays + i);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    o = {a.x, a.y, a.z};
+    d = {b.x, b.y, b.z};
+    tmax = b.w;
+}
+
+__device__ __forceinline__ void store_hit(cndl_hit* __restrict__ hits, size_t i, const cndl_hit& h) {
+    float4* p = reinterpret_cast<float4*>(hits + i);
+    p[0] = make_float4(h.t, h.u, h.v, h.w);
+    reinterpret_cast<int4*>(p)[1] = make_int4(h.mesh, h.tri, h.entity, h.iters);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mode 0: one thread per ray.
+template <bool STACK, int KIND>
+__global__ void __launch_bounds__(128) trace_simple_kernel(SceneView s, const cndl_ray* __restrict__ rays, size_t R,
+                                                           const unsigned* __restrict__ order, cndl_hit* __restrict__ hits,
+                                                           float* __restrict__ any_t) {
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= R) return;
+    const size_t i = order ? (size_t)__ldg(order + slot) : slot;
+    V3 o, d;
+    float ray_tmax;
+    load_ray(rays, i, o, d, ray_tmax);
+    if (KIND == Q_ANY) {
+        any_t[i] = scene_any<STACK>(s, o, d, ray_tmax);
+    } else {
+        store_hit(hits, i, scene_closest<STACK>(s, o, d, KIND == Q_CLOSEST_IGNORE_TRANSPARENT));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mode 1: persistent warps, stackless walk as a per-lane state machine.  A lane whose ray has
+// finished goes idle; when enough lanes of the warp are idle the warp claims a fresh run of rays
+// from a global counter (one atomic per refill), so divergence in walk length does not leave
+// lanes empty until the longest ray of the warp ends.  The per-ray sequence of node visits,
+// triangle tests and TMax updates is exactly walk_stackless()'s.
+struct Lane {
+    RayState r;
+    float tmax, closest;
+    int ptr, start, count, iters, ent;
+    int best_tri, best_ent;
+    unsigned rid;  // ray index, 0xFFFFFFFF = idle
+};
+
+template <int KIND>
+__device__ __forceinline__ bool begin_entity(const SceneView& s, const cndl_ray* __restrict__ rays, Lane& L) {
+    // advances L.ent to the next entity to traverse; false when the scene loop is over
+    while (L.ent < s.n_ents) {
+        const cndl_entity* e = s.ents + L.ent;
+        if (KIND == Q_CLOSEST_IGNORE_TRANSPARENT && __int_as_float(__ldg(&e->data[1])) < 0.99f) { ++L.ent; continue; }
+        V3 o, d;
+        float unused;
+        load_ray(rays, L.rid, o, d, unused);
+        L.r = to_object_space(e, o, d);
+        L.start = __ldg(&e->node_offset);
+        L.count = __ldg(&e->node_count);
+        L.ptr = L.start;
+        L.iters = 0;
+        return true;
+    }
+    return false;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128, 4) trace_persistent_stackless_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R,
+                                                                            const unsigned* __restrict__ order,
+                                                                            cndl_hit* __restrict__ hits, float* __restrict__ any_t,
+                                                                            unsigned* __restrict__ work_counter) {
+    constexpr bool ANY = KIND == Q_ANY;
+    const unsigned lane = threadIdx.x & 31u;
+    Lane L;
+    L.rid = 0xFFFFFFFFu;
+    L.iters = 0;
+    bool drained = false;  // the global counter ran past R
+
+    while (true) {
+        // ---- refill idle lanes ----
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, L.rid == 0xFFFFFFFFu);
+        if (idle == 0xFFFFFFFFu && drained) break;
+        if (!drained && (__popc(idle) >= 8 || idle == 0xFFFFFFFFu)) {
+            unsigned base = 0;
+            const int n = __popc(idle);
+            if (lane == 0) base = atomicAdd(work_counter, (unsigned)n);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base + (unsigned)n >= R) drained = true;  // uniform across the warp
+            if (L.rid == 0xFFFFFFFFu) {
+                const unsigned slot = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (slot < R) {
+                    L.rid = order ? __ldg(order + slot) : slot;
+                    L.ent = 0;
+                    L.closest = -1.0f;
+                    L.best_tri = -1;
+                    L.best_ent = -1;
+                    L.iters = 0;
+                    if (ANY) {
+                        const float rt = __ldg(&rays[L.rid].tmax);
+                        L.tmax = rt > 0.0f ? rt : 1000000.0f;
+                    } else {
+                        L.tmax = 1000000.0f;
+                    }
+                    if (!begin_entity<KIND>(s, rays, L)) {
+                        // no entity to traverse: miss
+                        if (ANY) any_t[L.rid] = -1.0f;
+                        else store_hit(hits, L.rid, cndl_hit{-1.0f, -1.0f, -1.0f, -1.0f, -1, -1, -1, 0});
+                        L.rid = 0xFFFFFFFFu;
+                    }
+                }
+            }
+        }
+
+        // ---- a bounded burst of node steps ----
+#pragma unroll 1
+        for (int burst = 0; burst < 16; ++burst) {
+            if (L.rid != 0xFFFFFFFFu) {
+                bool entity_done = false;
+                bool any_found = false;
+                // loop header of SL:192-199
+                if (!(L.ptr >= 0 && L.iters < 1024) || L.ptr < L.start || L.ptr > L.start + L.count || L.ptr > s.total_nodes) {
+                    entity_done = true;
+                } else {
+                    ++L.iters;
+                    const float4 mn = __ldg(s.nodes + 2 * (size_t)L.ptr), mx = __ldg(s.nodes + 2 * (size_t)L.ptr + 1);
+                    const int link = __float_as_int(mx.w);
+                    bool follow_link = true;
+                    if (enter_stackless(mn, mx, L.r, L.tmax)) {
+                        const int pack = __float_as_int(mn.w);
+                        if (pack != -1) {
+                            EntityResult er{-1.0f, -1, 0};
+                            any_found = leaf_triangles<ANY>(s, pack, L.r, L.tmax, er);
+                            if (er.tri >= 0) { L.closest = er.t; L.best_tri = er.tri; L.best_ent = L.ent; }
+                        } else {
+                            ++L.ptr;
+                            follow_link = false;
+                        }
+                    }
+                    if (follow_link) {
+                        L.ptr = link;
+                        if (link < 0) entity_done = true;
+                        else L.ptr += L.start;
+                    }
+                }
+                if (ANY && any_found) {
+                    any_t[L.rid] = L.closest;  // SL:567-569: the scene loop returns the first T > 0
+                    L.rid = 0xFFFFFFFFu;
+                } else if (entity_done) {
+                    // scene loop bookkeeping.  In the reference the per-entity result is accepted when
+                    // T > 0 && T < TMax(scene); the entity walk started from TMax(scene) and only
+                    // accepts t < TMax, so every accepted hit already satisfies that test and L.tmax
+                    // is the scene TMax carried into the next entity (SL:293-301).
+                    const int last_iters = L.iters;
+                    ++L.ent;
+                    if (!begin_entity<KIND>(s, rays, L)) {
+                        if (ANY) {
+                            any_t[L.rid] = -1.0f;
+                        } else {
+                            cndl_hit h{-1.0f, -1.0f, -1.0f, -1.0f, -1, L.best_tri, L.best_ent, last_iters};
+                            if (L.best_tri >= 0) h.mesh = __ldg(&s.tris[L.best_tri]).w;
+                            if (L.closest > 0.0f && L.best_tri > 0) {
+                                V3 o, d;
+                                float unused;
+                                load_ray(rays, L.rid, o, d, unused);
+                                const RayState r = to_object_space(s.ents + L.best_ent, o, d);
+                                const V3 p = {fadd(r.o.x, fmul(r.d.x, L.closest)), fadd(r.o.y, fmul(r.d.y, L.closest)),
+                                              fadd(r.o.z, fmul(r.d.z, L.closest))};
+                                h.t = L.closest;
+                                barycentrics(s.tri48, L.best_tri, p, h.u, h.v, h.w);
+                            }
+                            store_hit(hits, L.rid, h);
+                        }
+                        L.rid = 0xFFFFFFFFu;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void make_tri48_kernel(const int4* __restrict__ tris, const float4* __restrict__ verts, size_t T, float4* __restrict__ tri48) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const int4 t = tris[i];
+    const float4 a = verts[2 * (size_t)t.x], b = verts[2 * (size_t)t.y], c = verts[2 * (size_t)t.z];
+    const V3 v0 = {a.x, a.y, a.z};
+    const V3 e1 = vsub(V3{b.x, b.y, b.z}, v0);  // v1v0, SL:81
+    const V3 e2 = vsub(V3{c.x, c.y, c.z}, v0);  // v2v0, SL:82
+    const V3 n = vcross(e1, e2);                 // SL:85
+    tri48[3 * i + 0] = make_float4(v0.x, v0.y, v0.z, e1.x);
+    tri48[3 * i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    tri48[3 * i + 2] = make_float4(e2.z, n.x, n.y, n.z);
+}
+
+__global__ void rebase_triangles_kernel(int4* __restrict__ tris, size_t T, int offset) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    int4 t = tris[i];
+    t.x += offset; t.y += offset; t.z += offset;
+    tris[i] = t;
+}
+
+struct Mat2 { float iv[16]; float ip[16]; };
+
+__global__ void primary_rays_kernel(Mat2 m, int W, int H, cndl_ray* __restrict__ rays) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float tx = fdiv((float)x, (float)W), ty = fdiv((float)y, (float)H);  // vec2(Pixel) / u_Dims
+    const float cx = fsub(fmul(tx, 2.0f), 1.0f), cy = fsub(fmul(ty, 2.0f), 1.0f);
+    const float* ip = m.ip;
+    const float ex = fadd(fadd(fmul(ip[0], cx), fmul(ip[4], cy)), fadd(fmul(ip[8], -1.0f), fmul(ip[12], 1.0f)));
+    const float ey = fadd(fadd(fmul(ip[1], cx), fmul(ip[5], cy)), fadd(fmul(ip[9], -1.0f), fmul(ip[13], 1.0f)));
+    const V3 dir = xform(m.iv, V3{ex, ey, -1.0f}, 0.0f);
+    const float inv_len = fdiv(1.0f, __fsqrt_rn(vdot(dir, dir)));  // glm::normalize: v * inversesqrt(dot(v,v))
+    float4* p = reinterpret_cast<float4*>(rays + ((size_t)y * (size_t)W + (size_t)x));
+    p[0] = make_float4(m.iv[12], m.iv[13], m.iv[14], 0.0f);
+    p[1] = make_float4(fmul(dir.x, inv_len), fmul(dir.y, inv_len), fmul(dir.z, inv_len), 1000000.0f);
+}
+
+template <bool STACK>
+void dispatch_simple(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits, float* any_t,
+                     cudaStream_t stream) {
+    const unsigned block = 128;
+    const unsigned grid = (unsigned)((R + block - 1) / block);
+    switch (kind) {
+        case Q_CLOSEST: trace_simple_kernel<STACK, Q_CLOSEST><<<grid, block, 0, stream>>>(s, rays, R, order, hits, any_t); break;
+        case Q_CLOSEST_IGNORE_TRANSPARENT: trace_simple_kernel<STACK, Q_CLOSEST_IGNORE_TRANSPARENT><<<grid, block, 0, stream>>>(s, rays, R, order, hits, any_t); break;
+        default: trace_simple_kernel<STACK, Q_ANY><<<grid, block, 0, stream>>>(s, rays, R, order, hits, any_t); break;
+    }
+}
+
+}  // namespace
+
+void launch_trace_simple(const SceneView& s, bool stack, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits,
+                         float* any_t, cudaStream_t stream, LaunchCounter& lc) {
+    if (R == 0) return;
+    if (stack) dispatch_simple<true>(s, kind, rays, R, order, hits, any_t, stream);
+    else dispatch_simple<false>(s, kind, rays, R, order, hits, any_t, stream);
+    lc.n++;
+}
+
+void launch_trace_persistent(const SceneView& s, bool stack, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits,
+                             float* any_t, unsigned* work_counter, int sm_count, cudaStream_t stream, LaunchCounter& lc) {
+    if (R == 0) return;
+    if (stack) {  // the stack walk keeps a 64-entry private stack: one ray per thread is the fitting shape
+        launch_trace_simple(s, stack, kind, rays, R, order, hits, any_t, stream, lc);
+        return;
+    }
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned), stream);
+    const unsigned block = 128;
+    unsigned grid = (unsigned)sm_count * 8u;  // 8 CTAs x 4 warps resident per SM
+    const unsigned need = (unsigned)((R + block - 1) / block);
+    if (grid > need) grid = need;
+    switch (kind) {
+        case Q_CLOSEST: trace_persistent_stackless_kernel<Q_CLOSEST><<<grid, block, 0, stream>>>(s, rays, (unsigned)R, order, hits, any_t, work_counter); break;
+        case Q_CLOSEST_IGNORE_TRANSPARENT: trace_persistent_stackless_kernel<Q_CLOSEST_IGNORE_TRANSPARENT><<<grid, block, 0, stream>>>(s, rays, (unsigned)R, order, hits, any_t, work_counter); break;
+        default: trace_persistent_stackless_kernel<Q_ANY><<<grid, block, 0, stream>>>(s, rays, (unsigned)R, order, hits, any_t, work_counter); break;
+    }
+    lc.n++;
+}
+
+void launch_make_tri48(const int4* tris, const float4* verts, size_t T, float4* tri48, cudaStream_t stream, LaunchCounter& lc) {
+    if (T == 0) return;
+    make_tri48_kernel<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(tris, verts, T, tri48);
+    lc.n++;
+}
+
+void launch_rebase_triangles(int4* tris, size_t T, int offset, cudaStream_t stream, LaunchCounter& lc) {
+    if (T == 0 || offset == 0) return;
+    rebase_triangles_kernel<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(tris, T, offset);
+    lc.n++;
+}
+
+void launch_primary_rays(const float* iv, const float* ip, int W, int H, cndl_ray* rays, cudaStream_t stream, LaunchCounter& lc) {
+    if (W <= 0 || H <= 0) return;
+    Mat2 m;
+    for (int k = 0; k < 16; ++k) { m.iv[k] = iv[k]; m.ip[k] = ip[k]; }
+    const dim3 block(16, 16);  // the reference's local size (Intersectors/TraverseBVHStack.glsl:5)
+    const dim3 grid((unsigned)((W + 15) / 16), (unsigned)((H + 15) / 16));
+    primary_rays_kernel<<<grid, block, 0, stream>>>(m, W, H, rays);
+    lc.n++;
+}
+
+}  // namespace cndl

@@ -1,0 +1,173 @@
+/* candela_b200 — B200-native (sm_100a) BVH build + ray traversal backend.
+ *
+ * C ABI that replaces the hot path behind Candela's
+ *   template<typename T> class Candela::RayIntersector   (Source/Core/BVH/Intersector.h:60-124)
+ *   Candela::BVH::BuildBVH                                (Source/Core/BVH/BVHConstructor.h:86-87)
+ * and the GLSL traversal it binds to
+ *   Source/Core/Shaders/Intersectors/Include/TraverseBVHStackless.glsl
+ *   Source/Core/Shaders/Intersectors/Include/TraverseBVHStack.glsl
+ *
+ * Buffer records keep the reference's layouts byte for byte; every function
+ * below cites the reference interface it stands in for.  All functions return
+ * CNDL_OK (0) or a negative cndl_status and never throw across the boundary
+ * (the reference throws string literals, Intersector.h:147,:204).  There is
+ * no CPU fallback: without a usable CUDA device cndl_create fails.
+ *
+ * Threading: one context per device; calls on one context are serialised by
+ * the caller (the reference is single-threaded and its builder keeps file
+ * scope statics, BVHConstructor.cpp:58-66).  Pointers passed in are borrowed
+ * for the duration of the call only.
+ */
+#ifndef CANDELA_B200_H
+#define CANDELA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNDL_ABI_VERSION 1
+
+typedef enum cndl_status {
+    CNDL_OK = 0,
+    CNDL_ERR_INVALID = -1,      /* bad argument */
+    CNDL_ERR_CUDA = -2,         /* CUDA runtime error; see cndl_last_error */
+    CNDL_ERR_NO_DEVICE = -3,    /* no sm_100 device: there is no CPU fallback */
+    CNDL_ERR_UNKNOWN_OBJECT = -4, /* entity pushed for an object never added (Intersector.h:203-205) */
+    CNDL_ERR_NOT_COMMITTED = -5,  /* traversal before cndl_commit / cndl_buffer_entities */
+    CNDL_ERR_OOM = -6
+} cndl_status;
+
+/* node_format: the template argument T of RayIntersector<T> (Intersector.h:138-148) */
+enum { CNDL_STACKLESS = 0 /* BVH::FlattenedNode */, CNDL_STACK = 1 /* BVH::FlattenedStackNode */ };
+
+/* Candela::Vertex, Source/Core/Utils/Vertex.h:7-12 */
+typedef struct cndl_vertex { float position[4]; uint32_t normal_tangent[3]; uint32_t texcoords; } cndl_vertex;
+/* BVH::Triangle, BVHConstructor.h:79-84: three global vertex indices + GlobalMeshNumber */
+typedef struct cndl_triangle { int32_t v[3]; int32_t mesh; } cndl_triangle;
+/* BVH::FlattenedNode, BVHConstructor.h:66-70. min[3] bits: -1 inner, else (first_tri<<4)|count.
+ * max[3] bits: miss link (object-local node index, -1 terminates). First child is index+1. */
+typedef struct cndl_node { float min[4]; float max[4]; } cndl_node;
+/* BVH::FlattenedStackNode, BVHConstructor.h:72-77. Per child: min[3] bits -1 if the child is inner
+ * else its leaf pack; max[3] bits = the inner child's slot (object-local). */
+typedef struct cndl_stack_node { cndl_node left; cndl_node right; } cndl_stack_node;
+/* Candela::BVHEntity, Intersector.h:43-49. Column-major matrices. data[0] = emissive float bits,
+ * data[1] = (1 - translucency) float bits. */
+typedef struct cndl_entity { float model[16]; float inverse[16]; int32_t node_offset; int32_t node_count; int32_t data[14]; } cndl_entity;
+
+/* Ray and hit records of the new ABI. tmin is reserved (the reference has no
+ * per-ray tmin: 0.0001 in the stackless box test, t > 0 for triangles).  tmax is honoured by
+ * any-hit queries only (> 0: use it; <= 0: the reference's 1e6); closest-hit always starts at
+ * 1e6 like IntersectScene (…Stackless.glsl:284). */
+typedef struct cndl_ray { float ox, oy, oz, tmin; float dx, dy, dz, tmax; } cndl_ray;
+/* vec4 TUVW + out ints of IntersectScene (…Stackless.glsl:280-319): t, then the barycentric
+ * weights of vertices A, B, C; miss = t,u,v,w all -1.  mesh/tri/entity are -1 when nothing was
+ * accepted.  A hit on global triangle 0 reports t=u=v=w=-1 with tri = 0 (reference quirk, :300).
+ * iters = node iterations of the last entity traversed (the reference's `out int Iters`). */
+typedef struct cndl_hit { float t, u, v, w; int32_t mesh, tri, entity, iters; } cndl_hit;
+
+enum { CNDL_BUILDER_SAH_EXACT = 0, /* GPU binned SAH, buffers byte-identical to BVH::BuildBVH */
+       CNDL_BUILDER_LBVH = 1       /* GPU Morton/radix-sort LBVH: same layouts, different tree */ };
+enum { CNDL_SWAP_NONE = 0, CNDL_SWAP_HASHED = 1 };
+
+/* Build options; zero-initialised == the reference's compile-time constants
+ * (BVHConstructor.cpp:41-51: 64 bins, <= 2 triangles per leaf). */
+typedef struct cndl_build_opts {
+    int32_t builder;      /* CNDL_BUILDER_* */
+    int32_t swap_policy;  /* stackless only: child flips of BVHConstructor.cpp:599-609 */
+    uint64_t swap_seed;
+} cndl_build_opts;
+
+typedef struct cndl_ctx cndl_ctx;
+
+/* RayIntersector<T>::RayIntersector + Initialize (Intersector.h:126-167). */
+int cndl_create(cndl_ctx** out, int node_format, int device);
+void cndl_destroy(cndl_ctx* ctx);
+const char* cndl_last_error(const cndl_ctx* ctx);
+int cndl_abi_version(void);
+
+/* RayIntersector<T>::AddObject (Intersector.h:170-198) with the BVH built ON THE GPU.
+ * `indices` are object-local and already carry the per-mesh vertex offset of
+ * BuildBVH's concatenation (BVHConstructor.cpp:981-1002); one GlobalMeshNumber per triangle. */
+int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts, size_t V,
+                    const uint32_t* indices, size_t I, const int32_t* mesh_id_per_tri,
+                    const cndl_build_opts* opts);
+
+/* AddObject for an object whose BVH the engine already built with its own BVH::BuildBVH:
+ * `nodes` is FlattenedNode[] or FlattenedStackNode[] per the context format, triangle vertex
+ * indices are object-local (they are rebased by the running vertex count exactly like
+ * Intersector.h:190-197) and leaf packs must already include the triangle offset
+ * (= cndl_triangle_count before the call), as BuildBVH's last argument makes them. */
+int cndl_add_prebuilt_object(cndl_ctx* ctx, uint32_t object_id, const void* nodes, size_t N,
+                             const cndl_triangle* tris, size_t T, const cndl_vertex* verts, size_t V);
+
+/* Running totals (m_BVHNodes.size() etc.; Intersector.h:179-181). */
+size_t cndl_node_count(const cndl_ctx* ctx);
+size_t cndl_triangle_count(const cndl_ctx* ctx);
+size_t cndl_vertex_count(const cndl_ctx* ctx);
+/* _ObjectData of one object (Intersector.h:51-56). Any out pointer may be NULL. */
+int cndl_get_object(const cndl_ctx* ctx, uint32_t object_id, int32_t* node_offset, int32_t* node_count,
+                    int32_t* triangle_offset, int32_t* vertex_offset);
+
+/* RayIntersector<T>::BufferData(bool ClearCPUData) (Intersector.h:322-351): makes everything
+ * added so far visible to traversal and (re)builds the device-side acceleration copies. */
+int cndl_commit(cndl_ctx* ctx, int clear_host);
+
+/* Copies the reference-layout buffers (m_BVHNodes / m_BVHTriangles / m_BVHVertices, public in the
+ * reference and read by Physics.cpp:100-126) back to the host.  Any pointer may be NULL. */
+int cndl_read_buffers(cndl_ctx* ctx, void* nodes, cndl_triangle* tris, cndl_vertex* verts);
+/* Device pointers of the same buffers, valid until the next add/commit; for callers that bind
+ * them to their own kernels (the analogue of BindEverything's SSBO bindings 16..20, :269-293). */
+int cndl_device_buffers(cndl_ctx* ctx, const void** nodes, const cndl_triangle** tris,
+                        const cndl_vertex** verts, const cndl_entity** entities);
+
+/* PushEntity (Intersector.h:201-216): stages {Model, inverse(Model), NodeOffset, NodeCount,
+ * emissive, 1-translucency}; model is column-major; the inverse follows glm::inverse. */
+int cndl_push_entity(cndl_ctx* ctx, uint32_t object_id, const float model[16], float emissive, float translucency);
+/* Stages ready-made 192-byte records (what PushEntity would have produced). */
+int cndl_push_entity_records(cndl_ctx* ctx, const cndl_entity* records, size_t E);
+/* BufferEntities (Intersector.h:227-239): uploads the staged list and clears the staging list. */
+int cndl_buffer_entities(cndl_ctx* ctx);
+size_t cndl_entity_count(const cndl_ctx* ctx);
+
+/* Query flags */
+enum { CNDL_IGNORE_TRANSPARENT = 1 /* IntersectSceneIgnoreTransparent, …Stackless.glsl:321-366 */ };
+
+/* IntersectRay / IntersectRayIgnoreTransparent (closest hit) for a batch of rays in HOST memory.
+ * Copies in, traverses, copies out; pinned buffers (cndl_host_alloc) make the copies asynchronous
+ * and chunk-pipelined. */
+int cndl_intersect_closest(cndl_ctx* ctx, const cndl_ray* rays, size_t R, int flags, cndl_hit* hits);
+/* float IntersectRay(o, d) (any hit; …Stackless.glsl:558-579): t_out[i] = first accepted t or -1. */
+int cndl_intersect_any(cndl_ctx* ctx, const cndl_ray* rays, size_t R, float* t_out);
+/* Same queries on DEVICE buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream)
+ * and not synchronised. */
+int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, int flags, cndl_hit* d_hits, void* stream);
+int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, float* d_t_out, void* stream);
+
+/* RayIntersector<T>::IntersectPrimary (Intersector.h:241-266) with hit records instead of an
+ * albedo image: pixel (x,y) -> hits[y*W+x]; ray generation as in
+ * Intersectors/TraverseBVHStack.glsl:133-138,:414-431.  Matrices are column-major.
+ * hits is a HOST buffer; rays_out (HOST, optional) receives the generated rays. */
+int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H,
+                           cndl_hit* hits, cndl_ray* rays_out);
+int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H,
+                                  cndl_hit* d_hits, cndl_ray* d_rays_out, void* stream);
+
+/* Pinned host memory for ray / hit batches. */
+void* cndl_host_alloc(size_t bytes);
+void cndl_host_free(void* p);
+
+/* Traversal tuning (does not change results): 0 = one thread per ray, 1 = persistent warps with
+ * ray re-fetch; sort_rays != 0 reorders rays by origin cell and direction octant first. */
+int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays);
+/* Number of kernels launched by this context so far (bench.py's gpu_launches). */
+uint64_t cndl_launch_count(const cndl_ctx* ctx);
+/* Milliseconds of the last cndl_add_object build, measured with CUDA events. */
+float cndl_last_build_ms(const cndl_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CANDELA_B200_H */

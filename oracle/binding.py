@@ -174,7 +174,7 @@ class Scene:
     def add_object(self, object_id: int, verts, indices, mesh_ids=None, swap_policy=SWAP_NONE, swap_seed=0):
         b = build(self.format, verts, indices, mesh_ids, t_offset=len(self.tris), swap_policy=swap_policy, swap_seed=swap_seed)
         self.objects[object_id] = dict(node_offset=len(self.nodes), node_count=len(b.nodes), tri_offset=len(self.tris),
-                                       tri_count=len(b.tris), vert_offset=len(self.verts))
+                                       tri_count=len(b.tris), vert_offset=len(self.verts), vert_count=len(verts))
         tris = b.tris.copy()
         lib().orc_rebase_triangles(_p(tris), len(tris), len(self.verts))
         self.nodes = np.concatenate([self.nodes, b.nodes])

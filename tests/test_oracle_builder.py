@@ -1,0 +1,134 @@
+"""CPU tests: the oracle's builder restatement against the reference's golden digests, against the
+reference builder itself (where /root/reference exists), and structural invariants the reference
+only eyeballs."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+GOLD = json.loads((GOLDEN / "builder_golden.json").read_text())
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def fbits(a):
+    return np.ascontiguousarray(a).view(np.int32)
+
+
+@pytest.mark.parametrize("name", [k for k in GOLD if "(" not in k])
+def test_oracle_matches_reference_digests(ob, golden_meshes, name):
+    P, F = golden_meshes[name]
+    V = ob.make_vertices(P)
+    mids = np.full(len(F), 3, np.int32)
+    st = ob.build(ob.STACK, V, F.ravel(), mids, t_offset=5)
+    assert len(st.nodes) == GOLD[name]["stack"]["n_nodes"]
+    assert sha(st.nodes) == GOLD[name]["stack"]["nodes_sha256"]
+    assert sha(st.tris) == GOLD[name]["stack"]["tris_sha256"]
+    sl = ob.build(ob.STACKLESS, V, F.ravel(), mids, t_offset=5)
+    assert sha(sl.nodes) == GOLD[name]["stackless"]["nodes_sha256_unflipped"]
+    assert sha(sl.tris) == GOLD[name]["stackless"]["tris_sha256"]
+    for k, v in GOLD[name]["stats"].items():
+        if k != "stack_slots":
+            assert sl.stats[k] == v, k
+
+
+def test_multi_mesh_digest(ob, golden_meshes):
+    parts = [(ob.make_vertices(golden_meshes["zelda_market"][0]), golden_meshes["zelda_market"][1], 4),
+             (ob.make_vertices(golden_meshes["soup400"][0]), golden_meshes["soup400"][1], 9)]
+    cv, ci, cm = ob.concat_meshes(parts)
+    b = ob.build(ob.STACK, cv, ci, cm)
+    g = GOLD["multi_mesh(zelda_market+soup400)"]["stack"]
+    assert sha(b.nodes) == g["nodes_sha256"] and sha(b.tris) == g["tris_sha256"]
+    assert set(np.unique(b.tris["mesh"])) == {4, 9}
+
+
+@pytest.mark.parametrize("name", ["dragon", "soup400", "duplicates", "signed_zero"])
+def test_oracle_vs_reference_builder_live(ob, golden_meshes, name):
+    if not ob.REFERENCE_ROOT.exists():
+        pytest.skip("/root/reference not present (GPU box): covered by the committed digests")
+    P, F = golden_meshes[name]
+    V = ob.make_vertices(P)
+    mids = np.full(len(F), 1, np.int32)
+    assert ob.ref_sizes() == (32, 16, 32, 64)
+    rn, rt, rv = ob.ref_build(ob.STACK, [(V, F, 1)], t_offset=17)
+    b = ob.build(ob.STACK, V, F.ravel(), mids, t_offset=17)
+    assert rn.tobytes() == b.nodes.tobytes() and rt.tobytes() == b.tris.tobytes() and rv.tobytes() == V.tobytes()
+    rn, rt, _ = ob.ref_build(ob.STACKLESS, [(V, F, 1)], t_offset=17)
+    b = ob.build(ob.STACKLESS, V, F.ravel(), mids, t_offset=17, adopt_flips_from=rn)
+    assert rn.tobytes() == b.nodes.tobytes() and rt.tobytes() == b.tris.tobytes()
+
+
+def check_stackless_invariants(nodes, tris, n_tris, t_offset=0):
+    minw, maxw = fbits(nodes["min"])[:, 3], fbits(nodes["max"])[:, 3]
+    leaf = minw != -1
+    n = len(nodes)
+    assert n == 2 * leaf.sum() - 1                      # node count = 2*leaves - 1
+    ln = minw[leaf] & 0xF
+    assert ln.min() >= 1 and ln.max() <= 2              # leaf length in {1, 2}
+    first = (minw[leaf] >> 4) - t_offset
+    cover = np.zeros(n_tris, np.int32)
+    for f, l in zip(first, ln):
+        cover[f:f + l] += 1
+    assert np.all(cover == 1)                            # every triangle slot referenced exactly once
+    assert maxw[0] == -1
+    assert np.all((maxw == -1) | ((maxw > np.arange(n)) & (maxw < n)))  # miss links go forward and terminate
+    # every child box lies inside its parent box (walk with an explicit stack)
+    stack = [(0, None)]
+    while stack:
+        i, parent = stack.pop()
+        if parent is not None:
+            assert np.all(nodes["min"][i, :3] >= nodes["min"][parent, :3]) and np.all(nodes["max"][i, :3] <= nodes["max"][parent, :3])
+        if not leaf[i]:
+            stack.append((i + 1, i))
+            stack.append((int(maxw[i + 1]), i))
+
+
+@pytest.mark.parametrize("name", ["peach_castle", "soup400", "coplanar_grid", "duplicates", "collinear"])
+def test_structural_invariants(ob, golden_meshes, name):
+    P, F = golden_meshes[name]
+    b = ob.build(ob.STACKLESS, ob.make_vertices(P), F.ravel(), None, t_offset=9)
+    check_stackless_invariants(b.nodes, b.tris, len(F), t_offset=9)
+    assert sorted(b.order.tolist()) == list(range(len(F)))      # DEBUG_BVH permutation check (BVHConstructor.cpp:673-695)
+    assert np.array_equal(b.tris["v"], F[b.order].astype(np.int32))
+    # stack format: same triangles, inner slots = leaves - 1, the rest zero-filled
+    s = ob.build(ob.STACK, ob.make_vertices(P), F.ravel(), None, t_offset=9)
+    assert s.tris.tobytes() == b.tris.tobytes()
+    used = s.stats["stack_slots"]
+    assert used == b.stats["leaves"] - 1
+    assert not np.any(np.ascontiguousarray(s.nodes[used:]).view(np.uint8))
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 50])
+def test_tiny_meshes_are_defined(ob, T):
+    """The reference crashes below 100 triangles; the oracle defines the result."""
+    rng = np.random.default_rng(T)
+    P = rng.uniform(-1, 1, size=(3 * T, 3)).astype(np.float32)
+    F = np.arange(3 * T, dtype=np.uint32).reshape(-1, 3)
+    b = ob.build(ob.STACKLESS, ob.make_vertices(P), F.ravel())
+    check_stackless_invariants(b.nodes, b.tris, T)
+    s = ob.build(ob.STACK, ob.make_vertices(P), F.ravel())
+    assert len(s.nodes) == len(b.nodes)
+
+
+def test_hashed_flips_change_labels_not_triangles(ob, golden_meshes):
+    P, F = golden_meshes["peach_castle"]
+    V = ob.make_vertices(P)
+    a = ob.build(ob.STACKLESS, V, F.ravel())
+    b = ob.build(ob.STACKLESS, V, F.ravel(), swap_policy=ob.SWAP_HASHED, swap_seed=42)
+    c = ob.build(ob.STACKLESS, V, F.ravel(), swap_policy=ob.SWAP_HASHED, swap_seed=42)
+    assert a.tris.tobytes() == b.tris.tobytes()
+    assert a.nodes.tobytes() != b.nodes.tobytes() and b.nodes.tobytes() == c.nodes.tobytes()
+    check_stackless_invariants(b.nodes, b.tris, len(F))
+
+
+def test_bad_input_rejected(ob):
+    V = ob.make_vertices(np.zeros((3, 3), np.float32))
+    with pytest.raises(ValueError):
+        ob.build(ob.STACKLESS, V, np.array([0, 1], np.uint32))
+    with pytest.raises(ValueError):
+        ob.build(ob.STACKLESS, V, np.array([0, 1, 3], np.uint32))

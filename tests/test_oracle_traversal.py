@@ -1,0 +1,133 @@
+"""CPU tests of the traversal restatement.  The reference's traversal is GLSL with no tests and cannot
+run here, so these are closed-form known answers, a brute-force scan, stack-vs-stackless agreement
+and the reference quirks listed in SURVEY.md §7.3/§8a — and the committed oracle vectors."""
+import numpy as np
+import pytest
+
+from cases import build_cases
+from conftest import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def cases_sl(ob, golden_meshes):
+    return {c["name"]: c for c in build_cases(ob, golden_meshes, ob.STACKLESS)}
+
+
+@pytest.fixture(scope="module")
+def cases_st(ob, golden_meshes):
+    return {c["name"]: c for c in build_cases(ob, golden_meshes, ob.STACK)}
+
+
+@pytest.mark.parametrize("fmt_name", ["stackless", "stack"])
+def test_known_answers(ob, cases_sl, cases_st, fmt_name):
+    c = (cases_sl if fmt_name == "stackless" else cases_st)["known_answers"]
+    hits, _ = c["scene"].trace(ob.CLOSEST, c["rays"])
+    sc = c["scene"]
+    # which sorted slot holds the z = 5 triangle?
+    target = int(np.nonzero(sc.tris["v"][:, 0] == 0)[0][0])
+    other = 1 - target
+    h = hits[0] if target != 0 else hits[1]
+    if target != 0:
+        assert h["tri"] == target and h["mesh"] == 11 and h["entity"] == 0
+        assert h["t"] == np.float32(5.0) and (h["u"], h["v"], h["w"]) == (0.25, 0.25, 0.5)
+        # the other triangle is global triangle 0: accepted by the walk, reported as a miss (…Stackless.glsl:300)
+        b = hits[1]
+        assert b["tri"] == 0 and b["mesh"] == 12 and b["entity"] == 0 and b["t"] == -1 and b["u"] == -1
+    else:
+        assert hits[0]["tri"] == 0 and hits[0]["t"] == -1
+        assert hits[1]["tri"] == other and hits[1]["t"] == np.float32(9.0)
+    # pointing away / starting behind the triangle: nothing accepted
+    for k in (2, 3):
+        assert hits[k]["t"] == -1 and hits[k]["tri"] == -1 and hits[k]["mesh"] == -1 and hits[k]["entity"] == -1
+    any_t, _ = sc.trace(ob.ANY, c["rays"])
+    assert any_t[2] == -1 and any_t[3] == -1 and any_t[0] == 5.0
+
+
+def test_brute_force_agreement(ob, cases_sl):
+    c = cases_sl["dragon_random"]
+    rays = c["rays"][:1500]
+    sc = c["scene"]
+    hits, _ = sc.trace(ob.CLOSEST, rays)
+    bf = ob.brute_force(sc.tris, sc.verts, sc.entities, rays, nthreads=8)
+    hit = bf["t"] > 0
+    # the BVH walk may only lose a hit through its box tests; on this seed it loses none
+    assert np.array_equal(hit, (hits["tri"] >= 0))
+    assert np.array_equal(bf["t"][hit], np.where(hits["tri"][hit] > 0, hits["t"][hit], bf["t"][hit]))
+    same = bf["tri"][hit] == hits["tri"][hit]
+    assert same.mean() > 0.999  # exact ties may pick the other triangle
+
+
+@pytest.mark.parametrize("name", ["dragon_random", "multi_entity", "coplanar_grid", "signed_zero"])
+def test_stack_and_stackless_agree(ob, cases_sl, cases_st, name):
+    a, _ = cases_sl[name]["scene"].trace(ob.CLOSEST, cases_sl[name]["rays"], nthreads=4)
+    b, _ = cases_st[name]["scene"].trace(ob.CLOSEST, cases_st[name]["rays"], nthreads=4)
+    agree = (a["tri"] == b["tri"]) & (a["t"] == b["t"]) & (a["entity"] == b["entity"])
+    assert agree.mean() > 0.999, agree.mean()
+
+
+def test_iteration_cap(ob, cases_sl):
+    c = cases_sl["iteration_cap"]
+    hits, cnt = c["scene"].trace(ob.CLOSEST, c["rays"])
+    assert cnt["capped"] >= 1 and hits["iters"].max() == 1024
+
+
+def test_ignore_transparent_and_any(ob, cases_sl):
+    c = cases_sl["multi_entity"]
+    sc, rays = c["scene"], c["rays"]
+    full, _ = sc.trace(ob.CLOSEST, rays, nthreads=4)
+    opaque, _ = sc.trace(ob.CLOSEST_IGNORE_TRANSPARENT, rays, nthreads=4)
+    assert (full["entity"] == 2).any() and not (opaque["entity"] == 2).any()   # entity 2 has alpha 0.5
+    assert (opaque["entity"] == 4).any()                                         # alpha 0.995 >= 0.99 stays
+    any_t, _ = sc.trace(ob.ANY, rays, nthreads=4)
+    assert np.array_equal(any_t > 0, full["tri"] >= 0)
+    short = rays.copy()
+    short["tmax"] = 2.4
+    any_s, _ = sc.trace(ob.ANY, short, nthreads=4)
+    assert np.all(any_s[any_s > 0] < 2.4) and (any_s > 0).sum() < (any_t > 0).sum()
+    # closest t below the bound <=> some hit below the bound
+    closest_t = np.where(full["tri"] >= 0, 1, 0)
+    assert np.all((any_s > 0) <= (closest_t > 0))
+
+
+def test_entity_without_object_raises(ob):
+    sc = ob.Scene(ob.STACKLESS)
+    with pytest.raises(KeyError, match="parent object"):
+        sc.push_entity(99)
+
+
+def test_make_entity_inverse(ob):
+    m = np.eye(4, dtype=np.float32)
+    m[:3, :3] = [[0.5, 0.1, 0], [0, 2, 0.3], [0.2, 0, 1.5]]
+    m[:3, 3] = (1, -2, 3)
+    e = ob.make_entity(m, 3, 9, emissive=1.5, translucency=0.25)[0]
+    inv = e["inverse"].reshape(4, 4).T
+    assert np.allclose(inv @ m, np.eye(4), atol=1e-6)
+    assert e["node_offset"] == 3 and e["node_count"] == 9
+    assert e["data"][:2].view(np.float32).tolist() == [1.5, 0.75]
+
+
+def test_primary_rays_match_formula(ob):
+    from candela_b200 import scenes
+    iv, ip = scenes.camera((1, 2, 3), (4, 2, -1), 64, 36)
+    r = ob.primary_rays(iv, ip, 64, 36)
+    assert np.allclose(r["o"], (1, 2, 3)) and np.allclose(np.linalg.norm(r["d"], axis=1), 1, atol=1e-6)
+    x, y = 40, 9
+    clip = np.array([x / 64 * 2 - 1, y / 36 * 2 - 1, -1, 1], np.float64)
+    eye = ip.astype(np.float64) @ clip
+    d = iv.astype(np.float64) @ np.array([eye[0], eye[1], -1, 0])
+    d = d[:3] / np.linalg.norm(d[:3])
+    assert np.allclose(r["d"][y * 64 + x], d, atol=1e-6)
+
+
+def test_committed_traversal_vectors(ob, golden_meshes):
+    z = np.load(GOLDEN / "traversal_golden.npz")
+    P, F = golden_meshes["dragon"]
+    for fmt, label in ((ob.STACKLESS, "stackless"), (ob.STACK, "stack")):
+        sc = ob.Scene(fmt)
+        sc.add_object(2, ob.make_vertices(P), F.ravel(), np.zeros(len(F), np.int32))
+        sc.push_entity(2)
+        hits, c = sc.trace(ob.CLOSEST, z["rays"], nthreads=2)
+        assert hits.tobytes() == z[f"{label}_hits"].tobytes()
+        any_t, _ = sc.trace(ob.ANY, z["rays"])
+        assert any_t.tobytes() == z[f"{label}_any"].tobytes()
+        assert [c["node_iters"], c["tri_tests"], c["capped"], c["hits"]] == z[f"{label}_counters"].tolist()

@@ -1,0 +1,86 @@
+"""Developer micro-benchmark (not the driver's bench.py): times traversal variants on the S260k
+diffuse batch with device-resident inputs and checks each against the oracle.  Usage on the GPU box:
+    python tools/dev_bench.py [--rays-scale 1] [--check]
+"""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+import candela_b200 as cb  # noqa: E402
+from candela_b200 import scenes  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--modes", default="0,1")
+    ap.add_argument("--fmt", default="stackless")
+    args = ap.parse_args()
+    from oracle import binding as ob
+    fmt = ob.STACKLESS if args.fmt == "stackless" else ob.STACK
+    v, i, m = scenes.make_s260k()
+    t0 = time.time()
+    b = ob.build(fmt, v, i, m)
+    print(f"oracle build {1e3 * (time.time() - t0):.0f} ms, nodes {len(b.nodes)}", flush=True)
+    ri = cb.RayIntersector(fmt)
+    ri.AddPrebuiltObject(2, b.nodes, b.tris, v)
+    ri.BufferData()
+    ri.PushEntity(2)
+    ri.BufferEntities()
+    W, H = args.width, args.height
+    iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
+    hits, rays = ri.IntersectPrimary(iv, ip, W, H, return_rays=True)
+    drays, _ = scenes.bounce_rays(rays, hits, b.tris, v, seed=2)
+    R = len(drays)
+    ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(b.nodes))
+    ref = None
+    t0 = time.time()
+    ref, cnt = ob.trace(fmt, ob.CLOSEST, b.nodes, b.tris, v, ents, drays, nthreads=ob.hardware_threads())
+    cpu_s = time.time() - t0
+    nn, nt = cnt["node_iters"] / R, cnt["tri_tests"] / R
+    bray = nn * (32 if fmt == ob.STACKLESS else 64) + nt * 64
+    print(f"rays {R} Nn {nn:.2f} Nt {nt:.2f} B_ray {bray:.0f} cpu {R / cpu_s / 1e6:.2f} Mrays/s on {ob.hardware_threads()} threads", flush=True)
+    d_rays = torch.from_numpy(drays.view(np.float32).reshape(-1, 8)).cuda()
+    d_prim = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((max(R, len(rays)), 8), dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, dr, n in (("diffuse", d_rays, R), ("primary", d_prim, len(rays))):
+        for mode in [int(x) for x in args.modes.split(",")]:
+            ri.set_traversal_mode(mode)
+            for _ in range(3):
+                ri.intersect_closest_device(dr.data_ptr(), n, d_hits.data_ptr(), 0, stream)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(args.reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ri.intersect_closest_device(dr.data_ptr(), n, d_hits.data_ptr(), 0, stream)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts))
+            line = dict(batch=name, mode=mode, fmt=args.fmt, ms=round(ms, 4), mrays=round(n / ms / 1e3, 1))
+            if name == "diffuse":
+                line["roofline_frac"] = round(n / (ms * 1e-3) * bray / 6550.1e9, 4)
+                if args.check:
+                    got = d_hits[:R].cpu().numpy().view(ob.HIT_DT).reshape(-1)
+                    line["bit_identical"] = bool(got.tobytes() == ref.tobytes())
+            print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
