@@ -1,10 +1,679 @@
+// GPU binned-SAH BVH builder whose output is byte-identical to the reference's CPU builder
+// (Source/Core/BVH/BVHConstructor.cpp; line numbers below refer to it).
+//
+// The reference builds depth-first on one thread.  Its result, however, is a pure function of the
+// input that can be evaluated level by level:
+//   * bin counts / bin boxes, child boxes: min/max/+ reductions, order-independent (the sign of a
+//     zero is the only order-dependent bit; see zero-sign notes below);
+//   * the split search (:276-363): strict `<` over (axis, bin) in order == first minimum;
+//   * the Lomuto partition (:532-549) fixes the order of references inside each range; it is
+//     reproduced exactly by a chunk-parallel emulation (partition_range below);
+//   * leaves are emitted right-range-first (:624-625), so a leaf with build range [s, s+len) lands
+//     at sorted position T-(s+len);
+//   * FlattenBVH (:783-845) numbers nodes in pre-order, FlattenStackBVH (:847-930) numbers inner
+//     nodes in breadth-first order: both follow from subtree sizes / level order.
+// Every float operation uses the non-contracting wrappers of exact_math.cuh.
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
 #include "builder.cuh"
 
 namespace cndl {
 
+namespace {
+
+constexpr float kSentinelMax = 10000000.0f;   // BVHConstructor.h:20
+constexpr float kSentinelMin = -10000000.0f;  // BVHConstructor.h:21
+constexpr int kBins = 64;                      // :46
+constexpr unsigned kMaxLeaf = 2;               // :50
+constexpr float kInfCost = 1e29f;              // :56
+constexpr unsigned kBigNode = 2048;            // ranges longer than this get a 1024-thread block
+
+// glm 0.9.8.5 min/max (func_common.inl:15-28); argument order matters for +0/-0 ties
+__device__ __forceinline__ float gmin(float x, float y) { return x < y ? x : y; }
+__device__ __forceinline__ float gmax(float x, float y) { return x > y ? x : y; }
+
+// order-preserving float <-> int key (involution), for integer atomics on floats
+__device__ __forceinline__ int f2key(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+
+__device__ __forceinline__ float box_area(float mnx, float mny, float mnz, float mxx, float mxy, float mxz) {
+    const float ex = fsub(mxx, mnx), ey = fsub(mxy, mny), ez = fsub(mxz, mnz);  // Bounds::GetArea, BVHConstructor.h:41-44
+    return fadd(fadd(fmul(ex, ey), fmul(ey, ez)), fmul(ez, ex));
+}
+
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // SplitMix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+struct BuildArrays {
+    // per triangle
+    const float4* verts;     // 2 float4 per vertex
+    const uint32_t* indices; // 3 per triangle
+    const int32_t* mesh_ids; // may be null
+    float4* tmin;            // xyz = box min, w = centroid.x
+    float4* tmax;            // xyz = box max, w = centroid.y
+    float* tcz;              // centroid.z
+    int* refs;               // TriangleReferences, partitioned in place
+    unsigned T;
+    // per build node (ids in level order)
+    float4* nmin;            // xyz
+    float4* nmax;
+    unsigned* nstart;        // build range start (leaf: unchanged; pack derives from it)
+    unsigned* nlen;          // build range length
+    int* nchild;             // id of the left child (right = +1), -1 for a leaf
+    unsigned* nsize;         // subtree size in nodes
+    int* npre;               // pre-order index (stackless)
+    int* nlink;              // miss link (stackless)
+    // outputs
+    int4* tris_out;
+    int tri_offset;
+    // root box scratch: 6 ordered keys + 6 zero tie-break positions
+    int* root_scratch;
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-triangle boxes and centroids (:411-427) + root box
+__global__ void tri_precompute_kernel(BuildArrays a) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    float mn[3] = {kSentinelMax, kSentinelMax, kSentinelMax}, mx[3] = {kSentinelMin, kSentinelMin, kSentinelMin};
+    const bool valid = t < a.T;
+    if (valid) {
+        for (int c = 0; c < 3; ++c) {
+            const float4 p = a.verts[2 * (size_t)a.indices[3 * (size_t)t + c]];
+            const float pv[3] = {p.x, p.y, p.z};
+            for (int k = 0; k < 3; ++k) {
+                mn[k] = gmin(mn[k], pv[k]);
+                mx[k] = gmax(mx[k], pv[k]);
+            }
+        }
+        const float cx = fdiv(fadd(mn[0], mx[0]), 2.0f), cy = fdiv(fadd(mn[1], mx[1]), 2.0f), cz = fdiv(fadd(mn[2], mx[2]), 2.0f);
+        a.tmin[t] = make_float4(mn[0], mn[1], mn[2], cx);
+        a.tmax[t] = make_float4(mx[0], mx[1], mx[2], cy);
+        a.tcz[t] = cz;
+        a.refs[t] = (int)t;
+    }
+    // root box: numeric min/max by ordered-int atomics (warp-reduced first)
+    for (int k = 0; k < 3; ++k) {
+        int kmn = f2key(mn[k] == 0.0f ? 0.0f : mn[k]), kmx = f2key(mx[k] == 0.0f ? 0.0f : mx[k]);
+        for (int o = 16; o > 0; o >>= 1) {
+            kmn = min(kmn, __shfl_xor_sync(0xFFFFFFFFu, kmn, o));
+            kmx = max(kmx, __shfl_xor_sync(0xFFFFFFFFu, kmx, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(a.root_scratch + k, kmn);
+            atomicMax(a.root_scratch + 3 + k, kmx);
+        }
+        // MinInitial = glm::min(MinInitial, cur.Min) (:421): ties take the later triangle, so the sign of a
+        // zero result is that of the LAST triangle whose component is zero.
+        if (valid && mn[k] == 0.0f) atomicMax(a.root_scratch + 6 + k, (int)t);
+        if (valid && mx[k] == 0.0f) atomicMax(a.root_scratch + 9 + k, (int)t);
+    }
+}
+
+__global__ void root_finalize_kernel(BuildArrays a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) {
+        mn[k] = key2f(a.root_scratch[k]);
+        mx[k] = key2f(a.root_scratch[3 + k]);
+        if (mn[k] == 0.0f && a.root_scratch[6 + k] >= 0) { const float4 v = a.tmin[a.root_scratch[6 + k]]; mn[k] = k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+        if (mx[k] == 0.0f && a.root_scratch[9 + k] >= 0) { const float4 v = a.tmax[a.root_scratch[9 + k]]; mx[k] = k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+    }
+    a.nmin[0] = make_float4(mn[0], mn[1], mn[2], 0.0f);
+    a.nmax[0] = make_float4(mx[0], mx[1], mx[2], 0.0f);
+    a.nstart[0] = 0;
+    a.nlen[0] = a.T;
+    a.nchild[0] = -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide helpers
+template <int BLOCK>
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums /* BLOCK/32 + 1 */, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < BLOCK / 32 ? warp_sums[lane] : 0;
+        int winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        if (lane < BLOCK / 32) warp_sums[lane] = winc - w;
+        if (lane == 31) warp_sums[BLOCK / 32] = winc;
+    }
+    __syncthreads();
+    total = warp_sums[BLOCK / 32];
+    const int r = warp_sums[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ float centroid_of(const BuildArrays& a, int r, int axis) {
+    return axis == 0 ? a.tmin[r].w : (axis == 1 ? a.tmax[r].w : a.tcz[r]);
+}
+
+struct LevelArgs {
+    BuildArrays a;
+    const int* active;     // node ids to split at this level, in level order
+    const int* klist;      // positions in `active` handled by this launch (one size class)
+    int n_active;
+    int child_base;        // id of the first node of the next level
+    int stackless;
+    int swap_policy;
+    unsigned long long swap_seed;
+    unsigned char* nflip;  // per node: children exchanged at flatten time
+};
+
+// One block owns one node for one level: split search, partition, child boxes, leaf emission.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g) {
+    const BuildArrays& a = g.a;
+    __shared__ int s_count[kBins];
+    __shared__ int s_mn[3][kBins], s_mx[3][kBins];
+    __shared__ int s_warp[BLOCK / 32 + 1];
+    __shared__ float s_best_cost, s_border;
+    __shared__ int s_axis;
+    __shared__ int s_box[2][6];        // child boxes as ordered keys
+    __shared__ int s_zero_first[2][6]; // first position holding a zero component (sign tie-break)
+    __shared__ int s_elem[BLOCK];
+    __shared__ int s_rank[BLOCK];
+    __shared__ unsigned char s_flag[BLOCK];
+
+    const int k = g.klist[blockIdx.x];
+    const int id = g.active[k];
+    const unsigned start = a.nstart[id], len = a.nlen[id];
+    const float4 bmn = a.nmin[id], bmx = a.nmax[id];
+    const float nmn[3] = {bmn.x, bmn.y, bmn.z}, nmx[3] = {bmx.x, bmx.y, bmx.z};
+    const int tid = threadIdx.x;
+
+    // ---- SearchSAHPlaneBinned (:276-363) ----
+    if (tid == 0) { s_best_cost = kInfCost; s_axis = 0; s_border = nmn[0]; }
+    for (int axis = 0; axis < 3; ++axis) {
+        const float lo = nmn[axis], hi = nmx[axis];
+        if (lo == hi) continue;  // :285 (uniform for the block)
+        for (int b = tid; b < kBins; b += BLOCK) {
+            s_count[b] = 0;
+            for (int c = 0; c < 3; ++c) { s_mn[c][b] = f2key(kSentinelMax); s_mx[c][b] = f2key(kSentinelMin); }
+        }
+        __syncthreads();
+        const float extent = fsub(hi, lo);
+        const float scale = fdiv((float)kBins, extent);  // :295
+        for (unsigned i = tid; i < len; i += BLOCK) {
+            const int r = a.refs[start + i];
+            const float4 tm = a.tmin[r], tx = a.tmax[r];
+            const float c = axis == 0 ? tm.w : (axis == 1 ? tx.w : a.tcz[r]);
+            int b = __float2int_rz(fmul(fsub(c, lo), scale));  // :302
+            b = b > kBins - 1 ? kBins - 1 : (b < 0 ? 0 : b);
+            atomicAdd(&s_count[b], 1);
+            // the sign of a zero in a bin box never reaches a decision (only areas use bin boxes)
+            atomicMin(&s_mn[0][b], f2key(tm.x)); atomicMin(&s_mn[1][b], f2key(tm.y)); atomicMin(&s_mn[2][b], f2key(tm.z));
+            atomicMax(&s_mx[0][b], f2key(tx.x)); atomicMax(&s_mx[1][b], f2key(tx.y)); atomicMax(&s_mx[2][b], f2key(tx.z));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // prefix from the left, suffix from the right, then costs (:319-358), on one thread in the
+            // reference's order.  Right-side values are produced first so the cost loop runs ascending.
+            float r_area[kBins - 1];
+            int r_count[kBins - 1];
+            float rmn[3] = {kSentinelMax, kSentinelMax, kSentinelMax}, rmx[3] = {kSentinelMin, kSentinelMin, kSentinelMin};
+            int rsum = 0;
+            for (int j = kBins - 1; j >= 1; --j) {
+                rsum += s_count[j];
+                r_count[j - 1] = rsum;
+                for (int c = 0; c < 3; ++c) { rmn[c] = gmin(rmn[c], key2f(s_mn[c][j])); rmx[c] = gmax(rmx[c], key2f(s_mx[c][j])); }
+                r_area[j - 1] = box_area(rmn[0], rmn[1], rmn[2], rmx[0], rmx[1], rmx[2]);
+            }
+            float lmn[3] = {kSentinelMax, kSentinelMax, kSentinelMax}, lmx[3] = {kSentinelMin, kSentinelMin, kSentinelMin};
+            int lsum = 0;
+            const float step = fdiv(extent, (float)kBins);  // :347
+            float best = s_best_cost;
+            for (int i = 0; i < kBins - 1; ++i) {
+                lsum += s_count[i];
+                for (int c = 0; c < 3; ++c) { lmn[c] = gmin(lmn[c], key2f(s_mn[c][i])); lmx[c] = gmax(lmx[c], key2f(s_mx[c][i])); }
+                const float l_area = box_area(lmn[0], lmn[1], lmn[2], lmx[0], lmx[1], lmx[2]);
+                const float cost = fadd(fmul(__int2float_rn(lsum), l_area), fmul(__int2float_rn(r_count[i]), r_area[i]));  // :351
+                if (cost < best) {
+                    best = cost;
+                    s_axis = axis;
+                    s_border = fadd(lo, fmul(step, __int2float_rn(i + 1)));  // :356
+                }
+            }
+            s_best_cost = best;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const int axis = s_axis;
+    const float border = s_border;
+
+    // ---- Lomuto partition (:532-549), emulated chunk by chunk.  Position i is visited holding its
+    // original element; an element with flag L at chunk rank j lands at mid+j, and whatever sat there
+    // at that moment moves to the L element's old place.  "At that moment" is resolved by following
+    // the chain of earlier swaps inside the chunk (builder). ----
+    unsigned mid = start;
+    for (unsigned i0 = start; i0 < start + len; i0 += BLOCK) {
+        const unsigned n = min((unsigned)BLOCK, start + len - i0);
+        const bool valid = (unsigned)tid < n;
+        const int r = valid ? a.refs[i0 + tid] : -1;
+        const bool f = valid && centroid_of(a, r, axis) < border;
+        int nL;
+        const int rank = block_exclusive_scan<BLOCK>(f ? 1 : 0, s_warp, nL);
+        s_elem[tid] = r;
+        s_rank[tid] = rank;
+        s_flag[tid] = f ? 1 : 0;
+        __syncthreads();
+        const unsigned P = i0 + tid;
+        const unsigned s = mid + (unsigned)rank;
+        int displaced = -1;
+        const bool writes_back = f && s != P && !(P >= mid && P < mid + (unsigned)nL);
+        if (writes_back) {
+            long long q = (long long)s - (long long)i0;
+            while (q >= 0 && s_flag[q]) q = (long long)mid + s_rank[q] - (long long)i0;
+            displaced = q < 0 ? a.refs[(long long)i0 + q] : s_elem[q];
+        }
+        __syncthreads();
+        if (f) a.refs[s] = r;
+        if (writes_back) a.refs[P] = displaced;
+        mid += (unsigned)nL;
+        __syncthreads();
+    }
+    // ---- split failure (:553-556) ----
+    if (mid == start || mid == start + len) mid = start + len / 2;
+
+    // ---- child boxes (:574-597): glm::min(tri, acc) keeps acc on ties => the FIRST zero decides a zero's sign ----
+    if (tid < 12) {
+        const int c = tid % 6;
+        s_box[tid / 6][c] = c < 3 ? f2key(kSentinelMax) : f2key(kSentinelMin);
+        s_zero_first[tid / 6][c] = 0x7FFFFFFF;
+    }
+    __syncthreads();
+    {
+        // every thread accumulates privately per side, then one set of atomics per thread that saw data
+        float lmn[3] = {kSentinelMax, kSentinelMax, kSentinelMax}, lmx[3] = {kSentinelMin, kSentinelMin, kSentinelMin};
+        float rmn[3] = {kSentinelMax, kSentinelMax, kSentinelMax}, rmx[3] = {kSentinelMin, kSentinelMin, kSentinelMin};
+        bool sawl = false, sawr = false;
+        for (unsigned i = tid; i < len; i += BLOCK) {
+            const unsigned pos = start + i;
+            const int r = a.refs[pos];
+            const float4 tm = a.tmin[r], tx = a.tmax[r];
+            const float vmn[3] = {tm.x, tm.y, tm.z}, vmx[3] = {tx.x, tx.y, tx.z};
+            const int side = pos < mid ? 0 : 1;
+            for (int c = 0; c < 3; ++c) {
+                if (side == 0) { lmn[c] = fminf(lmn[c], vmn[c]); lmx[c] = fmaxf(lmx[c], vmx[c]); }
+                else { rmn[c] = fminf(rmn[c], vmn[c]); rmx[c] = fmaxf(rmx[c], vmx[c]); }
+                if (vmn[c] == 0.0f) atomicMin(&s_zero_first[side][c], (int)pos);
+                if (vmx[c] == 0.0f) atomicMin(&s_zero_first[side][3 + c], (int)pos);
+            }
+            if (side == 0) sawl = true; else sawr = true;
+        }
+        for (int c = 0; c < 3; ++c) {
+            if (sawl) { atomicMin(&s_box[0][c], f2key(lmn[c] == 0.0f ? 0.0f : lmn[c])); atomicMax(&s_box[0][3 + c], f2key(lmx[c] == 0.0f ? 0.0f : lmx[c])); }
+            if (sawr) { atomicMin(&s_box[1][c], f2key(rmn[c] == 0.0f ? 0.0f : rmn[c])); atomicMax(&s_box[1][3 + c], f2key(rmx[c] == 0.0f ? 0.0f : rmx[c])); }
+        }
+    }
+    __syncthreads();
+
+    // ---- create the two children (:559-572,:612-625) ----
+    const int child = g.child_base + 2 * k;
+    if (tid < 2) {
+        const int side = tid;
+        float bx[6];
+        for (int c = 0; c < 6; ++c) {
+            bx[c] = key2f(s_box[side][c]);
+            if (bx[c] == 0.0f && s_zero_first[side][c] != 0x7FFFFFFF) {
+                const int r = a.refs[s_zero_first[side][c]];
+                const float4 v = c < 3 ? a.tmin[r] : a.tmax[r];
+                const int cc = c % 3;
+                bx[c] = cc == 0 ? v.x : (cc == 1 ? v.y : v.z);
+            }
+        }
+        const unsigned cstart = side == 0 ? start : mid;
+        const unsigned clen = side == 0 ? mid - start : start + len - mid;
+        a.nmin[child + side] = make_float4(bx[0], bx[1], bx[2], 0.0f);
+        a.nmax[child + side] = make_float4(bx[3], bx[4], bx[5], 0.0f);
+        a.nstart[child + side] = cstart;
+        a.nlen[child + side] = clen;
+        a.nchild[child + side] = -1;
+        g.nflip[child + side] = 0;
+        if (clen <= kMaxLeaf) {
+            // leaf (:456-472): SortedTriangleReferences receives ranges right-first, so this range lands at T-(s+len)
+            const unsigned at = a.T - (cstart + clen);
+            for (unsigned j = 0; j < clen; ++j) {
+                const int r = a.refs[cstart + j];
+                a.tris_out[at + j] = make_int4((int)a.indices[3 * (size_t)r], (int)a.indices[3 * (size_t)r + 1], (int)a.indices[3 * (size_t)r + 2],
+                                               a.mesh_ids ? a.mesh_ids[r] : 0);  // GenerateTriangles, :630-650
+            }
+        }
+    }
+    if (tid == 0) {
+        a.nchild[id] = child;
+        unsigned char flip = 0;
+        if (g.stackless && g.swap_policy == CNDL_SWAP_HASHED)
+            flip = (unsigned char)(mix64(g.swap_seed ^ mix64(((unsigned long long)start << 32) | len)) & 1ull);
+        g.nflip[id] = flip;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of 32-bit values (reduce-then-scan, three launches)
+constexpr int kScanBlock = 512, kScanItems = 4, kScanTile = kScanBlock * kScanItems;
+
+__global__ void scan_reduce_kernel(const int* in, int n, int* block_sums) {
+    __shared__ int s_warp[kScanBlock / 32 + 1];
+    const int base = blockIdx.x * kScanTile;
+    int v = 0;
+    for (int j = 0; j < kScanItems; ++j) {
+        const int i = base + j * kScanBlock + threadIdx.x;
+        if (i < n) v += in[i];
+    }
+    int total;
+    block_exclusive_scan<kScanBlock>(v, s_warp, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void scan_spine_kernel(int* block_sums, int n_blocks, int* total_out) {
+    // single block, sequential over tiles of kScanBlock
+    __shared__ int s_warp[kScanBlock / 32 + 1];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += kScanBlock) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_blocks ? block_sums[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan<kScanBlock>(v, s_warp, total);
+        if (i < n_blocks) block_sums[i] = s_carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = s_carry;
+}
+
+__global__ void scan_apply_kernel(const int* in, int n, const int* block_sums, int* out) {
+    __shared__ int s_warp[kScanBlock / 32 + 1];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems], sum = 0;
+    for (int j = 0; j < kScanItems; ++j) { v[j] = base + j < n ? in[base + j] : 0; sum += v[j]; }
+    int total;
+    int ex = block_exclusive_scan<kScanBlock>(sum, s_warp, total) + block_sums[blockIdx.x];
+    for (int j = 0; j < kScanItems; ++j) {
+        if (base + j < n) out[base + j] = ex;
+        ex += v[j];
+    }
+}
+
+void exclusive_scan(const int* d_in, int n, int* d_out, int* d_block_sums, int* d_total, cudaStream_t st, LaunchCounter& lc) {
+    const int blocks = (n + kScanTile - 1) / kScanTile;
+    scan_reduce_kernel<<<blocks, kScanBlock, 0, st>>>(d_in, n, d_block_sums);
+    scan_spine_kernel<<<1, kScanBlock, 0, st>>>(d_block_sums, blocks, d_total);
+    scan_apply_kernel<<<blocks, kScanBlock, 0, st>>>(d_in, n, d_block_sums, d_out);
+    lc.n += 3;
+}
+
+// flags for the nodes of one level: [0,n) big-inner, [n,2n) small-inner
+__global__ void classify_kernel(const unsigned* nlen, int base, int n, int* flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned len = nlen[base + i];
+    flags[i] = len > kBigNode ? 1 : 0;
+    flags[n + i] = (len > kMaxLeaf && len <= kBigNode) ? 1 : 0;
+}
+
+// offsets = exclusive scan of flags.  Writes the ordered active list and, per size class, the list of
+// positions in it.
+__global__ void compact_kernel(const int* flags, const int* offsets, int base, int n, int* active, int* klist_big, int* klist_small) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int off_big = offsets[i], off_small = offsets[n + i] - offsets[n];
+    const int k = off_big + off_small;
+    if (flags[i]) { active[k] = base + i; klist_big[off_big] = k; }
+    if (flags[n + i]) { active[k] = base + i; klist_small[off_small] = k; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// flatten
+__global__ void subtree_size_kernel(BuildArrays a, int base, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = base + i, c = a.nchild[id];
+    a.nsize[id] = c < 0 ? 1u : 1u + a.nsize[c] + a.nsize[c + 1];
+}
+
+__device__ __forceinline__ int leaf_pack(const BuildArrays& a, int id) {
+    const unsigned s = a.nstart[id], len = a.nlen[id];
+    const unsigned at = a.T - (s + len) + (unsigned)a.tri_offset;  // :469
+    return (int)((at << 4) | (len & 0xF));                         // :794
+}
+
+// FlattenBVH (:783-845), one level per launch, top-down
+__global__ void flatten_stackless_kernel(BuildArrays a, const unsigned char* nflip, int base, int n, float4* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = base + i;
+    if (id == 0) { a.npre[0] = 0; a.nlink[0] = -1; }
+    const int pre = a.npre[id], link = a.nlink[id], c = a.nchild[id];
+    const float4 mn = a.nmin[id], mx = a.nmax[id];
+    int minw;
+    if (c < 0) {
+        minw = leaf_pack(a, id);
+    } else {
+        minw = -1;
+        const int first = nflip[id] ? c + 1 : c, second = nflip[id] ? c : c + 1;
+        a.npre[first] = pre + 1;
+        a.npre[second] = pre + 1 + (int)a.nsize[first];
+        a.nlink[first] = pre + 1 + (int)a.nsize[first];
+        a.nlink[second] = link;
+    }
+    out[2 * (size_t)pre] = make_float4(mn.x, mn.y, mn.z, __int_as_float(minw));
+    out[2 * (size_t)pre + 1] = make_float4(mx.x, mx.y, mx.z, __int_as_float(link));
+}
+
+__global__ void inner_flags_kernel(BuildArrays a, int n, int* flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = a.nchild[i] >= 0 ? 1 : 0;
+}
+
+// FlattenStackBVH (:847-930): inner nodes in breadth-first order == level order of ids
+__global__ void flatten_stack_kernel(BuildArrays a, int n, const int* slot, float4* out) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const int c = a.nchild[id];
+    if (c < 0) return;
+    float4* o = out + 4 * (size_t)slot[id];
+    for (int side = 0; side < 2; ++side) {
+        const int ch = c + side;
+        const float4 mn = a.nmin[ch], mx = a.nmax[ch];
+        const bool leaf = a.nchild[ch] < 0;
+        o[2 * side] = make_float4(mn.x, mn.y, mn.z, __int_as_float(leaf ? leaf_pack(a, ch) : -1));
+        o[2 * side + 1] = make_float4(mx.x, mx.y, mx.z, leaf ? 0.0f : __int_as_float(slot[ch]));
+    }
+}
+
+// a root that is itself a leaf (T <= 2)
+__global__ void single_leaf_kernel(BuildArrays a, int stackless, float4* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (unsigned j = 0; j < a.T; ++j)
+        a.tris_out[j] = make_int4((int)a.indices[3 * j], (int)a.indices[3 * j + 1], (int)a.indices[3 * j + 2], a.mesh_ids ? a.mesh_ids[j] : 0);
+    const float4 mn = a.nmin[0], mx = a.nmax[0];
+    const int pack = leaf_pack(a, 0);
+    if (stackless) {
+        out[0] = make_float4(mn.x, mn.y, mn.z, __int_as_float(pack));
+        out[1] = make_float4(mx.x, mx.y, mx.z, __int_as_float(-1));
+    } else {
+        // the reference dereferences null here; defined as: left = the leaf, right = an empty leaf
+        out[0] = make_float4(mn.x, mn.y, mn.z, __int_as_float(pack));
+        out[1] = make_float4(mx.x, mx.y, mx.z, 0.0f);
+        out[2] = make_float4(kSentinelMax, kSentinelMax, kSentinelMax, __int_as_float(0));
+        out[3] = make_float4(kSentinelMin, kSentinelMin, kSentinelMin, 0.0f);
+    }
+}
+
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    template <class T>
+    cudaError_t alloc(T** p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) { ptrs.push_back(q); *p = static_cast<T*>(q); }
+        return e;
+    }
+};
+
+}  // namespace
+
+int build_lbvh_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* build_ms, std::string& err);
+
+#define BK(call)                                                          \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) {                                         \
+            err = std::string(#call) + ": " + cudaGetErrorString(e__);    \
+            return e__ == cudaErrorMemoryAllocation ? CNDL_ERR_OOM : CNDL_ERR_CUDA; \
+        }                                                                 \
+    } while (0)
+
 int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* build_ms, std::string& err) {
+    if (rq.opts.builder == CNDL_BUILDER_LBVH) return build_lbvh_object(rq, st, lc, build_ms, err);
+    if (rq.opts.builder != CNDL_BUILDER_SAH_EXACT) { err = "unknown builder"; return CNDL_ERR_INVALID; }
+    const size_t T = rq.T;
+    if (T == 0 || T > (1ull << 27)) { err = "triangle count out of range"; return CNDL_ERR_INVALID; }
+    for (size_t i = 0; i < 3 * T; ++i)
+        if (rq.h_indices[i] >= rq.V) { err = "vertex index out of range"; return CNDL_ERR_INVALID; }
+    const size_t n_max = 2 * T - 1;
+    const bool stackless = rq.format == CNDL_STACKLESS;
+
+    Scratch sc;
+    BuildArrays a{};
+    uint32_t* d_idx = nullptr;
+    int32_t* d_mesh = nullptr;
+    unsigned char* d_flip = nullptr;
+    int *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr;
+    BK(sc.alloc(&d_idx, 3 * T));
+    if (rq.h_mesh_ids) BK(sc.alloc(&d_mesh, T));
+    BK(sc.alloc(&a.tmin, T)); BK(sc.alloc(&a.tmax, T)); BK(sc.alloc(&a.tcz, T)); BK(sc.alloc(&a.refs, T));
+    BK(sc.alloc(&a.nmin, n_max)); BK(sc.alloc(&a.nmax, n_max)); BK(sc.alloc(&a.nstart, n_max)); BK(sc.alloc(&a.nlen, n_max));
+    BK(sc.alloc(&a.nchild, n_max)); BK(sc.alloc(&a.nsize, n_max)); BK(sc.alloc(&a.npre, n_max)); BK(sc.alloc(&a.nlink, n_max));
+    BK(sc.alloc(&d_flip, n_max));
+    BK(sc.alloc(&a.root_scratch, 16));
+    const size_t scan_n = std::max<size_t>(2 * n_max, 16);
+    BK(sc.alloc(&d_flags, scan_n)); BK(sc.alloc(&d_offsets, scan_n));
+    BK(sc.alloc(&d_block_sums, scan_n / kScanTile + 2)); BK(sc.alloc(&d_totals, 4));
+    BK(sc.alloc(&d_active, n_max)); BK(sc.alloc(&d_active_next, n_max)); BK(sc.alloc(&d_kl_big, n_max)); BK(sc.alloc(&d_kl_small, n_max));
+
+    cudaEvent_t ev0, ev1;
+    BK(cudaEventCreate(&ev0));
+    BK(cudaEventCreate(&ev1));
+    BK(cudaMemcpyAsync(d_idx, rq.h_indices, 3 * T * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (rq.h_mesh_ids) BK(cudaMemcpyAsync(d_mesh, rq.h_mesh_ids, T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    BK(cudaEventRecord(ev0, st));  // build time: geometry resident, like the reference's timer around BuildBVH (:953)
+
+    a.verts = rq.d_verts;
+    a.indices = d_idx;
+    a.mesh_ids = d_mesh;
+    a.T = (unsigned)T;
+    a.tris_out = rq.d_tris_out;
+    a.tri_offset = rq.tri_offset;
+
+    const int h_root_init[12] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000, -1, -1, -1, -1, -1, -1};
+    BK(cudaMemcpyAsync(a.root_scratch, h_root_init, sizeof(h_root_init), cudaMemcpyHostToDevice, st));
+    BK(cudaMemsetAsync(d_flip, 0, n_max, st));
+    tri_precompute_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(a);
+    root_finalize_kernel<<<1, 32, 0, st>>>(a);
+    lc.n += 2;
+
+    std::vector<int> level_base{0}, level_count{1};
+    size_t n_nodes = 1;
+    float4* out = static_cast<float4*>(rq.d_nodes_out);
+
+    if (T <= kMaxLeaf) {
+        single_leaf_kernel<<<1, 32, 0, st>>>(a, stackless ? 1 : 0, out);
+        lc.n++;
+    } else {
+        // level 0: the root is the only active node
+        int n_big = T > kBigNode ? 1 : 0, n_small = 1 - n_big;
+        BK(cudaMemsetAsync(d_active, 0, sizeof(int), st));
+        BK(cudaMemsetAsync(d_kl_big, 0, sizeof(int), st));
+        BK(cudaMemsetAsync(d_kl_small, 0, sizeof(int), st));
+        while (n_big + n_small > 0) {
+            const int n_active = n_big + n_small;
+            LevelArgs g;
+            g.a = a;
+            g.active = d_active;
+            g.n_active = n_active;
+            g.child_base = (int)n_nodes;
+            g.stackless = stackless ? 1 : 0;
+            g.swap_policy = rq.opts.swap_policy;
+            g.swap_seed = rq.opts.swap_seed;
+            g.nflip = d_flip;
+            if (n_big) { g.klist = d_kl_big; level_step_kernel<1024><<<n_big, 1024, 0, st>>>(g); lc.n++; }
+            if (n_small) { g.klist = d_kl_small; level_step_kernel<128><<<n_small, 128, 0, st>>>(g); lc.n++; }
+            BK(cudaGetLastError());
+            const int base = (int)n_nodes, n = 2 * n_active;
+            level_base.push_back(base);
+            level_count.push_back(n);
+            n_nodes += (size_t)n;
+            // next level's active list
+            classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.nlen, base, n, d_flags);
+            lc.n++;
+            exclusive_scan(d_flags, 2 * n, d_offsets, d_block_sums, d_totals, st, lc);
+            compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_flags, d_offsets, base, n, d_active_next, d_kl_big, d_kl_small);
+            lc.n++;
+            int h_tot[2];
+            BK(cudaMemcpyAsync(&h_tot[0], d_totals, sizeof(int), cudaMemcpyDeviceToHost, st));
+            BK(cudaMemcpyAsync(&h_tot[1], d_offsets + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+            BK(cudaStreamSynchronize(st));
+            n_big = h_tot[1];
+            n_small = h_tot[0] - h_tot[1];
+            std::swap(d_active, d_active_next);
+        }
+        // flatten
+        for (int d = (int)level_base.size() - 1; d >= 0; --d) {
+            subtree_size_kernel<<<(level_count[d] + 255) / 256, 256, 0, st>>>(a, level_base[d], level_count[d]);
+            lc.n++;
+        }
+        if (stackless) {
+            for (size_t d = 0; d < level_base.size(); ++d) {
+                flatten_stackless_kernel<<<(level_count[d] + 255) / 256, 256, 0, st>>>(a, d_flip, level_base[d], level_count[d], out);
+                lc.n++;
+            }
+        } else {
+            const int n = (int)n_nodes;
+            BK(cudaMemsetAsync(out, 0, n_nodes * sizeof(cndl_stack_node), st));  // unused slots stay zero (:762-765)
+            inner_flags_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, n, d_flags);
+            exclusive_scan(d_flags, n, d_offsets, d_block_sums, d_totals, st, lc);
+            flatten_stack_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, n, d_offsets, out);
+            lc.n += 2;
+        }
+        BK(cudaGetLastError());
+    }
+    BK(cudaEventRecord(ev1, st));
+    BK(cudaStreamSynchronize(st));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    if (build_ms) *build_ms = ms;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    rq.n_nodes_out = n_nodes;
+    return CNDL_OK;
+}
+
+int build_lbvh_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* build_ms, std::string& err) {
     (void)rq; (void)st; (void)lc; (void)build_ms;
-    err = "GPU builder not implemented yet";
+    err = "LBVH builder not implemented yet";
     return CNDL_ERR_INVALID;
 }
 
