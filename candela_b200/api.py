@@ -33,7 +33,7 @@ EXPORTS = [
     "cndl_device_buffers", "cndl_push_entity", "cndl_push_entity_records", "cndl_buffer_entities", "cndl_entity_count",
     "cndl_intersect_closest", "cndl_intersect_any", "cndl_intersect_closest_device", "cndl_intersect_any_device",
     "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_host_alloc", "cndl_host_free",
-    "cndl_set_traversal_mode", "cndl_launch_count", "cndl_last_build_ms",
+    "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
     L.cndl_host_free.argtypes = [vp]
     L.cndl_host_free.restype = None
     L.cndl_set_traversal_mode.argtypes = [vp, C.c_int, C.c_int]
+    L.cndl_set_tuning.argtypes = [vp, C.c_int, C.c_int]
     L.cndl_launch_count.argtypes = [vp]
     L.cndl_launch_count.restype = C.c_uint64
     L.cndl_last_build_ms.argtypes = [vp]
@@ -269,6 +270,9 @@ class RayIntersector:
 
     def set_traversal_mode(self, mode: int, sort_rays: bool = False):
         self._check(self._lib.cndl_set_traversal_mode(self._h, mode, int(sort_rays)))
+
+    def set_tuning(self, knob: int, value: int):
+        self._check(self._lib.cndl_set_tuning(self._h, knob, value))
 
     # -- queries: host buffers --------------------------------------------------------------------
     def IntersectRays(self, rays, ignore_transparent: bool = False, out=None) -> np.ndarray:

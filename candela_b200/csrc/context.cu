@@ -71,7 +71,8 @@ struct cndl_ctx {
     DeviceBuffer d_rays, d_hits, d_order, d_keys, d_sort_tmp, d_counter;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaStream_t main_stream = nullptr;
-    int mode = 1, sort_rays = 0;
+    int mode = 2, sort_rays = 0;
+    int knobs[8] = {8, 8, 8, 2, 0, 0, 0, 0};  // CNDL_KNOB_*
     LaunchCounter launches;
     float last_build_ms = 0.0f;
 
@@ -114,6 +115,9 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
     const SceneView s = scene_view(ctx);
     const bool stack = ctx->format == CNDL_STACK;
     if (ctx->mode == 0 || stack) launch_trace_simple(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, st, ctx->launches);
+    else if (ctx->mode == 2)
+        launch_trace_ww(s, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM],
+                        ctx->knobs[CNDL_KNOB_LEAF_THRESHOLD], ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD], ctx->knobs[CNDL_KNOB_VARIANT], st, ctx->launches);
     else launch_trace_persistent(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, st, ctx->launches);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return ctx->cuda_fail(e, "traversal launch");
@@ -381,9 +385,16 @@ int cndl_buffer_entities(cndl_ctx* ctx) {
 }
 
 int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays) {
-    if (!ctx || mode < 0 || mode > 1) return CNDL_ERR_INVALID;
+    if (!ctx || mode < 0 || mode > 2) return CNDL_ERR_INVALID;
     ctx->mode = mode;
     ctx->sort_rays = sort_rays ? 1 : 0;
+    return CNDL_OK;
+}
+
+int cndl_set_tuning(cndl_ctx* ctx, int knob, int value) {
+    if (!ctx || knob < 0 || knob >= 8 || value < 0) return CNDL_ERR_INVALID;
+    if (knob == CNDL_KNOB_BLOCKS_PER_SM && (value < 1 || value > 16)) return CNDL_ERR_INVALID;
+    ctx->knobs[knob] = value;
     return CNDL_OK;
 }
 

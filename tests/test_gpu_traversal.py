@@ -39,7 +39,7 @@ def all_cases(ob, golden_meshes):
     return {f: build_cases(ob, golden_meshes, fmt_id(ob, f)) for f in FORMATS}
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("fmt", FORMATS)
 def test_closest_and_any_parity_all_cases(cb, ob, all_cases, fmt, mode):
     for c in all_cases[fmt]:

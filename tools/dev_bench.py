@@ -25,8 +25,10 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--modes", default="0,1")
+    ap.add_argument("--modes", default="0,1,2")
+    ap.add_argument("--knobs", default="", help="semicolon-separated bps,leaf,idle triples for mode 2")
     ap.add_argument("--fmt", default="stackless")
+    ap.add_argument("--presort", type=int, default=0, help="host-side Morton sort of the diffuse rays (experiment)")
     args = ap.parse_args()
     from oracle import binding as ob
     fmt = ob.STACKLESS if args.fmt == "stackless" else ob.STACK
@@ -43,6 +45,19 @@ def main():
     iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
     hits, rays = ri.IntersectPrimary(iv, ip, W, H, return_rays=True)
     drays, _ = scenes.bounce_rays(rays, hits, b.tris, v, seed=2)
+    if args.presort:
+        o = drays["o"]; d = drays["d"]
+        lo, hi = o.min(0), o.max(0)
+        q = np.clip(((o - lo) / (hi - lo) * (2 ** args.presort - 1)).astype(np.uint64), 0, 2 ** args.presort - 1)
+        def spread(x):
+            r = np.zeros_like(x)
+            for b in range(args.presort):
+                r |= ((x >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b)
+            return r
+        key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
+        octant = ((d[:, 0] > 0).astype(np.uint64) | ((d[:, 1] > 0).astype(np.uint64) << np.uint64(1)) | ((d[:, 2] > 0).astype(np.uint64) << np.uint64(2)))
+        key = (key << np.uint64(3)) | octant
+        drays = drays[np.argsort(key, kind="stable")]
     R = len(drays)
     ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(b.nodes))
     ref = None
@@ -58,8 +73,17 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     for name, dr, n in (("diffuse", d_rays, R), ("primary", d_prim, len(rays))):
+        variants = []
         for mode in [int(x) for x in args.modes.split(",")]:
+            if mode == 2 and args.knobs:
+                variants += [(2, tuple(int(v) for v in k.split(","))) for k in args.knobs.split(";")]
+            else:
+                variants.append((mode, None))
+        for mode, knobs in variants:
             ri.set_traversal_mode(mode)
+            if knobs:
+                for kid, val in enumerate(knobs):
+                    ri.set_tuning(kid, val)
             for _ in range(3):
                 ri.intersect_closest_device(dr.data_ptr(), n, d_hits.data_ptr(), 0, stream)
             torch.cuda.synchronize()
@@ -73,7 +97,7 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             ms = float(np.median(ts))
-            line = dict(batch=name, mode=mode, fmt=args.fmt, ms=round(ms, 4), mrays=round(n / ms / 1e3, 1))
+            line = dict(batch=name, mode=mode, knobs=knobs, fmt=args.fmt, ms=round(ms, 4), mrays=round(n / ms / 1e3, 1))
             if name == "diffuse":
                 line["roofline_frac"] = round(n / (ms * 1e-3) * bray / 6550.1e9, 4)
                 if args.check:
