@@ -1,0 +1,70 @@
+"""Multi-GPU host logic: the path shards with no exchange step.  Screen tiles are dealt
+round-robin to ranks, every rank traces its own tiles against its replica of the BVH, and hit
+records are gathered once for the final frame.  Works with any torch.distributed backend (NCCL on
+the GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def tile_ids(width: int, height: int, tile: int = 64) -> np.ndarray:
+    """Tile index of every pixel (row-major pixels, row-major tiles)."""
+    ys, xs = np.divmod(np.arange(width * height, dtype=np.int64), width)
+    return (ys // tile) * ((width + tile - 1) // tile) + (xs // tile)
+
+
+def shard_pixels(width: int, height: int, world: int, rank: int, tile: int = 64) -> np.ndarray:
+    """Pixel indices owned by `rank`: tiles dealt round-robin by tile index, pixels in tile-major order."""
+    tid = tile_ids(width, height, tile)
+    mine = np.nonzero(tid % world == rank)[0]
+    return mine[np.argsort(tid[mine], kind="stable")]
+
+
+def shard_range(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous split of n rays (config 5)."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def gather_frame(local_records, pixel_index, n_pixels: int, group=None):
+    """Assembles the final frame on every rank: `local_records` [n_local, K] (torch tensor on the
+    backend's device) belong to pixels `pixel_index` [n_local] (int64 tensor).  Returns [n_pixels, K].
+    One all_gather of padded shards; ranks may own different numbers of pixels."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        out = torch.full((n_pixels, local_records.shape[1]), -1, dtype=local_records.dtype, device=local_records.device)
+        out[pixel_index] = local_records
+        return out
+    n_local = torch.tensor([local_records.shape[0]], dtype=torch.int64, device=local_records.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    n_max = int(max(c.item() for c in counts))
+    pad_r = torch.zeros((n_max, local_records.shape[1]), dtype=local_records.dtype, device=local_records.device)
+    pad_i = torch.full((n_max,), -1, dtype=torch.int64, device=local_records.device)
+    pad_r[: local_records.shape[0]] = local_records
+    pad_i[: local_records.shape[0]] = pixel_index
+    all_r = [torch.empty_like(pad_r) for _ in range(world)]
+    all_i = [torch.empty_like(pad_i) for _ in range(world)]
+    dist.all_gather(all_r, pad_r, group=group)
+    dist.all_gather(all_i, pad_i, group=group)
+    out = torch.full((n_pixels, local_records.shape[1]), -1, dtype=local_records.dtype, device=local_records.device)
+    for r, i, c in zip(all_r, all_i, counts):
+        n = int(c.item())
+        out[i[:n]] = r[:n]
+    return out
+
+
+def reduce_timing(ms_local: float, units_local: float, device="cpu", group=None) -> tuple[float, float]:
+    """(max over ranks of the device time, sum over ranks of the units processed)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return ms_local, units_local
+    t = torch.tensor([ms_local], dtype=torch.float64, device=device)
+    u = torch.tensor([units_local], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item()), float(u.item())

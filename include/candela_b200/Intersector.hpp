@@ -1,0 +1,185 @@
+// Header-only C++17 mirror of Candela's host-side intersector API over the C ABI of
+// libcandela_b200.so.  It has the reference's class, method and public-member names
+// (Source/Core/BVH/Intersector.h:60-124, BVHConstructor.h:61-87) so that engine code such as
+//
+//     Candela::RayIntersector<Candela::BVH::StacklessTraversalNode> Intersector;
+//     Intersector.Initialize();
+//     Intersector.AddObject(MainModel);
+//     Intersector.BufferData(true);
+//     ... per frame: Intersector.PushEntities(EntityRenderList); Intersector.BufferEntities();
+//
+// (Pipeline.cpp:1019-1028, :1250-1251) compiles against it unchanged.  The OpenGL-specific members
+// (SSBO ids, BindEverything(shader), texture tables) have no meaning on a CUDA backend; their
+// replacement is DeviceBuffers() (device pointers for the caller's own kernels) and the batch
+// queries IntersectRays / IntersectRaysAny, which return the hit records the GLSL callers consumed.
+//
+// Object / Mesh / Entity are taken as template parameters ("duck typing"): anything with the
+// reference's member names works, including the engine's own classes
+// (Object::m_Meshes, Object::GetID(), Mesh::m_Vertices / m_Indices / GlobalMeshNumber,
+//  Entity::m_Object, m_Model, m_EmissiveAmount, m_TranslucencyAmount).
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../candela_b200.h"
+
+namespace Candela {
+
+struct Vertex {  // Utils/Vertex.h:7-12
+    float position[4];
+    std::uint32_t normal_tangent_data[3];
+    std::uint32_t texcoords;
+};
+
+namespace BVH {
+struct FBounds { float Min[4]; float Max[4]; };
+struct FlattenedNode { float Min[4]; float Max[4]; };            // BVHConstructor.h:66-70
+struct FlattenedStackNode { FBounds LBounds; FBounds RBounds; };  // BVHConstructor.h:72-77
+struct Triangle { int PackedData[4]; };                           // BVHConstructor.h:79-84
+typedef FlattenedNode StacklessTraversalNode;                     // Intersector.h:39
+typedef FlattenedStackNode StackTraversalNode;                    // Intersector.h:40
+}  // namespace BVH
+
+struct BVHEntity {  // Intersector.h:43-49
+    float ModelMatrix[16];
+    float InverseMatrix[16];
+    int NodeOffset;
+    int NodeCount;
+    int Data[14];
+};
+
+struct RayHit { float T, U, V, W; int Mesh, TriangleIdx, Entity, Iters; };  // cndl_hit
+struct Ray { float Origin[3]; float TMin; float Direction[3]; float TMax; }; // cndl_ray
+
+static_assert(sizeof(Vertex) == 32 && sizeof(BVH::Triangle) == 16 && sizeof(BVH::FlattenedNode) == 32 &&
+                  sizeof(BVH::FlattenedStackNode) == 64 && sizeof(BVHEntity) == 192 && sizeof(RayHit) == 32 && sizeof(Ray) == 32,
+              "record layouts are the contract (SURVEY.md §8a)");
+
+template <typename T>
+class RayIntersector {
+public:
+    RayIntersector() {
+        // Intersector.h:138-148
+        if (std::is_same<T, BVH::FlattenedStackNode>::value) m_Stackless = false;
+        else if (std::is_same<T, BVH::FlattenedNode>::value) m_Stackless = true;
+        else throw "\nTemplate <T> Passed to RayIntersector can only be of type BVH::FlattenedStackNode or BVH::FlattenedNode>!";
+    }
+    ~RayIntersector() { if (m_Ctx) cndl_destroy(m_Ctx); }
+    RayIntersector(const RayIntersector&) = delete;
+    RayIntersector& operator=(const RayIntersector&) = delete;
+
+    // Intersector.h:154 compiles the trace shader; here it opens the CUDA context on `Device`.
+    void Initialize(int Device = 0) {
+        if (m_Ctx) return;
+        if (cndl_create(&m_Ctx, m_Stackless ? CNDL_STACKLESS : CNDL_STACK, Device) != CNDL_OK)
+            throw "candela_b200: no usable sm_100 CUDA device (there is no CPU fallback)";
+    }
+
+    // Intersector.h:170-198.  The mesh concatenation of BuildBVH (BVHConstructor.cpp:981-1002) happens here on
+    // the host; the build itself runs on the GPU and is byte-identical to BVH::BuildBVH.
+    template <typename ObjectT>
+    void AddObject(const ObjectT& object, const cndl_build_opts* Options = nullptr) {
+        Require();
+        std::vector<Vertex> Vertices;
+        std::vector<std::uint32_t> MeshIndices;
+        std::vector<std::int32_t> MeshReferences;
+        std::uint32_t IndexOffset = 0;
+        for (const auto& Mesh : object.m_Meshes) {
+            for (std::size_t x = 0; x < Mesh.m_Indices.size(); ++x) {
+                MeshIndices.push_back(static_cast<std::uint32_t>(Mesh.m_Indices[x]) + IndexOffset);
+                if (x % 3 == 0) MeshReferences.push_back(Mesh.GlobalMeshNumber);
+            }
+            const std::size_t at = Vertices.size();
+            Vertices.resize(at + Mesh.m_Vertices.size());
+            static_assert(sizeof(Mesh.m_Vertices[0]) == sizeof(Vertex), "Vertex must be the 32-byte record");
+            if (!Mesh.m_Vertices.empty()) std::memcpy(&Vertices[at], &Mesh.m_Vertices[0], Mesh.m_Vertices.size() * sizeof(Vertex));
+            IndexOffset += static_cast<std::uint32_t>(Mesh.m_Vertices.size());
+        }
+        Check(cndl_add_object(m_Ctx, static_cast<std::uint32_t>(object.GetID()), reinterpret_cast<const cndl_vertex*>(Vertices.data()),
+                              Vertices.size(), MeshIndices.data(), MeshIndices.size(), MeshReferences.data(), Options));
+    }
+
+    // Intersector.h:201-216
+    template <typename EntityT>
+    void PushEntity(const EntityT& entity) {
+        Require();
+        const int rc = cndl_push_entity(m_Ctx, static_cast<std::uint32_t>(entity.m_Object->m_ObjectID), &entity.m_Model[0][0],
+                                        entity.m_EmissiveAmount, entity.m_TranslucencyAmount);
+        if (rc == CNDL_ERR_UNKNOWN_OBJECT) throw "Trying to push entity whose parent object hasn't been added to global BVH";
+        Check(rc);
+    }
+    template <typename EntityT>
+    void PushEntities(const std::vector<EntityT*>& Entities) {  // Intersector.h:219-224
+        for (const auto& e : Entities) PushEntity(*e);
+    }
+    void BufferEntities() { Require(); Check(cndl_buffer_entities(m_Ctx)); }           // Intersector.h:227-239
+    void BufferData(bool ClearCPUData) { Require(); Check(cndl_commit(m_Ctx, ClearCPUData ? 1 : 0)); }  // Intersector.h:322-351
+
+    // Intersector.h:241-266 with hit records instead of an albedo image. Matrices are glm::mat4-compatible (column-major).
+    void IntersectPrimary(RayHit* Output, int Width, int Height, const float* InverseView, const float* InverseProjection) {
+        Require();
+        Check(cndl_intersect_primary(m_Ctx, InverseView, InverseProjection, Width, Height, reinterpret_cast<cndl_hit*>(Output), nullptr));
+    }
+
+    // IntersectRay / IntersectRayIgnoreTransparent of TraverseBVH.glsl for a batch of rays (host buffers).
+    void IntersectRays(const Ray* Rays, std::size_t Count, RayHit* Hits, bool IgnoreTransparent = false) {
+        Require();
+        Check(cndl_intersect_closest(m_Ctx, reinterpret_cast<const cndl_ray*>(Rays), Count, IgnoreTransparent ? CNDL_IGNORE_TRANSPARENT : 0,
+                                     reinterpret_cast<cndl_hit*>(Hits)));
+    }
+    // float IntersectRay(o, d): first accepted t or -1.
+    void IntersectRaysAny(const Ray* Rays, std::size_t Count, float* Traversals) {
+        Require();
+        Check(cndl_intersect_any(m_Ctx, reinterpret_cast<const cndl_ray*>(Rays), Count, Traversals));
+    }
+
+    // Replacement for BindEverything (Intersector.h:269-320): device pointers of the five buffers.
+    void DeviceBuffers(const T** Nodes, const BVH::Triangle** Triangles, const Vertex** Vertices, const BVHEntity** Entities) {
+        Require();
+        const void* n = nullptr;
+        const cndl_triangle* t = nullptr;
+        const cndl_vertex* v = nullptr;
+        const cndl_entity* e = nullptr;
+        Check(cndl_device_buffers(m_Ctx, &n, &t, &v, &e));
+        if (Nodes) *Nodes = static_cast<const T*>(n);
+        if (Triangles) *Triangles = reinterpret_cast<const BVH::Triangle*>(t);
+        if (Vertices) *Vertices = reinterpret_cast<const Vertex*>(v);
+        if (Entities) *Entities = reinterpret_cast<const BVHEntity*>(e);
+    }
+
+    // Fills the public host arrays the reference exposes (Intersector.h:96-98; read by Physics.cpp:100-126).
+    void FetchCPUData() {
+        Require();
+        m_BVHNodes.resize(cndl_node_count(m_Ctx));
+        m_BVHTriangles.resize(cndl_triangle_count(m_Ctx));
+        m_BVHVertices.resize(cndl_vertex_count(m_Ctx));
+        Check(cndl_read_buffers(m_Ctx, m_BVHNodes.data(), reinterpret_cast<cndl_triangle*>(m_BVHTriangles.data()),
+                                reinterpret_cast<cndl_vertex*>(m_BVHVertices.data())));
+    }
+
+    bool Collide(const float* /*Point*/) { return false; }  // Intersector.h:354-358 (a stub in the reference too)
+    void Recompile() {}                                      // Intersector.h:361-365
+    cndl_ctx* Context() { return m_Ctx; }
+
+    std::vector<T> m_BVHNodes;
+    std::vector<Vertex> m_BVHVertices;
+    std::vector<BVH::Triangle> m_BVHTriangles;
+
+private:
+    void Require() { if (!m_Ctx) Initialize(0); }
+    void Check(int rc) {
+        if (rc != CNDL_OK) {
+            m_LastError = cndl_last_error(m_Ctx);
+            throw m_LastError.c_str();  // the reference throws C strings (Intersector.h:147,:204)
+        }
+    }
+    cndl_ctx* m_Ctx = nullptr;
+    bool m_Stackless = false;
+    std::string m_LastError;
+};
+
+}  // namespace Candela

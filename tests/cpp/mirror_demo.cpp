@@ -1,0 +1,93 @@
+// Drives include/candela_b200/Intersector.hpp the way Pipeline.cpp:1019-1028,:1250-1251 drives the
+// reference's RayIntersector: Initialize, AddObject, BufferData, PushEntities, BufferEntities, then a
+// batch of rays.  Prints "OK <hits> <checksum>" on success; exits 3 when there is no GPU (the
+// backend has no CPU fallback).  The Object/Mesh/Entity structs below stand in for the engine's.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "candela_b200/Intersector.hpp"
+
+struct Mesh {
+    std::vector<Candela::Vertex> m_Vertices;
+    std::vector<unsigned> m_Indices;
+    int GlobalMeshNumber = 0;
+};
+struct Object {
+    std::vector<Mesh> m_Meshes;
+    unsigned m_ObjectID = 2;  // Object.cpp:7-9: ids start at 2
+    unsigned GetID() const { return m_ObjectID; }
+};
+struct Entity {
+    const Object* m_Object;
+    float m_Model[4][4];
+    float m_EmissiveAmount = 0.0f, m_TranslucencyAmount = 0.0f;
+};
+
+int main() {
+    Object obj;
+    for (int m = 0; m < 2; ++m) {  // two meshes: a floor grid and a wall grid
+        Mesh mesh;
+        mesh.GlobalMeshNumber = 5 + m;
+        const int n = 12;
+        for (int i = 0; i <= n; ++i)
+            for (int j = 0; j <= n; ++j) {
+                Candela::Vertex v{};
+                v.position[0] = (float)i;
+                v.position[1] = m == 0 ? 0.0f : (float)j;
+                v.position[2] = m == 0 ? (float)j : 0.0f;
+                v.position[3] = 1.0f;
+                mesh.m_Vertices.push_back(v);
+            }
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                const unsigned a = i * (n + 1) + j, b = a + n + 1;
+                const unsigned idx[6] = {a, b, b + 1, a, b + 1, a + 1};
+                mesh.m_Indices.insert(mesh.m_Indices.end(), idx, idx + 6);
+            }
+        obj.m_Meshes.push_back(mesh);
+    }
+    try {
+        Candela::RayIntersector<Candela::BVH::StacklessTraversalNode> Intersector;
+        try {
+            Intersector.Initialize();
+        } catch (const char* e) {
+            std::printf("NO_GPU %s\n", e);
+            return 3;
+        }
+        Intersector.AddObject(obj);
+        Intersector.BufferData(true);
+        Entity ent{&obj, {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}}};
+        std::vector<Entity*> list{&ent};
+        Intersector.PushEntities(list);
+        Intersector.BufferEntities();
+        std::vector<Candela::Ray> rays;
+        for (int i = 0; i < 100; ++i) {
+            Candela::Ray r{{0.5f + 0.11f * i, 3.0f, 0.5f + 0.07f * i}, 0.0f, {0.0f, -1.0f, 0.0f}, 0.0f};
+            rays.push_back(r);
+        }
+        std::vector<Candela::RayHit> hits(rays.size());
+        Intersector.IntersectRays(rays.data(), rays.size(), hits.data());
+        int n_hit = 0;
+        double sum = 0;
+        for (auto& h : hits)
+            if (h.T > 0) { ++n_hit; sum += h.T; if (h.Mesh != 5) { std::printf("BAD mesh %d\n", h.Mesh); return 1; } }
+        Intersector.FetchCPUData();
+        std::printf("OK %d %.3f nodes=%zu tris=%zu\n", n_hit, sum, Intersector.m_BVHNodes.size(), Intersector.m_BVHTriangles.size());
+        // pushing an entity of an unknown object must throw the reference's message
+        Object other;
+        other.m_ObjectID = 77;
+        Entity bad{&other, {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}}};
+        try {
+            Intersector.PushEntity(bad);
+            std::printf("BAD no throw\n");
+            return 1;
+        } catch (const char* e) {
+            std::printf("THROW %s\n", e);
+        }
+    } catch (const char* e) {
+        std::printf("ERROR %s\n", e);
+        return 1;
+    }
+    return 0;
+}
