@@ -315,7 +315,7 @@ def run_ours(args):
         kernel_ms = statistics.mean(step_ms)  # one traversal launch per step on this rank
         achieved = b_ray * R / (kernel_ms * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                            "traffic": recorded_traffic(), "peak_source": peak_src, "kernel": "trace_persistent_stackless_kernel" if args.mode else "trace_simple_kernel",
+                            "traffic": recorded_traffic(), "peak_source": peak_src, "kernel": {0: "trace_simple_kernel", 1: "trace_persistent_stackless_kernel", 2: "trace_ww_stackless_kernel"}[args.mode],
                             "bytes_per_ray": round(b_ray, 1), "node_iters_per_ray": round(nn, 3), "tri_tests_per_ray": round(nt, 3),
                             "ray_io_bytes_per_ray_not_included": 64, "kernel_ms": round(kernel_ms, 4)}
         if world == 1:
@@ -347,7 +347,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", type=int, default=1, help="traversal kernel: 0 one thread per ray, 1 persistent warps")
+    ap.add_argument("--mode", type=int, default=2, help="traversal kernel: 0 one thread per ray, 1 persistent warps, 2 persistent while-while")
     ap.add_argument("--sort", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -29,6 +29,7 @@ constexpr int kBins = 64;                      // :46
 constexpr unsigned kMaxLeaf = 2;               // :50
 constexpr float kInfCost = 1e29f;              // :56
 constexpr unsigned kBigNode = 2048;            // ranges longer than this get a 1024-thread block
+constexpr unsigned kTinyNode = 64;             // ranges up to this get one warp
 
 // glm 0.9.8.5 min/max (func_common.inl:15-28); argument order matters for +0/-0 ties
 __device__ __forceinline__ float gmin(float x, float y) { return x < y ? x : y; }
@@ -164,6 +165,72 @@ __device__ __forceinline__ float centroid_of(const BuildArrays& a, int r, int ax
     return axis == 0 ? a.tmin[r].w : (axis == 1 ? a.tmax[r].w : a.tcz[r]);
 }
 
+
+// Split search over the 64 bins of one axis (:319-358), evaluated by one warp.  Bin boxes and counts
+// combine with min/max/+, so prefix (from the left) and suffix (from the right) scans give exactly the
+// values the reference accumulates sequentially (the sign of a zero aside, which areas cannot see);
+// the costs use the reference's expression; strict `<` over ascending splits == first minimum.
+struct BinAgg { int n; float mn[3], mx[3]; };
+__device__ __forceinline__ BinAgg agg_identity() { return {0, {kSentinelMax, kSentinelMax, kSentinelMax}, {kSentinelMin, kSentinelMin, kSentinelMin}}; }
+__device__ __forceinline__ BinAgg agg_join(const BinAgg& a, const BinAgg& b) {
+    BinAgg r;
+    r.n = a.n + b.n;
+    for (int c = 0; c < 3; ++c) { r.mn[c] = fminf(a.mn[c], b.mn[c]); r.mx[c] = fmaxf(a.mx[c], b.mx[c]); }
+    return r;
+}
+__device__ __forceinline__ BinAgg agg_shfl(const BinAgg& a, int src_lane) {
+    BinAgg r;
+    r.n = __shfl_sync(0xFFFFFFFFu, a.n, src_lane);
+    for (int c = 0; c < 3; ++c) { r.mn[c] = __shfl_sync(0xFFFFFFFFu, a.mn[c], src_lane); r.mx[c] = __shfl_sync(0xFFFFFFFFu, a.mx[c], src_lane); }
+    return r;
+}
+__device__ __forceinline__ float agg_cost(const BinAgg& l, const BinAgg& r) {
+    const float la = box_area(l.mn[0], l.mn[1], l.mn[2], l.mx[0], l.mx[1], l.mx[2]);
+    const float ra = box_area(r.mn[0], r.mn[1], r.mn[2], r.mx[0], r.mx[1], r.mx[2]);
+    return fadd(fmul(__int2float_rn(l.n), la), fmul(__int2float_rn(r.n), ra));  // :351
+}
+
+__device__ __forceinline__ void warp_sah_eval(const int* s_count, const int (*s_mn)[kBins], const int (*s_mx)[kBins], int axis, float lo,
+                                              float extent, float* s_best_cost, int* s_axis, float* s_border) {
+    const int lane = threadIdx.x & 31;
+    BinAgg b0, b1;
+    b0.n = s_count[2 * lane];
+    b1.n = s_count[2 * lane + 1];
+    for (int c = 0; c < 3; ++c) {
+        b0.mn[c] = key2f(s_mn[c][2 * lane]); b0.mx[c] = key2f(s_mx[c][2 * lane]);
+        b1.mn[c] = key2f(s_mn[c][2 * lane + 1]); b1.mx[c] = key2f(s_mx[c][2 * lane + 1]);
+    }
+    const BinAgg pair = agg_join(b0, b1);
+    BinAgg incl = pair, incr = pair;  // inclusive scans from the left / from the right
+    for (int o = 1; o < 32; o <<= 1) {
+        const BinAgg up = agg_shfl(incl, lane - o < 0 ? lane : lane - o);
+        if (lane >= o) incl = agg_join(up, incl);
+        const BinAgg dn = agg_shfl(incr, lane + o > 31 ? lane : lane + o);
+        if (lane + o <= 31) incr = agg_join(incr, dn);
+    }
+    BinAgg excl = agg_shfl(incl, lane == 0 ? 0 : lane - 1);
+    if (lane == 0) excl = agg_identity();
+    BinAgg excr = agg_shfl(incr, lane == 31 ? 31 : lane + 1);  // bins 2(lane+1) .. 63
+    if (lane == 31) excr = agg_identity();
+    // split i = 2*lane: left = bins 0..2lane, right = bins 2lane+1..63; split i = 2*lane+1: left = 0..2lane+1, right = 2lane+2..63
+    const float c0 = agg_cost(agg_join(excl, b0), agg_join(b1, excr));
+    float c1 = agg_cost(incl, excr);
+    float cost = c0;
+    int idx = 2 * lane;
+    if (lane < 31 && c1 < cost) { cost = c1; idx = 2 * lane + 1; }  // i = 63 is not a split
+    if (!(cost == cost)) cost = __int_as_float(0x7F800000);        // a NaN cost is never selected by `<`
+    for (int o = 16; o > 0; o >>= 1) {
+        const float pc = __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+        const int pi = __shfl_xor_sync(0xFFFFFFFFu, idx, o);
+        if (pc < cost || (pc == cost && pi < idx)) { cost = pc; idx = pi; }
+    }
+    if (lane == 0 && cost < *s_best_cost) {
+        *s_best_cost = cost;
+        *s_axis = axis;
+        *s_border = fadd(lo, fmul(fdiv(extent, (float)kBins), __int2float_rn(idx + 1)));  // :347,:356
+    }
+}
+
 struct LevelArgs {
     BuildArrays a;
     const int* active;     // node ids to split at this level, in level order
@@ -180,8 +247,9 @@ struct LevelArgs {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g) {
     const BuildArrays& a = g.a;
-    __shared__ int s_count[kBins];
-    __shared__ int s_mn[3][kBins], s_mx[3][kBins];
+    __shared__ int s_count[3][kBins];
+    __shared__ int s_mn[3][3][kBins], s_mx[3][3][kBins];  // [axis][component][bin]
+    constexpr bool AGG = BLOCK >= 128;
     __shared__ int s_warp[BLOCK / 32 + 1];
     __shared__ float s_best_cost, s_border;
     __shared__ int s_axis;
@@ -198,61 +266,63 @@ __global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g) {
     const float nmn[3] = {bmn.x, bmn.y, bmn.z}, nmx[3] = {bmx.x, bmx.y, bmx.z};
     const int tid = threadIdx.x;
 
-    // ---- SearchSAHPlaneBinned (:276-363) ----
+    // ---- SearchSAHPlaneBinned (:276-363): one pass over the range bins all three axes ----
     if (tid == 0) { s_best_cost = kInfCost; s_axis = 0; s_border = nmn[0]; }
-    for (int axis = 0; axis < 3; ++axis) {
-        const float lo = nmn[axis], hi = nmx[axis];
-        if (lo == hi) continue;  // :285 (uniform for the block)
-        for (int b = tid; b < kBins; b += BLOCK) {
-            s_count[b] = 0;
-            for (int c = 0; c < 3; ++c) { s_mn[c][b] = f2key(kSentinelMax); s_mx[c][b] = f2key(kSentinelMin); }
-        }
-        __syncthreads();
-        const float extent = fsub(hi, lo);
-        const float scale = fdiv((float)kBins, extent);  // :295
-        for (unsigned i = tid; i < len; i += BLOCK) {
+    for (int b = tid; b < 3 * kBins; b += BLOCK) (&s_count[0][0])[b] = 0;
+    for (int b = tid; b < 9 * kBins; b += BLOCK) { (&s_mn[0][0][0])[b] = f2key(kSentinelMax); (&s_mx[0][0][0])[b] = f2key(kSentinelMin); }
+    __syncthreads();
+    float scale[3], extent[3];
+    bool axis_on[3];
+    for (int ax = 0; ax < 3; ++ax) {
+        axis_on[ax] = !(nmn[ax] == nmx[ax]);                 // :285
+        extent[ax] = fsub(nmx[ax], nmn[ax]);
+        scale[ax] = fdiv((float)kBins, extent[ax]);          // :295
+    }
+    for (unsigned base = 0; base < len; base += BLOCK) {
+        const unsigned i = base + tid;
+        const bool valid = i < len;
+        const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (valid) {
             const int r = a.refs[start + i];
             const float4 tm = a.tmin[r], tx = a.tmax[r];
-            const float c = axis == 0 ? tm.w : (axis == 1 ? tx.w : a.tcz[r]);
-            int b = __float2int_rz(fmul(fsub(c, lo), scale));  // :302
-            b = b > kBins - 1 ? kBins - 1 : (b < 0 ? 0 : b);
-            atomicAdd(&s_count[b], 1);
+            const float cz = a.tcz[r];
             // the sign of a zero in a bin box never reaches a decision (only areas use bin boxes)
-            atomicMin(&s_mn[0][b], f2key(tm.x)); atomicMin(&s_mn[1][b], f2key(tm.y)); atomicMin(&s_mn[2][b], f2key(tm.z));
-            atomicMax(&s_mx[0][b], f2key(tx.x)); atomicMax(&s_mx[1][b], f2key(tx.y)); atomicMax(&s_mx[2][b], f2key(tx.z));
-        }
-        __syncthreads();
-        if (tid == 0) {
-            // prefix from the left, suffix from the right, then costs (:319-358), on one thread in the
-            // reference's order.  Right-side values are produced first so the cost loop runs ascending.
-            float r_area[kBins - 1];
-            int r_count[kBins - 1];
-            float rmn[3] = {kSentinelMax, kSentinelMax, kSentinelMax}, rmx[3] = {kSentinelMin, kSentinelMin, kSentinelMin};
-            int rsum = 0;
-            for (int j = kBins - 1; j >= 1; --j) {
-                rsum += s_count[j];
-                r_count[j - 1] = rsum;
-                for (int c = 0; c < 3; ++c) { rmn[c] = gmin(rmn[c], key2f(s_mn[c][j])); rmx[c] = gmax(rmx[c], key2f(s_mx[c][j])); }
-                r_area[j - 1] = box_area(rmn[0], rmn[1], rmn[2], rmx[0], rmx[1], rmx[2]);
-            }
-            float lmn[3] = {kSentinelMax, kSentinelMax, kSentinelMax}, lmx[3] = {kSentinelMin, kSentinelMin, kSentinelMin};
-            int lsum = 0;
-            const float step = fdiv(extent, (float)kBins);  // :347
-            float best = s_best_cost;
-            for (int i = 0; i < kBins - 1; ++i) {
-                lsum += s_count[i];
-                for (int c = 0; c < 3; ++c) { lmn[c] = gmin(lmn[c], key2f(s_mn[c][i])); lmx[c] = gmax(lmx[c], key2f(s_mx[c][i])); }
-                const float l_area = box_area(lmn[0], lmn[1], lmn[2], lmx[0], lmx[1], lmx[2]);
-                const float cost = fadd(fmul(__int2float_rn(lsum), l_area), fmul(__int2float_rn(r_count[i]), r_area[i]));  // :351
-                if (cost < best) {
-                    best = cost;
-                    s_axis = axis;
-                    s_border = fadd(lo, fmul(step, __int2float_rn(i + 1)));  // :356
+            const int kmn[3] = {f2key(tm.x), f2key(tm.y), f2key(tm.z)}, kmx[3] = {f2key(tx.x), f2key(tx.y), f2key(tx.z)};
+            const float cen[3] = {tm.w, tx.w, cz};
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                if (!axis_on[ax]) continue;  // uniform for the block
+                int b = __float2int_rz(fmul(fsub(cen[ax], nmn[ax]), scale[ax]));  // :302
+                b = b > kBins - 1 ? kBins - 1 : (b < 0 ? 0 : b);
+                // warp-level bin reduction: when every lane of the warp falls into the same bin (coherent input:
+                // grids, sorted meshes) the warp combines with REDUX and one lane updates shared memory; 32-way
+                // same-address atomics would serialise otherwise
+                bool uniform = false;
+                if (AGG) uniform = __all_sync(vmask, b == __shfl_sync(vmask, b, __ffs(vmask) - 1));
+                if (AGG && uniform) {
+                    int rmn[3], rmx[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { rmn[c] = __reduce_min_sync(vmask, kmn[c]); rmx[c] = __reduce_max_sync(vmask, kmx[c]); }
+                    if ((int)(threadIdx.x & 31) == __ffs(vmask) - 1) {
+                        atomicAdd(&s_count[ax][b], __popc(vmask));
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { atomicMin(&s_mn[ax][c][b], rmn[c]); atomicMax(&s_mx[ax][c][b], rmx[c]); }
+                    }
+                } else {
+                    atomicAdd(&s_count[ax][b], 1);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { atomicMin(&s_mn[ax][c][b], kmn[c]); atomicMax(&s_mx[ax][c][b], kmx[c]); }
                 }
             }
-            s_best_cost = best;
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    if (tid < 32) {
+        for (int ax = 0; ax < 3; ++ax) {
+            if (!axis_on[ax]) continue;
+            warp_sah_eval(s_count[ax], s_mn[ax], s_mx[ax], ax, nmn[ax], extent[ax], &s_best_cost, &s_axis, &s_border);
+            __syncwarp();
+        }
     }
     __syncthreads();
     const int axis = s_axis;
@@ -263,11 +333,20 @@ __global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g) {
     // at that moment moves to the L element's old place.  "At that moment" is resolved by following
     // the chain of earlier swaps inside the chunk (builder). ----
     unsigned mid = start;
+    // the next chunk's references and centroids are fetched while the current chunk is processed: positions
+    // past the current chunk are never written before they are visited
+    int r_next = (unsigned)tid < len ? a.refs[start + tid] : -1;
+    float c_next = r_next >= 0 ? centroid_of(a, r_next, axis) : 0.0f;
     for (unsigned i0 = start; i0 < start + len; i0 += BLOCK) {
         const unsigned n = min((unsigned)BLOCK, start + len - i0);
         const bool valid = (unsigned)tid < n;
-        const int r = valid ? a.refs[i0 + tid] : -1;
-        const bool f = valid && centroid_of(a, r, axis) < border;
+        const int r = r_next;
+        const bool f = valid && c_next < border;
+        {
+            const unsigned nxt = i0 + BLOCK + tid;
+            r_next = nxt < start + len ? a.refs[nxt] : -1;
+            c_next = r_next >= 0 ? centroid_of(a, r_next, axis) : 0.0f;
+        }
         int nL;
         const int rank = block_exclusive_scan<BLOCK>(f ? 1 : 0, s_warp, nL);
         s_elem[tid] = r;
@@ -423,24 +502,27 @@ void exclusive_scan(const int* d_in, int n, int* d_out, int* d_block_sums, int* 
     lc.n += 3;
 }
 
-// flags for the nodes of one level: [0,n) big-inner, [n,2n) small-inner
+// flags for the nodes of one level, one run of n per size class: [0,n) big, [n,2n) small, [2n,3n) tiny
 __global__ void classify_kernel(const unsigned* nlen, int base, int n, int* flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned len = nlen[base + i];
     flags[i] = len > kBigNode ? 1 : 0;
-    flags[n + i] = (len > kMaxLeaf && len <= kBigNode) ? 1 : 0;
+    flags[n + i] = (len > kTinyNode && len <= kBigNode) ? 1 : 0;
+    flags[2 * n + i] = (len > kMaxLeaf && len <= kTinyNode) ? 1 : 0;
 }
 
 // offsets = exclusive scan of flags.  Writes the ordered active list and, per size class, the list of
 // positions in it.
-__global__ void compact_kernel(const int* flags, const int* offsets, int base, int n, int* active, int* klist_big, int* klist_small) {
+__global__ void compact_kernel(const int* flags, const int* offsets, int base, int n, int* active, int* klist_big, int* klist_small,
+                               int* klist_tiny) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int off_big = offsets[i], off_small = offsets[n + i] - offsets[n];
-    const int k = off_big + off_small;
+    const int off_big = offsets[i], off_small = offsets[n + i] - offsets[n], off_tiny = offsets[2 * n + i] - offsets[2 * n];
+    const int k = off_big + off_small + off_tiny;
     if (flags[i]) { active[k] = base + i; klist_big[off_big] = k; }
     if (flags[n + i]) { active[k] = base + i; klist_small[off_small] = k; }
+    if (flags[2 * n + i]) { active[k] = base + i; klist_tiny[off_tiny] = k; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -561,7 +643,7 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     uint32_t* d_idx = nullptr;
     int32_t* d_mesh = nullptr;
     unsigned char* d_flip = nullptr;
-    int *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr;
+    int *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr, *d_kl_tiny = nullptr;
     BK(sc.alloc(&d_idx, 3 * T));
     if (rq.h_mesh_ids) BK(sc.alloc(&d_mesh, T));
     BK(sc.alloc(&a.tmin, T)); BK(sc.alloc(&a.tmax, T)); BK(sc.alloc(&a.tcz, T)); BK(sc.alloc(&a.refs, T));
@@ -569,10 +651,10 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     BK(sc.alloc(&a.nchild, n_max)); BK(sc.alloc(&a.nsize, n_max)); BK(sc.alloc(&a.npre, n_max)); BK(sc.alloc(&a.nlink, n_max));
     BK(sc.alloc(&d_flip, n_max));
     BK(sc.alloc(&a.root_scratch, 16));
-    const size_t scan_n = std::max<size_t>(2 * n_max, 16);
+    const size_t scan_n = std::max<size_t>(3 * n_max, 16);
     BK(sc.alloc(&d_flags, scan_n)); BK(sc.alloc(&d_offsets, scan_n));
     BK(sc.alloc(&d_block_sums, scan_n / kScanTile + 2)); BK(sc.alloc(&d_totals, 4));
-    BK(sc.alloc(&d_active, n_max)); BK(sc.alloc(&d_active_next, n_max)); BK(sc.alloc(&d_kl_big, n_max)); BK(sc.alloc(&d_kl_small, n_max));
+    BK(sc.alloc(&d_active, n_max)); BK(sc.alloc(&d_active_next, n_max)); BK(sc.alloc(&d_kl_big, n_max)); BK(sc.alloc(&d_kl_small, n_max)); BK(sc.alloc(&d_kl_tiny, n_max));
 
     cudaEvent_t ev0, ev1;
     BK(cudaEventCreate(&ev0));
@@ -604,12 +686,13 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
         lc.n++;
     } else {
         // level 0: the root is the only active node
-        int n_big = T > kBigNode ? 1 : 0, n_small = 1 - n_big;
+        int n_big = T > kBigNode ? 1 : 0, n_tiny = T <= kTinyNode ? 1 : 0, n_small = 1 - n_big - n_tiny;
         BK(cudaMemsetAsync(d_active, 0, sizeof(int), st));
         BK(cudaMemsetAsync(d_kl_big, 0, sizeof(int), st));
         BK(cudaMemsetAsync(d_kl_small, 0, sizeof(int), st));
-        while (n_big + n_small > 0) {
-            const int n_active = n_big + n_small;
+        BK(cudaMemsetAsync(d_kl_tiny, 0, sizeof(int), st));
+        while (n_big + n_small + n_tiny > 0) {
+            const int n_active = n_big + n_small + n_tiny;
             LevelArgs g;
             g.a = a;
             g.active = d_active;
@@ -621,6 +704,7 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
             g.nflip = d_flip;
             if (n_big) { g.klist = d_kl_big; level_step_kernel<1024><<<n_big, 1024, 0, st>>>(g); lc.n++; }
             if (n_small) { g.klist = d_kl_small; level_step_kernel<128><<<n_small, 128, 0, st>>>(g); lc.n++; }
+            if (n_tiny) { g.klist = d_kl_tiny; level_step_kernel<32><<<n_tiny, 32, 0, st>>>(g); lc.n++; }
             BK(cudaGetLastError());
             const int base = (int)n_nodes, n = 2 * n_active;
             level_base.push_back(base);
@@ -629,15 +713,17 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
             // next level's active list
             classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.nlen, base, n, d_flags);
             lc.n++;
-            exclusive_scan(d_flags, 2 * n, d_offsets, d_block_sums, d_totals, st, lc);
-            compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_flags, d_offsets, base, n, d_active_next, d_kl_big, d_kl_small);
+            exclusive_scan(d_flags, 3 * n, d_offsets, d_block_sums, d_totals, st, lc);
+            compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_flags, d_offsets, base, n, d_active_next, d_kl_big, d_kl_small, d_kl_tiny);
             lc.n++;
-            int h_tot[2];
+            int h_tot[3];
             BK(cudaMemcpyAsync(&h_tot[0], d_totals, sizeof(int), cudaMemcpyDeviceToHost, st));
             BK(cudaMemcpyAsync(&h_tot[1], d_offsets + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+            BK(cudaMemcpyAsync(&h_tot[2], d_offsets + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, st));
             BK(cudaStreamSynchronize(st));
             n_big = h_tot[1];
-            n_small = h_tot[0] - h_tot[1];
+            n_small = h_tot[2] - h_tot[1];
+            n_tiny = h_tot[0] - h_tot[2];
             std::swap(d_active, d_active_next);
         }
         // flatten
