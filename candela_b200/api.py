@@ -32,7 +32,7 @@ EXPORTS = [
     "cndl_node_count", "cndl_triangle_count", "cndl_vertex_count", "cndl_get_object", "cndl_commit", "cndl_read_buffers",
     "cndl_device_buffers", "cndl_push_entity", "cndl_push_entity_records", "cndl_buffer_entities", "cndl_entity_count",
     "cndl_intersect_closest", "cndl_intersect_any", "cndl_intersect_closest_device", "cndl_intersect_any_device",
-    "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_host_alloc", "cndl_host_free",
+    "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_generate_bounce_rays_device", "cndl_host_alloc", "cndl_host_free",
     "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms",
 ]
 
@@ -88,6 +88,7 @@ def load_library() -> C.CDLL:
     L.cndl_intersect_any_device.argtypes = [vp, vp, sz, vp, vp]
     L.cndl_intersect_primary.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
     L.cndl_intersect_primary_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+    L.cndl_generate_bounce_rays_device.argtypes = [vp, vp, vp, sz, C.c_int, C.c_float, C.c_float, C.c_uint32, vp, vp, C.POINTER(sz), vp]
     L.cndl_host_alloc.argtypes = [sz]
     L.cndl_host_alloc.restype = vp
     L.cndl_host_free.argtypes = [vp]
@@ -303,6 +304,14 @@ class RayIntersector:
 
     def intersect_any_device(self, d_rays: int, n_rays: int, d_t: int, stream: int = 0):
         self._check(self._lib.cndl_intersect_any_device(self._h, d_rays, n_rays, d_t, stream or None))
+
+    def generate_bounce_rays_device(self, d_rays: int, d_hits: int, n_rays: int, d_rays_out: int, spp: int = 1, offset: float = 0.05,
+                                    tmax: float = 1.0e6, seed: int = 1, d_parent_out: int = 0, stream: int = 0) -> int:
+        """Wavefront compaction between bounces; returns the number of rays written."""
+        n = C.c_size_t(0)
+        self._check(self._lib.cndl_generate_bounce_rays_device(self._h, d_rays, d_hits, n_rays, spp, offset, tmax, seed, d_rays_out,
+                                                               d_parent_out or None, C.byref(n), stream or None))
+        return int(n.value)
 
     def intersect_primary_device(self, inv_view, inv_proj, Width: int, Height: int, d_hits: int, d_rays: int = 0, stream: int = 0):
         iv, ip = _colmajor(inv_view), _colmajor(inv_proj)

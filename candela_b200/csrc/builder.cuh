@@ -19,6 +19,8 @@ struct BuildRequest {
     void* d_nodes_out;           // device, room for 2T-1 nodes of the context's format
     int4* d_tris_out;            // device, T records, vertex indices object-local
     size_t n_nodes_out;          // result: LastNodeIndex + 1
+    void** arena;                // scratch allocation kept by the context between builds
+    size_t* arena_cap;
 };
 
 // Returns CNDL_OK or a negative cndl_status with `err` set. Work is enqueued on `st` and complete on return.

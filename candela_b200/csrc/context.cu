@@ -75,6 +75,8 @@ struct cndl_ctx {
     int knobs[8] = {8, 8, 8, 2, 0, 0, 0, 0};  // CNDL_KNOB_*
     LaunchCounter launches;
     float last_build_ms = 0.0f;
+    void* build_arena = nullptr;
+    size_t build_arena_cap = 0;
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -190,6 +192,7 @@ void cndl_destroy(cndl_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& s : ctx->streams) if (s) cudaStreamDestroy(s);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    if (ctx->build_arena) cudaFree(ctx->build_arena);
     delete ctx;
 }
 
@@ -286,6 +289,8 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     rq.d_nodes_out = dn;
     rq.d_tris_out = reinterpret_cast<int4*>(dt);
     rq.n_nodes_out = 0;
+    rq.arena = &ctx->build_arena;
+    rq.arena_cap = &ctx->build_arena_cap;
     std::string berr;
     float ms = 0.0f;
     const int rc = build_object(rq, st, ctx->launches, &ms, berr);
@@ -494,6 +499,21 @@ int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float 
     CK(cudaMemcpyAsync(hits, ctx->d_hits.p, R * sizeof(cndl_hit), cudaMemcpyDeviceToHost, st));
     if (rays_out) CK(cudaMemcpyAsync(rays_out, ctx->d_rays.p, R * sizeof(cndl_ray), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return CNDL_OK;
+}
+
+int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R, int spp, float offset,
+                                     float tmax, uint32_t seed, cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!count_out || spp < 1 || (R && (!d_rays || !d_hits || !d_rays_out))) return ctx->fail(CNDL_ERR_INVALID, "bad bounce-ray arguments");
+    if (R * (size_t)spp > 0x7FFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "too many rays in one call");
+    int rc = check_ready(ctx);
+    if (rc != CNDL_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_sort_tmp.ensure_scratch((2 * R + R / 2048 + 16) * sizeof(int)));
+    const SceneView s = scene_view(ctx);
+    CK(generate_bounce_rays(s, d_rays, d_hits, R, spp, offset, tmax, seed, d_rays_out, d_parent_out, static_cast<int*>(ctx->d_sort_tmp.p),
+                            count_out, static_cast<cudaStream_t>(stream), ctx->launches));
     return CNDL_OK;
 }
 

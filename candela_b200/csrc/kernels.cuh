@@ -33,4 +33,9 @@ void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t 
 void launch_primary_rays(const float* inv_view16, const float* inv_proj16, int W, int H, cndl_ray* rays, cudaStream_t stream,
                          LaunchCounter& lc);
 
+// Wavefront compaction between bounces: diffuse rays from the hits of the previous batch (kernels_raygen.cu).
+cudaError_t generate_bounce_rays(const SceneView& s, const cndl_ray* rays, const cndl_hit* hits, size_t R, int spp, float offset, float tmax,
+                                 unsigned seed, cndl_ray* out, unsigned* parent, int* scratch, size_t* h_count, cudaStream_t stream,
+                                 LaunchCounter& lc);
+
 }  // namespace cndl

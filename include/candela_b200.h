@@ -155,6 +155,15 @@ int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float 
 int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H,
                                   cndl_hit* d_hits, cndl_ray* d_rays_out, void* stream);
 
+/* Wavefront step between bounces (DiffuseTrace.glsl:445-446,:516-517): for every ray whose hit record has
+ * t > 0, writes `spp` diffuse rays {origin = P + N*offset, direction = CosWeightedHemisphere(N, xi), tmax}
+ * to d_rays_out, compacted in input order (rays that missed emit nothing); N is the geometric normal turned
+ * against the incoming ray, xi a counter-based hash of (seed, ray, sample).  d_parent_out (optional) receives
+ * the index of the parent ray.  d_rays_out must hold R*spp rays.  *count_out = rays written; synchronises
+ * `stream`. */
+int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R, int spp, float offset,
+                                     float tmax, uint32_t seed, cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream);
+
 /* Pinned host memory for ray / hit batches. */
 void* cndl_host_alloc(size_t bytes);
 void cndl_host_free(void* p);

@@ -119,3 +119,77 @@ def test_bad_geometry_rejected(cb):
     with pytest.raises(cb.CandelaError):
         ri.AddObject(2, V, np.array([0, 1, 3], np.uint32))
     ri.close()
+
+
+# ---- LBVH builder (CNDL_BUILDER_LBVH): same layouts, different tree -> parity level P2 ----------------------
+def _lbvh_scene(cb, ob, fmt, V, F, mids):
+    ri = cb.RayIntersector(fmt)
+    ri.AddObject(2, V, F, mids, builder=cb.BUILDER_LBVH)
+    ri.BufferData()
+    ri.PushEntity(2)
+    ri.BufferEntities()
+    return ri
+
+
+@pytest.mark.parametrize("name", ["dragon", "peach_castle", "soup400", "duplicates", "coplanar_grid", "collinear"])
+def test_lbvh_structure_and_traversal(cb, ob, golden_meshes, name):
+    from helpers import rays_in_box
+    from test_oracle_builder import check_stackless_invariants
+    P, F = golden_meshes[name]
+    V = ob.make_vertices(P)
+    mids = (np.arange(len(F)) % 3).astype(np.int32)
+    rays = rays_in_box(P.min(0) - 0.5, P.max(0) + 0.5, 20000, 12)
+    sah = ob.Scene(ob.STACKLESS)
+    sah.add_object(2, V, F.ravel(), mids)
+    sah.push_entity(2)
+    want, _ = sah.trace(ob.CLOSEST, rays, nthreads=8)
+    for fmt in (ob.STACKLESS, ob.STACK):
+        ri = _lbvh_scene(cb, ob, fmt, V, F.ravel(), mids)
+        nodes, tris, verts = ri.read_buffers()
+        # the triangle buffer is a permutation of the input with mesh ids attached
+        got_set = sorted(map(tuple, np.concatenate([tris["v"], tris["mesh"][:, None]], 1).tolist()))
+        ref_set = sorted(map(tuple, np.concatenate([F.astype(np.int32), mids[:, None]], 1).tolist()))
+        assert got_set == ref_set
+        if fmt == ob.STACKLESS:
+            check_stackless_invariants(nodes, tris, len(F))
+        # P1 on the GPU-built buffers: GPU traversal == oracle traversal over the very same buffers
+        ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(nodes))
+        same_buf, _ = ob.trace(fmt, ob.CLOSEST, nodes, tris, V, ents, rays, nthreads=8)
+        got = ri.IntersectRays(rays)
+        assert got.tobytes() == same_buf.tobytes()
+        # P2 against the reference tree: same hit triangle (identity, not buffer index), same t
+        hit_w, hit_g = want["tri"] >= 0, got["tri"] >= 0
+        assert (hit_w == hit_g).mean() > 0.9995
+        both = hit_w & hit_g
+        ident_w = np.concatenate([sah.tris["v"][want["tri"][both]], sah.tris["mesh"][want["tri"][both], None]], 1)
+        ident_g = np.concatenate([tris["v"][got["tri"][both]], tris["mesh"][got["tri"][both], None]], 1)
+        same = np.all(ident_w == ident_g, axis=1)
+        if not both.any():                               # degenerate geometry: nothing can be hit
+            pass
+        elif name in ("duplicates", "coplanar_grid"):    # coincident triangles: any of the duplicates may win
+            assert np.array_equal(got["t"][both], want["t"][both]) or same.mean() > 0.9
+        else:
+            assert same.mean() > 0.999, same.mean()
+            sel = np.nonzero(both)[0][same]
+            ok = (got["tri"][sel] > 0) & (want["tri"][sel] > 0)    # the triangle-0 blind spot differs between trees
+            assert np.array_equal(got["t"][sel][ok], want["t"][sel][ok])
+        ri.close()
+
+
+def test_lbvh_tiny_and_build_time(cb, ob):
+    from candela_b200 import scenes
+    for T in (1, 2, 3, 5, 8):
+        rng = np.random.default_rng(T)
+        P = rng.uniform(-1, 1, size=(3 * T, 3)).astype(np.float32)
+        F = np.arange(3 * T, dtype=np.uint32)
+        for fmt in (ob.STACKLESS, ob.STACK):
+            ri = cb.RayIntersector(fmt)
+            ri.AddObject(2, ob.make_vertices(P), F, builder=cb.BUILDER_LBVH)
+            nodes, tris, _ = ri.read_buffers()
+            assert len(tris) == T and len(nodes) == 2 * ((T + 1) // 2) - 1
+            ri.close()
+    v, i, m = scenes.make_s260k()
+    ri = cb.RayIntersector(ob.STACKLESS)
+    ri.AddObject(2, v, i, m, builder=cb.BUILDER_LBVH)
+    assert 0 < ri.last_build_ms < 50
+    ri.close()

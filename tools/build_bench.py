@@ -25,7 +25,7 @@ for name, (v, i, m) in (("s260k", scenes.make_s260k()),) + ((("heightfield%d" % 
             if _ + 1 < args.reps:
                 ri.close()
         line = f"{name} fmt={fmt} T={len(i)//3} nodes={ri.node_count} gpu_build_ms min={min(ms):.3f} med={sorted(ms)[len(ms)//2]:.3f} wall_ms_last={wall:.1f} launches={ri.launch_count}"
-        if args.check:
+        if args.check and args.builder == 0:
             from oracle import binding as ob
             t0 = time.perf_counter()
             ref = ob.build(fmt, v, i, m)

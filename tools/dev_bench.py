@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--modes", default="0,1,2")
     ap.add_argument("--knobs", default="", help="semicolon-separated bps,leaf,idle triples for mode 2")
     ap.add_argument("--fmt", default="stackless")
+    ap.add_argument("--gpu-builder", type=int, default=-1, help="-1: oracle-built buffers; 0: GPU SAH; 1: GPU LBVH")
     ap.add_argument("--presort", type=int, default=0, help="host-side Morton sort of the diffuse rays (experiment)")
     args = ap.parse_args()
     from oracle import binding as ob
@@ -37,7 +38,15 @@ def main():
     b = ob.build(fmt, v, i, m)
     print(f"oracle build {1e3 * (time.time() - t0):.0f} ms, nodes {len(b.nodes)}", flush=True)
     ri = cb.RayIntersector(fmt)
-    ri.AddPrebuiltObject(2, b.nodes, b.tris, v)
+    if args.gpu_builder >= 0:
+        ri.AddObject(2, v, i, m, builder=args.gpu_builder)
+        print(f"gpu build {ri.last_build_ms:.3f} ms")
+        class _B: pass
+        sah = b
+        b = _B()
+        b.nodes, b.tris, _ = ri.read_buffers()
+    else:
+        ri.AddPrebuiltObject(2, b.nodes, b.tris, v)
     ri.BufferData()
     ri.PushEntity(2)
     ri.BufferEntities()

@@ -1,0 +1,244 @@
+"""Runs the BASELINE.json configurations other than the bench.py headline (configs[2..4]) and prints one
+JSON line per configuration.  Single process or under torchrun (one rank per GPU).
+
+  rtao      configs[2]: any-hit, tmax 2.4, 4 spp at 1920x1080, stackless                      (1 GPU)
+  bounce4k  configs[3]: 3840x2160, 8 spp, multi-bounce closest-hit, screen tiles dealt to the ranks
+  soup10m   configs[4]: ~10M-triangle synthetic scene: GPU build + 100M random rays split over ranks
+
+Every configuration checks a sample (or all) of its results bit-for-bit against the CPU oracle.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import candela_b200 as cb  # noqa: E402
+from candela_b200 import api, scenes, sharding  # noqa: E402
+
+PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+
+
+def dev_rays(rays: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(rays).view(np.float32).reshape(-1, 8)).cuda()
+
+
+def timed(fn, reps=3, flush=None):
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def setup_s260k(local_rank, fmt=cb.STACKLESS):
+    v, i, m = scenes.make_s260k()
+    ri = cb.RayIntersector(fmt, device=local_rank)
+    ri.AddObject(2, v, i, m)
+    ri.BufferData(True)
+    ri.PushEntity(2)
+    ri.BufferEntities()
+    return ri, v, i, m
+
+
+def oracle_scene(ri, verts):
+    from oracle import binding as ob
+    nodes, tris, _ = ri.read_buffers()
+    ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(nodes))
+    return ob, nodes, tris, ents
+
+
+def cfg_rtao(args, rank, world, local_rank):
+    if rank != 0:
+        return None
+    W, H, spp = 1920, 1080, 4
+    ri, v, i, m = setup_s260k(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
+    d_prim = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+    d_hits = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+    ri.intersect_primary_device(iv, ip, W, H, d_hits.data_ptr(), d_prim.data_ptr(), stream)
+    d_ao = torch.empty((W * H * spp, 8), dtype=torch.float32, device="cuda")
+    n = ri.generate_bounce_rays_device(d_prim.data_ptr(), d_hits.data_ptr(), W * H, d_ao.data_ptr(), spp=spp, offset=0.05, tmax=2.4, seed=7, stream=stream)
+    d_t = torch.empty(n, dtype=torch.float32, device="cuda")
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: ri.intersect_any_device(d_ao.data_ptr(), n, d_t.data_ptr(), stream), reps=args.reps, flush=flush)
+    ob, nodes, tris, ents = oracle_scene(ri, v)
+    rays = d_ao[:n].cpu().numpy().view(api.RAY_DT).reshape(-1)
+    t0 = time.perf_counter()
+    want, cnt = ob.trace(ob.STACKLESS, ob.ANY, nodes, tris, v, ents, rays, nthreads=ob.hardware_threads())
+    cpu_s = time.perf_counter() - t0
+    got = d_t.cpu().numpy()
+    b_ray = (cnt["node_iters"] * 32.0 + cnt["tri_tests"] * 64.0) / n
+    return dict(config="rtao_anyhit_1080p_4spp_tmax2.4", rays=n, ms=round(ms, 4), mrays_s=round(n / ms / 1e3, 1), occluded_frac=round(float((got > 0).mean()), 4),
+                bit_identical_to_oracle=bool(got.tobytes() == want.tobytes()), bytes_per_ray=round(b_ray, 1),
+                roofline_frac=round(n / (ms * 1e-3) * b_ray / (PEAK * 1e9), 4), node_iters_per_ray=round(cnt["node_iters"] / n, 2),
+                cpu_mrays_s=round(n / cpu_s / 1e6, 2), cpu_threads=ob.hardware_threads())
+
+
+def cfg_bounce4k(args, rank, world, local_rank):
+    W, H, spp, bounces = args.width or 3840, args.height or 2160, 8, 4
+    ri, v, i, m = setup_s260k(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
+    # this rank's pixels: 64x64 tiles dealt round-robin
+    pix = torch.from_numpy(sharding.shard_pixels(W, H, world, rank, tile=64)).cuda()
+    d_prim_all = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+    d_hits_all = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+    ri.intersect_primary_device(iv, ip, W, H, d_hits_all.data_ptr(), d_prim_all.data_ptr(), stream)
+    d_prim, d_phits = d_prim_all[pix].contiguous(), d_hits_all[pix].contiguous()
+    del d_prim_all, d_hits_all
+    n_pix = len(pix)
+    cap = n_pix * spp
+    bufs = [torch.empty((cap, 8), dtype=torch.float32, device="cuda") for _ in range(2)]
+    d_hits = torch.empty((cap, 8), dtype=torch.float32, device="cuda")
+    per_bounce = []
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms, total_rays = 0.0, 0
+    src_rays, src_hits, n_src, s = d_prim, d_phits, n_pix, spp
+    checks = []
+    for b in range(bounces):
+        out = bufs[b % 2]
+        g0, g1, t1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        g0.record()
+        n = ri.generate_bounce_rays_device(src_rays.data_ptr(), src_hits.data_ptr(), n_src, out.data_ptr(), spp=s, offset=0.05 if b == 0 else 0.02,
+                                           tmax=1.0e6, seed=100 + b, stream=stream)
+        g1.record()
+        if n == 0:
+            break
+        ri.intersect_closest_device(out.data_ptr(), n, d_hits.data_ptr(), api.IGNORE_TRANSPARENT if b == 0 else 0, stream)
+        t1.record()
+        torch.cuda.synchronize()
+        gen_ms, trace_ms = g0.elapsed_time(g1), g1.elapsed_time(t1)
+        per_bounce.append(dict(bounce=b, rays=n, gen_ms=round(gen_ms, 3), trace_ms=round(trace_ms, 3), mrays_s=round(n / trace_ms / 1e3, 1)))
+        total_ms += trace_ms
+        total_rays += n
+        if rank == 0:  # 1/64 subsample against the oracle
+            idx = torch.arange(0, n, 64, device="cuda")
+            checks.append((b, out[idx].cpu().numpy().view(api.RAY_DT).reshape(-1), d_hits[idx].cpu().numpy().view(api.HIT_DT).reshape(-1)))
+        # next bounce from these hits
+        src_rays, src_hits, n_src, s = out, d_hits.clone(), n, 1
+    t_max, rays_all = sharding.reduce_timing(total_ms, float(total_rays), device="cuda")
+    # final frame: hit records of the last bounce are not per pixel any more; gather the primary hit records instead
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    frame = sharding.gather_frame(d_phits, pix, W * H)
+    g1.record()
+    torch.cuda.synchronize()
+    gather_ms = g0.elapsed_time(g1)
+    if rank != 0:
+        return None
+    ob, nodes, tris, ents = oracle_scene(ri, v)
+    ok = True
+    for b, r, h in checks:
+        want, _ = ob.trace(ob.STACKLESS, ob.CLOSEST_IGNORE_TRANSPARENT if b == 0 else ob.CLOSEST, nodes, tris, v, ents, r, nthreads=ob.hardware_threads())
+        ok = ok and want.tobytes() == h.tobytes()
+    return dict(config=f"multibounce_{W}x{H}_8spp_tiles", n_gpus=world, rays_all_ranks=int(rays_all), trace_ms_max_over_ranks=round(t_max, 3),
+                mrays_s=round(rays_all / t_max / 1e3, 1), per_bounce_rank0=per_bounce, sample_bit_identical_to_oracle=bool(ok),
+                final_frame_gather_ms=round(gather_ms, 3), frame_pixels=int(frame.shape[0]))
+
+
+def cfg_soup10m(args, rank, world, local_rank):
+    n_grid = args.grid or 2237
+    n_rays = args.rays or 100_000_000
+    v, i, m = scenes.make_heightfield(n_grid)
+    T = len(i) // 3
+    ri = cb.RayIntersector(cb.STACKLESS, device=local_rank)
+    t0 = time.perf_counter()
+    ri.AddObject(2, v, i, m, builder=args.builder)
+    wall_build = time.perf_counter() - t0
+    build_ms = ri.last_build_ms
+    ri.BufferData(True)
+    ri.PushEntity(2)
+    ri.BufferEntities()
+    lo, hi = shard_lo_hi = sharding.shard_range(n_rays, world, rank)
+    n = hi - lo
+    pos = v["position"][:, :3]
+    box_lo, box_hi = pos.min(0), pos.max(0) + np.array([0, 10, 0], np.float32)
+    stream = torch.cuda.current_stream().cuda_stream
+    chunk = 12_500_000
+    total_ms, done, sample = 0.0, 0, None
+    d_hits = torch.empty((min(chunk, n), 8), dtype=torch.float32, device="cuda")
+    while done < n:
+        c = min(chunk, n - done)
+        rays = scenes.random_rays(box_lo, box_hi, c, seed=1 + rank * 1000 + done // chunk)
+        d_r = dev_rays(rays)
+        ri.intersect_closest_device(d_r.data_ptr(), c, d_hits.data_ptr(), 0, stream)  # warm-up / page-in
+        torch.cuda.synchronize()
+        total_ms += timed(lambda: ri.intersect_closest_device(d_r.data_ptr(), c, d_hits.data_ptr(), 0, stream), reps=1)
+        if sample is None and rank == 0:
+            k = min(c, args.check_rays)
+            sample = (rays[:k].copy(), d_hits[:k].cpu().numpy().view(api.HIT_DT).reshape(-1).copy())
+        done += c
+    t_max, rays_all = sharding.reduce_timing(total_ms, float(n), device="cuda")
+    if rank != 0:
+        return None
+    out = dict(config=f"heightfield_{T}_tris_random_rays", n_gpus=world, triangles=T, nodes=ri.node_count, gpu_build_ms=round(build_ms, 2),
+               build_wall_ms=round(1e3 * wall_build, 1), builder="sah_exact" if args.builder == 0 else "lbvh", rays_all_ranks=int(rays_all),
+               trace_ms_max_over_ranks=round(t_max, 2), mrays_s=round(rays_all / t_max / 1e3, 1))
+    if args.check_rays:
+        from oracle import binding as ob
+        nodes, tris, _ = ri.read_buffers()
+        ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(nodes))
+        t0 = time.perf_counter()
+        want, cnt = ob.trace(ob.STACKLESS, ob.CLOSEST, nodes, tris, v, ents, sample[0], nthreads=ob.hardware_threads())
+        cpu_s = time.perf_counter() - t0
+        k = len(sample[0])
+        b_ray = (cnt["node_iters"] * 32.0 + cnt["tri_tests"] * 64.0) / k
+        out.update(sample_rays=k, sample_bit_identical_to_oracle=bool(want.tobytes() == sample[1].tobytes()), bytes_per_ray=round(b_ray, 1),
+                   roofline_frac_per_gpu=round(rays_all / world / (t_max * 1e-3) * b_ray / (PEAK * 1e9), 4), hit_frac=round(float((want["t"] > 0).mean()), 3),
+                   cpu_mrays_s=round(k / cpu_s / 1e6, 2), cpu_threads=ob.hardware_threads())
+        if args.check_build:
+            t0 = time.perf_counter()
+            ref = ob.build(ob.STACKLESS, v, i, m)
+            out.update(cpu_build_ms=round(1e3 * (time.perf_counter() - t0)), build_byte_identical=bool(ref.nodes.tobytes() == nodes.tobytes() and ref.tris.tobytes() == tris.tobytes()))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="+", choices=["rtao", "bounce4k", "soup10m"])
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--grid", type=int, default=0)
+    ap.add_argument("--rays", type=int, default=0)
+    ap.add_argument("--builder", type=int, default=0)
+    ap.add_argument("--check-rays", type=int, default=1_000_000)
+    ap.add_argument("--check-build", action="store_true")
+    args = ap.parse_args()
+    world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    for c in args.configs:
+        res = {"rtao": cfg_rtao, "bounce4k": cfg_bounce4k, "soup10m": cfg_soup10m}[c](args, rank, world, local_rank)
+        if rank == 0 and res is not None:
+            print(json.dumps(res), flush=True)
+        if world > 1:
+            dist.barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
