@@ -182,12 +182,13 @@ def run_ours(args):
     ri = cb.RayIntersector(cb.STACKLESS, device=local_rank)
     ri.set_traversal_mode(args.mode, bool(args.sort))
     build_ms = []
-    for rep in range(3):
+    for rep in range(args.build_reps):
         tmp = cb.RayIntersector(cb.STACKLESS, device=local_rank)
         tmp.AddObject(2, verts, indices, mesh_ids)
         build_ms.append(tmp.last_build_ms)
         tmp.close()
     ri.AddObject(2, verts, indices, mesh_ids)
+    build_ms.append(ri.last_build_ms)
     ri.BufferData(True)
     ri.PushEntity(2)
     ri.BufferEntities()
@@ -349,6 +350,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", type=int, default=2, help="traversal kernel: 0 one thread per ray, 1 persistent warps, 2 persistent while-while")
     ap.add_argument("--sort", type=int, default=0)
+    ap.add_argument("--build-reps", type=int, default=3, help="extra timed GPU builds (0 keeps the ncu launch list short)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
