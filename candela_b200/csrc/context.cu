@@ -68,7 +68,8 @@ struct cndl_ctx {
     bool ents_buffered = false;
 
     // query scratch
-    DeviceBuffer d_rays, d_hits, d_order, d_keys, d_sort_tmp, d_counter;
+    DeviceBuffer d_rays, d_hits, d_order, d_keys, d_sort_tmp, d_counter, d_chunk_counters;
+    std::vector<cudaEvent_t> events;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaStream_t main_stream = nullptr;
     int mode = 2, sort_rays = 0;
@@ -193,6 +194,7 @@ void cndl_destroy(cndl_ctx* ctx) {
     for (auto& s : ctx->streams) if (s) cudaStreamDestroy(s);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     if (ctx->build_arena) cudaFree(ctx->build_arena);
+    for (auto& e : ctx->events) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -433,21 +435,34 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
     const size_t out_elt = kind == Q_ANY ? sizeof(float) : sizeof(cndl_hit);
     CK(ctx->d_rays.ensure_scratch(R * sizeof(cndl_ray)));
     CK(ctx->d_hits.ensure_scratch(R * out_elt));
-    size_t chunk = (R + 7) / 8;
-    if (chunk < (1u << 18)) chunk = 1u << 18;
+    // Three-stage pipeline over chunks: streams[0] carries every host->device copy back to back,
+    // streams[1] the traversal kernels, streams[2] every device->host copy; events chain the stages.
+    const int n_chunks_want = ctx->knobs[CNDL_KNOB_HOST_CHUNKS] > 0 ? ctx->knobs[CNDL_KNOB_HOST_CHUNKS] : 4;
+    size_t chunk = (R + n_chunks_want - 1) / n_chunks_want;
+    if (chunk < (1u << 16)) chunk = 1u << 16;
+    const size_t n_chunks = (R + chunk - 1) / chunk;
+    while (ctx->events.size() < 2 * n_chunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->events.push_back(e);
+    }
+    CK(ctx->d_chunk_counters.ensure_scratch(n_chunks * 64));
     size_t k = 0;
     for (size_t lo = 0; lo < R; lo += chunk, ++k) {
         const size_t n = R - lo < chunk ? R - lo : chunk;
-        cudaStream_t st = ctx->streams[k % 3];
         cndl_ray* dr = static_cast<cndl_ray*>(ctx->d_rays.p) + lo;
         char* dout = static_cast<char*>(ctx->d_hits.p) + lo * out_elt;
-        CK(cudaMemcpyAsync(dr, rays + lo, n * sizeof(cndl_ray), cudaMemcpyHostToDevice, st));
-        unsigned* counter = static_cast<unsigned*>(ctx->d_counter.p) + 16 * (k % 3);  // one counter per stream in flight
+        CK(cudaMemcpyAsync(dr, rays + lo, n * sizeof(cndl_ray), cudaMemcpyHostToDevice, ctx->streams[0]));
+        CK(cudaEventRecord(ctx->events[2 * k], ctx->streams[0]));
+        CK(cudaStreamWaitEvent(ctx->streams[1], ctx->events[2 * k], 0));
+        unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->d_chunk_counters.p) + 64 * k);
         rc = enqueue_trace(ctx, kind, dr, n, kind == Q_ANY ? nullptr : reinterpret_cast<cndl_hit*>(dout),
-                           kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter, st);
+                           kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter, ctx->streams[1]);
         if (rc != CNDL_OK) return rc;
+        CK(cudaEventRecord(ctx->events[2 * k + 1], ctx->streams[1]));
+        CK(cudaStreamWaitEvent(ctx->streams[2], ctx->events[2 * k + 1], 0));
         char* hout = kind == Q_ANY ? reinterpret_cast<char*>(any_t + lo) : reinterpret_cast<char*>(hits + lo);
-        CK(cudaMemcpyAsync(hout, dout, n * out_elt, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hout, dout, n * out_elt, cudaMemcpyDeviceToHost, ctx->streams[2]));
     }
     for (auto& s : ctx->streams) CK(cudaStreamSynchronize(s));
     return CNDL_OK;

@@ -175,7 +175,8 @@ int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays);
 enum { CNDL_KNOB_BLOCKS_PER_SM = 0,   /* persistent CTAs (128 threads) per SM */
        CNDL_KNOB_LEAF_THRESHOLD = 1,  /* mode 2: parked-at-leaf lanes that trigger the leaf phase */
        CNDL_KNOB_IDLE_THRESHOLD = 2,  /* mode 2: finished lanes that trigger retire/refill */
-       CNDL_KNOB_VARIANT = 3          /* mode 2: kernel variant (node steps per vote, leaf prefetch) */ };
+       CNDL_KNOB_VARIANT = 3,         /* mode 2: kernel variant (node steps per vote, leaf prefetch) */
+       CNDL_KNOB_HOST_CHUNKS = 4      /* host-buffer queries: chunks in the copy/traverse/copy pipeline (0 = default 4) */ };
 int cndl_set_tuning(cndl_ctx* ctx, int knob, int value);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */
 uint64_t cndl_launch_count(const cndl_ctx* ctx);
