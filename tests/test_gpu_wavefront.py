@@ -1,0 +1,120 @@
+"""GPU tests of the pieces around the traversal kernels: wavefront bounce-ray generation (compaction),
+size-independent properties at BASELINE sizes, tuning knobs (which must never change a result), and the
+host-buffer pipeline."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def s260k(cb, ob):
+    from candela_b200 import scenes
+    v, i, m = scenes.make_s260k()
+    ri = cb.RayIntersector(cb.STACKLESS)
+    ri.AddObject(2, v, i, m)
+    ri.BufferData()
+    ri.PushEntity(2)
+    ri.BufferEntities()
+    nodes, tris, _ = ri.read_buffers()
+    ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(nodes))
+    yield dict(ri=ri, v=v, nodes=nodes, tris=tris, ents=ents)
+    ri.close()
+
+
+def test_bounce_ray_generation_compacts_and_is_deterministic(cb, ob, s260k):
+    import torch
+    from candela_b200 import api, scenes
+    ri = s260k["ri"]
+    W, H, spp = 640, 360, 3
+    iv, ip = scenes.camera((-18.0, 5.0, 0.7), (10.0, 30.0, -0.4), W, H)     # looks partly at the ceiling/out: some misses
+    hits, rays = ri.IntersectPrimary(iv, ip, W, H, return_rays=True)
+    hits = hits.copy()
+    hits["t"][::7] = -1.0                                                     # force misses into the batch
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
+    d_hits = torch.from_numpy(hits.view(np.float32).reshape(-1, 8)).cuda()
+    outs = []
+    for _ in range(2):
+        d_out = torch.zeros((W * H * spp, 8), dtype=torch.float32, device="cuda")
+        d_par = torch.zeros(W * H * spp, dtype=torch.int32, device="cuda")
+        n = ri.generate_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), W * H, d_out.data_ptr(), spp=spp, offset=0.05, tmax=2.4, seed=9,
+                                           d_parent_out=d_par.data_ptr())
+        outs.append((n, d_out[:n].cpu().numpy().view(api.RAY_DT).reshape(-1), d_par[:n].cpu().numpy()))
+    n, out, par = outs[0]
+    ok = hits["t"] > 0
+    assert n == spp * int(ok.sum())
+    assert np.array_equal(par, np.repeat(np.nonzero(ok)[0], spp))             # compacted in input order
+    assert outs[1][0] == n and outs[1][1].tobytes() == out.tobytes()          # deterministic
+    assert np.all(out["tmax"] == np.float32(2.4))
+    assert np.allclose(np.linalg.norm(out["d"], axis=1), 1.0, atol=1e-5)
+    # origin = hit point + 0.05 * normal, direction in the normal's hemisphere
+    P = rays["o"][par] + rays["d"][par] * hits["t"][par][:, None]
+    N = (out["o"] - P) / 0.05
+    assert np.allclose(np.linalg.norm(N, axis=1), 1.0, atol=2e-3)
+    assert np.all(np.sum(N * out["d"], axis=1) > -1e-3)
+    assert np.all(np.sum(N * rays["d"][par], axis=1) < 1e-3)                  # turned against the incoming ray
+    # the generated rays trace identically on GPU and oracle
+    want, _ = ob.trace(ob.STACKLESS, ob.ANY, s260k["nodes"], s260k["tris"], s260k["v"], s260k["ents"], out, nthreads=ob.hardware_threads())
+    assert ri.IntersectRaysAny(out).tobytes() == want.tobytes()
+
+
+def test_knobs_and_modes_never_change_results(cb, ob, s260k):
+    from helpers import rays_in_box
+    ri = s260k["ri"]
+    rays = rays_in_box((-20, 0, -9), (20, 14, 9), 300000, 21)
+    want, _ = ob.trace(ob.STACKLESS, ob.CLOSEST, s260k["nodes"], s260k["tris"], s260k["v"], s260k["ents"], rays, nthreads=ob.hardware_threads())
+    for mode in (0, 1, 2):
+        ri.set_traversal_mode(mode)
+        assert ri.IntersectRays(rays).tobytes() == want.tobytes(), mode
+    for knobs in ((7, 1, 1, 1), (8, 32, 32, 4), (10, 3, 17, 3), (12, 8, 8, 9), (8, 8, 8, 10), (8, 8, 8, 2)):
+        for k, val in enumerate(knobs):
+            ri.set_tuning(k, val)
+        assert ri.IntersectRays(rays).tobytes() == want.tobytes(), knobs
+    for chunks in (1, 3, 16):
+        ri.set_tuning(4, chunks)
+        assert ri.IntersectRays(rays).tobytes() == want.tobytes(), chunks
+    ri.set_tuning(4, 0)
+
+
+def test_full_size_properties_rtao(cb, s260k):
+    """BASELINE configs[2] at full size (8.3 M any-hit rays): determinism, permutation equivariance,
+    consistency of any-hit with closest-hit, monotonicity in tmax."""
+    import torch
+    from candela_b200 import api, scenes
+    ri = s260k["ri"]
+    W, H, spp = 1920, 1080, 4
+    iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_prim = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+    d_hits = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+    ri.intersect_primary_device(iv, ip, W, H, d_hits.data_ptr(), d_prim.data_ptr(), stream)
+    d_ao = torch.empty((W * H * spp, 8), dtype=torch.float32, device="cuda")
+    n = ri.generate_bounce_rays_device(d_prim.data_ptr(), d_hits.data_ptr(), W * H, d_ao.data_ptr(), spp=spp, tmax=2.4, seed=3, stream=stream)
+    assert n > 8_000_000
+    d_ao = d_ao[:n]
+    t1 = torch.empty(n, dtype=torch.float32, device="cuda")
+    t2 = torch.empty(n, dtype=torch.float32, device="cuda")
+    ri.intersect_any_device(d_ao.data_ptr(), n, t1.data_ptr(), stream)
+    ri.intersect_any_device(d_ao.data_ptr(), n, t2.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert torch.equal(t1, t2)                                                 # idempotent / deterministic
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    d_p = d_ao[perm].contiguous()
+    ri.intersect_any_device(d_p.data_ptr(), n, t2.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert torch.equal(t2, t1[perm])                                           # a ray's result does not depend on its neighbours
+    assert bool(((t1 > 0) <= (t1 < 2.4)).all()) and bool(((t1 == -1) | (t1 > 0)).all())
+    # closest hit with t < 2.4  <=>  some hit with t < 2.4 (the walks differ only in how TMax evolves)
+    hc = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    ri.intersect_closest_device(d_ao.data_ptr(), n, hc.data_ptr(), 0, stream)
+    torch.cuda.synchronize()
+    tc = hc[:, 0]
+    agree = ((tc > 0) & (tc < 2.4)) == (t1 > 0)
+    assert float(agree.float().mean()) > 0.99999
+    assert bool((tc[(t1 > 0) & agree] <= t1[(t1 > 0) & agree]).all())          # the closest hit is never farther than the first found
+    # a longer ray can only find more
+    d_long = d_ao.clone()
+    d_long[:, 7] = 10.0
+    ri.intersect_any_device(d_long.data_ptr(), n, t2.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert bool(((t1 > 0) <= (t2 > 0)).all())
