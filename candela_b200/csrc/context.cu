@@ -73,7 +73,7 @@ struct cndl_ctx {
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaStream_t main_stream = nullptr;
     int mode = 2, sort_rays = 0;
-    int knobs[8] = {8, 8, 8, 2, 0, 0, 0, 0};  // CNDL_KNOB_*
+    int knobs[8] = {8, 8, 8, 2, 0, 12, 0, 0};  // CNDL_KNOB_*
     LaunchCounter launches;
     float last_build_ms = 0.0f;
     void* build_arena = nullptr;
@@ -117,7 +117,10 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
     if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 rays in one call");
     const SceneView s = scene_view(ctx);
     const bool stack = ctx->format == CNDL_STACK;
-    if (ctx->mode == 0 || stack) launch_trace_simple(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, st, ctx->launches);
+    if (ctx->mode == 0 || (stack && ctx->mode == 1)) launch_trace_simple(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, st, ctx->launches);
+    else if (stack)
+        launch_trace_ww_stack(s, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, ctx->knobs[CNDL_KNOB_STACK_LEAF_THRESHOLD],
+                              ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD], st, ctx->launches);
     else if (ctx->mode == 2)
         launch_trace_ww(s, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM],
                         ctx->knobs[CNDL_KNOB_LEAF_THRESHOLD], ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD], ctx->knobs[CNDL_KNOB_VARIANT], st, ctx->launches);

@@ -29,6 +29,9 @@ void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t 
                      unsigned* work_counter, int sm_count, int blocks_per_sm, int leaf_threshold, int idle_threshold, int variant, cudaStream_t stream,
                      LaunchCounter& lc);
 
+void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits, float* any_t,
+                           unsigned* work_counter, int sm_count, int leaf_threshold, int idle_threshold, cudaStream_t stream, LaunchCounter& lc);
+
 // Camera rays of the primary kernel (Intersectors/TraverseBVHStack.glsl:133-138,:414-431).
 void launch_primary_rays(const float* inv_view16, const float* inv_proj16, int W, int H, cndl_ray* rays, cudaStream_t stream,
                          LaunchCounter& lc);

@@ -205,6 +205,181 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The same scheme for the stack format (…/Include/TraverseBVHStack.glsl:168-324, :509-657).  One step
+// loads a 64-byte node (two children).  The choice of the next node (near child first, far child
+// pushed, pop when nothing is entered) uses box distances computed with TMax as it was BEFORE this
+// node's leaf children are intersected (ST:215-216), so it is taken first; the lane then parks with
+// up to two pending leaves, which the leaf phase tests left then right, exactly in the reference order.
+struct SLane {
+    RayState r;
+    float tmax;
+    int cur, start, lo, hi, iters, ent, sp;
+    int best_tri, best_ent;
+    int pend_l, pend_r, after;  // leaf packs to test (-1: none); state to enter afterwards (WALK, or DONE = entity finished)
+    unsigned rid;
+    int state;
+};
+
+template <int KIND>
+__device__ __forceinline__ void next_entity_stack(const SceneView& s, const cndl_ray* __restrict__ rays, SLane& L, int from) {
+    int e = from;
+    while (e < s.n_ents) {
+        const cndl_entity* ent = s.ents + e;
+        if (KIND == Q_CLOSEST_IGNORE_TRANSPARENT && __int_as_float(__ldg(&ent->data[1])) < 0.99f) { ++e; continue; }
+        const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
+        const float4 a = __ldg(rp), b = __ldg(rp + 1);
+        L.r = to_object_space(ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
+        L.start = __ldg(&ent->node_offset);
+        L.lo = L.start > 0 ? L.start : 0;  // ST:201-205
+        L.hi = min(L.start + __ldg(&ent->node_count), s.total_nodes);
+        L.cur = L.start;
+        L.sp = 0;
+        L.iters = 0;
+        L.ent = e;
+        L.state = WALK;
+        return;
+    }
+    L.state = DONE;
+}
+
+template <int KIND, int STEPS>
+__global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R,
+                                                                const unsigned* __restrict__ order, cndl_hit* __restrict__ hits,
+                                                                float* __restrict__ any_t, unsigned* __restrict__ work_counter,
+                                                                int leaf_threshold, int idle_threshold) {
+    constexpr bool ANY = KIND == Q_ANY;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    int stack[64];
+    SLane L;
+    L.state = EMPTY;
+    L.rid = 0;
+    L.iters = 0;
+    L.ent = 0;
+    L.sp = 0;
+    L.best_tri = -1;
+    L.best_ent = -1;
+    bool drained = false;
+
+    while (true) {
+        {   // retire + refill
+            const unsigned b0 = __ballot_sync(FULL, (L.state & 1) != 0), b1 = __ballot_sync(FULL, (L.state & 2) != 0);
+            const unsigned done = b0 & b1, empty = ~(b0 | b1), busy = b0 ^ b1;
+            const int serviceable = __popc(done) + (drained ? 0 : __popc(empty));
+            if (busy == 0u && done == 0u && drained) break;
+            if (serviceable >= idle_threshold || busy == 0u) {
+                if (L.state == DONE) {
+                    if (ANY) {
+                        any_t[L.rid] = L.best_tri >= 0 ? L.tmax : -1.0f;
+                    } else {
+                        float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
+                        int mesh = -1;
+                        if (L.best_tri >= 0) mesh = __ldg(&s.tris[L.best_tri]).w;
+                        if (L.best_tri > 0) {  // ClosestT > 0 && TriangleIdx > 0 (ST:347)
+                            RayState r = L.r;
+                            if (L.best_ent != L.ent) {
+                                const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
+                                const float4 a = __ldg(rp), b = __ldg(rp + 1);
+                                r = to_object_space(s.ents + L.best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
+                            }
+                            t = L.tmax;  // TMax == ClosestT once something was accepted
+                            const V3 p = {fadd(r.o.x, fmul(r.d.x, t)), fadd(r.o.y, fmul(r.d.y, t)), fadd(r.o.z, fmul(r.d.z, t))};
+                            barycentrics(s.tri48, L.best_tri, p, u, v, w);
+                        }
+                        store_hit(hits, L.rid, t, u, v, w, mesh, L.best_tri, L.best_ent, L.iters);
+                    }
+                    L.state = EMPTY;
+                }
+                if (!drained) {
+                    const unsigned want = __ballot_sync(FULL, L.state == EMPTY);
+                    const int n = __popc(want);
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(work_counter, (unsigned)n);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base + (unsigned)n >= R) drained = true;
+                    if (L.state == EMPTY) {
+                        const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
+                        if (slot < R) {
+                            L.rid = order ? __ldg(order + slot) : slot;
+                            L.best_tri = -1;
+                            L.best_ent = -1;
+                            L.iters = 0;
+                            L.ent = 0;
+                            if (ANY) {
+                                const float rt = __ldg(&rays[L.rid].tmax);
+                                L.tmax = rt > 0.0f ? rt : 1000000.0f;
+                            } else {
+                                L.tmax = 1000000.0f;
+                            }
+                            next_entity_stack<KIND>(s, rays, L, 0);
+                        }
+                    }
+                }
+            }
+        }
+        while (true) {  // node phase
+            const unsigned b0 = __ballot_sync(FULL, (L.state & 1) != 0), b1 = __ballot_sync(FULL, (L.state & 2) != 0);
+            if ((b0 & ~b1) == 0u) break;
+            if (__popc(b1 & ~b0) >= leaf_threshold) break;
+            if (__popc(b0 & b1) + (drained ? 0 : __popc(~(b0 | b1))) >= idle_threshold) break;
+#pragma unroll
+            for (int step = 0; step < STEPS; ++step) {
+                if (L.state == WALK) {
+                    if (L.iters >= 1024 || L.sp >= 64 || L.sp < 0 || L.cur < L.lo || L.cur > L.hi) {  // ST:198-205
+                        next_entity_stack<KIND>(s, rays, L, L.ent + 1);
+                    } else {
+                        ++L.iters;
+                        float4 lmn, lmx, rmn, rmx;
+                        ldg256(s.nodes + 4 * (size_t)L.cur, lmn, lmx);
+                        ldg256(s.nodes + 4 * (size_t)L.cur + 2, rmn, rmx);
+                        const int lpack = __float_as_int(lmn.w), rpack = __float_as_int(rmn.w);
+                        const bool lleaf = lpack != -1, rleaf = rpack != -1;
+                        const float lt = lleaf ? -1.0f : slab_stack(lmn, lmx, L.r, L.tmax);
+                        const float rt = rleaf ? -1.0f : slab_stack(rmn, rmx, L.r, L.tmax);
+                        const int lslot = __float_as_int(lmx.w) + L.start, rslot = __float_as_int(rmx.w) + L.start;
+                        int after = WALK;
+                        if (lt > 0.0f && rt > 0.0f) {  // ST:280-299
+                            int postponed = rslot;
+                            L.cur = lslot;
+                            if (rt < lt) { L.cur = rslot; postponed = lslot; }
+                            if (L.sp >= 63) after = DONE;
+                            else stack[L.sp++] = postponed;
+                        } else if (lt > 0.0f) {
+                            L.cur = lslot;
+                        } else if (rt > 0.0f) {
+                            L.cur = rslot;
+                        } else if (L.sp <= 0) {
+                            after = DONE;
+                        } else {
+                            L.cur = stack[--L.sp];
+                        }
+                        if (lleaf || rleaf) {
+                            L.pend_l = lleaf ? lpack : -1;
+                            L.pend_r = rleaf ? rpack : -1;
+                            L.after = after;
+                            L.state = LEAF;
+                        } else if (after == DONE) {
+                            next_entity_stack<KIND>(s, rays, L, L.ent + 1);
+                        }
+                    }
+                }
+            }
+        }
+        if (L.state == LEAF) {  // leaf phase: left leaf, then right leaf (ST:221-277)
+            EntityResult er{-1.0f, -1, 0};
+            bool found = false;
+            if (L.pend_l != -1) found = leaf_triangles<ANY>(s, L.pend_l, L.r, L.tmax, er);
+            if (!found && L.pend_r != -1) found = leaf_triangles<ANY>(s, L.pend_r, L.r, L.tmax, er);
+            if (er.tri >= 0) { L.best_tri = er.tri; L.best_ent = L.ent; }
+            if (ANY && found) L.state = DONE;
+            else if (L.after == DONE) next_entity_stack<KIND>(s, rays, L, L.ent + 1);
+            else L.state = WALK;
+        }
+    }
+}
+
 template <int KIND, int MINB, int STEPS, bool PREFETCH>
 void launch_one(unsigned grid, unsigned block, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const unsigned* order,
                 cndl_hit* hits, float* any_t, unsigned* work_counter, int leaf_threshold, int idle_threshold) {
@@ -234,6 +409,22 @@ void launch_variant(int variant, unsigned grid, unsigned block, cudaStream_t str
 }
 
 }  // namespace
+
+void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits, float* any_t,
+                           unsigned* work_counter, int sm_count, int leaf_threshold, int idle_threshold, cudaStream_t stream, LaunchCounter& lc) {
+    if (R == 0) return;
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned), stream);
+    const unsigned block = 128;
+    unsigned grid = (unsigned)(sm_count * 7);
+    const unsigned need = (unsigned)((R + block - 1) / block);
+    if (grid > need) grid = need;
+    switch (kind) {
+        case Q_CLOSEST: trace_ww_stack_kernel<Q_CLOSEST, 1><<<grid, block, 0, stream>>>(s, rays, (unsigned)R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold); break;
+        case Q_CLOSEST_IGNORE_TRANSPARENT: trace_ww_stack_kernel<Q_CLOSEST_IGNORE_TRANSPARENT, 1><<<grid, block, 0, stream>>>(s, rays, (unsigned)R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold); break;
+        default: trace_ww_stack_kernel<Q_ANY, 1><<<grid, block, 0, stream>>>(s, rays, (unsigned)R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold); break;
+    }
+    lc.n++;
+}
 
 void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits, float* any_t,
                      unsigned* work_counter, int sm_count, int blocks_per_sm, int leaf_threshold, int idle_threshold, int variant, cudaStream_t stream,

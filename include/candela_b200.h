@@ -169,13 +169,14 @@ void* cndl_host_alloc(size_t bytes);
 void cndl_host_free(void* p);
 
 /* Traversal tuning (never changes results): mode 0 = one thread per ray, 1 = persistent warps with
- * ray re-fetch, 2 = persistent while-while with postponed leaf tests (default; stackless format);
+ * ray re-fetch (stackless format only), 2 = persistent while-while with postponed leaf tests (default);
  * sort_rays != 0 reorders rays by origin cell and direction octant first. */
 int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays);
 enum { CNDL_KNOB_BLOCKS_PER_SM = 0,   /* persistent CTAs (128 threads) per SM */
        CNDL_KNOB_LEAF_THRESHOLD = 1,  /* mode 2: parked-at-leaf lanes that trigger the leaf phase */
        CNDL_KNOB_IDLE_THRESHOLD = 2,  /* mode 2: finished lanes that trigger retire/refill */
        CNDL_KNOB_VARIANT = 3,         /* mode 2: kernel variant (node steps per vote, leaf prefetch) */
+       CNDL_KNOB_STACK_LEAF_THRESHOLD = 5, /* mode 2, stack format: parked lanes that trigger the leaf phase */
        CNDL_KNOB_HOST_CHUNKS = 4      /* host-buffer queries: chunks in the copy/traverse/copy pipeline (0 = default 4) */ };
 int cndl_set_tuning(cndl_ctx* ctx, int knob, int value);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */

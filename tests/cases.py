@@ -97,6 +97,32 @@ def build_cases(ob, golden_meshes, fmt):
     lr["d"] = (1, 0, 0)
     add("iteration_cap", sc4, lr)
 
+    # stack format only: a hand-made chain of slots whose two children are both inner, both hit and point at the
+    # same next slot, so every iteration pushes: the walk must stop at StackPointer >= 63 (…Stack.glsl:293-295)
+    if fmt == ob.STACK:
+        Pt2, Ft2 = two_triangles()
+        tmp = ob.Scene(ob.STACK)
+        tmp.add_object(2, ob.make_vertices(Pt2), Ft2.ravel(), np.array([11, 12], np.int32))
+        n_slots = 80
+        nodes = np.zeros(n_slots, dtype=ob.NODE64_DT)
+        for k in range(n_slots - 1):
+            for side in ("l", "r"):
+                nodes[side + "min"][k] = (-2, -2, -1, 0)
+                nodes[side + "max"][k] = (2, 2, 20, 0)
+                nodes[side + "min"][k, 3:].view(np.int32)[0] = -1
+                nodes[side + "max"][k, 3:].view(np.int32)[0] = k + 1
+        leaf = tmp.nodes[0]                                   # the real (single-slot) tree: both children are leaves
+        nodes[n_slots - 1] = leaf
+        sc5 = ob.Scene(ob.STACK)
+        sc5.nodes, sc5.tris, sc5.verts = nodes, tmp.tris, tmp.verts
+        sc5.objects[2] = dict(node_offset=0, node_count=n_slots, tri_offset=0, tri_count=len(tmp.tris), vert_offset=0, vert_count=len(tmp.verts))
+        sc5.builds[2] = tmp.builds[2]
+        sc5.push_entity(2)
+        kr2 = np.zeros(3, dtype=ob.RAY_DT)
+        kr2["o"] = [(0, 0, 0), (0.1, 0.1, 0), (5, 5, 0)]
+        kr2["d"] = (0, 0, 1)
+        add("stack_overflow", sc5, kr2)
+
     # degenerate geometry
     for nm in ("coplanar_grid", "duplicates", "collinear", "signed_zero"):
         Pd, Fd = golden_meshes[nm]
