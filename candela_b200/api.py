@@ -26,6 +26,7 @@ STACK_NODE_DT = np.dtype([("lmin", "<f4", 4), ("lmax", "<f4", 4), ("rmin", "<f4"
 ENTITY_DT = np.dtype([("model", "<f4", 16), ("inverse", "<f4", 16), ("node_offset", "<i4"), ("node_count", "<i4"), ("data", "<i4", 14)])
 RAY_DT = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
 HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("w", "<f4"), ("mesh", "<i4"), ("tri", "<i4"), ("entity", "<i4"), ("iters", "<i4")])
+ATTR_DT = np.dtype([("normal", "<f4", 3), ("uv", "<f4", 2), ("emissivity", "<f4"), ("alpha", "<f4"), ("mesh", "<i4")])
 
 EXPORTS = [
     "cndl_abi_version", "cndl_create", "cndl_destroy", "cndl_last_error", "cndl_add_object", "cndl_add_prebuilt_object",
@@ -33,7 +34,7 @@ EXPORTS = [
     "cndl_device_buffers", "cndl_push_entity", "cndl_push_entity_records", "cndl_buffer_entities", "cndl_entity_count",
     "cndl_intersect_closest", "cndl_intersect_any", "cndl_intersect_closest_device", "cndl_intersect_any_device",
     "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_generate_bounce_rays_device", "cndl_host_alloc", "cndl_host_free",
-    "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms",
+    "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device",
 ]
 
 
@@ -89,6 +90,8 @@ def load_library() -> C.CDLL:
     L.cndl_intersect_primary.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
     L.cndl_intersect_primary_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
     L.cndl_generate_bounce_rays_device.argtypes = [vp, vp, vp, sz, C.c_int, C.c_float, C.c_float, C.c_uint32, vp, vp, C.POINTER(sz), vp]
+    L.cndl_get_data.argtypes = [vp, vp, sz, vp]
+    L.cndl_get_data_device.argtypes = [vp, vp, sz, vp, vp]
     L.cndl_host_alloc.argtypes = [sz]
     L.cndl_host_alloc.restype = vp
     L.cndl_host_free.argtypes = [vp]
@@ -298,6 +301,13 @@ class RayIntersector:
         self._check(self._lib.cndl_intersect_primary(self._h, _p(iv), _p(ip), Width, Height, _p(hits), _p(rays)))
         return (hits, rays) if return_rays else hits
 
+    def GetData(self, hits) -> np.ndarray:
+        """GetData (…/Include/TraverseBVHStackless.glsl:370-408) without the texture fetch, for a host batch of hit records."""
+        hits = np.ascontiguousarray(hits, dtype=HIT_DT)
+        out = np.zeros(len(hits), dtype=ATTR_DT)
+        self._check(self._lib.cndl_get_data(self._h, _p(hits), len(hits), _p(out)))
+        return out
+
     # -- queries: device buffers (raw pointers, e.g. torch tensors' data_ptr()) --------------------
     def intersect_closest_device(self, d_rays: int, n_rays: int, d_hits: int, flags: int = 0, stream: int = 0):
         self._check(self._lib.cndl_intersect_closest_device(self._h, d_rays, n_rays, flags, d_hits, stream or None))
@@ -316,3 +326,6 @@ class RayIntersector:
     def intersect_primary_device(self, inv_view, inv_proj, Width: int, Height: int, d_hits: int, d_rays: int = 0, stream: int = 0):
         iv, ip = _colmajor(inv_view), _colmajor(inv_proj)
         self._check(self._lib.cndl_intersect_primary_device(self._h, _p(iv), _p(ip), Width, Height, d_hits, d_rays or None, stream or None))
+
+    def get_data_device(self, d_hits: int, n: int, d_out: int, stream: int = 0):
+        self._check(self._lib.cndl_get_data_device(self._h, d_hits, n, d_out, stream or None))

@@ -535,6 +535,34 @@ int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, cons
     return CNDL_OK;
 }
 
+int cndl_get_data_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_attr* d_out, void* stream) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (R && (!d_hits || !d_out)) return ctx->fail(CNDL_ERR_INVALID, "null hit or attribute buffer");
+    if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 records in one call");
+    int rc = check_ready(ctx);
+    if (rc != CNDL_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    launch_get_data(scene_view(ctx), static_cast<const float4*>(ctx->verts.p), d_hits, R, d_out, static_cast<cudaStream_t>(stream), ctx->launches);
+    CK(cudaGetLastError());
+    return CNDL_OK;
+}
+
+int cndl_get_data(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_attr* out) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (R && (!hits || !out)) return ctx->fail(CNDL_ERR_INVALID, "null hit or attribute buffer");
+    if (R == 0) return check_ready(ctx);
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_hits.ensure_scratch(R * sizeof(cndl_hit)));
+    CK(ctx->d_rays.ensure_scratch(R * sizeof(cndl_hit_attr)));
+    cudaStream_t st = ctx->main_stream;
+    CK(cudaMemcpyAsync(ctx->d_hits.p, hits, R * sizeof(cndl_hit), cudaMemcpyHostToDevice, st));
+    int rc = cndl_get_data_device(ctx, static_cast<const cndl_hit*>(ctx->d_hits.p), R, static_cast<cndl_hit_attr*>(ctx->d_rays.p), st);
+    if (rc != CNDL_OK) return rc;
+    CK(cudaMemcpyAsync(out, ctx->d_rays.p, R * sizeof(cndl_hit_attr), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return CNDL_OK;
+}
+
 void* cndl_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -41,4 +41,7 @@ cudaError_t generate_bounce_rays(const SceneView& s, const cndl_ray* rays, const
                                  unsigned seed, cndl_ray* out, unsigned* parent, int* scratch, size_t* h_count, cudaStream_t stream,
                                  LaunchCounter& lc);
 
+// GetData without textures: interpolated normal / uv + entity emissive / alpha per hit record (kernels_raygen.cu).
+void launch_get_data(const SceneView& s, const float4* verts, const cndl_hit* hits, size_t R, cndl_hit_attr* out, cudaStream_t stream, LaunchCounter& lc);
+
 }  // namespace cndl

@@ -7,6 +7,8 @@
 #include "kernels.cuh"
 #include "scan.cuh"
 
+#include <cuda_fp16.h>
+
 namespace cndl {
 
 namespace {
@@ -64,7 +66,41 @@ __global__ void bounce_emit_kernel(const cndl_ray* __restrict__ rays, const cndl
     }
 }
 
+// GetData (…/Include/TraverseBVHStackless.glsl:370-408) without the texture fetch.
+__global__ void get_data_kernel(const int4* __restrict__ tris, const float4* __restrict__ verts, const cndl_entity* __restrict__ ents,
+                                const cndl_hit* __restrict__ hits, unsigned R, cndl_hit_attr* __restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(hits + i));
+    const int4 h1 = __ldg(reinterpret_cast<const int4*>(hits + i) + 1);
+    float4 o0 = make_float4(-1.0f, -1.0f, -1.0f, 0.0f);  // Normal = vec3(-1) on a miss (SL:377-382)
+    float4 o1 = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(h1.x));
+    if (!(h0.x < 0.0f || h1.x < 0)) {
+        const int4 t = __ldg(tris + h1.y);
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(verts + 2 * (size_t)t.x + 1));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(verts + 2 * (size_t)t.y + 1));
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(verts + 2 * (size_t)t.z + 1));
+        auto lo = [](unsigned p) { return __half2float(__ushort_as_half((unsigned short)(p & 0xFFFFu))); };
+        auto hi = [](unsigned p) { return __half2float(__ushort_as_half((unsigned short)(p >> 16))); };
+        auto mix3 = [&](float fa, float fb, float fc) { return fadd(fadd(fmul(fa, h0.y), fmul(fb, h0.z)), fmul(fc, h0.w)); };
+        const float u = mix3(lo(a.w), lo(b.w), lo(c.w)), v = mix3(hi(a.w), hi(b.w), hi(c.w));
+        const float nx = mix3(lo(a.x), lo(b.x), lo(c.x)), ny = mix3(hi(a.x), hi(b.x), hi(c.x)), nz = mix3(lo(a.y), lo(b.y), lo(c.y));
+        const float inv_len = fdiv(1.0f, __fsqrt_rn(fadd(fadd(fmul(nx, nx), fmul(ny, ny)), fmul(nz, nz))));
+        o0 = make_float4(fmul(nx, inv_len), fmul(ny, inv_len), fmul(nz, inv_len), u);
+        o1 = make_float4(v, __int_as_float(__ldg(&ents[h1.z].data[0])), __int_as_float(__ldg(&ents[h1.z].data[1])), __int_as_float(h1.x));
+    }
+    float4* p = reinterpret_cast<float4*>(out + i);
+    p[0] = o0;
+    p[1] = o1;
+}
+
 }  // namespace
+
+void launch_get_data(const SceneView& s, const float4* verts, const cndl_hit* hits, size_t R, cndl_hit_attr* out, cudaStream_t stream, LaunchCounter& lc) {
+    if (R == 0) return;
+    get_data_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(s.tris, verts, s.ents, hits, (unsigned)R, out);
+    lc.n++;
+}
 
 // Returns the number of rays written through *h_count (synchronises `stream`). `scratch` must hold
 // 2*R + R/2048 + 8 ints.

@@ -170,11 +170,6 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
                                 L.pend_pack = pack;
                                 L.pend_link = link;
                                 L.state = LEAF;
-                                if (PREFETCH) {
-                                    const char* tp = reinterpret_cast<const char*>(s.tri48 + 3 * (size_t)(pack >> 4));
-                                    prefetch_l1(tp);
-                                    prefetch_l1(tp + 48 * (pack & 0xF) - 16);
-                                }
                             } else {
                                 ++L.ptr;
                             }
@@ -186,6 +181,8 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
                     }
                 }
             }
+            // the vote round separates this step from the next load: start fetching the next node now
+            if (PREFETCH && L.state == WALK) prefetch_l1(s.nodes + 2 * (size_t)L.ptr);
         }
 
         // ---------------- leaf phase ----------------

@@ -164,6 +164,13 @@ int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const
 int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R, int spp, float offset,
                                      float tmax, uint32_t seed, cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream);
 
+/* GetData (…/Include/TraverseBVHStackless.glsl:370-408) without the texture fetch — the step right after
+ * the path: for every hit record, the interpolated half-float vertex normal (normalised) and UV and the
+ * entity's emissive / alpha floats.  A miss (t < 0 or mesh < 0) gives normal (-1,-1,-1) and zeros. */
+typedef struct cndl_hit_attr { float nx, ny, nz, u, v, emissivity, alpha; int32_t mesh; } cndl_hit_attr;
+int cndl_get_data_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_attr* d_out, void* stream);
+int cndl_get_data(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_attr* out);
+
 /* Pinned host memory for ray / hit batches. */
 void* cndl_host_alloc(size_t bytes);
 void cndl_host_free(void* p);

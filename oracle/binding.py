@@ -28,6 +28,7 @@ NODE32_DT = np.dtype([("min", "<f4", 4), ("max", "<f4", 4)])
 NODE64_DT = np.dtype([("lmin", "<f4", 4), ("lmax", "<f4", 4), ("rmin", "<f4", 4), ("rmax", "<f4", 4)])
 ENTITY_DT = np.dtype([("model", "<f4", 16), ("inverse", "<f4", 16), ("node_offset", "<i4"), ("node_count", "<i4"), ("data", "<i4", 14)])
 RAY_DT = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
+ATTR_DT = np.dtype([("normal", "<f4", 3), ("uv", "<f4", 2), ("emissivity", "<f4"), ("alpha", "<f4"), ("mesh", "<i4")])
 HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("w", "<f4"), ("mesh", "<i4"), ("tri", "<i4"), ("entity", "<i4"), ("iters", "<i4")])
 assert (VERTEX_DT.itemsize, TRIANGLE_DT.itemsize, NODE32_DT.itemsize, NODE64_DT.itemsize, ENTITY_DT.itemsize, RAY_DT.itemsize, HIT_DT.itemsize) == (32, 16, 32, 64, 192, 32, 32)
 
@@ -72,6 +73,7 @@ def lib() -> C.CDLL:
         L.orc_primary_rays.argtypes = [vp, vp, C.c_int, C.c_int, vp]
         L.orc_trace.argtypes = [C.c_int, C.c_int, vp, u64, vp, vp, vp, i32, vp, u64, vp, vp, vp, C.c_int]
         L.orc_brute_force.argtypes = [vp, u64, vp, vp, i32, vp, u64, vp, C.c_int]
+        L.orc_get_data.argtypes = [vp, vp, vp, vp, u64, vp]
         L.orc_hardware_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -222,6 +224,27 @@ def brute_force(tris, verts, entities, rays, nthreads=1):
     out = np.zeros(len(rays), dtype=HIT_DT)
     lib().orc_brute_force(_p(tris), len(tris), _p(verts), _p(entities), len(entities), _p(rays), len(rays), _p(out), nthreads)
     return out
+
+
+def get_data(tris, verts, entities, hits):
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
+    verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DT)
+    hits = np.ascontiguousarray(hits, dtype=HIT_DT)
+    out = np.zeros(len(hits), dtype=ATTR_DT)
+    lib().orc_get_data(_p(tris), _p(verts), _p(entities), _p(hits), len(hits), _p(out))
+    return out
+
+
+def pack_vertices(positions, normals, uvs):
+    """Vertex records with packed half-float normal / uv like ModelFileLoader.cpp:133-155 (tangent = 0)."""
+    v = make_vertices(positions)
+    n16 = np.asarray(normals, dtype=np.float32).astype(np.float16).view(np.uint16).astype(np.uint32)
+    t16 = np.asarray(uvs, dtype=np.float32).astype(np.float16).view(np.uint16).astype(np.uint32)
+    v["normal_tangent"][:, 0] = n16[:, 0] | (n16[:, 1] << 16)
+    v["normal_tangent"][:, 1] = n16[:, 2]
+    v["texcoords"] = t16[:, 0] | (t16[:, 1] << 16)
+    return v
 
 
 def primary_rays(inv_view: np.ndarray, inv_proj: np.ndarray, W: int, H: int) -> np.ndarray:

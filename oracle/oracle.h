@@ -124,6 +124,11 @@ void orc_trace(int format, int kind,
 void orc_brute_force(const void* tris, uint64_t T, const void* verts, const void* entities, int32_t n_entities,
                      const orc_ray* rays, uint64_t R, orc_hit* hits, int nthreads);
 
+/* GetData (...Stackless.glsl:370-408) without the texture fetch: per hit record, the interpolated half-float
+ * vertex normal (normalised) and UV, and the entity's emissive / alpha floats.  out: R records of 32 bytes
+ * {float nx,ny,nz,u,v,emissivity,alpha; int32 mesh}; a miss (t < 0 or mesh < 0) gives normal (-1,-1,-1), rest 0. */
+void orc_get_data(const void* tris, const void* verts, const void* entities, const orc_hit* hits, uint64_t R, void* out);
+
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus

@@ -405,3 +405,54 @@ void orc_make_entity(const float m[16], int32_t node_offset, int32_t node_count,
 }
 
 }  // extern "C"
+
+// ---- GetData: hit attribute fetch (SL:370-408), the step right after the path ----
+namespace {
+// unpackHalf2x16 component: IEEE binary16 -> binary32, exact
+inline float half_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {
+            int e = -1;
+            do { man <<= 1; ++e; } while (!(man & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FFu) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+    else bits = sign | ((exp + 112u) << 23) | (man << 13);
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f;
+}
+struct Attr32 { float nx, ny, nz, u, v, emissivity, alpha; int32_t mesh; };
+}  // namespace
+
+extern "C" void orc_get_data(const void* tris_, const void* verts_, const void* entities, const orc_hit* hits, uint64_t R, void* out_) {
+    const Tri16* tris = static_cast<const Tri16*>(tris_);
+    const Vertex32* verts = static_cast<const Vertex32*>(verts_);
+    const Entity192* ents = static_cast<const Entity192*>(entities);
+    Attr32* out = static_cast<Attr32*>(out_);
+    for (uint64_t i = 0; i < R; ++i) {
+        const orc_hit& h = hits[i];
+        Attr32 a{-1.0f, -1.0f, -1.0f, 0.0f, 0.0f, 0.0f, 0.0f, h.mesh};
+        if (!(h.t < 0.0f || h.mesh < 0)) {  // SL:377-382
+            const Tri16& tri = tris[h.tri];
+            const Vertex32 &A = verts[tri.v[0]], &B = verts[tri.v[1]], &C = verts[tri.v[2]];
+            auto lo = [](uint32_t p) { return half_to_float((uint16_t)(p & 0xFFFFu)); };
+            auto hi = [](uint32_t p) { return half_to_float((uint16_t)(p >> 16)); };
+            // vec2 UV = uvA * TUVW.y + uvB * TUVW.z + uvC * TUVW.w  (left to right)
+            a.u = (lo(A.packed[3]) * h.u + lo(B.packed[3]) * h.v) + lo(C.packed[3]) * h.w;
+            a.v = (hi(A.packed[3]) * h.u + hi(B.packed[3]) * h.v) + hi(C.packed[3]) * h.w;
+            // UnpackNormal(Packed.xy) = (unpackHalf2x16(x).xy, unpackHalf2x16(y).x)
+            const float nx = (lo(A.packed[0]) * h.u + lo(B.packed[0]) * h.v) + lo(C.packed[0]) * h.w;
+            const float ny = (hi(A.packed[0]) * h.u + hi(B.packed[0]) * h.v) + hi(C.packed[0]) * h.w;
+            const float nz = (lo(A.packed[1]) * h.u + lo(B.packed[1]) * h.v) + lo(C.packed[1]) * h.w;
+            const float inv_len = 1.0f / std::sqrt((nx * nx + ny * ny) + nz * nz);  // normalize = v * inversesqrt(dot(v,v))
+            a.nx = nx * inv_len; a.ny = ny * inv_len; a.nz = nz * inv_len;
+            a.emissivity = ibits(ents[h.entity].data[0]);
+            a.alpha = ibits(ents[h.entity].data[1]);
+        }
+        out[i] = a;
+    }
+}
