@@ -73,7 +73,7 @@ struct cndl_ctx {
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaStream_t main_stream = nullptr;
     int mode = 2, sort_rays = 0;
-    int knobs[8] = {8, 8, 8, 2, 0, 12, 0, 0};  // CNDL_KNOB_*
+    int knobs[8] = {8, 12, 8, 18, 0, 12, 0, 0};  // CNDL_KNOB_*
     LaunchCounter launches;
     float last_build_ms = 0.0f;
     void* build_arena = nullptr;

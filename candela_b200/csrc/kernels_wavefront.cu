@@ -204,6 +204,151 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
 
 
 // ---------------------------------------------------------------------------------------------
+// Second generation of the stackless while-while kernel.  Same per-ray sequence of operations;
+// what changed is what the WARP executes around it (ncu source counters of the first version:
+// 36 of ~150 warp instructions per vote round were the three-way threshold test, and the
+// enter / miss-link sides of each node step ran one after the other with half the lanes each):
+//   * a node step is branch-free: next pointer and next state are selected, never branched on;
+//   * DONE means "this entity is finished".  Moving on to the next entity (matrix loads, the
+//     object-space ray, three IEEE divisions) happens in the batched service phase together with
+//     retiring and refilling, not inline in the node loop (three inlined copies before);
+//   * one ballot per vote round: the node phase runs until `park` of the lanes that were walking
+//     when it started have parked (at a leaf or at the end of an entity); the count adapts to the
+//     number of walkers (a quarter of them, at most `park_threshold`) so the tail of a batch does
+//     not serialise behind its last long rays.
+template <int KIND, int MINB, int STEPS>
+__global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R,
+                                                                     const unsigned* __restrict__ order, cndl_hit* __restrict__ hits,
+                                                                     float* __restrict__ any_t, unsigned* __restrict__ work_counter,
+                                                                     int park_threshold, int idle_threshold) {
+    constexpr bool ANY = KIND == Q_ANY;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr int NO_MORE_ENTITIES = 0x3FFFFFFF;
+    const unsigned lane = threadIdx.x & 31u;
+    WLane L;
+    L.state = EMPTY;
+    L.rid = 0;
+    L.iters = 0;
+    L.ent = 0;
+    L.best_tri = -1;
+    L.best_ent = -1;
+    L.closest = -1.0f;
+    L.pend_pack = 0;
+    L.pend_link = -1;
+    bool drained = false;
+    bool warp_exact = false;  // some lane's ray needs the literal GLSL min/max (warp-uniform: no divergence on it)
+
+    while (true) {
+        // ---------------- service: next entity / retire / refill ----------------
+        {
+            const unsigned b0 = __ballot_sync(FULL, (L.state & 1) != 0), b1 = __ballot_sync(FULL, (L.state & 2) != 0);
+            const unsigned done = b0 & b1, empty = ~(b0 | b1), busy = b0 ^ b1;
+            if (busy == 0u && done == 0u && drained) break;
+            const int serviceable = __popc(done) + (drained ? 0 : __popc(empty));
+            if (serviceable >= idle_threshold || busy == 0u) {
+                if (L.state == DONE) {
+                    next_entity<KIND>(s, rays, L, L.ent + 1);  // WALK again, or still DONE: the scene loop is over
+                    if (L.state == DONE) {
+                        if (ANY) {
+                            any_t[L.rid] = L.closest;
+                        } else {
+                            // tail of IntersectScene (SL:300-318)
+                            float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
+                            int mesh = -1;
+                            if (L.best_tri >= 0) mesh = __ldg(&s.tris[L.best_tri]).w;
+                            if (L.closest > 0.0f && L.best_tri > 0) {
+                                RayState r = L.r;
+                                if (L.best_ent != L.ent) {
+                                    const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
+                                    const float4 a = __ldg(rp), b = __ldg(rp + 1);
+                                    r = to_object_space(s.ents + L.best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
+                                }
+                                const V3 p = {fadd(r.o.x, fmul(r.d.x, L.closest)), fadd(r.o.y, fmul(r.d.y, L.closest)), fadd(r.o.z, fmul(r.d.z, L.closest))};
+                                t = L.closest;
+                                barycentrics(s.tri48, L.best_tri, p, u, v, w);
+                            }
+                            store_hit(hits, L.rid, t, u, v, w, mesh, L.best_tri, L.best_ent, L.iters);
+                        }
+                        L.state = EMPTY;
+                    }
+                }
+                if (!drained) {
+                    const unsigned want = __ballot_sync(FULL, L.state == EMPTY);
+                    const int n = __popc(want);
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(work_counter, (unsigned)n);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base + (unsigned)n >= R) drained = true;
+                    if (L.state == EMPTY) {
+                        const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
+                        if (slot < R) {
+                            L.rid = order ? __ldg(order + slot) : slot;
+                            L.closest = -1.0f;
+                            L.best_tri = -1;
+                            L.best_ent = -1;
+                            L.iters = 0;
+                            L.ent = 0;
+                            if (ANY) {
+                                const float rt = __ldg(&rays[L.rid].tmax);
+                                L.tmax = rt > 0.0f ? rt : 1000000.0f;
+                            } else {
+                                L.tmax = 1000000.0f;
+                            }
+                            next_entity<KIND>(s, rays, L, 0);
+                        }
+                    }
+                }
+                warp_exact = __any_sync(FULL, (L.state == WALK || L.state == LEAF) && L.r.nan_path);
+            }
+        }
+
+        // ---------------- node phase ----------------
+        {
+            const int walk0 = __popc(__ballot_sync(FULL, L.state == WALK));
+            if (walk0 > 0) {
+                int park = walk0 >> 2;
+                park = park < 1 ? 1 : (park > park_threshold ? park_threshold : park);
+                const int min_walk = walk0 - park + 1;  // >= 1
+                do {
+#pragma unroll
+                    for (int step = 0; step < STEPS; ++step) {
+                        if (L.state == WALK) {
+                            // loop header of SL:192-199 (Pointer >= 0, Iterations < 1024, range checks)
+                            if (L.iters >= 1024 || L.ptr < L.lo || L.ptr > L.hi) {
+                                L.state = DONE;
+                            } else {
+                                ++L.iters;
+                                float4 mn, mx;
+                                ldg256(s.nodes + 2 * (size_t)L.ptr, mn, mx);
+                                const int link = __float_as_int(mx.w), pack = __float_as_int(mn.w);
+                                const bool enter = enter_stackless(mn, mx, L.r, L.tmax, warp_exact);
+                                L.pend_pack = pack;
+                                L.pend_link = link;
+                                L.ptr = enter ? L.ptr + 1 : link + L.start;  // a leaf's pointer is set again after its triangles
+                                L.state = enter ? (pack != -1 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
+                            }
+                        }
+                    }
+                } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+            }
+        }
+
+        // ---------------- leaf phase ----------------
+        if (L.state == LEAF) {
+            EntityResult er{-1.0f, -1, 0};
+            const bool found = leaf_triangles<ANY>(s, L.pend_pack, L.r, L.tmax, er);
+            if (er.tri >= 0) { L.closest = er.t; L.best_tri = er.tri; L.best_ent = L.ent; }
+            L.ptr = L.pend_link + L.start;
+            L.state = L.pend_link < 0 ? DONE : WALK;
+            if (ANY && found) {  // SL:567-569: the scene loop returns the first T > 0
+                L.state = DONE;
+                L.ent = NO_MORE_ENTITIES;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The same scheme for the stack format (…/Include/TraverseBVHStack.glsl:168-324, :509-657).  One step
 // loads a 64-byte node (two children).  The choice of the next node (near child first, far child
 // pushed, pop when nothing is entered) uses box distances computed with TMax as it was BEFORE this
@@ -389,6 +534,18 @@ void launch_one(unsigned grid, unsigned block, cudaStream_t stream, const SceneV
     k<<<grid, block, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold);
 }
 
+template <int KIND, int MINB, int STEPS>
+void launch_one2(unsigned grid, unsigned block, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const unsigned* order,
+                 cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
+    auto k = trace_ww2_stackless_kernel<KIND, MINB, STEPS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        configured = true;
+    }
+    k<<<grid, block, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
+}
+
 template <int KIND, int MINB>
 void launch_variant(int variant, unsigned grid, unsigned block, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R,
                     const unsigned* order, cndl_hit* hits, float* any_t, unsigned* work_counter, int leaf_threshold, int idle_threshold) {
@@ -400,6 +557,10 @@ void launch_variant(int variant, unsigned grid, unsigned block, cudaStream_t str
         case 4: launch_one<KIND, MINB, 4, false>(CNDL_WW_ARGS); break;
         case 9: launch_one<KIND, MINB, 1, true>(CNDL_WW_ARGS); break;
         case 10: launch_one<KIND, MINB, 2, true>(CNDL_WW_ARGS); break;
+        case 17: launch_one2<KIND, MINB, 1>(CNDL_WW_ARGS); break;
+        case 18: launch_one2<KIND, MINB, 2>(CNDL_WW_ARGS); break;
+        case 19: launch_one2<KIND, MINB, 3>(CNDL_WW_ARGS); break;
+        case 20: launch_one2<KIND, MINB, 4>(CNDL_WW_ARGS); break;
         default: launch_one<KIND, MINB, 2, false>(CNDL_WW_ARGS); break;
     }
 #undef CNDL_WW_ARGS

@@ -55,22 +55,26 @@ __device__ __forceinline__ float ray_triangle(const float4* __restrict__ tri48, 
 }
 
 // RayBounds, SL:100-109, followed by the caller's `Box > 0 && Box < TMax` (SL:207).
-// Returns whether the node is entered.
-__device__ __forceinline__ bool enter_stackless(float4 mn, float4 mx, const RayState& r, float tmax_cur) {
+// Returns whether the node is entered.  `exact` selects the literal GLSL min/max forms, which is
+// required whenever a slab product can be NaN (0 * inf) and correct always.
+__device__ __forceinline__ bool enter_stackless(float4 mn, float4 mx, const RayState& r, float tmax_cur, bool exact) {
     const float t0x = fmul(fsub(mn.x, r.o.x), r.inv.x), t0y = fmul(fsub(mn.y, r.o.y), r.inv.y), t0z = fmul(fsub(mn.z, r.o.z), r.inv.z);
     const float t1x = fmul(fsub(mx.x, r.o.x), r.inv.x), t1y = fmul(fsub(mx.y, r.o.y), r.inv.y), t1z = fmul(fsub(mx.z, r.o.z), r.inv.z);
-    float tmin, tmax;
-    if (!r.nan_path) {
-        // No NaN can occur: fminf/fmaxf equal the GLSL forms up to the sign of a zero, which no
-        // comparison below can observe (tmin >= 0.0001 whenever it is returned).
-        tmin = fmaxf(fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z)), 0.0001f);
-        tmax = fminf(fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z))), tmax_cur);
-    } else {
-        tmin = glsl_max(glsl_max(glsl_max(glsl_min(t0x, t1x), glsl_min(t0y, t1y)), glsl_min(t0z, t1z)), 0.0001f);
-        tmax = glsl_min(glsl_min(glsl_max(t0x, t1x), glsl_min(glsl_max(t0y, t1y), glsl_max(t0z, t1z))), tmax_cur);
+    if (!exact) {
+        // No NaN can occur (finite origin, finite non-zero inverse direction): fminf/fmaxf equal the GLSL
+        // forms up to the sign of a zero, which no comparison below can observe.  With tmin >= 0.0001:
+        //   Box = (min(far, TMax) >= tmin) ? tmin : -1;  Box > 0 && Box < TMax   <=>   far >= tmin && tmin < TMax
+        const float tmin = fmaxf(fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z)), 0.0001f);
+        const float far = fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z)));
+        return far >= tmin && tmin < tmax_cur;
     }
+    const float tmin = glsl_max(glsl_max(glsl_max(glsl_min(t0x, t1x), glsl_min(t0y, t1y)), glsl_min(t0z, t1z)), 0.0001f);
+    const float tmax = glsl_min(glsl_min(glsl_max(t0x, t1x), glsl_min(glsl_max(t0y, t1y), glsl_max(t0z, t1z))), tmax_cur);
     const float box = (tmax >= tmin) ? tmin : -1.0f;
     return box > 0.0f && box < tmax_cur;
+}
+__device__ __forceinline__ bool enter_stackless(float4 mn, float4 mx, const RayState& r, float tmax_cur) {
+    return enter_stackless(mn, mx, r, tmax_cur, r.nan_path);
 }
 
 // RayBounds, ST:107-116
