@@ -2,6 +2,7 @@
 // (Source/Core/BVH/Intersector.h:60-124) held in device memory, plus the query entry points.
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <string>
 #include <unordered_map>
@@ -73,7 +74,14 @@ struct cndl_ctx {
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaStream_t main_stream = nullptr;
     int mode = 2, sort_rays = 0;
-    int knobs[8] = {8, 12, 8, 18, 0, 12, 0, 0};  // CNDL_KNOB_*
+    int knobs[8] = {8, 12, 8, 18, 0, 12, 2048, 1024};  // CNDL_KNOB_*
+    // hot-first derived layout of the stackless nodes (kernels_hot.cu), rebuilt by cndl_commit
+    DeviceBuffer nodes2, perm, ents2, hot_scratch, d_objects;
+    std::vector<int2> h_objects;                 // (node_offset, node_count) in insertion order
+    std::vector<int> h_roots;                    // root of each object in nodes2
+    std::vector<cndl_entity> buffered;           // the entity records last uploaded
+    int n_hot = 0;
+    bool hot_ready = false, hot_entities_ok = false;
     LaunchCounter launches;
     float last_build_ms = 0.0f;
     void* build_arena = nullptr;
@@ -105,6 +113,23 @@ SceneView scene_view(const cndl_ctx* ctx) {
     return s;
 }
 
+// Entity records for the derived layout: node_offset becomes the root's index in nodes2.  Every
+// record must name an object's whole node range, as PushEntity produces (Intersector.h:210-211).
+int upload_hot_entities(cndl_ctx* ctx) {
+    ctx->hot_entities_ok = false;
+    if (!ctx->hot_ready) return CNDL_OK;
+    std::vector<cndl_entity> e2 = ctx->buffered;
+    for (auto& e : e2) {
+        auto it = std::lower_bound(ctx->h_objects.begin(), ctx->h_objects.end(), e.node_offset, [](const int2& o, int v) { return o.x < v; });
+        if (it == ctx->h_objects.end() || it->x != e.node_offset || it->y != e.node_count) return CNDL_OK;  // irregular: reference-layout kernel
+        e.node_offset = ctx->h_roots[(size_t)(it - ctx->h_objects.begin())];
+    }
+    CK(ctx->ents2.ensure_scratch((e2.size() ? e2.size() : 1) * sizeof(cndl_entity)));
+    if (!e2.empty()) CK(cudaMemcpy(ctx->ents2.p, e2.data(), e2.size() * sizeof(cndl_entity), cudaMemcpyHostToDevice));
+    ctx->hot_entities_ok = true;
+    return CNDL_OK;
+}
+
 int check_ready(cndl_ctx* ctx) {
     if (!ctx->committed) return ctx->fail(CNDL_ERR_NOT_COMMITTED, "cndl_commit has not been called");
     if (!ctx->ents_buffered) return ctx->fail(CNDL_ERR_NOT_COMMITTED, "cndl_buffer_entities has not been called");
@@ -121,9 +146,17 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
     else if (stack)
         launch_trace_ww_stack(s, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, ctx->knobs[CNDL_KNOB_STACK_LEAF_THRESHOLD],
                               ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD], st, ctx->launches);
-    else if (ctx->mode == 2)
+    else if (ctx->mode == 2 && ctx->knobs[CNDL_KNOB_VARIANT] >= 32 && ctx->hot_ready && ctx->hot_entities_ok) {
+        HotView hv;
+        hv.nodes2 = static_cast<const float4*>(ctx->nodes2.p);
+        hv.ents2 = static_cast<const cndl_entity*>(ctx->ents2.p);
+        hv.n_hot = ctx->n_hot;
+        launch_trace_hot(s, hv, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCK_THREADS],
+                         ctx->knobs[CNDL_KNOB_LEAF_THRESHOLD], ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD], ctx->knobs[CNDL_KNOB_VARIANT] - 32, st, ctx->launches);
+    } else if (ctx->mode == 2)
         launch_trace_ww(s, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM],
-                        ctx->knobs[CNDL_KNOB_LEAF_THRESHOLD], ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD], ctx->knobs[CNDL_KNOB_VARIANT], st, ctx->launches);
+                        ctx->knobs[CNDL_KNOB_LEAF_THRESHOLD], ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD],
+                        ctx->knobs[CNDL_KNOB_VARIANT] >= 32 ? ctx->knobs[CNDL_KNOB_VARIANT] - 16 : ctx->knobs[CNDL_KNOB_VARIANT], st, ctx->launches);
     else launch_trace_persistent(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, st, ctx->launches);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return ctx->cuda_fail(e, "traversal launch");
@@ -336,6 +369,30 @@ int cndl_commit(cndl_ctx* ctx, int clear_host) {
     ctx->committed_nodes = ctx->n_nodes;  // m_NodeCountBuffered, Intersector.h:345
     ctx->committed_tris = ctx->n_tris;
     ctx->committed = true;
+    ctx->hot_ready = false;
+    if (ctx->format == CNDL_STACKLESS) {
+        // derived hot-first node layout for the shared-memory staged kernel (kernels_hot.cu)
+        ctx->h_objects.clear();
+        for (const auto& kv : ctx->objects) ctx->h_objects.push_back(make_int2(kv.second.node_offset, kv.second.node_count));
+        std::sort(ctx->h_objects.begin(), ctx->h_objects.end(), [](const int2& a, const int2& b) { return a.x < b.x; });
+        const int n_obj = (int)ctx->h_objects.size();
+        const size_t N = ctx->n_nodes;
+        CK(ctx->nodes2.ensure_scratch(N * sizeof(cndl_node)));
+        CK(ctx->perm.ensure_scratch(N * sizeof(int)));
+        CK(ctx->hot_scratch.ensure_scratch(hot_scratch_ints(N, n_obj) * sizeof(int)));
+        CK(ctx->d_objects.ensure_scratch((size_t)n_obj * sizeof(int2)));
+        CK(cudaMemcpyAsync(ctx->d_objects.p, ctx->h_objects.data(), (size_t)n_obj * sizeof(int2), cudaMemcpyHostToDevice, st));
+        ctx->h_roots.assign((size_t)n_obj, -1);
+        int invalid = 0;
+        CK(derive_hot_layout(static_cast<const float4*>(ctx->nodes.p), N, static_cast<const int2*>(ctx->d_objects.p), ctx->h_objects.data(), n_obj,
+                             ctx->n_tris, ctx->knobs[CNDL_KNOB_HOT_NODES], static_cast<float4*>(ctx->nodes2.p), static_cast<int*>(ctx->perm.p),
+                             static_cast<int*>(ctx->hot_scratch.p), ctx->h_roots.data(), &ctx->n_hot, &invalid, st, ctx->launches));
+        ctx->hot_ready = invalid == 0;  // a buffer with out-of-range links keeps the reference-layout kernel and its range checks
+        if (ctx->ents_buffered) {
+            const int rc = upload_hot_entities(ctx);
+            if (rc != CNDL_OK) return rc;
+        }
+    }
     return CNDL_OK;
 }
 
@@ -389,9 +446,10 @@ int cndl_buffer_entities(cndl_ctx* ctx) {
     CK(ctx->ents.ensure_scratch((E ? E : 1) * sizeof(cndl_entity)));
     if (E) CK(cudaMemcpy(ctx->ents.p, ctx->staged.data(), E * sizeof(cndl_entity), cudaMemcpyHostToDevice));
     ctx->n_ents = E;  // m_EntityPushed
+    ctx->buffered.swap(ctx->staged);
     ctx->staged.clear();
     ctx->ents_buffered = true;
-    return CNDL_OK;
+    return upload_hot_entities(ctx);
 }
 
 int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays) {

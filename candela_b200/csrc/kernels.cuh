@@ -44,4 +44,21 @@ cudaError_t generate_bounce_rays(const SceneView& s, const cndl_ray* rays, const
 // GetData without textures: interpolated normal / uv + entity emissive / alpha per hit record (kernels_raygen.cu).
 void launch_get_data(const SceneView& s, const float4* verts, const cndl_hit* hits, size_t R, cndl_hit_attr* out, cudaStream_t stream, LaunchCounter& lc);
 
+// Hot-first derived node layout + shared-memory staged traversal (kernels_hot.cu).
+constexpr int kMaxHotNodes = 7168;  // 224 KB of shared memory
+struct HotView {
+    const float4* nodes2;       // derived node array (hot nodes first)
+    const cndl_entity* ents2;   // entity records whose node_offset is the root's index in nodes2
+    int n_hot;                  // nodes staged in shared memory
+};
+size_t hot_scratch_ints(size_t N, int n_objects);
+// objects: (node_offset, node_count) per object in insertion order, on the device and on the host.
+// h_roots_out[o] = index of object o's root in nodes2; *h_invalid != 0 when a link or leaf range is out of bounds.
+cudaError_t derive_hot_layout(const float4* nodes, size_t N, const int2* d_objects, const int2* h_objects, int n_objects, size_t n_tris, int H,
+                              float4* nodes2, int* perm, int* scratch, int* h_roots_out, int* h_n_hot, int* h_invalid, cudaStream_t st,
+                              LaunchCounter& lc);
+void launch_trace_hot(const SceneView& s, const HotView& hv, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits,
+                      float* any_t, unsigned* work_counter, int sm_count, int block_threads, int park_threshold, int idle_threshold, int steps,
+                      cudaStream_t stream, LaunchCounter& lc);
+
 }  // namespace cndl

@@ -216,7 +216,27 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
 //     when it started have parked (at a leaf or at the end of an entity); the count adapts to the
 //     number of walkers (a quarter of them, at most `park_threshold`) so the tail of a batch does
 //     not serialise behind its last long rays.
-template <int KIND, int MINB, int STEPS>
+// One node visit of a walking lane (SL:192-246), branch-free: the next pointer and the next state are selected.
+// DONE = this entity is finished (miss link -1, or the loop header's cap / range checks fail).
+__device__ __forceinline__ void node_step(const SceneView& s, WLane& L, bool warp_exact) {
+    if (L.state == WALK) {
+        if (L.iters >= 1024 || L.ptr < L.lo || L.ptr > L.hi) {  // loop header of SL:192-199
+            L.state = DONE;
+        } else {
+            ++L.iters;
+            float4 mn, mx;
+            ldg256(s.nodes + 2 * (size_t)L.ptr, mn, mx);
+            const int link = __float_as_int(mx.w), pack = __float_as_int(mn.w);
+            const bool enter = enter_stackless(mn, mx, L.r, L.tmax, warp_exact);
+            L.pend_pack = pack;
+            L.pend_link = link;
+            L.ptr = enter ? L.ptr + 1 : link + L.start;  // a leaf's pointer is set again after its triangles
+            L.state = enter ? (pack != -1 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
+        }
+    }
+}
+
+template <int KIND, int MINB, int STEPS, int POLICY>
 __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R,
                                                                      const unsigned* __restrict__ order, cndl_hit* __restrict__ hits,
                                                                      float* __restrict__ any_t, unsigned* __restrict__ work_counter,
@@ -245,7 +265,12 @@ __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneVie
             const unsigned done = b0 & b1, empty = ~(b0 | b1), busy = b0 ^ b1;
             if (busy == 0u && done == 0u && drained) break;
             const int serviceable = __popc(done) + (drained ? 0 : __popc(empty));
-            if (serviceable >= idle_threshold || busy == 0u) {
+            int ks = idle_threshold;
+            if (POLICY == 1) {  // the node phase's adaptive threshold (see there)
+                const int half = (__popc(busy) + 1) >> 1;
+                ks = half < idle_threshold ? (half < 1 ? 1 : half) : idle_threshold;
+            }
+            if (serviceable >= ks || busy == 0u) {
                 if (L.state == DONE) {
                     next_entity<KIND>(s, rays, L, L.ent + 1);  // WALK again, or still DONE: the scene loop is over
                     if (L.state == DONE) {
@@ -303,7 +328,8 @@ __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneVie
         }
 
         // ---------------- node phase ----------------
-        {
+        bool run_leaves = true;
+        if (POLICY == 0) {
             const int walk0 = __popc(__ballot_sync(FULL, L.state == WALK));
             if (walk0 > 0) {
                 int park = walk0 >> 2;
@@ -312,29 +338,33 @@ __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneVie
                 do {
 #pragma unroll
                     for (int step = 0; step < STEPS; ++step) {
-                        if (L.state == WALK) {
-                            // loop header of SL:192-199 (Pointer >= 0, Iterations < 1024, range checks)
-                            if (L.iters >= 1024 || L.ptr < L.lo || L.ptr > L.hi) {
-                                L.state = DONE;
-                            } else {
-                                ++L.iters;
-                                float4 mn, mx;
-                                ldg256(s.nodes + 2 * (size_t)L.ptr, mn, mx);
-                                const int link = __float_as_int(mx.w), pack = __float_as_int(mn.w);
-                                const bool enter = enter_stackless(mn, mx, L.r, L.tmax, warp_exact);
-                                L.pend_pack = pack;
-                                L.pend_link = link;
-                                L.ptr = enter ? L.ptr + 1 : link + L.start;  // a leaf's pointer is set again after its triangles
-                                L.state = enter ? (pack != -1 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
-                            }
-                        }
+                        node_step(s, L, warp_exact);
                     }
                 } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
             }
+        } else {
+            // Parked lanes wait until enough of them can share the long triangle / service code: the node
+            // phase runs until `kl` lanes sit at a leaf, or `ks` lanes can be serviced, or nobody walks.
+            // Both thresholds shrink with the number of live rays so that the tail does not serialise.
+            const unsigned b0 = __ballot_sync(FULL, (L.state & 1) != 0), b1 = __ballot_sync(FULL, (L.state & 2) != 0);
+            int nw = __popc(b0 & ~b1), nl = __popc(b1 & ~b0);
+            const int half = (nw + nl + 1) >> 1;
+            const int kl = half < park_threshold ? (half < 1 ? 1 : half) : park_threshold;
+            const int ks = half < idle_threshold ? (half < 1 ? 1 : half) : idle_threshold;
+            const int floor_busy = 32 - (drained ? __popc(~(b0 | b1)) : 0) - ks;  // walking + at-leaf lanes at which ks are serviceable
+            while (nw > 0 && nl < kl && nw + nl > floor_busy) {
+#pragma unroll
+                for (int step = 0; step < STEPS; ++step) {
+                        node_step(s, L, warp_exact);
+                }
+                nw = __popc(__ballot_sync(FULL, L.state == WALK));
+                nl = __popc(__ballot_sync(FULL, L.state == LEAF));
+            }
+            run_leaves = nl >= kl || nw == 0;
         }
 
         // ---------------- leaf phase ----------------
-        if (L.state == LEAF) {
+        if (run_leaves && L.state == LEAF) {
             EntityResult er{-1.0f, -1, 0};
             const bool found = leaf_triangles<ANY>(s, L.pend_pack, L.r, L.tmax, er);
             if (er.tri >= 0) { L.closest = er.t; L.best_tri = er.tri; L.best_ent = L.ent; }
@@ -534,10 +564,10 @@ void launch_one(unsigned grid, unsigned block, cudaStream_t stream, const SceneV
     k<<<grid, block, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold);
 }
 
-template <int KIND, int MINB, int STEPS>
+template <int KIND, int MINB, int STEPS, int POLICY>
 void launch_one2(unsigned grid, unsigned block, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const unsigned* order,
                  cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
-    auto k = trace_ww2_stackless_kernel<KIND, MINB, STEPS>;
+    auto k = trace_ww2_stackless_kernel<KIND, MINB, STEPS, POLICY>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -557,10 +587,14 @@ void launch_variant(int variant, unsigned grid, unsigned block, cudaStream_t str
         case 4: launch_one<KIND, MINB, 4, false>(CNDL_WW_ARGS); break;
         case 9: launch_one<KIND, MINB, 1, true>(CNDL_WW_ARGS); break;
         case 10: launch_one<KIND, MINB, 2, true>(CNDL_WW_ARGS); break;
-        case 17: launch_one2<KIND, MINB, 1>(CNDL_WW_ARGS); break;
-        case 18: launch_one2<KIND, MINB, 2>(CNDL_WW_ARGS); break;
-        case 19: launch_one2<KIND, MINB, 3>(CNDL_WW_ARGS); break;
-        case 20: launch_one2<KIND, MINB, 4>(CNDL_WW_ARGS); break;
+        case 17: launch_one2<KIND, MINB, 1, 0>(CNDL_WW_ARGS); break;
+        case 18: launch_one2<KIND, MINB, 2, 0>(CNDL_WW_ARGS); break;
+        case 19: launch_one2<KIND, MINB, 3, 0>(CNDL_WW_ARGS); break;
+        case 20: launch_one2<KIND, MINB, 4, 0>(CNDL_WW_ARGS); break;
+        case 25: launch_one2<KIND, MINB, 1, 1>(CNDL_WW_ARGS); break;
+        case 26: launch_one2<KIND, MINB, 2, 1>(CNDL_WW_ARGS); break;
+        case 27: launch_one2<KIND, MINB, 3, 1>(CNDL_WW_ARGS); break;
+        case 28: launch_one2<KIND, MINB, 4, 1>(CNDL_WW_ARGS); break;
         default: launch_one<KIND, MINB, 2, false>(CNDL_WW_ARGS); break;
     }
 #undef CNDL_WW_ARGS

@@ -70,6 +70,14 @@ def test_knobs_and_modes_never_change_results(cb, ob, s260k):
         for k, val in enumerate(knobs):
             ri.set_tuning(k, val)
         assert ri.IntersectRays(rays).tobytes() == want.tobytes(), knobs
+    # the shared-memory staged kernel (hot-first derived node layout): variants 33..35, staged-node counts, CTA sizes
+    for hot, block, variant in ((2048, 1024, 34), (1, 256, 33), (511, 512, 35), (7168, 1024, 34), (100000, 256, 34)):
+        ri.set_tuning(6, hot)
+        ri.set_tuning(7, block)
+        ri.set_tuning(3, variant)
+        ri.BufferData()
+        assert ri.IntersectRays(rays).tobytes() == want.tobytes(), (hot, block, variant)
+    ri.set_tuning(3, 18)
     for chunks in (1, 3, 16):
         ri.set_tuning(4, chunks)
         assert ri.IntersectRays(rays).tobytes() == want.tobytes(), chunks

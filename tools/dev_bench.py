@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--modes", default="0,1,2")
-    ap.add_argument("--knobs", default="", help="semicolon-separated bps,leaf,idle triples for mode 2")
+    ap.add_argument("--knobs", default="", help="semicolon-separated knob lists for mode 2, in knob-id order: bps,leaf,idle,variant,chunks,stack_leaf,hot_nodes,block_threads")
     ap.add_argument("--fmt", default="stackless")
     ap.add_argument("--gpu-builder", type=int, default=-1, help="-1: oracle-built buffers; 0: GPU SAH; 1: GPU LBVH")
     ap.add_argument("--presort", type=int, default=0, help="host-side Morton sort of the diffuse rays (experiment)")
@@ -93,6 +93,8 @@ def main():
             if knobs:
                 for kid, val in enumerate(knobs):
                     ri.set_tuning(kid, val)
+                if len(knobs) > 6:
+                    ri.BufferData()     # the staged-node count takes effect at commit
             for _ in range(3):
                 ri.intersect_closest_device(dr.data_ptr(), n, d_hits.data_ptr(), 0, stream)
             torch.cuda.synchronize()
