@@ -136,28 +136,43 @@ int check_ready(cndl_ctx* ctx) {
     return CNDL_OK;
 }
 
-// Enqueues one traversal batch on `st`.
-int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cndl_hit* d_hits, float* d_any, unsigned* d_counter,
-                  cudaStream_t st) {
+// Enqueues one traversal batch on `st`.  scratch: 16 unsigned ints ([0] work counter, [8..15] octant counts);
+// order_region: 8 * R unsigned ints, used when ray bucketing is on.
+int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cndl_hit* d_hits, float* d_any, unsigned* scratch,
+                  unsigned* order_region, cudaStream_t st) {
     if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 rays in one call");
     const SceneView s = scene_view(ctx);
     const bool stack = ctx->format == CNDL_STACK;
     if (ctx->mode == 0 || (stack && ctx->mode == 1)) launch_trace_simple(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, st, ctx->launches);
-    else if (stack)
-        launch_trace_ww_stack(s, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, ctx->knobs[CNDL_KNOB_STACK_LEAF_THRESHOLD],
-                              ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD], st, ctx->launches);
-    else if (ctx->mode == 2 && ctx->knobs[CNDL_KNOB_VARIANT] >= 32 && ctx->hot_ready && ctx->hot_entities_ok) {
-        HotView hv;
-        hv.nodes2 = static_cast<const float4*>(ctx->nodes2.p);
-        hv.ents2 = static_cast<const cndl_entity*>(ctx->ents2.p);
-        hv.n_hot = ctx->n_hot;
-        launch_trace_hot(s, hv, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCK_THREADS],
-                         ctx->knobs[CNDL_KNOB_LEAF_THRESHOLD], ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD], ctx->knobs[CNDL_KNOB_VARIANT] - 32, st, ctx->launches);
-    } else if (ctx->mode == 2)
-        launch_trace_ww(s, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM],
-                        ctx->knobs[CNDL_KNOB_LEAF_THRESHOLD], ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD],
-                        ctx->knobs[CNDL_KNOB_VARIANT] >= 32 ? ctx->knobs[CNDL_KNOB_VARIANT] - 16 : ctx->knobs[CNDL_KNOB_VARIANT], st, ctx->launches);
-    else launch_trace_persistent(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, d_counter, ctx->sm_count, st, ctx->launches);
+    else if (ctx->mode == 1) launch_trace_persistent(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, scratch, ctx->sm_count, st, ctx->launches);
+    else {
+        RayOrder order{nullptr, nullptr, 0};
+        if (ctx->sort_rays && order_region && R >= 65536) {
+            launch_octant_partition(d_rays, R, order_region, scratch + 8, st, ctx->launches);
+            order = RayOrder{order_region, scratch + 8, (unsigned)R};
+        }
+        const int variant = ctx->knobs[CNDL_KNOB_VARIANT];
+        int steps = variant & 7;
+        if (steps < 1 || steps > 4) steps = 2;
+        const int park = ctx->knobs[stack ? CNDL_KNOB_STACK_LEAF_THRESHOLD : CNDL_KNOB_LEAF_THRESHOLD], idle = ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD];
+        if (stack) {
+            launch_trace_ww_stack(s, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, park, idle, steps, st, ctx->launches);
+        } else if (variant >= 32 && ctx->hot_ready && ctx->hot_entities_ok) {
+            HotView hv;
+            hv.nodes2 = static_cast<const float4*>(ctx->nodes2.p);
+            hv.ents2 = static_cast<const cndl_entity*>(ctx->ents2.p);
+            hv.n_hot = ctx->n_hot;
+            if (variant >= 40)
+                launch_trace_pair(s, hv, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM], park, idle, steps,
+                                  st, ctx->launches);
+            else
+                launch_trace_hot(s, hv, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCK_THREADS], park, idle, steps,
+                                 st, ctx->launches);
+        } else {
+            launch_trace_ww(s, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM], park, idle, steps, st,
+                            ctx->launches);
+        }
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return ctx->cuda_fail(e, "traversal launch");
     return CNDL_OK;
@@ -473,7 +488,9 @@ int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t 
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     const int kind = (flags & CNDL_IGNORE_TRANSPARENT) ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST;
-    return enqueue_trace(ctx, kind, d_rays, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), static_cast<cudaStream_t>(stream));
+    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(8 * R * sizeof(unsigned)));
+    return enqueue_trace(ctx, kind, d_rays, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), static_cast<unsigned*>(ctx->d_order.p),
+                         static_cast<cudaStream_t>(stream));
 }
 
 int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, float* d_t_out, void* stream) {
@@ -482,7 +499,9 @@ int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, f
     int rc = check_ready(ctx);
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
-    return enqueue_trace(ctx, Q_ANY, d_rays, R, nullptr, d_t_out, static_cast<unsigned*>(ctx->d_counter.p), static_cast<cudaStream_t>(stream));
+    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(8 * R * sizeof(unsigned)));
+    return enqueue_trace(ctx, Q_ANY, d_rays, R, nullptr, d_t_out, static_cast<unsigned*>(ctx->d_counter.p), static_cast<unsigned*>(ctx->d_order.p),
+                         static_cast<cudaStream_t>(stream));
 }
 
 // Host-buffer queries: the batch is cut into chunks that rotate over three streams, so the
@@ -508,6 +527,7 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
         ctx->events.push_back(e);
     }
     CK(ctx->d_chunk_counters.ensure_scratch(n_chunks * 64));
+    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(8 * R * sizeof(unsigned)));
     size_t k = 0;
     for (size_t lo = 0; lo < R; lo += chunk, ++k) {
         const size_t n = R - lo < chunk ? R - lo : chunk;
@@ -518,7 +538,8 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
         CK(cudaStreamWaitEvent(ctx->streams[1], ctx->events[2 * k], 0));
         unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->d_chunk_counters.p) + 64 * k);
         rc = enqueue_trace(ctx, kind, dr, n, kind == Q_ANY ? nullptr : reinterpret_cast<cndl_hit*>(dout),
-                           kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter, ctx->streams[1]);
+                           kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter,
+                           ctx->sort_rays ? static_cast<unsigned*>(ctx->d_order.p) + 8 * lo : nullptr, ctx->streams[1]);
         if (rc != CNDL_OK) return rc;
         CK(cudaEventRecord(ctx->events[2 * k + 1], ctx->streams[1]));
         CK(cudaStreamWaitEvent(ctx->streams[2], ctx->events[2 * k + 1], 0));
@@ -557,7 +578,7 @@ int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const
     }
     launch_primary_rays(inv_view, inv_proj, W, H, dr, st, ctx->launches);
     CK(cudaGetLastError());
-    return enqueue_trace(ctx, Q_CLOSEST, dr, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), st);
+    return enqueue_trace(ctx, Q_CLOSEST, dr, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), nullptr, st);  // camera rays are coherent already
 }
 
 int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H, cndl_hit* hits,

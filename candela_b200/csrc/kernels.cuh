@@ -24,13 +24,15 @@ void launch_trace_persistent(const SceneView& s, bool stack, int kind, const cnd
                              cndl_hit* hits, float* any_t, unsigned* work_counter, int sm_count, cudaStream_t stream,
                              LaunchCounter& lc);
 
-// Mode 2: persistent while-while traversal with postponed leaf tests and batched retire/refill (stackless only).
-void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits, float* any_t,
-                     unsigned* work_counter, int sm_count, int blocks_per_sm, int leaf_threshold, int idle_threshold, int variant, cudaStream_t stream,
+// Mode 2: persistent while-while traversal with postponed leaf tests and a batched service phase (kernels_wavefront.cu).
+void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
+                     unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, cudaStream_t stream,
                      LaunchCounter& lc);
-
-void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits, float* any_t,
-                           unsigned* work_counter, int sm_count, int leaf_threshold, int idle_threshold, cudaStream_t stream, LaunchCounter& lc);
+void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
+                           unsigned* work_counter, int sm_count, int park_threshold, int idle_threshold, int steps, cudaStream_t stream,
+                           LaunchCounter& lc);
+// Buckets the ray indices by direction octant: buckets[o * R + k], counts[o] (8 counters, zeroed here).
+void launch_octant_partition(const cndl_ray* rays, size_t R, unsigned* buckets, unsigned* counts, cudaStream_t stream, LaunchCounter& lc);
 
 // Camera rays of the primary kernel (Intersectors/TraverseBVHStack.glsl:133-138,:414-431).
 void launch_primary_rays(const float* inv_view16, const float* inv_proj16, int W, int H, cndl_ray* rays, cudaStream_t stream,
@@ -57,8 +59,13 @@ size_t hot_scratch_ints(size_t N, int n_objects);
 cudaError_t derive_hot_layout(const float4* nodes, size_t N, const int2* d_objects, const int2* h_objects, int n_objects, size_t n_tris, int H,
                               float4* nodes2, int* perm, int* scratch, int* h_roots_out, int* h_n_hot, int* h_invalid, cudaStream_t st,
                               LaunchCounter& lc);
-void launch_trace_hot(const SceneView& s, const HotView& hv, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits,
+void launch_trace_hot(const SceneView& s, const HotView& hv, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits,
                       float* any_t, unsigned* work_counter, int sm_count, int block_threads, int park_threshold, int idle_threshold, int steps,
                       cudaStream_t stream, LaunchCounter& lc);
+
+// Two rays per lane over the derived layout (kernels_hot.cu).
+void launch_trace_pair(const SceneView& s, const HotView& hv, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits,
+                       float* any_t, unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps,
+                       cudaStream_t stream, LaunchCounter& lc);
 
 }  // namespace cndl

@@ -217,7 +217,7 @@ template <int KIND, int BLOCK, int STEPS>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kernel(SceneView s, const float4* __restrict__ nodes2,
                                                                                 const cndl_entity* __restrict__ ents2, int n_hot,
                                                                                 const cndl_ray* __restrict__ rays, unsigned R,
-                                                                                const unsigned* __restrict__ order, cndl_hit* __restrict__ hits,
+                                                                                RayOrder order, cndl_hit* __restrict__ hits,
                                                                                 float* __restrict__ any_t, unsigned* __restrict__ work_counter,
                                                                                 int park_threshold, int idle_threshold) {
     constexpr bool ANY = KIND == Q_ANY;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
                     if (L.state == EMPTY) {
                         const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
                         if (slot < R) {
-                            L.rid = order ? __ldg(order + slot) : slot;
+                            L.rid = ray_of_slot(order, slot);
                             L.closest = -1.0f;
                             L.best_tri = -1;
                             L.best_ent = -1;
@@ -342,9 +342,265 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TWO RAYS PER LANE.  The second-generation kernel is latency bound (ncu: 50 % of the warp stall
+// samples are long-scoreboard waits on the node load, issue slots 59 % busy, 32 warps per SM at
+// 62 registers).  Here every lane walks two independent rays over the derived layout:
+//   * a node step issues both rays' node loads back to back and then both box tests, in one
+//     straight-line block (idle slots load node 0 and discard it), so twice as many loads are in
+//     flight per warp and the two dependency chains fill each other's fixed-latency gaps;
+//   * the long phases (triangles, next entity / retire / refill) run once per outer iteration on a
+//     MERGED row: each lane contributes whichever of its two slots needs the phase, so sparse
+//     per-slot work packs into fewer, fuller passes.
+// The per-ray operation sequence is unchanged: results stay bit-identical.
+struct PSlot {
+    V3 o, d, inv;  // object-space ray of the entity being traversed
+    float tmax;
+    int ptr, iters, ent, best_tri, best_ent, pend_pack, pend_link;
+    unsigned rid;
+    int state;
+};
+
+__device__ __forceinline__ bool slot_needs_exact(const PSlot& S) {
+    return (S.state == WALK || S.state == LEAF) && !(finite3(S.o) && finite3(S.inv));
+}
+
+template <int KIND>
+__device__ __forceinline__ void pair_next_entity(const SceneView& s, const cndl_entity* __restrict__ ents2, const cndl_ray* __restrict__ rays, PSlot& S,
+                                                 int from) {
+    int e = from;
+    while (e < s.n_ents) {
+        const cndl_entity* ent = ents2 + e;
+        if (KIND == Q_CLOSEST_IGNORE_TRANSPARENT && __int_as_float(__ldg(&ent->data[1])) < 0.99f) { ++e; continue; }
+        const float4* rp = reinterpret_cast<const float4*>(rays + S.rid);
+        const float4 a = __ldg(rp), b = __ldg(rp + 1);
+        const RayState r = to_object_space(ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
+        S.o = r.o; S.d = r.d; S.inv = r.inv;
+        S.ptr = __ldg(&ent->node_offset);
+        S.iters = 0;
+        S.ent = e;
+        S.state = S.ptr >= 0 ? WALK : DONE;
+        return;
+    }
+    S.state = DONE;
+    S.ent = 0x3FFFFFFF;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void pair_step(const float4* __restrict__ nodes2, PSlot& A, PSlot& B) {
+    const bool actA = A.state == WALK && A.iters < 1024, actB = B.state == WALK && B.iters < 1024;  // SL:192
+    float4 amn, amx, bmn, bmx;
+    ldg256(nodes2 + 2 * (size_t)(actA ? A.ptr : 0), amn, amx);
+    ldg256(nodes2 + 2 * (size_t)(actB ? B.ptr : 0), bmn, bmx);
+    {
+        const int word = __float_as_int(amn.w), link = __float_as_int(amx.w);
+        const RayState r{A.o, A.d, A.inv, false};
+        const bool enter = enter_stackless(amn, amx, r, A.tmax, EXACT);
+        const int nstate = enter ? (word >= 0 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
+        const int nptr = enter ? ~word : link;
+        A.state = actA ? nstate : (A.state == WALK ? DONE : A.state);  // a walker that is not active hit the iteration cap
+        A.ptr = actA ? nptr : A.ptr;
+        A.pend_pack = actA ? word : A.pend_pack;
+        A.pend_link = actA ? link : A.pend_link;
+        A.iters += actA ? 1 : 0;
+    }
+    {
+        const int word = __float_as_int(bmn.w), link = __float_as_int(bmx.w);
+        const RayState r{B.o, B.d, B.inv, false};
+        const bool enter = enter_stackless(bmn, bmx, r, B.tmax, EXACT);
+        const int nstate = enter ? (word >= 0 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
+        const int nptr = enter ? ~word : link;
+        B.state = actB ? nstate : (B.state == WALK ? DONE : B.state);
+        B.ptr = actB ? nptr : B.ptr;
+        B.pend_pack = actB ? word : B.pend_pack;
+        B.pend_link = actB ? link : B.pend_link;
+        B.iters += actB ? 1 : 0;
+    }
+}
+
+template <int KIND, int MINB, int STEPS>
+__global__ void __launch_bounds__(128, MINB) trace_pair_stackless_kernel(SceneView s, const float4* __restrict__ nodes2,
+                                                                      const cndl_entity* __restrict__ ents2, const cndl_ray* __restrict__ rays,
+                                                                      unsigned R, RayOrder order, cndl_hit* __restrict__ hits,
+                                                                      float* __restrict__ any_t, unsigned* __restrict__ work_counter,
+                                                                      int park_threshold, int idle_threshold) {
+    constexpr bool ANY = KIND == Q_ANY;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    PSlot A, B;
+    A.state = B.state = EMPTY;
+    A.rid = B.rid = 0;
+    A.iters = B.iters = 0;
+    A.ent = B.ent = 0;
+    A.ptr = B.ptr = 0;
+    A.best_tri = B.best_tri = -1;
+    A.best_ent = B.best_ent = -1;
+    A.pend_pack = B.pend_pack = 0;
+    A.pend_link = B.pend_link = -1;
+    A.tmax = B.tmax = 0.0f;
+    A.o = A.d = A.inv = B.o = B.d = B.inv = V3{0.0f, 0.0f, 0.0f};
+    bool drained = false;
+    bool warp_exact = false;
+
+    while (true) {
+        // ---------------- service on the merged row: next entity / retire / refill ----------------
+        {
+            const unsigned doneA = __ballot_sync(FULL, A.state == DONE), doneB = __ballot_sync(FULL, B.state == DONE);
+            const unsigned emptyA = __ballot_sync(FULL, A.state == EMPTY), emptyB = __ballot_sync(FULL, B.state == EMPTY);
+            const int busy = 64 - __popc(doneA) - __popc(doneB) - __popc(emptyA) - __popc(emptyB);
+            const int n_done = __popc(doneA) + __popc(doneB);
+            if (busy == 0 && n_done == 0 && drained) break;
+            const int serviceable = n_done + (drained ? 0 : __popc(emptyA) + __popc(emptyB));
+            if (serviceable >= idle_threshold || busy == 0) {
+                // each lane services one slot: A if it needs it, else B
+                const bool needA = A.state == DONE || (A.state == EMPTY && !drained);
+                const bool needB = B.state == DONE || (B.state == EMPTY && !drained);
+                const int sel = needA ? 0 : (needB ? 1 : -1);
+                PSlot T = sel == 1 ? B : A;
+                if (sel < 0) T.state = WALK;  // neither: take no part below
+                if (T.state == DONE) {
+                    const int last_ent = T.ent;
+                    pair_next_entity<KIND>(s, ents2, rays, T, T.ent + 1);
+                    if (T.state == DONE) {
+                        if (ANY) {
+                            any_t[T.rid] = T.best_tri >= 0 ? T.tmax : -1.0f;
+                        } else {
+                            // tail of IntersectScene (SL:300-318); TMax == ClosestT once something was accepted
+                            float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
+                            int mesh = -1;
+                            if (T.best_tri >= 0) mesh = __ldg(&s.tris[T.best_tri]).w;
+                            if (T.best_tri > 0) {
+                                V3 ro = T.o, rd = T.d;
+                                if (T.best_ent != last_ent) {
+                                    const float4* rp = reinterpret_cast<const float4*>(rays + T.rid);
+                                    const float4 a = __ldg(rp), b = __ldg(rp + 1);
+                                    const RayState r = to_object_space(ents2 + T.best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
+                                    ro = r.o; rd = r.d;
+                                }
+                                t = T.tmax;
+                                const V3 p = {fadd(ro.x, fmul(rd.x, t)), fadd(ro.y, fmul(rd.y, t)), fadd(ro.z, fmul(rd.z, t))};
+                                barycentrics(s.tri48, T.best_tri, p, u, v, w);
+                            }
+                            store_hit(hits, T.rid, t, u, v, w, mesh, T.best_tri, T.best_ent, T.iters);
+                        }
+                        T.state = EMPTY;
+                    }
+                }
+                if (!drained) {
+                    const unsigned want = __ballot_sync(FULL, sel >= 0 && T.state == EMPTY);
+                    const int n = __popc(want);
+                    unsigned base = 0;
+                    if (lane == 0 && n > 0) base = atomicAdd(work_counter, (unsigned)n);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base + (unsigned)n >= R) drained = true;
+                    if (sel >= 0 && T.state == EMPTY) {
+                        const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
+                        if (slot < R) {
+                            T.rid = ray_of_slot(order, slot);
+                            T.best_tri = -1;
+                            T.best_ent = -1;
+                            T.iters = 0;
+                            T.ent = 0;
+                            if (ANY) {
+                                const float rt = __ldg(&rays[T.rid].tmax);
+                                T.tmax = rt > 0.0f ? rt : 1000000.0f;
+                            } else {
+                                T.tmax = 1000000.0f;
+                            }
+                            pair_next_entity<KIND>(s, ents2, rays, T, 0);
+                        }
+                    }
+                }
+                if (sel == 0) A = T;
+                if (sel == 1) B = T;
+                warp_exact = __any_sync(FULL, slot_needs_exact(A) || slot_needs_exact(B));
+            }
+        }
+
+        // ---------------- node phase ----------------
+        {
+            const int walk0 = __popc(__ballot_sync(FULL, A.state == WALK)) + __popc(__ballot_sync(FULL, B.state == WALK));
+            if (walk0 > 0) {
+                int park = walk0 >> 2;
+                park = park < 1 ? 1 : (park > park_threshold ? park_threshold : park);
+                const int min_walk = walk0 - park + 1;  // >= 1
+                if (!warp_exact) {
+                    do {
+#pragma unroll
+                        for (int step = 0; step < STEPS; ++step) pair_step<false>(nodes2, A, B);
+                    } while (__popc(__ballot_sync(FULL, A.state == WALK)) + __popc(__ballot_sync(FULL, B.state == WALK)) >= min_walk);
+                } else {
+                    do {
+                        pair_step<true>(nodes2, A, B);
+                    } while (__popc(__ballot_sync(FULL, A.state == WALK)) + __popc(__ballot_sync(FULL, B.state == WALK)) >= min_walk);
+                }
+            }
+        }
+
+        // ---------------- leaf phase on the merged row ----------------
+        {
+            const int sel = A.state == LEAF ? 0 : (B.state == LEAF ? 1 : -1);
+            if (sel >= 0) {
+                const bool b = sel == 1;
+                const RayState r{b ? B.o : A.o, b ? B.d : A.d, b ? B.inv : A.inv, false};
+                float tmax = b ? B.tmax : A.tmax;
+                const int pack = b ? B.pend_pack : A.pend_pack, link = b ? B.pend_link : A.pend_link;
+                EntityResult er{-1.0f, -1, 0};
+                const bool found = leaf_triangles<ANY>(s, pack, r, tmax, er);
+                int nstate = link < 0 ? DONE : WALK;
+                int nent = b ? B.ent : A.ent;
+                const int cur_ent = nent;
+                if (ANY && found) {  // SL:567-569: the scene loop returns the first T > 0
+                    nstate = DONE;
+                    nent = 0x3FFFFFFF;
+                }
+                if (!b) {
+                    A.tmax = tmax; A.ptr = link; A.state = nstate; A.ent = nent;
+                    if (er.tri >= 0) { A.best_tri = er.tri; A.best_ent = cur_ent; }
+                } else {
+                    B.tmax = tmax; B.ptr = link; B.state = nstate; B.ent = nent;
+                    if (er.tri >= 0) { B.best_tri = er.tri; B.best_ent = cur_ent; }
+                }
+            }
+        }
+    }
+}
+
+template <int KIND, int MINB>
+void launch_pair_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const HotView& hv, const cndl_ray* rays, unsigned R,
+                       const RayOrder& order, cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
+#define CNDL_PAIR_LAUNCH(STEPS)                                                                                  \
+    {                                                                                                            \
+        auto k = trace_pair_stackless_kernel<KIND, MINB, STEPS>;                                                 \
+        static bool configured = false;                                                                          \
+        if (!configured) {                                                                                       \
+            cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0);                          \
+            configured = true;                                                                                   \
+        }                                                                                                        \
+        k<<<grid, 128, 0, stream>>>(s, hv.nodes2, hv.ents2, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); \
+    }
+    switch (steps) {
+        case 1: CNDL_PAIR_LAUNCH(1) break;
+        case 3: CNDL_PAIR_LAUNCH(3) break;
+        default: CNDL_PAIR_LAUNCH(2) break;
+    }
+#undef CNDL_PAIR_LAUNCH
+}
+
+template <int MINB>
+void launch_pair_kind(int kind, int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const HotView& hv, const cndl_ray* rays, unsigned R,
+                      const RayOrder& order, cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
+    switch (kind) {
+        case Q_CLOSEST: launch_pair_steps<Q_CLOSEST, MINB>(steps, grid, stream, s, hv, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        case Q_CLOSEST_IGNORE_TRANSPARENT: launch_pair_steps<Q_CLOSEST_IGNORE_TRANSPARENT, MINB>(steps, grid, stream, s, hv, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        default: launch_pair_steps<Q_ANY, MINB>(steps, grid, stream, s, hv, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+    }
+}
+
 template <int KIND, int BLOCK, int STEPS>
 void launch_hot_one(unsigned grid, size_t smem, cudaStream_t stream, const SceneView& s, const HotView& hv, const cndl_ray* rays, unsigned R,
-                    const unsigned* order, cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
+                    const RayOrder& order, cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
     auto k = trace_hot_stackless_kernel<KIND, BLOCK, STEPS>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -360,7 +616,7 @@ void launch_hot_one(unsigned grid, size_t smem, cudaStream_t stream, const Scene
 
 template <int KIND, int BLOCK>
 void launch_hot_steps(int steps, unsigned grid, size_t smem, cudaStream_t stream, const SceneView& s, const HotView& hv, const cndl_ray* rays,
-                      unsigned R, const unsigned* order, cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold,
+                      unsigned R, const RayOrder& order, cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold,
                       int idle_threshold) {
 #define CNDL_HOT_ARGS grid, smem, stream, s, hv, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold
     switch (steps) {
@@ -373,7 +629,7 @@ void launch_hot_steps(int steps, unsigned grid, size_t smem, cudaStream_t stream
 
 template <int BLOCK>
 void launch_hot_kind(int kind, int steps, unsigned grid, size_t smem, cudaStream_t stream, const SceneView& s, const HotView& hv,
-                     const cndl_ray* rays, unsigned R, const unsigned* order, cndl_hit* hits, float* any_t, unsigned* work_counter,
+                     const cndl_ray* rays, unsigned R, const RayOrder& order, cndl_hit* hits, float* any_t, unsigned* work_counter,
                      int park_threshold, int idle_threshold) {
 #define CNDL_HOT_ARGS steps, grid, smem, stream, s, hv, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold
     switch (kind) {
@@ -429,7 +685,7 @@ cudaError_t derive_hot_layout(const float4* nodes, size_t N, const int2* d_objec
 
 size_t hot_scratch_ints(size_t N, int n_objects) { return 16 + 2 * 8192 + 2 * N + (N / 2048 + 8) + (size_t)n_objects + 16; }
 
-void launch_trace_hot(const SceneView& s, const HotView& hv, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits,
+void launch_trace_hot(const SceneView& s, const HotView& hv, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits,
                       float* any_t, unsigned* work_counter, int sm_count, int block_threads, int park_threshold, int idle_threshold, int steps,
                       cudaStream_t stream, LaunchCounter& lc) {
     if (R == 0) return;
@@ -448,6 +704,21 @@ void launch_trace_hot(const SceneView& s, const HotView& hv, int kind, const cnd
     else if (block == 512) launch_hot_kind<512>(CNDL_HOT_ARGS);
     else launch_hot_kind<256>(CNDL_HOT_ARGS);
 #undef CNDL_HOT_ARGS
+    lc.n++;
+}
+
+void launch_trace_pair(const SceneView& s, const HotView& hv, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits,
+                       float* any_t, unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps,
+                       cudaStream_t stream, LaunchCounter& lc) {
+    if (R == 0) return;
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned), stream);
+    unsigned grid = (unsigned)(sm_count * blocks_per_sm);
+    const unsigned need = (unsigned)((R + 255) / 256);  // 128 lanes x 2 rays
+    if (grid > need) grid = need;
+    // register budget follows the requested residency: 4 CTAs/SM -> 128 regs, 5 -> 96, 6 -> 80
+    if (blocks_per_sm <= 4) launch_pair_kind<4>(kind, steps, grid, stream, s, hv, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
+    else if (blocks_per_sm <= 5) launch_pair_kind<5>(kind, steps, grid, stream, s, hv, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
+    else launch_pair_kind<6>(kind, steps, grid, stream, s, hv, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
     lc.n++;
 }
 

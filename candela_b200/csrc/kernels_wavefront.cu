@@ -1,16 +1,28 @@
-// Mode 2: persistent warps, "while-while" stackless traversal with postponed leaf tests and
-// batched retire/refill (after Aila & Laine's persistent while-while, adapted to the threaded
-// stackless walk of …/Include/TraverseBVHStackless.glsl:175-278).
+// Mode 2: persistent warps, "while-while" traversal with postponed leaf tests and a batched
+// service phase (after Aila & Laine's persistent while-while, adapted to the threaded stackless
+// walk of …/Include/TraverseBVHStackless.glsl:175-278 and to the stack walk of
+// …/Include/TraverseBVHStack.glsl:168-324).
 //
 // Per ray the sequence of node visits, box tests, triangle tests and TMax updates is exactly the
-// reference's; only the interleaving BETWEEN rays of a warp changes:
-//   * node phase   : lanes that are walking take node steps; a lane that enters a leaf parks
-//                    (it cannot go on before its triangles are tested: TMax feeds the next box test);
-//   * leaf phase   : runs when enough lanes are parked, so the long triangle path executes with many
-//                    lanes active instead of one or two per iteration;
-//   * retire/refill: finished rays park too; barycentrics + hit store + fetching fresh rays run for
-//                    a batch of lanes at once, from a global counter (one atomic per refill).
+// reference's; only the interleaving BETWEEN the rays of a warp changes.  Every lane owns one ray
+// as a small state machine {EMPTY, WALK, LEAF, DONE}:
+//   * node phase   : walking lanes take node steps.  A step is branch-free (next pointer and next
+//                    state are selected, not branched on).  A lane that enters a leaf parks (LEAF):
+//                    it cannot go on before its triangles are tested, because TMax feeds the next
+//                    box test.  A lane whose walk of the current entity ends parks as DONE.
+//                    One ballot per vote round: the phase runs until a quarter (at most
+//                    `park_threshold`) of the lanes that were walking at its start have parked, so
+//                    the tail of a batch does not serialise behind its last long rays.
+//   * leaf phase   : the long triangle path runs for all parked lanes at once.
+//   * service phase: runs when `idle_threshold` lanes are DONE or EMPTY: moving on to the next
+//                    entity (matrix loads, object-space ray, three IEEE divisions), or retiring the
+//                    ray (barycentrics + hit store), then fetching fresh rays from a global counter
+//                    (one atomic per warp).
 // Nodes are fetched with one 256-bit load (LDG.E.256) per visit: a FlattenedNode is one 32 B sector.
+//
+// History (profiles/r1_experiments.md): the first version tested three thresholds per vote round
+// (36 of ~150 warp instructions per round) and branched on enter / miss-link, which ran both sides
+// with half the lanes each; removing both took the diffuse batch from 0.97 to 0.78 ms.
 #include "kernels.cuh"
 
 namespace cndl {
@@ -18,6 +30,8 @@ namespace cndl {
 namespace {
 
 enum LaneState : int { EMPTY = 0, WALK = 1, LEAF = 2, DONE = 3 };
+constexpr int NO_MORE_ENTITIES = 0x3FFFFFFF;
+constexpr unsigned FULL = 0xFFFFFFFFu;
 
 __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -25,17 +39,38 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
                  : "l"(p));
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 __device__ __forceinline__ void store_hit(cndl_hit* __restrict__ hits, size_t i, float t, float u, float v, float w, int mesh, int tri, int ent, int iters) {
     float4* p = reinterpret_cast<float4*>(hits + i);
     p[0] = make_float4(t, u, v, w);
     reinterpret_cast<int4*>(p)[1] = make_int4(mesh, tri, ent, iters);
 }
 
+// tail of IntersectScene (SL:300-318 / ST:347-365): `closest` is TMax after the last acceptance
+__device__ __forceinline__ void retire_closest(const SceneView& s, const cndl_ray* __restrict__ rays, cndl_hit* __restrict__ hits, unsigned rid,
+                                               const RayState& cur, int cur_ent, float closest, int best_tri, int best_ent, int iters) {
+    float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
+    int mesh = -1;
+    if (best_tri >= 0) mesh = __ldg(&s.tris[best_tri]).w;
+    if (best_tri > 0) {  // ClosestT > 0 && TriangleIdx > 0: global triangle 0 reports as a miss
+        RayState r = cur;
+        if (best_ent != cur_ent) {
+            const float4* rp = reinterpret_cast<const float4*>(rays + rid);
+            const float4 a = __ldg(rp), b = __ldg(rp + 1);
+            r = to_object_space(s.ents + best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
+        }
+        t = closest;
+        const V3 p = {fadd(r.o.x, fmul(r.d.x, t)), fadd(r.o.y, fmul(r.d.y, t)), fadd(r.o.z, fmul(r.d.z, t))};
+        barycentrics(s.tri48, best_tri, p, u, v, w);
+    }
+    store_hit(hits, rid, t, u, v, w, mesh, best_tri, best_ent, iters);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stackless format
+
 struct WLane {
     RayState r;          // object-space ray of the entity being traversed
-    float tmax, closest;
+    float tmax;          // TMax; equals the closest accepted t once best_tri >= 0
     int ptr, start, lo, hi, iters, ent;  // lo..hi: pointers the loop header admits (SL:196)
     int best_tri, best_ent;
     int pend_pack, pend_link;
@@ -43,7 +78,7 @@ struct WLane {
     int state;
 };
 
-// Scene loop bookkeeping (SL:290-301 / :333-337): move to the next entity to traverse, or finish the ray.
+// Scene loop bookkeeping (SL:290-301 / :333-337): start on the next entity to traverse, or stay DONE.
 template <int KIND>
 __device__ __forceinline__ void next_entity(const SceneView& s, const cndl_ray* __restrict__ rays, WLane& L, int from) {
     int e = from;
@@ -66,158 +101,8 @@ __device__ __forceinline__ void next_entity(const SceneView& s, const cndl_ray* 
     L.state = DONE;
 }
 
-template <int KIND, int MINB, int STEPS, bool PREFETCH>
-__global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R,
-                                                                    const unsigned* __restrict__ order, cndl_hit* __restrict__ hits,
-                                                                    float* __restrict__ any_t, unsigned* __restrict__ work_counter,
-                                                                    int leaf_threshold, int idle_threshold) {
-    constexpr bool ANY = KIND == Q_ANY;
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    const unsigned lane = threadIdx.x & 31u;
-    WLane L;
-    L.state = EMPTY;
-    L.rid = 0;
-    L.iters = 0;
-    L.ent = 0;
-    L.best_tri = -1;
-    L.best_ent = -1;
-    L.closest = -1.0f;
-    bool drained = false;
-
-    while (true) {
-        // ---------------- retire finished rays, fetch fresh ones ----------------
-        {
-            const unsigned done = __ballot_sync(FULL, L.state == DONE);
-            const unsigned empty = __ballot_sync(FULL, L.state == EMPTY);
-            const unsigned busy = ~(done | empty);
-            const int serviceable = __popc(done) + (drained ? 0 : __popc(empty));
-            if (busy == 0u && done == 0u && drained) break;
-            if (serviceable >= idle_threshold || busy == 0u) {
-                if (L.state == DONE) {
-                    if (ANY) {
-                        any_t[L.rid] = L.closest;
-                    } else {
-                        // tail of IntersectScene (SL:300-318)
-                        float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
-                        int mesh = -1;
-                        if (L.best_tri >= 0) mesh = __ldg(&s.tris[L.best_tri]).w;
-                        if (L.closest > 0.0f && L.best_tri > 0) {
-                            RayState r = L.r;
-                            if (L.best_ent != L.ent) {
-                                const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
-                                const float4 a = __ldg(rp), b = __ldg(rp + 1);
-                                r = to_object_space(s.ents + L.best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
-                            }
-                            const V3 p = {fadd(r.o.x, fmul(r.d.x, L.closest)), fadd(r.o.y, fmul(r.d.y, L.closest)), fadd(r.o.z, fmul(r.d.z, L.closest))};
-                            t = L.closest;
-                            barycentrics(s.tri48, L.best_tri, p, u, v, w);
-                        }
-                        store_hit(hits, L.rid, t, u, v, w, mesh, L.best_tri, L.best_ent, L.iters);
-                    }
-                    L.state = EMPTY;
-                }
-                if (!drained) {
-                    const unsigned want = __ballot_sync(FULL, L.state == EMPTY);
-                    const int n = __popc(want);
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(work_counter, (unsigned)n);
-                    base = __shfl_sync(FULL, base, 0);
-                    if (base + (unsigned)n >= R) drained = true;
-                    if (L.state == EMPTY) {
-                        const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
-                        if (slot < R) {
-                            L.rid = order ? __ldg(order + slot) : slot;
-                            L.closest = -1.0f;
-                            L.best_tri = -1;
-                            L.best_ent = -1;
-                            L.iters = 0;
-                            L.ent = 0;
-                            if (ANY) {
-                                const float rt = __ldg(&rays[L.rid].tmax);
-                                L.tmax = rt > 0.0f ? rt : 1000000.0f;
-                            } else {
-                                L.tmax = 1000000.0f;
-                            }
-                            next_entity<KIND>(s, rays, L, 0);
-                        }
-                    }
-                }
-            }
-        }
-
-        // ---------------- node phase ----------------
-        while (true) {
-            // lane states are two bits: two ballots give all four masks
-            const unsigned b0 = __ballot_sync(FULL, (L.state & 1) != 0), b1 = __ballot_sync(FULL, (L.state & 2) != 0);
-            const unsigned walking = b0 & ~b1;
-            if (walking == 0u) break;
-            if (__popc(b1 & ~b0) >= leaf_threshold) break;                                  // parked at a leaf
-            if (__popc(b0 & b1) + (drained ? 0 : __popc(~(b0 | b1))) >= idle_threshold) break;  // finished / empty
-#pragma unroll
-            for (int step = 0; step < STEPS; ++step) {
-                if (L.state == WALK) {
-                    // loop header of SL:192-199 (Pointer >= 0, Iterations < 1024, range checks)
-                    if (L.iters >= 1024 || L.ptr < L.lo || L.ptr > L.hi) {
-                        next_entity<KIND>(s, rays, L, L.ent + 1);
-                    } else {
-                        ++L.iters;
-                        float4 mn, mx;
-                        ldg256(s.nodes + 2 * (size_t)L.ptr, mn, mx);
-                        const int link = __float_as_int(mx.w);
-                        if (enter_stackless(mn, mx, L.r, L.tmax)) {
-                            const int pack = __float_as_int(mn.w);
-                            if (pack != -1) {
-                                L.pend_pack = pack;
-                                L.pend_link = link;
-                                L.state = LEAF;
-                            } else {
-                                ++L.ptr;
-                            }
-                        } else if (link < 0) {
-                            next_entity<KIND>(s, rays, L, L.ent + 1);
-                        } else {
-                            L.ptr = link + L.start;
-                        }
-                    }
-                }
-            }
-            // the vote round separates this step from the next load: start fetching the next node now
-            if (PREFETCH && L.state == WALK) prefetch_l1(s.nodes + 2 * (size_t)L.ptr);
-        }
-
-        // ---------------- leaf phase ----------------
-        if (L.state == LEAF) {
-            EntityResult er{-1.0f, -1, 0};
-            const bool found = leaf_triangles<ANY>(s, L.pend_pack, L.r, L.tmax, er);
-            if (er.tri >= 0) { L.closest = er.t; L.best_tri = er.tri; L.best_ent = L.ent; }
-            if (ANY && found) {
-                L.state = DONE;  // SL:567-569: the scene loop returns the first T > 0
-            } else if (L.pend_link < 0) {
-                next_entity<KIND>(s, rays, L, L.ent + 1);
-            } else {
-                L.ptr = L.pend_link + L.start;
-                L.state = WALK;
-            }
-        }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Second generation of the stackless while-while kernel.  Same per-ray sequence of operations;
-// what changed is what the WARP executes around it (ncu source counters of the first version:
-// 36 of ~150 warp instructions per vote round were the three-way threshold test, and the
-// enter / miss-link sides of each node step ran one after the other with half the lanes each):
-//   * a node step is branch-free: next pointer and next state are selected, never branched on;
-//   * DONE means "this entity is finished".  Moving on to the next entity (matrix loads, the
-//     object-space ray, three IEEE divisions) happens in the batched service phase together with
-//     retiring and refilling, not inline in the node loop (three inlined copies before);
-//   * one ballot per vote round: the node phase runs until `park` of the lanes that were walking
-//     when it started have parked (at a leaf or at the end of an entity); the count adapts to the
-//     number of walkers (a quarter of them, at most `park_threshold`) so the tail of a batch does
-//     not serialise behind its last long rays.
-// One node visit of a walking lane (SL:192-246), branch-free: the next pointer and the next state are selected.
-// DONE = this entity is finished (miss link -1, or the loop header's cap / range checks fail).
+// One node visit of a walking lane (SL:192-246).  DONE = this entity is finished (miss link -1, or the
+// loop header's cap / range checks fail).
 __device__ __forceinline__ void node_step(const SceneView& s, WLane& L, bool warp_exact) {
     if (L.state == WALK) {
         if (L.iters >= 1024 || L.ptr < L.lo || L.ptr > L.hi) {  // loop header of SL:192-199
@@ -236,14 +121,11 @@ __device__ __forceinline__ void node_step(const SceneView& s, WLane& L, bool war
     }
 }
 
-template <int KIND, int MINB, int STEPS, int POLICY>
-__global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R,
-                                                                     const unsigned* __restrict__ order, cndl_hit* __restrict__ hits,
-                                                                     float* __restrict__ any_t, unsigned* __restrict__ work_counter,
-                                                                     int park_threshold, int idle_threshold) {
+template <int KIND, int MINB, int STEPS>
+__global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R, RayOrder order,
+                                                                    cndl_hit* __restrict__ hits, float* __restrict__ any_t,
+                                                                    unsigned* __restrict__ work_counter, int park_threshold, int idle_threshold) {
     constexpr bool ANY = KIND == Q_ANY;
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    constexpr int NO_MORE_ENTITIES = 0x3FFFFFFF;
     const unsigned lane = threadIdx.x & 31u;
     WLane L;
     L.state = EMPTY;
@@ -252,7 +134,6 @@ __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneVie
     L.ent = 0;
     L.best_tri = -1;
     L.best_ent = -1;
-    L.closest = -1.0f;
     L.pend_pack = 0;
     L.pend_link = -1;
     bool drained = false;
@@ -265,35 +146,12 @@ __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneVie
             const unsigned done = b0 & b1, empty = ~(b0 | b1), busy = b0 ^ b1;
             if (busy == 0u && done == 0u && drained) break;
             const int serviceable = __popc(done) + (drained ? 0 : __popc(empty));
-            int ks = idle_threshold;
-            if (POLICY == 1) {  // the node phase's adaptive threshold (see there)
-                const int half = (__popc(busy) + 1) >> 1;
-                ks = half < idle_threshold ? (half < 1 ? 1 : half) : idle_threshold;
-            }
-            if (serviceable >= ks || busy == 0u) {
+            if (serviceable >= idle_threshold || busy == 0u) {
                 if (L.state == DONE) {
                     next_entity<KIND>(s, rays, L, L.ent + 1);  // WALK again, or still DONE: the scene loop is over
                     if (L.state == DONE) {
-                        if (ANY) {
-                            any_t[L.rid] = L.closest;
-                        } else {
-                            // tail of IntersectScene (SL:300-318)
-                            float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
-                            int mesh = -1;
-                            if (L.best_tri >= 0) mesh = __ldg(&s.tris[L.best_tri]).w;
-                            if (L.closest > 0.0f && L.best_tri > 0) {
-                                RayState r = L.r;
-                                if (L.best_ent != L.ent) {
-                                    const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
-                                    const float4 a = __ldg(rp), b = __ldg(rp + 1);
-                                    r = to_object_space(s.ents + L.best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
-                                }
-                                const V3 p = {fadd(r.o.x, fmul(r.d.x, L.closest)), fadd(r.o.y, fmul(r.d.y, L.closest)), fadd(r.o.z, fmul(r.d.z, L.closest))};
-                                t = L.closest;
-                                barycentrics(s.tri48, L.best_tri, p, u, v, w);
-                            }
-                            store_hit(hits, L.rid, t, u, v, w, mesh, L.best_tri, L.best_ent, L.iters);
-                        }
+                        if (ANY) any_t[L.rid] = L.best_tri >= 0 ? L.tmax : -1.0f;
+                        else retire_closest(s, rays, hits, L.rid, L.r, L.ent, L.tmax, L.best_tri, L.best_ent, L.iters);
                         L.state = EMPTY;
                     }
                 }
@@ -307,8 +165,7 @@ __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneVie
                     if (L.state == EMPTY) {
                         const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
                         if (slot < R) {
-                            L.rid = order ? __ldg(order + slot) : slot;
-                            L.closest = -1.0f;
+                            L.rid = ray_of_slot(order, slot);
                             L.best_tri = -1;
                             L.best_ent = -1;
                             L.iters = 0;
@@ -328,8 +185,7 @@ __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneVie
         }
 
         // ---------------- node phase ----------------
-        bool run_leaves = true;
-        if (POLICY == 0) {
+        {
             const int walk0 = __popc(__ballot_sync(FULL, L.state == WALK));
             if (walk0 > 0) {
                 int park = walk0 >> 2;
@@ -337,37 +193,16 @@ __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneVie
                 const int min_walk = walk0 - park + 1;  // >= 1
                 do {
 #pragma unroll
-                    for (int step = 0; step < STEPS; ++step) {
-                        node_step(s, L, warp_exact);
-                    }
+                    for (int step = 0; step < STEPS; ++step) node_step(s, L, warp_exact);
                 } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
             }
-        } else {
-            // Parked lanes wait until enough of them can share the long triangle / service code: the node
-            // phase runs until `kl` lanes sit at a leaf, or `ks` lanes can be serviced, or nobody walks.
-            // Both thresholds shrink with the number of live rays so that the tail does not serialise.
-            const unsigned b0 = __ballot_sync(FULL, (L.state & 1) != 0), b1 = __ballot_sync(FULL, (L.state & 2) != 0);
-            int nw = __popc(b0 & ~b1), nl = __popc(b1 & ~b0);
-            const int half = (nw + nl + 1) >> 1;
-            const int kl = half < park_threshold ? (half < 1 ? 1 : half) : park_threshold;
-            const int ks = half < idle_threshold ? (half < 1 ? 1 : half) : idle_threshold;
-            const int floor_busy = 32 - (drained ? __popc(~(b0 | b1)) : 0) - ks;  // walking + at-leaf lanes at which ks are serviceable
-            while (nw > 0 && nl < kl && nw + nl > floor_busy) {
-#pragma unroll
-                for (int step = 0; step < STEPS; ++step) {
-                        node_step(s, L, warp_exact);
-                }
-                nw = __popc(__ballot_sync(FULL, L.state == WALK));
-                nl = __popc(__ballot_sync(FULL, L.state == LEAF));
-            }
-            run_leaves = nl >= kl || nw == 0;
         }
 
         // ---------------- leaf phase ----------------
-        if (run_leaves && L.state == LEAF) {
+        if (L.state == LEAF) {
             EntityResult er{-1.0f, -1, 0};
             const bool found = leaf_triangles<ANY>(s, L.pend_pack, L.r, L.tmax, er);
-            if (er.tri >= 0) { L.closest = er.t; L.best_tri = er.tri; L.best_ent = L.ent; }
+            if (er.tri >= 0) { L.best_tri = er.tri; L.best_ent = L.ent; }
             L.ptr = L.pend_link + L.start;
             L.state = L.pend_link < 0 ? DONE : WALK;
             if (ANY && found) {  // SL:567-569: the scene loop returns the first T > 0
@@ -379,11 +214,11 @@ __global__ void __launch_bounds__(128, MINB) trace_ww2_stackless_kernel(SceneVie
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same scheme for the stack format (…/Include/TraverseBVHStack.glsl:168-324, :509-657).  One step
-// loads a 64-byte node (two children).  The choice of the next node (near child first, far child
-// pushed, pop when nothing is entered) uses box distances computed with TMax as it was BEFORE this
-// node's leaf children are intersected (ST:215-216), so it is taken first; the lane then parks with
-// up to two pending leaves, which the leaf phase tests left then right, exactly in the reference order.
+// The same scheme for the stack format (ST:168-324, :509-657).  One step loads a 64-byte node (two
+// children).  The choice of the next node (near child first, far child pushed, pop when nothing is
+// entered) uses box distances computed with TMax as it was BEFORE this node's leaf children are
+// intersected (ST:215-216), so it is taken first; the lane then parks with up to two pending leaves,
+// which the leaf phase tests left then right, exactly in the reference order.
 struct SLane {
     RayState r;
     float tmax;
@@ -416,13 +251,46 @@ __device__ __forceinline__ void next_entity_stack(const SceneView& s, const cndl
     L.state = DONE;
 }
 
+__device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, int* stack, bool warp_exact) {
+    if (L.state == WALK) {
+        if (L.iters >= 1024 || L.sp >= 64 || L.sp < 0 || L.cur < L.lo || L.cur > L.hi) {  // ST:198-205
+            L.state = DONE;
+        } else {
+            ++L.iters;
+            float4 lmn, lmx, rmn, rmx;
+            ldg256(s.nodes + 4 * (size_t)L.cur, lmn, lmx);
+            ldg256(s.nodes + 4 * (size_t)L.cur + 2, rmn, rmx);
+            const int lpack = __float_as_int(lmn.w), rpack = __float_as_int(rmn.w);
+            const bool lleaf = lpack != -1, rleaf = rpack != -1;
+            const float lt = lleaf ? -1.0f : slab_stack(lmn, lmx, L.r, L.tmax, warp_exact);
+            const float rt = rleaf ? -1.0f : slab_stack(rmn, rmx, L.r, L.tmax, warp_exact);
+            const int lslot = __float_as_int(lmx.w) + L.start, rslot = __float_as_int(rmx.w) + L.start;
+            const bool hl = lt > 0.0f, hr = rt > 0.0f, both = hl && hr, right_first = rt < lt;
+            int after = WALK;
+            if (both) {  // ST:280-299: near child first (ties go left), far child pushed
+                L.cur = right_first ? rslot : lslot;
+                if (L.sp >= 63) after = DONE;
+                else stack[L.sp++] = right_first ? lslot : rslot;
+            } else if (hl || hr) {
+                L.cur = hl ? lslot : rslot;
+            } else if (L.sp <= 0) {
+                after = DONE;
+            } else {
+                L.cur = stack[--L.sp];
+            }
+            L.pend_l = lleaf ? lpack : -1;
+            L.pend_r = rleaf ? rpack : -1;
+            L.after = after;
+            L.state = (lleaf || rleaf) ? LEAF : after;
+        }
+    }
+}
+
 template <int KIND, int STEPS>
-__global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R,
-                                                                const unsigned* __restrict__ order, cndl_hit* __restrict__ hits,
-                                                                float* __restrict__ any_t, unsigned* __restrict__ work_counter,
-                                                                int leaf_threshold, int idle_threshold) {
+__global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R, RayOrder order,
+                                                                cndl_hit* __restrict__ hits, float* __restrict__ any_t,
+                                                                unsigned* __restrict__ work_counter, int park_threshold, int idle_threshold) {
     constexpr bool ANY = KIND == Q_ANY;
-    constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
     int stack[64];
     SLane L;
@@ -433,36 +301,25 @@ __global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, con
     L.sp = 0;
     L.best_tri = -1;
     L.best_ent = -1;
+    L.pend_l = L.pend_r = -1;
+    L.after = WALK;
     bool drained = false;
+    bool warp_exact = false;
 
     while (true) {
-        {   // retire + refill
+        {   // service: next entity / retire / refill
             const unsigned b0 = __ballot_sync(FULL, (L.state & 1) != 0), b1 = __ballot_sync(FULL, (L.state & 2) != 0);
             const unsigned done = b0 & b1, empty = ~(b0 | b1), busy = b0 ^ b1;
-            const int serviceable = __popc(done) + (drained ? 0 : __popc(empty));
             if (busy == 0u && done == 0u && drained) break;
+            const int serviceable = __popc(done) + (drained ? 0 : __popc(empty));
             if (serviceable >= idle_threshold || busy == 0u) {
                 if (L.state == DONE) {
-                    if (ANY) {
-                        any_t[L.rid] = L.best_tri >= 0 ? L.tmax : -1.0f;
-                    } else {
-                        float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
-                        int mesh = -1;
-                        if (L.best_tri >= 0) mesh = __ldg(&s.tris[L.best_tri]).w;
-                        if (L.best_tri > 0) {  // ClosestT > 0 && TriangleIdx > 0 (ST:347)
-                            RayState r = L.r;
-                            if (L.best_ent != L.ent) {
-                                const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
-                                const float4 a = __ldg(rp), b = __ldg(rp + 1);
-                                r = to_object_space(s.ents + L.best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
-                            }
-                            t = L.tmax;  // TMax == ClosestT once something was accepted
-                            const V3 p = {fadd(r.o.x, fmul(r.d.x, t)), fadd(r.o.y, fmul(r.d.y, t)), fadd(r.o.z, fmul(r.d.z, t))};
-                            barycentrics(s.tri48, L.best_tri, p, u, v, w);
-                        }
-                        store_hit(hits, L.rid, t, u, v, w, mesh, L.best_tri, L.best_ent, L.iters);
+                    next_entity_stack<KIND>(s, rays, L, L.ent + 1);
+                    if (L.state == DONE) {
+                        if (ANY) any_t[L.rid] = L.best_tri >= 0 ? L.tmax : -1.0f;
+                        else retire_closest(s, rays, hits, L.rid, L.r, L.ent, L.tmax, L.best_tri, L.best_ent, L.iters);
+                        L.state = EMPTY;
                     }
-                    L.state = EMPTY;
                 }
                 if (!drained) {
                     const unsigned want = __ballot_sync(FULL, L.state == EMPTY);
@@ -474,7 +331,7 @@ __global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, con
                     if (L.state == EMPTY) {
                         const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
                         if (slot < R) {
-                            L.rid = order ? __ldg(order + slot) : slot;
+                            L.rid = ray_of_slot(order, slot);
                             L.best_tri = -1;
                             L.best_ent = -1;
                             L.iters = 0;
@@ -489,54 +346,19 @@ __global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, con
                         }
                     }
                 }
+                warp_exact = __any_sync(FULL, (L.state == WALK || L.state == LEAF) && L.r.nan_path);
             }
         }
-        while (true) {  // node phase
-            const unsigned b0 = __ballot_sync(FULL, (L.state & 1) != 0), b1 = __ballot_sync(FULL, (L.state & 2) != 0);
-            if ((b0 & ~b1) == 0u) break;
-            if (__popc(b1 & ~b0) >= leaf_threshold) break;
-            if (__popc(b0 & b1) + (drained ? 0 : __popc(~(b0 | b1))) >= idle_threshold) break;
+        {   // node phase
+            const int walk0 = __popc(__ballot_sync(FULL, L.state == WALK));
+            if (walk0 > 0) {
+                int park = walk0 >> 2;
+                park = park < 1 ? 1 : (park > park_threshold ? park_threshold : park);
+                const int min_walk = walk0 - park + 1;
+                do {
 #pragma unroll
-            for (int step = 0; step < STEPS; ++step) {
-                if (L.state == WALK) {
-                    if (L.iters >= 1024 || L.sp >= 64 || L.sp < 0 || L.cur < L.lo || L.cur > L.hi) {  // ST:198-205
-                        next_entity_stack<KIND>(s, rays, L, L.ent + 1);
-                    } else {
-                        ++L.iters;
-                        float4 lmn, lmx, rmn, rmx;
-                        ldg256(s.nodes + 4 * (size_t)L.cur, lmn, lmx);
-                        ldg256(s.nodes + 4 * (size_t)L.cur + 2, rmn, rmx);
-                        const int lpack = __float_as_int(lmn.w), rpack = __float_as_int(rmn.w);
-                        const bool lleaf = lpack != -1, rleaf = rpack != -1;
-                        const float lt = lleaf ? -1.0f : slab_stack(lmn, lmx, L.r, L.tmax);
-                        const float rt = rleaf ? -1.0f : slab_stack(rmn, rmx, L.r, L.tmax);
-                        const int lslot = __float_as_int(lmx.w) + L.start, rslot = __float_as_int(rmx.w) + L.start;
-                        int after = WALK;
-                        if (lt > 0.0f && rt > 0.0f) {  // ST:280-299
-                            int postponed = rslot;
-                            L.cur = lslot;
-                            if (rt < lt) { L.cur = rslot; postponed = lslot; }
-                            if (L.sp >= 63) after = DONE;
-                            else stack[L.sp++] = postponed;
-                        } else if (lt > 0.0f) {
-                            L.cur = lslot;
-                        } else if (rt > 0.0f) {
-                            L.cur = rslot;
-                        } else if (L.sp <= 0) {
-                            after = DONE;
-                        } else {
-                            L.cur = stack[--L.sp];
-                        }
-                        if (lleaf || rleaf) {
-                            L.pend_l = lleaf ? lpack : -1;
-                            L.pend_r = rleaf ? rpack : -1;
-                            L.after = after;
-                            L.state = LEAF;
-                        } else if (after == DONE) {
-                            next_entity_stack<KIND>(s, rays, L, L.ent + 1);
-                        }
-                    }
-                }
+                    for (int step = 0; step < STEPS; ++step) node_step_stack(s, L, stack, warp_exact);
+                } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
             }
         }
         if (L.state == LEAF) {  // leaf phase: left leaf, then right leaf (ST:221-277)
@@ -545,101 +367,137 @@ __global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, con
             if (L.pend_l != -1) found = leaf_triangles<ANY>(s, L.pend_l, L.r, L.tmax, er);
             if (!found && L.pend_r != -1) found = leaf_triangles<ANY>(s, L.pend_r, L.r, L.tmax, er);
             if (er.tri >= 0) { L.best_tri = er.tri; L.best_ent = L.ent; }
-            if (ANY && found) L.state = DONE;
-            else if (L.after == DONE) next_entity_stack<KIND>(s, rays, L, L.ent + 1);
-            else L.state = WALK;
+            L.state = L.after;
+            if (ANY && found) {
+                L.state = DONE;
+                L.ent = NO_MORE_ENTITIES;
+            }
         }
     }
 }
 
-template <int KIND, int MINB, int STEPS, bool PREFETCH>
-void launch_one(unsigned grid, unsigned block, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const unsigned* order,
-                cndl_hit* hits, float* any_t, unsigned* work_counter, int leaf_threshold, int idle_threshold) {
-    auto k = trace_ww_stackless_kernel<KIND, MINB, STEPS, PREFETCH>;
-    static bool configured = false;
-    if (!configured) {  // no shared memory is used: give the whole 256 KB array to L1
-        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-        configured = true;
-    }
-    k<<<grid, block, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold);
-}
+// ---------------------------------------------------------------------------------------------
+// Ray bucketing by direction octant.  With the rays of a warp sharing the signs of their direction
+// the lanes' walks stay closer together (fewer distinct 128-byte lines per warp-wide node load, which
+// is what the L1 pipe charges for): -8.7 % on the diffuse batch.  Grouping only helps globally (every
+// ray in flight in the same octant), not within chunks, because refilled lanes take the next slots.
+// One pass: a block counts its rays per octant, reserves a run in each bucket with one atomic per
+// octant, and writes the ray indices there.
+constexpr int kPartBlock = 256, kPartItems = 8;
 
-template <int KIND, int MINB, int STEPS, int POLICY>
-void launch_one2(unsigned grid, unsigned block, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const unsigned* order,
-                 cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
-    auto k = trace_ww2_stackless_kernel<KIND, MINB, STEPS, POLICY>;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-        configured = true;
+__global__ void __launch_bounds__(kPartBlock) octant_partition_kernel(const cndl_ray* __restrict__ rays, unsigned R, unsigned* __restrict__ buckets,
+                                                                      unsigned stride, unsigned* __restrict__ counts) {
+    __shared__ unsigned s_cnt[8], s_base[8], s_run[8];
+    if (threadIdx.x < 8) { s_cnt[threadIdx.x] = 0; s_run[threadIdx.x] = 0; }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned first = blockIdx.x * (kPartBlock * kPartItems);
+    unsigned oct[kPartItems];
+#pragma unroll
+    for (int j = 0; j < kPartItems; ++j) {
+        const unsigned i = first + j * kPartBlock + threadIdx.x;
+        oct[j] = 8;
+        if (i < R) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+            oct[j] = (d.x > 0.0f ? 1u : 0u) | (d.y > 0.0f ? 2u : 0u) | (d.z > 0.0f ? 4u : 0u);
+        }
+        const unsigned peers = __match_any_sync(FULL, oct[j]);
+        if (oct[j] < 8 && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_cnt[oct[j]], (unsigned)__popc(peers));
     }
-    k<<<grid, block, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
+    __syncthreads();
+    if (threadIdx.x < 8) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]) : 0u;
+    __syncthreads();
+    // the order inside a block's run follows the arrival of its warps, which is harmless: a ray's result
+    // does not depend on its slot
+#pragma unroll
+    for (int j = 0; j < kPartItems; ++j) {
+        const unsigned i = first + j * kPartBlock + threadIdx.x;
+        const unsigned peers = __match_any_sync(FULL, oct[j]);
+        unsigned off = 0;
+        const unsigned leader = (unsigned)(__ffs(peers) - 1);
+        if (oct[j] < 8 && lane == leader) off = atomicAdd(&s_run[oct[j]], (unsigned)__popc(peers));
+        off = __shfl_sync(FULL, off, leader);
+        if (oct[j] < 8) buckets[(size_t)oct[j] * stride + s_base[oct[j]] + off + (unsigned)__popc(peers & ((1u << lane) - 1u))] = i;
+    }
 }
 
 template <int KIND, int MINB>
-void launch_variant(int variant, unsigned grid, unsigned block, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R,
-                    const unsigned* order, cndl_hit* hits, float* any_t, unsigned* work_counter, int leaf_threshold, int idle_threshold) {
-    // variant = node steps per vote round (1..4), +8 to prefetch the parked leaf's triangles
-#define CNDL_WW_ARGS grid, block, stream, s, rays, R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold
-    switch (variant) {
-        case 1: launch_one<KIND, MINB, 1, false>(CNDL_WW_ARGS); break;
-        case 3: launch_one<KIND, MINB, 3, false>(CNDL_WW_ARGS); break;
-        case 4: launch_one<KIND, MINB, 4, false>(CNDL_WW_ARGS); break;
-        case 9: launch_one<KIND, MINB, 1, true>(CNDL_WW_ARGS); break;
-        case 10: launch_one<KIND, MINB, 2, true>(CNDL_WW_ARGS); break;
-        case 17: launch_one2<KIND, MINB, 1, 0>(CNDL_WW_ARGS); break;
-        case 18: launch_one2<KIND, MINB, 2, 0>(CNDL_WW_ARGS); break;
-        case 19: launch_one2<KIND, MINB, 3, 0>(CNDL_WW_ARGS); break;
-        case 20: launch_one2<KIND, MINB, 4, 0>(CNDL_WW_ARGS); break;
-        case 25: launch_one2<KIND, MINB, 1, 1>(CNDL_WW_ARGS); break;
-        case 26: launch_one2<KIND, MINB, 2, 1>(CNDL_WW_ARGS); break;
-        case 27: launch_one2<KIND, MINB, 3, 1>(CNDL_WW_ARGS); break;
-        case 28: launch_one2<KIND, MINB, 4, 1>(CNDL_WW_ARGS); break;
-        default: launch_one<KIND, MINB, 2, false>(CNDL_WW_ARGS); break;
+void launch_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const RayOrder& order,
+                  cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
+#define CNDL_WW_LAUNCH(STEPS)                                                                                     \
+    {                                                                                                             \
+        auto k = trace_ww_stackless_kernel<KIND, MINB, STEPS>;                                                    \
+        static bool configured = false;                                                                           \
+        if (!configured) { /* no shared memory is used: give the whole 256 KB array to L1 */                      \
+            cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0);                           \
+            configured = true;                                                                                    \
+        }                                                                                                         \
+        k<<<grid, 128, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); \
     }
-#undef CNDL_WW_ARGS
+    switch (steps) {
+        case 1: CNDL_WW_LAUNCH(1) break;
+        case 3: CNDL_WW_LAUNCH(3) break;
+        case 4: CNDL_WW_LAUNCH(4) break;
+        default: CNDL_WW_LAUNCH(2) break;
+    }
+#undef CNDL_WW_LAUNCH
+}
+
+template <int MINB>
+void launch_kind(int kind, int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const RayOrder& order,
+                 cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
+    switch (kind) {
+        case Q_CLOSEST: launch_steps<Q_CLOSEST, MINB>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        case Q_CLOSEST_IGNORE_TRANSPARENT: launch_steps<Q_CLOSEST_IGNORE_TRANSPARENT, MINB>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        default: launch_steps<Q_ANY, MINB>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+    }
+}
+
+template <int KIND>
+void launch_stack_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const RayOrder& order,
+                        cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
+    if (steps == 2) trace_ww_stack_kernel<KIND, 2><<<grid, 128, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
+    else trace_ww_stack_kernel<KIND, 1><<<grid, 128, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
 }
 
 }  // namespace
 
-void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits, float* any_t,
-                           unsigned* work_counter, int sm_count, int leaf_threshold, int idle_threshold, cudaStream_t stream, LaunchCounter& lc) {
+void launch_octant_partition(const cndl_ray* rays, size_t R, unsigned* buckets, unsigned* counts, cudaStream_t stream, LaunchCounter& lc) {
+    if (R == 0) return;
+    cudaMemsetAsync(counts, 0, 8 * sizeof(unsigned), stream);
+    const unsigned per_block = kPartBlock * kPartItems;
+    octant_partition_kernel<<<(unsigned)((R + per_block - 1) / per_block), kPartBlock, 0, stream>>>(rays, (unsigned)R, buckets, (unsigned)R, counts);
+    lc.n++;
+}
+
+void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
+                           unsigned* work_counter, int sm_count, int park_threshold, int idle_threshold, int steps, cudaStream_t stream,
+                           LaunchCounter& lc) {
     if (R == 0) return;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned), stream);
-    const unsigned block = 128;
-    unsigned grid = (unsigned)(sm_count * 7);
-    const unsigned need = (unsigned)((R + block - 1) / block);
+    unsigned grid = (unsigned)(sm_count * 6);
+    const unsigned need = (unsigned)((R + 127) / 128);
     if (grid > need) grid = need;
     switch (kind) {
-        case Q_CLOSEST: trace_ww_stack_kernel<Q_CLOSEST, 1><<<grid, block, 0, stream>>>(s, rays, (unsigned)R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold); break;
-        case Q_CLOSEST_IGNORE_TRANSPARENT: trace_ww_stack_kernel<Q_CLOSEST_IGNORE_TRANSPARENT, 1><<<grid, block, 0, stream>>>(s, rays, (unsigned)R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold); break;
-        default: trace_ww_stack_kernel<Q_ANY, 1><<<grid, block, 0, stream>>>(s, rays, (unsigned)R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold); break;
+        case Q_CLOSEST: launch_stack_steps<Q_CLOSEST>(steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        case Q_CLOSEST_IGNORE_TRANSPARENT: launch_stack_steps<Q_CLOSEST_IGNORE_TRANSPARENT>(steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        default: launch_stack_steps<Q_ANY>(steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
     }
     lc.n++;
 }
 
-void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const unsigned* order, cndl_hit* hits, float* any_t,
-                     unsigned* work_counter, int sm_count, int blocks_per_sm, int leaf_threshold, int idle_threshold, int variant, cudaStream_t stream,
+void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
+                     unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, cudaStream_t stream,
                      LaunchCounter& lc) {
     if (R == 0) return;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned), stream);
-    const unsigned block = 128;
     unsigned grid = (unsigned)(sm_count * blocks_per_sm);
-    const unsigned need = (unsigned)((R + block - 1) / block);
+    const unsigned need = (unsigned)((R + 127) / 128);
     if (grid > need) grid = need;
-#define CNDL_WW_LAUNCH(KIND, MINB) \
-    launch_variant<KIND, MINB>(variant, grid, block, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, leaf_threshold, idle_threshold)
-#define CNDL_WW_KIND(MINB)                                                                  \
-    switch (kind) {                                                                         \
-        case Q_CLOSEST: CNDL_WW_LAUNCH(Q_CLOSEST, MINB); break;                             \
-        case Q_CLOSEST_IGNORE_TRANSPARENT: CNDL_WW_LAUNCH(Q_CLOSEST_IGNORE_TRANSPARENT, MINB); break; \
-        default: CNDL_WW_LAUNCH(Q_ANY, MINB); break;                                        \
-    }
-    // register budget follows the requested residency: 7 CTAs/SM -> <= 72 regs, 8 -> 64, 10 -> 48, 12 -> 40
-    if (blocks_per_sm <= 7) { CNDL_WW_KIND(7) }
-    else if (blocks_per_sm <= 8) { CNDL_WW_KIND(8) }
-    else if (blocks_per_sm <= 10) { CNDL_WW_KIND(10) }
-    else { CNDL_WW_KIND(12) }
+    // register budget follows the requested residency: <= 8 CTAs/SM -> 64 registers, 10 -> 48, 12 -> 40
+    if (blocks_per_sm <= 8) launch_kind<8>(kind, steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
+    else if (blocks_per_sm <= 10) launch_kind<10>(kind, steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
+    else launch_kind<12>(kind, steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
     lc.n++;
 }
 

@@ -27,6 +27,27 @@ struct SceneView {
     int n_ents;       // u_EntityCount
 };
 
+// Which ray a launch slot processes.  list == nullptr: slot i is ray i.  counts == nullptr: ray list[i].
+// Otherwise the rays are bucketed by direction octant (octant_partition_kernel): bucket o holds counts[o]
+// ray indices at list + o * stride, and slots run through bucket 0, then bucket 1, ...
+struct RayOrder {
+    const unsigned* __restrict__ list;
+    const unsigned* __restrict__ counts;
+    unsigned stride;
+};
+
+__device__ __forceinline__ unsigned ray_of_slot(const RayOrder& ro, unsigned slot) {
+    if (!ro.list) return slot;
+    if (!ro.counts) return __ldg(ro.list + slot);
+    unsigned base = 0, o = 0, next = 0;
+#pragma unroll
+    for (unsigned k = 0; k < 7; ++k) {
+        next += __ldg(ro.counts + k);
+        if (slot >= next) { base = next; o = k + 1; }
+    }
+    return __ldg(ro.list + (size_t)o * ro.stride + (slot - base));
+}
+
 struct RayState {
     V3 o, d, inv;
     bool nan_path;  // some operand can make 0*inf: use the literal GLSL min/max
@@ -77,12 +98,12 @@ __device__ __forceinline__ bool enter_stackless(float4 mn, float4 mx, const RayS
     return enter_stackless(mn, mx, r, tmax_cur, r.nan_path);
 }
 
-// RayBounds, ST:107-116
-__device__ __forceinline__ float slab_stack(float4 mn, float4 mx, const RayState& r, float maxt) {
+// RayBounds, ST:107-116.  `exact`: see enter_stackless.
+__device__ __forceinline__ float slab_stack(float4 mn, float4 mx, const RayState& r, float maxt, bool exact) {
     const float fx = fmul(fsub(mx.x, r.o.x), r.inv.x), fy = fmul(fsub(mx.y, r.o.y), r.inv.y), fz = fmul(fsub(mx.z, r.o.z), r.inv.z);
     const float nx = fmul(fsub(mn.x, r.o.x), r.inv.x), ny = fmul(fsub(mn.y, r.o.y), r.inv.y), nz = fmul(fsub(mn.z, r.o.z), r.inv.z);
     float t0, t1;
-    if (!r.nan_path) {
+    if (!exact) {
         t1 = fminf(fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz))), maxt);
         t0 = fmaxf(fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz))), 0.0f);
     } else {
@@ -91,6 +112,7 @@ __device__ __forceinline__ float slab_stack(float4 mn, float4 mx, const RayState
     }
     return (t1 >= t0) ? (t0 > 0.0f ? t0 : t1) : -1.0f;
 }
+__device__ __forceinline__ float slab_stack(float4 mn, float4 mx, const RayState& r, float maxt) { return slab_stack(mn, mx, r, maxt, r.nan_path); }
 
 __device__ __forceinline__ RayState to_object_space(const cndl_entity* __restrict__ e, V3 ro, V3 rd) {
     // SL:177-180: the direction is not renormalised, so t is the same in both spaces

@@ -77,11 +77,52 @@ def test_knobs_and_modes_never_change_results(cb, ob, s260k):
         ri.set_tuning(3, variant)
         ri.BufferData()
         assert ri.IntersectRays(rays).tobytes() == want.tobytes(), (hot, block, variant)
+    # two rays per lane over the derived layout (variants 41..43), 4 / 5 / 6 CTAs per SM
+    for bps, park, idle, variant in ((5, 16, 16, 42), (4, 1, 1, 41), (6, 24, 40, 43), (5, 64, 64, 42)):
+        for k, val in enumerate((bps, park, idle, variant)):
+            ri.set_tuning(k, val)
+        assert ri.IntersectRays(rays).tobytes() == want.tobytes(), (bps, park, idle, variant)
+    for k, val in enumerate((8, 12, 8, 18)):
+        ri.set_tuning(k, val)
+    # ray bucketing by direction octant inside the call (every kernel family reads its rays through the bucket lists)
+    for variant in (18, 34, 42):
+        ri.set_tuning(3, variant)
+        ri.set_traversal_mode(2, True)
+        assert ri.IntersectRays(rays).tobytes() == want.tobytes(), ("bucketed", variant)
+        short = rays.copy()
+        short["tmax"] = 3.0
+        t_b = ri.IntersectRaysAny(short)
+        ri.set_traversal_mode(2, False)
+        assert t_b.tobytes() == ri.IntersectRaysAny(short).tobytes(), ("bucketed any-hit", variant)
     ri.set_tuning(3, 18)
     for chunks in (1, 3, 16):
         ri.set_tuning(4, chunks)
         assert ri.IntersectRays(rays).tobytes() == want.tobytes(), chunks
     ri.set_tuning(4, 0)
+
+
+def test_stack_kernel_knobs_and_bucketing(cb, ob):
+    """Stack format: the while-while kernel's thresholds / steps and ray bucketing never change a result."""
+    from candela_b200 import scenes
+    from helpers import rays_in_box
+    P, F = scenes.load_dragon()
+    V = cb.make_vertices(P)
+    ri = cb.RayIntersector(cb.STACK)
+    ri.AddObject(2, V, F.ravel(), np.zeros(len(F), np.int32))
+    ri.BufferData()
+    ri.PushEntity(2)
+    ri.BufferEntities()
+    nodes, tris, _ = ri.read_buffers()
+    ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(nodes))
+    rays = rays_in_box(P.min(0), P.max(0), 200000, 33)
+    want, _ = ob.trace(ob.STACK, ob.CLOSEST, nodes, tris, V, ents, rays, nthreads=ob.hardware_threads())
+    for park, idle, steps, sort in ((12, 8, 1, False), (1, 1, 2, False), (32, 32, 2, True), (5, 20, 1, True)):
+        ri.set_tuning(5, park)
+        ri.set_tuning(2, idle)
+        ri.set_tuning(3, steps)
+        ri.set_traversal_mode(2, sort)
+        assert ri.IntersectRays(rays).tobytes() == want.tobytes(), (park, idle, steps, sort)
+    ri.close()
 
 
 def test_full_size_properties_rtao(cb, s260k):

@@ -28,8 +28,10 @@ def main():
     ap.add_argument("--modes", default="0,1,2")
     ap.add_argument("--knobs", default="", help="semicolon-separated knob lists for mode 2, in knob-id order: bps,leaf,idle,variant,chunks,stack_leaf,hot_nodes,block_threads")
     ap.add_argument("--fmt", default="stackless")
+    ap.add_argument("--sort", type=int, default=0, help="1: bucket the rays by direction octant inside the call (cndl_set_traversal_mode sort_rays)")
     ap.add_argument("--gpu-builder", type=int, default=-1, help="-1: oracle-built buffers; 0: GPU SAH; 1: GPU LBVH")
-    ap.add_argument("--presort", type=int, default=0, help="host-side Morton sort of the diffuse rays (experiment)")
+    ap.add_argument("--presort", type=int, default=0, help="host-side Morton sort of the diffuse rays (experiment): bits per axis")
+    ap.add_argument("--presort-mode", type=int, default=0, help="0: origin cell major, octant minor; 1: octant major; 2: direction cell (16x16 on the octahedron) major")
     args = ap.parse_args()
     from oracle import binding as ob
     fmt = ob.STACKLESS if args.fmt == "stackless" else ob.STACK
@@ -65,7 +67,31 @@ def main():
             return r
         key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
         octant = ((d[:, 0] > 0).astype(np.uint64) | ((d[:, 1] > 0).astype(np.uint64) << np.uint64(1)) | ((d[:, 2] > 0).astype(np.uint64) << np.uint64(2)))
-        key = (key << np.uint64(3)) | octant
+        if args.presort_mode >= 100:   # global stable buckets by direction class
+            ad = np.abs(d); dom = np.argmax(ad, axis=1).astype(np.uint64)
+            sgn_dom = (np.take_along_axis(d, dom[:, None].astype(np.int64), 1)[:, 0] > 0).astype(np.uint64)
+            cls = {100: (d[:, 0] > 0).astype(np.uint64),                       # sign of x
+                   101: (d[:, 1] > 0).astype(np.uint64),                       # sign of y
+                   102: dom * np.uint64(2) + sgn_dom,                          # dominant axis + sign (6)
+                   103: octant * np.uint64(3) + dom,                           # octant x dominant axis (24)
+                   104: (octant & np.uint64(3)),                               # signs of x,y (4)
+                   105: (octant & np.uint64(5)),                               # signs of x,z (4)
+                   }[args.presort_mode]
+            key = cls
+        elif args.presort_mode >= 10:   # chunk-local octant grouping: chunks of 2^mode consecutive rays, stable
+            key = ((np.arange(len(d), dtype=np.uint64) >> np.uint64(args.presort_mode)) << np.uint64(3)) | octant
+        elif args.presort_mode == 0:
+            key = (key << np.uint64(3)) | octant
+        elif args.presort_mode == 1:
+            key = key | (octant << np.uint64(3 * args.presort))
+        else:
+            n1 = d / np.abs(d).sum(1, keepdims=True)
+            u, w = n1[:, 0].copy(), n1[:, 1].copy()
+            neg = n1[:, 2] < 0
+            u2 = (1 - np.abs(w)) * np.sign(u + 1e-30); w2 = (1 - np.abs(n1[:, 0])) * np.sign(w + 1e-30)
+            u[neg], w[neg] = u2[neg], w2[neg]
+            cu = np.clip(((u * 0.5 + 0.5) * 16).astype(np.uint64), 0, 15); cw = np.clip(((w * 0.5 + 0.5) * 16).astype(np.uint64), 0, 15)
+            key = key | ((cu * np.uint64(16) + cw) << np.uint64(3 * args.presort))
         drays = drays[np.argsort(key, kind="stable")]
     R = len(drays)
     ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(b.nodes))
@@ -89,7 +115,7 @@ def main():
             else:
                 variants.append((mode, None))
         for mode, knobs in variants:
-            ri.set_traversal_mode(mode)
+            ri.set_traversal_mode(mode, bool(args.sort))
             if knobs:
                 for kid, val in enumerate(knobs):
                     ri.set_tuning(kid, val)
@@ -108,7 +134,7 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             ms = float(np.median(ts))
-            line = dict(batch=name, mode=mode, knobs=knobs, fmt=args.fmt, ms=round(ms, 4), mrays=round(n / ms / 1e3, 1))
+            line = dict(batch=name, mode=mode, sort=args.sort, knobs=knobs, fmt=args.fmt, ms=round(ms, 4), mrays=round(n / ms / 1e3, 1))
             if name == "diffuse":
                 line["roofline_frac"] = round(n / (ms * 1e-3) * bray / 6550.1e9, 4)
                 if args.check:
