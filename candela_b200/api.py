@@ -34,7 +34,7 @@ EXPORTS = [
     "cndl_device_buffers", "cndl_push_entity", "cndl_push_entity_records", "cndl_buffer_entities", "cndl_entity_count",
     "cndl_intersect_closest", "cndl_intersect_any", "cndl_intersect_closest_device", "cndl_intersect_any_device",
     "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_generate_bounce_rays_device", "cndl_host_alloc", "cndl_host_free",
-    "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device",
+    "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device", "cndl_generate_rays_device",
 ]
 
 
@@ -43,6 +43,16 @@ class CandelaError(RuntimeError):
         super().__init__(f"[{code}] {message}")
         self.code = code
         self.message = message
+
+
+GEN_DIFFUSE, GEN_SPECULAR, GEN_SHADOW = 0, 1, 2
+GEN_BUCKET_OCTANTS = 1
+
+
+class RaygenParams(C.Structure):
+    """cndl_raygen_params (include/candela_b200.h)."""
+    _fields_ = [("kind", C.c_int32), ("spp", C.c_int32), ("seed", C.c_uint32), ("flags", C.c_uint32), ("offset", C.c_float), ("tmax", C.c_float),
+                ("roughness", C.c_float), ("light_dir", C.c_float * 3), ("light_cone", C.c_float)]
 
 
 class BuildOpts(C.Structure):
@@ -92,6 +102,7 @@ def load_library() -> C.CDLL:
     L.cndl_generate_bounce_rays_device.argtypes = [vp, vp, vp, sz, C.c_int, C.c_float, C.c_float, C.c_uint32, vp, vp, C.POINTER(sz), vp]
     L.cndl_get_data.argtypes = [vp, vp, sz, vp]
     L.cndl_get_data_device.argtypes = [vp, vp, sz, vp, vp]
+    L.cndl_generate_rays_device.argtypes = [vp, C.POINTER(RaygenParams), vp, vp, sz, vp, vp, C.POINTER(sz), vp]
     L.cndl_host_alloc.argtypes = [sz]
     L.cndl_host_alloc.restype = vp
     L.cndl_host_free.argtypes = [vp]
@@ -321,6 +332,16 @@ class RayIntersector:
         n = C.c_size_t(0)
         self._check(self._lib.cndl_generate_bounce_rays_device(self._h, d_rays, d_hits, n_rays, spp, offset, tmax, seed, d_rays_out,
                                                                d_parent_out or None, C.byref(n), stream or None))
+        return int(n.value)
+
+    def generate_rays_device(self, kind: int, d_rays: int, d_hits: int, n_rays: int, d_rays_out: int, spp: int = 1, offset: float = 0.05,
+                             tmax: float = 1.0e6, seed: int = 1, roughness: float = 0.0, light_dir=(0.0, 1.0, 0.0), light_cone: float = 0.0,
+                             bucket_octants: bool = False, d_parent_out: int = 0, stream: int = 0) -> int:
+        """Diffuse / specular / shadow rays from the hits of the previous batch (cndl_generate_rays_device); returns the count."""
+        p = RaygenParams(kind, spp, seed, GEN_BUCKET_OCTANTS if bucket_octants else 0, offset, tmax, roughness, (C.c_float * 3)(*light_dir), light_cone)
+        n = C.c_size_t(0)
+        self._check(self._lib.cndl_generate_rays_device(self._h, C.byref(p), d_rays, d_hits, n_rays, d_rays_out, d_parent_out or None, C.byref(n),
+                                                        stream or None))
         return int(n.value)
 
     def intersect_primary_device(self, inv_view, inv_proj, Width: int, Height: int, d_hits: int, d_rays: int = 0, stream: int = 0):

@@ -130,6 +130,8 @@ int upload_hot_entities(cndl_ctx* ctx) {
     return CNDL_OK;
 }
 
+size_t order_region_ints(size_t R) { return R + octant_partition_scratch_ints(R) + 16; }
+
 int check_ready(cndl_ctx* ctx) {
     if (!ctx->committed) return ctx->fail(CNDL_ERR_NOT_COMMITTED, "cndl_commit has not been called");
     if (!ctx->ents_buffered) return ctx->fail(CNDL_ERR_NOT_COMMITTED, "cndl_buffer_entities has not been called");
@@ -137,7 +139,7 @@ int check_ready(cndl_ctx* ctx) {
 }
 
 // Enqueues one traversal batch on `st`.  scratch: 16 unsigned ints ([0] work counter, [8..15] octant counts);
-// order_region: 8 * R unsigned ints, used when ray bucketing is on.
+// order_region: order_region_ints(R) unsigned ints, used when ray bucketing is on.
 int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cndl_hit* d_hits, float* d_any, unsigned* scratch,
                   unsigned* order_region, cudaStream_t st) {
     if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 rays in one call");
@@ -148,8 +150,8 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
     else {
         RayOrder order{nullptr, nullptr, 0};
         if (ctx->sort_rays && order_region && R >= 65536) {
-            launch_octant_partition(d_rays, R, order_region, scratch + 8, st, ctx->launches);
-            order = RayOrder{order_region, scratch + 8, (unsigned)R};
+            launch_octant_partition(d_rays, R, order_region, reinterpret_cast<int*>(order_region + R), st, ctx->launches);
+            order = RayOrder{order_region, nullptr, 0};
         }
         const int variant = ctx->knobs[CNDL_KNOB_VARIANT];
         int steps = variant & 7;
@@ -488,7 +490,7 @@ int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t 
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     const int kind = (flags & CNDL_IGNORE_TRANSPARENT) ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST;
-    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(8 * R * sizeof(unsigned)));
+    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
     return enqueue_trace(ctx, kind, d_rays, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), static_cast<unsigned*>(ctx->d_order.p),
                          static_cast<cudaStream_t>(stream));
 }
@@ -499,7 +501,7 @@ int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, f
     int rc = check_ready(ctx);
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
-    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(8 * R * sizeof(unsigned)));
+    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
     return enqueue_trace(ctx, Q_ANY, d_rays, R, nullptr, d_t_out, static_cast<unsigned*>(ctx->d_counter.p), static_cast<unsigned*>(ctx->d_order.p),
                          static_cast<cudaStream_t>(stream));
 }
@@ -527,7 +529,7 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
         ctx->events.push_back(e);
     }
     CK(ctx->d_chunk_counters.ensure_scratch(n_chunks * 64));
-    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(8 * R * sizeof(unsigned)));
+    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch((order_region_ints(chunk) * n_chunks) * sizeof(unsigned)));
     size_t k = 0;
     for (size_t lo = 0; lo < R; lo += chunk, ++k) {
         const size_t n = R - lo < chunk ? R - lo : chunk;
@@ -539,7 +541,7 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
         unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->d_chunk_counters.p) + 64 * k);
         rc = enqueue_trace(ctx, kind, dr, n, kind == Q_ANY ? nullptr : reinterpret_cast<cndl_hit*>(dout),
                            kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter,
-                           ctx->sort_rays ? static_cast<unsigned*>(ctx->d_order.p) + 8 * lo : nullptr, ctx->streams[1]);
+                           ctx->sort_rays ? static_cast<unsigned*>(ctx->d_order.p) + order_region_ints(chunk) * k : nullptr, ctx->streams[1]);
         if (rc != CNDL_OK) return rc;
         CK(cudaEventRecord(ctx->events[2 * k + 1], ctx->streams[1]));
         CK(cudaStreamWaitEvent(ctx->streams[2], ctx->events[2 * k + 1], 0));
@@ -599,19 +601,32 @@ int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float 
     return CNDL_OK;
 }
 
-int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R, int spp, float offset,
-                                     float tmax, uint32_t seed, cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream) {
+int cndl_generate_rays_device(cndl_ctx* ctx, const cndl_raygen_params* params, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R,
+                              cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream) {
     if (!ctx) return CNDL_ERR_INVALID;
-    if (!count_out || spp < 1 || (R && (!d_rays || !d_hits || !d_rays_out))) return ctx->fail(CNDL_ERR_INVALID, "bad bounce-ray arguments");
-    if (R * (size_t)spp > 0x7FFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "too many rays in one call");
+    if (!params || !count_out || params->spp < 1 || params->kind < CNDL_GEN_DIFFUSE || params->kind > CNDL_GEN_SHADOW ||
+        (R && (!d_rays || !d_hits || !d_rays_out)))
+        return ctx->fail(CNDL_ERR_INVALID, "bad ray-generation arguments");
+    if (R * (size_t)params->spp > 0x7FFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "too many rays in one call");
     int rc = check_ready(ctx);
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
-    CK(ctx->d_sort_tmp.ensure_scratch((2 * R + R / 2048 + 16) * sizeof(int)));
-    const SceneView s = scene_view(ctx);
-    CK(generate_bounce_rays(s, d_rays, d_hits, R, spp, offset, tmax, seed, d_rays_out, d_parent_out, static_cast<int*>(ctx->d_sort_tmp.p),
-                            count_out, static_cast<cudaStream_t>(stream), ctx->launches));
+    CK(ctx->d_sort_tmp.ensure_scratch(generate_rays_scratch_ints(R, params->spp) * sizeof(int)));
+    CK(generate_rays(scene_view(ctx), *params, d_rays, d_hits, R, d_rays_out, d_parent_out, static_cast<int*>(ctx->d_sort_tmp.p), count_out,
+                     static_cast<cudaStream_t>(stream), ctx->launches));
     return CNDL_OK;
+}
+
+int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R, int spp, float offset,
+                                     float tmax, uint32_t seed, cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream) {
+    cndl_raygen_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.kind = CNDL_GEN_DIFFUSE;
+    p.spp = spp;
+    p.seed = seed;
+    p.offset = offset;
+    p.tmax = tmax;
+    return cndl_generate_rays_device(ctx, &p, d_rays, d_hits, R, d_rays_out, d_parent_out, count_out, stream);
 }
 
 int cndl_get_data_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_attr* d_out, void* stream) {

@@ -31,17 +31,20 @@ void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t 
 void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
                            unsigned* work_counter, int sm_count, int park_threshold, int idle_threshold, int steps, cudaStream_t stream,
                            LaunchCounter& lc);
-// Buckets the ray indices by direction octant: buckets[o * R + k], counts[o] (8 counters, zeroed here).
-void launch_octant_partition(const cndl_ray* rays, size_t R, unsigned* buckets, unsigned* counts, cudaStream_t stream, LaunchCounter& lc);
+// Stable partition of the ray indices by direction octant (kernels_raygen.cu): order[0..R) lists the rays of octant 0
+// in their original order, then octant 1, ...  scratch: octant_partition_scratch_ints(R) ints.
+size_t octant_partition_scratch_ints(size_t R);
+void launch_octant_partition(const cndl_ray* rays, size_t R, unsigned* order, int* scratch, cudaStream_t stream, LaunchCounter& lc);
 
 // Camera rays of the primary kernel (Intersectors/TraverseBVHStack.glsl:133-138,:414-431).
 void launch_primary_rays(const float* inv_view16, const float* inv_proj16, int W, int H, cndl_ray* rays, cudaStream_t stream,
                          LaunchCounter& lc);
 
-// Wavefront compaction between bounces: diffuse rays from the hits of the previous batch (kernels_raygen.cu).
-cudaError_t generate_bounce_rays(const SceneView& s, const cndl_ray* rays, const cndl_hit* hits, size_t R, int spp, float offset, float tmax,
-                                 unsigned seed, cndl_ray* out, unsigned* parent, int* scratch, size_t* h_count, cudaStream_t stream,
-                                 LaunchCounter& lc);
+// Wavefront ray generation between bounces (kernels_raygen.cu): diffuse / specular / shadow rays from the hits of the
+// previous batch, compacted (and optionally octant-bucketed) with a stable partition.
+size_t generate_rays_scratch_ints(size_t R, int spp);
+cudaError_t generate_rays(const SceneView& s, const cndl_raygen_params& prm, const cndl_ray* rays, const cndl_hit* hits, size_t R, cndl_ray* out,
+                          unsigned* parent, int* scratch, size_t* h_count, cudaStream_t stream, LaunchCounter& lc);
 
 // GetData without textures: interpolated normal / uv + entity emissive / alpha per hit record (kernels_raygen.cu).
 void launch_get_data(const SceneView& s, const float4* verts, const cndl_hit* hits, size_t R, cndl_hit_attr* out, cudaStream_t stream, LaunchCounter& lc);

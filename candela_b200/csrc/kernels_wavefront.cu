@@ -376,51 +376,6 @@ __global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, con
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Ray bucketing by direction octant.  With the rays of a warp sharing the signs of their direction
-// the lanes' walks stay closer together (fewer distinct 128-byte lines per warp-wide node load, which
-// is what the L1 pipe charges for): -8.7 % on the diffuse batch.  Grouping only helps globally (every
-// ray in flight in the same octant), not within chunks, because refilled lanes take the next slots.
-// One pass: a block counts its rays per octant, reserves a run in each bucket with one atomic per
-// octant, and writes the ray indices there.
-constexpr int kPartBlock = 256, kPartItems = 8;
-
-__global__ void __launch_bounds__(kPartBlock) octant_partition_kernel(const cndl_ray* __restrict__ rays, unsigned R, unsigned* __restrict__ buckets,
-                                                                      unsigned stride, unsigned* __restrict__ counts) {
-    __shared__ unsigned s_cnt[8], s_base[8], s_run[8];
-    if (threadIdx.x < 8) { s_cnt[threadIdx.x] = 0; s_run[threadIdx.x] = 0; }
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned first = blockIdx.x * (kPartBlock * kPartItems);
-    unsigned oct[kPartItems];
-#pragma unroll
-    for (int j = 0; j < kPartItems; ++j) {
-        const unsigned i = first + j * kPartBlock + threadIdx.x;
-        oct[j] = 8;
-        if (i < R) {
-            const float4 d = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
-            oct[j] = (d.x > 0.0f ? 1u : 0u) | (d.y > 0.0f ? 2u : 0u) | (d.z > 0.0f ? 4u : 0u);
-        }
-        const unsigned peers = __match_any_sync(FULL, oct[j]);
-        if (oct[j] < 8 && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_cnt[oct[j]], (unsigned)__popc(peers));
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]) : 0u;
-    __syncthreads();
-    // the order inside a block's run follows the arrival of its warps, which is harmless: a ray's result
-    // does not depend on its slot
-#pragma unroll
-    for (int j = 0; j < kPartItems; ++j) {
-        const unsigned i = first + j * kPartBlock + threadIdx.x;
-        const unsigned peers = __match_any_sync(FULL, oct[j]);
-        unsigned off = 0;
-        const unsigned leader = (unsigned)(__ffs(peers) - 1);
-        if (oct[j] < 8 && lane == leader) off = atomicAdd(&s_run[oct[j]], (unsigned)__popc(peers));
-        off = __shfl_sync(FULL, off, leader);
-        if (oct[j] < 8) buckets[(size_t)oct[j] * stride + s_base[oct[j]] + off + (unsigned)__popc(peers & ((1u << lane) - 1u))] = i;
-    }
-}
-
 template <int KIND, int MINB>
 void launch_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const RayOrder& order,
                   cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
@@ -461,14 +416,6 @@ void launch_stack_steps(int steps, unsigned grid, cudaStream_t stream, const Sce
 }
 
 }  // namespace
-
-void launch_octant_partition(const cndl_ray* rays, size_t R, unsigned* buckets, unsigned* counts, cudaStream_t stream, LaunchCounter& lc) {
-    if (R == 0) return;
-    cudaMemsetAsync(counts, 0, 8 * sizeof(unsigned), stream);
-    const unsigned per_block = kPartBlock * kPartItems;
-    octant_partition_kernel<<<(unsigned)((R + per_block - 1) / per_block), kPartBlock, 0, stream>>>(rays, (unsigned)R, buckets, (unsigned)R, counts);
-    lc.n++;
-}
 
 void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
                            unsigned* work_counter, int sm_count, int park_threshold, int idle_threshold, int steps, cudaStream_t stream,

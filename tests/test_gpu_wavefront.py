@@ -58,6 +58,107 @@ def test_bounce_ray_generation_compacts_and_is_deterministic(cb, ob, s260k):
     assert ri.IntersectRaysAny(out).tobytes() == want.tobytes()
 
 
+def _pcg(v):
+    v = np.asarray(v, dtype=np.uint64) & np.uint64(0xFFFFFFFF)
+    s = (v * np.uint64(747796405) + np.uint64(2891336453)) & np.uint64(0xFFFFFFFF)
+    w = (((s >> ((s >> np.uint64(28)) + np.uint64(4))) ^ s) * np.uint64(277803737)) & np.uint64(0xFFFFFFFF)
+    return ((w >> np.uint64(22)) ^ w) & np.uint64(0xFFFFFFFF)
+
+
+def _u01(h):
+    return ((h >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)).astype(np.float32)
+
+
+def _specular_reference(I, N, rough_pbr, seed, idx):
+    """StochasticReflectionDirection restated (SpecularTrace.glsl:102-135 + Include/Sampling.glsl:63-83), spp = 1,
+    with the generator's counter-based xi instead of the shader's fract(sin()) hash."""
+    rough = np.float32(rough_pbr) * np.float32(0.9)
+    k = _pcg(np.uint64(seed) ^ _pcg(idx))
+    M = N.copy()
+    if rough >= 0.01:
+        a2 = np.float32(rough * rough) ** 2
+        up = np.where((np.abs(N[:, 2]) < 0.999)[:, None], np.array([0, 0, 1], np.float32), np.array([1, 0, 0], np.float32))
+        T = np.cross(up, N)
+        T /= np.linalg.norm(T, axis=1, keepdims=True)
+        B = np.cross(N, T)
+        found = np.zeros(len(N), bool)
+        for t in range(12):
+            x1 = _u01(_pcg(k + np.uint64((2 * t + 1) * 0x9E3779B9))) * np.float32(0.8)
+            x2 = _u01(_pcg(k + np.uint64((2 * t + 2) * 0x9E3779B9))) * np.float32(0.7)
+            phi = np.float32(2 * np.pi) * x1
+            ct = np.sqrt((1 - x2) / (1 + (a2 - 1) * x2))
+            st = np.sqrt(np.maximum(1 - ct * ct, 0))
+            S = T * (np.cos(phi) * st)[:, None] + B * (np.sin(phi) * st)[:, None] + N * ct[:, None]
+            S /= np.linalg.norm(S, axis=1, keepdims=True)
+            ok = (np.sum(S * N, axis=1) > 0.001) & ~found
+            M[ok] = S[ok]
+            found |= ok
+    D = I - 2 * np.sum(M * I, axis=1, keepdims=True) * M
+    return D / np.linalg.norm(D, axis=1, keepdims=True)
+
+
+def test_specular_shadow_and_bucketed_generation(cb, ob, s260k):
+    """cndl_generate_rays_device: specular rays against a numpy restatement of the reference's sampler, shadow rays,
+    and the octant-major emission order (a stable partition of the plain order)."""
+    import torch
+    from candela_b200 import api, scenes
+    ri = s260k["ri"]
+    W, H = 640, 360
+    iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
+    hits, rays = ri.IntersectPrimary(iv, ip, W, H, return_rays=True)
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
+    d_hits = torch.from_numpy(hits.view(np.float32).reshape(-1, 8)).cuda()
+    R = W * H
+    ok = np.nonzero(hits["t"] > 0)[0]
+
+    def run(kind, **kw):
+        spp = kw.get("spp", 1)
+        d_out = torch.zeros((R * spp, 8), dtype=torch.float32, device="cuda")
+        d_par = torch.zeros(R * spp, dtype=torch.int32, device="cuda")
+        n = ri.generate_rays_device(kind, d_rays.data_ptr(), d_hits.data_ptr(), R, d_out.data_ptr(), d_parent_out=d_par.data_ptr(), **kw)
+        return d_out[:n].cpu().numpy().view(api.RAY_DT).reshape(-1), d_par[:n].cpu().numpy()
+
+    # geometric normal and hit point, as the generator defines them
+    tv = s260k["tris"]["v"][hits["tri"][ok]]
+    Pv = s260k["v"]["position"][:, :3]
+    N = np.cross(Pv[tv[:, 1]] - Pv[tv[:, 0]], Pv[tv[:, 2]] - Pv[tv[:, 0]]).astype(np.float32)
+    N /= np.linalg.norm(N, axis=1, keepdims=True)
+    I = rays["d"][ok]
+    flip = np.sum(N * I, axis=1) > 0
+    N[flip] = -N[flip]
+    P = rays["o"][ok] + I * hits["t"][ok][:, None]
+
+    for rough in (0.0, 0.3, 0.8):
+        out, par = run(api.GEN_SPECULAR, roughness=rough, offset=-1.0, seed=11)
+        assert len(out) == len(ok) and np.array_equal(par, ok)
+        want = _specular_reference(I, N, rough, 11, ok.astype(np.uint64))
+        assert np.abs(out["d"] - want).max() < 2e-4, rough
+        off = 0.05 + 0.05 * min(max(rough * 1.4, 0.0), 1.0)
+        assert np.abs(out["o"] - (P + N * np.float32(off))).max() < 1e-4
+    mirror, _ = run(api.GEN_SPECULAR, roughness=0.0, offset=0.05)
+    assert np.abs(np.sum(mirror["d"] * N, axis=1) + np.sum(I * N, axis=1)).max() < 1e-5        # angle out = angle in
+
+    L = np.array([0.3, 0.9, 0.2], np.float32)
+    L /= np.linalg.norm(L)
+    sh, par = run(api.GEN_SHADOW, light_dir=tuple(float(x) for x in L), light_cone=0.0, tmax=200.0, offset=0.02)
+    lit = np.sum(N * L, axis=1) > 0
+    assert np.array_equal(par, ok[lit]) and np.abs(sh["d"] - L).max() < 1e-6 and np.all(sh["tmax"] == np.float32(200.0))
+    soft, _ = run(api.GEN_SHADOW, light_dir=tuple(float(x) for x in L), light_cone=0.05, spp=2, seed=4)
+    cosang = np.sum(soft["d"] * L, axis=1)
+    assert len(soft) == 2 * int(lit.sum()) and cosang.min() > np.cos(np.arcsin(0.05)) - 1e-4 and cosang.std() > 0
+
+    # octant-major emission = stable partition of the plain emission by the direction signs
+    plain, ppar = run(api.GEN_DIFFUSE, spp=3, seed=9)
+    buck, bpar = run(api.GEN_DIFFUSE, spp=3, seed=9, bucket_octants=True)
+    octant = (plain["d"][:, 0] > 0).astype(np.int64) | ((plain["d"][:, 1] > 0).astype(np.int64) << 1) | ((plain["d"][:, 2] > 0).astype(np.int64) << 2)
+    order = np.argsort(octant, kind="stable")
+    assert buck.tobytes() == plain[order].tobytes() and np.array_equal(bpar, ppar[order])
+    # and the traversal of the bucketed batch gives the same records, permuted
+    a = ri.IntersectRays(plain)
+    b = ri.IntersectRays(buck)
+    assert b.tobytes() == a[order].tobytes()
+
+
 def test_knobs_and_modes_never_change_results(cb, ob, s260k):
     from helpers import rays_in_box
     ri = s260k["ri"]
