@@ -26,6 +26,8 @@ STACK_NODE_DT = np.dtype([("lmin", "<f4", 4), ("lmax", "<f4", 4), ("rmin", "<f4"
 ENTITY_DT = np.dtype([("model", "<f4", 16), ("inverse", "<f4", 16), ("node_offset", "<i4"), ("node_count", "<i4"), ("data", "<i4", 14)])
 RAY_DT = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
 HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("w", "<f4"), ("mesh", "<i4"), ("tri", "<i4"), ("entity", "<i4"), ("iters", "<i4")])
+BOX_DT = np.dtype([("min", "<f4", 3), ("pad0", "<f4"), ("max", "<f4", 3), ("pad1", "<f4")])
+COLLISION_DT = np.dtype([("collided", "<i4"), ("mesh", "<i4"), ("tri", "<i4"), ("entity", "<i4")])
 ATTR_DT = np.dtype([("normal", "<f4", 3), ("uv", "<f4", 2), ("emissivity", "<f4"), ("alpha", "<f4"), ("mesh", "<i4")])
 
 EXPORTS = [
@@ -34,7 +36,7 @@ EXPORTS = [
     "cndl_device_buffers", "cndl_push_entity", "cndl_push_entity_records", "cndl_buffer_entities", "cndl_entity_count",
     "cndl_intersect_closest", "cndl_intersect_any", "cndl_intersect_closest_device", "cndl_intersect_any_device",
     "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_generate_bounce_rays_device", "cndl_host_alloc", "cndl_host_free",
-    "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device", "cndl_generate_rays_device",
+    "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device", "cndl_generate_rays_device", "cndl_collide_boxes", "cndl_collide_boxes_device",
 ]
 
 
@@ -103,6 +105,8 @@ def load_library() -> C.CDLL:
     L.cndl_get_data.argtypes = [vp, vp, sz, vp]
     L.cndl_get_data_device.argtypes = [vp, vp, sz, vp, vp]
     L.cndl_generate_rays_device.argtypes = [vp, C.POINTER(RaygenParams), vp, vp, sz, vp, vp, C.POINTER(sz), vp]
+    L.cndl_collide_boxes.argtypes = [vp, vp, sz, vp]
+    L.cndl_collide_boxes_device.argtypes = [vp, vp, sz, vp, vp]
     L.cndl_host_alloc.argtypes = [sz]
     L.cndl_host_alloc.restype = vp
     L.cndl_host_free.argtypes = [vp]
@@ -319,6 +323,23 @@ class RayIntersector:
         self._check(self._lib.cndl_get_data(self._h, _p(hits), len(hits), _p(out)))
         return out
 
+    def CollideBoxes(self, mins, maxs) -> np.ndarray:
+        """Physics::CollideBox (Physics.cpp:203-228) for a batch of boxes -> records {collided, mesh, tri, entity}."""
+        mins = np.asarray(mins, dtype=np.float32).reshape(-1, 3)
+        boxes = np.zeros(len(mins), dtype=BOX_DT)
+        boxes["min"], boxes["max"] = mins, np.asarray(maxs, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(len(boxes), dtype=COLLISION_DT)
+        self._check(self._lib.cndl_collide_boxes(self._h, _p(boxes), len(boxes), _p(out)))
+        return out
+
+    def CollideBox(self, Min, Max) -> bool:
+        return bool(self.CollideBoxes([Min], [Max])["collided"][0])
+
+    def CollidePoint(self, Point) -> bool:
+        """Physics::CollidePoint (Physics.cpp:175-201): the box Point -+ 0.01."""
+        p = np.asarray(Point, dtype=np.float32)
+        return self.CollideBox(p - np.float32(0.01), p + np.float32(0.01))
+
     # -- queries: device buffers (raw pointers, e.g. torch tensors' data_ptr()) --------------------
     def intersect_closest_device(self, d_rays: int, n_rays: int, d_hits: int, flags: int = 0, stream: int = 0):
         self._check(self._lib.cndl_intersect_closest_device(self._h, d_rays, n_rays, flags, d_hits, stream or None))
@@ -350,3 +371,6 @@ class RayIntersector:
 
     def get_data_device(self, d_hits: int, n: int, d_out: int, stream: int = 0):
         self._check(self._lib.cndl_get_data_device(self._h, d_hits, n, d_out, stream or None))
+
+    def collide_boxes_device(self, d_boxes: int, n: int, d_out: int, stream: int = 0):
+        self._check(self._lib.cndl_collide_boxes_device(self._h, d_boxes, n, d_out, stream or None))

@@ -657,6 +657,35 @@ int cndl_get_data(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_attr* 
     return CNDL_OK;
 }
 
+int cndl_collide_boxes_device(cndl_ctx* ctx, const cndl_box* d_boxes, size_t n, cndl_collision* d_out, void* stream) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (ctx->format != CNDL_STACKLESS) return ctx->fail(CNDL_ERR_INVALID, "the collide query walks FlattenedNode buffers (Physics.h:15): stackless contexts only");
+    if (n && (!d_boxes || !d_out)) return ctx->fail(CNDL_ERR_INVALID, "null box or result buffer");
+    if (n > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 boxes in one call");
+    int rc = check_ready(ctx);
+    if (rc != CNDL_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    launch_collide_boxes(scene_view(ctx), static_cast<const float4*>(ctx->verts.p), d_boxes, n, d_out, static_cast<cudaStream_t>(stream), ctx->launches);
+    CK(cudaGetLastError());
+    return CNDL_OK;
+}
+
+int cndl_collide_boxes(cndl_ctx* ctx, const cndl_box* boxes, size_t n, cndl_collision* out) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (n && (!boxes || !out)) return ctx->fail(CNDL_ERR_INVALID, "null box or result buffer");
+    if (n == 0) return check_ready(ctx);
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_rays.ensure_scratch(n * sizeof(cndl_box)));
+    CK(ctx->d_hits.ensure_scratch(n * sizeof(cndl_collision)));
+    cudaStream_t st = ctx->main_stream;
+    CK(cudaMemcpyAsync(ctx->d_rays.p, boxes, n * sizeof(cndl_box), cudaMemcpyHostToDevice, st));
+    int rc = cndl_collide_boxes_device(ctx, static_cast<const cndl_box*>(ctx->d_rays.p), n, static_cast<cndl_collision*>(ctx->d_hits.p), st);
+    if (rc != CNDL_OK) return rc;
+    CK(cudaMemcpyAsync(out, ctx->d_hits.p, n * sizeof(cndl_collision), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return CNDL_OK;
+}
+
 void* cndl_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -36,6 +36,10 @@ void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, s
 size_t octant_partition_scratch_ints(size_t R);
 void launch_octant_partition(const cndl_ray* rays, size_t R, unsigned* order, int* scratch, cudaStream_t stream, LaunchCounter& lc);
 
+// Physics::CollideBox for a batch of boxes over the stackless buffers (kernels_traverse.cu).
+void launch_collide_boxes(const SceneView& s, const float4* verts, const cndl_box* boxes, size_t n, cndl_collision* out, cudaStream_t stream,
+                          LaunchCounter& lc);
+
 // Camera rays of the primary kernel (Intersectors/TraverseBVHStack.glsl:133-138,:414-431).
 void launch_primary_rays(const float* inv_view16, const float* inv_proj16, int W, int H, cndl_ray* rays, cudaStream_t stream,
                          LaunchCounter& lc);

@@ -207,6 +207,77 @@ __global__ void rebase_triangles_kernel(int4* __restrict__ tris, size_t T, int o
     tris[i] = t;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Physics::CollideBox / CollideBVH (Source/Core/Physics.cpp:21-228): does an axis-aligned box touch the scene?  The
+// same threaded walk with a box-overlap predicate; one thread per query box.  Quirks kept: the box is taken to object
+// space corner by corner (:84-85), `e` is the full extent (:31), nine cross-product axes only, the sixth repeating
+// cross(u2, f2) (:46-54); the first overlapping triangle in walk order wins.
+__device__ __forceinline__ bool box_triangle_overlap(V3 v0, V3 v1, V3 v2, V3 bmin, V3 bmax) {
+    const V3 c = {fdiv(fadd(bmin.x, bmax.x), 2.0f), fdiv(fadd(bmin.y, bmax.y), 2.0f), fdiv(fadd(bmin.z, bmax.z), 2.0f)};
+    const V3 e = vsub(bmax, bmin);
+    v0 = vsub(v0, c); v1 = vsub(v1, c); v2 = vsub(v2, c);
+    const V3 f0 = vsub(v1, v0), f1 = vsub(v2, v1), f2 = vsub(v0, v2);
+    const V3 u0 = {1.0f, 0.0f, 0.0f}, u1 = {0.0f, 1.0f, 0.0f}, u2 = {0.0f, 0.0f, 1.0f};
+    const V3 axes[9] = {vcross(u0, f0), vcross(u0, f1), vcross(u0, f2), vcross(u1, f0), vcross(u1, f1), vcross(u2, f2), vcross(u2, f0), vcross(u2, f1), vcross(u2, f2)};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const V3 a = axes[i];
+        const float p0 = vdot(v0, a), p1 = vdot(v1, a), p2 = vdot(v2, a);
+        const float r = fadd(fadd(fmul(e.x, fabsf(vdot(u0, a))), fmul(e.y, fabsf(vdot(u1, a)))), fmul(e.z, fabsf(vdot(u2, a))));
+        if (glsl_max(-glsl_max(glsl_max(p0, p1), p2), glsl_min(glsl_min(p0, p1), p2)) > r) return false;
+    }
+    return true;
+}
+
+__global__ void collide_boxes_kernel(SceneView s, const float4* __restrict__ verts, const float4* __restrict__ boxes, unsigned n, int4* __restrict__ out) {
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const float4 b0 = __ldg(boxes + 2 * (size_t)q), b1 = __ldg(boxes + 2 * (size_t)q + 1);
+    int4 res = make_int4(0, -1, -1, -1);
+    for (int ei = 0; ei < s.n_ents && !res.x; ++ei) {  // CollideBox :203-228
+        const cndl_entity* en = s.ents + ei;
+        float m[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) m[k] = __ldg(&en->inverse[k]);
+        const V3 cmin = xform(m, V3{b0.x, b0.y, b0.z}, 1.0f), cmax = xform(m, V3{b1.x, b1.y, b1.z}, 1.0f);
+        const int start = __ldg(&en->node_offset), count = __ldg(&en->node_count);
+        int ptr = start, iters = 0;
+        while (ptr >= 0 && iters < 1024) {
+            // :101 also admits Pointer == m_BVHNodes.size(), an out-of-bounds read; oracle and kernel stop there instead
+            if (ptr < start || ptr > start + count || ptr >= s.total_nodes) break;
+            ++iters;
+            const float4 mn = __ldg(s.nodes + 2 * (size_t)ptr), mx = __ldg(s.nodes + 2 * (size_t)ptr + 1);
+            const int link = __float_as_int(mx.w);
+            const bool overlap = (mn.x <= cmax.x && mx.x >= cmin.x) && (mn.y <= cmax.y && mx.y >= cmin.y) && (mn.z <= cmax.z && mx.z >= cmin.z);  // :23-27
+            if (overlap) {
+                const int pack = __float_as_int(mn.w);
+                if (pack != -1) {
+                    const int len = pack & 0xF;
+                    for (int idx = pack >> 4; idx < (pack >> 4) + len; ++idx) {
+                        const int4 t = __ldg(s.tris + idx);
+                        const float4 a = __ldg(verts + 2 * (size_t)t.x), b = __ldg(verts + 2 * (size_t)t.y), c = __ldg(verts + 2 * (size_t)t.z);
+                        if (box_triangle_overlap(V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z}, V3{c.x, c.y, c.z}, cmin, cmax)) {
+                            res = make_int4(1, t.w, idx, ei);
+                            break;
+                        }
+                    }
+                    if (res.x) break;
+                    ptr = link;
+                    if (ptr < 0) break;
+                    ptr += start;
+                } else {
+                    ++ptr;
+                }
+            } else {
+                ptr = link;
+                if (ptr < 0) break;
+                ptr += start;
+            }
+        }
+    }
+    out[q] = res;
+}
+
 struct Mat2 { float iv[16]; float ip[16]; };
 
 __global__ void primary_rays_kernel(Mat2 m, int W, int H, cndl_ray* __restrict__ rays) {
@@ -275,6 +346,14 @@ void launch_make_tri48(const int4* tris, const float4* verts, size_t T, float4* 
 void launch_rebase_triangles(int4* tris, size_t T, int offset, cudaStream_t stream, LaunchCounter& lc) {
     if (T == 0 || offset == 0) return;
     rebase_triangles_kernel<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(tris, T, offset);
+    lc.n++;
+}
+
+void launch_collide_boxes(const SceneView& s, const float4* verts, const cndl_box* boxes, size_t n, cndl_collision* out, cudaStream_t stream,
+                          LaunchCounter& lc) {
+    if (n == 0) return;
+    collide_boxes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(s, verts, reinterpret_cast<const float4*>(boxes), (unsigned)n,
+                                                                        reinterpret_cast<int4*>(out));
     lc.n++;
 }
 

@@ -192,6 +192,15 @@ typedef struct cndl_hit_attr { float nx, ny, nz, u, v, emissivity, alpha; int32_
 int cndl_get_data_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_attr* d_out, void* stream);
 int cndl_get_data(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_attr* out);
 
+/* Physics::CollideBox (Source/Core/Physics.cpp:203-228; declared Physics.h:15) for a batch of axis-aligned boxes: does the
+ * box touch any triangle of any entity?  collided = 0/1; mesh / tri / entity identify the first overlapping triangle in the
+ * reference's walk order (the reference computes them and returns only the bool).  Physics::CollidePoint is the box
+ * (P - 0.01, P + 0.01) (:177-179).  Stackless contexts only, like the reference's signature. */
+typedef struct cndl_box { float min[3]; float pad0; float max[3]; float pad1; } cndl_box;
+typedef struct cndl_collision { int32_t collided, mesh, tri, entity; } cndl_collision;
+int cndl_collide_boxes(cndl_ctx* ctx, const cndl_box* boxes, size_t n, cndl_collision* out);
+int cndl_collide_boxes_device(cndl_ctx* ctx, const cndl_box* d_boxes, size_t n, cndl_collision* d_out, void* stream);
+
 /* Pinned host memory for ray / hit batches. */
 void* cndl_host_alloc(size_t bytes);
 void cndl_host_free(void* p);

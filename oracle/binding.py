@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
         L.orc_trace.argtypes = [C.c_int, C.c_int, vp, u64, vp, vp, vp, i32, vp, u64, vp, vp, vp, C.c_int]
         L.orc_brute_force.argtypes = [vp, u64, vp, vp, i32, vp, u64, vp, C.c_int]
         L.orc_get_data.argtypes = [vp, vp, vp, vp, u64, vp]
+        L.orc_collide_boxes.argtypes = [vp, u64, vp, vp, vp, i32, vp, u64, vp]
         L.orc_hardware_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -236,6 +237,28 @@ def get_data(tris, verts, entities, hits):
     return out
 
 
+BOX_DT = np.dtype([("min", "<f4", 3), ("pad0", "<f4"), ("max", "<f4", 3), ("pad1", "<f4")])
+COLLISION_DT = np.dtype([("collided", "<i4"), ("mesh", "<i4"), ("tri", "<i4"), ("entity", "<i4")])
+
+
+def make_boxes(mins, maxs):
+    b = np.zeros(len(mins), dtype=BOX_DT)
+    b["min"], b["max"] = np.asarray(mins, np.float32), np.asarray(maxs, np.float32)
+    return b
+
+
+def collide_boxes(nodes, tris, verts, entities, boxes):
+    """Physics::CollideBox restated (oracle_trace.cpp) for a batch of boxes; stackless buffers only."""
+    nodes = np.ascontiguousarray(nodes, dtype=NODE32_DT)
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
+    verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DT)
+    boxes = np.ascontiguousarray(boxes, dtype=BOX_DT)
+    out = np.zeros(len(boxes), dtype=COLLISION_DT)
+    lib().orc_collide_boxes(_p(nodes), len(nodes), _p(tris), _p(verts), _p(entities), len(entities), _p(boxes), len(boxes), _p(out))
+    return out
+
+
 def pack_vertices(positions, normals, uvs):
     """Vertex records with packed half-float normal / uv like ModelFileLoader.cpp:133-155 (tangent = 0)."""
     v = make_vertices(positions)
@@ -276,6 +299,7 @@ def ref_lib() -> C.CDLL:
         R.ref_build.restype = C.c_int
         R.ref_build.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]
         R.ref_fetch.argtypes = [vp, vp, vp]
+        R.ref_collide_box.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp]
         _ref = R
     return _ref
 
@@ -304,3 +328,15 @@ def ref_build(fmt: int, meshes, t_offset: int = 0):
     ov = np.zeros(int(n[2]), dtype=VERTEX_DT)
     R.ref_fetch(_p(nodes), _p(tris), _p(ov))
     return nodes, tris, ov
+
+
+def ref_collide_boxes(nodes, tris, verts, entities, boxes) -> np.ndarray:
+    """Physics::CollideBox of the compiled reference itself (oracle/_ref): one 0/1 answer per box."""
+    nodes = np.ascontiguousarray(nodes, dtype=NODE32_DT)
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
+    verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DT)
+    boxes = np.ascontiguousarray(boxes, dtype=BOX_DT)
+    out = np.zeros(len(boxes), dtype=np.int32)
+    ref_lib().ref_collide_box(_p(nodes), len(nodes), _p(tris), len(tris), _p(verts), len(verts), _p(entities), len(entities), _p(boxes), len(boxes), _p(out))
+    return out

@@ -129,6 +129,11 @@ void orc_brute_force(const void* tris, uint64_t T, const void* verts, const void
  * {float nx,ny,nz,u,v,emissivity,alpha; int32 mesh}; a miss (t < 0 or mesh < 0) gives normal (-1,-1,-1), rest 0. */
 void orc_get_data(const void* tris, const void* verts, const void* entities, const orc_hit* hits, uint64_t R, void* out);
 
+/* Physics::CollideBox (Source/Core/Physics.cpp:21-228) for n query boxes of 32 bytes {min.xyz, pad, max.xyz, pad} over the
+ * stackless buffers.  out: n x {collided, mesh, tri, entity} (the first overlapping triangle in walk order). */
+void orc_collide_boxes(const void* nodes, uint64_t n_nodes, const void* tris, const void* verts, const void* entities, int32_t n_entities,
+                       const float* boxes, uint64_t n, int32_t* out);
+
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus

@@ -456,3 +456,79 @@ extern "C" void orc_get_data(const void* tris_, const void* verts_, const void* 
         out[i] = a;
     }
 }
+
+// ---- AABB collide query: Physics::CollideBox / CollideBVH (Source/Core/Physics.cpp:21-228), the other consumer of the
+// stackless buffers.  PINNED: the reference's Physics.cpp compiles here (oracle/_ref) and
+// tests/test_collide.py requires identical answers.  Quirks kept: the query box is taken to object space corner by
+// corner (:84-85), `e` is the full extent (:31), only nine cross-product axes are tested and the sixth repeats
+// cross(u2, f2) (:46-54), and the first overlapping triangle in walk order wins.
+namespace {
+inline bool aabb_overlap(V3 amin, V3 amax, V3 bmin, V3 bmax) {  // :23-27
+    return (amin.x <= bmax.x && amax.x >= bmin.x) && (amin.y <= bmax.y && amax.y >= bmin.y) && (amin.z <= bmax.z && amax.z >= bmin.z);
+}
+inline bool box_triangle_overlap(V3 v0, V3 v1, V3 v2, V3 bmin, V3 bmax) {  // :29-77
+    const V3 c = {(bmin.x + bmax.x) / 2.0f, (bmin.y + bmax.y) / 2.0f, (bmin.z + bmax.z) / 2.0f};
+    const V3 e = sub(bmax, bmin);
+    v0 = sub(v0, c); v1 = sub(v1, c); v2 = sub(v2, c);
+    const V3 f0 = sub(v1, v0), f1 = sub(v2, v1), f2 = sub(v0, v2);
+    const V3 u0 = {1.0f, 0.0f, 0.0f}, u1 = {0.0f, 1.0f, 0.0f}, u2 = {0.0f, 0.0f, 1.0f};
+    const V3 axes[9] = {cross(u0, f0), cross(u0, f1), cross(u0, f2), cross(u1, f0), cross(u1, f1), cross(u2, f2), cross(u2, f0), cross(u2, f1), cross(u2, f2)};
+    for (int i = 0; i < 9; ++i) {
+        const V3 a = axes[i];
+        const float p0 = dot(v0, a), p1 = dot(v1, a), p2 = dot(v2, a);
+        const float r = e.x * std::fabs(dot(u0, a)) + e.y * std::fabs(dot(u1, a)) + e.z * std::fabs(dot(u2, a));
+        if (smax(-smax(smax(p0, p1), p2), smin(smin(p0, p1), p2)) > r) return false;
+    }
+    return true;
+}
+}  // namespace
+
+extern "C" void orc_collide_boxes(const void* nodes_, uint64_t n_nodes, const void* tris_, const void* verts_, const void* entities, int32_t n_entities,
+                                  const float* boxes, uint64_t n, int32_t* out) {
+    const Node32* nodes = static_cast<const Node32*>(nodes_);
+    const Tri16* tris = static_cast<const Tri16*>(tris_);
+    const Vertex32* verts = static_cast<const Vertex32*>(verts_);
+    const Entity192* ents = static_cast<const Entity192*>(entities);
+    for (uint64_t q = 0; q < n; ++q) {
+        const V3 wmin = {boxes[8 * q], boxes[8 * q + 1], boxes[8 * q + 2]}, wmax = {boxes[8 * q + 4], boxes[8 * q + 5], boxes[8 * q + 6]};
+        int32_t res[4] = {0, -1, -1, -1};
+        for (int32_t ei = 0; ei < n_entities && !res[0]; ++ei) {  // CollideBox :203-228
+            const Entity192& en = ents[ei];
+            const V3 cmin = xform(en.inv, wmin, 1.0f), cmax = xform(en.inv, wmax, 1.0f);  // :84-85
+            const int32_t start = en.node_offset, count = en.node_count;
+            int32_t ptr = start, iters = 0;
+            while (ptr >= 0 && iters < 1024) {
+                // :101 also admits Pointer == m_BVHNodes.size(), an out-of-bounds read; both sides stop there instead
+                if (ptr < start || ptr > start + count || (uint64_t)ptr >= n_nodes) break;
+                ++iters;
+                const Node32& nd = nodes[ptr];
+                const int32_t link = fbits(nd.mx[3]);
+                if (aabb_overlap({nd.mn[0], nd.mn[1], nd.mn[2]}, {nd.mx[0], nd.mx[1], nd.mx[2]}, cmin, cmax)) {
+                    const int32_t pack = fbits(nd.mn[3]);
+                    if (pack != -1) {
+                        const int32_t len = pack & 0xF;
+                        for (int32_t idx = pack >> 4; idx < (pack >> 4) + len; ++idx) {
+                            const Tri16& t = tris[idx];
+                            if (box_triangle_overlap(pos3(verts[t.v[0]]), pos3(verts[t.v[1]]), pos3(verts[t.v[2]]), cmin, cmax)) {
+                                res[0] = 1; res[1] = t.v[3]; res[2] = idx; res[3] = ei;
+                                break;
+                            }
+                        }
+                        if (res[0]) break;
+                        ptr = link;
+                        if (ptr < 0) break;
+                        ptr += start;
+                    } else {
+                        ++ptr;
+                    }
+                } else {
+                    ptr = link;
+                    if (ptr < 0) break;
+                    ptr += start;
+                }
+            }
+        }
+        for (int k = 0; k < 4; ++k) out[4 * q + k] = res[k];
+    }
+}
+

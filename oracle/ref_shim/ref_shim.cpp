@@ -21,6 +21,9 @@
 
 #include "BVH/BVHConstructor.h"
 #include "Object.h"
+#include "Physics.h"
+
+#include <new>
 
 namespace {
 
@@ -124,6 +127,33 @@ void ref_fetch(void* nodes, void* tris, void* verts) {
     }
     if (tris) std::memcpy(tris, g_tris.data(), g_tris.size() * sizeof(g_tris[0]));
     if (verts) std::memcpy(verts, g_verts.data(), g_verts.size() * sizeof(g_verts[0]));
+}
+
+// Physics::CollideBox (Physics.cpp:203-228) of the UNMODIFIED reference on caller-supplied stackless buffers.  The
+// function only reads the intersector's public vectors (Intersector.h:96-99); an intersector cannot be constructed
+// without a GL context (its members compile shaders), so the four vectors are placement-constructed inside raw
+// storage of the right type and nothing else of the object is touched.
+int ref_collide_box(const void* nodes, uint64_t n_nodes, const void* tris, uint64_t n_tris, const void* verts, uint64_t n_verts,
+                    const void* entities, uint64_t n_entities, const float* boxes, uint64_t n, int32_t* out) {
+    using namespace Candela;
+    typedef RayIntersector<BVH::StacklessTraversalNode> RI;
+    alignas(64) static unsigned char storage[sizeof(RI)];
+    RI* ri = reinterpret_cast<RI*>(storage);
+    auto* np_ = static_cast<const BVH::StacklessTraversalNode*>(nodes);
+    auto* tp = static_cast<const BVH::Triangle*>(tris);
+    auto* vp = static_cast<const Vertex*>(verts);
+    auto* ep = static_cast<const BVHEntity*>(entities);
+    new (&ri->m_BVHNodes) std::vector<BVH::StacklessTraversalNode>(np_, np_ + n_nodes);
+    new (&ri->m_BVHTriangles) std::vector<BVH::Triangle>(tp, tp + n_tris);
+    new (&ri->m_BVHVertices) std::vector<Vertex>(vp, vp + n_verts);
+    new (&ri->m_BVHEntities) std::vector<BVHEntity>(ep, ep + n_entities);
+    for (uint64_t q = 0; q < n; ++q) {
+        const glm::vec3 mn(boxes[8 * q], boxes[8 * q + 1], boxes[8 * q + 2]), mx(boxes[8 * q + 4], boxes[8 * q + 5], boxes[8 * q + 6]);
+        out[q] = Physics::CollideBox(mn, mx, *ri) ? 1 : 0;
+    }
+    using VN = std::vector<BVH::StacklessTraversalNode>; using VT = std::vector<BVH::Triangle>; using VV = std::vector<Vertex>; using VE = std::vector<BVHEntity>;
+    ri->m_BVHNodes.~VN(); ri->m_BVHTriangles.~VT(); ri->m_BVHVertices.~VV(); ri->m_BVHEntities.~VE();
+    return 0;
 }
 
 }  // extern "C"

@@ -76,7 +76,8 @@ def cfg_rtao(args, rank, world, local_rank):
     d_hits = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
     ri.intersect_primary_device(iv, ip, W, H, d_hits.data_ptr(), d_prim.data_ptr(), stream)
     d_ao = torch.empty((W * H * spp, 8), dtype=torch.float32, device="cuda")
-    n = ri.generate_bounce_rays_device(d_prim.data_ptr(), d_hits.data_ptr(), W * H, d_ao.data_ptr(), spp=spp, offset=0.05, tmax=2.4, seed=7, stream=stream)
+    n = ri.generate_rays_device(api.GEN_DIFFUSE, d_prim.data_ptr(), d_hits.data_ptr(), W * H, d_ao.data_ptr(), spp=spp, offset=0.05, tmax=2.4, seed=7,
+                                bucket_octants=bool(args.bucket), stream=stream)
     d_t = torch.empty(n, dtype=torch.float32, device="cuda")
     flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
     ms = timed(lambda: ri.intersect_any_device(d_ao.data_ptr(), n, d_t.data_ptr(), stream), reps=args.reps, flush=flush)
@@ -87,7 +88,7 @@ def cfg_rtao(args, rank, world, local_rank):
     cpu_s = time.perf_counter() - t0
     got = d_t.cpu().numpy()
     b_ray = (cnt["node_iters"] * 32.0 + cnt["tri_tests"] * 64.0) / n
-    return dict(config="rtao_anyhit_1080p_4spp_tmax2.4", rays=n, ms=round(ms, 4), mrays_s=round(n / ms / 1e3, 1), occluded_frac=round(float((got > 0).mean()), 4),
+    return dict(config="rtao_anyhit_1080p_4spp_tmax2.4", octant_bucketed=bool(args.bucket), rays=n, ms=round(ms, 4), mrays_s=round(n / ms / 1e3, 1), occluded_frac=round(float((got > 0).mean()), 4),
                 bit_identical_to_oracle=bool(got.tobytes() == want.tobytes()), bytes_per_ray=round(b_ray, 1),
                 roofline_frac=round(n / (ms * 1e-3) * b_ray / (PEAK * 1e9), 4), node_iters_per_ray=round(cnt["node_iters"] / n, 2),
                 cpu_mrays_s=round(n / cpu_s / 1e6, 2), cpu_threads=ob.hardware_threads())
@@ -120,8 +121,8 @@ def cfg_bounce4k(args, rank, world, local_rank):
         out = bufs[b % 2]
         g0, g1, t1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         g0.record()
-        n = ri.generate_bounce_rays_device(src_rays.data_ptr(), src_hits.data_ptr(), n_src, out.data_ptr(), spp=s, offset=0.05 if b == 0 else 0.02,
-                                           tmax=1.0e6, seed=100 + b, stream=stream)
+        n = ri.generate_rays_device(api.GEN_DIFFUSE, src_rays.data_ptr(), src_hits.data_ptr(), n_src, out.data_ptr(), spp=s, offset=0.05 if b == 0 else 0.02,
+                                    tmax=1.0e6, seed=100 + b, bucket_octants=bool(args.bucket), stream=stream)
         g1.record()
         if n == 0:
             break
@@ -152,7 +153,7 @@ def cfg_bounce4k(args, rank, world, local_rank):
     for b, r, h in checks:
         want, _ = ob.trace(ob.STACKLESS, ob.CLOSEST_IGNORE_TRANSPARENT if b == 0 else ob.CLOSEST, nodes, tris, v, ents, r, nthreads=ob.hardware_threads())
         ok = ok and want.tobytes() == h.tobytes()
-    return dict(config=f"multibounce_{W}x{H}_8spp_tiles", n_gpus=world, rays_all_ranks=int(rays_all), trace_ms_max_over_ranks=round(t_max, 3),
+    return dict(config=f"multibounce_{W}x{H}_8spp_tiles", octant_bucketed=bool(args.bucket), n_gpus=world, rays_all_ranks=int(rays_all), trace_ms_max_over_ranks=round(t_max, 3),
                 mrays_s=round(rays_all / t_max / 1e3, 1), per_bounce_rank0=per_bounce, sample_bit_identical_to_oracle=bool(ok),
                 final_frame_gather_ms=round(gather_ms, 3), frame_pixels=int(frame.shape[0]))
 
@@ -223,6 +224,7 @@ def main():
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--rays", type=int, default=0)
     ap.add_argument("--builder", type=int, default=0)
+    ap.add_argument("--bucket", type=int, default=0, help="1: the generator emits each batch octant-major (CNDL_GEN_BUCKET_OCTANTS)")
     ap.add_argument("--check-rays", type=int, default=1_000_000)
     ap.add_argument("--check-build", action="store_true")
     args = ap.parse_args()
