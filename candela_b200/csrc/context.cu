@@ -71,7 +71,7 @@ struct cndl_ctx {
     // query scratch
     DeviceBuffer d_rays, d_hits, d_order, d_keys, d_sort_tmp, d_counter, d_chunk_counters;
     std::vector<cudaEvent_t> events;
-    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};  // H2D, traversal (even chunks), D2H, traversal (odd chunks)
     cudaStream_t main_stream = nullptr;
     int mode = 2, sort_rays = 0;
     int knobs[8] = {8, 12, 8, 18, 0, 12, 2048, 1024};  // CNDL_KNOB_*
@@ -518,8 +518,10 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
     CK(ctx->d_rays.ensure_scratch(R * sizeof(cndl_ray)));
     CK(ctx->d_hits.ensure_scratch(R * out_elt));
     // Three-stage pipeline over chunks: streams[0] carries every host->device copy back to back,
-    // streams[1] the traversal kernels, streams[2] every device->host copy; events chain the stages.
-    const int n_chunks_want = ctx->knobs[CNDL_KNOB_HOST_CHUNKS] > 0 ? ctx->knobs[CNDL_KNOB_HOST_CHUNKS] : 4;
+    // streams[1] / streams[3] the traversal kernels of even / odd chunks (so that the CTAs of the next
+    // chunk fill the SMs while the persistent kernel of the previous one drains its last rays),
+    // streams[2] every device->host copy; events chain the stages.
+    const int n_chunks_want = ctx->knobs[CNDL_KNOB_HOST_CHUNKS] > 0 ? ctx->knobs[CNDL_KNOB_HOST_CHUNKS] : 12;
     size_t chunk = (R + n_chunks_want - 1) / n_chunks_want;
     if (chunk < (1u << 16)) chunk = 1u << 16;
     const size_t n_chunks = (R + chunk - 1) / chunk;
@@ -537,13 +539,14 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
         char* dout = static_cast<char*>(ctx->d_hits.p) + lo * out_elt;
         CK(cudaMemcpyAsync(dr, rays + lo, n * sizeof(cndl_ray), cudaMemcpyHostToDevice, ctx->streams[0]));
         CK(cudaEventRecord(ctx->events[2 * k], ctx->streams[0]));
-        CK(cudaStreamWaitEvent(ctx->streams[1], ctx->events[2 * k], 0));
+        cudaStream_t ks = ctx->streams[(k & 1) ? 3 : 1];
+        CK(cudaStreamWaitEvent(ks, ctx->events[2 * k], 0));
         unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->d_chunk_counters.p) + 64 * k);
         rc = enqueue_trace(ctx, kind, dr, n, kind == Q_ANY ? nullptr : reinterpret_cast<cndl_hit*>(dout),
                            kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter,
-                           ctx->sort_rays ? static_cast<unsigned*>(ctx->d_order.p) + order_region_ints(chunk) * k : nullptr, ctx->streams[1]);
+                           ctx->sort_rays ? static_cast<unsigned*>(ctx->d_order.p) + order_region_ints(chunk) * k : nullptr, ks);
         if (rc != CNDL_OK) return rc;
-        CK(cudaEventRecord(ctx->events[2 * k + 1], ctx->streams[1]));
+        CK(cudaEventRecord(ctx->events[2 * k + 1], ks));
         CK(cudaStreamWaitEvent(ctx->streams[2], ctx->events[2 * k + 1], 0));
         char* hout = kind == Q_ANY ? reinterpret_cast<char*>(any_t + lo) : reinterpret_cast<char*>(hits + lo);
         CK(cudaMemcpyAsync(hout, dout, n * out_elt, cudaMemcpyDeviceToHost, ctx->streams[2]));

@@ -214,7 +214,7 @@ enum { CNDL_KNOB_BLOCKS_PER_SM = 0,   /* persistent CTAs (128 threads) per SM */
        CNDL_KNOB_IDLE_THRESHOLD = 2,  /* mode 2: finished lanes that trigger retire/refill */
        CNDL_KNOB_VARIANT = 3,         /* mode 2: kernel variant (node steps per vote, leaf prefetch) */
        CNDL_KNOB_STACK_LEAF_THRESHOLD = 5, /* mode 2, stack format: parked lanes that trigger the leaf phase */
-       CNDL_KNOB_HOST_CHUNKS = 4,     /* host-buffer queries: chunks in the copy/traverse/copy pipeline (0 = default 4) */
+       CNDL_KNOB_HOST_CHUNKS = 4,     /* host-buffer queries: chunks in the copy/traverse/copy pipeline (0 = default 12) */
        CNDL_KNOB_HOT_NODES = 6,       /* mode 2, stackless: top-of-tree nodes staged in shared memory (<= 7168; takes effect at cndl_commit) */
        CNDL_KNOB_BLOCK_THREADS = 7    /* mode 2, stackless, staged kernel: threads per CTA (256, 512 or 1024; CTAs per SM = 1024 / threads) */ };
 int cndl_set_tuning(cndl_ctx* ctx, int knob, int value);

@@ -53,10 +53,12 @@ struct BVHEntity {  // Intersector.h:43-49
 };
 
 struct RayHit { float T, U, V, W; int Mesh, TriangleIdx, Entity, Iters; };  // cndl_hit
+struct HitData { float Normal[3]; float UV[2]; float Emissivity; float Alpha; int Mesh; };  // cndl_hit_attr: the outputs of GetData
 struct Ray { float Origin[3]; float TMin; float Direction[3]; float TMax; }; // cndl_ray
 
 static_assert(sizeof(Vertex) == 32 && sizeof(BVH::Triangle) == 16 && sizeof(BVH::FlattenedNode) == 32 &&
-                  sizeof(BVH::FlattenedStackNode) == 64 && sizeof(BVHEntity) == 192 && sizeof(RayHit) == 32 && sizeof(Ray) == 32,
+                  sizeof(BVH::FlattenedStackNode) == 64 && sizeof(BVHEntity) == 192 && sizeof(RayHit) == 32 && sizeof(Ray) == 32 &&
+                  sizeof(HitData) == 32,
               "record layouts are the contract (SURVEY.md §8a)");
 
 template <typename T>
@@ -137,6 +139,25 @@ public:
         Check(cndl_intersect_any(m_Ctx, reinterpret_cast<const cndl_ray*>(Rays), Count, Traversals));
     }
 
+    // GetData (Include/TraverseBVHStackless.glsl:370-408) without the texture fetch: interpolated normal / UV, entity emissive / alpha.
+    void GetData(const RayHit* Hits, std::size_t Count, HitData* Output) {
+        Require();
+        Check(cndl_get_data(m_Ctx, reinterpret_cast<const cndl_hit*>(Hits), Count, reinterpret_cast<cndl_hit_attr*>(Output)));
+    }
+
+    // Physics::CollideBox / CollidePoint (Physics.cpp:175-228) on the GPU; stackless intersectors only, like Physics.h:15.
+    bool CollideBox(const float* Min, const float* Max) {
+        Require();
+        cndl_box b = {{Min[0], Min[1], Min[2]}, 0.0f, {Max[0], Max[1], Max[2]}, 0.0f};
+        cndl_collision c;
+        Check(cndl_collide_boxes(m_Ctx, &b, 1, &c));
+        return c.collided != 0;
+    }
+    bool CollidePoint(const float* Point) {
+        const float mn[3] = {Point[0] - 0.01f, Point[1] - 0.01f, Point[2] - 0.01f}, mx[3] = {Point[0] + 0.01f, Point[1] + 0.01f, Point[2] + 0.01f};
+        return CollideBox(mn, mx);
+    }
+
     // Replacement for BindEverything (Intersector.h:269-320): device pointers of the five buffers.
     void DeviceBuffers(const T** Nodes, const BVH::Triangle** Triangles, const Vertex** Vertices, const BVHEntity** Entities) {
         Require();
@@ -161,7 +182,7 @@ public:
                                 reinterpret_cast<cndl_vertex*>(m_BVHVertices.data())));
     }
 
-    bool Collide(const float* /*Point*/) { return false; }  // Intersector.h:354-358 (a stub in the reference too)
+    bool Collide(const float* Point) { return CollidePoint(Point); }  // Intersector.h:354-358 is a stub in the reference; here it answers
     void Recompile() {}                                      // Intersector.h:361-365
     cndl_ctx* Context() { return m_Ctx; }
 
@@ -181,5 +202,10 @@ private:
     bool m_Stackless = false;
     std::string m_LastError;
 };
+
+namespace Physics {  // Physics.h:14-15
+inline bool CollideBox(const float* Min, const float* Max, RayIntersector<BVH::StacklessTraversalNode>& Intersector) { return Intersector.CollideBox(Min, Max); }
+inline bool CollidePoint(const float* Point, RayIntersector<BVH::StacklessTraversalNode>& Intersector) { return Intersector.CollidePoint(Point); }
+}  // namespace Physics
 
 }  // namespace Candela

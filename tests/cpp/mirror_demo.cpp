@@ -74,6 +74,16 @@ int main() {
             if (h.T > 0) { ++n_hit; sum += h.T; if (h.Mesh != 5) { std::printf("BAD mesh %d\n", h.Mesh); return 1; } }
         Intersector.FetchCPUData();
         std::printf("OK %d %.3f nodes=%zu tris=%zu\n", n_hit, sum, Intersector.m_BVHNodes.size(), Intersector.m_BVHTriangles.size());
+        // GetData on the hit records and the collide query (Physics::CollideBox / CollidePoint)
+        std::vector<Candela::HitData> data(hits.size());
+        Intersector.GetData(hits.data(), hits.size(), data.data());
+        int n_data = 0;
+        for (std::size_t i = 0; i < hits.size(); ++i)
+            if (hits[i].T > 0 && data[i].Mesh == 5) ++n_data;
+        const float on_floor[3] = {1.0f, 0.0f, 1.0f}, in_air[3] = {1.0f, 1.5f, 1.0f};
+        const float bmin[3] = {0.5f, -0.2f, 0.5f}, bmax[3] = {0.8f, 0.2f, 0.8f};
+        std::printf("EXTRA data=%d collide=%d%d%d\n", n_data, (int)Candela::Physics::CollidePoint(on_floor, Intersector),
+                    (int)Candela::Physics::CollidePoint(in_air, Intersector), (int)Candela::Physics::CollideBox(bmin, bmax, Intersector));
         // pushing an entity of an unknown object must throw the reference's message
         Object other;
         other.m_ObjectID = 77;
