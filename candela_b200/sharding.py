@@ -68,3 +68,61 @@ def reduce_timing(ms_local: float, units_local: float, device="cpu", group=None)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(u, op=dist.ReduceOp.SUM, group=group)
     return float(t.item()), float(u.item())
+
+
+def broadcast_arrays(arrays, src: int = 0, device="cpu", group=None):
+    """Broadcasts a list of numpy arrays (any dtypes / shapes) from rank `src`; the other ranks pass None and
+    receive copies.  Sizes travel first, then the raw bytes of each array (torch.distributed.broadcast:
+    NCCL over NVLink on the GPUs, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return arrays
+    rank = dist.get_rank(group)
+    n = torch.tensor([len(arrays) if rank == src else 0], dtype=torch.int64, device=device)
+    dist.broadcast(n, src, group=group)
+    sizes = torch.zeros(int(n.item()), dtype=torch.int64, device=device)
+    if rank == src:
+        sizes = torch.tensor([a.nbytes for a in arrays], dtype=torch.int64, device=device)
+    dist.broadcast(sizes, src, group=group)
+    out = []
+    for k, nbytes in enumerate(int(x) for x in sizes.tolist()):
+        if rank == src:
+            buf = torch.from_numpy(np.ascontiguousarray(arrays[k]).view(np.uint8).reshape(-1).copy()).to(device)
+        else:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        if nbytes:
+            dist.broadcast(buf, src, group=group)
+        out.append(arrays[k] if rank == src else buf.cpu().numpy())
+    return out
+
+
+def broadcast_scene(ri, object_ids, src: int = 0, device="cuda", group=None):
+    """BVH distribution of SURVEY.md §8e: rank `src` has built (or loaded) the objects `object_ids` in `ri`; every
+    other rank passes an empty intersector of the same node format and receives them as prebuilt objects
+    (reference-layout nodes / triangles / vertices), so the scene is built once and replicated over NVLink.
+    Call BufferData() afterwards on every rank."""
+    import torch.distributed as dist
+    from . import api
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    rank = dist.get_rank(group)
+    arrays = None
+    if rank == src:
+        nodes, tris, verts = ri.read_buffers()
+        arrays = []
+        for oid in object_ids:
+            o = ri.object_data(oid)
+            ends = sorted(ri.object_data(x)["tri_offset"] for x in object_ids) + [len(tris)]
+            vends = sorted(ri.object_data(x)["vert_offset"] for x in object_ids) + [len(verts)]
+            t1 = min(e for e in ends if e > o["tri_offset"])
+            v1 = min(e for e in vends if e > o["vert_offset"])
+            t = tris[o["tri_offset"]:t1].copy()
+            t["v"] -= o["vert_offset"]          # AddPrebuiltObject takes object-local vertex indices (Intersector.h:190-197 rebases them)
+            arrays += [nodes[o["node_offset"]:o["node_offset"] + o["node_count"]], t, verts[o["vert_offset"]:v1]]
+    arrays = broadcast_arrays(arrays, src, device, group)
+    if rank != src:
+        for k, oid in enumerate(object_ids):
+            n, t, v = arrays[3 * k:3 * k + 3]
+            ri.AddPrebuiltObject(oid, n.view(ri.node_dtype), t.view(api.TRIANGLE_DT), v.view(api.VERTEX_DT))
+

@@ -75,3 +75,35 @@ def test_single_process_gather_is_identity():
     rec = torch.arange(len(pix) * 8, dtype=torch.float32).reshape(-1, 8)
     frame = sharding.gather_frame(rec, torch.from_numpy(pix), 40 * 30)
     assert torch.equal(frame[torch.from_numpy(pix)], rec)
+
+
+def _bcast_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    src = [rng.random((1000, 8)).astype(np.float32), rng.integers(0, 99, size=(333, 4)).astype(np.int32), np.zeros(0, np.uint8),
+           rng.integers(0, 255, size=77).astype(np.uint8)]
+    got = sharding.broadcast_arrays(src if rank == 0 else None, src=0)
+    if rank == 1:
+        out.put([np.asarray(a).tobytes() for a in got])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_broadcast_arrays_world2():
+    """BVH distribution: byte-exact replication of rank 0's buffers."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(3)
+    want = [rng.random((1000, 8)).astype(np.float32), rng.integers(0, 99, size=(333, 4)).astype(np.int32), np.zeros(0, np.uint8),
+            rng.integers(0, 255, size=77).astype(np.uint8)]
+    assert got == [a.tobytes() for a in want]
+

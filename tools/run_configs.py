@@ -165,7 +165,20 @@ def cfg_soup10m(args, rank, world, local_rank):
     T = len(i) // 3
     ri = cb.RayIntersector(cb.STACKLESS, device=local_rank)
     t0 = time.perf_counter()
-    ri.AddObject(2, v, i, m, builder=args.builder)
+    bcast_ms = None
+    if args.bvh == "broadcast" and world > 1:
+        # SURVEY.md §8e baseline: build on one GPU, replicate the reference-layout buffers over NVLink (NCCL broadcast)
+        if rank == 0:
+            ri.AddObject(2, v, i, m, builder=args.builder)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t1 = time.perf_counter()
+        sharding.broadcast_scene(ri, [2], src=0, device="cuda")
+        torch.cuda.synchronize()
+        dist.barrier()
+        bcast_ms = 1e3 * (time.perf_counter() - t1)
+    else:
+        ri.AddObject(2, v, i, m, builder=args.builder)
     wall_build = time.perf_counter() - t0
     build_ms = ri.last_build_ms
     ri.BufferData(True)
@@ -195,7 +208,8 @@ def cfg_soup10m(args, rank, world, local_rank):
         return None
     out = dict(config=f"heightfield_{T}_tris_random_rays", n_gpus=world, triangles=T, nodes=ri.node_count, gpu_build_ms=round(build_ms, 2),
                build_wall_ms=round(1e3 * wall_build, 1), builder="sah_exact" if args.builder == 0 else "lbvh", rays_all_ranks=int(rays_all),
-               trace_ms_max_over_ranks=round(t_max, 2), mrays_s=round(rays_all / t_max / 1e3, 1))
+               trace_ms_max_over_ranks=round(t_max, 2), mrays_s=round(rays_all / t_max / 1e3, 1), bvh=args.bvh,
+               bvh_broadcast_wall_ms=None if bcast_ms is None else round(bcast_ms, 1))
     if args.check_rays:
         from oracle import binding as ob
         nodes, tris, _ = ri.read_buffers()
@@ -224,6 +238,7 @@ def main():
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--rays", type=int, default=0)
     ap.add_argument("--builder", type=int, default=0)
+    ap.add_argument("--bvh", default="build", choices=["build", "broadcast"], help="soup10m at N > 1: every rank builds, or rank 0 builds and broadcasts")
     ap.add_argument("--bucket", type=int, default=0, help="1: the generator emits each batch octant-major (CNDL_GEN_BUCKET_OCTANTS)")
     ap.add_argument("--check-rays", type=int, default=1_000_000)
     ap.add_argument("--check-build", action="store_true")
