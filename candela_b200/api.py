@@ -37,6 +37,8 @@ EXPORTS = [
     "cndl_intersect_closest", "cndl_intersect_any", "cndl_intersect_closest_device", "cndl_intersect_any_device",
     "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_generate_bounce_rays_device", "cndl_host_alloc", "cndl_host_free",
     "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device", "cndl_generate_rays_device", "cndl_collide_boxes", "cndl_collide_boxes_device",
+    "cndl_model_load_obj", "cndl_model_free", "cndl_model_vertex_count", "cndl_model_index_count", "cndl_model_mesh_count", "cndl_model_vertices",
+    "cndl_model_indices", "cndl_model_mesh_ids", "cndl_model_mesh_name", "cndl_add_model", "cndl_pack_half2x16", "cndl_save", "cndl_load",
 ]
 
 
@@ -107,6 +109,22 @@ def load_library() -> C.CDLL:
     L.cndl_generate_rays_device.argtypes = [vp, C.POINTER(RaygenParams), vp, vp, sz, vp, vp, C.POINTER(sz), vp]
     L.cndl_collide_boxes.argtypes = [vp, vp, sz, vp]
     L.cndl_collide_boxes_device.argtypes = [vp, vp, sz, vp, vp]
+    L.cndl_model_load_obj.argtypes = [C.c_char_p, C.c_int32, C.POINTER(vp), C.c_char_p, sz]
+    L.cndl_model_free.argtypes = [vp]
+    L.cndl_model_free.restype = None
+    for f in ("cndl_model_vertex_count", "cndl_model_index_count", "cndl_model_mesh_count"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = sz
+    for f in ("cndl_model_vertices", "cndl_model_indices", "cndl_model_mesh_ids"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = vp
+    L.cndl_model_mesh_name.argtypes = [vp, sz]
+    L.cndl_model_mesh_name.restype = C.c_char_p
+    L.cndl_add_model.argtypes = [vp, C.c_uint32, vp, C.POINTER(BuildOpts)]
+    L.cndl_pack_half2x16.argtypes = [C.c_float, C.c_float]
+    L.cndl_pack_half2x16.restype = C.c_uint32
+    L.cndl_save.argtypes = [vp, C.c_char_p]
+    L.cndl_load.argtypes = [vp, C.c_char_p]
     L.cndl_host_alloc.argtypes = [sz]
     L.cndl_host_alloc.restype = vp
     L.cndl_host_free.argtypes = [vp]
@@ -146,6 +164,26 @@ def make_rays(origins, directions, tmax=0.0) -> np.ndarray:
     r["d"] = np.asarray(directions, dtype=np.float32).reshape(-1, 3)
     r["tmax"] = tmax
     return r
+
+
+def load_obj(path, first_mesh_number: int = 0):
+    """cndl_model_load_obj -> (vertices[VERTEX_DT], indices[u32], mesh_ids[i32 per triangle], mesh names): what
+    ModelFileLoader.cpp:101-185 hands to the intersector, without Assimp.  Host only."""
+    L = load_library()
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = L.cndl_model_load_obj(str(path).encode(), first_mesh_number, C.byref(h), err, len(err))
+    if rc != 0:
+        raise CandelaError(rc, err.value.decode())
+    try:
+        nv, ni, nm = L.cndl_model_vertex_count(h), L.cndl_model_index_count(h), L.cndl_model_mesh_count(h)
+        verts = np.frombuffer((C.c_char * (nv * 32)).from_address(L.cndl_model_vertices(h)), dtype=VERTEX_DT).copy()
+        idx = np.frombuffer((C.c_char * (ni * 4)).from_address(L.cndl_model_indices(h)), dtype=np.uint32).copy()
+        mids = np.frombuffer((C.c_char * (ni // 3 * 4)).from_address(L.cndl_model_mesh_ids(h)), dtype=np.int32).copy()
+        names = [L.cndl_model_mesh_name(h, k).decode() for k in range(nm)]
+    finally:
+        L.cndl_model_free(h)
+    return verts, idx, mids, names
 
 
 class PinnedBuffer:
@@ -227,6 +265,14 @@ class RayIntersector:
         tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
         verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
         self._check(self._lib.cndl_add_prebuilt_object(self._h, object_id, _p(nodes), len(nodes), _p(tris), len(tris), _p(verts), len(verts)))
+
+    def Save(self, path):
+        """Flat-buffer cache of every object's reference-layout buffers (cndl_save)."""
+        self._check(self._lib.cndl_save(self._h, str(path).encode()))
+
+    def Load(self, path):
+        """Restores a cndl_save file into this (empty) intersector; call BufferData() afterwards."""
+        self._check(self._lib.cndl_load(self._h, str(path).encode()))
 
     def BufferData(self, ClearCPUData: bool = True):
         """Intersector.h:322-351."""

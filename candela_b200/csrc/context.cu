@@ -46,7 +46,7 @@ struct DeviceBuffer {
     }
 };
 
-struct ObjectData { int tri_offset, vert_offset, node_offset, node_count; };  // _ObjectData, Intersector.h:51-56
+struct ObjectData { int tri_offset, vert_offset, node_offset, node_count, tri_count, vert_count; };  // _ObjectData, Intersector.h:51-56 (+ counts)
 
 }  // namespace
 
@@ -74,7 +74,7 @@ struct cndl_ctx {
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};  // H2D, traversal (even chunks), D2H, traversal (odd chunks)
     cudaStream_t main_stream = nullptr;
     int mode = 2, sort_rays = 0;
-    int knobs[8] = {8, 12, 8, 18, 0, 12, 2048, 1024};  // CNDL_KNOB_*
+    int knobs[8] = {8, 12, 8, 0, 0, 12, 4096, 1024};  // CNDL_KNOB_*
     // hot-first derived layout of the stackless nodes (kernels_hot.cu), rebuilt by cndl_commit
     DeviceBuffer nodes2, perm, ents2, hot_scratch, d_objects;
     std::vector<int2> h_objects;                 // (node_offset, node_count) in insertion order
@@ -153,7 +153,13 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
             launch_octant_partition(d_rays, R, order_region, reinterpret_cast<int*>(order_region + R), st, ctx->launches);
             order = RayOrder{order_region, nullptr, 0};
         }
-        const int variant = ctx->knobs[CNDL_KNOB_VARIANT];
+        int variant = ctx->knobs[CNDL_KNOB_VARIANT];
+        if (variant == 0) {
+            // automatic: a scene that fits the 126 MB L2 is served best by the plain kernel; once the node and triangle
+            // records spill to DRAM, staging the top of the tree in shared memory wins (10 M triangles: +8.7 %)
+            const size_t working_set = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 48;
+            variant = (!stack && working_set > ((size_t)96 << 20)) ? 34 : 18;
+        }
         int steps = variant & 7;
         if (steps < 1 || steps > 4) steps = 2;
         const int park = ctx->knobs[stack ? CNDL_KNOB_STACK_LEAF_THRESHOLD : CNDL_KNOB_LEAF_THRESHOLD], idle = ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD];
@@ -300,6 +306,8 @@ int cndl_add_prebuilt_object(cndl_ctx* ctx, uint32_t object_id, const void* node
     od.tri_offset = (int)ctx->n_tris;
     od.vert_offset = (int)ctx->n_verts;
     od.node_count = (int)N;
+    od.tri_count = (int)T;
+    od.vert_count = (int)V;
     ctx->objects[object_id] = od;
     ctx->n_nodes += N;
     ctx->n_tris += T;
@@ -361,6 +369,8 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     od.tri_offset = (int)ctx->n_tris;
     od.vert_offset = (int)ctx->n_verts;
     od.node_count = (int)N;
+    od.tri_count = (int)T;
+    od.vert_count = (int)V;
     ctx->objects[object_id] = od;
     ctx->n_nodes += N;
     ctx->n_tris += T;
@@ -686,6 +696,94 @@ int cndl_collide_boxes(cndl_ctx* ctx, const cndl_box* boxes, size_t n, cndl_coll
     if (rc != CNDL_OK) return rc;
     CK(cudaMemcpyAsync(out, ctx->d_hits.p, n * sizeof(cndl_collision), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return CNDL_OK;
+}
+
+// ---- flat-buffer serialisation of the built scene (the reference rebuilds every BVH at every
+// launch, Pipeline.cpp:1019-1028).  File: header, object table, then the reference-layout node / triangle / vertex
+// buffers exactly as cndl_read_buffers returns them.
+namespace {
+struct FileHeader { char magic[8]; uint32_t version, format; uint64_t n_objects, n_nodes, n_tris, n_verts; };
+struct FileObject { uint32_t id; int32_t node_offset, node_count, tri_offset, tri_count, vert_offset, vert_count; };
+const char kMagic[8] = {'C', 'N', 'D', 'L', 'B', 'V', 'H', '1'};
+}  // namespace
+
+int cndl_save(cndl_ctx* ctx, const char* path) {
+    if (!ctx || !path) return CNDL_ERR_INVALID;
+    if (ctx->n_tris == 0) return ctx->fail(CNDL_ERR_INVALID, "nothing to save");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<char> nodes(ctx->n_nodes * ctx->node_size);
+    std::vector<cndl_triangle> tris(ctx->n_tris);
+    std::vector<cndl_vertex> verts(ctx->n_verts);
+    int rc = cndl_read_buffers(ctx, nodes.data(), tris.data(), verts.data());
+    if (rc != CNDL_OK) return rc;
+    FileHeader h;
+    std::memcpy(h.magic, kMagic, 8);
+    h.version = 1;
+    h.format = (uint32_t)ctx->format;
+    h.n_objects = ctx->objects.size();
+    h.n_nodes = ctx->n_nodes; h.n_tris = ctx->n_tris; h.n_verts = ctx->n_verts;
+    std::vector<FileObject> table;
+    for (const auto& kv : ctx->objects)
+        table.push_back(FileObject{kv.first, kv.second.node_offset, kv.second.node_count, kv.second.tri_offset, kv.second.tri_count, kv.second.vert_offset,
+                                   kv.second.vert_count});
+    std::sort(table.begin(), table.end(), [](const FileObject& a, const FileObject& b) { return a.node_offset < b.node_offset; });
+    std::FILE* f = std::fopen(path, "wb");
+    if (!f) return ctx->fail(CNDL_ERR_INVALID, std::string("cannot open ") + path + " for writing");
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(table.data(), sizeof(FileObject), table.size(), f) == table.size() &&
+              std::fwrite(nodes.data(), 1, nodes.size(), f) == nodes.size() && std::fwrite(tris.data(), sizeof(cndl_triangle), tris.size(), f) == tris.size() &&
+              std::fwrite(verts.data(), sizeof(cndl_vertex), verts.size(), f) == verts.size();
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? CNDL_OK : ctx->fail(CNDL_ERR_INVALID, std::string("short write to ") + path);
+}
+
+int cndl_load(cndl_ctx* ctx, const char* path) {
+    if (!ctx || !path) return CNDL_ERR_INVALID;
+    if (ctx->n_tris != 0) return ctx->fail(CNDL_ERR_INVALID, "cndl_load needs an empty context: leaf packs in the file hold global triangle offsets");
+    std::FILE* f = std::fopen(path, "rb");
+    if (!f) return ctx->fail(CNDL_ERR_INVALID, std::string("cannot open ") + path);
+    FileHeader h;
+    auto bad = [&](const char* why) { std::fclose(f); return ctx->fail(CNDL_ERR_INVALID, std::string(path) + ": " + why); };
+    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, kMagic, 8) != 0 || h.version != 1) return bad("not a candela_b200 BVH file");
+    if ((int)h.format != ctx->format) return bad("node format differs from the context's (stackless vs stack)");
+    if (h.n_objects == 0 || h.n_objects > (1u << 24) || h.n_nodes == 0 || h.n_nodes > 0x7FFFFFF0ull || h.n_tris == 0 || h.n_tris > (1ull << 27) ||
+        h.n_verts == 0 || h.n_verts > 0x7FFFFFF0ull)
+        return bad("implausible sizes");
+    std::vector<FileObject> table(h.n_objects);
+    std::vector<char> nodes(h.n_nodes * ctx->node_size);
+    std::vector<cndl_triangle> tris(h.n_tris);
+    std::vector<cndl_vertex> verts(h.n_verts);
+    if (std::fread(table.data(), sizeof(FileObject), table.size(), f) != table.size() || std::fread(nodes.data(), 1, nodes.size(), f) != nodes.size() ||
+        std::fread(tris.data(), sizeof(cndl_triangle), tris.size(), f) != tris.size() || std::fread(verts.data(), sizeof(cndl_vertex), verts.size(), f) != verts.size())
+        return bad("truncated file");
+    std::fclose(f);
+    for (const auto& o : table)
+        if (o.node_offset < 0 || o.node_count <= 0 || (uint64_t)o.node_offset + (uint64_t)o.node_count > h.n_nodes || o.tri_offset < 0 || o.tri_count <= 0 ||
+            (uint64_t)o.tri_offset + (uint64_t)o.tri_count > h.n_tris || o.vert_offset < 0 || o.vert_count <= 0 ||
+            (uint64_t)o.vert_offset + (uint64_t)o.vert_count > h.n_verts)
+            return ctx->fail(CNDL_ERR_INVALID, std::string(path) + ": object table out of range");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->main_stream;
+    const size_t ns = ctx->node_size;
+    CK(ctx->nodes.reserve((h.n_nodes + 1) * ns, st));
+    CK(ctx->tris.reserve(h.n_tris * sizeof(cndl_triangle), st));
+    CK(ctx->verts.reserve(h.n_verts * sizeof(cndl_vertex), st));
+    CK(cudaMemcpyAsync(ctx->nodes.p, nodes.data(), h.n_nodes * ns, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(static_cast<char*>(ctx->nodes.p) + h.n_nodes * ns, 0, ns, st));
+    CK(cudaMemcpyAsync(ctx->tris.p, tris.data(), h.n_tris * sizeof(cndl_triangle), cudaMemcpyHostToDevice, st));  // vertex indices are global already
+    CK(cudaMemcpyAsync(ctx->verts.p, verts.data(), h.n_verts * sizeof(cndl_vertex), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    for (const auto& o : table) {
+        ObjectData od;
+        od.node_offset = o.node_offset; od.node_count = o.node_count; od.tri_offset = o.tri_offset; od.tri_count = o.tri_count;
+        od.vert_offset = o.vert_offset; od.vert_count = o.vert_count;
+        ctx->objects[o.id] = od;
+    }
+    ctx->n_nodes = h.n_nodes; ctx->n_tris = h.n_tris; ctx->n_verts = h.n_verts;
+    ctx->nodes.bytes = h.n_nodes * ns;
+    ctx->tris.bytes = h.n_tris * sizeof(cndl_triangle);
+    ctx->verts.bytes = h.n_verts * sizeof(cndl_vertex);
+    ctx->committed = false;
     return CNDL_OK;
 }
 

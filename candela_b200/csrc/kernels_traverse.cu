@@ -243,7 +243,7 @@ __global__ void collide_boxes_kernel(SceneView s, const float4* __restrict__ ver
         const int start = __ldg(&en->node_offset), count = __ldg(&en->node_count);
         int ptr = start, iters = 0;
         while (ptr >= 0 && iters < 1024) {
-            // :101 also admits Pointer == m_BVHNodes.size(), an out-of-bounds read; oracle and kernel stop there instead
+            // :101 also admits Pointer == m_BVHNodes.size(), an out-of-bounds read; the walk stops there instead
             if (ptr < start || ptr > start + count || ptr >= s.total_nodes) break;
             ++iters;
             const float4 mn = __ldg(s.nodes + 2 * (size_t)ptr), mx = __ldg(s.nodes + 2 * (size_t)ptr + 1);

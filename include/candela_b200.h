@@ -201,6 +201,31 @@ typedef struct cndl_collision { int32_t collided, mesh, tri, entity; } cndl_coll
 int cndl_collide_boxes(cndl_ctx* ctx, const cndl_box* boxes, size_t n, cndl_collision* out);
 int cndl_collide_boxes_device(cndl_ctx* ctx, const cndl_box* d_boxes, size_t n, cndl_collision* d_out, void* stream);
 
+/* Scene ingest without Assimp (ModelFileLoader.cpp:101-185): reads a Wavefront OBJ into what AddObject consumes — 32-byte Vertex
+ * records (normal / UV packed like glm::packHalf2x16, ModelFileLoader.cpp:133-155; tangents zero), object-local indices with
+ * the per-mesh vertex offset applied, and one GlobalMeshNumber per triangle (one mesh per usemtl / o / g run, numbered
+ * consecutively from first_mesh_number like GlobalMeshCounter, :104-105).  Polygons are fan-triangulated; vertices are joined per
+ * mesh on their (v, vt, vn) triple.  err (optional) receives a message on failure.  Host only; no GPU needed. */
+typedef struct cndl_model cndl_model;
+int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model** out, char* err, size_t err_cap);
+void cndl_model_free(cndl_model* m);
+size_t cndl_model_vertex_count(const cndl_model* m);
+size_t cndl_model_index_count(const cndl_model* m);
+size_t cndl_model_mesh_count(const cndl_model* m);
+const cndl_vertex* cndl_model_vertices(const cndl_model* m);
+const uint32_t* cndl_model_indices(const cndl_model* m);
+const int32_t* cndl_model_mesh_ids(const cndl_model* m);
+const char* cndl_model_mesh_name(const cndl_model* m, size_t mesh);
+int cndl_add_model(cndl_ctx* ctx, uint32_t object_id, const cndl_model* m, const cndl_build_opts* opts);  /* = cndl_add_object */
+/* glm::packHalf2x16 (glm 0.9.8.5 detail::toFloat16: round to nearest, ties up in magnitude). */
+uint32_t cndl_pack_half2x16(float x, float y);
+
+/* Flat-buffer cache of the built scene (the reference rebuilds every BVH at every launch, Pipeline.cpp:1019-1028):
+ * cndl_save writes every object's reference-layout nodes / triangles / vertices and the object table; cndl_load restores
+ * them into an EMPTY context of the same node format (call cndl_commit afterwards). */
+int cndl_save(cndl_ctx* ctx, const char* path);
+int cndl_load(cndl_ctx* ctx, const char* path);
+
 /* Pinned host memory for ray / hit batches. */
 void* cndl_host_alloc(size_t bytes);
 void cndl_host_free(void* p);
@@ -212,7 +237,8 @@ int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays);
 enum { CNDL_KNOB_BLOCKS_PER_SM = 0,   /* persistent CTAs (128 threads) per SM */
        CNDL_KNOB_LEAF_THRESHOLD = 1,  /* mode 2: parked-at-leaf lanes that trigger the leaf phase */
        CNDL_KNOB_IDLE_THRESHOLD = 2,  /* mode 2: finished lanes that trigger retire/refill */
-       CNDL_KNOB_VARIANT = 3,         /* mode 2: kernel variant (node steps per vote, leaf prefetch) */
+       CNDL_KNOB_VARIANT = 3,         /* mode 2: 0 = automatic; low 3 bits = node steps per vote round (1..4); 32+ = top of the tree
+                                         staged in shared memory, 40+ = two rays per lane (both stackless only) */
        CNDL_KNOB_STACK_LEAF_THRESHOLD = 5, /* mode 2, stack format: parked lanes that trigger the leaf phase */
        CNDL_KNOB_HOST_CHUNKS = 4,     /* host-buffer queries: chunks in the copy/traverse/copy pipeline (0 = default 12) */
        CNDL_KNOB_HOT_NODES = 6,       /* mode 2, stackless: top-of-tree nodes staged in shared memory (<= 7168; takes effect at cndl_commit) */

@@ -299,6 +299,8 @@ def ref_lib() -> C.CDLL:
         R.ref_build.restype = C.c_int
         R.ref_build.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]
         R.ref_fetch.argtypes = [vp, vp, vp]
+        R.ref_pack_half2x16.argtypes = [C.c_float, C.c_float]
+        R.ref_pack_half2x16.restype = C.c_uint32
         R.ref_collide_box.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp]
         _ref = R
     return _ref
@@ -340,3 +342,9 @@ def ref_collide_boxes(nodes, tris, verts, entities, boxes) -> np.ndarray:
     out = np.zeros(len(boxes), dtype=np.int32)
     ref_lib().ref_collide_box(_p(nodes), len(nodes), _p(tris), len(tris), _p(verts), len(verts), _p(entities), len(entities), _p(boxes), len(boxes), _p(out))
     return out
+
+
+def ref_pack_half2x16(x: float, y: float) -> int:
+    """glm::packHalf2x16 of the reference's vendored glm (oracle/_ref)."""
+    return int(ref_lib().ref_pack_half2x16(float(x), float(y)))
+

@@ -22,6 +22,8 @@
 #include "BVH/BVHConstructor.h"
 #include "Object.h"
 #include "Physics.h"
+#include <glm/glm.hpp>
+#include <glm/gtc/packing.hpp>
 
 #include <new>
 
@@ -155,5 +157,8 @@ int ref_collide_box(const void* nodes, uint64_t n_nodes, const void* tris, uint6
     ri->m_BVHNodes.~VN(); ri->m_BVHTriangles.~VT(); ri->m_BVHVertices.~VV(); ri->m_BVHEntities.~VE();
     return 0;
 }
+
+// glm::packHalf2x16 of the reference's vendored glm 0.9.8.5 (what ModelFileLoader.cpp:133-155 packs vertices with).
+uint32_t ref_pack_half2x16(float x, float y) { return glm::packHalf2x16(glm::vec2(x, y)); }
 
 }  // extern "C"

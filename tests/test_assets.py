@@ -1,0 +1,145 @@
+"""Scene ingest (OBJ -> Vertex packing of ModelFileLoader.cpp:101-185) and the flat-buffer BVH cache —
+SURVEY.md §8f ranks 3 and 4a.  The half-float packing is PINNED against glm::packHalf2x16 of the reference's
+vendored glm, compiled into oracle/_ref."""
+import numpy as np
+import pytest
+
+
+def _glm_like_pack(x):
+    """numpy restatement of detail::toFloat16 for normal-range inputs: round to nearest, ties UP in magnitude."""
+    x = np.asarray(x, np.float32)
+    i = x.view(np.int32).astype(np.int64)
+    s = (i >> 16) & 0x8000
+    e = ((i >> 23) & 0xFF) - 112
+    m = i & 0x7FFFFF
+    up = (m & 0x1000) != 0
+    m = np.where(up, m + 0x2000, m)
+    carry = (m & 0x800000) != 0
+    m = np.where(carry, 0, m)
+    e = np.where(carry, e + 1, e)
+    return (s | (e << 10) | (m >> 13)).astype(np.uint32)
+
+
+def test_pack_half_matches_the_reference_glm(cb, ob):
+    L = cb.api.load_library()
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.normal(size=4000).astype(np.float32), (rng.random(2000, dtype=np.float32) * 2 - 1) * np.float32(1e-6),
+                           (rng.random(2000, dtype=np.float32) * 2 - 1) * np.float32(7e4),
+                           np.array([0.0, -0.0, 1.0, -1.0, 65504.0, 65519.9, 65520.0, 1e9, np.inf, -np.inf, np.nan, 6.1e-5, 5.96e-8, 2.98e-8, 1e-10], np.float32),
+                           np.arange(1024, dtype=np.uint32).astype(np.uint32).__lshift__(13).__add__(0x3F801000).view(np.float32)])  # exact ties
+    mine = np.array([L.cndl_pack_half2x16(float(v), float(-v)) for v in vals], np.uint32)
+    normal = np.isfinite(vals) & (np.abs(vals) > 1e-4) & (np.abs(vals) < 6e4)
+    assert np.array_equal(mine[normal] & 0xFFFF, _glm_like_pack(vals[normal]))
+    rne = vals.astype(np.float16).view(np.uint16).astype(np.uint32)
+    ties = np.arange(1024, dtype=np.uint32)
+    assert np.mean((mine[normal] & 0xFFFF) == rne[normal]) > 0.9 and np.any((mine[-1024:] & 0xFFFF) != rne[-1024:])   # differs from IEEE RNE exactly on ties
+    if ob.REFERENCE_ROOT.exists():
+        ref = np.array([ob.ref_pack_half2x16(float(v), float(-v)) for v in vals], np.uint32)
+        assert np.array_equal(mine, ref), "cndl_pack_half2x16 differs from the reference's glm::packHalf2x16"
+
+
+def _write_obj(path, P, F, N=None, UV=None, groups=None):
+    with open(path, "w") as f:
+        f.write("# test asset\n")
+        for p in P:
+            f.write(f"v {p[0]:.9g} {p[1]:.9g} {p[2]:.9g}\n")
+        if UV is not None:
+            for t in UV:
+                f.write(f"vt {t[0]:.9g} {t[1]:.9g}\n")
+        if N is not None:
+            for n in N:
+                f.write(f"vn {n[0]:.9g} {n[1]:.9g} {n[2]:.9g}\n")
+        groups = groups or [("all", 0, len(F))]
+        for name, lo, hi in groups:
+            f.write(f"usemtl {name}\n")
+            for a, b, c in F[lo:hi]:
+                if N is not None and UV is not None:
+                    f.write(f"f {a+1}/{a+1}/{a+1} {b+1}/{b+1}/{b+1} {c+1}/{c+1}/{c+1}\n")
+                elif N is not None:
+                    f.write(f"f {a+1}//{a+1} {b+1}//{b+1} {c+1}//{c+1}\n")
+                else:
+                    f.write(f"f {a+1} {b+1} {c+1}\n")
+
+
+def test_obj_loader_reproduces_the_vertex_packing(cb, golden_meshes, tmp_path):
+    P, F = golden_meshes["soup400"]
+    rng = np.random.default_rng(1)
+    N = rng.normal(size=P.shape).astype(np.float32)
+    N /= np.linalg.norm(N, axis=1, keepdims=True)
+    UV = rng.random((len(P), 2), dtype=np.float32) * 3 - 1
+    path = tmp_path / "soup.obj"
+    groups = [("stone", 0, 150), ("wood", 150, 151), ("glass", 151, len(F))]
+    _write_obj(path, P, F, N, UV, groups)
+    verts, idx, mids, names = cb.api.load_obj(path, first_mesh_number=7)
+    assert names == ["stone", "wood", "glass"] and len(idx) == 3 * len(F)
+    assert np.array_equal(mids, np.repeat([7, 8, 9], [150, 1, len(F) - 151]))
+    # geometry survives: the same triangles, corner for corner (%.9g round-trips float32)
+    assert np.array_equal(verts["position"][idx.reshape(-1, 3)][..., :3], P[F])
+    assert np.all(verts["position"][:, 3] == 1.0)
+    # indices of a mesh stay inside its own vertex range (per-mesh join, offset applied like BVHConstructor.cpp:981-1002)
+    tri_first = idx.reshape(-1, 3).min(1)
+    assert tri_first[150] > idx.reshape(-1, 3)[:150].max() and tri_first[151:].min() > idx.reshape(-1, 3)[150].max()
+    # packing: data.x = packHalf2x16(n.xy), data.y = packHalf2x16(n.z, tan.x = 0), data.z = 0, texcoords = packHalf2x16(uv)
+    L = cb.api.load_library()
+    src = F.reshape(-1)
+    for k in rng.integers(0, len(idx), 300):
+        v, s = verts[idx[k]], src[k]
+        assert v["normal_tangent"][0] == L.cndl_pack_half2x16(float(N[s, 0]), float(N[s, 1]))
+        assert v["normal_tangent"][1] == L.cndl_pack_half2x16(float(N[s, 2]), 0.0) and v["normal_tangent"][2] == 0
+        assert v["texcoords"] == L.cndl_pack_half2x16(float(UV[s, 0]), float(UV[s, 1]))
+    # quads and negative indices; no normals / UVs -> zeros
+    q = tmp_path / "quad.obj"
+    q.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nf -5 -4 -3 -2\ng top\nf 1 2 5\n")
+    verts, idx, mids, names = cb.api.load_obj(q)
+    assert len(idx) == 9 and list(mids) == [0, 0, 1] and names == ["default", "top"] and np.all(verts["texcoords"] == 0)
+    assert np.array_equal(verts["position"][idx[:6]][:, :3], np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32))
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nf 1 2 3\n")
+    with pytest.raises(cb.CandelaError, match="out of range"):
+        cb.api.load_obj(bad)
+    with pytest.raises(cb.CandelaError, match="cannot open"):
+        cb.api.load_obj(tmp_path / "missing.obj")
+
+
+@pytest.mark.gpu
+def test_loaded_model_builds_and_cache_round_trips(cb, ob, golden_meshes, tmp_path):
+    from helpers import rays_in_box
+    P, F = golden_meshes["dragon"]
+    path = tmp_path / "dragon.obj"
+    _write_obj(path, P, F, groups=[("a", 0, 9000), ("b", 9000, len(F))])
+    verts, idx, mids, _ = cb.api.load_obj(path, first_mesh_number=3)
+    Ps, Fs = golden_meshes["soup400"]
+    rays = rays_in_box(P.min(0) - 1, P.max(0) + 1, 50000, 8)
+    for fmt, ofmt in ((cb.STACKLESS, ob.STACKLESS), (cb.STACK, ob.STACK)):
+        ri = cb.RayIntersector(fmt)
+        ri.AddObject(2, verts, idx, mids)
+        ri.AddObject(3, cb.make_vertices(Ps), Fs.ravel(), np.full(len(Fs), 9, np.int32))
+        ri.BufferData()
+        ri.PushEntity(2)
+        ri.PushEntity(3, model=np.array([[1, 0, 0, 0.5], [0, 1, 0, 0.2], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32))
+        ri.BufferEntities()
+        sc = ob.Scene(ofmt)
+        sc.add_object(2, verts, idx, mids)
+        sc.add_object(3, ob.make_vertices(Ps), Fs.ravel(), np.full(len(Fs), 9, np.int32))
+        nodes, tris, vv = ri.read_buffers()
+        assert nodes.tobytes() == sc.nodes.tobytes() and tris.tobytes() == sc.tris.tobytes()
+        want = ri.IntersectRays(rays)
+        assert set(np.unique(want["mesh"])) >= {3, 4}
+        cache = tmp_path / f"scene_{fmt}.cndl"
+        ri.Save(cache)
+        r2 = cb.RayIntersector(fmt)
+        r2.Load(cache)
+        r2.BufferData()
+        r2.PushEntity(2)
+        r2.PushEntity(3, model=np.array([[1, 0, 0, 0.5], [0, 1, 0, 0.2], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32))
+        r2.BufferEntities()
+        n2, t2, v2 = r2.read_buffers()
+        assert n2.tobytes() == nodes.tobytes() and t2.tobytes() == tris.tobytes() and v2.tobytes() == vv.tobytes()
+        assert r2.object_data(3) == ri.object_data(3)
+        assert r2.IntersectRays(rays).tobytes() == want.tobytes()
+        with pytest.raises(cb.CandelaError, match="empty context"):
+            r2.Load(cache)
+        other = cb.RayIntersector(cb.STACK if fmt == cb.STACKLESS else cb.STACKLESS)
+        with pytest.raises(cb.CandelaError, match="node format"):
+            other.Load(cache)
+        other.close(); r2.close(); ri.close()

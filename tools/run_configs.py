@@ -181,6 +181,9 @@ def cfg_soup10m(args, rank, world, local_rank):
         ri.AddObject(2, v, i, m, builder=args.builder)
     wall_build = time.perf_counter() - t0
     build_ms = ri.last_build_ms
+    if args.knobs:
+        for kid, val in enumerate(int(x) for x in args.knobs.split(",")):
+            ri.set_tuning(kid, val)
     ri.BufferData(True)
     ri.PushEntity(2)
     ri.BufferEntities()
@@ -238,6 +241,7 @@ def main():
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--rays", type=int, default=0)
     ap.add_argument("--builder", type=int, default=0)
+    ap.add_argument("--knobs", default="", help="comma-separated tuning knobs in knob-id order (see dev_bench.py)")
     ap.add_argument("--bvh", default="build", choices=["build", "broadcast"], help="soup10m at N > 1: every rank builds, or rank 0 builds and broadcasts")
     ap.add_argument("--bucket", type=int, default=0, help="1: the generator emits each batch octant-major (CNDL_GEN_BUCKET_OCTANTS)")
     ap.add_argument("--check-rays", type=int, default=1_000_000)
