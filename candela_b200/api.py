@@ -333,7 +333,8 @@ class RayIntersector:
         self._check(self._lib.cndl_read_buffers(self._h, _p(nodes), _p(tris), _p(verts)))
         return nodes, tris, verts
 
-    def set_traversal_mode(self, mode: int, sort_rays: bool = False):
+    def set_traversal_mode(self, mode: int, sort_rays: int = 0):
+        """sort_rays: 0 off, 1 (or True) octant buckets, 2 octant + origin Morton order."""
         self._check(self._lib.cndl_set_traversal_mode(self._h, mode, int(sort_rays)))
 
     def set_tuning(self, knob: int, value: int):

@@ -1054,4 +1054,55 @@ int build_lbvh_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, floa
     return CNDL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ray ordering for scenes that do not fit the L2 (sort_rays = 2): rays sorted by direction octant (major) and the
+// Morton code of their origin cell (6 bits per axis inside `lo`..`hi`, the world bounds of the scene), with the LBVH
+// builder's radix sort.  Rays that follow each other then walk neighbouring subtrees, so node and triangle records
+// fetched from DRAM by one warp are found in L2 by the next.  10 M-triangle scene, 12.5 M random rays: 5.26 -> 4.33 ms
+// of traversal, but 1.4 ms of sorting (three LSD passes), so it is opt-in.  A ray's result does not depend on its slot.
+namespace {
+__global__ void ray_morton_keys_kernel(const cndl_ray* __restrict__ rays, unsigned R, float3 lo, float3 scale, unsigned* __restrict__ keys,
+                                       unsigned* __restrict__ vals) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const float4 o = __ldg(reinterpret_cast<const float4*>(rays + i)), d = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+    const unsigned qx = (unsigned)fminf(fmaxf((o.x - lo.x) * scale.x, 0.0f), 63.0f), qy = (unsigned)fminf(fmaxf((o.y - lo.y) * scale.y, 0.0f), 63.0f),
+                   qz = (unsigned)fminf(fmaxf((o.z - lo.z) * scale.z, 0.0f), 63.0f);
+    const unsigned octant = (d.x > 0.0f ? 1u : 0u) | (d.y > 0.0f ? 2u : 0u) | (d.z > 0.0f ? 4u : 0u);
+    keys[i] = (octant << 18) | (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);
+    vals[i] = i;
+}
+}  // namespace
+
+size_t ray_sort_scratch_ints(size_t R) {
+    const size_t n_tiles = (R + kRsTile - 1) / kRsTile;
+    const size_t scan_n = (size_t)kRsBins * n_tiles + 16;
+    return 3 * R + 2 * scan_n + scan_n / kScanTile + 64;
+}
+
+cudaError_t sort_rays_morton(const cndl_ray* rays, size_t R, const float lo[3], const float hi[3], unsigned* order_out, int* scratch, cudaStream_t st,
+                             LaunchCounter& lc) {
+    if (R == 0) return cudaSuccess;
+    const size_t n_tiles = (R + kRsTile - 1) / kRsTile;
+    const size_t scan_n = (size_t)kRsBins * n_tiles + 16;
+    unsigned* k0 = reinterpret_cast<unsigned*>(scratch);
+    unsigned* k1 = k0 + R;
+    unsigned* v0 = k1 + R;  // 21-bit keys = three 8-bit passes: starting in the scratch list, the third pass lands in order_out
+    unsigned* v1 = order_out;
+    int* counts = scratch + 3 * R;
+    int* offsets = counts + scan_n;
+    int* block_sums = offsets + scan_n;
+    int* total = block_sums + scan_n / kScanTile + 32;
+    float3 l = make_float3(lo[0], lo[1], lo[2]), sc;
+    sc.x = hi[0] > lo[0] ? 64.0f / (hi[0] - lo[0]) : 0.0f;
+    sc.y = hi[1] > lo[1] ? 64.0f / (hi[1] - lo[1]) : 0.0f;
+    sc.z = hi[2] > lo[2] ? 64.0f / (hi[2] - lo[2]) : 0.0f;
+    ray_morton_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(rays, (unsigned)R, l, sc, k0, v0);
+    lc.n++;
+    cudaError_t e = radix_sort_pairs(&k0, &v0, &k1, &v1, (unsigned)R, 21, counts, offsets, block_sums, total, st, lc);
+    if (e != cudaSuccess) return e;
+    if (v0 != order_out) e = cudaMemcpyAsync(order_out, v0, R * sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
+    return e;
+}
+
 }  // namespace cndl

@@ -26,4 +26,9 @@ struct BuildRequest {
 // Returns CNDL_OK or a negative cndl_status with `err` set. Work is enqueued on `st` and complete on return.
 int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* build_ms, std::string& err);
 
+// sort_rays = 2: order[0..R) = ray indices sorted by (direction octant, Morton code of the origin cell inside lo..hi).
+size_t ray_sort_scratch_ints(size_t R);
+cudaError_t sort_rays_morton(const cndl_ray* rays, size_t R, const float lo[3], const float hi[3], unsigned* order_out, int* scratch, cudaStream_t st,
+                             LaunchCounter& lc);
+
 }  // namespace cndl

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <array>
 #include <new>
 #include <string>
 #include <unordered_map>
@@ -73,7 +74,8 @@ struct cndl_ctx {
     std::vector<cudaEvent_t> events;
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};  // H2D, traversal (even chunks), D2H, traversal (odd chunks)
     cudaStream_t main_stream = nullptr;
-    int mode = 2, sort_rays = 0;
+    int mode = 2, sort_rays = 0;   // sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order
+    float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};  // bounds of all entities (for sort_rays = 2)
     int knobs[8] = {8, 12, 8, 0, 0, 12, 4096, 1024};  // CNDL_KNOB_*
     // hot-first derived layout of the stackless nodes (kernels_hot.cu), rebuilt by cndl_commit
     DeviceBuffer nodes2, perm, ents2, hot_scratch, d_objects;
@@ -130,7 +132,7 @@ int upload_hot_entities(cndl_ctx* ctx) {
     return CNDL_OK;
 }
 
-size_t order_region_ints(size_t R) { return R + octant_partition_scratch_ints(R) + 16; }
+size_t order_region_ints(size_t R) { return R + std::max(octant_partition_scratch_ints(R), ray_sort_scratch_ints(R)) + 16; }
 
 int check_ready(cndl_ctx* ctx) {
     if (!ctx->committed) return ctx->fail(CNDL_ERR_NOT_COMMITTED, "cndl_commit has not been called");
@@ -150,7 +152,13 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
     else {
         RayOrder order{nullptr, nullptr, 0};
         if (ctx->sort_rays && order_region && R >= 65536) {
-            launch_octant_partition(d_rays, R, order_region, reinterpret_cast<int*>(order_region + R), st, ctx->launches);
+            if (ctx->sort_rays == 2) {
+                cudaError_t se = sort_rays_morton(d_rays, R, ctx->world_lo, ctx->world_hi, order_region, reinterpret_cast<int*>(order_region + R), st,
+                                                  ctx->launches);
+                if (se != cudaSuccess) return ctx->cuda_fail(se, "ray sort");
+            } else {
+                launch_octant_partition(d_rays, R, order_region, reinterpret_cast<int*>(order_region + R), st, ctx->launches);
+            }
             order = RayOrder{order_region, nullptr, 0};
         }
         int variant = ctx->knobs[CNDL_KNOB_VARIANT];
@@ -473,6 +481,31 @@ int cndl_buffer_entities(cndl_ctx* ctx) {
     CK(ctx->ents.ensure_scratch((E ? E : 1) * sizeof(cndl_entity)));
     if (E) CK(cudaMemcpy(ctx->ents.p, ctx->staged.data(), E * sizeof(cndl_entity), cudaMemcpyHostToDevice));
     ctx->n_ents = E;  // m_EntityPushed
+    {   // world bounds of the scene: the eight corners of every entity's root box through its model matrix
+        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        std::unordered_map<int, std::array<float, 6>> root_box;
+        for (const auto& e : ctx->staged) {
+            if (e.node_offset < 0 || (size_t)e.node_offset >= ctx->n_nodes) continue;
+            auto it = root_box.find(e.node_offset);
+            if (it == root_box.end()) {
+                float b[16];
+                CK(cudaMemcpy(b, static_cast<const char*>(ctx->nodes.p) + (size_t)e.node_offset * ctx->node_size, ctx->node_size, cudaMemcpyDeviceToHost));
+                std::array<float, 6> r;
+                if (ctx->format == CNDL_STACKLESS) r = {b[0], b[1], b[2], b[4], b[5], b[6]};
+                else r = {std::min(b[0], b[8]), std::min(b[1], b[9]), std::min(b[2], b[10]), std::max(b[4], b[12]), std::max(b[5], b[13]), std::max(b[6], b[14])};
+                it = root_box.emplace(e.node_offset, r).first;
+            }
+            const auto& r = it->second;
+            for (int c = 0; c < 8; ++c) {
+                const float x = (c & 1) ? r[3] : r[0], y = (c & 2) ? r[4] : r[1], z = (c & 4) ? r[5] : r[2];
+                for (int k = 0; k < 3; ++k) {
+                    const float w = e.model[k] * x + e.model[4 + k] * y + e.model[8 + k] * z + e.model[12 + k];
+                    if (w == w) { lo[k] = std::min(lo[k], w); hi[k] = std::max(hi[k], w); }
+                }
+            }
+        }
+        for (int k = 0; k < 3; ++k) { ctx->world_lo[k] = lo[k] <= hi[k] ? lo[k] : 0.0f; ctx->world_hi[k] = lo[k] <= hi[k] ? hi[k] : 0.0f; }
+    }
     ctx->buffered.swap(ctx->staged);
     ctx->staged.clear();
     ctx->ents_buffered = true;
@@ -480,9 +513,9 @@ int cndl_buffer_entities(cndl_ctx* ctx) {
 }
 
 int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays) {
-    if (!ctx || mode < 0 || mode > 2) return CNDL_ERR_INVALID;
+    if (!ctx || mode < 0 || mode > 2 || sort_rays < 0 || sort_rays > 2) return CNDL_ERR_INVALID;
     ctx->mode = mode;
-    ctx->sort_rays = sort_rays ? 1 : 0;
+    ctx->sort_rays = sort_rays;
     return CNDL_OK;
 }
 

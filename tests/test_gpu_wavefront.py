@@ -186,15 +186,16 @@ def test_knobs_and_modes_never_change_results(cb, ob, s260k):
     for k, val in enumerate((8, 12, 8, 18)):
         ri.set_tuning(k, val)
     # ray bucketing by direction octant inside the call (every kernel family reads its rays through the bucket lists)
-    for variant in (18, 34, 42):
+    # (sort_rays 1) or sorted by octant + origin Morton code (sort_rays 2)
+    for variant, sort in ((18, 1), (34, 1), (42, 1), (18, 2), (34, 2)):
         ri.set_tuning(3, variant)
-        ri.set_traversal_mode(2, True)
-        assert ri.IntersectRays(rays).tobytes() == want.tobytes(), ("bucketed", variant)
+        ri.set_traversal_mode(2, sort)
+        assert ri.IntersectRays(rays).tobytes() == want.tobytes(), ("reordered", variant, sort)
         short = rays.copy()
         short["tmax"] = 3.0
         t_b = ri.IntersectRaysAny(short)
-        ri.set_traversal_mode(2, False)
-        assert t_b.tobytes() == ri.IntersectRaysAny(short).tobytes(), ("bucketed any-hit", variant)
+        ri.set_traversal_mode(2, 0)
+        assert t_b.tobytes() == ri.IntersectRaysAny(short).tobytes(), ("reordered any-hit", variant, sort)
     ri.set_tuning(3, 18)
     for chunks in (1, 3, 16):
         ri.set_tuning(4, chunks)
@@ -217,7 +218,7 @@ def test_stack_kernel_knobs_and_bucketing(cb, ob):
     ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(nodes))
     rays = rays_in_box(P.min(0), P.max(0), 200000, 33)
     want, _ = ob.trace(ob.STACK, ob.CLOSEST, nodes, tris, V, ents, rays, nthreads=ob.hardware_threads())
-    for park, idle, steps, sort in ((12, 8, 1, False), (1, 1, 2, False), (32, 32, 2, True), (5, 20, 1, True)):
+    for park, idle, steps, sort in ((12, 8, 1, 0), (1, 1, 2, 0), (32, 32, 2, 1), (5, 20, 1, 2)):
         ri.set_tuning(5, park)
         ri.set_tuning(2, idle)
         ri.set_tuning(3, steps)

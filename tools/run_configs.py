@@ -184,6 +184,7 @@ def cfg_soup10m(args, rank, world, local_rank):
     if args.knobs:
         for kid, val in enumerate(int(x) for x in args.knobs.split(",")):
             ri.set_tuning(kid, val)
+    ri.set_traversal_mode(2, args.sort)
     ri.BufferData(True)
     ri.PushEntity(2)
     ri.BufferEntities()
@@ -198,6 +199,18 @@ def cfg_soup10m(args, rank, world, local_rank):
     while done < n:
         c = min(chunk, n - done)
         rays = scenes.random_rays(box_lo, box_hi, c, seed=1 + rank * 1000 + done // chunk)
+        if args.presort:      # experiment: rays in Morton order of their origin cell (bits per axis), direction octant minor / major
+            o, d = rays["o"], rays["d"]
+            q = np.clip(((o - box_lo) / (box_hi - box_lo) * (2 ** args.presort - 1)).astype(np.uint64), 0, 2 ** args.presort - 1)
+            def spread(x):
+                r = np.zeros_like(x)
+                for b in range(args.presort):
+                    r |= ((x >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b)
+                return r
+            key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
+            octant = (d[:, 0] > 0).astype(np.uint64) | ((d[:, 1] > 0).astype(np.uint64) << np.uint64(1)) | ((d[:, 2] > 0).astype(np.uint64) << np.uint64(2))
+            key = (key << np.uint64(3)) | octant if args.presort_mode == 0 else key | (octant << np.uint64(3 * args.presort))
+            rays = rays[np.argsort(key, kind="stable")]
         d_r = dev_rays(rays)
         ri.intersect_closest_device(d_r.data_ptr(), c, d_hits.data_ptr(), 0, stream)  # warm-up / page-in
         torch.cuda.synchronize()
@@ -211,7 +224,7 @@ def cfg_soup10m(args, rank, world, local_rank):
         return None
     out = dict(config=f"heightfield_{T}_tris_random_rays", n_gpus=world, triangles=T, nodes=ri.node_count, gpu_build_ms=round(build_ms, 2),
                build_wall_ms=round(1e3 * wall_build, 1), builder="sah_exact" if args.builder == 0 else "lbvh", rays_all_ranks=int(rays_all),
-               trace_ms_max_over_ranks=round(t_max, 2), mrays_s=round(rays_all / t_max / 1e3, 1), bvh=args.bvh,
+               trace_ms_max_over_ranks=round(t_max, 2), mrays_s=round(rays_all / t_max / 1e3, 1), sort_rays=args.sort, bvh=args.bvh,
                bvh_broadcast_wall_ms=None if bcast_ms is None else round(bcast_ms, 1))
     if args.check_rays:
         from oracle import binding as ob
@@ -241,6 +254,9 @@ def main():
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--rays", type=int, default=0)
     ap.add_argument("--builder", type=int, default=0)
+    ap.add_argument("--presort", type=int, default=0, help="soup10m experiment: host-side Morton sort of each ray chunk, bits per axis")
+    ap.add_argument("--presort-mode", type=int, default=0, help="0: origin cell major; 1: direction octant major")
+    ap.add_argument("--sort", type=int, default=0, help="soup10m: cndl_set_traversal_mode sort_rays (0 off, 1 octant buckets, 2 octant + origin Morton order)")
     ap.add_argument("--knobs", default="", help="comma-separated tuning knobs in knob-id order (see dev_bench.py)")
     ap.add_argument("--bvh", default="build", choices=["build", "broadcast"], help="soup10m at N > 1: every rank builds, or rank 0 builds and broadcasts")
     ap.add_argument("--bucket", type=int, default=0, help="1: the generator emits each batch octant-major (CNDL_GEN_BUCKET_OCTANTS)")
