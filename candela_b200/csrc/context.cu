@@ -76,7 +76,7 @@ struct cndl_ctx {
     cudaStream_t main_stream = nullptr;
     int mode = 2, sort_rays = 0;   // sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};  // bounds of all entities (for sort_rays = 2)
-    int knobs[8] = {8, 12, 8, 0, 0, 12, 4096, 1024};  // CNDL_KNOB_*
+    int knobs[8] = {8, 14, 10, 0, 0, 12, 4096, 1024};  // CNDL_KNOB_*
     // hot-first derived layout of the stackless nodes (kernels_hot.cu), rebuilt by cndl_commit
     DeviceBuffer nodes2, perm, ents2, hot_scratch, d_objects;
     std::vector<int2> h_objects;                 // (node_offset, node_count) in insertion order
@@ -185,8 +185,8 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
                 launch_trace_hot(s, hv, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCK_THREADS], park, idle, steps,
                                  st, ctx->launches);
         } else {
-            launch_trace_ww(s, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM], park, idle, steps, st,
-                            ctx->launches);
+            launch_trace_ww(s, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM], park, idle, steps,
+                            ctx->hot_ready && ctx->hot_entities_ok && !(variant & 8), st, ctx->launches);  // variant bit 3: keep the range checks
         }
     }
     cudaError_t e = cudaGetLastError();

@@ -102,26 +102,34 @@ __device__ __forceinline__ void next_entity(const SceneView& s, const cndl_ray* 
 }
 
 // One node visit of a walking lane (SL:192-246).  DONE = this entity is finished (miss link -1, or the
-// loop header's cap / range checks fail).
-__device__ __forceinline__ void node_step(const SceneView& s, WLane& L, bool warp_exact) {
+// loop header's cap / range checks fail).  CHECKED = false: the node buffer and the entity ranges were validated at
+// commit (every link and first child inside its object), so the pointer range checks of SL:196 cannot fire.
+template <bool CHECKED, bool EXACT>
+__device__ __forceinline__ void node_step(const SceneView& s, WLane& L) {
     if (L.state == WALK) {
-        if (L.iters >= 1024 || L.ptr < L.lo || L.ptr > L.hi) {  // loop header of SL:192-199
-            L.state = DONE;
-        } else {
-            ++L.iters;
-            float4 mn, mx;
-            ldg256(s.nodes + 2 * (size_t)L.ptr, mn, mx);
-            const int link = __float_as_int(mx.w), pack = __float_as_int(mn.w);
-            const bool enter = enter_stackless(mn, mx, L.r, L.tmax, warp_exact);
-            L.pend_pack = pack;
-            L.pend_link = link;
-            L.ptr = enter ? L.ptr + 1 : link + L.start;  // a leaf's pointer is set again after its triangles
-            L.state = enter ? (pack != -1 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
+        if (CHECKED) {
+            if (L.iters >= 1024 || L.ptr < L.lo || L.ptr > L.hi) {  // loop header of SL:192-199
+                L.state = DONE;
+                return;
+            }
         }
+        // !CHECKED: the pointer is valid, so a lane that has reached the iteration cap may load its node anyway; the
+        // visit is then discarded by the selects below instead of being branched around
+        const bool capped = !CHECKED && L.iters >= 1024;
+        float4 mn, mx;
+        ldg256(s.nodes + 2 * (size_t)L.ptr, mn, mx);
+        const int link = __float_as_int(mx.w), pack = __float_as_int(mn.w);
+        const bool enter = enter_stackless(mn, mx, L.r, L.tmax, EXACT);
+        L.pend_pack = pack;
+        L.pend_link = link;
+        L.ptr = enter ? L.ptr + 1 : link + L.start;  // a leaf's pointer is set again after its triangles
+        const int next = enter ? (pack != -1 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
+        L.state = capped ? DONE : next;
+        L.iters += capped ? 0 : 1;
     }
 }
 
-template <int KIND, int MINB, int STEPS>
+template <int KIND, int MINB, int STEPS, bool CHECKED>
 __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R, RayOrder order,
                                                                     cndl_hit* __restrict__ hits, float* __restrict__ any_t,
                                                                     unsigned* __restrict__ work_counter, int park_threshold, int idle_threshold) {
@@ -191,10 +199,16 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
                 int park = walk0 >> 2;
                 park = park < 1 ? 1 : (park > park_threshold ? park_threshold : park);
                 const int min_walk = walk0 - park + 1;  // >= 1
-                do {
+                if (!warp_exact) {  // the common case: no lane needs the literal GLSL min/max, and the loop does not test for it
+                    do {
 #pragma unroll
-                    for (int step = 0; step < STEPS; ++step) node_step(s, L, warp_exact);
-                } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+                        for (int step = 0; step < STEPS; ++step) node_step<CHECKED, false>(s, L);
+                    } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+                } else {
+                    do {
+                        node_step<CHECKED, true>(s, L);
+                    } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+                }
             }
         }
 
@@ -251,7 +265,8 @@ __device__ __forceinline__ void next_entity_stack(const SceneView& s, const cndl
     L.state = DONE;
 }
 
-__device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, int* stack, bool warp_exact) {
+template <bool EXACT>
+__device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, int* stack) {
     if (L.state == WALK) {
         if (L.iters >= 1024 || L.sp >= 64 || L.sp < 0 || L.cur < L.lo || L.cur > L.hi) {  // ST:198-205
             L.state = DONE;
@@ -262,8 +277,8 @@ __device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, in
             ldg256(s.nodes + 4 * (size_t)L.cur + 2, rmn, rmx);
             const int lpack = __float_as_int(lmn.w), rpack = __float_as_int(rmn.w);
             const bool lleaf = lpack != -1, rleaf = rpack != -1;
-            const float lt = lleaf ? -1.0f : slab_stack(lmn, lmx, L.r, L.tmax, warp_exact);
-            const float rt = rleaf ? -1.0f : slab_stack(rmn, rmx, L.r, L.tmax, warp_exact);
+            const float lt = lleaf ? -1.0f : slab_stack(lmn, lmx, L.r, L.tmax, EXACT);
+            const float rt = rleaf ? -1.0f : slab_stack(rmn, rmx, L.r, L.tmax, EXACT);
             const int lslot = __float_as_int(lmx.w) + L.start, rslot = __float_as_int(rmx.w) + L.start;
             const bool hl = lt > 0.0f, hr = rt > 0.0f, both = hl && hr, right_first = rt < lt;
             int after = WALK;
@@ -355,10 +370,16 @@ __global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, con
                 int park = walk0 >> 2;
                 park = park < 1 ? 1 : (park > park_threshold ? park_threshold : park);
                 const int min_walk = walk0 - park + 1;
-                do {
+                if (!warp_exact) {
+                    do {
 #pragma unroll
-                    for (int step = 0; step < STEPS; ++step) node_step_stack(s, L, stack, warp_exact);
-                } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+                        for (int step = 0; step < STEPS; ++step) node_step_stack<false>(s, L, stack);
+                    } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+                } else {
+                    do {
+                        node_step_stack<true>(s, L, stack);
+                    } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+                }
             }
         }
         if (L.state == LEAF) {  // leaf phase: left leaf, then right leaf (ST:221-277)
@@ -376,12 +397,12 @@ __global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, con
     }
 }
 
-template <int KIND, int MINB>
+template <int KIND, int MINB, bool CHECKED>
 void launch_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const RayOrder& order,
                   cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
 #define CNDL_WW_LAUNCH(STEPS)                                                                                     \
     {                                                                                                             \
-        auto k = trace_ww_stackless_kernel<KIND, MINB, STEPS>;                                                    \
+        auto k = trace_ww_stackless_kernel<KIND, MINB, STEPS, CHECKED>;                                           \
         static bool configured = false;                                                                           \
         if (!configured) { /* no shared memory is used: give the whole 256 KB array to L1 */                      \
             cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0);                           \
@@ -398,13 +419,13 @@ void launch_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView
 #undef CNDL_WW_LAUNCH
 }
 
-template <int MINB>
+template <int MINB, bool CHECKED>
 void launch_kind(int kind, int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const RayOrder& order,
                  cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
     switch (kind) {
-        case Q_CLOSEST: launch_steps<Q_CLOSEST, MINB>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
-        case Q_CLOSEST_IGNORE_TRANSPARENT: launch_steps<Q_CLOSEST_IGNORE_TRANSPARENT, MINB>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
-        default: launch_steps<Q_ANY, MINB>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        case Q_CLOSEST: launch_steps<Q_CLOSEST, MINB, CHECKED>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        case Q_CLOSEST_IGNORE_TRANSPARENT: launch_steps<Q_CLOSEST_IGNORE_TRANSPARENT, MINB, CHECKED>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        default: launch_steps<Q_ANY, MINB, CHECKED>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
     }
 }
 
@@ -434,17 +455,20 @@ void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, s
 }
 
 void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
-                     unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, cudaStream_t stream,
-                     LaunchCounter& lc) {
+                     unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, bool validated,
+                     cudaStream_t stream, LaunchCounter& lc) {
     if (R == 0) return;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned), stream);
     unsigned grid = (unsigned)(sm_count * blocks_per_sm);
     const unsigned need = (unsigned)((R + 127) / 128);
     if (grid > need) grid = need;
     // register budget follows the requested residency: <= 8 CTAs/SM -> 64 registers, 10 -> 48, 12 -> 40
-    if (blocks_per_sm <= 8) launch_kind<8>(kind, steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
-    else if (blocks_per_sm <= 10) launch_kind<10>(kind, steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
-    else launch_kind<12>(kind, steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
+#define CNDL_WW_ARGS kind, steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold
+    if (blocks_per_sm <= 8) { if (validated) launch_kind<8, false>(CNDL_WW_ARGS); else launch_kind<8, true>(CNDL_WW_ARGS); }
+    else if (blocks_per_sm == 9 && validated) launch_kind<9, false>(CNDL_WW_ARGS);  // 56 registers
+    else if (blocks_per_sm <= 10) launch_kind<10, true>(CNDL_WW_ARGS);
+    else launch_kind<12, true>(CNDL_WW_ARGS);
+#undef CNDL_WW_ARGS
     lc.n++;
 }
 
