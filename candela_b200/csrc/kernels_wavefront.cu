@@ -125,7 +125,7 @@ __device__ __forceinline__ void node_step(const SceneView& s, WLane& L) {
         L.ptr = enter ? L.ptr + 1 : link + L.start;  // a leaf's pointer is set again after its triangles
         const int next = enter ? (pack != -1 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
         L.state = capped ? DONE : next;
-        L.iters += capped ? 0 : 1;
+        ++L.iters;  // a discarded visit counts too: the ray retires with min(iters, 1024)
     }
 }
 
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
                     next_entity<KIND>(s, rays, L, L.ent + 1);  // WALK again, or still DONE: the scene loop is over
                     if (L.state == DONE) {
                         if (ANY) any_t[L.rid] = L.best_tri >= 0 ? L.tmax : -1.0f;
-                        else retire_closest(s, rays, hits, L.rid, L.r, L.ent, L.tmax, L.best_tri, L.best_ent, L.iters);
+                        else retire_closest(s, rays, hits, L.rid, L.r, L.ent, L.tmax, L.best_tri, L.best_ent, min(L.iters, 1024));
                         L.state = EMPTY;
                     }
                 }
