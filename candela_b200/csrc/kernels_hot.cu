@@ -189,27 +189,28 @@ __device__ __forceinline__ void next_entity_hot(const SceneView& s, const cndl_e
     L.ent = 0x3FFFFFFF;
 }
 
-// One node visit of a walking lane (SL:192-246), branch-free apart from where the node lives.
-__device__ __forceinline__ void node_step_hot(const float4* __restrict__ nodes2, const float4* s_lo, const float4* s_hi, int n_hot, HLane& L, bool warp_exact) {
+// One node visit of a walking lane (SL:192-246), branch-free apart from where the node lives.  The pointer is
+// always valid on a validated buffer, so a lane at the iteration cap (SL:192) loads its node anyway and the visit is
+// discarded by a select; the iteration counter runs on and is clamped to 1024 when the ray retires.
+template <bool EXACT>
+__device__ __forceinline__ void node_step_hot(const float4* __restrict__ nodes2, const float4* s_lo, const float4* s_hi, int n_hot, HLane& L) {
     if (L.state == WALK) {
-        if (L.iters >= 1024) {  // SL:192; the pointer range checks of SL:196 cannot fire on a validated buffer
-            L.state = DONE;
+        const bool capped = L.iters >= 1024;
+        float4 mn, mx;
+        if (L.ptr < n_hot) {
+            mn = s_lo[L.ptr];
+            mx = s_hi[L.ptr];
         } else {
-            ++L.iters;
-            float4 mn, mx;
-            if (L.ptr < n_hot) {
-                mn = s_lo[L.ptr];
-                mx = s_hi[L.ptr];
-            } else {
-                ldg256(nodes2 + 2 * (size_t)L.ptr, mn, mx);
-            }
-            const int word = __float_as_int(mn.w), link = __float_as_int(mx.w);
-            const bool enter = enter_stackless(mn, mx, L.r, L.tmax, warp_exact);
-            L.pend_pack = word;
-            L.pend_link = link;
-            L.ptr = enter ? ~word : link;  // a leaf's pointer is set again after its triangles
-            L.state = enter ? (word >= 0 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
+            ldg256(nodes2 + 2 * (size_t)L.ptr, mn, mx);
         }
+        const int word = __float_as_int(mn.w), link = __float_as_int(mx.w);
+        const bool enter = enter_stackless(mn, mx, L.r, L.tmax, EXACT);
+        L.pend_pack = word;
+        L.pend_link = link;
+        L.ptr = enter ? ~word : link;  // a leaf's pointer is set again after its triangles
+        const int next = enter ? (word >= 0 ? LEAF : WALK) : (link < 0 ? DONE : WALK);
+        L.state = capped ? DONE : next;
+        ++L.iters;
     }
 }
 
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
                                 t = L.closest;
                                 barycentrics(s.tri48, L.best_tri, p, u, v, w);
                             }
-                            store_hit(hits, L.rid, t, u, v, w, mesh, L.best_tri, L.best_ent, L.iters);
+                            store_hit(hits, L.rid, t, u, v, w, mesh, L.best_tri, L.best_ent, min(L.iters, 1024));
                         }
                         L.state = EMPTY;
                     }
@@ -320,10 +321,16 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
                 int park = walk0 >> 2;
                 park = park < 1 ? 1 : (park > park_threshold ? park_threshold : park);
                 const int min_walk = walk0 - park + 1;  // >= 1
-                do {
+                if (!warp_exact) {
+                    do {
 #pragma unroll
-                    for (int step = 0; step < STEPS; ++step) node_step_hot(nodes2, s_lo, s_hi, n_hot, L, warp_exact);
-                } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+                        for (int step = 0; step < STEPS; ++step) node_step_hot<false>(nodes2, s_lo, s_hi, n_hot, L);
+                    } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+                } else {
+                    do {
+                        node_step_hot<true>(nodes2, s_lo, s_hi, n_hot, L);
+                    } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
+                }
             }
         }
 
