@@ -175,7 +175,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import candela_b200 as cb
-    from candela_b200 import api
+    from candela_b200 import api, sharding
+    numa_bound = sharding.bind_to_gpu_numa_node(local_rank)   # before any pinned allocation: e2e stages rays through host memory
     scenes, verts, indices, mesh_ids, iv, ip = build_workload(rank)
 
     # ---- scene: GPU build behind RayIntersector::AddObject, BVH replicated per rank ----
@@ -292,8 +293,9 @@ def run_ours(args):
             "config": {"workload": "diffuse_gi_1080p_1spp_closest_hit", "scene": "S260k stand-in (262,624 triangles, GPU-built binned SAH)",
                        "node_format": "stackless", "rays_per_gpu_per_step": R, "resolution": [WIDTH, HEIGHT], "bvh": "replicated per GPU",
                        "l2": "flushed between steps (192 MiB memset, untimed)", "traversal_mode": args.mode, "sort_rays": bool(args.sort)},
-            "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": R * 32, "d2h_bytes_per_step": R * 32,
-                    "timing": "host wall clock around the synchronous C-ABI call, max over ranks"},
+            "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": int(rays_all) * 32, "d2h_bytes_per_step": int(rays_all) * 32,
+                    "timing": "host wall clock around the synchronous C-ABI call, max over ranks",
+                    "host_buffers": "pinned; each rank bound to its GPU's NUMA node" if numa_bound else "pinned"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "build": {"gpu_ms": round(min(build_ms), 3), "triangles": int(len(indices) // 3), "nodes": int(len(nodes)),

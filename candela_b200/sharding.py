@@ -126,3 +126,25 @@ def broadcast_scene(ri, object_ids, src: int = 0, device="cuda", group=None):
             n, t, v = arrays[3 * k:3 * k + 3]
             ri.AddPrebuiltObject(oid, n.view(ri.node_dtype), t.view(api.TRIANGLE_DT), v.view(api.VERTEX_DT))
 
+
+def bind_to_gpu_numa_node(gpu_index: int) -> bool:
+    """Restricts this process to the CPU cores NVML reports as local to GPU `gpu_index`, so that pinned host buffers
+    allocated afterwards (first touch) and the copy-issuing thread sit on the GPU's own NUMA node.  With one process per
+    GPU on a two-socket box, half of the ranks otherwise stage their rays through the remote socket.  Returns False
+    (and changes nothing) when NVML or the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
