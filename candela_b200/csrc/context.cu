@@ -96,6 +96,12 @@ struct cndl_ctx {
     }
 };
 
+// Nothing may throw across the C boundary (std::vector / std::string / unordered_map allocate): every entry point that
+// allocates is a function-try-block ending in CNDL_CATCH.
+#define CNDL_CATCH                                        \
+    catch (const std::bad_alloc&) { return CNDL_ERR_OOM; } \
+    catch (...) { return CNDL_ERR_INVALID; }
+
 #define CK(call)                                                   \
     do {                                                           \
         cudaError_t e__ = (call);                                  \
@@ -287,7 +293,7 @@ int cndl_get_object(const cndl_ctx* ctx, uint32_t object_id, int32_t* node_offse
 }
 
 int cndl_add_prebuilt_object(cndl_ctx* ctx, uint32_t object_id, const void* nodes, size_t N, const cndl_triangle* tris, size_t T,
-                             const cndl_vertex* verts, size_t V) {
+                             const cndl_vertex* verts, size_t V) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (!nodes || !tris || !verts || N == 0 || T == 0 || V == 0) return ctx->fail(CNDL_ERR_INVALID, "null or empty buffer");
     if (ctx->n_nodes + N > 0x7FFFFFF0ull || ctx->n_tris + T > (1ull << 27) || ctx->n_verts + V > 0x7FFFFFF0ull)
@@ -325,10 +331,10 @@ int cndl_add_prebuilt_object(cndl_ctx* ctx, uint32_t object_id, const void* node
     ctx->verts.bytes = ctx->n_verts * sizeof(cndl_vertex);
     ctx->committed = false;
     return CNDL_OK;
-}
+} CNDL_CATCH
 
 int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts, size_t V, const uint32_t* indices, size_t I,
-                    const int32_t* mesh_id_per_tri, const cndl_build_opts* opts) {
+                    const int32_t* mesh_id_per_tri, const cndl_build_opts* opts) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (!verts || !indices || V == 0 || I == 0 || I % 3 != 0) return ctx->fail(CNDL_ERR_INVALID, "null or empty geometry, or index count not a multiple of 3");
     const size_t T = I / 3;
@@ -388,9 +394,9 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     ctx->verts.bytes = ctx->n_verts * sizeof(cndl_vertex);
     ctx->committed = false;
     return CNDL_OK;
-}
+} CNDL_CATCH
 
-int cndl_commit(cndl_ctx* ctx, int clear_host) {
+int cndl_commit(cndl_ctx* ctx, int clear_host) try {
     (void)clear_host;  // the host never keeps a copy: the device buffers are the only ones
     if (!ctx) return CNDL_ERR_INVALID;
     if (ctx->n_tris == 0) return ctx->fail(CNDL_ERR_INVALID, "nothing to commit");
@@ -429,16 +435,16 @@ int cndl_commit(cndl_ctx* ctx, int clear_host) {
         }
     }
     return CNDL_OK;
-}
+} CNDL_CATCH
 
-int cndl_read_buffers(cndl_ctx* ctx, void* nodes, cndl_triangle* tris, cndl_vertex* verts) {
+int cndl_read_buffers(cndl_ctx* ctx, void* nodes, cndl_triangle* tris, cndl_vertex* verts) try {
     if (!ctx) return CNDL_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (nodes && ctx->n_nodes) CK(cudaMemcpy(nodes, ctx->nodes.p, ctx->n_nodes * ctx->node_size, cudaMemcpyDeviceToHost));
     if (tris && ctx->n_tris) CK(cudaMemcpy(tris, ctx->tris.p, ctx->n_tris * sizeof(cndl_triangle), cudaMemcpyDeviceToHost));
     if (verts && ctx->n_verts) CK(cudaMemcpy(verts, ctx->verts.p, ctx->n_verts * sizeof(cndl_vertex), cudaMemcpyDeviceToHost));
     return CNDL_OK;
-}
+} CNDL_CATCH
 
 int cndl_device_buffers(cndl_ctx* ctx, const void** nodes, const cndl_triangle** tris, const cndl_vertex** verts,
                         const cndl_entity** entities) {
@@ -450,7 +456,7 @@ int cndl_device_buffers(cndl_ctx* ctx, const void** nodes, const cndl_triangle**
     return CNDL_OK;
 }
 
-int cndl_push_entity(cndl_ctx* ctx, uint32_t object_id, const float model[16], float emissive, float translucency) {
+int cndl_push_entity(cndl_ctx* ctx, uint32_t object_id, const float model[16], float emissive, float translucency) try {
     if (!ctx || !model) return CNDL_ERR_INVALID;
     auto it = ctx->objects.find(object_id);
     if (it == ctx->objects.end())
@@ -466,15 +472,15 @@ int cndl_push_entity(cndl_ctx* ctx, uint32_t object_id, const float model[16], f
     std::memcpy(&e.data[1], &alpha, 4);     // Intersector.h:213
     ctx->staged.push_back(e);
     return CNDL_OK;
-}
+} CNDL_CATCH
 
-int cndl_push_entity_records(cndl_ctx* ctx, const cndl_entity* records, size_t E) {
+int cndl_push_entity_records(cndl_ctx* ctx, const cndl_entity* records, size_t E) try {
     if (!ctx || (!records && E)) return CNDL_ERR_INVALID;
     ctx->staged.insert(ctx->staged.end(), records, records + E);
     return CNDL_OK;
-}
+} CNDL_CATCH
 
-int cndl_buffer_entities(cndl_ctx* ctx) {
+int cndl_buffer_entities(cndl_ctx* ctx) try {
     if (!ctx) return CNDL_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     const size_t E = ctx->staged.size();
@@ -510,7 +516,7 @@ int cndl_buffer_entities(cndl_ctx* ctx) {
     ctx->staged.clear();
     ctx->ents_buffered = true;
     return upload_hot_entities(ctx);
-}
+} CNDL_CATCH
 
 int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays) {
     if (!ctx || mode < 0 || mode > 2 || sort_rays < 0 || sort_rays > 2) return CNDL_ERR_INVALID;
@@ -526,7 +532,7 @@ int cndl_set_tuning(cndl_ctx* ctx, int knob, int value) {
     return CNDL_OK;
 }
 
-int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, int flags, cndl_hit* d_hits, void* stream) {
+int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, int flags, cndl_hit* d_hits, void* stream) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (R && (!d_rays || !d_hits)) return ctx->fail(CNDL_ERR_INVALID, "null ray or hit buffer");
     int rc = check_ready(ctx);
@@ -536,9 +542,9 @@ int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t 
     if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
     return enqueue_trace(ctx, kind, d_rays, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), static_cast<unsigned*>(ctx->d_order.p),
                          static_cast<cudaStream_t>(stream));
-}
+} CNDL_CATCH
 
-int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, float* d_t_out, void* stream) {
+int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, float* d_t_out, void* stream) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (R && (!d_rays || !d_t_out)) return ctx->fail(CNDL_ERR_INVALID, "null ray or output buffer");
     int rc = check_ready(ctx);
@@ -547,7 +553,7 @@ int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, f
     if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
     return enqueue_trace(ctx, Q_ANY, d_rays, R, nullptr, d_t_out, static_cast<unsigned*>(ctx->d_counter.p), static_cast<unsigned*>(ctx->d_order.p),
                          static_cast<cudaStream_t>(stream));
-}
+} CNDL_CATCH
 
 // Host-buffer queries: the batch is cut into chunks that rotate over three streams, so the
 // host->device copy of chunk k+1, the traversal of chunk k and the device->host copy of chunk
@@ -598,20 +604,20 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
     return CNDL_OK;
 }
 
-int cndl_intersect_closest(cndl_ctx* ctx, const cndl_ray* rays, size_t R, int flags, cndl_hit* hits) {
+int cndl_intersect_closest(cndl_ctx* ctx, const cndl_ray* rays, size_t R, int flags, cndl_hit* hits) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (R && (!rays || !hits)) return ctx->fail(CNDL_ERR_INVALID, "null ray or hit buffer");
     return host_query(ctx, (flags & CNDL_IGNORE_TRANSPARENT) ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST, rays, R, hits, nullptr);
-}
+} CNDL_CATCH
 
-int cndl_intersect_any(cndl_ctx* ctx, const cndl_ray* rays, size_t R, float* t_out) {
+int cndl_intersect_any(cndl_ctx* ctx, const cndl_ray* rays, size_t R, float* t_out) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (R && (!rays || !t_out)) return ctx->fail(CNDL_ERR_INVALID, "null ray or output buffer");
     return host_query(ctx, Q_ANY, rays, R, nullptr, t_out);
-}
+} CNDL_CATCH
 
 int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H, cndl_hit* d_hits,
-                                  cndl_ray* d_rays_out, void* stream) {
+                                  cndl_ray* d_rays_out, void* stream) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (!inv_view || !inv_proj || W <= 0 || H <= 0 || !d_hits) return ctx->fail(CNDL_ERR_INVALID, "bad primary-ray arguments");
     int rc = check_ready(ctx);
@@ -627,10 +633,10 @@ int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const
     launch_primary_rays(inv_view, inv_proj, W, H, dr, st, ctx->launches);
     CK(cudaGetLastError());
     return enqueue_trace(ctx, Q_CLOSEST, dr, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), nullptr, st);  // camera rays are coherent already
-}
+} CNDL_CATCH
 
 int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H, cndl_hit* hits,
-                           cndl_ray* rays_out) {
+                           cndl_ray* rays_out) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (!hits || W <= 0 || H <= 0) return ctx->fail(CNDL_ERR_INVALID, "bad primary-ray arguments");
     const size_t R = (size_t)W * (size_t)H;
@@ -645,10 +651,10 @@ int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float 
     if (rays_out) CK(cudaMemcpyAsync(rays_out, ctx->d_rays.p, R * sizeof(cndl_ray), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return CNDL_OK;
-}
+} CNDL_CATCH
 
 int cndl_generate_rays_device(cndl_ctx* ctx, const cndl_raygen_params* params, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R,
-                              cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream) {
+                              cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (!params || !count_out || params->spp < 1 || params->kind < CNDL_GEN_DIFFUSE || params->kind > CNDL_GEN_SHADOW ||
         (R && (!d_rays || !d_hits || !d_rays_out)))
@@ -661,10 +667,10 @@ int cndl_generate_rays_device(cndl_ctx* ctx, const cndl_raygen_params* params, c
     CK(generate_rays(scene_view(ctx), *params, d_rays, d_hits, R, d_rays_out, d_parent_out, static_cast<int*>(ctx->d_sort_tmp.p), count_out,
                      static_cast<cudaStream_t>(stream), ctx->launches));
     return CNDL_OK;
-}
+} CNDL_CATCH
 
 int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R, int spp, float offset,
-                                     float tmax, uint32_t seed, cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream) {
+                                     float tmax, uint32_t seed, cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream) try {
     cndl_raygen_params p;
     std::memset(&p, 0, sizeof(p));
     p.kind = CNDL_GEN_DIFFUSE;
@@ -673,9 +679,9 @@ int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, cons
     p.offset = offset;
     p.tmax = tmax;
     return cndl_generate_rays_device(ctx, &p, d_rays, d_hits, R, d_rays_out, d_parent_out, count_out, stream);
-}
+} CNDL_CATCH
 
-int cndl_get_data_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_attr* d_out, void* stream) {
+int cndl_get_data_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_attr* d_out, void* stream) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (R && (!d_hits || !d_out)) return ctx->fail(CNDL_ERR_INVALID, "null hit or attribute buffer");
     if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 records in one call");
@@ -685,9 +691,9 @@ int cndl_get_data_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_h
     launch_get_data(scene_view(ctx), static_cast<const float4*>(ctx->verts.p), d_hits, R, d_out, static_cast<cudaStream_t>(stream), ctx->launches);
     CK(cudaGetLastError());
     return CNDL_OK;
-}
+} CNDL_CATCH
 
-int cndl_get_data(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_attr* out) {
+int cndl_get_data(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_attr* out) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (R && (!hits || !out)) return ctx->fail(CNDL_ERR_INVALID, "null hit or attribute buffer");
     if (R == 0) return check_ready(ctx);
@@ -701,9 +707,9 @@ int cndl_get_data(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_attr* 
     CK(cudaMemcpyAsync(out, ctx->d_rays.p, R * sizeof(cndl_hit_attr), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return CNDL_OK;
-}
+} CNDL_CATCH
 
-int cndl_collide_boxes_device(cndl_ctx* ctx, const cndl_box* d_boxes, size_t n, cndl_collision* d_out, void* stream) {
+int cndl_collide_boxes_device(cndl_ctx* ctx, const cndl_box* d_boxes, size_t n, cndl_collision* d_out, void* stream) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (ctx->format != CNDL_STACKLESS) return ctx->fail(CNDL_ERR_INVALID, "the collide query walks FlattenedNode buffers (Physics.h:15): stackless contexts only");
     if (n && (!d_boxes || !d_out)) return ctx->fail(CNDL_ERR_INVALID, "null box or result buffer");
@@ -714,9 +720,9 @@ int cndl_collide_boxes_device(cndl_ctx* ctx, const cndl_box* d_boxes, size_t n, 
     launch_collide_boxes(scene_view(ctx), static_cast<const float4*>(ctx->verts.p), d_boxes, n, d_out, static_cast<cudaStream_t>(stream), ctx->launches);
     CK(cudaGetLastError());
     return CNDL_OK;
-}
+} CNDL_CATCH
 
-int cndl_collide_boxes(cndl_ctx* ctx, const cndl_box* boxes, size_t n, cndl_collision* out) {
+int cndl_collide_boxes(cndl_ctx* ctx, const cndl_box* boxes, size_t n, cndl_collision* out) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (n && (!boxes || !out)) return ctx->fail(CNDL_ERR_INVALID, "null box or result buffer");
     if (n == 0) return check_ready(ctx);
@@ -730,7 +736,7 @@ int cndl_collide_boxes(cndl_ctx* ctx, const cndl_box* boxes, size_t n, cndl_coll
     CK(cudaMemcpyAsync(out, ctx->d_hits.p, n * sizeof(cndl_collision), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return CNDL_OK;
-}
+} CNDL_CATCH
 
 // ---- flat-buffer serialisation of the built scene (the reference rebuilds every BVH at every
 // launch, Pipeline.cpp:1019-1028).  File: header, object table, then the reference-layout node / triangle / vertex
@@ -741,7 +747,7 @@ struct FileObject { uint32_t id; int32_t node_offset, node_count, tri_offset, tr
 const char kMagic[8] = {'C', 'N', 'D', 'L', 'B', 'V', 'H', '1'};
 }  // namespace
 
-int cndl_save(cndl_ctx* ctx, const char* path) {
+int cndl_save(cndl_ctx* ctx, const char* path) try {
     if (!ctx || !path) return CNDL_ERR_INVALID;
     if (ctx->n_tris == 0) return ctx->fail(CNDL_ERR_INVALID, "nothing to save");
     CK(cudaSetDevice(ctx->device));
@@ -768,9 +774,9 @@ int cndl_save(cndl_ctx* ctx, const char* path) {
               std::fwrite(verts.data(), sizeof(cndl_vertex), verts.size(), f) == verts.size();
     ok = (std::fclose(f) == 0) && ok;
     return ok ? CNDL_OK : ctx->fail(CNDL_ERR_INVALID, std::string("short write to ") + path);
-}
+} CNDL_CATCH
 
-int cndl_load(cndl_ctx* ctx, const char* path) {
+int cndl_load(cndl_ctx* ctx, const char* path) try {
     if (!ctx || !path) return CNDL_ERR_INVALID;
     if (ctx->n_tris != 0) return ctx->fail(CNDL_ERR_INVALID, "cndl_load needs an empty context: leaf packs in the file hold global triangle offsets");
     std::FILE* f = std::fopen(path, "rb");
@@ -818,7 +824,7 @@ int cndl_load(cndl_ctx* ctx, const char* path) {
     ctx->verts.bytes = h.n_verts * sizeof(cndl_vertex);
     ctx->committed = false;
     return CNDL_OK;
-}
+} CNDL_CATCH
 
 void* cndl_host_alloc(size_t bytes) {
     void* p = nullptr;

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <unordered_map>
@@ -62,7 +63,7 @@ extern "C" {
 
 uint32_t cndl_pack_half2x16(float x, float y) { return (uint32_t)to_float16(x) | ((uint32_t)to_float16(y) << 16); }
 
-int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model** out, char* err, size_t err_cap) {
+int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model** out, char* err, size_t err_cap) try {
     auto fail = [&](const std::string& msg) {
         if (err && err_cap) std::snprintf(err, err_cap, "%s", msg.c_str());
         return (int)CNDL_ERR_INVALID;
@@ -71,8 +72,9 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
     *out = nullptr;
     std::FILE* f = std::fopen(path, "rb");
     if (!f) return fail(std::string("cannot open ") + path + ": " + std::strerror(errno));
-    cndl_model* M = new (std::nothrow) cndl_model;
-    if (!M) { std::fclose(f); return CNDL_ERR_OOM; }
+    struct FileCloser { std::FILE* f; ~FileCloser() { if (f) std::fclose(f); } } closer{f};
+    std::unique_ptr<cndl_model> owner(new cndl_model);
+    cndl_model* M = owner.get();
 
     std::vector<float> P, N, T;  // v (3), vn (3), vt (2)
     struct Key { long v, t, n; bool operator==(const Key& o) const { return v == o.v && t == o.t && n == o.n; } };
@@ -164,19 +166,19 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
             else if (mesh_open) M->mesh_names.back() = pending_name;
         }
     }
-    std::fclose(f);
-    if (!problem.empty() || M->indices.empty()) {
-        delete M;
-        return fail(problem.empty() ? std::string("no faces in ") + path : problem);
-    }
+    if (!problem.empty() || M->indices.empty()) return fail(problem.empty() ? std::string("no faces in ") + path : problem);
     // one GlobalMeshNumber per mesh, consecutive from first_mesh_number; one entry per triangle
     M->mesh_ids.resize(M->indices.size() / 3);
     for (size_t m = 0; m < M->mesh_first_index.size(); ++m) {
         const size_t lo = M->mesh_first_index[m] / 3, hi = (m + 1 < M->mesh_first_index.size() ? M->mesh_first_index[m + 1] : M->indices.size()) / 3;
         for (size_t t = lo; t < hi; ++t) M->mesh_ids[t] = first_mesh_number + (std::int32_t)m;
     }
-    *out = M;
+    *out = owner.release();
     return CNDL_OK;
+} catch (const std::bad_alloc&) {
+    return CNDL_ERR_OOM;
+} catch (...) {
+    return CNDL_ERR_INVALID;
 }
 
 void cndl_model_free(cndl_model* m) { delete m; }
