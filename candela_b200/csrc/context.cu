@@ -178,7 +178,8 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
         if (steps < 1 || steps > 4) steps = 2;
         const int park = ctx->knobs[stack ? CNDL_KNOB_STACK_LEAF_THRESHOLD : CNDL_KNOB_LEAF_THRESHOLD], idle = ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD];
         if (stack) {
-            launch_trace_ww_stack(s, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, park, idle, steps, st, ctx->launches);
+            launch_trace_ww_stack(s, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM], park, idle, steps, st,
+                                  ctx->launches);
         } else if (variant >= 32 && ctx->hot_ready && ctx->hot_entities_ok) {
             HotView hv;
             hv.nodes2 = static_cast<const float4*>(ctx->nodes2.p);

@@ -29,8 +29,8 @@ void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t 
                      unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, bool validated,
                      cudaStream_t stream, LaunchCounter& lc);
 void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
-                           unsigned* work_counter, int sm_count, int park_threshold, int idle_threshold, int steps, cudaStream_t stream,
-                           LaunchCounter& lc);
+                           unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps,
+                           cudaStream_t stream, LaunchCounter& lc);
 // Stable partition of the ray indices by direction octant (kernels_raygen.cu): order[0..R) lists the rays of octant 0
 // in their original order, then octant 1, ...  scratch: octant_partition_scratch_ints(R) ints.
 size_t octant_partition_scratch_ints(size_t R);

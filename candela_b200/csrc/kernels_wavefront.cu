@@ -302,7 +302,7 @@ __device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, in
 }
 
 template <int KIND, int STEPS>
-__global__ void __launch_bounds__(128, 6) trace_ww_stack_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R, RayOrder order,
+__global__ void __launch_bounds__(128, 8) trace_ww_stack_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R, RayOrder order,
                                                                 cndl_hit* __restrict__ hits, float* __restrict__ any_t,
                                                                 unsigned* __restrict__ work_counter, int park_threshold, int idle_threshold) {
     constexpr bool ANY = KIND == Q_ANY;
@@ -439,11 +439,11 @@ void launch_stack_steps(int steps, unsigned grid, cudaStream_t stream, const Sce
 }  // namespace
 
 void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
-                           unsigned* work_counter, int sm_count, int park_threshold, int idle_threshold, int steps, cudaStream_t stream,
-                           LaunchCounter& lc) {
+                           unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps,
+                           cudaStream_t stream, LaunchCounter& lc) {
     if (R == 0) return;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned), stream);
-    unsigned grid = (unsigned)(sm_count * 6);
+    unsigned grid = (unsigned)(sm_count * (blocks_per_sm < 1 ? 1 : (blocks_per_sm > 8 ? 8 : blocks_per_sm)));  // 64 registers: 8 CTAs per SM
     const unsigned need = (unsigned)((R + 127) / 128);
     if (grid > need) grid = need;
     switch (kind) {
