@@ -193,7 +193,8 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
                                  st, ctx->launches);
         } else {
             launch_trace_ww(s, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM], park, idle, steps,
-                            ctx->hot_ready && ctx->hot_entities_ok && !(variant & 8), st, ctx->launches);  // variant bit 3: keep the range checks
+                            ctx->hot_ready && ctx->hot_entities_ok && !(variant & 8), (variant & 16) != 0, st,
+                            ctx->launches);  // variant bit 3: keep the range checks; bit 4: helper lanes in the leaf phase
         }
     }
     cudaError_t e = cudaGetLastError();

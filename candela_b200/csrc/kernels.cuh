@@ -27,7 +27,7 @@ void launch_trace_persistent(const SceneView& s, bool stack, int kind, const cnd
 // Mode 2: persistent while-while traversal with postponed leaf tests and a batched service phase (kernels_wavefront.cu).
 void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
                      unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, bool validated,
-                     cudaStream_t stream, LaunchCounter& lc);
+                     bool helper_lanes, cudaStream_t stream, LaunchCounter& lc);
 void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
                            unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps,
                            cudaStream_t stream, LaunchCounter& lc);

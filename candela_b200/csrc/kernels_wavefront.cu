@@ -129,11 +129,13 @@ __device__ __forceinline__ void node_step(const SceneView& s, WLane& L) {
     }
 }
 
-template <int KIND, int MINB, int STEPS, bool CHECKED>
+template <int KIND, int MINB, int STEPS, bool CHECKED, bool HELP>
 __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R, RayOrder order,
                                                                     cndl_hit* __restrict__ hits, float* __restrict__ any_t,
                                                                     unsigned* __restrict__ work_counter, int park_threshold, int idle_threshold) {
     constexpr bool ANY = KIND == Q_ANY;
+    __shared__ float4 s_box[HELP ? 4 : 1][HELP ? 64 : 1];  // per warp: up to 32 posted (ray, triangle) pairs
+    __shared__ float s_res[HELP ? 4 : 1][HELP ? 32 : 1];
     const unsigned lane = threadIdx.x & 31u;
     WLane L;
     L.state = EMPTY;
@@ -213,15 +215,71 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
         }
 
         // ---------------- leaf phase ----------------
-        if (L.state == LEAF) {
-            EntityResult er{-1.0f, -1, 0};
-            const bool found = leaf_triangles<ANY>(s, L.pend_pack, L.r, L.tmax, er);
-            if (er.tri >= 0) { L.best_tri = er.tri; L.best_ent = L.ent; }
-            L.ptr = L.pend_link + L.start;
-            L.state = L.pend_link < 0 ? DONE : WALK;
-            if (ANY && found) {  // SL:567-569: the scene loop returns the first T > 0
-                L.state = DONE;
-                L.ent = NO_MORE_ENTITIES;
+        if (!HELP) {
+            if (L.state == LEAF) {
+                EntityResult er{-1.0f, -1, 0};
+                const bool found = leaf_triangles<ANY>(s, L.pend_pack, L.r, L.tmax, er);
+                if (er.tri >= 0) { L.best_tri = er.tri; L.best_ent = L.ent; }
+                L.ptr = L.pend_link + L.start;
+                L.state = L.pend_link < 0 ? DONE : WALK;
+                if (ANY && found) {  // SL:567-569: the scene loop returns the first T > 0
+                    L.state = DONE;
+                    L.ent = NO_MORE_ENTITIES;
+                }
+            }
+        } else {
+            // Helper lanes: a leaf holds one or two triangles, and only a handful of lanes are parked, so the second
+            // triangle of every parked lane is tested in the SAME pass by a lane that is not parked.  The owner posts
+            // its ray and the triangle index in a shared-memory mailbox, the helper posts t back, and the owner applies
+            // the accept rule to its two results in the reference's order (t itself does not depend on TMax).
+            const bool own = L.state == LEAF;
+            const unsigned owners = __ballot_sync(FULL, own);
+            if (owners != 0u) {
+                const int first = L.pend_pack >> 4, len = L.pend_pack & 0xF;
+                const bool has2 = own && len >= 2;
+                const unsigned extra = __ballot_sync(FULL, has2), helpers = ~owners;
+                const unsigned lt = (1u << lane) - 1u;
+                const int my_extra = __popc(extra & lt), n_helpers = __popc(helpers);
+                float4* box = s_box[threadIdx.x >> 5];
+                float* res = s_res[threadIdx.x >> 5];
+                const bool posted = has2 && my_extra < n_helpers;
+                if (posted) {
+                    box[2 * my_extra] = make_float4(L.r.o.x, L.r.o.y, L.r.o.z, __int_as_float(first + 1));
+                    box[2 * my_extra + 1] = make_float4(L.r.d.x, L.r.d.y, L.r.d.z, 0.0f);
+                }
+                __syncwarp();
+                const int my_help = __popc(helpers & lt);
+                const bool help = !own && my_help < __popc(extra);
+                V3 o = L.r.o, d = L.r.d;
+                int tri = first;
+                if (help) {
+                    const float4 a = box[2 * my_help], b = box[2 * my_help + 1];
+                    o = {a.x, a.y, a.z};
+                    d = {b.x, b.y, b.z};
+                    tri = __float_as_int(a.w);
+                }
+                float t0 = -1.0f;
+                if ((own && len > 0) || help) t0 = ray_triangle(s.tri48, tri, o, d);
+                if (help) res[my_help] = t0;
+                __syncwarp();
+                if (own) {
+                    bool found = false;
+                    if (t0 > 0.0f && t0 < L.tmax) { L.tmax = t0; L.best_tri = first; L.best_ent = L.ent; found = true; }
+                    if (len >= 2 && !(ANY && found)) {
+                        const float t1 = posted ? res[my_extra] : ray_triangle(s.tri48, first + 1, L.r.o, L.r.d);
+                        if (t1 > 0.0f && t1 < L.tmax) { L.tmax = t1; L.best_tri = first + 1; L.best_ent = L.ent; found = true; }
+                        for (int idx = first + 2; idx < first + len && !(ANY && found); ++idx) {  // leaves of 3+ triangles: prebuilt buffers only
+                            const float t = ray_triangle(s.tri48, idx, L.r.o, L.r.d);
+                            if (t > 0.0f && t < L.tmax) { L.tmax = t; L.best_tri = idx; L.best_ent = L.ent; found = true; }
+                        }
+                    }
+                    L.ptr = L.pend_link + L.start;
+                    L.state = L.pend_link < 0 ? DONE : WALK;
+                    if (ANY && found) {  // SL:567-569: the scene loop returns the first T > 0
+                        L.state = DONE;
+                        L.ent = NO_MORE_ENTITIES;
+                    }
+                }
             }
         }
     }
@@ -397,15 +455,15 @@ __global__ void __launch_bounds__(128, 8) trace_ww_stack_kernel(SceneView s, con
     }
 }
 
-template <int KIND, int MINB, bool CHECKED>
+template <int KIND, int MINB, bool CHECKED, bool HELP>
 void launch_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const RayOrder& order,
                   cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
 #define CNDL_WW_LAUNCH(STEPS)                                                                                     \
     {                                                                                                             \
-        auto k = trace_ww_stackless_kernel<KIND, MINB, STEPS, CHECKED>;                                           \
+        auto k = trace_ww_stackless_kernel<KIND, MINB, STEPS, CHECKED, HELP>;                                     \
         static bool configured = false;                                                                           \
         if (!configured) { /* no shared memory is used: give the whole 256 KB array to L1 */                      \
-            cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0);                           \
+            cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, HELP ? 20 : 0);               \
             configured = true;                                                                                    \
         }                                                                                                         \
         k<<<grid, 128, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); \
@@ -419,13 +477,13 @@ void launch_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView
 #undef CNDL_WW_LAUNCH
 }
 
-template <int MINB, bool CHECKED>
+template <int MINB, bool CHECKED, bool HELP>
 void launch_kind(int kind, int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const RayOrder& order,
                  cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
     switch (kind) {
-        case Q_CLOSEST: launch_steps<Q_CLOSEST, MINB, CHECKED>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
-        case Q_CLOSEST_IGNORE_TRANSPARENT: launch_steps<Q_CLOSEST_IGNORE_TRANSPARENT, MINB, CHECKED>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
-        default: launch_steps<Q_ANY, MINB, CHECKED>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        case Q_CLOSEST: launch_steps<Q_CLOSEST, MINB, CHECKED, HELP>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        case Q_CLOSEST_IGNORE_TRANSPARENT: launch_steps<Q_CLOSEST_IGNORE_TRANSPARENT, MINB, CHECKED, HELP>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        default: launch_steps<Q_ANY, MINB, CHECKED, HELP>(steps, grid, stream, s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
     }
 }
 
@@ -456,7 +514,7 @@ void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, s
 
 void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
                      unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, bool validated,
-                     cudaStream_t stream, LaunchCounter& lc) {
+                     bool helper_lanes, cudaStream_t stream, LaunchCounter& lc) {
     if (R == 0) return;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned), stream);
     unsigned grid = (unsigned)(sm_count * blocks_per_sm);
@@ -464,10 +522,14 @@ void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t 
     if (grid > need) grid = need;
     // register budget follows the requested residency: <= 8 CTAs/SM -> 64 registers, 10 -> 48, 12 -> 40
 #define CNDL_WW_ARGS kind, steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold
-    if (blocks_per_sm <= 8) { if (validated) launch_kind<8, false>(CNDL_WW_ARGS); else launch_kind<8, true>(CNDL_WW_ARGS); }
-    else if (blocks_per_sm == 9 && validated) launch_kind<9, false>(CNDL_WW_ARGS);  // 56 registers
-    else if (blocks_per_sm <= 10) launch_kind<10, true>(CNDL_WW_ARGS);
-    else launch_kind<12, true>(CNDL_WW_ARGS);
+    if (blocks_per_sm <= 8) {
+        if (validated && helper_lanes) launch_kind<8, false, true>(CNDL_WW_ARGS);
+        else if (validated) launch_kind<8, false, false>(CNDL_WW_ARGS);
+        else launch_kind<8, true, false>(CNDL_WW_ARGS);
+    }
+    else if (blocks_per_sm == 9 && validated) launch_kind<9, false, false>(CNDL_WW_ARGS);  // 56 registers
+    else if (blocks_per_sm <= 10) launch_kind<10, true, false>(CNDL_WW_ARGS);
+    else launch_kind<12, true, false>(CNDL_WW_ARGS);
 #undef CNDL_WW_ARGS
     lc.n++;
 }
