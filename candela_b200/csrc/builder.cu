@@ -196,7 +196,9 @@ __device__ __forceinline__ void warp_sah_eval(const int* s_count, const int (*s_
         const int pi = __shfl_xor_sync(0xFFFFFFFFu, idx, o);
         if (pc < cost || (pc == cost && pi < idx)) { cost = pc; idx = pi; }
     }
-    if (lane == 0 && cost < *s_best_cost) {
+    const float best_so_far = *s_best_cost;  // every lane reads (the compiler hoists the load anyway); order it before lane 0's write
+    __syncwarp();
+    if (lane == 0 && cost < best_so_far) {
         *s_best_cost = cost;
         *s_axis = axis;
         *s_border = fadd(lo, fmul(fdiv(extent, (float)kBins), __int2float_rn(idx + 1)));  // :347,:356

@@ -25,6 +25,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums /* BLO
             const int n = __shfl_up_sync(0xFFFFFFFFu, winc, o);
             if (lane >= o) winc += n;
         }
+        __syncwarp();  // every lane's read of warp_sums above is ordered before the writes below
         if (lane < BLOCK / 32) warp_sums[lane] = winc - w;
         if (lane == 31) warp_sums[BLOCK / 32] = winc;
     }
