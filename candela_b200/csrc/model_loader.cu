@@ -3,10 +3,14 @@
 // and UV packed as half floats exactly like glm::packHalf2x16 (ModelFileLoader.cpp:133-155), object-local
 // indices with the per-mesh vertex offset already applied (BVHConstructor.cpp:981-1002) and one
 // GlobalMeshNumber per triangle (ModelFileLoader.cpp:104-105: a running counter, one per mesh).
-// Host code only.  Assimp splits an OBJ into one mesh per material and joins identical vertices; this
-// reader does the same (one mesh per `usemtl` / `o` / `g` run, vertices de-duplicated per mesh on their
-// (v, vt, vn) index triple).  The ORDER of the joined vertices is not Assimp's — which cannot matter:
-// the builder and the traversal only ever see the arrays this loader returns.
+// Host code only.  The reference imports with aiProcess_JoinIdenticalVertices | Triangulate | CalcTangentSpace |
+// GenUVCoords | FlipUVs | GenNormals (ModelFileLoader.cpp:243-252).  This reader does the same where the
+// intersector can see it: one mesh per `usemtl` / `o` / `g` run (Assimp: one mesh per material), polygons
+// fan-triangulated, v flipped (uv.y = 1 - uv.y), a flat face normal generated for corners that name no `vn`, and
+// vertices joined per mesh when their position index, UV index and normal agree.  Tangents are left zero
+// (CalcTangentSpace feeds the raster pass only; GetData reads normal and UV).  The ORDER of the joined
+// vertices is not Assimp's — which cannot matter: the builder and the traversal only ever see the arrays
+// this loader returns.
 #include <cerrno>
 #include <cstdint>
 #include <cmath>
@@ -77,8 +81,19 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
     cndl_model* M = owner.get();
 
     std::vector<float> P, N, T;  // v (3), vn (3), vt (2)
-    struct Key { long v, t, n; bool operator==(const Key& o) const { return v == o.v && t == o.t && n == o.n; } };
-    struct KeyHash { size_t operator()(const Key& k) const { return (size_t)k.v * 73856093u ^ (size_t)(k.t + 1) * 19349663u ^ (size_t)(k.n + 1) * 83492791u; } };
+    // n >= 0: index into the file's `vn` list; n == -1: generated face normal, whose value is in g[]
+    struct Key {
+        long v, t, n;
+        float g[3];
+        bool operator==(const Key& o) const { return v == o.v && t == o.t && n == o.n && std::memcmp(g, o.g, sizeof(g)) == 0; }
+    };
+    struct KeyHash {
+        size_t operator()(const Key& k) const {
+            std::uint32_t b[3];
+            std::memcpy(b, k.g, sizeof(b));
+            return (size_t)k.v * 73856093u ^ (size_t)(k.t + 1) * 19349663u ^ (size_t)(k.n + 1) * 83492791u ^ b[0] ^ (b[1] * 31u) ^ (b[2] * 131u);
+        }
+    };
     std::unordered_map<Key, std::uint32_t, KeyHash> seen;  // per mesh
     bool mesh_open = false;
     std::string pending_name = "default";
@@ -95,9 +110,9 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
         cndl_vertex v;
         std::memset(&v, 0, sizeof(v));
         v.position[0] = P[3 * k.v]; v.position[1] = P[3 * k.v + 1]; v.position[2] = P[3 * k.v + 2]; v.position[3] = 1.0f;
-        float nx = 0.0f, ny = 0.0f, nz = 0.0f, tu = 0.0f, tv = 0.0f;
+        float nx = k.g[0], ny = k.g[1], nz = k.g[2], tu = 0.0f, tv = 0.0f;
         if (k.n >= 0) { nx = N[3 * k.n]; ny = N[3 * k.n + 1]; nz = N[3 * k.n + 2]; }
-        if (k.t >= 0) { tu = T[2 * k.t]; tv = T[2 * k.t + 1]; }
+        if (k.t >= 0) { tu = T[2 * k.t]; tv = 1.0f - T[2 * k.t + 1]; }  // aiProcess_FlipUVs
         v.normal_tangent[0] = cndl_pack_half2x16(nx, ny);    // data.x = packHalf2x16(vnormal.xy)   (ModelFileLoader.cpp:150)
         v.normal_tangent[1] = cndl_pack_half2x16(nz, 0.0f);  // data.y = packHalf2x16(vnormal.z, vtan.x); no tangents in an OBJ
         v.normal_tangent[2] = cndl_pack_half2x16(0.0f, 0.0f);
@@ -131,7 +146,7 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
             while (true) {
                 while (*e == ' ' || *e == '\t') ++e;
                 if (*e == '\0' || *e == '\n' || *e == '\r' || *e == '#') break;
-                Key k{0, -1, -1};
+                Key k{0, -1, -1, {0.0f, 0.0f, 0.0f}};
                 long v = std::strtol(e, &e, 10), t = 0, n = 0;
                 bool has_t = false, has_n = false;
                 if (*e == '/') {
@@ -150,6 +165,17 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
                 corners.push_back(k);
             }
             if (!problem.empty()) break;
+            if (corners.size() >= 3) {  // aiProcess_GenNormals: corners without a `vn` get the face's normal
+                const float* a = &P[3 * corners[0].v];
+                const float* b = &P[3 * corners[1].v];
+                const float* c = &P[3 * corners[2].v];
+                const float e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+                float fn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+                const float len = std::sqrt(fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2]);
+                if (len > 0.0f) { fn[0] /= len; fn[1] /= len; fn[2] /= len; }
+                for (auto& k : corners)
+                    if (k.n < 0) { k.g[0] = fn[0]; k.g[1] = fn[1]; k.g[2] = fn[2]; }
+            }
             for (size_t c = 1; c + 1 < corners.size(); ++c) {  // triangle fan, like aiProcess_Triangulate on convex polygons
                 M->indices.push_back(vertex_of(corners[0]));
                 M->indices.push_back(vertex_of(corners[c]));

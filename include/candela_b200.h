@@ -204,8 +204,9 @@ int cndl_collide_boxes_device(cndl_ctx* ctx, const cndl_box* d_boxes, size_t n, 
 /* Scene ingest without Assimp (ModelFileLoader.cpp:101-185): reads a Wavefront OBJ into what AddObject consumes — 32-byte Vertex
  * records (normal / UV packed like glm::packHalf2x16, ModelFileLoader.cpp:133-155; tangents zero), object-local indices with
  * the per-mesh vertex offset applied, and one GlobalMeshNumber per triangle (one mesh per usemtl / o / g run, numbered
- * consecutively from first_mesh_number like GlobalMeshCounter, :104-105).  Polygons are fan-triangulated; vertices are joined per
- * mesh on their (v, vt, vn) triple.  err (optional) receives a message on failure.  Host only; no GPU needed. */
+ * consecutively from first_mesh_number like GlobalMeshCounter, :104-105).  Like the reference's import flags (:243-252): polygons
+ * are fan-triangulated, v is flipped (1 - v), corners without a normal get their face's normal, and vertices are joined per mesh
+ * when position index, UV index and normal agree.  err (optional) receives a message on failure.  Host only; no GPU needed. */
 typedef struct cndl_model cndl_model;
 int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model** out, char* err, size_t err_cap);
 void cndl_model_free(cndl_model* m);

@@ -86,12 +86,17 @@ def test_obj_loader_reproduces_the_vertex_packing(cb, golden_meshes, tmp_path):
         v, s = verts[idx[k]], src[k]
         assert v["normal_tangent"][0] == L.cndl_pack_half2x16(float(N[s, 0]), float(N[s, 1]))
         assert v["normal_tangent"][1] == L.cndl_pack_half2x16(float(N[s, 2]), 0.0) and v["normal_tangent"][2] == 0
-        assert v["texcoords"] == L.cndl_pack_half2x16(float(UV[s, 0]), float(UV[s, 1]))
+        assert v["texcoords"] == L.cndl_pack_half2x16(float(UV[s, 0]), float(np.float32(1.0) - UV[s, 1]))   # aiProcess_FlipUVs
     # quads and negative indices; no normals / UVs -> zeros
     q = tmp_path / "quad.obj"
     q.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nf -5 -4 -3 -2\ng top\nf 1 2 5\n")
     verts, idx, mids, names = cb.api.load_obj(q)
     assert len(idx) == 9 and list(mids) == [0, 0, 1] and names == ["default", "top"] and np.all(verts["texcoords"] == 0)
+    # aiProcess_GenNormals: no `vn` in the file -> the quad's corners carry its face normal (0, 0, 1), the other face (0, -1, 0);
+    # the quad's four corners are joined across its two triangles
+    L = cb.api.load_library()
+    assert len(verts) == 7 and np.all(verts["normal_tangent"][:4, 0] == L.cndl_pack_half2x16(0.0, 0.0)) and np.all(verts["normal_tangent"][:4, 1] == L.cndl_pack_half2x16(1.0, 0.0))
+    assert np.all(verts["normal_tangent"][4:, 0] == L.cndl_pack_half2x16(0.0, -1.0)) and np.all(verts["normal_tangent"][4:, 1] == L.cndl_pack_half2x16(0.0, 0.0))
     assert np.array_equal(verts["position"][idx[:6]][:, :3], np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32))
     bad = tmp_path / "bad.obj"
     bad.write_text("v 0 0 0\nf 1 2 3\n")
