@@ -37,7 +37,7 @@ EXPORTS = [
     "cndl_intersect_closest", "cndl_intersect_any", "cndl_intersect_closest_device", "cndl_intersect_any_device",
     "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_generate_bounce_rays_device", "cndl_host_alloc", "cndl_host_free",
     "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device", "cndl_generate_rays_device", "cndl_collide_boxes", "cndl_collide_boxes_device",
-    "cndl_model_load_obj", "cndl_model_free", "cndl_model_vertex_count", "cndl_model_index_count", "cndl_model_mesh_count", "cndl_model_vertices",
+    "cndl_model_load_obj", "cndl_model_load_gltf", "cndl_model_load", "cndl_model_free", "cndl_model_vertex_count", "cndl_model_index_count", "cndl_model_mesh_count", "cndl_model_vertices",
     "cndl_model_indices", "cndl_model_mesh_ids", "cndl_model_mesh_name", "cndl_add_model", "cndl_pack_half2x16", "cndl_save", "cndl_load",
 ]
 
@@ -109,7 +109,8 @@ def load_library() -> C.CDLL:
     L.cndl_generate_rays_device.argtypes = [vp, C.POINTER(RaygenParams), vp, vp, sz, vp, vp, C.POINTER(sz), vp]
     L.cndl_collide_boxes.argtypes = [vp, vp, sz, vp]
     L.cndl_collide_boxes_device.argtypes = [vp, vp, sz, vp, vp]
-    L.cndl_model_load_obj.argtypes = [C.c_char_p, C.c_int32, C.POINTER(vp), C.c_char_p, sz]
+    for f in ("cndl_model_load_obj", "cndl_model_load_gltf", "cndl_model_load"):
+        getattr(L, f).argtypes = [C.c_char_p, C.c_int32, C.POINTER(vp), C.c_char_p, sz]
     L.cndl_model_free.argtypes = [vp]
     L.cndl_model_free.restype = None
     for f in ("cndl_model_vertex_count", "cndl_model_index_count", "cndl_model_mesh_count"):
@@ -166,13 +167,13 @@ def make_rays(origins, directions, tmax=0.0) -> np.ndarray:
     return r
 
 
-def load_obj(path, first_mesh_number: int = 0):
-    """cndl_model_load_obj -> (vertices[VERTEX_DT], indices[u32], mesh_ids[i32 per triangle], mesh names): what
+def load_model(path, first_mesh_number: int = 0):
+    """cndl_model_load (.obj / .gltf / .glb) -> (vertices[VERTEX_DT], indices[u32], mesh_ids[i32 per triangle], mesh names): what
     ModelFileLoader.cpp:101-185 hands to the intersector, without Assimp.  Host only."""
     L = load_library()
     h = C.c_void_p()
     err = C.create_string_buffer(512)
-    rc = L.cndl_model_load_obj(str(path).encode(), first_mesh_number, C.byref(h), err, len(err))
+    rc = L.cndl_model_load(str(path).encode(), first_mesh_number, C.byref(h), err, len(err))
     if rc != 0:
         raise CandelaError(rc, err.value.decode())
     try:
@@ -184,6 +185,9 @@ def load_obj(path, first_mesh_number: int = 0):
     finally:
         L.cndl_model_free(h)
     return verts, idx, mids, names
+
+
+load_obj = load_model
 
 
 class PinnedBuffer:

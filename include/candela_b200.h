@@ -209,6 +209,10 @@ int cndl_collide_boxes_device(cndl_ctx* ctx, const cndl_box* d_boxes, size_t n, 
  * when position index, UV index and normal agree.  err (optional) receives a message on failure.  Host only; no GPU needed. */
 typedef struct cndl_model cndl_model;
 int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model** out, char* err, size_t err_cap);
+/* glTF 2.0 (.gltf with external or base64 buffers, .glb): scene nodes depth first, one mesh per primitive, node transforms NOT
+ * applied (ProcessAssimpNode, ModelFileLoader.cpp:187-227, adds meshes as they stand); flat normals when a primitive has none. */
+int cndl_model_load_gltf(const char* path, int32_t first_mesh_number, cndl_model** out, char* err, size_t err_cap);
+int cndl_model_load(const char* path, int32_t first_mesh_number, cndl_model** out, char* err, size_t err_cap);  /* by extension */
 void cndl_model_free(cndl_model* m);
 size_t cndl_model_vertex_count(const cndl_model* m);
 size_t cndl_model_index_count(const cndl_model* m);

@@ -30,7 +30,8 @@ def test_pack_half_matches_the_reference_glm(cb, ob):
     mine = np.array([L.cndl_pack_half2x16(float(v), float(-v)) for v in vals], np.uint32)
     normal = np.isfinite(vals) & (np.abs(vals) > 1e-4) & (np.abs(vals) < 6e4)
     assert np.array_equal(mine[normal] & 0xFFFF, _glm_like_pack(vals[normal]))
-    rne = vals.astype(np.float16).view(np.uint16).astype(np.uint32)
+    with np.errstate(over="ignore"):
+        rne = vals.astype(np.float16).view(np.uint16).astype(np.uint32)
     ties = np.arange(1024, dtype=np.uint32)
     assert np.mean((mine[normal] & 0xFFFF) == rne[normal]) > 0.9 and np.any((mine[-1024:] & 0xFFFF) != rne[-1024:])   # differs from IEEE RNE exactly on ties
     if ob.REFERENCE_ROOT.exists():
@@ -104,6 +105,84 @@ def test_obj_loader_reproduces_the_vertex_packing(cb, golden_meshes, tmp_path):
         cb.api.load_obj(bad)
     with pytest.raises(cb.CandelaError, match="cannot open"):
         cb.api.load_obj(tmp_path / "missing.obj")
+
+
+def _write_gltf(tmp_path, kind):
+    """Two meshes under a small node tree (root -> [child A (mesh 1), child B (mesh 0)], root has mesh 0 too):
+    mesh 0 = indexed quad with normals + UVs (u16 indices, interleaved vertex buffer), mesh 1 = one unindexed triangle
+    without normals.  kind: 'bin' (external buffer), 'uri' (base64) or 'glb'."""
+    import base64
+    import json
+    import struct
+    quad_p = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    quad_n = np.array([[0, 0, 1]] * 4, np.float32)
+    quad_uv = np.array([[0, 0], [1, 0], [1, 0.25], [0, 0.75]], np.float32)
+    inter = np.concatenate([quad_p, quad_n, quad_uv], 1).astype(np.float32)          # stride 32
+    quad_i = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    tri_p = np.array([[0, 0, 2], [0, 3, 2], [4, 0, 2]], np.float32)
+    blob = inter.tobytes() + quad_i.tobytes() + tri_p.tobytes()
+    o_i, o_t = inter.nbytes, inter.nbytes + quad_i.nbytes
+    doc = {
+        "asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}],
+        "nodes": [{"mesh": 0, "children": [1, 2], "translation": [100, 0, 0]}, {"mesh": 1, "name": "A"}, {"mesh": 0, "name": "B"}],
+        "meshes": [{"name": "quad", "primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 3}]},
+                   {"name": "tri", "primitives": [{"attributes": {"POSITION": 4}}]}],
+        "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": inter.nbytes, "byteStride": 32},
+                        {"buffer": 0, "byteOffset": o_i, "byteLength": quad_i.nbytes}, {"buffer": 0, "byteOffset": o_t, "byteLength": tri_p.nbytes}],
+        "accessors": [{"bufferView": 0, "byteOffset": 0, "componentType": 5126, "count": 4, "type": "VEC3"},
+                      {"bufferView": 0, "byteOffset": 12, "componentType": 5126, "count": 4, "type": "VEC3"},
+                      {"bufferView": 0, "byteOffset": 24, "componentType": 5126, "count": 4, "type": "VEC2"},
+                      {"bufferView": 1, "componentType": 5123, "count": 6, "type": "SCALAR"},
+                      {"bufferView": 2, "componentType": 5126, "count": 3, "type": "VEC3"}],
+    }
+    if kind == "bin":
+        (tmp_path / "geo.bin").write_bytes(blob)
+        doc["buffers"] = [{"uri": "geo.bin", "byteLength": len(blob)}]
+        path = tmp_path / "scene.gltf"
+        path.write_text(json.dumps(doc))
+    elif kind == "uri":
+        doc["buffers"] = [{"uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode(), "byteLength": len(blob)}]
+        path = tmp_path / "scene_uri.gltf"
+        path.write_text(json.dumps(doc, indent=2))
+    else:
+        doc["buffers"] = [{"byteLength": len(blob)}]
+        js = json.dumps(doc).encode()
+        js += b" " * (-len(js) % 4)
+        bn = blob + b"\0" * (-len(blob) % 4)
+        path = tmp_path / "scene.glb"
+        path.write_bytes(b"glTF" + struct.pack("<II", 2, 12 + 8 + len(js) + 8 + len(bn)) + struct.pack("<I", len(js)) + b"JSON" + js +
+                         struct.pack("<I", len(bn)) + b"BIN\0" + bn)
+    return path, quad_p, quad_uv, tri_p
+
+
+@pytest.mark.parametrize("kind", ["bin", "uri", "glb"])
+def test_gltf_loader(cb, tmp_path, kind):
+    path, quad_p, quad_uv, tri_p = _write_gltf(tmp_path, kind)
+    verts, idx, mids, names = cb.api.load_model(path, first_mesh_number=5)
+    L = cb.api.load_library()
+    # node walk: root (quad), child A (tri), child B (quad again); transforms are NOT applied, as in ProcessAssimpNode
+    assert names == ["quad", "tri", "quad"] and list(mids) == [5, 5, 6, 7, 7]
+    assert len(verts) == 4 + 3 + 4 and list(idx) == [0, 1, 2, 0, 2, 3, 4, 5, 6, 7, 8, 9, 7, 9, 10]
+    assert np.array_equal(verts["position"][:4, :3], quad_p) and np.array_equal(verts["position"][4:7, :3], tri_p) and np.array_equal(verts["position"][7:, :3], quad_p)
+    for k in range(4):
+        assert verts["texcoords"][k] == L.cndl_pack_half2x16(float(quad_uv[k, 0]), float(np.float32(1) - quad_uv[k, 1]))      # FlipUVs
+        assert verts["normal_tangent"][k, 0] == L.cndl_pack_half2x16(0.0, 0.0) and verts["normal_tangent"][k, 1] == L.cndl_pack_half2x16(1.0, 0.0)
+    # the bare triangle gets its face normal: cross((0,3,0), (4,0,0)) = (0,0,-12) -> (0,0,-1)
+    assert np.all(verts["normal_tangent"][4:7, 1] == L.cndl_pack_half2x16(-1.0, 0.0)) and np.all(verts["texcoords"][4:7] == L.cndl_pack_half2x16(0.0, 0.0))
+
+
+def test_gltf_errors(cb, tmp_path):
+    (tmp_path / "a.gltf").write_text("{ not json")
+    with pytest.raises(cb.CandelaError, match="JSON"):
+        cb.api.load_model(tmp_path / "a.gltf")
+    (tmp_path / "b.gltf").write_text('{"asset":{"version":"2.0"},"buffers":[{"uri":"nope.bin","byteLength":4}],"bufferViews":[],"accessors":[],"meshes":[]}')
+    with pytest.raises(cb.CandelaError, match="cannot open buffer"):
+        cb.api.load_model(tmp_path / "b.gltf")
+    (tmp_path / "c.gltf").write_text('{"asset":{"version":"2.0"},"buffers":[{"uri":"data:application/octet-stream;base64,AAAA","byteLength":3}],'
+                                     '"bufferViews":[{"buffer":0,"byteLength":3}],"accessors":[{"bufferView":0,"componentType":5126,"count":9,"type":"VEC3"}],'
+                                     '"meshes":[{"primitives":[{"attributes":{"POSITION":0}}]}]}')
+    with pytest.raises(cb.CandelaError, match="past its buffer"):
+        cb.api.load_model(tmp_path / "c.gltf")
 
 
 @pytest.mark.gpu
