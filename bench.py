@@ -11,7 +11,8 @@ scene, stackless node format.  One "step" = one pass of the hot path over one su
                buffers: H2D copy of the rays and D2H copy of the hit records inside the timed region.
   roofline   : algorithmic bytes per ray (oracle counters on the same rays and BVH)
                x rays / kernel time, against the measured HBM bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline: the oracle port of the reference's traversal on all host cores (rank 0, N=1 only).
+  cpu_baseline: the reference's GLSL traversal compiled against its glm (oracle/_ref; else the oracle port) on all host cores
+                (rank 0, N=1 only).
 
 --impl reference times the reference's CPU path (the oracle port: the reference's traversal is GLSL
 and has no CPU implementation; its builder is timed through oracle/_ref when that library exists).
@@ -115,8 +116,26 @@ def build_workload(rank: int):
     return scenes, verts, indices, mesh_ids, iv, ip
 
 
+def reference_tracer(ob, threads):
+    """(trace function, kind, description): the reference's own GLSL traversal compiled against its glm (oracle/_ref, built in the
+    container where /root/reference exists and shipped with the snapshot) when that library loads, else the oracle port."""
+    if ob.REF_LIB_PATH.exists():
+        try:
+            ob.ref_lib()
+
+            def trace(kind, nodes, tris, verts, ents, rays):
+                return ob.ref_glsl_trace(ob.STACKLESS, kind, nodes, tris, verts, ents, rays, nthreads=threads)
+            return trace, "reference", "the reference's TraverseBVHStackless.glsl compiled against its vendored glm (oracle/_ref), std::thread over ray ranges"
+        except OSError:
+            pass
+
+    def trace(kind, nodes, tris, verts, ents, rays):
+        return ob.trace(ob.STACKLESS, kind, nodes, tris, verts, ents, rays, nthreads=threads)[0]
+    return trace, "port", "oracle port of the GLSL traversal, std::thread over ray ranges"
+
+
 def run_reference(args):
-    """The reference's CPU path on the host cores: oracle port (traversal) [+ oracle/_ref builder]."""
+    """The reference's CPU path on the host cores: its GLSL traversal compiled (oracle/_ref) or the oracle port [+ oracle/_ref builder]."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -139,11 +158,12 @@ def run_reference(args):
     hits, _ = ob.trace(ob.STACKLESS, ob.CLOSEST, b.nodes, b.tris, verts, ents, prim, nthreads=threads)
     rays, _ = scenes.bounce_rays(prim, hits, b.tris, verts, seed=1000)
     R = len(rays)
+    trace, kind, how = reference_tracer(ob, threads)
     for _ in range(args.warmup):
-        ob.trace(ob.STACKLESS, ob.CLOSEST_IGNORE_TRANSPARENT, b.nodes, b.tris, verts, ents, rays, nthreads=threads)
+        trace(ob.CLOSEST_IGNORE_TRANSPARENT, b.nodes, b.tris, verts, ents, rays)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, cnt = ob.trace(ob.STACKLESS, ob.CLOSEST_IGNORE_TRANSPARENT, b.nodes, b.tris, verts, ents, rays, nthreads=threads)
+        trace(ob.CLOSEST_IGNORE_TRANSPARENT, b.nodes, b.tris, verts, ents, rays)
     dt = time.perf_counter() - t0
     mrays = R * args.steps / dt / 1e6
     line = {
@@ -152,8 +172,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "diffuse_gi_1080p_1spp_closest_hit", "scene": "S260k stand-in (262,624 triangles)", "node_format": "stackless",
                    "rays_per_step": R, "resolution": [WIDTH, HEIGHT]},
-        "cpu_baseline": {"value": round(mrays, 3), "unit": "Mrays/s", "cores": threads, "kind": "port",
-                         "sample": f"the full {R}-ray diffuse batch per step, oracle port of the GLSL traversal, std::thread over ray ranges",
+        "cpu_baseline": {"value": round(mrays, 3), "unit": "Mrays/s", "cores": threads, "kind": kind,
+                         "sample": f"the full {R}-ray diffuse batch per step; {how}",
                          "build_ms_port_1thread": round(port_build_ms, 1), "build_ms_reference_builder_1thread": None if ref_build_ms is None else round(ref_build_ms, 1)},
         "e2e": {"value": round(mrays, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -322,17 +342,20 @@ def run_ours(args):
                             "bytes_per_ray": round(b_ray, 1), "node_iters_per_ray": round(nn, 3), "tri_tests_per_ray": round(nt, 3),
                             "ray_io_bytes_per_ray_not_included": 64, "kernel_ms": round(kernel_ms, 4)}
         if world == 1:
+            cpu_trace, cpu_kind, cpu_how = reference_tracer(ob, threads)
             reps, t_cpu = 0, 0.0
             while t_cpu < 1.5 and reps < 20:
                 t0 = time.perf_counter()
-                ob.trace(ob.STACKLESS, ob.CLOSEST_IGNORE_TRANSPARENT, nodes, tris, verts, ents, rays, nthreads=threads)
+                cpu_hits = cpu_trace(ob.CLOSEST_IGNORE_TRANSPARENT, nodes, tris, verts, ents, rays)
                 t_cpu += time.perf_counter() - t0
                 reps += 1
+            if cpu_kind == "reference":   # the benchmarked batch against the compiled reference shaders themselves
+                line["parity"]["bit_identical_to_compiled_reference_glsl"] = bool(cpu_hits.tobytes() == got.tobytes())
             t0 = time.perf_counter()
             ob.build(ob.STACKLESS, verts, indices, mesh_ids)
             cpu_build_ms = 1e3 * (time.perf_counter() - t0)
-            line["cpu_baseline"] = {"value": round(R * reps / t_cpu / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": "port",
-                                    "sample": f"{reps} passes over the full {R}-ray batch ({t_cpu * threads:.0f} core-seconds)",
+            line["cpu_baseline"] = {"value": round(R * reps / t_cpu / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": cpu_kind,
+                                    "sample": f"{reps} passes over the full {R}-ray batch ({t_cpu * threads:.0f} core-seconds); {cpu_how}",
                                     "build_ms_1thread": round(cpu_build_ms, 1)}
         print(json.dumps(line), flush=True)
 

@@ -16,10 +16,12 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
-// GLSL 4.50 §8.3: min(x,y) = y<x ? y : x, max(x,y) = x<y ? y : x.  These differ from
-// fminf/fmaxf only when an operand is NaN (or in the sign of a zero result).
-__device__ __forceinline__ float glsl_min(float x, float y) { return y < x ? y : x; }
-__device__ __forceinline__ float glsl_max(float x, float y) { return x < y ? y : x; }
+// min / max exactly as the reference's vendored glm 0.9.8.5 evaluates them (glm/detail/func_common.inl:15-28:
+// x < y ? x : y and x > y ? x : y) — the forms its CPU code (Physics.cpp) runs, and the ones its GLSL runs when the
+// shader files are compiled against glm (GLSL 4.50 §8.3 leaves the result undefined when an operand is NaN).  They
+// differ from fminf/fmaxf only when an operand is NaN (or in the sign of a zero result).
+__device__ __forceinline__ float glsl_min(float x, float y) { return x < y ? x : y; }
+__device__ __forceinline__ float glsl_max(float x, float y) { return x > y ? x : y; }
 
 __device__ __forceinline__ V3 vsub(V3 a, V3 b) { return {fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)}; }
 __device__ __forceinline__ V3 vneg(V3 a) { return {-a.x, -a.y, -a.z}; }

@@ -299,6 +299,9 @@ def ref_lib() -> C.CDLL:
         R.ref_build.restype = C.c_int
         R.ref_build.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]
         R.ref_fetch.argtypes = [vp, vp, vp]
+        R.ref_glsl_trace.argtypes = [C.c_int, C.c_int, vp, C.c_uint64, vp, vp, vp, C.c_int32, vp, C.c_uint64, vp]
+        R.ref_glsl_trace_mt.argtypes = [C.c_int, C.c_int, vp, C.c_uint64, vp, vp, vp, C.c_int32, vp, C.c_uint64, vp, C.c_int]
+        R.ref_glsl_get_data.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_uint64, vp]
         R.ref_pack_half2x16.argtypes = [C.c_float, C.c_float]
         R.ref_pack_half2x16.restype = C.c_uint32
         R.ref_collide_box.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp]
@@ -347,4 +350,28 @@ def ref_collide_boxes(nodes, tris, verts, entities, boxes) -> np.ndarray:
 def ref_pack_half2x16(x: float, y: float) -> int:
     """glm::packHalf2x16 of the reference's vendored glm (oracle/_ref)."""
     return int(ref_lib().ref_pack_half2x16(float(x), float(y)))
+
+
+def ref_glsl_trace(fmt, kind, nodes, tris, verts, entities, rays, nthreads=1):
+    """The reference's own GLSL traversal (TraverseBVHStackless.glsl / TraverseBVHStack.glsl), transliterated
+    syntactically and compiled against its vendored glm (oracle/_ref): hit records, or any-hit distances."""
+    rays = np.ascontiguousarray(rays, dtype=RAY_DT)
+    nodes = np.ascontiguousarray(nodes)
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
+    verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DT)
+    out = np.zeros(len(rays), dtype=np.float32 if kind == ANY else HIT_DT)
+    ref_lib().ref_glsl_trace_mt(fmt, kind, _p(nodes), len(nodes), _p(tris), _p(verts), _p(entities), len(entities), _p(rays), len(rays), _p(out), nthreads)
+    return out
+
+
+def ref_glsl_get_data(tris, verts, entities, hits):
+    """GetData of the compiled reference shader (texture references with Albedo = -1)."""
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
+    verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DT)
+    hits = np.ascontiguousarray(hits, dtype=HIT_DT)
+    out = np.zeros(len(hits), dtype=ATTR_DT)
+    ref_lib().ref_glsl_get_data(_p(tris), _p(verts), _p(entities), len(entities), _p(hits), len(hits), _p(out))
+    return out
 

@@ -18,11 +18,16 @@
  *              tests/golden/make_golden.py from the compiled, unmodified
  *              reference builder in oracle/_ref/) require byte equality of the
  *              node, triangle and vertex buffers.
- *   traversal: PARITY UNPINNED by the reference.  The reference's traversal
- *              exists only as GLSL, has no tests or golden vectors, and cannot
- *              be executed here (no GL context, no GLSL compiler).  It is
- *              checked against closed-form known-answer cases, a brute-force
- *              all-triangles scan, and stack-vs-stackless agreement only.
+ *   traversal: PINNED.  The reference's traversal exists only as GLSL and has no
+ *              tests of its own, but its two shader include files compile as C++
+ *              against the reference's vendored glm after a purely syntactic
+ *              rewrite (oracle/ref_shim/glsl_to_cpp.py + ref_glsl.cpp ->
+ *              oracle/_ref/libcandela_ref.so).  tests/test_oracle_traversal.py
+ *              requires bit-identical hit records / any-hit distances on every
+ *              case (live where /root/reference exists; everywhere through the
+ *              committed outputs tests/golden/reference_traversal_golden.npz).
+ *   GetData  : PINNED the same way (tests/test_get_data.py).
+ *   collide  : PINNED against the compiled Physics.cpp (tests/test_collide.py).
  *
  * Build flags are part of the definition of "the reference result":
  *   g++ -std=c++17 -O2 -ffp-contract=off   (no -march=native, no -ffast-math)

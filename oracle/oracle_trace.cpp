@@ -1,12 +1,14 @@
-// TEST INFRASTRUCTURE ONLY — see oracle.h.  PARITY UNPINNED for this file:
-// the reference's traversal exists only as GLSL and cannot be executed here.
+// TEST INFRASTRUCTURE ONLY — see oracle.h.  PINNED: the reference's traversal exists only as GLSL, but its two
+// shader include files compile as C++ against the reference's own glm after a purely syntactic rewrite
+// (oracle/ref_shim/glsl_to_cpp.py, ref_glsl.cpp -> oracle/_ref); tests/test_oracle_traversal.py requires this
+// restatement to return bit-identical hit records, any-hit distances and GetData outputs.
 //
 // Scalar C++ restatement of the reference's GLSL traversal.  Paths are
 // relative to /root/reference/Source/Core/Shaders/Intersectors/Include/ :
 //   SL = TraverseBVHStackless.glsl,  ST = TraverseBVHStack.glsl.
 // GLSL leaves FP contraction and min/max-on-NaN to the implementation; the
 // oracle fixes them: no contraction (-ffp-contract=off), IEEE division,
-// min(x,y) = y<x?y:x and max(x,y) = x<y?y:x (GLSL 4.50 spec, 8.3), dot and
+// min(x,y) = x<y?x:y and max(x,y) = x>y?x:y (glm's forms; GLSL leaves NaN operands undefined), dot and
 // mat*vec summed in glm 0.9.8.5's order.
 #include "oracle.h"
 
@@ -28,8 +30,11 @@ static_assert(sizeof(Entity192) == 192, "BVHEntity is 192 bytes (Intersector.h:4
 inline int32_t fbits(float f) { int32_t i; std::memcpy(&i, &f, 4); return i; }
 inline float ibits(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 
-inline float smin(float x, float y) { return y < x ? y : x; }
-inline float smax(float x, float y) { return x < y ? y : x; }
+// min / max as the reference's vendored glm 0.9.8.5 evaluates them (glm/detail/func_common.inl:15-28), which is what the
+// compiled reference shaders (oracle/_ref, ref_glsl.cpp) execute.  GLSL leaves the result undefined when an operand is
+// NaN; the two forms differ from `y < x ? y : x` / `x < y ? y : x` only there (and in the sign of a zero).
+inline float smin(float x, float y) { return x < y ? x : y; }
+inline float smax(float x, float y) { return x > y ? x : y; }
 inline V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 inline V3 neg(V3 a) { return {-a.x, -a.y, -a.z}; }
 inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }

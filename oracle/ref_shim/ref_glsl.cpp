@@ -1,0 +1,139 @@
+// TEST INFRASTRUCTURE ONLY — never linked into the product library.
+//
+// The reference's GLSL traversal (Source/Core/Shaders/Intersectors/Include/TraverseBVHStackless.glsl and
+// TraverseBVHStack.glsl) executed on the CPU: oracle/ref_shim/glsl_to_cpp.py rewrites the two include files
+// syntactically (qualifiers, literals, swizzles, SSBO blocks -> pointers) into oracle/_ref/gen/*.inc, and this
+// file compiles them against the reference's own vendored glm 0.9.8.5, whose vector functions follow the GLSL
+// specification (min(x,y) = y<x?y:x, max(x,y) = x<y?y:x, component-wise operators, mat*vec).  Compiled with
+// -O2 -ffp-contract=off like the oracle, so every float operation is a separately rounded IEEE operation.
+// This is what pins the oracle's traversal restatement: tests require identical hit records.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+#undef INFINITY
+
+#include <glm/glm.hpp>
+#include <glm/gtc/packing.hpp>
+
+namespace glsl_prelude {
+struct sampler2D {};
+inline glm::vec4 texture(const sampler2D&, const glm::vec2&) { return glm::vec4(0.0f); }  // no texture unit here: the ModelColor branch is the one exercised
+}  // namespace glsl_prelude
+
+namespace ref_stackless {
+using namespace glm;
+using namespace glsl_prelude;
+#include "gen/stackless.inc"
+}  // namespace ref_stackless
+
+namespace ref_stack {
+using namespace glm;
+using namespace glsl_prelude;
+#include "gen/stack.inc"
+}  // namespace ref_stack
+
+namespace {
+struct Hit32 { float t, u, v, w; int32_t mesh, tri, entity, iters; };
+struct Attr32 { float nx, ny, nz, u, v, emissivity, alpha; int32_t mesh; };
+}  // namespace
+
+#define BIND(NS)                                                                  \
+    NS::BVHNodes = static_cast<const NS::Node*>(nodes);                           \
+    NS::BVHTris = static_cast<const NS::Triangle*>(tris);                         \
+    NS::BVHVertices = static_cast<const NS::Vertex*>(verts);                      \
+    NS::BVHEntities = static_cast<const NS::BVHEntity*>(ents);                    \
+    NS::u_EntityCount = n_ents;                                                   \
+    NS::u_TotalNodes = (int)n_nodes;
+
+extern "C" {
+
+// kind: 0 IntersectScene, 1 IntersectSceneIgnoreTransparent -> 32-byte hit records; 2 any-hit -> one float per ray.
+// Any-hit with ray tmax <= 0 calls the shader's own `float IntersectScene(o, d)`; with tmax > 0 (the ABI's extension)
+// it runs that function's six-line entity loop around the shader's Intersect*Occlusion with the ray's TMax.
+int ref_glsl_trace(int format, int kind, const void* nodes, uint64_t n_nodes, const void* tris, const void* verts, const void* ents, int32_t n_ents,
+                   const float* rays, uint64_t R, void* out) {
+    if (format == 0) { BIND(ref_stackless) } else { BIND(ref_stack) }
+    for (uint64_t i = 0; i < R; ++i) {
+        const glm::vec3 o(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2]), d(rays[8 * i + 4], rays[8 * i + 5], rays[8 * i + 6]);
+        const float ray_tmax = rays[8 * i + 7];
+        if (kind == 2) {
+            float t;
+            if (!(ray_tmax > 0.0f)) {
+                t = format == 0 ? ref_stackless::IntersectRay(o, d) : ref_stack::IntersectRay(o, d);  // float IntersectRay(o, d): the any-hit entry point of both files
+            } else {
+                t = -1.0f;
+                for (int e = 0; e < n_ents; ++e) {
+                    const float tr = format == 0
+                        ? ref_stackless::IntersectBVHStacklessOcclusion(o, d, ref_stackless::BVHEntities[e].NodeOffset, ref_stackless::BVHEntities[e].NodeCount,
+                                                                        ref_stackless::BVHEntities[e].InverseMatrix, ray_tmax)
+                        : ref_stack::IntersectBVHStackOcclusion(o, d, ref_stack::BVHEntities[e].NodeOffset, ref_stack::BVHEntities[e].NodeCount,
+                                                                ref_stack::BVHEntities[e].InverseMatrix, ray_tmax);
+                    if (tr > 0.0f) { t = tr; break; }
+                }
+            }
+            static_cast<float*>(out)[i] = t;
+        } else {
+            int mesh = -1, tri = -1, entity = -1, iters = 0;  // `out` parameters the shader leaves unwritten on a miss
+            glm::vec4 tuvw;
+            if (format == 0) tuvw = kind == 0 ? ref_stackless::IntersectScene(o, d, mesh, tri, entity, iters) : ref_stackless::IntersectSceneIgnoreTransparent(o, d, mesh, tri, entity, iters);
+            else tuvw = kind == 0 ? ref_stack::IntersectScene(o, d, mesh, tri, entity, iters) : ref_stack::IntersectSceneIgnoreTransparent(o, d, mesh, tri, entity, iters);
+            static_cast<Hit32*>(out)[i] = Hit32{tuvw.x, tuvw.y, tuvw.z, tuvw.w, mesh, tri, entity, iters};
+        }
+    }
+    return 0;
+}
+
+// The same over `nthreads` host threads (contiguous ray ranges).  The shader globals are bound once, before the threads
+// start, and only read afterwards.  This is the reference arm of bench.py (`--impl reference`, cpu_baseline kind "reference").
+int ref_glsl_trace_mt(int format, int kind, const void* nodes, uint64_t n_nodes, const void* tris, const void* verts, const void* ents, int32_t n_ents,
+                      const float* rays, uint64_t R, void* out, int nthreads) {
+    if (nthreads <= 1 || R < 4096) return ref_glsl_trace(format, kind, nodes, n_nodes, tris, verts, ents, n_ents, rays, R, out);
+    ref_glsl_trace(format, kind, nodes, n_nodes, tris, verts, ents, n_ents, rays, 0, out);  // binds the globals
+    const uint64_t chunk = (R + (uint64_t)nthreads - 1) / (uint64_t)nthreads;
+    const size_t out_elt = kind == 2 ? sizeof(float) : sizeof(Hit32);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) {
+        const uint64_t lo = (uint64_t)t * chunk, hi = lo + chunk < R ? lo + chunk : R;
+        if (lo >= hi) break;
+        pool.emplace_back([=] {
+            ref_glsl_trace(format, kind, nodes, n_nodes, tris, verts, ents, n_ents, rays + 8 * lo, hi - lo, static_cast<char*>(out) + lo * out_elt);
+        });
+    }
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
+// GetData (TraverseBVHStackless.glsl:375-408) on hit records; texture references all carry Albedo = -1, so Albedo is the
+// ModelColor branch and is not reported.
+int ref_glsl_get_data(const void* tris, const void* verts, const void* ents, int32_t n_ents, const void* hits_, uint64_t R, void* out_) {
+    const void* nodes = nullptr;
+    const uint64_t n_nodes = 0;
+    BIND(ref_stackless)
+    const Hit32* hits = static_cast<const Hit32*>(hits_);
+    int max_mesh = 0;
+    for (uint64_t i = 0; i < R; ++i) max_mesh = hits[i].mesh > max_mesh ? hits[i].mesh : max_mesh;
+    std::vector<ref_stackless::TextureReferences> refs((size_t)max_mesh + 1);
+    for (auto& r : refs) { r.ModelColor = glm::vec4(1.0f); r.Albedo = -1; r.Normal = -1; r.Pad[0] = r.Pad[1] = 0; }
+    ref_stackless::BVHTextureReferences = refs.data();
+    Attr32* out = static_cast<Attr32*>(out_);
+    for (uint64_t i = 0; i < R; ++i) {
+        const Hit32& h = hits[i];
+        glm::vec3 normal(0.0f), albedo(0.0f);
+        float emissivity = 0.0f, alpha = 0.0f;
+        // on a miss the shader writes Normal / Albedo / Emissivity and leaves Alpha alone
+        ref_stackless::GetData(glm::vec4(h.t, h.u, h.v, h.w), h.mesh, h.tri, h.entity, normal, albedo, emissivity, alpha);
+        const bool miss = h.t < 0.0f || h.mesh < 0;
+        glm::vec2 uv(0.0f);
+        if (!miss) {  // UV is a local of GetData: the same expression, evaluated by the same glm code
+            const auto& T = ref_stackless::BVHTris[h.tri];
+            const auto &A = ref_stackless::BVHVertices[T.PackedData[0]], &B = ref_stackless::BVHVertices[T.PackedData[1]], &C = ref_stackless::BVHVertices[T.PackedData[2]];
+            uv = (glm::unpackHalf2x16(A.PackedData.w) * h.u) + (glm::unpackHalf2x16(B.PackedData.w) * h.v) + (glm::unpackHalf2x16(C.PackedData.w) * h.w);
+        }
+        out[i] = Attr32{normal.x, normal.y, normal.z, uv.x, uv.y, emissivity, alpha, h.mesh};
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -58,6 +58,34 @@ def test_oracle_half_unpack_is_exact_for_every_finite_pattern(ob):
     assert np.array_equal(a["uv"][:, 1], want[::-1] + np.float32(0))
 
 
+def test_oracle_get_data_vs_compiled_reference_glsl(ob, golden_meshes):
+    """GetData of the reference's shader file itself, compiled against its glm (oracle/_ref), on traced hit records of a
+    scene with real packed normals / UVs and three entities."""
+    if not ob.REFERENCE_ROOT.exists():
+        pytest.skip("/root/reference is not present (GPU box): tests/golden/reference_traversal_golden.npz covers GetData there")
+    from cases import scale_rot, translate
+    from helpers import rays_in_box
+    P, F = golden_meshes["dragon"]
+    N, UV = _sphere_like_attributes(P, 3)
+    V = ob.pack_vertices(P, N, UV)
+    sc = ob.Scene(ob.STACKLESS)
+    sc.add_object(2, V, F.ravel(), (np.arange(len(F)) % 5).astype(np.int32))
+    sc.push_entity(2, emissive=1.5)
+    sc.push_entity(2, model=scale_rot(0.5, 30.0, (3.0, 0.5, 0.0)), translucency=0.4)
+    sc.push_entity(2, model=translate(-3.0, 0.0, 1.0), emissive=7.0, translucency=1.0)
+    rays = rays_in_box(P.min(0) - (3.5, 0.5, 0.5), P.max(0) + (3.5, 0.5, 1.5), 20000, 11)
+    hits, _ = sc.trace(ob.CLOSEST, rays, nthreads=ob.hardware_threads())
+    assert hits.tobytes() == ob.ref_glsl_trace(ob.STACKLESS, ob.CLOSEST, sc.nodes, sc.tris, sc.verts, sc.entities, rays).tobytes()
+    mine = ob.get_data(sc.tris, sc.verts, sc.entities, hits)
+    ref = ob.ref_glsl_get_data(sc.tris, sc.verts, sc.entities, hits)
+    hit = hits["t"] > 0
+    assert hit.sum() > 3000
+    # the shader leaves Alpha unwritten on a miss (the record says 0 there); everything else is compared bit for bit
+    assert mine[hit].tobytes() == ref[hit].tobytes()
+    for f in ("normal", "uv", "emissivity", "mesh"):
+        assert mine[f][~hit].tobytes() == ref[f][~hit].tobytes(), f
+
+
 @pytest.mark.gpu
 def test_gpu_get_data_bit_identical_to_oracle(cb, ob, golden_meshes):
     from cases import scale_rot, translate

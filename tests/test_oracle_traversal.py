@@ -131,3 +131,52 @@ def test_committed_traversal_vectors(ob, golden_meshes):
         any_t, _ = sc.trace(ob.ANY, z["rays"])
         assert any_t.tobytes() == z[f"{label}_any"].tobytes()
         assert [c["node_iters"], c["tri_tests"], c["capped"], c["hits"]] == z[f"{label}_counters"].tolist()
+
+
+# ---- the reference's own GLSL, compiled (oracle/_ref): this is what pins the restatement ----------------------------
+
+def _reference_cases(ob, golden_meshes):
+    import reference_cases
+    for fmt, label in ((ob.STACKLESS, "stackless"), (ob.STACK, "stack")):
+        for c in reference_cases.build(ob, golden_meshes, fmt):
+            yield fmt, label, c
+
+
+def test_oracle_matches_committed_reference_outputs(ob, golden_meshes):
+    """tests/golden/reference_traversal_golden.npz holds outputs of the reference's GLSL traversal itself (compiled against
+    its glm by oracle/ref_shim; made by tests/golden/make_reference_traversal_golden.py).  Runs everywhere, also on the GPU box."""
+    import reference_cases
+    z = np.load(GOLDEN / "reference_traversal_golden.npz")
+    n = 0
+    for fmt, label, c in _reference_cases(ob, golden_meshes):
+        sc, rays = c["scene"], c["rays"]
+        assert rays.view(np.float32).reshape(-1, 8).tobytes() == z[f"{label}/{c['name']}/rays"].tobytes(), "fixture made from other rays"
+        for kname, kind, tmax in reference_cases.KINDS:
+            got, _ = sc.trace(kind, reference_cases.with_tmax(rays, tmax), nthreads=2)
+            assert got.tobytes() == z[f"{label}/{c['name']}/{kname}"].tobytes(), (label, c["name"], kname)
+            n += len(rays)
+        if fmt == ob.STACKLESS:
+            hits, _ = sc.trace(ob.CLOSEST, rays)
+            assert ob.get_data(sc.tris, sc.verts, sc.entities, hits).tobytes() == z[f"{label}/{c['name']}/get_data"].tobytes(), (c["name"], "GetData")
+    assert n > 70000
+
+
+def test_oracle_vs_compiled_reference_glsl_live(ob, golden_meshes):
+    """Every case of cases.py at full size against the compiled reference shaders (only where /root/reference exists)."""
+    if not ob.REFERENCE_ROOT.exists():
+        pytest.skip("/root/reference is not present (GPU box): the committed fixture covers this")
+    import cases
+    n = 0
+    for fmt in (ob.STACKLESS, ob.STACK):
+        for c in cases.build_cases(ob, golden_meshes, fmt):
+            sc = c["scene"]
+            rays = c["rays"][:6000]
+            for kind, tmax in ((ob.CLOSEST, 0.0), (ob.CLOSEST_IGNORE_TRANSPARENT, 0.0), (ob.ANY, 0.0), (ob.ANY, 2.4)):
+                r = rays.copy()
+                r["tmax"] = tmax
+                mine, _ = sc.trace(kind, r, nthreads=ob.hardware_threads())
+                ref = ob.ref_glsl_trace(fmt, kind, sc.nodes, sc.tris, sc.verts, sc.entities, r)
+                assert mine.tobytes() == ref.tobytes(), (fmt, c["name"], kind, tmax)
+                n += len(r)
+    assert n > 200000
+
