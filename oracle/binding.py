@@ -301,6 +301,8 @@ def ref_lib() -> C.CDLL:
         R.ref_fetch.argtypes = [vp, vp, vp]
         R.ref_glsl_trace.argtypes = [C.c_int, C.c_int, vp, C.c_uint64, vp, vp, vp, C.c_int32, vp, C.c_uint64, vp]
         R.ref_glsl_trace_mt.argtypes = [C.c_int, C.c_int, vp, C.c_uint64, vp, vp, vp, C.c_int32, vp, C.c_uint64, vp, C.c_int]
+        R.ref_glsl_primary_rays.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        R.ref_glm_inverse.argtypes = [vp, vp]
         R.ref_glsl_get_data.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_uint64, vp]
         R.ref_pack_half2x16.argtypes = [C.c_float, C.c_float]
         R.ref_pack_half2x16.restype = C.c_uint32
@@ -374,4 +376,21 @@ def ref_glsl_get_data(tris, verts, entities, hits):
     out = np.zeros(len(hits), dtype=ATTR_DT)
     ref_lib().ref_glsl_get_data(_p(tris), _p(verts), _p(entities), len(entities), _p(hits), len(hits), _p(out))
     return out
+
+
+def ref_primary_rays(inv_view, inv_proj, W, H) -> np.ndarray:
+    """Primary rays formed by the reference shader's own GetRayDirectionAt + main() arithmetic (oracle/_ref)."""
+    iv = np.ascontiguousarray(np.asarray(inv_view, dtype=np.float32).reshape(4, 4).T).ravel()
+    ip = np.ascontiguousarray(np.asarray(inv_proj, dtype=np.float32).reshape(4, 4).T).ravel()
+    rays = np.zeros(W * H, dtype=RAY_DT)
+    ref_lib().ref_glsl_primary_rays(_p(iv), _p(ip), W, H, _p(rays))
+    return rays
+
+
+def ref_glm_inverse(model) -> np.ndarray:
+    """glm::inverse of the reference's vendored glm; model and result are 4x4 (row, column) matrices."""
+    m = np.ascontiguousarray(np.asarray(model, dtype=np.float32).reshape(4, 4).T).ravel()
+    out = np.zeros(16, dtype=np.float32)
+    ref_lib().ref_glm_inverse(_p(m), _p(out))
+    return out.reshape(4, 4).T.copy()
 

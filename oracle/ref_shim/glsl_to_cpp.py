@@ -102,6 +102,22 @@ def transliterate(text: str) -> str:
     return "\n".join(out) + "\n"
 
 
+def extract_function(text: str, name: str) -> str:
+    """The definition of one top-level function (from its signature line to the closing brace in column 0)."""
+    lines = text.splitlines()
+    for i, ln in enumerate(lines):
+        if re.match(r"^\w[\w\s]*\b" + re.escape(name) + r"\s*\(", ln):
+            j = i
+            while lines[j].rstrip() != "}":
+                j += 1
+            return "\n".join(lines[i:j + 1]) + "\n"
+    raise SystemExit(f"{name} not found")
+
+
 if __name__ == "__main__":
-    src, dst = sys.argv[1], sys.argv[2]
-    open(dst, "w").write(transliterate(open(src, errors="replace").read()))
+    if sys.argv[1] == "--function":   # glsl_to_cpp.py --function NAME in.glsl out.inc
+        name, src, dst = sys.argv[2], sys.argv[3], sys.argv[4]
+        open(dst, "w").write(transliterate(extract_function(open(src, errors="replace").read(), name)))
+    else:
+        src, dst = sys.argv[1], sys.argv[2]
+        open(dst, "w").write(transliterate(open(src, errors="replace").read()))

@@ -34,6 +34,12 @@ using namespace glsl_prelude;
 #include "gen/stack.inc"
 }  // namespace ref_stack
 
+namespace ref_primary {  // GetRayDirectionAt of the primary-ray kernel (Intersectors/TraverseBVHStack.glsl:133-138)
+using namespace glm;
+static mat4 u_InverseProjection, u_InverseView;
+#include "gen/primary.inc"
+}  // namespace ref_primary
+
 namespace {
 struct Hit32 { float t, u, v, w; int32_t mesh, tri, entity, iters; };
 struct Attr32 { float nx, ny, nz, u, v, emissivity, alpha; int32_t mesh; };
@@ -103,6 +109,32 @@ int ref_glsl_trace_mt(int format, int kind, const void* nodes, uint64_t n_nodes,
     }
     for (auto& th : pool) th.join();
     return 0;
+}
+
+// Primary rays exactly as main() of Intersectors/TraverseBVHStack.glsl:414-421 forms them: TexCoords = vec2(Pixel) / u_Dims,
+// rD = normalize(GetRayDirectionAt(TexCoords)), rO = u_InverseView[3].xyz.  Matrices column-major; rays: 8 floats each.
+int ref_glsl_primary_rays(const float* inv_view16, const float* inv_proj16, int W, int H, float* rays) {
+    std::memcpy(&ref_primary::u_InverseView[0][0], inv_view16, 64);
+    std::memcpy(&ref_primary::u_InverseProjection[0][0], inv_proj16, 64);
+    const glm::vec2 dims((float)W, (float)H);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const glm::vec2 tex = glm::vec2(glm::ivec2(x, y)) / dims;
+            const glm::vec3 rd = glm::normalize(ref_primary::GetRayDirectionAt(tex));
+            const glm::vec3 ro = glm::vec3(ref_primary::u_InverseView[3]);
+            float* r = rays + 8 * ((size_t)y * W + x);
+            r[0] = ro.x; r[1] = ro.y; r[2] = ro.z; r[3] = 0.0f;
+            r[4] = rd.x; r[5] = rd.y; r[6] = rd.z; r[7] = 1000000.0f;
+        }
+    return 0;
+}
+
+// glm::inverse as RayIntersector::PushEntity applies it (Intersector.h:209).
+void ref_glm_inverse(const float* m16, float* out16) {
+    glm::mat4 m;
+    std::memcpy(&m[0][0], m16, 64);
+    const glm::mat4 inv = glm::inverse(m);
+    std::memcpy(out16, &inv[0][0], 64);
 }
 
 // GetData (TraverseBVHStackless.glsl:375-408) on hit records; texture references all carry Albedo = -1, so Albedo is the

@@ -180,3 +180,21 @@ def test_oracle_vs_compiled_reference_glsl_live(ob, golden_meshes):
                 n += len(r)
     assert n > 200000
 
+
+def test_primary_rays_and_entity_inverse_vs_compiled_reference(ob):
+    """Primary-ray generation against the shader's own GetRayDirectionAt + main() arithmetic (Intersectors/TraverseBVHStack.glsl:
+    133-138, :414-421) and PushEntity's glm::inverse (Intersector.h:209), both compiled from the reference (oracle/_ref)."""
+    if not ob.REFERENCE_ROOT.exists():
+        pytest.skip("/root/reference is not present (GPU box)")
+    from candela_b200 import scenes
+    for pos, look, W, H in (((-18.0, 5.0, 0.7), (10.0, 30.0, -0.4), 320, 180), ((0, 1, 2), (3, -2, 5), 257, 131), ((5, 5, 5), (0, 0, 0), 64, 64)):
+        iv, ip = scenes.camera(pos, look, W, H)
+        assert ob.primary_rays(iv, ip, W, H).tobytes() == ob.ref_primary_rays(iv, ip, W, H).tobytes()
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        m = np.eye(4, dtype=np.float32)
+        m[:3, :3] = rng.normal(size=(3, 3)).astype(np.float32) * np.float32(rng.uniform(0.1, 5))
+        m[:3, 3] = rng.normal(size=3) * 10
+        e = ob.make_entity(m, 0, 1)
+        assert np.asarray(e["inverse"][0]).reshape(4, 4).T.tobytes() == ob.ref_glm_inverse(m).tobytes()
+
