@@ -303,6 +303,7 @@ def ref_lib() -> C.CDLL:
         R.ref_glsl_trace_mt.argtypes = [C.c_int, C.c_int, vp, C.c_uint64, vp, vp, vp, C.c_int32, vp, C.c_uint64, vp, C.c_int]
         R.ref_glsl_primary_rays.argtypes = [vp, vp, C.c_int, C.c_int, vp]
         R.ref_glm_inverse.argtypes = [vp, vp]
+        R.ref_glsl_sample.argtypes = [C.c_int, vp, vp, C.c_float, C.c_uint64, vp]
         R.ref_glsl_get_data.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_uint64, vp]
         R.ref_pack_half2x16.argtypes = [C.c_float, C.c_float]
         R.ref_pack_half2x16.restype = C.c_uint32
@@ -393,4 +394,13 @@ def ref_glm_inverse(model) -> np.ndarray:
     out = np.zeros(16, dtype=np.float32)
     ref_lib().ref_glm_inverse(_p(m), _p(out))
     return out.reshape(4, 4).T.copy()
+
+
+def ref_sample(which: int, normals, xi, roughness: float = 0.0) -> np.ndarray:
+    """The reference's own direction samplers, compiled (Include/Sampling.glsl): 0 CosWeightedHemisphere, 1 SampleGGXVNDF."""
+    n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    x = np.ascontiguousarray(xi, dtype=np.float32).reshape(-1, 2)
+    out = np.zeros_like(n)
+    ref_lib().ref_glsl_sample(which, _p(n), _p(x), roughness, len(n), _p(out))
+    return out
 

@@ -40,6 +40,12 @@ static mat4 u_InverseProjection, u_InverseView;
 #include "gen/primary.inc"
 }  // namespace ref_primary
 
+namespace ref_sampling {  // CosWeightedHemisphere, SampleGGXVNDF (Shaders/Include/Sampling.glsl:1-12, :63-83)
+using namespace glm;
+#include "gen/cos_hemisphere.inc"
+#include "gen/ggx_vndf.inc"
+}  // namespace ref_sampling
+
 namespace {
 struct Hit32 { float t, u, v, w; int32_t mesh, tri, entity, iters; };
 struct Attr32 { float nx, ny, nz, u, v, emissivity, alpha; int32_t mesh; };
@@ -127,6 +133,16 @@ int ref_glsl_primary_rays(const float* inv_view16, const float* inv_proj16, int 
             r[4] = rd.x; r[5] = rd.y; r[6] = rd.z; r[7] = 1000000.0f;
         }
     return 0;
+}
+
+// The reference's direction samplers on n inputs: which = 0 CosWeightedHemisphere(N, xi), 1 SampleGGXVNDF(N, roughness, xi).
+void ref_glsl_sample(int which, const float* normals, const float* xi, float roughness, uint64_t n, float* out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const glm::vec3 N(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+        const glm::vec2 X(xi[2 * i], xi[2 * i + 1]);
+        const glm::vec3 d = which == 0 ? ref_sampling::CosWeightedHemisphere(N, X) : ref_sampling::SampleGGXVNDF(N, roughness, X);
+        out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+    }
 }
 
 // glm::inverse as RayIntersector::PushEntity applies it (Intersector.h:209).
