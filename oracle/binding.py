@@ -39,8 +39,8 @@ def build_library(force: bool = False) -> Path:
     stale = force or not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
     if stale:
         subprocess.run(["make", "-C", str(HERE), "all"], check=True, capture_output=True)
-    if REFERENCE_ROOT.exists() and (force or not REF_LIB_PATH.exists()):
-        subprocess.run(["make", "-C", str(HERE), "ref"], check=True, capture_output=True)
+    if REFERENCE_ROOT.exists():  # make decides whether oracle/_ref is stale (it depends on the shim sources)
+        subprocess.run(["make", "-C", str(HERE), "ref"] + (["-B"] if force else []), check=True, capture_output=True)
     return LIB_PATH
 
 
