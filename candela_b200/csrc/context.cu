@@ -84,6 +84,7 @@ struct cndl_ctx {
     std::vector<cndl_entity> buffered;           // the entity records last uploaded
     int n_hot = 0;
     bool hot_ready = false, hot_entities_ok = false;
+    bool nodes_valid = false, entities_regular = false;  // links / slots / leaf ranges in bounds; every entity names a whole object
     LaunchCounter launches;
     float last_build_ms = 0.0f;
     void* build_arena = nullptr;
@@ -125,13 +126,16 @@ SceneView scene_view(const cndl_ctx* ctx) {
 // record must name an object's whole node range, as PushEntity produces (Intersector.h:210-211).
 int upload_hot_entities(cndl_ctx* ctx) {
     ctx->hot_entities_ok = false;
-    if (!ctx->hot_ready) return CNDL_OK;
+    ctx->entities_regular = false;
+    if (!ctx->nodes_valid) return CNDL_OK;
     std::vector<cndl_entity> e2 = ctx->buffered;
     for (auto& e : e2) {
         auto it = std::lower_bound(ctx->h_objects.begin(), ctx->h_objects.end(), e.node_offset, [](const int2& o, int v) { return o.x < v; });
         if (it == ctx->h_objects.end() || it->x != e.node_offset || it->y != e.node_count) return CNDL_OK;  // irregular: reference-layout kernel
-        e.node_offset = ctx->h_roots[(size_t)(it - ctx->h_objects.begin())];
+        if (ctx->hot_ready) e.node_offset = ctx->h_roots[(size_t)(it - ctx->h_objects.begin())];
     }
+    ctx->entities_regular = true;
+    if (!ctx->hot_ready) return CNDL_OK;
     CK(ctx->ents2.ensure_scratch((e2.size() ? e2.size() : 1) * sizeof(cndl_entity)));
     if (!e2.empty()) CK(cudaMemcpy(ctx->ents2.p, e2.data(), e2.size() * sizeof(cndl_entity), cudaMemcpyHostToDevice));
     ctx->hot_entities_ok = true;
@@ -178,8 +182,8 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
         if (steps < 1 || steps > 4) steps = 2;
         const int park = ctx->knobs[stack ? CNDL_KNOB_STACK_LEAF_THRESHOLD : CNDL_KNOB_LEAF_THRESHOLD], idle = ctx->knobs[CNDL_KNOB_IDLE_THRESHOLD];
         if (stack) {
-            launch_trace_ww_stack(s, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM], park, idle, steps, st,
-                                  ctx->launches);
+            launch_trace_ww_stack(s, kind, d_rays, R, order, d_hits, d_any, scratch, ctx->sm_count, ctx->knobs[CNDL_KNOB_BLOCKS_PER_SM], park, idle, steps,
+                                  ctx->nodes_valid && ctx->entities_regular && !(variant & 8), st, ctx->launches);
         } else if (variant >= 32 && ctx->hot_ready && ctx->hot_entities_ok) {
             HotView hv;
             hv.nodes2 = static_cast<const float4*>(ctx->nodes2.p);
@@ -413,12 +417,23 @@ int cndl_commit(cndl_ctx* ctx, int clear_host) try {
     ctx->committed_tris = ctx->n_tris;
     ctx->committed = true;
     ctx->hot_ready = false;
+    ctx->nodes_valid = false;
+    ctx->h_objects.clear();
+    for (const auto& kv : ctx->objects) ctx->h_objects.push_back(make_int2(kv.second.node_offset, kv.second.node_count));
+    std::sort(ctx->h_objects.begin(), ctx->h_objects.end(), [](const int2& a, const int2& b) { return a.x < b.x; });
+    const int n_obj = (int)ctx->h_objects.size();
+    if (ctx->format == CNDL_STACK) {
+        int invalid = 0;
+        CK(validate_stack_nodes(static_cast<const float4*>(ctx->nodes.p), ctx->h_objects.data(), n_obj, ctx->n_tris, static_cast<int*>(ctx->d_counter.p) + 32,
+                                &invalid, st, ctx->launches));
+        ctx->nodes_valid = invalid == 0;
+        if (ctx->ents_buffered) {
+            const int rc = upload_hot_entities(ctx);
+            if (rc != CNDL_OK) return rc;
+        }
+    }
     if (ctx->format == CNDL_STACKLESS) {
         // derived hot-first node layout for the shared-memory staged kernel (kernels_hot.cu)
-        ctx->h_objects.clear();
-        for (const auto& kv : ctx->objects) ctx->h_objects.push_back(make_int2(kv.second.node_offset, kv.second.node_count));
-        std::sort(ctx->h_objects.begin(), ctx->h_objects.end(), [](const int2& a, const int2& b) { return a.x < b.x; });
-        const int n_obj = (int)ctx->h_objects.size();
         const size_t N = ctx->n_nodes;
         CK(ctx->nodes2.ensure_scratch(N * sizeof(cndl_node)));
         CK(ctx->perm.ensure_scratch(N * sizeof(int)));
@@ -431,6 +446,7 @@ int cndl_commit(cndl_ctx* ctx, int clear_host) try {
                              ctx->n_tris, ctx->knobs[CNDL_KNOB_HOT_NODES], static_cast<float4*>(ctx->nodes2.p), static_cast<int*>(ctx->perm.p),
                              static_cast<int*>(ctx->hot_scratch.p), ctx->h_roots.data(), &ctx->n_hot, &invalid, st, ctx->launches));
         ctx->hot_ready = invalid == 0;  // a buffer with out-of-range links keeps the reference-layout kernel and its range checks
+        ctx->nodes_valid = ctx->hot_ready;
         if (ctx->ents_buffered) {
             const int rc = upload_hot_entities(ctx);
             if (rc != CNDL_OK) return rc;

@@ -29,7 +29,7 @@ void launch_trace_ww(const SceneView& s, int kind, const cndl_ray* rays, size_t 
                      unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, bool validated,
                      bool helper_lanes, cudaStream_t stream, LaunchCounter& lc);
 void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
-                           unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps,
+                           unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, bool validated,
                            cudaStream_t stream, LaunchCounter& lc);
 // Stable partition of the ray indices by direction octant (kernels_raygen.cu): order[0..R) lists the rays of octant 0
 // in their original order, then octant 1, ...  scratch: octant_partition_scratch_ints(R) ints.
@@ -66,6 +66,9 @@ size_t hot_scratch_ints(size_t N, int n_objects);
 cudaError_t derive_hot_layout(const float4* nodes, size_t N, const int2* d_objects, const int2* h_objects, int n_objects, size_t n_tris, int H,
                               float4* nodes2, int* perm, int* scratch, int* h_roots_out, int* h_n_hot, int* h_invalid, cudaStream_t st,
                               LaunchCounter& lc);
+// Stack format: *h_invalid != 0 when a child slot or a leaf range is out of bounds (d_flag: one int of device scratch).
+cudaError_t validate_stack_nodes(const float4* nodes, const int2* h_objects, int n_objects, size_t n_tris, int* d_flag, int* h_invalid, cudaStream_t st,
+                                 LaunchCounter& lc);
 void launch_trace_hot(const SceneView& s, const HotView& hv, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits,
                       float* any_t, unsigned* work_counter, int sm_count, int block_threads, int park_threshold, int idle_threshold, int steps,
                       cudaStream_t stream, LaunchCounter& lc);

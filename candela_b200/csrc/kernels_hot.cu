@@ -143,6 +143,21 @@ __global__ void derive_nodes_kernel(const float4* __restrict__ nodes, int start,
     nodes2[2 * j + 1] = hi;
 }
 
+// Stack format: every inner child's slot and every leaf child's triangle range must lie inside the object / the scene.
+__global__ void validate_stack_kernel(const float4* __restrict__ nodes, int start, int count, int n_tris, int* __restrict__ invalid) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    bool bad = false;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const float4 mn = nodes[4 * (size_t)(start + k) + 2 * side], mx = nodes[4 * (size_t)(start + k) + 2 * side + 1];
+        const int pack = __float_as_int(mn.w), slot = __float_as_int(mx.w);
+        if (pack == -1) bad = bad || slot < 0 || slot >= count;
+        else bad = bad || pack < 0 || (pack >> 4) + (pack & 0xF) > n_tris;
+    }
+    if (bad) atomicExch(invalid, 1);
+}
+
 __global__ void gather_kernel(const int* __restrict__ perm, const int2* __restrict__ objects, int n, int* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = objects[i].y > 0 ? perm[objects[i].x] : -1;
@@ -686,6 +701,20 @@ cudaError_t derive_hot_layout(const float4* nodes, size_t N, const int2* d_objec
     e = cudaMemcpyAsync(h_n_hot, d_n_hot, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_invalid, d_invalid, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_roots_out, d_roots, n_objects * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e;
+}
+
+cudaError_t validate_stack_nodes(const float4* nodes, const int2* h_objects, int n_objects, size_t n_tris, int* d_flag, int* h_invalid, cudaStream_t st,
+                                 LaunchCounter& lc) {
+    cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+    for (int o = 0; o < n_objects; ++o) {
+        if (h_objects[o].y <= 0) continue;
+        validate_stack_kernel<<<(unsigned)((h_objects[o].y + 255) / 256), 256, 0, st>>>(nodes, h_objects[o].x, h_objects[o].y, (int)n_tris, d_flag);
+        lc.n++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_invalid, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     return e;
 }

@@ -323,10 +323,12 @@ __device__ __forceinline__ void next_entity_stack(const SceneView& s, const cndl
     L.state = DONE;
 }
 
-template <bool EXACT>
+// CHECKED = false: slots and leaf ranges were validated at commit and every entity names a whole object, so the pointer
+// range checks of ST:201-205 cannot fire; the stack pointer stays in 0..63 by construction (a push at 63 ends the walk).
+template <bool EXACT, bool CHECKED>
 __device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, int* stack) {
     if (L.state == WALK) {
-        if (L.iters >= 1024 || L.sp >= 64 || L.sp < 0 || L.cur < L.lo || L.cur > L.hi) {  // ST:198-205
+        if (L.iters >= 1024 || (CHECKED && (L.sp >= 64 || L.sp < 0 || L.cur < L.lo || L.cur > L.hi))) {  // ST:198-205
             L.state = DONE;
         } else {
             ++L.iters;
@@ -359,7 +361,7 @@ __device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, in
     }
 }
 
-template <int KIND, int STEPS>
+template <int KIND, int STEPS, bool CHECKED>
 __global__ void __launch_bounds__(128, 8) trace_ww_stack_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R, RayOrder order,
                                                                 cndl_hit* __restrict__ hits, float* __restrict__ any_t,
                                                                 unsigned* __restrict__ work_counter, int park_threshold, int idle_threshold) {
@@ -431,11 +433,11 @@ __global__ void __launch_bounds__(128, 8) trace_ww_stack_kernel(SceneView s, con
                 if (!warp_exact) {
                     do {
 #pragma unroll
-                        for (int step = 0; step < STEPS; ++step) node_step_stack<false>(s, L, stack);
+                        for (int step = 0; step < STEPS; ++step) node_step_stack<false, CHECKED>(s, L, stack);
                     } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
                 } else {
                     do {
-                        node_step_stack<true>(s, L, stack);
+                        node_step_stack<true, CHECKED>(s, L, stack);
                     } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
                 }
             }
@@ -488,16 +490,20 @@ void launch_kind(int kind, int steps, unsigned grid, cudaStream_t stream, const 
 }
 
 template <int KIND>
-void launch_stack_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R, const RayOrder& order,
-                        cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
-    if (steps == 2) trace_ww_stack_kernel<KIND, 2><<<grid, 128, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
-    else trace_ww_stack_kernel<KIND, 1><<<grid, 128, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
+void launch_stack_steps(int steps, bool validated, unsigned grid, cudaStream_t stream, const SceneView& s, const cndl_ray* rays, unsigned R,
+                        const RayOrder& order, cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
+#define CNDL_ST_ARGS s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold
+    if (steps == 2 && validated) trace_ww_stack_kernel<KIND, 2, false><<<grid, 128, 0, stream>>>(CNDL_ST_ARGS);
+    else if (steps == 2) trace_ww_stack_kernel<KIND, 2, true><<<grid, 128, 0, stream>>>(CNDL_ST_ARGS);
+    else if (validated) trace_ww_stack_kernel<KIND, 1, false><<<grid, 128, 0, stream>>>(CNDL_ST_ARGS);
+    else trace_ww_stack_kernel<KIND, 1, true><<<grid, 128, 0, stream>>>(CNDL_ST_ARGS);
+#undef CNDL_ST_ARGS
 }
 
 }  // namespace
 
 void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits, float* any_t,
-                           unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps,
+                           unsigned* work_counter, int sm_count, int blocks_per_sm, int park_threshold, int idle_threshold, int steps, bool validated,
                            cudaStream_t stream, LaunchCounter& lc) {
     if (R == 0) return;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned), stream);
@@ -505,9 +511,9 @@ void launch_trace_ww_stack(const SceneView& s, int kind, const cndl_ray* rays, s
     const unsigned need = (unsigned)((R + 127) / 128);
     if (grid > need) grid = need;
     switch (kind) {
-        case Q_CLOSEST: launch_stack_steps<Q_CLOSEST>(steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
-        case Q_CLOSEST_IGNORE_TRANSPARENT: launch_stack_steps<Q_CLOSEST_IGNORE_TRANSPARENT>(steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
-        default: launch_stack_steps<Q_ANY>(steps, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        case Q_CLOSEST: launch_stack_steps<Q_CLOSEST>(steps, validated, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        case Q_CLOSEST_IGNORE_TRANSPARENT: launch_stack_steps<Q_CLOSEST_IGNORE_TRANSPARENT>(steps, validated, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
+        default: launch_stack_steps<Q_ANY>(steps, validated, grid, stream, s, rays, (unsigned)R, order, hits, any_t, work_counter, park_threshold, idle_threshold); break;
     }
     lc.n++;
 }
