@@ -94,6 +94,42 @@ def cfg_rtao(args, rank, world, local_rank):
                 cpu_mrays_s=round(n / cpu_s / 1e6, 2), cpu_threads=ob.hardware_threads())
 
 
+def cfg_spec_shadow(args, rank, world, local_rank):
+    """The other two ray batches the engine traces: specular reflection rays (SpecularTrace.glsl, closest hit) and shadow rays
+    towards a directional light (any hit), both generated on the GPU from the 1080p primary hits."""
+    if rank != 0:
+        return None
+    W, H = 1920, 1080
+    ri, v, i, m = setup_s260k(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
+    d_prim = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+    d_hits = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+    ri.intersect_primary_device(iv, ip, W, H, d_hits.data_ptr(), d_prim.data_ptr(), stream)
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
+    ob, nodes, tris, ents = oracle_scene(ri, v)
+    out = []
+    for label, kind, kw, any_hit in (("specular_rough0.3_1080p_closest_hit", api.GEN_SPECULAR, dict(roughness=0.3, offset=-1.0, seed=21), False),
+                                     ("specular_mirror_1080p_closest_hit", api.GEN_SPECULAR, dict(roughness=0.0, offset=-1.0, seed=22), False),
+                                     ("shadow_sun_1080p_any_hit", api.GEN_SHADOW, dict(light_dir=(0.3244, 0.8111, 0.4867), light_cone=0.02, tmax=200.0, offset=0.02, seed=23), True)):
+        d_r = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+        n = ri.generate_rays_device(kind, d_prim.data_ptr(), d_hits.data_ptr(), W * H, d_r.data_ptr(), stream=stream, **kw)
+        if any_hit:
+            d_o = torch.empty(n, dtype=torch.float32, device="cuda")
+            ms = timed(lambda: ri.intersect_any_device(d_r.data_ptr(), n, d_o.data_ptr(), stream), reps=args.reps, flush=flush)
+        else:
+            d_o = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+            ms = timed(lambda: ri.intersect_closest_device(d_r.data_ptr(), n, d_o.data_ptr(), 0, stream), reps=args.reps, flush=flush)
+        rays = d_r[:n].cpu().numpy().view(api.RAY_DT).reshape(-1)
+        want, cnt = ob.trace(ob.STACKLESS, ob.ANY if any_hit else ob.CLOSEST, nodes, tris, v, ents, rays, nthreads=ob.hardware_threads())
+        got = d_o.cpu().numpy() if any_hit else d_o.cpu().numpy().view(api.HIT_DT).reshape(-1)
+        b_ray = (cnt["node_iters"] * 32.0 + cnt["tri_tests"] * 64.0) / n
+        out.append(dict(config=label, rays=n, ms=round(ms, 4), mrays_s=round(n / ms / 1e3, 1), bit_identical_to_oracle=bool(got.tobytes() == want.tobytes()),
+                        bytes_per_ray=round(b_ray, 1), roofline_frac=round(n / (ms * 1e-3) * b_ray / (PEAK * 1e9), 4),
+                        node_iters_per_ray=round(cnt["node_iters"] / n, 2), hit_frac=round(float(((got > 0) if any_hit else (got["t"] > 0)).mean()), 4)))
+    return out
+
+
 def cfg_bounce4k(args, rank, world, local_rank):
     W, H, spp, bounces = args.width or 3840, args.height or 2160, 8, 4
     ri, v, i, m = setup_s260k(local_rank)
@@ -247,7 +283,7 @@ def cfg_soup10m(args, rank, world, local_rank):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("configs", nargs="+", choices=["rtao", "bounce4k", "soup10m"])
+    ap.add_argument("configs", nargs="+", choices=["rtao", "spec_shadow", "bounce4k", "soup10m"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
@@ -268,9 +304,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     for c in args.configs:
-        res = {"rtao": cfg_rtao, "bounce4k": cfg_bounce4k, "soup10m": cfg_soup10m}[c](args, rank, world, local_rank)
+        res = {"rtao": cfg_rtao, "spec_shadow": cfg_spec_shadow, "bounce4k": cfg_bounce4k, "soup10m": cfg_soup10m}[c](args, rank, world, local_rank)
         if rank == 0 and res is not None:
-            print(json.dumps(res), flush=True)
+            for line in (res if isinstance(res, list) else [res]):
+                print(json.dumps(line), flush=True)
         if world > 1:
             dist.barrier()
     if world > 1:
