@@ -35,7 +35,7 @@ EXPORTS = [
     "cndl_node_count", "cndl_triangle_count", "cndl_vertex_count", "cndl_get_object", "cndl_commit", "cndl_read_buffers",
     "cndl_device_buffers", "cndl_push_entity", "cndl_push_entity_records", "cndl_buffer_entities", "cndl_entity_count",
     "cndl_intersect_closest", "cndl_intersect_any", "cndl_intersect_closest_device", "cndl_intersect_any_device",
-    "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_generate_bounce_rays_device", "cndl_host_alloc", "cndl_host_free",
+    "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_generate_bounce_rays_device", "cndl_host_alloc", "cndl_host_alloc_write_combined", "cndl_host_free",
     "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device", "cndl_generate_rays_device", "cndl_collide_boxes", "cndl_collide_boxes_device",
     "cndl_model_load_obj", "cndl_model_load_gltf", "cndl_model_load", "cndl_model_free", "cndl_model_vertex_count", "cndl_model_index_count", "cndl_model_mesh_count", "cndl_model_vertices",
     "cndl_model_indices", "cndl_model_mesh_ids", "cndl_model_mesh_name", "cndl_add_model", "cndl_pack_half2x16", "cndl_save", "cndl_load",
@@ -128,6 +128,8 @@ def load_library() -> C.CDLL:
     L.cndl_load.argtypes = [vp, C.c_char_p]
     L.cndl_host_alloc.argtypes = [sz]
     L.cndl_host_alloc.restype = vp
+    L.cndl_host_alloc_write_combined.argtypes = [sz]
+    L.cndl_host_alloc_write_combined.restype = vp
     L.cndl_host_free.argtypes = [vp]
     L.cndl_host_free.restype = None
     L.cndl_set_traversal_mode.argtypes = [vp, C.c_int, C.c_int]
@@ -193,11 +195,11 @@ load_obj = load_model
 class PinnedBuffer:
     """cndl_host_alloc()'d memory viewed as a numpy array (for ray / hit batches)."""
 
-    def __init__(self, count: int, dtype):
+    def __init__(self, count: int, dtype, write_combined: bool = False):
         self._lib = load_library()
         self.dtype = np.dtype(dtype)
         self.nbytes = max(1, count * self.dtype.itemsize)
-        self.ptr = self._lib.cndl_host_alloc(self.nbytes)
+        self.ptr = (self._lib.cndl_host_alloc_write_combined if write_combined else self._lib.cndl_host_alloc)(self.nbytes)
         if not self.ptr:
             raise MemoryError("cndl_host_alloc failed")
         buf = (C.c_char * self.nbytes).from_address(self.ptr)

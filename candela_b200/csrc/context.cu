@@ -850,6 +850,15 @@ void* cndl_host_alloc(size_t bytes) {
     return p;
 }
 
+// Upload-only buffers (ray batches): write-combined pinned memory is not snooped by the CPU caches, which some hosts
+// turn into a higher host-to-device rate (no difference on the B200 boxes measured); reading it back on the CPU is slow,
+// so never use it for results.
+void* cndl_host_alloc_write_combined(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocWriteCombined) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
 void cndl_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 }  // extern "C"

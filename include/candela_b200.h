@@ -233,6 +233,7 @@ int cndl_load(cndl_ctx* ctx, const char* path);
 
 /* Pinned host memory for ray / hit batches. */
 void* cndl_host_alloc(size_t bytes);
+void* cndl_host_alloc_write_combined(size_t bytes);  /* upload-only (rays): the CPU must not read it back */
 void cndl_host_free(void* p);
 
 /* Traversal tuning (never changes results): mode 0 = one thread per ray, 1 = persistent warps with
