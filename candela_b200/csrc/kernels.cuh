@@ -8,6 +8,15 @@ enum QueryKind { Q_CLOSEST = 0, Q_CLOSEST_IGNORE_TRANSPARENT = 1, Q_ANY = 2 };
 
 struct LaunchCounter { unsigned long long n = 0; };
 
+// Function attributes (shared-memory carve-out, dynamic shared memory size) are per device: launchers keep one slot per
+// device so that contexts on several GPUs in one process each configure their own copy of a kernel.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d >= 0 && d < kMaxDevices ? d : 0;
+}
+
 // Derives tri48 from the reference-layout triangle and vertex buffers (commit time).
 void launch_make_tri48(const int4* tris, const float4* verts /* 2 float4 per vertex */, size_t T, float4* tri48,
                        cudaStream_t stream, LaunchCounter& lc);

@@ -595,10 +595,11 @@ void launch_pair_steps(int steps, unsigned grid, cudaStream_t stream, const Scen
 #define CNDL_PAIR_LAUNCH(STEPS)                                                                                  \
     {                                                                                                            \
         auto k = trace_pair_stackless_kernel<KIND, MINB, STEPS>;                                                 \
-        static bool configured = false;                                                                          \
-        if (!configured) {                                                                                       \
+        static bool configured[kMaxDevices] = {};                                                                          \
+        const int dev_slot = current_device_slot();                                                                          \
+        if (!configured[dev_slot]) {                                                                                       \
             cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0);                          \
-            configured = true;                                                                                   \
+            configured[dev_slot] = true;                                                                                   \
         }                                                                                                        \
         k<<<grid, 128, 0, stream>>>(s, hv.nodes2, hv.ents2, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); \
     }
@@ -624,14 +625,15 @@ template <int KIND, int BLOCK, int STEPS>
 void launch_hot_one(unsigned grid, size_t smem, cudaStream_t stream, const SceneView& s, const HotView& hv, const cndl_ray* rays, unsigned R,
                     const RayOrder& order, cndl_hit* hits, float* any_t, unsigned* work_counter, int park_threshold, int idle_threshold) {
     auto k = trace_hot_stackless_kernel<KIND, BLOCK, STEPS>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[kMaxDevices] = {};
+    const int dev_slot = current_device_slot();
+    if (smem > configured[dev_slot] || (smem == 0 && configured[dev_slot] == 0)) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         // everything the staged nodes do not need stays L1: carve out just enough for the resident CTAs
         const size_t per_sm = smem * (1024 / BLOCK) + 1024 * (1024 / BLOCK);
         const size_t pct = (per_sm * 100 + 228 * 1024 - 1) / (228 * 1024);
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)(pct > 100 ? 100 : pct));
-        configured = smem;
+        configured[dev_slot] = smem ? smem : 1;
     }
     k<<<grid, BLOCK, smem, stream>>>(s, hv.nodes2, hv.ents2, (int)(smem / 32), rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold);
 }

@@ -463,10 +463,11 @@ void launch_steps(int steps, unsigned grid, cudaStream_t stream, const SceneView
 #define CNDL_WW_LAUNCH(STEPS)                                                                                     \
     {                                                                                                             \
         auto k = trace_ww_stackless_kernel<KIND, MINB, STEPS, CHECKED, HELP>;                                     \
-        static bool configured = false;                                                                           \
-        if (!configured) { /* no shared memory is used: give the whole 256 KB array to L1 */                      \
+        static bool configured[kMaxDevices] = {};                                                                           \
+        const int dev_slot = current_device_slot();                                                                           \
+        if (!configured[dev_slot]) { /* no shared memory is used: give the whole 256 KB array to L1 */                      \
             cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, HELP ? 20 : 0);               \
-            configured = true;                                                                                    \
+            configured[dev_slot] = true;                                                                                    \
         }                                                                                                         \
         k<<<grid, 128, 0, stream>>>(s, rays, R, order, hits, any_t, work_counter, park_threshold, idle_threshold); \
     }

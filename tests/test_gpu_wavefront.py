@@ -269,3 +269,31 @@ def test_full_size_properties_rtao(cb, s260k):
     ri.intersect_any_device(d_long.data_ptr(), n, t2.data_ptr(), stream)
     torch.cuda.synchronize()
     assert bool(((t1 > 0) <= (t2 > 0)).all())
+
+
+def test_two_devices_in_one_process(cb, ob):
+    """One context per device, both in this process: kernel attributes (carve-out, dynamic shared memory) are configured per device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from candela_b200 import scenes
+    from helpers import rays_in_box
+    P, F = scenes.load_dragon()
+    V = cb.make_vertices(P)
+    rays = rays_in_box(P.min(0), P.max(0), 150000, 44)
+    outs = []
+    for dev in (0, 1):
+        ri = cb.RayIntersector(cb.STACKLESS, device=dev)
+        ri.AddObject(2, V, F.ravel(), np.zeros(len(F), np.int32))
+        ri.BufferData()
+        ri.PushEntity(2)
+        ri.BufferEntities()
+        res = [ri.IntersectRays(rays).tobytes()]
+        for variant in (34, 42):          # staged (dynamic shared memory) and paired kernels on this device too
+            ri.set_tuning(3, variant)
+            res.append(ri.IntersectRays(rays).tobytes())
+        assert res[0] == res[1] == res[2]
+        outs.append(res[0])
+        ri.close()
+    assert outs[0] == outs[1]
+
