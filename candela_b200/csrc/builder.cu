@@ -31,6 +31,9 @@ constexpr unsigned kMaxLeaf = 2;               // :50
 constexpr float kInfCost = 1e29f;              // :56
 constexpr unsigned kBigNode = 2048;            // ranges longer than this get a 1024-thread block
 constexpr unsigned kTinyNode = 64;             // ranges up to this get one warp
+constexpr unsigned kSplitNodeDefault = 16384;  // ranges longer than this are split across CTAs (split_* kernels)
+constexpr int kSplitBlock = 256, kSplitItems = 8, kSplitChunk = kSplitBlock * kSplitItems;  // one CTA of a split node covers 2048 references
+constexpr int kBinInts = 3 * kBins + 18 * kBins;  // count[3][64], mn[3][3][64], mx[3][3][64] as ordered keys
 
 // glm 0.9.8.5 min/max (func_common.inl:15-28); argument order matters for +0/-0 ties
 __device__ __forceinline__ float gmin(float x, float y) { return x < y ? x : y; }
@@ -217,6 +220,49 @@ struct LevelArgs {
     unsigned char* nflip;  // per node: children exchanged at flatten time
 };
 
+// Child `side` of the node at position k of the active list: box (zero signs resolved), range, and — for a range of
+// <= 2 references — the leaf's triangles (:559-572,:612-625).  box_keys / zero_first: 6 entries (min xyz, max xyz).
+__device__ __forceinline__ void create_child(const LevelArgs& g, int k, int side, unsigned start, unsigned len, unsigned mid, const int* box_keys,
+                                             const int* zero_first, const int* refs) {
+    const BuildArrays& a = g.a;
+    const int child = g.child_base + 2 * k;
+    float bx[6];
+    for (int c = 0; c < 6; ++c) {
+        bx[c] = key2f(box_keys[c]);
+        if (bx[c] == 0.0f && zero_first[c] != 0x7FFFFFFF) {
+            const int r = refs[zero_first[c]];
+            const float4 v = c < 3 ? a.tmin[r] : a.tmax[r];
+            const int cc = c % 3;
+            bx[c] = cc == 0 ? v.x : (cc == 1 ? v.y : v.z);
+        }
+    }
+    const unsigned cstart = side == 0 ? start : mid;
+    const unsigned clen = side == 0 ? mid - start : start + len - mid;
+    a.nmin[child + side] = make_float4(bx[0], bx[1], bx[2], 0.0f);
+    a.nmax[child + side] = make_float4(bx[3], bx[4], bx[5], 0.0f);
+    a.nstart[child + side] = cstart;
+    a.nlen[child + side] = clen;
+    a.nchild[child + side] = -1;
+    g.nflip[child + side] = 0;
+    if (clen <= kMaxLeaf) {
+        // leaf (:456-472): SortedTriangleReferences receives ranges right-first, so this range lands at T-(s+len)
+        const unsigned at = a.T - (cstart + clen);
+        for (unsigned j = 0; j < clen; ++j) {
+            const int r = refs[cstart + j];
+            a.tris_out[at + j] = make_int4((int)a.indices[3 * (size_t)r], (int)a.indices[3 * (size_t)r + 1], (int)a.indices[3 * (size_t)r + 2],
+                                           a.mesh_ids ? a.mesh_ids[r] : 0);  // GenerateTriangles, :630-650
+        }
+    }
+}
+
+__device__ __forceinline__ void finish_parent(const LevelArgs& g, int k, int id, unsigned start, unsigned len) {
+    g.a.nchild[id] = g.child_base + 2 * k;
+    unsigned char flip = 0;
+    if (g.stackless && g.swap_policy == CNDL_SWAP_HASHED)
+        flip = (unsigned char)(mix64(g.swap_seed ^ mix64(((unsigned long long)start << 32) | len)) & 1ull);
+    g.nflip[id] = flip;
+}
+
 // One block owns one node for one level: split search, partition, child boxes, leaf emission.
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g) {
@@ -379,67 +425,395 @@ __global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g) {
     __syncthreads();
 
     // ---- create the two children (:559-572,:612-625) ----
-    const int child = g.child_base + 2 * k;
-    if (tid < 2) {
-        const int side = tid;
-        float bx[6];
-        for (int c = 0; c < 6; ++c) {
-            bx[c] = key2f(s_box[side][c]);
-            if (bx[c] == 0.0f && s_zero_first[side][c] != 0x7FFFFFFF) {
-                const int r = a.refs[s_zero_first[side][c]];
-                const float4 v = c < 3 ? a.tmin[r] : a.tmax[r];
-                const int cc = c % 3;
-                bx[c] = cc == 0 ? v.x : (cc == 1 ? v.y : v.z);
-            }
-        }
-        const unsigned cstart = side == 0 ? start : mid;
-        const unsigned clen = side == 0 ? mid - start : start + len - mid;
-        a.nmin[child + side] = make_float4(bx[0], bx[1], bx[2], 0.0f);
-        a.nmax[child + side] = make_float4(bx[3], bx[4], bx[5], 0.0f);
-        a.nstart[child + side] = cstart;
-        a.nlen[child + side] = clen;
-        a.nchild[child + side] = -1;
-        g.nflip[child + side] = 0;
-        if (clen <= kMaxLeaf) {
-            // leaf (:456-472): SortedTriangleReferences receives ranges right-first, so this range lands at T-(s+len)
-            const unsigned at = a.T - (cstart + clen);
-            for (unsigned j = 0; j < clen; ++j) {
-                const int r = a.refs[cstart + j];
-                a.tris_out[at + j] = make_int4((int)a.indices[3 * (size_t)r], (int)a.indices[3 * (size_t)r + 1], (int)a.indices[3 * (size_t)r + 2],
-                                               a.mesh_ids ? a.mesh_ids[r] : 0);  // GenerateTriangles, :630-650
-            }
-        }
+    if (tid < 2) create_child(g, k, tid, start, len, mid, s_box[tid], s_zero_first[tid], a.refs);
+    if (tid == 0) finish_parent(g, k, id, start, len);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same level step for ranges longer than the split threshold, spread over one CTA per 2048 references.
+// One CTA would walk a 262k-reference root three times alone (~1 ms); every result below is a pure function of
+// the range, so the passes can be cut anywhere:
+//   split_bin     bins its chunk in shared memory and merges into the node's global bins (min / max / + only);
+//                 the last CTA of a node runs the split search on the merged bins;
+//   split_count   writes each reference's side and counts the left ones per chunk; the last CTA scans the counts;
+//   split_rank    gives every left reference its rank r in the range: it lands at start + r (Lomuto keeps the left
+//                 references in order);
+//   split_gather  fills the positions from start + nL on.  The sequential loop leaves position P alone when its
+//                 reference is a right one; when it is the k-th left one, P receives whatever position start + k held
+//                 when the loop got to P, which is again either an untouched right reference or the filling of an
+//                 earlier left one's place: follow q -> start + rank(q) until a right reference turns up.  The chains of
+//                 different P are disjoint (rank is injective), but one chain can be long: inside a run of left references
+//                 that follows the c-th right one every hop is q -> q - c, so the walk takes a whole run per iteration
+//                 (rpos gives the run's first position) and a chain costs at most O(sqrt(len)) dependent loads;
+//   split_finish  copies the new order back, reduces the two child boxes and the last CTA creates the children.
+struct SplitArgs {
+    LevelArgs g;         // klist = positions of this level's split nodes in the active list
+    int n_split;
+    int* chunk_base;     // n_split + 1: first chunk of every split node, total
+    int* bins;           // n_split x kBinInts
+    int* done;           // n_split x 3 arrival counters
+    int* split;          // n_split x 4: axis, border bits, nL
+    int* boxes;          // n_split x 24: box keys [2][6], first zero position [2][6]
+    int* chunk_l;        // per chunk: left count, replaced by its exclusive prefix inside the node
+    int* rankflag;       // per position: rank of a left reference, -1 for a right one
+    int* rpos;           // start + j: position (relative to start) of the range's j-th right reference
+    int* alt;            // per position: the partitioned order
+};
+
+struct SplitWhere { int h, chunk, n_chunks, id, k; unsigned start, len; };
+
+__device__ __forceinline__ bool split_locate(const SplitArgs& s, SplitWhere& w) {
+    const int total = s.chunk_base[s.n_split];
+    if ((int)blockIdx.x >= total) return false;
+    int lo = 0, hi = s.n_split - 1;  // last h with chunk_base[h] <= blockIdx.x
+    while (lo < hi) {
+        const int m = (lo + hi + 1) >> 1;
+        if (s.chunk_base[m] <= (int)blockIdx.x) lo = m; else hi = m - 1;
     }
-    if (tid == 0) {
-        a.nchild[id] = child;
-        unsigned char flip = 0;
-        if (g.stackless && g.swap_policy == CNDL_SWAP_HASHED)
-            flip = (unsigned char)(mix64(g.swap_seed ^ mix64(((unsigned long long)start << 32) | len)) & 1ull);
-        g.nflip[id] = flip;
+    w.h = lo;
+    w.chunk = (int)blockIdx.x - s.chunk_base[lo];
+    w.n_chunks = s.chunk_base[lo + 1] - s.chunk_base[lo];
+    w.k = s.g.klist[lo];
+    w.id = s.g.active[w.k];
+    w.start = s.g.a.nstart[w.id];
+    w.len = s.g.a.nlen[w.id];
+    return true;
+}
+
+// true in the CTA that arrives last at counter `which` of node h; everything written before by the others is visible to it
+__device__ __forceinline__ bool split_arrive_last(const SplitArgs& s, const SplitWhere& w, int which, int* s_flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *s_flag = atomicAdd(&s.done[3 * w.h + which], 1) == w.n_chunks - 1;
+    __syncthreads();
+    const bool last = *s_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+__global__ void __launch_bounds__(1024) split_prep_kernel(SplitArgs s) {
+    __shared__ int s_warp[1024 / 32 + 1];
+    const int tid = threadIdx.x;
+    int carry = 0;
+    for (int base = 0; base < s.n_split; base += 1024) {
+        const int h = base + tid;
+        int nch = 0;
+        if (h < s.n_split) nch = (int)((s.g.a.nlen[s.g.active[s.g.klist[h]]] + kSplitChunk - 1) / kSplitChunk);
+        int total;
+        const int ex = block_exclusive_scan<1024>(nch, s_warp, total);
+        if (h < s.n_split) s.chunk_base[h] = carry + ex;
+        carry += total;
+    }
+    if (tid == 0) s.chunk_base[s.n_split] = carry;
+    for (int i = tid; i < s.n_split * kBinInts; i += 1024) {
+        const int j = i % kBinInts;
+        s.bins[i] = j < 3 * kBins ? 0 : (j < 12 * kBins ? f2key(kSentinelMax) : f2key(kSentinelMin));
+    }
+    for (int i = tid; i < s.n_split * 3; i += 1024) s.done[i] = 0;
+    for (int i = tid; i < s.n_split * 24; i += 1024) {
+        const int j = i % 24;
+        s.boxes[i] = j >= 12 ? 0x7FFFFFFF : (j % 6 < 3 ? f2key(kSentinelMax) : f2key(kSentinelMin));
     }
 }
 
-// flags for the nodes of one level, one run of n per size class: [0,n) big, [n,2n) small, [2n,3n) tiny
-__global__ void classify_kernel(const unsigned* nlen, int base, int n, int* flags) {
+__global__ void __launch_bounds__(kSplitBlock) split_bin_kernel(SplitArgs s) {
+    __shared__ int s_count[3][kBins];
+    __shared__ int s_mn[3][3][kBins], s_mx[3][3][kBins];
+    __shared__ float s_best_cost, s_border;
+    __shared__ int s_axis, s_last;
+    SplitWhere w;
+    if (!split_locate(s, w)) return;
+    const BuildArrays& a = s.g.a;
+    const int tid = threadIdx.x;
+    const float4 bmn = a.nmin[w.id], bmx = a.nmax[w.id];
+    const float nmn[3] = {bmn.x, bmn.y, bmn.z}, nmx[3] = {bmx.x, bmx.y, bmx.z};
+    for (int b = tid; b < 3 * kBins; b += kSplitBlock) (&s_count[0][0])[b] = 0;
+    for (int b = tid; b < 9 * kBins; b += kSplitBlock) { (&s_mn[0][0][0])[b] = f2key(kSentinelMax); (&s_mx[0][0][0])[b] = f2key(kSentinelMin); }
+    __syncthreads();
+    float scale[3], extent[3];
+    bool axis_on[3];
+    for (int ax = 0; ax < 3; ++ax) {
+        axis_on[ax] = !(nmn[ax] == nmx[ax]);                 // :285
+        extent[ax] = fsub(nmx[ax], nmn[ax]);
+        scale[ax] = fdiv((float)kBins, extent[ax]);          // :295
+    }
+    for (int j = 0; j < kSplitItems; ++j) {
+        const unsigned i = (unsigned)w.chunk * kSplitChunk + j * kSplitBlock + tid;
+        const bool valid = i < w.len;
+        const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (valid) {
+            const int r = a.refs[w.start + i];
+            const float4 tm = a.tmin[r], tx = a.tmax[r];
+            const float cz = a.tcz[r];
+            const int kmn[3] = {f2key(tm.x), f2key(tm.y), f2key(tm.z)}, kmx[3] = {f2key(tx.x), f2key(tx.y), f2key(tx.z)};
+            const float cen[3] = {tm.w, tx.w, cz};
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                if (!axis_on[ax]) continue;
+                int b = __float2int_rz(fmul(fsub(cen[ax], nmn[ax]), scale[ax]));  // :302
+                b = b > kBins - 1 ? kBins - 1 : (b < 0 ? 0 : b);
+                if (__all_sync(vmask, b == __shfl_sync(vmask, b, __ffs(vmask) - 1))) {
+                    int rmn[3], rmx[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { rmn[c] = __reduce_min_sync(vmask, kmn[c]); rmx[c] = __reduce_max_sync(vmask, kmx[c]); }
+                    if ((int)(threadIdx.x & 31) == __ffs(vmask) - 1) {
+                        atomicAdd(&s_count[ax][b], __popc(vmask));
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { atomicMin(&s_mn[ax][c][b], rmn[c]); atomicMax(&s_mx[ax][c][b], rmx[c]); }
+                    }
+                } else {
+                    atomicAdd(&s_count[ax][b], 1);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { atomicMin(&s_mn[ax][c][b], kmn[c]); atomicMax(&s_mx[ax][c][b], kmx[c]); }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    int* gb = s.bins + (size_t)w.h * kBinInts;
+    for (int b = tid; b < 3 * kBins; b += kSplitBlock) {
+        const int n = (&s_count[0][0])[b];
+        if (n) atomicAdd(gb + b, n);
+    }
+    for (int b = tid; b < 9 * kBins; b += kSplitBlock) {
+        const int mn = (&s_mn[0][0][0])[b], mx = (&s_mx[0][0][0])[b];
+        if (mn != f2key(kSentinelMax)) atomicMin(gb + 3 * kBins + b, mn);
+        if (mx != f2key(kSentinelMin)) atomicMax(gb + 12 * kBins + b, mx);
+    }
+    if (!split_arrive_last(s, w, 0, &s_last)) return;
+    for (int b = tid; b < 3 * kBins; b += kSplitBlock) (&s_count[0][0])[b] = __ldcg(gb + b);
+    for (int b = tid; b < 9 * kBins; b += kSplitBlock) {
+        (&s_mn[0][0][0])[b] = __ldcg(gb + 3 * kBins + b);
+        (&s_mx[0][0][0])[b] = __ldcg(gb + 12 * kBins + b);
+    }
+    if (tid == 0) { s_best_cost = kInfCost; s_axis = 0; s_border = nmn[0]; }
+    __syncthreads();
+    if (tid < 32) {
+        for (int ax = 0; ax < 3; ++ax) {
+            if (!axis_on[ax]) continue;
+            warp_sah_eval(s_count[ax], s_mn[ax], s_mx[ax], ax, nmn[ax], extent[ax], &s_best_cost, &s_axis, &s_border);
+            __syncwarp();
+        }
+        if (tid == 0) {
+            s.split[4 * w.h] = s_axis;
+            s.split[4 * w.h + 1] = __float_as_int(s_border);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSplitBlock) split_count_kernel(SplitArgs s) {
+    __shared__ int s_warp[kSplitBlock / 32 + 1];
+    __shared__ int s_last;
+    SplitWhere w;
+    if (!split_locate(s, w)) return;
+    const BuildArrays& a = s.g.a;
+    const int tid = threadIdx.x;
+    const int axis = s.split[4 * w.h];
+    const float border = __int_as_float(s.split[4 * w.h + 1]);
+    int cnt = 0;
+    for (int j = 0; j < kSplitItems; ++j) {
+        const unsigned i = (unsigned)w.chunk * kSplitChunk + j * kSplitBlock + tid;
+        if (i < w.len) {
+            const bool f = centroid_of(a, a.refs[w.start + i], axis) < border;  // :534
+            s.rankflag[w.start + i] = f ? 0 : -1;
+            cnt += f ? 1 : 0;
+        }
+    }
+    int total;
+    block_exclusive_scan<kSplitBlock>(cnt, s_warp, total);
+    int* cl = s.chunk_l + s.chunk_base[w.h];
+    if (tid == 0) cl[w.chunk] = total;
+    if (!split_arrive_last(s, w, 1, &s_last)) return;
+    int carry = 0;
+    for (int base = 0; base < w.n_chunks; base += kSplitBlock) {
+        const int c = base + tid;
+        const int v = c < w.n_chunks ? __ldcg(cl + c) : 0;
+        int tot;
+        const int ex = block_exclusive_scan<kSplitBlock>(v, s_warp, tot);
+        if (c < w.n_chunks) cl[c] = carry + ex;
+        carry += tot;
+    }
+    if (tid == 0) s.split[4 * w.h + 2] = carry;
+}
+
+__global__ void __launch_bounds__(kSplitBlock) split_rank_kernel(SplitArgs s) {
+    __shared__ int s_warp[kSplitBlock / 32 + 1];
+    SplitWhere w;
+    if (!split_locate(s, w)) return;
+    const BuildArrays& a = s.g.a;
+    const int tid = threadIdx.x;
+    const unsigned i0 = (unsigned)w.chunk * kSplitChunk + (unsigned)tid * kSplitItems;  // this thread's kSplitItems consecutive positions
+    bool fl[kSplitItems];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kSplitItems; ++j) {
+        fl[j] = i0 + j < w.len && s.rankflag[w.start + i0 + j] >= 0;
+        cnt += fl[j] ? 1 : 0;
+    }
+    int total;
+    int rank = s.chunk_l[s.chunk_base[w.h] + w.chunk] + block_exclusive_scan<kSplitBlock>(cnt, s_warp, total);
+#pragma unroll
+    for (int j = 0; j < kSplitItems; ++j) {
+        if (fl[j]) {
+            s.rankflag[w.start + i0 + j] = rank;
+            s.alt[w.start + rank] = a.refs[w.start + i0 + j];
+            ++rank;
+        } else if (i0 + j < w.len) {
+            s.rpos[w.start + (i0 + j - (unsigned)rank)] = (int)(i0 + j);  // i0 + j - rank right references precede this one
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSplitBlock) split_gather_kernel(SplitArgs s) {
+    SplitWhere w;
+    if (!split_locate(s, w)) return;
+    const BuildArrays& a = s.g.a;
+    const unsigned nL = (unsigned)s.split[4 * w.h + 2];
+    for (int j = 0; j < kSplitItems; ++j) {
+        const unsigned i = (unsigned)w.chunk * kSplitChunk + j * kSplitBlock + threadIdx.x;
+        if (i < w.len && i >= nL) {
+            unsigned p = i;  // relative to start
+            for (int rf = s.rankflag[w.start + p]; rf >= 0; rf = s.rankflag[w.start + p]) {
+                const unsigned c = p - (unsigned)rf;  // right references before p: >= 1 on a chain that starts at or after nL
+                if (c == 0) break;
+                const unsigned run0 = (unsigned)s.rpos[w.start + c - 1] + 1;  // first position of the run of left references around p
+                p -= (p - run0) / c * c;  // the hops that stay inside the run (every position of the run has the same c) ...
+                p -= c;                   // ... and the one that leaves it
+            }
+            s.alt[w.start + i] = a.refs[w.start + p];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSplitBlock) split_finish_kernel(SplitArgs s) {
+    __shared__ int s_box[2][6], s_zero_first[2][6];
+    __shared__ int s_last;
+    SplitWhere w;
+    if (!split_locate(s, w)) return;
+    const BuildArrays& a = s.g.a;
+    const int tid = threadIdx.x;
+    const unsigned start = w.start, len = w.len;
+    unsigned mid = start + (unsigned)s.split[4 * w.h + 2];
+    if (mid == start || mid == start + len) mid = start + len / 2;  // split failure (:553-556)
+    if (tid < 12) {
+        const int c = tid % 6;
+        s_box[tid / 6][c] = c < 3 ? f2key(kSentinelMax) : f2key(kSentinelMin);
+        s_zero_first[tid / 6][c] = 0x7FFFFFFF;
+    }
+    __syncthreads();
+    {
+        float lmn[3] = {kSentinelMax, kSentinelMax, kSentinelMax}, lmx[3] = {kSentinelMin, kSentinelMin, kSentinelMin};
+        float rmn[3] = {kSentinelMax, kSentinelMax, kSentinelMax}, rmx[3] = {kSentinelMin, kSentinelMin, kSentinelMin};
+        bool sawl = false, sawr = false;
+        for (int j = 0; j < kSplitItems; ++j) {
+            const unsigned i = (unsigned)w.chunk * kSplitChunk + j * kSplitBlock + tid;
+            if (i >= len) continue;
+            const unsigned pos = start + i;
+            const int r = s.alt[pos];
+            a.refs[pos] = r;
+            const float4 tm = a.tmin[r], tx = a.tmax[r];
+            const float vmn[3] = {tm.x, tm.y, tm.z}, vmx[3] = {tx.x, tx.y, tx.z};
+            const int side = pos < mid ? 0 : 1;
+            for (int c = 0; c < 3; ++c) {
+                if (side == 0) { lmn[c] = fminf(lmn[c], vmn[c]); lmx[c] = fmaxf(lmx[c], vmx[c]); }
+                else { rmn[c] = fminf(rmn[c], vmn[c]); rmx[c] = fmaxf(rmx[c], vmx[c]); }
+                if (vmn[c] == 0.0f) atomicMin(&s_zero_first[side][c], (int)pos);
+                if (vmx[c] == 0.0f) atomicMin(&s_zero_first[side][3 + c], (int)pos);
+            }
+            if (side == 0) sawl = true; else sawr = true;
+        }
+        for (int c = 0; c < 3; ++c) {
+            if (sawl) { atomicMin(&s_box[0][c], f2key(lmn[c] == 0.0f ? 0.0f : lmn[c])); atomicMax(&s_box[0][3 + c], f2key(lmx[c] == 0.0f ? 0.0f : lmx[c])); }
+            if (sawr) { atomicMin(&s_box[1][c], f2key(rmn[c] == 0.0f ? 0.0f : rmn[c])); atomicMax(&s_box[1][3 + c], f2key(rmx[c] == 0.0f ? 0.0f : rmx[c])); }
+        }
+    }
+    __syncthreads();
+    int* gb = s.boxes + 24 * (size_t)w.h;
+    if (tid < 12) {
+        const int side = tid / 6, c = tid % 6;
+        if (c < 3) atomicMin(gb + tid, s_box[side][c]); else atomicMax(gb + tid, s_box[side][c]);
+        if (s_zero_first[side][c] != 0x7FFFFFFF) atomicMin(gb + 12 + tid, s_zero_first[side][c]);
+    }
+    if (!split_arrive_last(s, w, 2, &s_last)) return;
+    if (tid < 12) {
+        s_box[tid / 6][tid % 6] = __ldcg(gb + tid);
+        s_zero_first[tid / 6][tid % 6] = __ldcg(gb + 12 + tid);
+    }
+    __syncthreads();
+    // the children read the partitioned order from `alt`: complete since the previous launch, whereas other CTAs' copies
+    // into refs are ordered only by the arrival counter
+    if (tid < 2) create_child(s.g, w.k, tid, start, len, mid, s_box[tid], s_zero_first[tid], s.alt);
+    if (tid == 0) finish_parent(s.g, w.k, w.id, start, len);
+}
+
+// flags for the nodes of one level, one run of n per size class: [0,n) split, [n,2n) big, [2n,3n) small, [3n,4n) tiny
+__global__ void classify_kernel(const unsigned* nlen, int base, int n, unsigned split_node, int* flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned len = nlen[base + i];
-    flags[i] = len > kBigNode ? 1 : 0;
-    flags[n + i] = (len > kTinyNode && len <= kBigNode) ? 1 : 0;
-    flags[2 * n + i] = (len > kMaxLeaf && len <= kTinyNode) ? 1 : 0;
+    const bool split = len > split_node;
+    flags[i] = split ? 1 : 0;
+    flags[n + i] = (!split && len > kBigNode) ? 1 : 0;
+    flags[2 * n + i] = (!split && len > kTinyNode && len <= kBigNode) ? 1 : 0;
+    flags[3 * n + i] = (!split && len > kMaxLeaf && len <= kTinyNode) ? 1 : 0;
 }
 
 // offsets = exclusive scan of flags.  Writes the ordered active list and, per size class, the list of
 // positions in it.
-__global__ void compact_kernel(const int* flags, const int* offsets, int base, int n, int* active, int* klist_big, int* klist_small,
-                               int* klist_tiny) {
+__global__ void compact_kernel(const int* flags, const int* offsets, const int* total, int base, int n, int* active, int* klist_split,
+                               int* klist_big, int* klist_small, int* klist_tiny, int* class_counts /* mapped host memory */) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int off_big = offsets[i], off_small = offsets[n + i] - offsets[n], off_tiny = offsets[2 * n + i] - offsets[2 * n];
-    const int k = off_big + off_small + off_tiny;
-    if (flags[i]) { active[k] = base + i; klist_big[off_big] = k; }
-    if (flags[n + i]) { active[k] = base + i; klist_small[off_small] = k; }
-    if (flags[2 * n + i]) { active[k] = base + i; klist_tiny[off_tiny] = k; }
+    if (i == 0) {
+        class_counts[0] = offsets[n];
+        class_counts[1] = offsets[2 * n] - offsets[n];
+        class_counts[2] = offsets[3 * n] - offsets[2 * n];
+        class_counts[3] = *total - offsets[3 * n];
+    }
+    const int off_split = offsets[i], off_big = offsets[n + i] - offsets[n], off_small = offsets[2 * n + i] - offsets[2 * n],
+              off_tiny = offsets[3 * n + i] - offsets[3 * n];
+    const int k = off_split + off_big + off_small + off_tiny;
+    if (flags[i]) { active[k] = base + i; klist_split[off_split] = k; }
+    if (flags[n + i]) { active[k] = base + i; klist_big[off_big] = k; }
+    if (flags[2 * n + i]) { active[k] = base + i; klist_small[off_small] = k; }
+    if (flags[3 * n + i]) { active[k] = base + i; klist_tiny[off_tiny] = k; }
+}
+
+// classify + scan + compact of a level of at most kSmallLevel nodes in one CTA (one launch instead of five)
+constexpr int kSmallLevel = 4096, kMaxRunLevels = 2048;
+__global__ void __launch_bounds__(1024) level_compact_small_kernel(const unsigned* nlen, int base, int n, unsigned split_node, int* active,
+                                                                   int* klist_split, int* klist_big, int* klist_small, int* klist_tiny,
+                                                                   int* class_counts /* mapped host memory */) {
+    __shared__ int s_warp[1024 / 32 + 1];
+    const int tid = threadIdx.x;
+    int cls[4], c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = tid * 4 + j;
+        cls[j] = -1;
+        if (i < n) {
+            const unsigned len = nlen[base + i];
+            cls[j] = len > split_node ? 0 : (len > kBigNode ? 1 : (len > kTinyNode ? 2 : (len > kMaxLeaf ? 3 : -1)));
+        }
+        c0 += cls[j] == 0; c1 += cls[j] == 1; c2 += cls[j] == 2; c3 += cls[j] == 3;
+    }
+    int t0, t1, t2, t3;
+    int o0 = block_exclusive_scan<1024>(c0, s_warp, t0);
+    int o1 = block_exclusive_scan<1024>(c1, s_warp, t1);
+    int o2 = block_exclusive_scan<1024>(c2, s_warp, t2);
+    int o3 = block_exclusive_scan<1024>(c3, s_warp, t3);
+    int k = o0 + o1 + o2 + o3;  // active nodes before this thread's first one, in level order
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (cls[j] < 0) continue;
+        active[k] = base + tid * 4 + j;
+        if (cls[j] == 0) klist_split[o0++] = k;
+        else if (cls[j] == 1) klist_big[o1++] = k;
+        else if (cls[j] == 2) klist_small[o2++] = k;
+        else klist_tiny[o3++] = k;
+        ++k;
+    }
+    if (tid == 0) { class_counts[0] = t0; class_counts[1] = t1; class_counts[2] = t2; class_counts[3] = t3; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -451,6 +825,18 @@ __global__ void subtree_size_kernel(BuildArrays a, int base, int n) {
     a.nsize[id] = c < 0 ? 1u : 1u + a.nsize[c] + a.nsize[c + 1];
 }
 
+// the same for a run of consecutive small levels d_hi, d_hi - 1, ..., d_lo in one CTA (levels[2d] = base, levels[2d+1] = count)
+__global__ void __launch_bounds__(1024) subtree_size_run_kernel(BuildArrays a, const int* levels, int d_hi, int d_lo) {
+    for (int d = d_hi; d >= d_lo; --d) {
+        const int base = levels[2 * d], n = levels[2 * d + 1];
+        for (int i = threadIdx.x; i < n; i += 1024) {
+            const int id = base + i, c = a.nchild[id];
+            a.nsize[id] = c < 0 ? 1u : 1u + a.nsize[c] + a.nsize[c + 1];
+        }
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ int leaf_pack(const BuildArrays& a, int id) {
     const unsigned s = a.nstart[id], len = a.nlen[id];
     const unsigned at = a.T - (s + len) + (unsigned)a.tri_offset;  // :469
@@ -458,10 +844,7 @@ __device__ __forceinline__ int leaf_pack(const BuildArrays& a, int id) {
 }
 
 // FlattenBVH (:783-845), one level per launch, top-down
-__global__ void flatten_stackless_kernel(BuildArrays a, const unsigned char* nflip, int base, int n, float4* out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int id = base + i;
+__device__ __forceinline__ void flatten_stackless_node(const BuildArrays& a, const unsigned char* nflip, int id, float4* out) {
     if (id == 0) { a.npre[0] = 0; a.nlink[0] = -1; }
     const int pre = a.npre[id], link = a.nlink[id], c = a.nchild[id];
     const float4 mn = a.nmin[id], mx = a.nmax[id];
@@ -478,6 +861,21 @@ __global__ void flatten_stackless_kernel(BuildArrays a, const unsigned char* nfl
     }
     out[2 * (size_t)pre] = make_float4(mn.x, mn.y, mn.z, __int_as_float(minw));
     out[2 * (size_t)pre + 1] = make_float4(mx.x, mx.y, mx.z, __int_as_float(link));
+}
+
+__global__ void flatten_stackless_kernel(BuildArrays a, const unsigned char* nflip, int base, int n, float4* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flatten_stackless_node(a, nflip, base + i, out);
+}
+
+// a run of consecutive small levels d_lo .. d_hi, top-down, in one CTA
+__global__ void __launch_bounds__(1024) flatten_stackless_run_kernel(BuildArrays a, const unsigned char* nflip, const int* levels, int d_lo, int d_hi,
+                                                                     float4* out) {
+    for (int d = d_lo; d <= d_hi; ++d) {
+        const int base = levels[2 * d], n = levels[2 * d + 1];
+        for (int i = threadIdx.x; i < n; i += 1024) flatten_stackless_node(a, nflip, base + i, out);
+        __syncthreads();
+    }
 }
 
 __global__ void inner_flags_kernel(BuildArrays a, int n, int* flags) {
@@ -560,8 +958,11 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     uint32_t* d_idx = nullptr;
     int32_t* d_mesh = nullptr;
     unsigned char* d_flip = nullptr;
-    int *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr, *d_kl_tiny = nullptr;
-    const size_t scan_n = std::max<size_t>(3 * n_max, 16);
+    int *d_levels = nullptr, *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr, *d_kl_tiny = nullptr, *d_kl_split = nullptr;
+    const size_t scan_n = std::max<size_t>(4 * n_max, 16);
+    const unsigned split_node = rq.split_node ? std::max(rq.split_node, kTinyNode) : kSplitNodeDefault;
+    const size_t n_split_max = T / split_node + 2, split_chunks_max = T / kSplitChunk + n_split_max + 1;
+    SplitArgs sp{};
     auto layout = [&](Scratch& sc) {
         sc.alloc(&d_idx, 3 * T);
         if (rq.h_mesh_ids) sc.alloc(&d_mesh, T);
@@ -573,6 +974,10 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
         sc.alloc(&d_flags, scan_n); sc.alloc(&d_offsets, scan_n);
         sc.alloc(&d_block_sums, scan_n / kScanTile + 2); sc.alloc(&d_totals, 4);
         sc.alloc(&d_active, n_max); sc.alloc(&d_active_next, n_max); sc.alloc(&d_kl_big, n_max); sc.alloc(&d_kl_small, n_max); sc.alloc(&d_kl_tiny, n_max);
+        sc.alloc(&d_kl_split, n_split_max); sc.alloc(&d_levels, 2 * (size_t)kMaxRunLevels);
+        sc.alloc(&sp.chunk_base, n_split_max + 1); sc.alloc(&sp.bins, n_split_max * kBinInts); sc.alloc(&sp.done, n_split_max * 3);
+        sc.alloc(&sp.split, n_split_max * 4); sc.alloc(&sp.boxes, n_split_max * 24); sc.alloc(&sp.chunk_l, split_chunks_max);
+        sc.alloc(&sp.rankflag, T); sc.alloc(&sp.rpos, T); sc.alloc(&sp.alt, T);
     };
     Scratch measure;
     layout(measure);
@@ -586,6 +991,11 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     Scratch sc;
     sc.base = static_cast<char*>(*rq.arena);
     layout(sc);
+
+    if (!*rq.host_counts) BK(cudaHostAlloc(reinterpret_cast<void**>(rq.host_counts), 4 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    volatile int* h_counts = *rq.host_counts;
+    int* d_counts = nullptr;
+    BK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_counts), *rq.host_counts, 0));
 
     cudaEvent_t ev0, ev1;
     BK(cudaEventCreate(&ev0));
@@ -617,13 +1027,15 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
         lc.n++;
     } else {
         // level 0: the root is the only active node
-        int n_big = T > kBigNode ? 1 : 0, n_tiny = T <= kTinyNode ? 1 : 0, n_small = 1 - n_big - n_tiny;
+        int n_split = T > split_node ? 1 : 0, n_big = !n_split && T > kBigNode ? 1 : 0, n_tiny = T <= kTinyNode ? 1 : 0,
+            n_small = 1 - n_split - n_big - n_tiny;
         BK(cudaMemsetAsync(d_active, 0, sizeof(int), st));
+        BK(cudaMemsetAsync(d_kl_split, 0, sizeof(int), st));
         BK(cudaMemsetAsync(d_kl_big, 0, sizeof(int), st));
         BK(cudaMemsetAsync(d_kl_small, 0, sizeof(int), st));
         BK(cudaMemsetAsync(d_kl_tiny, 0, sizeof(int), st));
-        while (n_big + n_small + n_tiny > 0) {
-            const int n_active = n_big + n_small + n_tiny;
+        while (n_split + n_big + n_small + n_tiny > 0) {
+            const int n_active = n_split + n_big + n_small + n_tiny;
             LevelArgs g;
             g.a = a;
             g.active = d_active;
@@ -633,6 +1045,20 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
             g.swap_policy = rq.opts.swap_policy;
             g.swap_seed = rq.opts.swap_seed;
             g.nflip = d_flip;
+            if (n_split) {
+                g.klist = d_kl_split;
+                sp.g = g;
+                sp.n_split = n_split;
+                // every split node is longer than split_node, so its chunks number at most T / chunk + one partial chunk per node
+                const unsigned grid = (unsigned)(T / kSplitChunk + (size_t)n_split);
+                split_prep_kernel<<<1, 1024, 0, st>>>(sp);
+                split_bin_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
+                split_count_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
+                split_rank_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
+                split_gather_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
+                split_finish_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
+                lc.n += 6;
+            }
             if (n_big) { g.klist = d_kl_big; level_step_kernel<1024><<<n_big, 1024, 0, st>>>(g); lc.n++; }
             if (n_small) { g.klist = d_kl_small; level_step_kernel<128><<<n_small, 128, 0, st>>>(g); lc.n++; }
             if (n_tiny) { g.klist = d_kl_tiny; level_step_kernel<32><<<n_tiny, 32, 0, st>>>(g); lc.n++; }
@@ -642,30 +1068,52 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
             level_count.push_back(n);
             n_nodes += (size_t)n;
             // next level's active list
-            classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.nlen, base, n, d_flags);
-            lc.n++;
-            exclusive_scan(d_flags, 3 * n, d_offsets, d_block_sums, d_totals, st, lc);
-            compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_flags, d_offsets, base, n, d_active_next, d_kl_big, d_kl_small, d_kl_tiny);
-            lc.n++;
-            int h_tot[3];
-            BK(cudaMemcpyAsync(&h_tot[0], d_totals, sizeof(int), cudaMemcpyDeviceToHost, st));
-            BK(cudaMemcpyAsync(&h_tot[1], d_offsets + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-            BK(cudaMemcpyAsync(&h_tot[2], d_offsets + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, st));
+            // the four class sizes of the next level land in mapped host memory: one synchronisation per level, no copies
+            if (n <= kSmallLevel) {
+                level_compact_small_kernel<<<1, 1024, 0, st>>>(a.nlen, base, n, split_node, d_active_next, d_kl_split, d_kl_big, d_kl_small, d_kl_tiny,
+                                                               d_counts);
+                lc.n++;
+            } else {
+                classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.nlen, base, n, split_node, d_flags);
+                exclusive_scan(d_flags, 4 * n, d_offsets, d_block_sums, d_totals, st, lc);
+                compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_flags, d_offsets, d_totals, base, n, d_active_next, d_kl_split, d_kl_big, d_kl_small,
+                                                                d_kl_tiny, d_counts);
+                lc.n += 2;
+            }
             BK(cudaStreamSynchronize(st));
-            n_big = h_tot[1];
-            n_small = h_tot[2] - h_tot[1];
-            n_tiny = h_tot[0] - h_tot[2];
+            n_split = h_counts[0];
+            n_big = h_counts[1];
+            n_small = h_counts[2];
+            n_tiny = h_counts[3];
             std::swap(d_active, d_active_next);
         }
-        // flatten
-        for (int d = (int)level_base.size() - 1; d >= 0; --d) {
-            subtree_size_kernel<<<(level_count[d] + 255) / 256, 256, 0, st>>>(a, level_base[d], level_count[d]);
+        // flatten.  Runs of consecutive levels of at most kSmallLevel nodes (the top and the bottom of the tree) take one
+        // single-CTA launch each instead of one launch per level.
+        const int D = (int)level_base.size();
+        const bool runs = D <= kMaxRunLevels;
+        if (runs) {
+            std::vector<int> h_levels(2 * (size_t)D);
+            for (int d = 0; d < D; ++d) { h_levels[2 * d] = level_base[d]; h_levels[2 * d + 1] = level_count[d]; }
+            BK(cudaMemcpyAsync(d_levels, h_levels.data(), h_levels.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+            BK(cudaStreamSynchronize(st));  // h_levels goes out of scope
+        }
+        auto small = [&](int d) { return runs && level_count[d] <= kSmallLevel; };
+        for (int d = D - 1; d >= 0;) {
+            int e = d;
+            while (small(d) && e > 0 && small(e - 1)) --e;
+            if (e < d) subtree_size_run_kernel<<<1, 1024, 0, st>>>(a, d_levels, d, e);
+            else subtree_size_kernel<<<(level_count[d] + 255) / 256, 256, 0, st>>>(a, level_base[d], level_count[d]);
             lc.n++;
+            d = e - 1;
         }
         if (stackless) {
-            for (size_t d = 0; d < level_base.size(); ++d) {
-                flatten_stackless_kernel<<<(level_count[d] + 255) / 256, 256, 0, st>>>(a, d_flip, level_base[d], level_count[d], out);
+            for (int d = 0; d < D;) {
+                int e = d;
+                while (small(d) && e + 1 < D && small(e + 1)) ++e;
+                if (e > d) flatten_stackless_run_kernel<<<1, 1024, 0, st>>>(a, d_flip, d_levels, d, e, out);
+                else flatten_stackless_kernel<<<(level_count[d] + 255) / 256, 256, 0, st>>>(a, d_flip, level_base[d], level_count[d], out);
                 lc.n++;
+                d = e + 1;
             }
         } else {
             const int n = (int)n_nodes;

@@ -21,6 +21,8 @@ struct BuildRequest {
     size_t n_nodes_out;          // result: LastNodeIndex + 1
     void** arena;                // scratch allocation kept by the context between builds
     size_t* arena_cap;
+    int** host_counts;           // 4 ints of mapped pinned memory kept by the context (per-level class sizes)
+    unsigned split_node = 0;     // SAH builder: ranges longer than this are split across CTAs (0 = default)
 };
 
 // Returns CNDL_OK or a negative cndl_status with `err` set. Work is enqueued on `st` and complete on return.

@@ -76,7 +76,7 @@ struct cndl_ctx {
     cudaStream_t main_stream = nullptr;
     int mode = 2, sort_rays = 0;   // sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};  // bounds of all entities (for sort_rays = 2)
-    int knobs[8] = {8, 14, 10, 0, 0, 12, 4096, 1024};  // CNDL_KNOB_*
+    int knobs[9] = {8, 14, 10, 0, 0, 12, 4096, 1024, 0};  // CNDL_KNOB_*
     // hot-first derived layout of the stackless nodes (kernels_hot.cu), rebuilt by cndl_commit
     DeviceBuffer nodes2, perm, ents2, hot_scratch, d_objects;
     std::vector<int2> h_objects;                 // (node_offset, node_count) in insertion order
@@ -89,6 +89,7 @@ struct cndl_ctx {
     float last_build_ms = 0.0f;
     void* build_arena = nullptr;
     size_t build_arena_cap = 0;
+    int* build_host_counts = nullptr;
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -273,6 +274,7 @@ void cndl_destroy(cndl_ctx* ctx) {
     for (auto& s : ctx->streams) if (s) cudaStreamDestroy(s);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     if (ctx->build_arena) cudaFree(ctx->build_arena);
+    if (ctx->build_host_counts) cudaFreeHost(ctx->build_host_counts);
     for (auto& e : ctx->events) cudaEventDestroy(e);
     delete ctx;
 }
@@ -374,6 +376,8 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     rq.n_nodes_out = 0;
     rq.arena = &ctx->build_arena;
     rq.arena_cap = &ctx->build_arena_cap;
+    rq.host_counts = &ctx->build_host_counts;
+    rq.split_node = (unsigned)ctx->knobs[CNDL_KNOB_BUILD_SPLIT_NODE];
     std::string berr;
     float ms = 0.0f;
     const int rc = build_object(rq, st, ctx->launches, &ms, berr);
@@ -544,7 +548,7 @@ int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays) {
 }
 
 int cndl_set_tuning(cndl_ctx* ctx, int knob, int value) {
-    if (!ctx || knob < 0 || knob >= 8 || value < 0) return CNDL_ERR_INVALID;
+    if (!ctx || knob < 0 || knob >= 9 || value < 0) return CNDL_ERR_INVALID;
     if (knob == CNDL_KNOB_BLOCKS_PER_SM && (value < 1 || value > 16)) return CNDL_ERR_INVALID;
     ctx->knobs[knob] = value;
     return CNDL_OK;

@@ -111,6 +111,34 @@ def test_heightfield_sorted_input(cb, ob):
         ri.close()
 
 
+@pytest.mark.parametrize("split_node", [64, 300, 5000, 1 << 26])
+def test_split_node_threshold_never_changes_the_buffers(cb, ob, golden_meshes, split_node):
+    """Ranges above CNDL_KNOB_BUILD_SPLIT_NODE go through the multi-CTA level step (one CTA per 2048 references, global bins,
+    ranks and the Lomuto chain across CTAs), the others through the one-CTA-per-node step: same bytes for every threshold,
+    from "nearly every level split" (64) to "never" (2^26), on meshes with split failures, duplicates and signed zeros."""
+    from candela_b200 import scenes
+    cases = [(n,) + tuple(golden_meshes[n]) for n in ("dragon", "coplanar_grid", "duplicates", "signed_zero", "soup400")]
+    v, i, m = scenes.make_heightfield(120)
+    for fmt in (ob.STACKLESS, ob.STACK):
+        for name, P, F in cases:
+            V = ob.make_vertices(P)
+            ref = ob.build(fmt, V, F.ravel())
+            ri = cb.RayIntersector(fmt)
+            ri.set_tuning(8, split_node)
+            ri.AddObject(2, V, F.ravel())
+            nodes, tris, _ = ri.read_buffers()
+            assert tris.tobytes() == ref.tris.tobytes(), (name, first_diff(tris, ref.tris))
+            assert nodes.tobytes() == ref.nodes.tobytes(), (name, first_diff(nodes, ref.nodes))
+            ri.close()
+        ref = ob.build(fmt, v, i, m, swap_policy=ob.SWAP_HASHED, swap_seed=7)
+        ri = cb.RayIntersector(fmt)
+        ri.set_tuning(8, split_node)
+        ri.AddObject(2, v, i, m, swap_policy=ob.SWAP_HASHED, swap_seed=7)
+        nodes, tris, _ = ri.read_buffers()
+        assert tris.tobytes() == ref.tris.tobytes() and nodes.tobytes() == ref.nodes.tobytes(), ("heightfield", first_diff(nodes, ref.nodes))
+        ri.close()
+
+
 def test_bad_geometry_rejected(cb):
     ri = cb.RayIntersector(cb.STACKLESS)
     V = cb.make_vertices(np.zeros((3, 3), np.float32))

@@ -1,36 +1,45 @@
-"""Developer tool: GPU build time on the S260k scene and (optionally) a heightfield, checked against the oracle."""
-import argparse, sys, time
+"""Build times of the exact SAH builder for several multi-CTA split thresholds (knob 8), with a byte comparison
+against the CPU oracle.  python tools/build_bench.py [--big] [--check]"""
+import argparse
+import sys
 from pathlib import Path
-import numpy as np
-ROOT = Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT))
-import candela_b200 as cb
-from candela_b200 import scenes
 
-ap = argparse.ArgumentParser()
-ap.add_argument("--heightfield", type=int, default=0, help="grid size n: (n-1)^2*2 triangles")
-ap.add_argument("--check", action="store_true")
-ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--builder", type=int, default=0)
-args = ap.parse_args()
-for name, (v, i, m) in (("s260k", scenes.make_s260k()),) + ((("heightfield%d" % args.heightfield, scenes.make_heightfield(args.heightfield)),) if args.heightfield else ()):
-    for fmt in (cb.STACKLESS, cb.STACK):
-        ms = []
-        for _ in range(args.reps):
-            ri = cb.RayIntersector(fmt)
-            t0 = time.perf_counter()
-            ri.AddObject(2, v, i, m, builder=args.builder)
-            wall = 1e3 * (time.perf_counter() - t0)
-            ms.append(ri.last_build_ms)
-            if _ + 1 < args.reps:
-                ri.close()
-        line = f"{name} fmt={fmt} T={len(i)//3} nodes={ri.node_count} gpu_build_ms min={min(ms):.3f} med={sorted(ms)[len(ms)//2]:.3f} wall_ms_last={wall:.1f} launches={ri.launch_count}"
-        if args.check and args.builder == 0:
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from candela_b200 import api as cb, scenes  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--big", action="store_true", help="also the 2.0 M-triangle heightfield")
+    ap.add_argument("--check", action="store_true", help="byte-compare with the CPU oracle (tests only)")
+    ap.add_argument("--thresholds", default="0,2048,4096,8192,32768,65536,67108864")
+    args = ap.parse_args()
+    cases = [("s260k", scenes.make_s260k())]
+    if args.big:
+        cases.append(("heightfield1000", scenes.make_heightfield(1000)))
+    for name, (v, i, m) in cases:
+        ref = None
+        if args.check:
             from oracle import binding as ob
-            t0 = time.perf_counter()
-            ref = ob.build(fmt, v, i, m)
-            cpu = 1e3 * (time.perf_counter() - t0)
-            nodes, tris, _v = ri.read_buffers()
-            line += f" cpu_oracle_ms={cpu:.0f} identical={nodes.tobytes() == ref.nodes.tobytes() and tris.tobytes() == ref.tris.tobytes()}"
-        print(line, flush=True)
-        ri.close()
+            ref = {f: ob.build(f, v, i, m) for f in (ob.STACKLESS, ob.STACK)}
+        for fmt in (cb.STACKLESS, cb.STACK):
+            for thr in [int(t) for t in args.thresholds.split(",")]:
+                times = []
+                ok = None
+                for rep in range(5):
+                    ri = cb.RayIntersector(fmt)
+                    ri.set_tuning(8, thr)
+                    ri.AddObject(2, v, i, m)
+                    times.append(ri.last_build_ms)
+                    if rep == 0 and ref is not None:
+                        nodes, tris, _ = ri.read_buffers()
+                        ok = nodes.tobytes() == ref[fmt].nodes.tobytes() and tris.tobytes() == ref[fmt].tris.tobytes()
+                    ri.close()
+                print(f"{name} fmt={fmt} split_node={thr}: build ms min {min(times):.3f} median {float(np.median(times)):.3f}"
+                      + ("" if ok is None else f" byte-identical={ok}"), flush=True)
+
+
+if __name__ == "__main__":
+    main()
