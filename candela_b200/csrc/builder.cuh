@@ -22,6 +22,7 @@ struct BuildRequest {
     void** arena;                // scratch allocation kept by the context between builds
     size_t* arena_cap;
     int** host_counts;           // 4 ints of mapped pinned memory kept by the context (per-level class sizes)
+    cudaStream_t side[2] = {nullptr, nullptr};  // SAH builder: streams for the size classes of one level (optional)
     unsigned split_node = 0;     // SAH builder: ranges longer than this are split across CTAs (0 = default)
 };
 

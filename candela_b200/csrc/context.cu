@@ -377,6 +377,8 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     rq.arena = &ctx->build_arena;
     rq.arena_cap = &ctx->build_arena_cap;
     rq.host_counts = &ctx->build_host_counts;
+    rq.side[0] = ctx->streams[1];
+    rq.side[1] = ctx->streams[3];
     rq.split_node = (unsigned)ctx->knobs[CNDL_KNOB_BUILD_SPLIT_NODE];
     std::string berr;
     float ms = 0.0f;

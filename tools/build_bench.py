@@ -13,18 +13,22 @@ from candela_b200 import api as cb, scenes  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--big", action="store_true", help="also the 2.0 M-triangle heightfield")
+    ap.add_argument("--grid", type=int, default=0, help="also a heightfield of 2 * grid^2 triangles (2236 -> 10 M)")
+    ap.add_argument("--fmts", default="0,1")
     ap.add_argument("--check", action="store_true", help="byte-compare with the CPU oracle (tests only)")
     ap.add_argument("--thresholds", default="0,2048,4096,8192,32768,65536,67108864")
     args = ap.parse_args()
     cases = [("s260k", scenes.make_s260k())]
     if args.big:
         cases.append(("heightfield1000", scenes.make_heightfield(1000)))
+    if args.grid:
+        cases.append((f"heightfield{args.grid}", scenes.make_heightfield(args.grid)))
     for name, (v, i, m) in cases:
         ref = None
         if args.check:
             from oracle import binding as ob
             ref = {f: ob.build(f, v, i, m) for f in (ob.STACKLESS, ob.STACK)}
-        for fmt in (cb.STACKLESS, cb.STACK):
+        for fmt in [int(f) for f in args.fmts.split(',')]:
             for thr in [int(t) for t in args.thresholds.split(",")]:
                 times = []
                 ok = None
