@@ -102,22 +102,31 @@ __global__ void tri_precompute_kernel(BuildArrays a) {
         a.tcz[t] = cz;
         a.refs[t] = (int)t;
     }
-    // root box: numeric min/max by ordered-int atomics (warp-reduced first)
+    // root box: numeric min/max by ordered-int atomics, reduced per warp and per block first (one set of global atomics per block:
+    // at 10 M triangles the per-warp version spent 1.3 ms on twelve contended addresses)
+    __shared__ int s_root[12];
+    if (threadIdx.x < 12) s_root[threadIdx.x] = threadIdx.x < 3 ? 0x7FFFFFFF : (threadIdx.x < 6 ? (int)0x80000000 : -1);
+    __syncthreads();
     for (int k = 0; k < 3; ++k) {
         int kmn = f2key(mn[k] == 0.0f ? 0.0f : mn[k]), kmx = f2key(mx[k] == 0.0f ? 0.0f : mx[k]);
-        for (int o = 16; o > 0; o >>= 1) {
-            kmn = min(kmn, __shfl_xor_sync(0xFFFFFFFFu, kmn, o));
-            kmx = max(kmx, __shfl_xor_sync(0xFFFFFFFFu, kmx, o));
-        }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(a.root_scratch + k, kmn);
-            atomicMax(a.root_scratch + 3 + k, kmx);
-        }
         // MinInitial = glm::min(MinInitial, cur.Min) (:421): ties take the later triangle, so the sign of a
         // zero result is that of the LAST triangle whose component is zero.
-        if (valid && mn[k] == 0.0f) atomicMax(a.root_scratch + 6 + k, (int)t);
-        if (valid && mx[k] == 0.0f) atomicMax(a.root_scratch + 9 + k, (int)t);
+        int zmn = valid && mn[k] == 0.0f ? (int)t : -1, zmx = valid && mx[k] == 0.0f ? (int)t : -1;
+        kmn = __reduce_min_sync(0xFFFFFFFFu, kmn);
+        kmx = __reduce_max_sync(0xFFFFFFFFu, kmx);
+        zmn = __reduce_max_sync(0xFFFFFFFFu, zmn);
+        zmx = __reduce_max_sync(0xFFFFFFFFu, zmx);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&s_root[k], kmn);
+            atomicMax(&s_root[3 + k], kmx);
+            if (zmn >= 0) atomicMax(&s_root[6 + k], zmn);
+            if (zmx >= 0) atomicMax(&s_root[9 + k], zmx);
+        }
     }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicMin(a.root_scratch + threadIdx.x, s_root[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicMax(a.root_scratch + threadIdx.x, s_root[threadIdx.x]);
+    else if (threadIdx.x < 12 && s_root[threadIdx.x] >= 0) atomicMax(a.root_scratch + threadIdx.x, s_root[threadIdx.x]);
 }
 
 __global__ void root_finalize_kernel(BuildArrays a) {
@@ -427,6 +436,179 @@ __global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g) {
     // ---- create the two children (:559-572,:612-625) ----
     if (tid < 2) create_child(g, k, tid, start, len, mid, s_box[tid], s_zero_first[tid], a.refs);
     if (tid == 0) finish_parent(g, k, id, start, len);
+}
+
+// The level step for ranges of 3..64 references, one WARP per node, kTinyWarps nodes per CTA.  The bottom levels of a
+// tree hold most of its nodes (10 M triangles: 1.6 M ranges in one level); with one-warp CTAs the 32-CTA limit left
+// the SMs half empty, and the three-axis bins made shared memory the next limit.  Here a lane keeps its (at most two)
+// references in registers, the 64 bins of ONE axis at a time live in 1.8 KB of shared memory per warp, ranks come
+// from ballots and the child boxes from warp reductions.  Same arithmetic, same order of decisions as level_step_kernel.
+// 64 registers / 4 CTAs per SM: more resident warps (48 or 40 registers, with spills) measured 3-6 % slower.
+constexpr int kTinyWarps = 8;
+constexpr unsigned kDirectLen = 9;  // ranges up to this length search their split without bins (3 x 10 candidates <= 32 lanes)
+__global__ void __launch_bounds__(32 * kTinyWarps, 4) level_step_tiny_kernel(LevelArgs g, int n_nodes) {
+    const BuildArrays& a = g.a;
+    __shared__ int s_count[kTinyWarps][kBins];
+    __shared__ int s_mn[kTinyWarps][3][kBins], s_mx[kTinyWarps][3][kBins];
+    __shared__ float s_best_cost[kTinyWarps], s_border[kTinyWarps];
+    __shared__ int s_axis[kTinyWarps];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int node = blockIdx.x * kTinyWarps + wp;
+    if (node >= n_nodes) return;  // whole warps leave; nothing below synchronises across warps
+    const int k = g.klist[node];
+    const int id = g.active[k];
+    const unsigned start = a.nstart[id], len = a.nlen[id];
+    const float4 bmn = a.nmin[id], bmx = a.nmax[id];
+    const unsigned lt = (1u << lane) - 1u;
+
+    // this lane's references: positions lane and lane + 32 of the range
+    const bool v0 = (unsigned)lane < len, v1 = (unsigned)lane + 32 < len;
+    const int r0 = v0 ? a.refs[start + lane] : -1, r1 = v1 ? a.refs[start + 32 + lane] : -1;
+    // ---- SearchSAHPlaneBinned (:276-363) ----
+    if (len <= kDirectLen) {
+        // Up to 9 references (three quarters of all tiny ranges): no bins.  The cost of split i only changes where a bin is
+        // occupied, and strict `<` over ascending i keeps the first index of every constant stretch, so the candidates per axis
+        // are i = 0 and the bins of the references themselves: at most 10 x 3 (axis, candidate) pairs, one per lane, each
+        // accumulating its two sides over the references staged in shared memory.  The minimum over (cost, axis, i) in that
+        // order is the pair the sequential search ends with.
+        float* stage = reinterpret_cast<float*>(&s_mn[wp][0][0]);  // 9 words per reference: box min, box max, centroid
+        if (v0) {
+            const float4 tm = a.tmin[r0], tx = a.tmax[r0];
+            float* e = stage + 9 * lane;
+            e[0] = tm.x; e[1] = tm.y; e[2] = tm.z; e[3] = tx.x; e[4] = tx.y; e[5] = tx.z; e[6] = tm.w; e[7] = tx.w; e[8] = a.tcz[r0];
+        }
+        __syncwarp();
+        const int ax = lane / (kDirectLen + 1), j = lane % (kDirectLen + 1);
+        const float lo = ax == 0 ? bmn.x : (ax == 1 ? bmn.y : bmn.z), hi = ax == 0 ? bmx.x : (ax == 1 ? bmx.y : bmx.z);
+        const float extent = fsub(hi, lo);
+        const float scale = fdiv((float)kBins, extent);         // :295
+        int ci = 0;
+        if ((unsigned)j < len) {
+            ci = __float2int_rz(fmul(fsub(stage[9 * j + 6 + (ax < 3 ? ax : 0)], lo), scale));  // :302
+            ci = ci > kBins - 1 ? kBins - 1 : (ci < 0 ? 0 : ci);
+        }
+        const bool active = ax < 3 && (unsigned)j <= len && !(lo == hi) && ci < kBins - 1;  // :285; i = 63 is not a split
+        BinAgg L = agg_identity(), R = agg_identity();
+        for (unsigned e = 0; e < len; ++e) {
+            const float* el = stage + 9 * e;
+            int b = __float2int_rz(fmul(fsub(el[6 + (ax < 3 ? ax : 0)], lo), scale));
+            b = b > kBins - 1 ? kBins - 1 : (b < 0 ? 0 : b);
+            BinAgg one;
+            one.n = 1;
+            one.mn[0] = el[0]; one.mn[1] = el[1]; one.mn[2] = el[2]; one.mx[0] = el[3]; one.mx[1] = el[4]; one.mx[2] = el[5];
+            if (b <= ci) L = agg_join(L, one); else R = agg_join(R, one);
+        }
+        float cost = agg_cost(L, R);
+        if (!active || !(cost == cost)) cost = __int_as_float(0x7F800000);  // a NaN cost is never selected by `<`
+        int key = ax * kBins + ci, who = lane;
+        for (int o = 16; o > 0; o >>= 1) {
+            const float pc = __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+            const int pk = __shfl_xor_sync(0xFFFFFFFFu, key, o), pw = __shfl_xor_sync(0xFFFFFFFFu, who, o);
+            if (pc < cost || (pc == cost && pk < key)) { cost = pc; key = pk; who = pw; }
+        }
+        const float my_border = fadd(lo, fmul(fdiv(extent, (float)kBins), __int2float_rn(ci + 1)));  // :347,:356
+        const float win_border = __shfl_sync(0xFFFFFFFFu, my_border, who);
+        __syncwarp();
+        if (lane == 0) {
+            const bool found = cost < kInfCost;
+            s_axis[wp] = found ? key / kBins : 0;
+            s_border[wp] = found ? win_border : bmn.x;
+        }
+        __syncwarp();
+    } else {
+        // one axis at a time through 64 bins
+        if (lane == 0) { s_best_cost[wp] = kInfCost; s_axis[wp] = 0; s_border[wp] = bmn.x; }
+        for (int ax = 0; ax < 3; ++ax) {
+            const float lo = ax == 0 ? bmn.x : (ax == 1 ? bmn.y : bmn.z), hi = ax == 0 ? bmx.x : (ax == 1 ? bmx.y : bmx.z);
+            if (lo == hi) continue;                                 // :285
+            const float extent = fsub(hi, lo);
+            const float scale = fdiv((float)kBins, extent);         // :295
+            for (int b = lane; b < kBins; b += 32) s_count[wp][b] = 0;
+            for (int b = lane; b < 3 * kBins; b += 32) { (&s_mn[wp][0][0])[b] = f2key(kSentinelMax); (&s_mx[wp][0][0])[b] = f2key(kSentinelMin); }
+            __syncwarp();
+            // the boxes are re-read per axis (L1 hits) instead of being held in registers across the split search
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = half ? r1 : r0;
+                if (r < 0) continue;
+                const float4 tm = a.tmin[r], tx = a.tmax[r];
+                const float cen = ax == 0 ? tm.w : (ax == 1 ? tx.w : a.tcz[r]);
+                int b = __float2int_rz(fmul(fsub(cen, lo), scale));  // :302
+                b = b > kBins - 1 ? kBins - 1 : (b < 0 ? 0 : b);
+                atomicAdd(&s_count[wp][b], 1);
+                atomicMin(&s_mn[wp][0][b], f2key(tm.x)); atomicMin(&s_mn[wp][1][b], f2key(tm.y)); atomicMin(&s_mn[wp][2][b], f2key(tm.z));
+                atomicMax(&s_mx[wp][0][b], f2key(tx.x)); atomicMax(&s_mx[wp][1][b], f2key(tx.y)); atomicMax(&s_mx[wp][2][b], f2key(tx.z));
+            }
+            __syncwarp();
+            warp_sah_eval(s_count[wp], s_mn[wp], s_mx[wp], ax, lo, extent, &s_best_cost[wp], &s_axis[wp], &s_border[wp]);
+            __syncwarp();
+        }
+    }
+    const int axis = s_axis[wp];
+    const float border = s_border[wp];
+
+    // ---- Lomuto partition (:532-549), 32 positions at a time (see level_step_kernel) ----
+    unsigned mid = start;
+    const float c0 = v0 ? centroid_of(a, r0, axis) : 0.0f, c1 = v1 ? centroid_of(a, r1, axis) : 0.0f;
+    for (int half = 0; half < 2; ++half) {
+        const unsigned i0 = start + 32u * half;
+        if (i0 >= start + len) break;
+        const int r = half ? r1 : r0;
+        const bool f = (half ? v1 : v0) && (half ? c1 : c0) < border;
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, f);
+        const int rank = __popc(mask & lt), nL = __popc(mask);
+        const unsigned P = i0 + lane, s = mid + (unsigned)rank;
+        const bool writes_back = f && s != P && !(P >= mid && P < mid + (unsigned)nL);
+        long long q = (long long)s - (long long)i0;
+        if (writes_back)
+            while (q >= 0 && ((mask >> q) & 1u)) q = (long long)mid + __popc(mask & ((1u << q) - 1u)) - (long long)i0;
+        const int from_chunk = __shfl_sync(0xFFFFFFFFu, r, q < 0 ? 0 : (int)q);
+        int displaced = -1;
+        if (writes_back) displaced = q < 0 ? a.refs[(long long)i0 + q] : from_chunk;
+        __syncwarp();
+        if (f) a.refs[s] = r;
+        if (writes_back) a.refs[P] = displaced;
+        mid += (unsigned)nL;
+        __syncwarp();
+    }
+    if (mid == start || mid == start + len) mid = start + len / 2;  // split failure (:553-556)
+
+    // ---- child boxes (:574-597): the FIRST zero decides a zero's sign ----
+    int box[2][6], zf[2][6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        box[0][c] = box[1][c] = c < 3 ? f2key(kSentinelMax) : f2key(kSentinelMin);
+        zf[0][c] = zf[1][c] = 0x7FFFFFFF;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const unsigned pos = start + 32u * half + lane;
+        if (pos < start + len) {
+            const int r = a.refs[pos];
+            const float4 tm = a.tmin[r], tx = a.tmax[r];
+            const float v[6] = {tm.x, tm.y, tm.z, tx.x, tx.y, tx.z};
+            const int side = pos < mid ? 0 : 1;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const int key = f2key(v[c] == 0.0f ? 0.0f : v[c]);
+                if (side == 0) { box[0][c] = c < 3 ? min(box[0][c], key) : max(box[0][c], key); if (v[c] == 0.0f) zf[0][c] = min(zf[0][c], (int)pos); }
+                else { box[1][c] = c < 3 ? min(box[1][c], key) : max(box[1][c], key); if (v[c] == 0.0f) zf[1][c] = min(zf[1][c], (int)pos); }
+            }
+        }
+    }
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            box[sd][c] = c < 3 ? __reduce_min_sync(0xFFFFFFFFu, box[sd][c]) : __reduce_max_sync(0xFFFFFFFFu, box[sd][c]);
+            zf[sd][c] = __reduce_min_sync(0xFFFFFFFFu, zf[sd][c]);
+        }
+    __syncwarp();  // the partition's writes to refs are visible to the two lanes below
+
+    // ---- create the two children (:559-572,:612-625) ----
+    if (lane == 0) create_child(g, k, 0, start, len, mid, box[0], zf[0], a.refs);
+    if (lane == 1) create_child(g, k, 1, start, len, mid, box[1], zf[1], a.refs);
+    if (lane == 0) finish_parent(g, k, id, start, len);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1077,7 +1259,12 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
             }
             if (n_big) { g.klist = d_kl_big; level_step_kernel<1024><<<n_big, 1024, 0, s_big>>>(g); lc.n++; }
             if (n_small) { g.klist = d_kl_small; level_step_kernel<128><<<n_small, 128, 0, s_small>>>(g); lc.n++; }
-            if (n_tiny) { g.klist = d_kl_tiny; level_step_kernel<32><<<n_tiny, 32, 0, st>>>(g); lc.n++; }
+            if (n_tiny) {
+                g.klist = d_kl_tiny;
+                const unsigned grid = (unsigned)((n_tiny + kTinyWarps - 1) / kTinyWarps);
+                level_step_tiny_kernel<<<grid, 32 * kTinyWarps, 0, st>>>(g, n_tiny);
+                lc.n++;
+            }
             BK(cudaGetLastError());
             if (fork) {
                 if (s_big != st) { BK(cudaEventRecord(ev_join[0], s_big)); BK(cudaStreamWaitEvent(st, ev_join[0], 0)); }
