@@ -32,7 +32,8 @@ constexpr float kInfCost = 1e29f;              // :56
 constexpr unsigned kBigNode = 512;             // ranges longer than this get a 1024-thread block (2048: +2 % build time)
 constexpr unsigned kTinyNode = 64;             // ranges up to this get one warp
 constexpr unsigned kSplitNodeDefault = 16384;  // ranges longer than this are split across CTAs (split_* kernels)
-constexpr int kSplitBlock = 256, kSplitItems = 8, kSplitChunk = kSplitBlock * kSplitItems;  // one CTA of a split node covers 2048 references
+constexpr int kSplitBlock = 256;  // a CTA of a split node covers 256 x ITEMS references: 512 up to 2^20 triangles (more CTAs: the passes are
+                                   // latency-bound there, 2.39 -> 2.12 ms at 262k), 2048 beyond (fewer merges into the global bins: 22.2 -> 20.9 ms at 10 M)
 constexpr int kBinInts = 3 * kBins + 18 * kBins;  // count[3][64], mn[3][3][64], mx[3][3][64] as ordered keys
 
 // glm 0.9.8.5 min/max (func_common.inl:15-28); argument order matters for +0/-0 ties
@@ -612,7 +613,7 @@ __global__ void __launch_bounds__(32 * kTinyWarps, 4) level_step_tiny_kernel(Lev
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same level step for ranges longer than the split threshold, spread over one CTA per 2048 references.
+// The same level step for ranges longer than the split threshold, spread over one CTA per 512 or 2048 references.
 // One CTA would walk a 262k-reference root three times alone (~1 ms); every result below is a pure function of
 // the range, so the passes can be cut anywhere:
 //   split_bin     bins its chunk in shared memory and merges into the node's global bins (min / max / + only);
@@ -673,14 +674,14 @@ __device__ __forceinline__ bool split_arrive_last(const SplitArgs& s, const Spli
     return last;
 }
 
-__global__ void __launch_bounds__(1024) split_prep_kernel(SplitArgs s) {
+__global__ void __launch_bounds__(1024) split_prep_kernel(SplitArgs s, int chunk_len) {
     __shared__ int s_warp[1024 / 32 + 1];
     const int tid = threadIdx.x;
     int carry = 0;
     for (int base = 0; base < s.n_split; base += 1024) {
         const int h = base + tid;
         int nch = 0;
-        if (h < s.n_split) nch = (int)((s.g.a.nlen[s.g.active[s.g.klist[h]]] + kSplitChunk - 1) / kSplitChunk);
+        if (h < s.n_split) nch = (int)((s.g.a.nlen[s.g.active[s.g.klist[h]]] + chunk_len - 1) / chunk_len);
         int total;
         const int ex = block_exclusive_scan<1024>(nch, s_warp, total);
         if (h < s.n_split) s.chunk_base[h] = carry + ex;
@@ -698,7 +699,9 @@ __global__ void __launch_bounds__(1024) split_prep_kernel(SplitArgs s) {
     }
 }
 
+template <int ITEMS>
 __global__ void __launch_bounds__(kSplitBlock) split_bin_kernel(SplitArgs s) {
+    constexpr int kSplitItems = ITEMS, kSplitChunk = kSplitBlock * ITEMS;
     __shared__ int s_count[3][kBins];
     __shared__ int s_mn[3][3][kBins], s_mx[3][3][kBins];
     __shared__ float s_best_cost, s_border;
@@ -783,7 +786,9 @@ __global__ void __launch_bounds__(kSplitBlock) split_bin_kernel(SplitArgs s) {
     }
 }
 
+template <int ITEMS>
 __global__ void __launch_bounds__(kSplitBlock) split_count_kernel(SplitArgs s) {
+    constexpr int kSplitItems = ITEMS, kSplitChunk = kSplitBlock * ITEMS;
     __shared__ int s_warp[kSplitBlock / 32 + 1];
     __shared__ int s_last;
     SplitWhere w;
@@ -818,7 +823,9 @@ __global__ void __launch_bounds__(kSplitBlock) split_count_kernel(SplitArgs s) {
     if (tid == 0) s.split[4 * w.h + 2] = carry;
 }
 
+template <int ITEMS>
 __global__ void __launch_bounds__(kSplitBlock) split_rank_kernel(SplitArgs s) {
+    constexpr int kSplitItems = ITEMS, kSplitChunk = kSplitBlock * ITEMS;
     __shared__ int s_warp[kSplitBlock / 32 + 1];
     SplitWhere w;
     if (!split_locate(s, w)) return;
@@ -846,7 +853,9 @@ __global__ void __launch_bounds__(kSplitBlock) split_rank_kernel(SplitArgs s) {
     }
 }
 
+template <int ITEMS>
 __global__ void __launch_bounds__(kSplitBlock) split_gather_kernel(SplitArgs s) {
+    constexpr int kSplitItems = ITEMS, kSplitChunk = kSplitBlock * ITEMS;
     SplitWhere w;
     if (!split_locate(s, w)) return;
     const BuildArrays& a = s.g.a;
@@ -867,7 +876,9 @@ __global__ void __launch_bounds__(kSplitBlock) split_gather_kernel(SplitArgs s) 
     }
 }
 
+template <int ITEMS>
 __global__ void __launch_bounds__(kSplitBlock) split_finish_kernel(SplitArgs s) {
+    constexpr int kSplitItems = ITEMS, kSplitChunk = kSplitBlock * ITEMS;
     __shared__ int s_box[2][6], s_zero_first[2][6];
     __shared__ int s_last;
     SplitWhere w;
@@ -1143,7 +1154,8 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     int *d_levels = nullptr, *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr, *d_kl_tiny = nullptr, *d_kl_split = nullptr;
     const size_t scan_n = std::max<size_t>(4 * n_max, 16);
     const unsigned split_node = rq.split_node ? std::max(rq.split_node, kTinyNode) : kSplitNodeDefault;
-    const size_t n_split_max = T / split_node + 2, split_chunks_max = T / kSplitChunk + n_split_max + 1;
+    const int split_items = T <= (1u << 20) ? 2 : 8, split_chunk = kSplitBlock * split_items;
+    const size_t n_split_max = T / split_node + 2, split_chunks_max = T / split_chunk + n_split_max + 1;
     SplitArgs sp{};
     auto layout = [&](Scratch& sc) {
         sc.alloc(&d_idx, 3 * T);
@@ -1238,13 +1250,21 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
                 sp.g = g;
                 sp.n_split = n_split;
                 // every split node is longer than split_node, so its chunks number at most T / chunk + one partial chunk per node
-                const unsigned grid = (unsigned)(T / kSplitChunk + (size_t)n_split);
-                split_prep_kernel<<<1, 1024, 0, st>>>(sp);
-                split_bin_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
-                split_count_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
-                split_rank_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
-                split_gather_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
-                split_finish_kernel<<<grid, kSplitBlock, 0, st>>>(sp);
+                const unsigned grid = (unsigned)(T / split_chunk + (size_t)n_split);
+                split_prep_kernel<<<1, 1024, 0, st>>>(sp, split_chunk);
+                if (split_items == 2) {
+                    split_bin_kernel<2><<<grid, kSplitBlock, 0, st>>>(sp);
+                    split_count_kernel<2><<<grid, kSplitBlock, 0, st>>>(sp);
+                    split_rank_kernel<2><<<grid, kSplitBlock, 0, st>>>(sp);
+                    split_gather_kernel<2><<<grid, kSplitBlock, 0, st>>>(sp);
+                    split_finish_kernel<2><<<grid, kSplitBlock, 0, st>>>(sp);
+                } else {
+                    split_bin_kernel<8><<<grid, kSplitBlock, 0, st>>>(sp);
+                    split_count_kernel<8><<<grid, kSplitBlock, 0, st>>>(sp);
+                    split_rank_kernel<8><<<grid, kSplitBlock, 0, st>>>(sp);
+                    split_gather_kernel<8><<<grid, kSplitBlock, 0, st>>>(sp);
+                    split_finish_kernel<8><<<grid, kSplitBlock, 0, st>>>(sp);
+                }
                 lc.n += 6;
             }
             // the size classes of one level touch disjoint nodes and ranges: they run side by side on up to three streams

@@ -113,7 +113,7 @@ def test_heightfield_sorted_input(cb, ob):
 
 @pytest.mark.parametrize("split_node", [64, 300, 5000, 1 << 26])
 def test_split_node_threshold_never_changes_the_buffers(cb, ob, golden_meshes, split_node):
-    """Ranges above CNDL_KNOB_BUILD_SPLIT_NODE go through the multi-CTA level step (one CTA per 2048 references, global bins,
+    """Ranges above CNDL_KNOB_BUILD_SPLIT_NODE go through the multi-CTA level step (one CTA per 512 or 2048 references, global bins,
     ranks and the Lomuto chain across CTAs), the others through the one-CTA-per-node step: same bytes for every threshold,
     from "nearly every level split" (64) to "never" (2^26), on meshes with split failures, duplicates and signed zeros."""
     from candela_b200 import scenes
