@@ -38,7 +38,7 @@ EXPORTS = [
     "cndl_intersect_primary", "cndl_intersect_primary_device", "cndl_generate_bounce_rays_device", "cndl_host_alloc", "cndl_host_alloc_write_combined", "cndl_host_free",
     "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device", "cndl_generate_rays_device", "cndl_collide_boxes", "cndl_collide_boxes_device",
     "cndl_model_load_obj", "cndl_model_load_gltf", "cndl_model_load", "cndl_model_free", "cndl_model_vertex_count", "cndl_model_index_count", "cndl_model_mesh_count", "cndl_model_vertices",
-    "cndl_model_indices", "cndl_model_mesh_ids", "cndl_model_mesh_name", "cndl_add_model", "cndl_pack_half2x16", "cndl_save", "cndl_load",
+    "cndl_model_indices", "cndl_model_mesh_ids", "cndl_model_mesh_name", "cndl_add_model", "cndl_pack_half2x16", "cndl_save", "cndl_load", "cndl_build_bvh",
 ]
 
 
@@ -86,6 +86,8 @@ def load_library() -> C.CDLL:
     L.cndl_last_error.argtypes = [vp]
     L.cndl_last_error.restype = C.c_char_p
     L.cndl_add_object.argtypes = [vp, C.c_uint32, vp, sz, vp, sz, vp, C.POINTER(BuildOpts)]
+    L.cndl_build_bvh.argtypes = [C.c_int, C.c_int, vp, sz, vp, sz, vp, C.c_int32, C.POINTER(BuildOpts), vp, sz, C.POINTER(sz), vp, C.POINTER(C.c_float)]
+    L.cndl_build_bvh.restype = C.c_int
     L.cndl_add_prebuilt_object.argtypes = [vp, C.c_uint32, vp, sz, vp, sz, vp, sz]
     for f in ("cndl_node_count", "cndl_triangle_count", "cndl_vertex_count", "cndl_entity_count"):
         getattr(L, f).argtypes = [vp]
@@ -167,6 +169,27 @@ def make_rays(origins, directions, tmax=0.0) -> np.ndarray:
     r["d"] = np.asarray(directions, dtype=np.float32).reshape(-1, 3)
     r["tmax"] = tmax
     return r
+
+
+def BuildBVH(node_format: int, verts, indices, mesh_ids=None, t_offset: int = 0, device: int = 0, builder: int = BUILDER_SAH_EXACT,
+             swap_policy: int = SWAP_NONE, swap_seed: int = 0):
+    """BVH::BuildBVH (BVHConstructor.cpp:951-1108) as a stand-alone call on the GPU: returns (nodes, triangles, build_ms) as the
+    reference leaves them in FlattenedNodes / FlattenedTris (leaf packs include t_offset, vertex indices object-local)."""
+    L = load_library()
+    verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32).ravel()
+    if mesh_ids is not None:
+        mesh_ids = np.ascontiguousarray(mesh_ids, dtype=np.int32)
+    T = len(indices) // 3
+    nodes = np.zeros(max(2 * T - 1, 1), dtype=NODE_DT if node_format == STACKLESS else STACK_NODE_DT)
+    tris = np.zeros(T, dtype=TRIANGLE_DT)
+    n, ms = C.c_size_t(0), C.c_float(0.0)
+    opts = BuildOpts(builder, swap_policy, swap_seed)
+    rc = L.cndl_build_bvh(node_format, device, _p(verts), len(verts), _p(indices), len(indices), _p(mesh_ids), t_offset, C.byref(opts), _p(nodes),
+                          len(nodes), C.byref(n), _p(tris), C.byref(ms))
+    if rc != 0:
+        raise CandelaError(rc, "cndl_build_bvh rejected the geometry or found no usable device")
+    return nodes[: n.value].copy(), tris, ms.value
 
 
 def load_model(path, first_mesh_number: int = 0):

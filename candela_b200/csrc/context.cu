@@ -90,6 +90,7 @@ struct cndl_ctx {
     void* build_arena = nullptr;
     size_t build_arena_cap = 0;
     int* build_host_counts = nullptr;
+    int tri_offset_bias = 0;  // cndl_build_bvh: BuildBVH's t_offset for a stand-alone build
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -346,7 +347,7 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     if (!ctx) return CNDL_ERR_INVALID;
     if (!verts || !indices || V == 0 || I == 0 || I % 3 != 0) return ctx->fail(CNDL_ERR_INVALID, "null or empty geometry, or index count not a multiple of 3");
     const size_t T = I / 3;
-    if (ctx->n_tris + T > (1ull << 27) || ctx->n_verts + V > 0x7FFFFFF0ull)
+    if (ctx->n_tris + T + (size_t)ctx->tri_offset_bias > (1ull << 27) || ctx->n_verts + V > 0x7FFFFFF0ull)
         return ctx->fail(CNDL_ERR_INVALID, "scene exceeds the leaf-pack limits (2^27 triangles, BVHConstructor.cpp:794)");
     cndl_build_opts o;
     std::memset(&o, 0, sizeof(o));
@@ -370,7 +371,7 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     rq.h_indices = indices;
     rq.h_mesh_ids = mesh_id_per_tri;
     rq.T = T;
-    rq.tri_offset = (int)ctx->n_tris;
+    rq.tri_offset = (int)ctx->n_tris + ctx->tri_offset_bias;
     rq.d_nodes_out = dn;
     rq.d_tris_out = reinterpret_cast<int4*>(dt);
     rq.n_nodes_out = 0;
@@ -407,6 +408,25 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     ctx->committed = false;
     return CNDL_OK;
 } CNDL_CATCH
+
+int cndl_build_bvh(int node_format, int device, const cndl_vertex* verts, size_t V, const uint32_t* indices, size_t I,
+                   const int32_t* mesh_id_per_tri, int32_t tri_offset, const cndl_build_opts* opts, void* nodes_out, size_t nodes_capacity,
+                   size_t* n_nodes_out, cndl_triangle* tris_out, float* build_ms) {
+    if (!n_nodes_out || tri_offset < 0) return CNDL_ERR_INVALID;
+    cndl_ctx* ctx = nullptr;
+    int rc = cndl_create(&ctx, node_format, device);
+    if (rc != CNDL_OK) return rc;
+    ctx->tri_offset_bias = tri_offset;
+    rc = cndl_add_object(ctx, 2, verts, V, indices, I, mesh_id_per_tri, opts);
+    if (rc == CNDL_OK) {
+        *n_nodes_out = ctx->n_nodes;
+        if (build_ms) *build_ms = ctx->last_build_ms;
+        if (nodes_out && nodes_capacity < ctx->n_nodes) rc = CNDL_ERR_INVALID;  // 2 * T - 1 always suffices
+        else rc = cndl_read_buffers(ctx, nodes_out, tris_out, nullptr);
+    }
+    cndl_destroy(ctx);
+    return rc;
+}
 
 int cndl_commit(cndl_ctx* ctx, int clear_host) try {
     (void)clear_host;  // the host never keeps a copy: the device buffers are the only ones

@@ -111,6 +111,16 @@ size_t cndl_vertex_count(const cndl_ctx* ctx);
 int cndl_get_object(const cndl_ctx* ctx, uint32_t object_id, int32_t* node_offset, int32_t* node_count,
                     int32_t* triangle_offset, int32_t* vertex_offset);
 
+/* BVH::BuildBVH (BVHConstructor.h:86-87, BVHConstructor.cpp:951-1108) as a stand-alone call, for callers that want the
+ * flattened buffers themselves: builds on GPU `device` and returns host buffers exactly as the reference's function
+ * leaves them in FlattenedNodes / FlattenedTris — leaf packs include tri_offset (its `int t_offset`), triangle records
+ * carry OBJECT-LOCAL vertex indices (the rebasing of AddObject, Intersector.h:190-197, is the caller's).  nodes_out has
+ * room for nodes_capacity nodes of the format (2 * I / 3 - 1 always suffices); *n_nodes_out = LastNodeIndex + 1.
+ * nodes_out / tris_out / build_ms may be NULL. */
+int cndl_build_bvh(int node_format, int device, const cndl_vertex* verts, size_t V, const uint32_t* indices, size_t I,
+                   const int32_t* mesh_id_per_tri, int32_t tri_offset, const cndl_build_opts* opts, void* nodes_out,
+                   size_t nodes_capacity, size_t* n_nodes_out, cndl_triangle* tris_out, float* build_ms);
+
 /* RayIntersector<T>::BufferData(bool ClearCPUData) (Intersector.h:322-351): makes everything
  * added so far visible to traversal and (re)builds the device-side acceleration copies. */
 int cndl_commit(cndl_ctx* ctx, int clear_host);

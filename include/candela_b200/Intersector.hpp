@@ -42,6 +42,64 @@ struct FlattenedStackNode { FBounds LBounds; FBounds RBounds; };  // BVHConstruc
 struct Triangle { int PackedData[4]; };                           // BVHConstructor.h:79-84
 typedef FlattenedNode StacklessTraversalNode;                     // Intersector.h:39
 typedef FlattenedStackNode StackTraversalNode;                    // Intersector.h:40
+struct Node;  // the reference returns its heap root (BVHConstructor.h:86-87), which every caller drops; here it is always null
+}  // namespace BVH
+
+namespace detail {
+// The mesh concatenation of BuildBVH (BVHConstructor.cpp:981-1002): indices + running vertex offset, vertices appended, one
+// GlobalMeshNumber per triangle.
+template <typename ObjectT>
+inline void ConcatenateMeshes(const ObjectT& object, std::vector<Vertex>& Vertices, std::vector<std::uint32_t>& MeshIndices,
+                              std::vector<std::int32_t>& MeshReferences) {
+    std::uint32_t IndexOffset = 0;
+    for (const auto& Mesh : object.m_Meshes) {
+        for (std::size_t x = 0; x < Mesh.m_Indices.size(); ++x) {
+            MeshIndices.push_back(static_cast<std::uint32_t>(Mesh.m_Indices[x]) + IndexOffset);
+            if (x % 3 == 0) MeshReferences.push_back(Mesh.GlobalMeshNumber);
+        }
+        const std::size_t at = Vertices.size();
+        Vertices.resize(at + Mesh.m_Vertices.size());
+        static_assert(sizeof(Mesh.m_Vertices[0]) == sizeof(Vertex), "Vertex must be the 32-byte record");
+        if (!Mesh.m_Vertices.empty()) std::memcpy(&Vertices[at], &Mesh.m_Vertices[0], Mesh.m_Vertices.size() * sizeof(Vertex));
+        IndexOffset += static_cast<std::uint32_t>(Mesh.m_Vertices.size());
+    }
+}
+template <typename NodeT, typename ObjectT>
+inline BVH::Node* BuildBVH(int Format, const ObjectT& object, std::vector<NodeT>& FlattenedNodes, std::vector<Vertex>& MeshVertices,
+                           std::vector<BVH::Triangle>& FlattenedTris, int t_offset, int Device, const cndl_build_opts* Options) {
+    std::vector<std::uint32_t> MeshIndices;
+    std::vector<std::int32_t> MeshReferences;
+    const std::size_t FirstVertex = MeshVertices.size();
+    ConcatenateMeshes(object, MeshVertices, MeshIndices, MeshReferences);
+    const std::size_t T = MeshIndices.size() / 3;
+    if (T == 0) throw std::string("candela_b200: BuildBVH on an object without triangles");
+    FlattenedNodes.resize(2 * T - 1);
+    FlattenedTris.resize(T);
+    std::size_t N = 0;
+    const int rc = cndl_build_bvh(Format, Device, reinterpret_cast<const cndl_vertex*>(MeshVertices.data() + FirstVertex),
+                                  MeshVertices.size() - FirstVertex, MeshIndices.data(), MeshIndices.size(), MeshReferences.data(), t_offset,
+                                  Options, FlattenedNodes.data(), FlattenedNodes.size(), &N, reinterpret_cast<cndl_triangle*>(FlattenedTris.data()),
+                                  nullptr);
+    if (rc != CNDL_OK) throw std::string("candela_b200: cndl_build_bvh failed with status ") + std::to_string(rc);
+    FlattenedNodes.resize(N);
+    return nullptr;
+}
+}  // namespace detail
+
+namespace BVH {
+// BVH::BuildBVH (BVHConstructor.h:86-87; .cpp:951-1028 stackless, :1032-1108 stack), built on the GPU, buffers byte-identical:
+// fills FlattenedNodes (leaf packs include t_offset) and FlattenedTris (object-local vertex indices), appends the object's
+// vertices to MeshVertices.
+template <typename ObjectT>
+inline Node* BuildBVH(const ObjectT& object, std::vector<FlattenedNode>& FlattenedNodes, std::vector<Vertex>& MeshVertices,
+                      std::vector<Triangle>& FlattenedTris, int t_offset, int Device = 0, const cndl_build_opts* Options = nullptr) {
+    return detail::BuildBVH(CNDL_STACKLESS, object, FlattenedNodes, MeshVertices, FlattenedTris, t_offset, Device, Options);
+}
+template <typename ObjectT>
+inline Node* BuildBVH(const ObjectT& object, std::vector<FlattenedStackNode>& FlattenedNodes, std::vector<Vertex>& MeshVertices,
+                      std::vector<Triangle>& FlattenedTris, int t_offset, int Device = 0, const cndl_build_opts* Options = nullptr) {
+    return detail::BuildBVH(CNDL_STACK, object, FlattenedNodes, MeshVertices, FlattenedTris, t_offset, Device, Options);
+}
 }  // namespace BVH
 
 struct BVHEntity {  // Intersector.h:43-49
@@ -89,18 +147,7 @@ public:
         std::vector<Vertex> Vertices;
         std::vector<std::uint32_t> MeshIndices;
         std::vector<std::int32_t> MeshReferences;
-        std::uint32_t IndexOffset = 0;
-        for (const auto& Mesh : object.m_Meshes) {
-            for (std::size_t x = 0; x < Mesh.m_Indices.size(); ++x) {
-                MeshIndices.push_back(static_cast<std::uint32_t>(Mesh.m_Indices[x]) + IndexOffset);
-                if (x % 3 == 0) MeshReferences.push_back(Mesh.GlobalMeshNumber);
-            }
-            const std::size_t at = Vertices.size();
-            Vertices.resize(at + Mesh.m_Vertices.size());
-            static_assert(sizeof(Mesh.m_Vertices[0]) == sizeof(Vertex), "Vertex must be the 32-byte record");
-            if (!Mesh.m_Vertices.empty()) std::memcpy(&Vertices[at], &Mesh.m_Vertices[0], Mesh.m_Vertices.size() * sizeof(Vertex));
-            IndexOffset += static_cast<std::uint32_t>(Mesh.m_Vertices.size());
-        }
+        detail::ConcatenateMeshes(object, Vertices, MeshIndices, MeshReferences);
         Check(cndl_add_object(m_Ctx, static_cast<std::uint32_t>(object.GetID()), reinterpret_cast<const cndl_vertex*>(Vertices.data()),
                               Vertices.size(), MeshIndices.data(), MeshIndices.size(), MeshReferences.data(), Options));
     }

@@ -4,6 +4,7 @@
 // backend has no CPU fallback).  The Object/Mesh/Entity structs below stand in for the engine's.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "candela_b200/Intersector.hpp"
@@ -84,6 +85,22 @@ int main() {
         const float bmin[3] = {0.5f, -0.2f, 0.5f}, bmax[3] = {0.8f, 0.2f, 0.8f};
         std::printf("EXTRA data=%d collide=%d%d%d\n", n_data, (int)Candela::Physics::CollidePoint(on_floor, Intersector),
                     (int)Candela::Physics::CollidePoint(in_air, Intersector), (int)Candela::Physics::CollideBox(bmin, bmax, Intersector));
+        // BVH::BuildBVH as a free function (BVHConstructor.h:86-87): same bytes as the intersector's own buffers for its first object
+        {
+            std::vector<Candela::BVH::FlattenedNode> Nodes;
+            std::vector<Candela::Vertex> Vertices;
+            std::vector<Candela::BVH::Triangle> Triangles;
+            Candela::BVH::Node* Root = Candela::BVH::BuildBVH(obj, Nodes, Vertices, Triangles, 0);
+            const bool same = Root == nullptr && Nodes.size() == Intersector.m_BVHNodes.size() && Triangles.size() == Intersector.m_BVHTriangles.size() &&
+                              Vertices.size() == Intersector.m_BVHVertices.size() &&
+                              std::memcmp(Nodes.data(), Intersector.m_BVHNodes.data(), Nodes.size() * sizeof(Nodes[0])) == 0 &&
+                              std::memcmp(Triangles.data(), Intersector.m_BVHTriangles.data(), Triangles.size() * sizeof(Triangles[0])) == 0;
+            std::vector<Candela::BVH::FlattenedStackNode> StackNodes;
+            std::vector<Candela::Vertex> V2;
+            std::vector<Candela::BVH::Triangle> T2;
+            Candela::BVH::BuildBVH(obj, StackNodes, V2, T2, 1000);
+            std::printf("BUILDBVH same=%d stack_nodes=%zu tris=%zu\n", (int)same, StackNodes.size(), T2.size());
+        }
         // pushing an entity of an unknown object must throw the reference's message
         Object other;
         other.m_ObjectID = 77;

@@ -38,4 +38,6 @@ def test_mirror_runs_the_reference_call_sequence():
     assert n_hit > 90 and abs(total - 3.0 * n_hit) < 1e-3      # floor at y = 0, rays from y = 3 straight down
     extra = [l for l in lines if l.startswith("EXTRA ")][0].split()
     assert extra[1] == f"data={n_hit}" and extra[2] == "collide=101"          # floor point collides, air point does not, box does
+    build = [l for l in lines if l.startswith("BUILDBVH ")][0].split()
+    assert build[1] == "same=1" and build[3] == "tris=576"                    # BVH::BuildBVH free function: same bytes as AddObject's buffers
     assert "THROW Trying to push entity whose parent object hasn't been added to global BVH" in p.stdout

@@ -139,6 +139,23 @@ def test_split_node_threshold_never_changes_the_buffers(cb, ob, golden_meshes, s
         ri.close()
 
 
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_build_bvh_free_function_with_triangle_offset(cb, ob, golden_meshes, fmt):
+    """cndl_build_bvh == BVH::BuildBVH(object, nodes, vertices, triangles, t_offset) (BVHConstructor.h:86-87): the leaf packs carry
+    t_offset, the triangle records keep object-local vertex indices."""
+    P, F = golden_meshes["peach_castle"]
+    V = ob.make_vertices(P)
+    mids = (np.arange(len(F)) % 3).astype(np.int32)
+    for t_offset in (0, 12345):
+        ref = ob.build(fmt_id(ob, fmt), V, F.ravel(), mids, t_offset=t_offset)
+        nodes, tris, ms = cb.BuildBVH(fmt_id(ob, fmt), V, F.ravel(), mids, t_offset=t_offset)
+        assert ms > 0 and len(nodes) == len(ref.nodes)
+        assert tris.tobytes() == ref.tris.tobytes(), first_diff(tris, ref.tris)
+        assert nodes.tobytes() == ref.nodes.tobytes(), first_diff(nodes, ref.nodes)
+    with pytest.raises(cb.CandelaError):
+        cb.BuildBVH(fmt_id(ob, fmt), V, F.ravel()[:-1], None)
+
+
 def test_bad_geometry_rejected(cb):
     ri = cb.RayIntersector(cb.STACKLESS)
     V = cb.make_vertices(np.zeros((3, 3), np.float32))
