@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libcandela_b200.so"
-SOURCES = ["context.cu", "kernels_traverse.cu", "kernels_wavefront.cu", "kernels_raygen.cu", "kernels_hot.cu", "builder.cu", "model_loader.cu"]
+SOURCES = ["context.cu", "kernels_traverse.cu", "kernels_wavefront.cu", "kernels_raygen.cu", "kernels_hot.cu", "builder.cu", "builder_lbvh.cu", "ray_order.cu", "model_loader.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",

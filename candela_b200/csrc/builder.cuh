@@ -34,4 +34,13 @@ size_t ray_sort_scratch_ints(size_t R);
 cudaError_t sort_rays_morton(const cndl_ray* rays, size_t R, const float lo[3], const float hi[3], unsigned* order_out, int* scratch, cudaStream_t st,
                              LaunchCounter& lc);
 
+// Morton helper shared by the LBVH builder and the ray ordering
+static __device__ __forceinline__ unsigned expand10(unsigned v) {  // 10 bits -> every third bit
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
 }  // namespace cndl
