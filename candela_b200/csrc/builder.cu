@@ -808,39 +808,6 @@ __global__ void __launch_bounds__(kSplitBlock) split_finish_kernel(SplitArgs s) 
     if (tid == 0) finish_parent(s.g, w.k, w.id, start, len);
 }
 
-// flags for the nodes of one level, one run of n per size class: [0,n) split, [n,2n) big, [2n,3n) small, [3n,4n) tiny
-__global__ void classify_kernel(const unsigned* nlen, int base, int n, unsigned split_node, int* flags) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned len = nlen[base + i];
-    const bool split = len > split_node;
-    flags[i] = split ? 1 : 0;
-    flags[n + i] = (!split && len > kBigNode) ? 1 : 0;
-    flags[2 * n + i] = (!split && len > kTinyNode && len <= kBigNode) ? 1 : 0;
-    flags[3 * n + i] = (!split && len > kMaxLeaf && len <= kTinyNode) ? 1 : 0;
-}
-
-// offsets = exclusive scan of flags.  Writes the ordered active list and, per size class, the list of
-// positions in it.
-__global__ void compact_kernel(const int* flags, const int* offsets, const int* total, int base, int n, int* active, int* klist_split,
-                               int* klist_big, int* klist_small, int* klist_tiny, int* class_counts /* mapped host memory */) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (i == 0) {
-        class_counts[0] = offsets[n];
-        class_counts[1] = offsets[2 * n] - offsets[n];
-        class_counts[2] = offsets[3 * n] - offsets[2 * n];
-        class_counts[3] = *total - offsets[3 * n];
-    }
-    const int off_split = offsets[i], off_big = offsets[n + i] - offsets[n], off_small = offsets[2 * n + i] - offsets[2 * n],
-              off_tiny = offsets[3 * n + i] - offsets[3 * n];
-    const int k = off_split + off_big + off_small + off_tiny;
-    if (flags[i]) { active[k] = base + i; klist_split[off_split] = k; }
-    if (flags[n + i]) { active[k] = base + i; klist_big[off_big] = k; }
-    if (flags[2 * n + i]) { active[k] = base + i; klist_small[off_small] = k; }
-    if (flags[3 * n + i]) { active[k] = base + i; klist_tiny[off_tiny] = k; }
-}
-
 // classify + scan + compact of a level of at most kSmallLevel nodes in one CTA (one launch instead of five)
 constexpr int kSmallLevel = 4096, kMaxRunLevels = 2048;
 __global__ void __launch_bounds__(1024) level_compact_small_kernel(const unsigned* nlen, int base, int n, unsigned split_node, int* active,
@@ -876,6 +843,79 @@ __global__ void __launch_bounds__(1024) level_compact_small_kernel(const unsigne
         ++k;
     }
     if (tid == 0) { class_counts[0] = t0; class_counts[1] = t1; class_counts[2] = t2; class_counts[3] = t3; }
+}
+
+// The same for larger levels in ONE pass: tiles of 1024 nodes, chained by decoupled look-back over the four class counts
+// (replaces classify + three scan launches + compact, ~25 us of serial launches per level).  Tiles take their index from
+// a ticket, so a tile only ever waits for tiles that are already running.  Tile states carry the level number (epoch)
+// instead of being cleared between levels; the last tile publishes the class sizes and resets the ticket.
+struct TileState { int status; int agg[4]; int incl[4]; };
+constexpr int kCompactTile = 1024;
+__global__ void __launch_bounds__(256) level_compact_chained_kernel(const unsigned* nlen, int base, int n, unsigned split_node, int* active,
+                                                                    int* klist_split, int* klist_big, int* klist_small, int* klist_tiny,
+                                                                    int* class_counts /* mapped host memory */, TileState* tiles, int* ticket,
+                                                                    int epoch) {
+    __shared__ int s_warp[256 / 32 + 1];
+    __shared__ int s_tile, s_prefix[4];
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int tile = s_tile, n_tiles = (n + kCompactTile - 1) / kCompactTile;
+    int cls[4], c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = tile * kCompactTile + tid * 4 + j;
+        cls[j] = -1;
+        if (i < n) {
+            const unsigned len = nlen[base + i];
+            cls[j] = len > split_node ? 0 : (len > kBigNode ? 1 : (len > kTinyNode ? 2 : (len > kMaxLeaf ? 3 : -1)));
+        }
+        c0 += cls[j] == 0; c1 += cls[j] == 1; c2 += cls[j] == 2; c3 += cls[j] == 3;
+    }
+    int t[4];
+    int o0 = block_exclusive_scan<256>(c0, s_warp, t[0]);
+    int o1 = block_exclusive_scan<256>(c1, s_warp, t[1]);
+    int o2 = block_exclusive_scan<256>(c2, s_warp, t[2]);
+    int o3 = block_exclusive_scan<256>(c3, s_warp, t[3]);
+    if (tid == 0) {
+        const int have_agg = 2 * epoch + 1, have_incl = 2 * epoch + 2;
+        int pre[4] = {0, 0, 0, 0};
+        if (tile > 0) {
+            for (int c = 0; c < 4; ++c) tiles[tile].agg[c] = t[c];
+            __threadfence();
+            *reinterpret_cast<volatile int*>(&tiles[tile].status) = have_agg;
+            for (int p = tile - 1; p >= 0; --p) {
+                int st;
+                do { st = *reinterpret_cast<volatile int*>(&tiles[p].status); } while (st < have_agg);
+                __threadfence();
+                if (st == have_incl) {
+                    for (int c = 0; c < 4; ++c) pre[c] += __ldcg(&tiles[p].incl[c]);
+                    break;
+                }
+                for (int c = 0; c < 4; ++c) pre[c] += __ldcg(&tiles[p].agg[c]);
+            }
+        }
+        for (int c = 0; c < 4; ++c) { tiles[tile].incl[c] = pre[c] + t[c]; s_prefix[c] = pre[c]; }
+        __threadfence();
+        *reinterpret_cast<volatile int*>(&tiles[tile].status) = have_incl;
+        if (tile == n_tiles - 1) {
+            for (int c = 0; c < 4; ++c) class_counts[c] = pre[c] + t[c];
+            *ticket = 0;  // every tile has taken its ticket by now
+        }
+    }
+    __syncthreads();
+    o0 += s_prefix[0]; o1 += s_prefix[1]; o2 += s_prefix[2]; o3 += s_prefix[3];
+    int k = o0 + o1 + o2 + o3;  // active nodes before this thread's first one, in level order
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (cls[j] < 0) continue;
+        active[k] = base + tile * kCompactTile + tid * 4 + j;
+        if (cls[j] == 0) klist_split[o0++] = k;
+        else if (cls[j] == 1) klist_big[o1++] = k;
+        else if (cls[j] == 2) klist_small[o2++] = k;
+        else klist_tiny[o3++] = k;
+        ++k;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -973,6 +1013,8 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     uint32_t* d_idx = nullptr;
     int32_t* d_mesh = nullptr;
     unsigned char* d_flip = nullptr;
+    TileState* d_tiles = nullptr;
+    int* d_ticket = nullptr;
     int *d_levels = nullptr, *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr, *d_kl_tiny = nullptr, *d_kl_split = nullptr;
     const size_t scan_n = std::max<size_t>(4 * n_max, 16);
     const unsigned split_node = rq.split_node ? std::max(rq.split_node, kTinyNode) : kSplitNodeDefault;
@@ -991,6 +1033,7 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
         sc.alloc(&d_block_sums, scan_n / kScanTile + 2); sc.alloc(&d_totals, 4);
         sc.alloc(&d_active, n_max); sc.alloc(&d_active_next, n_max); sc.alloc(&d_kl_big, n_max); sc.alloc(&d_kl_small, n_max); sc.alloc(&d_kl_tiny, n_max);
         sc.alloc(&d_kl_split, n_split_max); sc.alloc(&d_levels, 2 * (size_t)kMaxRunLevels);
+        sc.alloc(&d_tiles, n_max / kCompactTile + 2); sc.alloc(&d_ticket, 1);
         sc.alloc(&sp.chunk_base, n_split_max + 1); sc.alloc(&sp.bins, n_split_max * kBinInts); sc.alloc(&sp.done, n_split_max * 3);
         sc.alloc(&sp.split, n_split_max * 4); sc.alloc(&sp.boxes, n_split_max * 24); sc.alloc(&sp.chunk_l, split_chunks_max);
         sc.alloc(&sp.rankflag, T); sc.alloc(&sp.rpos, T); sc.alloc(&sp.alt, T);
@@ -1036,6 +1079,8 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     const int h_root_init[12] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000, -1, -1, -1, -1, -1, -1};
     BK(cudaMemcpyAsync(a.root_scratch, h_root_init, sizeof(h_root_init), cudaMemcpyHostToDevice, st));
     BK(cudaMemsetAsync(d_flip, 0, n_max, st));
+    BK(cudaMemsetAsync(d_tiles, 0, (n_max / kCompactTile + 2) * sizeof(TileState), st));
+    BK(cudaMemsetAsync(d_ticket, 0, sizeof(int), st));
     tri_precompute_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(a);
     root_finalize_kernel<<<1, 32, 0, st>>>(a);
     lc.n += 2;
@@ -1123,11 +1168,10 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
                                                                d_counts);
                 lc.n++;
             } else {
-                classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.nlen, base, n, split_node, d_flags);
-                exclusive_scan(d_flags, 4 * n, d_offsets, d_block_sums, d_totals, st, lc);
-                compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_flags, d_offsets, d_totals, base, n, d_active_next, d_kl_split, d_kl_big, d_kl_small,
-                                                                d_kl_tiny, d_counts);
-                lc.n += 2;
+                level_compact_chained_kernel<<<(n + kCompactTile - 1) / kCompactTile, 256, 0, st>>>(
+                    a.nlen, base, n, split_node, d_active_next, d_kl_split, d_kl_big, d_kl_small, d_kl_tiny, d_counts, d_tiles, d_ticket,
+                    (int)level_base.size());
+                lc.n++;
             }
             BK(cudaStreamSynchronize(st));
             n_split = h_counts[0];
