@@ -93,3 +93,102 @@ def test_chain_length_with_and_without_run_jumping():
         for p_left in (0.1, 0.5, 0.9, 0.99):
             f = list((rng.random(n) < p_left).astype(int))
             assert closed_form(f, True)[2] <= 2 * math.isqrt(2 * n) + 2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The bin-free split search of level_step_tiny_kernel (ranges of <= 9 references) against the sequential search of
+# SearchSAHPlaneBinned (BVHConstructor.cpp:276-363), both restated in float32 numpy (no FMA, like -ffp-contract=off).
+F = np.float32
+BINS = 64
+SENT_MAX, SENT_MIN, INF_COST = F(10000000.0), F(-10000000.0), F(1e29)
+
+
+def _area(mn, mx):
+    e = mx - mn                                            # Bounds::GetArea, BVHConstructor.h:41-44
+    return F(F(e[0] * e[1]) + F(e[1] * e[2])) + F(e[2] * e[0])
+
+
+def _bin_of(c, lo, scale):
+    return min(BINS - 1, max(0, int(F(F(c - lo) * scale))))
+
+
+def sequential_search(node_mn, node_mx, boxes_mn, boxes_mx, cents):
+    best, axis, border = INF_COST, 0, node_mn[0]
+    for ax in range(3):
+        lo, hi = node_mn[ax], node_mx[ax]
+        if lo == hi:
+            continue
+        extent = F(hi - lo)
+        scale = F(F(BINS) / extent)
+        cnt = np.zeros(BINS, int)
+        bmn = np.full((BINS, 3), SENT_MAX, F)
+        bmx = np.full((BINS, 3), SENT_MIN, F)
+        for k in range(len(cents)):
+            b = _bin_of(cents[k][ax], lo, scale)
+            cnt[b] += 1
+            bmn[b] = np.minimum(bmn[b], boxes_mn[k])
+            bmx[b] = np.maximum(bmx[b], boxes_mx[k])
+        step = F(extent / F(BINS))
+        for i in range(BINS - 1):
+            lmn, lmx = bmn[: i + 1].min(0), bmx[: i + 1].max(0)
+            rmn, rmx = bmn[i + 1:].min(0), bmx[i + 1:].max(0)
+            cost = F(F(F(int(cnt[: i + 1].sum())) * _area(lmn, lmx)) + F(F(int(cnt[i + 1:].sum())) * _area(rmn, rmx)))
+            if cost < best:
+                best, axis, border = cost, ax, F(lo + F(step * F(i + 1)))
+    return axis, border
+
+
+def candidate_search(node_mn, node_mx, boxes_mn, boxes_mx, cents):
+    """One (axis, candidate) pair per lane: candidates are i = 0 and the references' own bins; minimum over (cost, axis, i)."""
+    pairs = []
+    n = len(cents)
+    for ax in range(3):
+        lo, hi = node_mn[ax], node_mx[ax]
+        if lo == hi:
+            continue
+        extent = F(hi - lo)
+        scale = F(F(BINS) / extent)
+        bins = [_bin_of(cents[k][ax], lo, scale) for k in range(n)]
+        for ci in [0] + bins:
+            if ci >= BINS - 1:
+                continue
+            left = [k for k in range(n) if bins[k] <= ci]
+            right = [k for k in range(n) if bins[k] > ci]
+
+            def side(idx):
+                if not idx:
+                    return 0, np.full(3, SENT_MAX, F), np.full(3, SENT_MIN, F)
+                return len(idx), boxes_mn[idx].min(0), boxes_mx[idx].max(0)
+            (nl, lmn, lmx), (nr, rmn, rmx) = side(left), side(right)
+            cost = F(F(F(nl) * _area(lmn, lmx)) + F(F(nr) * _area(rmn, rmx)))
+            if cost == cost:
+                pairs.append((cost, ax, ci, F(lo + F(F(extent / F(BINS)) * F(ci + 1)))))
+    if not pairs:
+        return 0, node_mn[0]
+    cost, ax, ci, border = min(pairs, key=lambda p: (p[0], p[1], p[2]))
+    return (ax, border) if cost < INF_COST else (0, node_mn[0])
+
+
+def _random_range(rng, n, kind):
+    c = rng.uniform(-4, 4, size=(n, 3)).astype(F)
+    if kind == "duplicates":
+        c[:] = c[0]
+    elif kind == "flat":
+        c[:, 1] = F(0.5)                                   # all boxes in one plane: that axis may be degenerate
+    elif kind == "lattice":
+        c = np.round(c).astype(F)                          # many equal centroids and equal costs
+    half = rng.uniform(0, 0.6, size=(n, 3)).astype(F) if kind != "flat" else np.abs(rng.normal(0, 0.3, (n, 3))).astype(F) * np.array([1, 0, 1], F)
+    mn, mx = (c - half).astype(F), (c + half).astype(F)
+    cents = ((mn + mx) / F(2)).astype(F)                   # Bounds::GetCenter
+    return mn.min(0), mx.max(0), mn, mx, cents
+
+
+@pytest.mark.parametrize("kind", ["random", "duplicates", "flat", "lattice"])
+def test_candidate_split_search_equals_the_sequential_search(kind):
+    rng = np.random.default_rng(11)
+    for trial in range(150):
+        n = int(rng.integers(3, 10))
+        node_mn, node_mx, mn, mx, cents = _random_range(rng, n, kind)
+        want = sequential_search(node_mn, node_mx, mn, mx, cents)
+        got = candidate_search(node_mn, node_mx, mn, mx, cents)
+        assert got[0] == want[0] and got[1].tobytes() == want[1].tobytes(), (kind, trial, got, want)
