@@ -53,6 +53,12 @@ def test_no_gpu_means_no_context(lib):
     from candela_b200 import CandelaError, RayIntersector
     with pytest.raises(CandelaError):
         RayIntersector()
+    # the stand-alone BuildBVH has no CPU path either
+    import numpy as np
+    from candela_b200 import BuildBVH, STACKLESS, make_vertices
+    with pytest.raises(CandelaError) as e:
+        BuildBVH(STACKLESS, make_vertices(np.eye(3, dtype=np.float32)), np.arange(3, dtype=np.uint32))
+    assert e.value.code == -3
 
 
 def test_bad_node_format_rejected(lib):
