@@ -1016,7 +1016,7 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     TileState* d_tiles = nullptr;
     int* d_ticket = nullptr;
     int *d_levels = nullptr, *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr, *d_kl_tiny = nullptr, *d_kl_split = nullptr;
-    const size_t scan_n = std::max<size_t>(4 * n_max, 16);
+    const size_t scan_n = std::max<size_t>(n_max, 16);  // inner-node flags of the stack flatten (the level compaction scans in its own kernels)
     const unsigned split_node = rq.split_node ? std::max(rq.split_node, kTinyNode) : kSplitNodeDefault;
     const int split_items = T <= (1u << 20) ? 2 : 8, split_chunk = kSplitBlock * split_items;
     const size_t n_split_max = T / split_node + 2, split_chunks_max = T / split_chunk + n_split_max + 1;
