@@ -192,3 +192,19 @@ def test_candidate_split_search_equals_the_sequential_search(kind):
         want = sequential_search(node_mn, node_mx, mn, mx, cents)
         got = candidate_search(node_mn, node_mx, mn, mx, cents)
         assert got[0] == want[0] and got[1].tobytes() == want[1].tobytes(), (kind, trial, got, want)
+
+
+def test_closed_form_on_arbitrary_flag_strings():
+    """Property check (hypothesis): any flag string, with and without run jumping."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.booleans(), max_size=300))
+    def check(flags):
+        want, mid = lomuto(flags)
+        for jumping in (False, True):
+            got, n_left, _ = closed_form(flags, jumping)
+            assert (got, n_left) == (want, mid)
+
+    check()
