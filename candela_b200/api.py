@@ -39,6 +39,7 @@ EXPORTS = [
     "cndl_set_traversal_mode", "cndl_set_tuning", "cndl_launch_count", "cndl_last_build_ms", "cndl_get_data", "cndl_get_data_device", "cndl_generate_rays_device", "cndl_collide_boxes", "cndl_collide_boxes_device",
     "cndl_model_load_obj", "cndl_model_load_gltf", "cndl_model_load", "cndl_model_free", "cndl_model_vertex_count", "cndl_model_index_count", "cndl_model_mesh_count", "cndl_model_vertices",
     "cndl_model_indices", "cndl_model_mesh_ids", "cndl_model_mesh_name", "cndl_add_model", "cndl_pack_half2x16", "cndl_save", "cndl_load", "cndl_build_bvh",
+    "cndl_generate_probe_rays_device",
 ]
 
 
@@ -56,7 +57,7 @@ GEN_BUCKET_OCTANTS = 1
 class RaygenParams(C.Structure):
     """cndl_raygen_params (include/candela_b200.h)."""
     _fields_ = [("kind", C.c_int32), ("spp", C.c_int32), ("seed", C.c_uint32), ("flags", C.c_uint32), ("offset", C.c_float), ("tmax", C.c_float),
-                ("roughness", C.c_float), ("light_dir", C.c_float * 3), ("light_cone", C.c_float)]
+                ("roughness", C.c_float), ("light_dir", C.c_float * 3), ("light_cone", C.c_float), ("d_ids_in", C.c_void_p), ("d_ids_out", C.c_void_p)]
 
 
 class BuildOpts(C.Structure):
@@ -109,6 +110,7 @@ def load_library() -> C.CDLL:
     L.cndl_get_data.argtypes = [vp, vp, sz, vp]
     L.cndl_get_data_device.argtypes = [vp, vp, sz, vp, vp]
     L.cndl_generate_rays_device.argtypes = [vp, C.POINTER(RaygenParams), vp, vp, sz, vp, vp, C.POINTER(sz), vp]
+    L.cndl_generate_probe_rays_device.argtypes = [vp, vp, vp, vp, C.c_uint32, vp, vp]
     L.cndl_collide_boxes.argtypes = [vp, vp, sz, vp]
     L.cndl_collide_boxes_device.argtypes = [vp, vp, sz, vp, vp]
     for f in ("cndl_model_load_obj", "cndl_model_load_gltf", "cndl_model_load"):
@@ -433,13 +435,21 @@ class RayIntersector:
 
     def generate_rays_device(self, kind: int, d_rays: int, d_hits: int, n_rays: int, d_rays_out: int, spp: int = 1, offset: float = 0.05,
                              tmax: float = 1.0e6, seed: int = 1, roughness: float = 0.0, light_dir=(0.0, 1.0, 0.0), light_cone: float = 0.0,
-                             bucket_octants: bool = False, d_parent_out: int = 0, stream: int = 0) -> int:
+                             bucket_octants: bool = False, d_parent_out: int = 0, stream: int = 0, d_ids_in: int = 0, d_ids_out: int = 0) -> int:
         """Diffuse / specular / shadow rays from the hits of the previous batch (cndl_generate_rays_device); returns the count."""
-        p = RaygenParams(kind, spp, seed, GEN_BUCKET_OCTANTS if bucket_octants else 0, offset, tmax, roughness, (C.c_float * 3)(*light_dir), light_cone)
+        p = RaygenParams(kind, spp, seed, GEN_BUCKET_OCTANTS if bucket_octants else 0, offset, tmax, roughness, (C.c_float * 3)(*light_dir), light_cone,
+                         d_ids_in or None, d_ids_out or None)
         n = C.c_size_t(0)
         self._check(self._lib.cndl_generate_rays_device(self._h, C.byref(p), d_rays, d_hits, n_rays, d_rays_out, d_parent_out or None, C.byref(n),
                                                         stream or None))
         return int(n.value)
+
+    def generate_probe_rays_device(self, box_origin, size, res, seed: int, d_rays_out: int, stream: int = 0):
+        """Probe-update rays (UpdateRadianceProbes.glsl:408-427) for a res[0] x res[1] x res[2] probe grid."""
+        o = np.ascontiguousarray(box_origin, dtype=np.float32)
+        sz = np.ascontiguousarray(size, dtype=np.float32)
+        r = np.ascontiguousarray(res, dtype=np.int32)
+        self._check(self._lib.cndl_generate_probe_rays_device(self._h, _p(o), _p(sz), _p(r), seed, d_rays_out, stream or None))
 
     def intersect_primary_device(self, inv_view, inv_proj, Width: int, Height: int, d_hits: int, d_rays: int = 0, stream: int = 0):
         iv, ip = _colmajor(inv_view), _colmajor(inv_proj)

@@ -1,117 +1,10 @@
 // C ABI of libcandela_b200.so (include/candela_b200.h): the state RayIntersector<T> keeps
 // (Source/Core/BVH/Intersector.h:60-124) held in device memory, plus the query entry points.
-#include <cstdio>
-#include <cstring>
-#include <algorithm>
-#include <array>
-#include <new>
-#include <string>
-#include <unordered_map>
-#include <vector>
-
-#include "builder.cuh"
-#include "kernels.cuh"
+#include "context.cuh"
 
 using namespace cndl;
 
-namespace {
-
-struct DeviceBuffer {
-    void* p = nullptr;
-    size_t bytes = 0, cap = 0;
-    ~DeviceBuffer() { if (p) cudaFree(p); }
-    // grows keeping the contents
-    cudaError_t reserve(size_t want, cudaStream_t st) {
-        if (want <= cap) return cudaSuccess;
-        size_t ncap = cap ? cap : 4096;
-        while (ncap < want) ncap *= 2;
-        void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, ncap);
-        if (e != cudaSuccess) return e;
-        if (bytes) e = cudaMemcpyAsync(q, p, bytes, cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (p) cudaFree(p);
-        p = q;
-        cap = ncap;
-        return e;
-    }
-    // contents not preserved
-    cudaError_t ensure_scratch(size_t want) {
-        if (want <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-};
-
-struct ObjectData { int tri_offset, vert_offset, node_offset, node_count, tri_count, vert_count; };  // _ObjectData, Intersector.h:51-56 (+ counts)
-
-}  // namespace
-
-struct cndl_ctx {
-    int format = CNDL_STACKLESS;
-    int device = 0;
-    int sm_count = 148;
-    size_t node_size = 32;
-    std::string err;
-
-    // m_BVHNodes / m_BVHTriangles / m_BVHVertices (device-resident) and their element counts
-    DeviceBuffer nodes, tris, verts, tri48, ents;
-    size_t n_nodes = 0, n_tris = 0, n_verts = 0;
-    size_t committed_nodes = 0, committed_tris = 0;  // m_NodeCountBuffered
-    bool committed = false;
-    std::unordered_map<uint32_t, ObjectData> objects;
-
-    std::vector<cndl_entity> staged;  // m_Entities
-    size_t n_ents = 0;                 // m_EntityPushed
-    bool ents_buffered = false;
-
-    // query scratch
-    DeviceBuffer d_rays, d_hits, d_order, d_keys, d_sort_tmp, d_counter, d_chunk_counters;
-    std::vector<cudaEvent_t> events;
-    cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};  // H2D, traversal (even chunks), D2H, traversal (odd chunks)
-    cudaStream_t main_stream = nullptr;
-    int mode = 2, sort_rays = 0;   // sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order
-    float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};  // bounds of all entities (for sort_rays = 2)
-    int knobs[9] = {8, 14, 10, 0, 0, 12, 4096, 1024, 0};  // CNDL_KNOB_*
-    // hot-first derived layout of the stackless nodes (kernels_hot.cu), rebuilt by cndl_commit
-    DeviceBuffer nodes2, perm, ents2, hot_scratch, d_objects;
-    std::vector<int2> h_objects;                 // (node_offset, node_count) in insertion order
-    std::vector<int> h_roots;                    // root of each object in nodes2
-    std::vector<cndl_entity> buffered;           // the entity records last uploaded
-    int n_hot = 0;
-    bool hot_ready = false, hot_entities_ok = false;
-    bool nodes_valid = false, entities_regular = false;  // links / slots / leaf ranges in bounds; every entity names a whole object
-    LaunchCounter launches;
-    float last_build_ms = 0.0f;
-    void* build_arena = nullptr;
-    size_t build_arena_cap = 0;
-    int* build_host_counts = nullptr;
-    int tri_offset_bias = 0;  // cndl_build_bvh: BuildBVH's t_offset for a stand-alone build
-
-    int fail(int code, const std::string& msg) { err = msg; return code; }
-    int cuda_fail(cudaError_t e, const char* what) {
-        err = std::string(what) + ": " + cudaGetErrorString(e);
-        return e == cudaErrorMemoryAllocation ? CNDL_ERR_OOM : CNDL_ERR_CUDA;
-    }
-};
-
-// Nothing may throw across the C boundary (std::vector / std::string / unordered_map allocate): every entry point that
-// allocates is a function-try-block ending in CNDL_CATCH.
-#define CNDL_CATCH                                        \
-    catch (const std::bad_alloc&) { return CNDL_ERR_OOM; } \
-    catch (...) { return CNDL_ERR_INVALID; }
-
-#define CK(call)                                                   \
-    do {                                                           \
-        cudaError_t e__ = (call);                                  \
-        if (e__ != cudaSuccess) return ctx->cuda_fail(e__, #call); \
-    } while (0)
-
-namespace {
+namespace cndl {
 
 SceneView scene_view(const cndl_ctx* ctx) {
     SceneView s;
@@ -126,7 +19,7 @@ SceneView scene_view(const cndl_ctx* ctx) {
 
 // Entity records for the derived layout: node_offset becomes the root's index in nodes2.  Every
 // record must name an object's whole node range, as PushEntity produces (Intersector.h:210-211).
-int upload_hot_entities(cndl_ctx* ctx) {
+static int upload_hot_entities(cndl_ctx* ctx) {
     ctx->hot_entities_ok = false;
     ctx->entities_regular = false;
     if (!ctx->nodes_valid) return CNDL_OK;
@@ -152,18 +45,27 @@ int check_ready(cndl_ctx* ctx) {
     return CNDL_OK;
 }
 
+// 64-byte work-counter slots handed out round-robin: two device calls in flight on different streams never share one
+// (a slot is reused after kCounterSlots further calls on the context).
+unsigned* next_counter(cndl_ctx* ctx) {
+    unsigned* p = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->d_counter.p) + 256 + 64 * (size_t)(ctx->counter_next % kCounterSlots));
+    ctx->counter_next++;
+    return p;
+}
+
 // Enqueues one traversal batch on `st`.  scratch: 16 unsigned ints ([0] work counter, [8..15] octant counts);
 // order_region: order_region_ints(R) unsigned ints, used when ray bucketing is on.
-int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cndl_hit* d_hits, float* d_any, unsigned* scratch,
+int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, const unsigned* d_R, cndl_hit* d_hits, float* d_any, unsigned* scratch,
                   unsigned* order_region, cudaStream_t st) {
     if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 rays in one call");
+    if (d_R && ctx->mode != 2) return ctx->fail(CNDL_ERR_INVALID, "a device-side batch length needs traversal mode 2");
     const SceneView s = scene_view(ctx);
     const bool stack = ctx->format == CNDL_STACK;
     if (ctx->mode == 0 || (stack && ctx->mode == 1)) launch_trace_simple(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, st, ctx->launches);
     else if (ctx->mode == 1) launch_trace_persistent(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, scratch, ctx->sm_count, st, ctx->launches);
     else {
-        RayOrder order{nullptr, nullptr, 0};
-        if (ctx->sort_rays && order_region && R >= 65536) {
+        RayOrder order{nullptr, nullptr, 0, d_R};
+        if (ctx->sort_rays && order_region && R >= 65536 && !d_R) {
             if (ctx->sort_rays == 2) {
                 cudaError_t se = sort_rays_morton(d_rays, R, ctx->world_lo, ctx->world_hi, order_region, reinterpret_cast<int*>(order_region + R), st,
                                                   ctx->launches);
@@ -171,7 +73,7 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, cnd
             } else {
                 launch_octant_partition(d_rays, R, order_region, reinterpret_cast<int*>(order_region + R), st, ctx->launches);
             }
-            order = RayOrder{order_region, nullptr, 0};
+            order = RayOrder{order_region, nullptr, 0, nullptr};
         }
         int variant = ctx->knobs[CNDL_KNOB_VARIANT];
         if (variant == 0) {
@@ -235,7 +137,7 @@ void glm_inverse(const float* m, float* out) {
     for (int k = 0; k < 16; ++k) out[k] = inv[k] * ood;
 }
 
-}  // namespace
+}  // namespace cndl
 
 extern "C" {
 
@@ -263,7 +165,7 @@ int cndl_create(cndl_ctx** out, int node_format, int device) {
     for (auto& s : ctx->streams)
         if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CNDL_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CNDL_ERR_CUDA; }
-    if (ctx->d_counter.ensure_scratch(256) != cudaSuccess) { delete ctx; return CNDL_ERR_CUDA; }
+    if (ctx->d_counter.ensure_scratch(256 + 64 * kCounterSlots) != cudaSuccess) { delete ctx; return CNDL_ERR_CUDA; }
     *out = ctx;
     return CNDL_OK;
 }
@@ -584,7 +486,7 @@ int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t 
     CK(cudaSetDevice(ctx->device));
     const int kind = (flags & CNDL_IGNORE_TRANSPARENT) ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST;
     if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
-    return enqueue_trace(ctx, kind, d_rays, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), static_cast<unsigned*>(ctx->d_order.p),
+    return enqueue_trace(ctx, kind, d_rays, R, nullptr, d_hits, nullptr, next_counter(ctx), static_cast<unsigned*>(ctx->d_order.p),
                          static_cast<cudaStream_t>(stream));
 } CNDL_CATCH
 
@@ -595,7 +497,7 @@ int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, f
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
-    return enqueue_trace(ctx, Q_ANY, d_rays, R, nullptr, d_t_out, static_cast<unsigned*>(ctx->d_counter.p), static_cast<unsigned*>(ctx->d_order.p),
+    return enqueue_trace(ctx, Q_ANY, d_rays, R, nullptr, nullptr, d_t_out, next_counter(ctx), static_cast<unsigned*>(ctx->d_order.p),
                          static_cast<cudaStream_t>(stream));
 } CNDL_CATCH
 
@@ -635,7 +537,7 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
         cudaStream_t ks = ctx->streams[(k & 1) ? 3 : 1];
         CK(cudaStreamWaitEvent(ks, ctx->events[2 * k], 0));
         unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->d_chunk_counters.p) + 64 * k);
-        rc = enqueue_trace(ctx, kind, dr, n, kind == Q_ANY ? nullptr : reinterpret_cast<cndl_hit*>(dout),
+        rc = enqueue_trace(ctx, kind, dr, n, nullptr, kind == Q_ANY ? nullptr : reinterpret_cast<cndl_hit*>(dout),
                            kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter,
                            ctx->sort_rays ? static_cast<unsigned*>(ctx->d_order.p) + order_region_ints(chunk) * k : nullptr, ks);
         if (rc != CNDL_OK) return rc;
@@ -676,7 +578,7 @@ int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const
     }
     launch_primary_rays(inv_view, inv_proj, W, H, dr, st, ctx->launches);
     CK(cudaGetLastError());
-    return enqueue_trace(ctx, Q_CLOSEST, dr, R, d_hits, nullptr, static_cast<unsigned*>(ctx->d_counter.p), nullptr, st);  // camera rays are coherent already
+    return enqueue_trace(ctx, Q_CLOSEST, dr, R, nullptr, d_hits, nullptr, next_counter(ctx), nullptr, st);  // camera rays are coherent already
 } CNDL_CATCH
 
 int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H, cndl_hit* hits,
@@ -708,7 +610,7 @@ int cndl_generate_rays_device(cndl_ctx* ctx, const cndl_raygen_params* params, c
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     CK(ctx->d_sort_tmp.ensure_scratch(generate_rays_scratch_ints(R, params->spp) * sizeof(int)));
-    CK(generate_rays(scene_view(ctx), *params, d_rays, d_hits, R, d_rays_out, d_parent_out, static_cast<int*>(ctx->d_sort_tmp.p), count_out,
+    CK(generate_rays(scene_view(ctx), *params, d_rays, d_hits, R, nullptr, d_rays_out, d_parent_out, static_cast<int*>(ctx->d_sort_tmp.p), nullptr, count_out,
                      static_cast<cudaStream_t>(stream), ctx->launches));
     return CNDL_OK;
 } CNDL_CATCH
@@ -723,6 +625,18 @@ int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, cons
     p.offset = offset;
     p.tmax = tmax;
     return cndl_generate_rays_device(ctx, &p, d_rays, d_hits, R, d_rays_out, d_parent_out, count_out, stream);
+} CNDL_CATCH
+
+int cndl_generate_probe_rays_device(cndl_ctx* ctx, const float box_origin[3], const float size[3], const int32_t res[3], uint32_t seed,
+                                    cndl_ray* d_rays_out, void* stream) try {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!box_origin || !size || !res || !d_rays_out || res[0] <= 0 || res[1] <= 0 || res[2] <= 0 ||
+        (size_t)res[0] * (size_t)res[1] * (size_t)res[2] > 0x7FFFFFF0ull)
+        return ctx->fail(CNDL_ERR_INVALID, "bad probe-grid arguments");
+    CK(cudaSetDevice(ctx->device));
+    launch_probe_rays(box_origin, size, res, seed, d_rays_out, static_cast<cudaStream_t>(stream), ctx->launches);
+    CK(cudaGetLastError());
+    return CNDL_OK;
 } CNDL_CATCH
 
 int cndl_get_data_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_attr* d_out, void* stream) try {

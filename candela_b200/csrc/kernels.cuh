@@ -56,8 +56,15 @@ void launch_primary_rays(const float* inv_view16, const float* inv_proj16, int W
 // Wavefront ray generation between bounces (kernels_raygen.cu): diffuse / specular / shadow rays from the hits of the
 // previous batch, compacted (and optionally octant-bucketed) with a stable partition.
 size_t generate_rays_scratch_ints(size_t R, int spp);
-cudaError_t generate_rays(const SceneView& s, const cndl_raygen_params& prm, const cndl_ray* rays, const cndl_hit* hits, size_t R, cndl_ray* out,
-                          unsigned* parent, int* scratch, size_t* h_count, cudaStream_t stream, LaunchCounter& lc);
+// d_R (optional): the input batch length in device memory, R being its upper bound.  *d_count_out: where the number of rays
+// written lives on the device; h_count (optional): also copied to the host, which synchronises `stream`.
+cudaError_t generate_rays(const SceneView& s, const cndl_raygen_params& prm, const cndl_ray* rays, const cndl_hit* hits, size_t R, const unsigned* d_R,
+                          cndl_ray* out, unsigned* parent, int* scratch, const unsigned** d_count_out, size_t* h_count, cudaStream_t stream,
+                          LaunchCounter& lc);
+// element e = i * spp + s of the last generate_rays call on `scratch`: keys[e] < 8 iff it produced a ray, stored at dest[e]
+void generate_rays_maps(int* scratch, size_t R, int spp, const unsigned char** keys, const unsigned** dest);
+// Probe-update rays (UpdateRadianceProbes.glsl:408-427), one per probe of a res[0] x res[1] x res[2] grid.
+void launch_probe_rays(const float box_origin[3], const float size[3], const int res[3], unsigned seed, cndl_ray* out, cudaStream_t stream, LaunchCounter& lc);
 
 // GetData without textures: interpolated normal / uv + entity emissive / alpha per hit record (kernels_raygen.cu).
 void launch_get_data(const SceneView& s, const float4* verts, const cndl_hit* hits, size_t R, cndl_hit_attr* out, cudaStream_t stream, LaunchCounter& lc);

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
                                                                                 RayOrder order, cndl_hit* __restrict__ hits,
                                                                                 float* __restrict__ any_t, unsigned* __restrict__ work_counter,
                                                                                 int park_threshold, int idle_threshold) {
+    R = batch_length(order, R);
     constexpr bool ANY = KIND == Q_ANY;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     extern __shared__ float4 s_nodes[];
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(128, MINB) trace_pair_stackless_kernel(SceneVi
                                                                       unsigned R, RayOrder order, cndl_hit* __restrict__ hits,
                                                                       float* __restrict__ any_t, unsigned* __restrict__ work_counter,
                                                                       int park_threshold, int idle_threshold) {
+    R = batch_length(order, R);
     constexpr bool ANY = KIND == Q_ANY;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;

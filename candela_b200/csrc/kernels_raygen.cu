@@ -9,6 +9,7 @@
 // here are INPUTS to traversal.  Compaction and bucketing are scans, so the output order is deterministic.
 #include "kernels.cuh"
 #include "scan.cuh"
+#include "exact_trig.cuh"
 
 #include <cuda_fp16.h>
 
@@ -111,13 +112,100 @@ void partition8(KeyFn keyfn, size_t n, unsigned* out, int out_is_order, const P8
 
 // ---------------------------------------------------------------------------------------------
 // ray generation
+//
+// Bit-exact contract (the test-side CPU checker states the same arithmetic and is pinned against the shader
+// functions compiled from the reference): every float operation is a separately rounded IEEE operation in the order the
+// shader text (over glm 0.9.8.5) evaluates it — normalize(v) = v * (1 / sqrt(dot(v, v))), dot = (x*x + y*y) + z*z,
+// cross and reflect in glm's forms — the random numbers come from the counter stream below, and sin / cos / acos / pow are
+// the defined functions of exact_trig.cuh.
 
 __device__ __forceinline__ unsigned pcg_hash(unsigned v) {
     unsigned s = v * 747796405u + 2891336453u;
     unsigned w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
     return (w >> 22u) ^ w;
 }
-__device__ __forceinline__ float u01(unsigned h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float u01(unsigned h) { return fmul((float)(h >> 8), 1.0f / 16777216.0f); }
+
+// The stream that stands in for the shaders' hash2(): draw n of stream k is u01(pcg_hash(k + n * 0x9E3779B9)); a hash2()
+// call takes two consecutive draws.  The stream key of element e under `seed` is pcg_hash(seed ^ pcg_hash(e)).
+struct Hash2 {
+    unsigned k, n;
+    __device__ __forceinline__ float next() { return u01(pcg_hash(k + (n++) * 0x9E3779B9u)); }
+};
+__device__ __forceinline__ unsigned stream_key(unsigned seed, unsigned element) { return pcg_hash(seed ^ pcg_hash(element)); }
+
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return {fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z)}; }
+__device__ __forceinline__ V3 vscale(V3 a, float s) { return {fmul(a.x, s), fmul(a.y, s), fmul(a.z, s)}; }
+__device__ __forceinline__ V3 vnormalize(V3 v) { return vscale(v, fdiv(1.0f, __fsqrt_rn(vdot(v, v)))); }      // glm compute_normalize
+__device__ __forceinline__ V3 vreflect(V3 I, V3 N) { return vsub(I, vscale(vscale(N, vdot(N, I)), 2.0f)); }    // glm compute_reflect: I - N * dot(N, I) * 2
+
+#define CNDL_PI2_F (2.0f * 3.14159265359f)
+
+// CosWeightedHemisphere, Include/Sampling.glsl:1-12
+__device__ __forceinline__ V3 cos_weighted_hemisphere(V3 n, float r_x, float r_y) {
+    const V3 uu = vnormalize(vcross(n, V3{0.0f, 1.0f, 1.0f}));
+    const V3 vv = vcross(uu, n);
+    const float ra = __fsqrt_rn(r_y);
+    float sn, cs;
+    xm::xsincos(fmul(CNDL_PI2_F, r_x), sn, cs);
+    const float rx = fmul(ra, cs), ry = fmul(ra, sn), rz = __fsqrt_rn(fsub(1.0f, r_y));
+    const V3 rr = vadd(vadd(vscale(uu, rx), vscale(vv, ry)), vscale(n, rz));
+    return vnormalize(rr);
+}
+
+// SampleGGXVNDF, Include/Sampling.glsl:63-83
+__device__ __forceinline__ V3 sample_ggx_vndf(V3 N, float roughness, float xi_x, float xi_y) {
+    const float alpha = fmul(roughness, roughness), alpha2 = fmul(alpha, alpha);
+    const float phi = fmul(CNDL_PI2_F, xi_x);
+    const float cos_theta = __fsqrt_rn(fdiv(fsub(1.0f, xi_y), fadd(1.0f, fmul(fsub(alpha2, 1.0f), xi_y))));
+    const float sin_theta = __fsqrt_rn(fsub(1.0f, fmul(cos_theta, cos_theta)));
+    float sn, cs;
+    xm::xsincos(phi, sn, cs);
+    const V3 H = {fmul(cs, sin_theta), fmul(sn, sin_theta), cos_theta};
+    const V3 up = fabsf(N.z) < 0.999f ? V3{0.0f, 0.0f, 1.0f} : V3{1.0f, 0.0f, 0.0f};
+    const V3 tangent = vnormalize(vcross(up, N));
+    const V3 bitangent = vcross(N, tangent);
+    const V3 sv = vadd(vadd(vscale(tangent, H.x), vscale(bitangent, H.y)), vscale(N, H.z));
+    return vnormalize(sv);
+}
+
+// StochasticReflectionDirection, SpecularTrace.glsl:102-135
+__device__ __forceinline__ V3 stochastic_reflection_direction(V3 incident, V3 normal, float roughness, Hash2& h) {
+    if (roughness < 0.01f) return vreflect(incident, normal);
+    V3 microfacet = normal;
+    for (int i = 0; i < 12; ++i) {
+        const float a = fmul(h.next(), 0.8f), b = fmul(h.next(), 0.7f);  // hash2() * TailControl
+        const V3 s = sample_ggx_vndf(normal, roughness, a, b);
+        if (vdot(s, normal) > 0.001f) { microfacet = s; break; }
+    }
+    return vreflect(incident, microfacet);
+}
+
+// SampleCone(Direction, Xi, CosTheta) = mat3(T, B, L) * SampleCone(Xi, CosTheta), Include/Sampling.glsl:43-61
+__device__ __forceinline__ V3 sample_cone(V3 L, float xi_x, float xi_y, float cos_theta_max) {
+    const float cos_theta = fadd(fsub(1.0f, xi_x), fmul(xi_x, cos_theta_max));
+    const float sin_theta = __fsqrt_rn(fsub(1.0f, fmul(cos_theta, cos_theta)));
+    const float phi = fmul(fmul(xi_y, 3.14159265359f), 2.0f);
+    float sn, cs;
+    xm::xsincos(phi, sn, cs);
+    const V3 l = {fmul(sin_theta, cs), fmul(sin_theta, sn), cos_theta};
+    const V3 T = vnormalize(vcross(L, V3{0.0f, 1.0f, 1.0f}));
+    const V3 B = vcross(T, L);
+    return {fadd(fadd(fmul(T.x, l.x), fmul(B.x, l.y)), fmul(L.x, l.z)), fadd(fadd(fmul(T.y, l.x), fmul(B.y, l.y)), fmul(L.y, l.z)),
+            fadd(fadd(fmul(T.z, l.x), fmul(B.z, l.y)), fmul(L.z, l.z))};
+}
+
+// LambertBRDF, UpdateRadianceProbes.glsl:351-362 (PI = 3.1415926535 in that file)
+__device__ __forceinline__ V3 lambert_brdf(float hx, float hy, float hz) {
+    const float phi = fmul(2.0f * 3.1415926535f, hx);
+    const float cos_theta = fsub(fmul(2.0f, hy), 1.0f);
+    const float theta = xm::xacos(cos_theta);
+    const float r = xm::xpow(hz, 1.0f / 3.0f);
+    float sp, cp, st, ct;
+    xm::xsincos(phi, sp, cp);
+    xm::xsincos(theta, st, ct);
+    return {fmul(fmul(r, st), cp), fmul(fmul(r, st), sp), fmul(r, ct)};
+}
 
 struct GenParams {
     int kind, spp, bucket;
@@ -126,9 +214,9 @@ struct GenParams {
 };
 
 struct HitFrame {  // what every sample of one hit shares
-    float px, py, pz;     // hit point
-    float nx, ny, nz;     // geometric normal, world space, turned against the incoming ray
-    float ix, iy, iz;     // incoming direction
+    V3 p;   // hit point: RayOrigin + RayDirection * TUVW.x (DiffuseTrace.glsl:511)
+    V3 n;   // geometric normal, world space, turned against the incoming ray
+    V3 in;  // incoming direction
     bool valid;
 };
 
@@ -140,119 +228,113 @@ __device__ __forceinline__ HitFrame hit_frame(const cndl_ray* __restrict__ rays,
     if (!f.valid) return f;
     const int4 h1 = __ldg(reinterpret_cast<const int4*>(hits + i) + 1);
     const float4 ra = __ldg(reinterpret_cast<const float4*>(rays + i)), rb = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
-    const float t = h0.x;
-    f.px = ra.x + rb.x * t; f.py = ra.y + rb.y * t; f.pz = ra.z + rb.z * t;
-    f.ix = rb.x; f.iy = rb.y; f.iz = rb.z;
-    const float4 c = __ldg(tri48 + 3 * (size_t)h1.y + 2);
+    const V3 o = {ra.x, ra.y, ra.z}, d = {rb.x, rb.y, rb.z};
+    f.p = vadd(o, vscale(d, h0.x));
+    f.in = d;
+    const float4 c = __ldg(tri48 + 3 * (size_t)h1.y + 2);  // .yzw = cross(v1 - v0, v2 - v0), object space
     const float* m = ents[h1.z].model;
-    float nx = m[0] * c.y + m[4] * c.z + m[8] * c.w, ny = m[1] * c.y + m[5] * c.z + m[9] * c.w, nz = m[2] * c.y + m[6] * c.z + m[10] * c.w;
-    const float inv = rsqrtf(fmaxf(nx * nx + ny * ny + nz * nz, 1e-30f));
-    nx *= inv; ny *= inv; nz *= inv;
-    if (nx * rb.x + ny * rb.y + nz * rb.z > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
-    f.nx = nx; f.ny = ny; f.nz = nz;
+    const V3 nw = {fadd(fadd(fmul(__ldg(m + 0), c.y), fmul(__ldg(m + 4), c.z)), fmul(__ldg(m + 8), c.w)),
+                   fadd(fadd(fmul(__ldg(m + 1), c.y), fmul(__ldg(m + 5), c.z)), fmul(__ldg(m + 9), c.w)),
+                   fadd(fadd(fmul(__ldg(m + 2), c.y), fmul(__ldg(m + 6), c.z)), fmul(__ldg(m + 10), c.w))};
+    const float dd = vdot(nw, nw);
+    if (!(dd > 0.0f) || isinf(dd)) { f.valid = false; return f; }  // degenerate triangle: no ray
+    V3 n = vscale(nw, fdiv(1.0f, __fsqrt_rn(dd)));
+    if (vdot(n, d) > 0.0f) n = vneg(n);
+    f.n = n;
     return f;
 }
 
-// Sample s of hit i: origin + direction.  false: this sample emits no ray.
-__device__ __forceinline__ bool gen_ray(const GenParams& g, const HitFrame& f, unsigned i, int s, float4& o, float4& d) {
-    const unsigned k = pcg_hash(g.seed ^ pcg_hash(i * (unsigned)g.spp + (unsigned)s));
-    float off = g.offset, dx, dy, dz;
+// The ray of stream element `element` for hit frame f.  false: this sample emits no ray.
+__device__ __forceinline__ bool gen_ray(const GenParams& g, const HitFrame& f, unsigned element, float4& o, float4& d) {
+    Hash2 h{stream_key(g.seed, element), 0u};
+    float off = g.offset;
+    V3 dir;
     if (g.kind == CNDL_GEN_DIFFUSE) {
-        // CosWeightedHemisphere (Sampling.glsl:1-12): uu = normalize(cross(n, (0,1,1))), vv = cross(uu, n)
-        float ux = f.ny - f.nz, uy = -f.nx, uz = f.nx;
-        float inv = rsqrtf(fmaxf(ux * ux + uy * uy + uz * uz, 1e-30f));
-        ux *= inv; uy *= inv; uz *= inv;
-        const float vx = uy * f.nz - uz * f.ny, vy = uz * f.nx - ux * f.nz, vz = ux * f.ny - uy * f.nx;
-        const float r1 = u01(k), r2 = u01(pcg_hash(k + 0x9E3779B9u));
-        const float rad = sqrtf(r2), ang = 6.28318530718f * r1;
-        float sn, cs;
-        sincosf(ang, &sn, &cs);
-        const float rx = rad * cs, ry = rad * sn, rz = sqrtf(1.0f - r2);
-        dx = rx * ux + ry * vx + rz * f.nx; dy = rx * uy + ry * vy + rz * f.ny; dz = rx * uz + ry * vz + rz * f.nz;
+        const float a = h.next(), b = h.next();
+        dir = cos_weighted_hemisphere(f.n, a, b);
     } else if (g.kind == CNDL_GEN_SPECULAR) {
-        // StochasticReflectionDirection(Incident, Normal, PBR.x * 0.9) (SpecularTrace.glsl:102-135,:513)
-        const float rough = g.roughness * 0.9f;
-        float mx = f.nx, my = f.ny, mz = f.nz;  // Microfacet = Normal
-        if (rough >= 0.01f) {
-            const float alpha = rough * rough, alpha2 = alpha * alpha;
-            // tangent frame of SampleGGXVNDF (Sampling.glsl:77-79)
-            const bool upz = fabsf(f.nz) < 0.999f;
-            const float ax = upz ? 0.0f : 1.0f, az = upz ? 1.0f : 0.0f;  // up
-            float tx = -az * f.ny, ty = az * f.nx - ax * f.nz, tz = ax * f.ny;  // cross(up, N) with up.y = 0
-            float inv = rsqrtf(fmaxf(tx * tx + ty * ty + tz * tz, 1e-30f));
-            tx *= inv; ty *= inv; tz *= inv;
-            const float bx = f.ny * tz - f.nz * ty, by = f.nz * tx - f.nx * tz, bz = f.nx * ty - f.ny * tx;  // cross(N, tangent)
-            for (int t = 0; t < 12; ++t) {
-                const float x1 = u01(pcg_hash(k + (unsigned)(2 * t + 1) * 0x9E3779B9u)) * 0.8f;  // TailControl (:118)
-                const float x2 = u01(pcg_hash(k + (unsigned)(2 * t + 2) * 0x9E3779B9u)) * 0.7f;
-                const float phi = 6.28318530718f * x1;
-                const float ct = sqrtf((1.0f - x2) / (1.0f + (alpha2 - 1.0f) * x2)), st = sqrtf(fmaxf(1.0f - ct * ct, 0.0f));
-                float sp, cp;
-                sincosf(phi, &sp, &cp);
-                const float hx = cp * st, hy = sp * st, hz = ct;
-                float sx = tx * hx + bx * hy + f.nx * hz, sy = ty * hx + by * hy + f.ny * hz, sz = tz * hx + bz * hy + f.nz * hz;
-                inv = rsqrtf(fmaxf(sx * sx + sy * sy + sz * sz, 1e-30f));
-                sx *= inv; sy *= inv; sz *= inv;
-                if (sx * f.nx + sy * f.ny + sz * f.nz > 0.001f) { mx = sx; my = sy; mz = sz; break; }
-            }
+        dir = stochastic_reflection_direction(f.in, f.n, fmul(g.roughness, 0.9f), h);  // SpecularTrace.glsl:513
+        if (g.offset < 0.0f) {  // mix(0.05f, 0.1f, clamp(PBR.x * 1.4f, 0, 1)) (:512); glm: x + a * (y - x), clamp = min(max(x, lo), hi)
+            const float a = glsl_min(glsl_max(fmul(g.roughness, 1.4f), 0.0f), 1.0f);
+            off = fadd(0.05f, fmul(a, fsub(0.1f, 0.05f)));
         }
-        const float di = 2.0f * (mx * f.ix + my * f.iy + mz * f.iz);  // reflect(I, M) = I - 2 dot(M, I) M
-        dx = f.ix - di * mx; dy = f.iy - di * my; dz = f.iz - di * mz;
-        if (g.offset < 0.0f) off = 0.05f + 0.05f * fminf(fmaxf(g.roughness * 1.4f, 0.0f), 1.0f);  // mix(0.05, 0.1, clamp(PBR.x*1.4)) (:512)
     } else {
-        // shadow ray towards the light, jittered inside a cone; surfaces facing away from the light need no ray
-        if (f.nx * g.lx + f.ny * g.ly + f.nz * g.lz <= 0.0f) return false;
-        const bool upz = fabsf(g.lz) < 0.999f;
-        const float ax = upz ? 0.0f : 1.0f, az = upz ? 1.0f : 0.0f;
-        float tx = -az * g.ly, ty = az * g.lx - ax * g.lz, tz = ax * g.ly;
-        const float inv = rsqrtf(fmaxf(tx * tx + ty * ty + tz * tz, 1e-30f));
-        tx *= inv; ty *= inv; tz *= inv;
-        const float bx = g.ly * tz - g.lz * ty, by = g.lz * tx - g.lx * tz, bz = g.lx * ty - g.ly * tx;
-        const float r1 = u01(k), r2 = u01(pcg_hash(k + 0x9E3779B9u));
-        const float rad = sqrtf(r2) * g.cone, ang = 6.28318530718f * r1;
-        float sn, cs;
-        sincosf(ang, &sn, &cs);
-        dx = g.lx + rad * (cs * tx + sn * bx); dy = g.ly + rad * (cs * ty + sn * by); dz = g.lz + rad * (cs * tz + sn * bz);
+        // shadow ray towards the light, jittered inside a cone with the reference's SampleCone; surfaces facing away need no ray
+        const V3 L = {g.lx, g.ly, g.lz};
+        if (!(vdot(f.n, L) > 0.0f)) return false;
+        const float a = h.next(), b = h.next();
+        const float cos_max = __fsqrt_rn(fsub(1.0f, fmul(g.cone, g.cone)));
+        dir = vnormalize(sample_cone(L, a, b, cos_max));
     }
-    const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f));
-    o = make_float4(f.px + f.nx * off, f.py + f.ny * off, f.pz + f.nz * off, 0.0f);
-    d = make_float4(dx * inv, dy * inv, dz * inv, g.tmax);
+    const V3 org = vadd(f.p, vscale(f.n, off));
+    o = make_float4(org.x, org.y, org.z, 0.0f);
+    d = make_float4(dir.x, dir.y, dir.z, g.tmax);
     return true;
 }
 
 // Pass 1: the partition key of every potential output ray (8 = none).
-__global__ void gen_keys_kernel(GenParams g, const cndl_ray* __restrict__ rays, const cndl_hit* __restrict__ hits, const float4* __restrict__ tri48,
-                                const cndl_entity* __restrict__ ents, unsigned R, unsigned char* __restrict__ keys) {
+__global__ void gen_keys_kernel(GenParams g, const cndl_ray* __restrict__ rays, const cndl_hit* __restrict__ hits, const unsigned* __restrict__ ids,
+                                const float4* __restrict__ tri48, const cndl_entity* __restrict__ ents, const unsigned* __restrict__ d_R, unsigned R,
+                                unsigned char* __restrict__ keys) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
-    const HitFrame f = hit_frame(rays, hits, tri48, ents, i);
+    const bool live = !d_R || i < __ldg(d_R);  // d_R: the batch length when it is only known on the device (slots beyond it emit nothing)
+    HitFrame f;
+    f.valid = false;
+    if (live) f = hit_frame(rays, hits, tri48, ents, i);
+    const unsigned id = ids && live ? __ldg(ids + i) : i;
     for (int s = 0; s < g.spp; ++s) {
         unsigned key = 8;
         float4 o, d;
-        if (f.valid && gen_ray(g, f, i, s, o, d)) key = g.bucket ? ((d.x > 0.0f ? 1u : 0u) | (d.y > 0.0f ? 2u : 0u) | (d.z > 0.0f ? 4u : 0u)) : 0u;
+        if (f.valid && gen_ray(g, f, id * (unsigned)g.spp + (unsigned)s, o, d))
+            key = g.bucket ? ((d.x > 0.0f ? 1u : 0u) | (d.y > 0.0f ? 2u : 0u) | (d.z > 0.0f ? 4u : 0u)) : 0u;
         keys[(size_t)i * g.spp + s] = (unsigned char)key;
     }
 }
 
 // Pass 3: the rays, written where the partition put them.
-__global__ void gen_emit_kernel(GenParams g, const cndl_ray* __restrict__ rays, const cndl_hit* __restrict__ hits, const float4* __restrict__ tri48,
-                                const cndl_entity* __restrict__ ents, unsigned R, const unsigned char* __restrict__ keys,
-                                const unsigned* __restrict__ dest, cndl_ray* __restrict__ out, unsigned* __restrict__ parent) {
+__global__ void gen_emit_kernel(GenParams g, const cndl_ray* __restrict__ rays, const cndl_hit* __restrict__ hits, const unsigned* __restrict__ ids,
+                                const float4* __restrict__ tri48, const cndl_entity* __restrict__ ents, unsigned R, const unsigned char* __restrict__ keys,
+                                const unsigned* __restrict__ dest, cndl_ray* __restrict__ out, unsigned* __restrict__ parent, unsigned* __restrict__ ids_out) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
+    bool any = false;
+    for (int s = 0; s < g.spp; ++s) any = any || keys[(size_t)i * g.spp + s] < 8;
+    if (!any) return;
     const HitFrame f = hit_frame(rays, hits, tri48, ents, i);
-    if (!f.valid) return;
+    const unsigned id = ids ? __ldg(ids + i) : i;
     for (int s = 0; s < g.spp; ++s) {
         const size_t e = (size_t)i * g.spp + s;
         if (keys[e] >= 8) continue;
         float4 o, d;
-        gen_ray(g, f, i, s, o, d);
+        const unsigned element = id * (unsigned)g.spp + (unsigned)s;
+        gen_ray(g, f, element, o, d);
         const unsigned pos = dest[e];
         float4* q = reinterpret_cast<float4*>(out + pos);
         q[0] = o;
         q[1] = d;
         if (parent) parent[pos] = i;
+        if (ids_out) ids_out[pos] = element;
     }
+}
+
+// Probe-update rays (UpdateRadianceProbes.glsl:408-427): probe (x, y, z) of a res.x * res.y * res.z grid -> ray index
+// (z * res.y + y) * res.x + x; RayOrigin = u_BoxOrigin + (vec3(Pixel) / u_Resolution * 2 - 1) * u_Size; direction =
+// ImportanceSample() with its importance branch off = normalize(LambertBRDF(vec3(hash2(), hash2().x))) (:365-374).
+__global__ void probe_rays_kernel(float3 org, float3 size, int3 res, unsigned seed, cndl_ray* __restrict__ out) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n = (unsigned)res.x * (unsigned)res.y * (unsigned)res.z;
+    if (idx >= n) return;
+    const int x = (int)(idx % (unsigned)res.x), y = (int)((idx / (unsigned)res.x) % (unsigned)res.y), z = (int)(idx / ((unsigned)res.x * (unsigned)res.y));
+    const V3 tex = {fdiv((float)x, (float)res.x), fdiv((float)y, (float)res.y), fdiv((float)z, (float)res.z)};
+    const V3 clip = {fsub(fmul(tex.x, 2.0f), 1.0f), fsub(fmul(tex.y, 2.0f), 1.0f), fsub(fmul(tex.z, 2.0f), 1.0f)};
+    const V3 o = {fadd(org.x, fmul(clip.x, size.x)), fadd(org.y, fmul(clip.y, size.y)), fadd(org.z, fmul(clip.z, size.z))};
+    Hash2 h{stream_key(seed, idx), 0u};
+    const float a = h.next(), b = h.next(), c = h.next();
+    const V3 d = vnormalize(lambert_brdf(a, b, c));
+    float4* q = reinterpret_cast<float4*>(out + idx);
+    q[0] = make_float4(o.x, o.y, o.z, 0.0f);
+    q[1] = make_float4(d.x, d.y, d.z, 1000000.0f);
 }
 
 // GetData (…/Include/TraverseBVHStackless.glsl:370-408) without the texture fetch.
@@ -304,10 +386,14 @@ size_t generate_rays_scratch_ints(size_t R, int spp) {
     return (n + 3) / 4 + n + p8_scratch_ints(n) + 16;
 }
 
-// Returns the number of rays written through *h_count (synchronises `stream`).
-cudaError_t generate_rays(const SceneView& s, const cndl_raygen_params& prm, const cndl_ray* rays, const cndl_hit* hits, size_t R, cndl_ray* out,
-                          unsigned* parent, int* scratch, size_t* h_count, cudaStream_t stream, LaunchCounter& lc) {
-    *h_count = 0;
+// Writes the rays and leaves their number in device memory (returned through *d_count_out, valid until the scratch is
+// reused); when h_count is given, also copies it to the host and synchronises `stream`.  d_R (optional): the input batch
+// length on the device, R being its upper bound.
+cudaError_t generate_rays(const SceneView& s, const cndl_raygen_params& prm, const cndl_ray* rays, const cndl_hit* hits, size_t R, const unsigned* d_R,
+                          cndl_ray* out, unsigned* parent, int* scratch, const unsigned** d_count_out, size_t* h_count, cudaStream_t stream,
+                          LaunchCounter& lc) {
+    if (h_count) *h_count = 0;
+    if (d_count_out) *d_count_out = nullptr;
     if (R == 0) return cudaSuccess;
     GenParams g;
     g.kind = prm.kind;
@@ -324,18 +410,36 @@ cudaError_t generate_rays(const SceneView& s, const cndl_raygen_params& prm, con
     unsigned* dest = reinterpret_cast<unsigned*>(scratch + (n + 3) / 4);
     const P8Scratch p = p8_carve(scratch + (n + 3) / 4 + n, n);
     const unsigned grid = (unsigned)((R + 255) / 256);
-    gen_keys_kernel<<<grid, 256, 0, stream>>>(g, rays, hits, s.tri48, s.ents, (unsigned)R, keys);
+    gen_keys_kernel<<<grid, 256, 0, stream>>>(g, rays, hits, prm.d_ids_in, s.tri48, s.ents, d_R, (unsigned)R, keys);
     lc.n++;
     partition8(KeyFromBytes{keys}, n, dest, 0, p, stream, lc);
-    gen_emit_kernel<<<grid, 256, 0, stream>>>(g, rays, hits, s.tri48, s.ents, (unsigned)R, keys, dest, out, parent);
+    gen_emit_kernel<<<grid, 256, 0, stream>>>(g, rays, hits, prm.d_ids_in, s.tri48, s.ents, (unsigned)R, keys, dest, out, parent, prm.d_ids_out);
     lc.n++;
-    int h_total = 0;
-    cudaError_t e = cudaMemcpyAsync(&h_total, p.total, sizeof(int), cudaMemcpyDeviceToHost, stream);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) return e;
-    *h_count = (size_t)h_total;
+    if (d_count_out) *d_count_out = reinterpret_cast<const unsigned*>(p.total);
+    if (h_count) {
+        int h_total = 0;
+        cudaError_t e = cudaMemcpyAsync(&h_total, p.total, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        *h_count = (size_t)h_total;
+    }
     return cudaGetLastError();
+}
+
+// keys / dest of the last generate_rays call on `scratch` (element e = i * spp + s: keys[e] < 8 iff it produced a ray, at dest[e])
+void generate_rays_maps(int* scratch, size_t R, int spp, const unsigned char** keys, const unsigned** dest) {
+    const size_t n = R * (size_t)spp;
+    *keys = reinterpret_cast<const unsigned char*>(scratch);
+    *dest = reinterpret_cast<const unsigned*>(scratch + (n + 3) / 4);
+}
+
+void launch_probe_rays(const float box_origin[3], const float size[3], const int res[3], unsigned seed, cndl_ray* out, cudaStream_t stream, LaunchCounter& lc) {
+    const size_t n = (size_t)res[0] * (size_t)res[1] * (size_t)res[2];
+    if (n == 0) return;
+    probe_rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(make_float3(box_origin[0], box_origin[1], box_origin[2]), make_float3(size[0], size[1], size[2]),
+                                                                      make_int3(res[0], res[1], res[2]), seed, out);
+    lc.n++;
 }
 
 }  // namespace cndl

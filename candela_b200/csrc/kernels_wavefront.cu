@@ -133,6 +133,7 @@ template <int KIND, int MINB, int STEPS, bool CHECKED, bool HELP>
 __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R, RayOrder order,
                                                                     cndl_hit* __restrict__ hits, float* __restrict__ any_t,
                                                                     unsigned* __restrict__ work_counter, int park_threshold, int idle_threshold) {
+    R = batch_length(order, R);
     constexpr bool ANY = KIND == Q_ANY;
     __shared__ float4 s_box[HELP ? 4 : 1][HELP ? 64 : 1];  // per warp: up to 32 posted (ray, triangle) pairs
     __shared__ float s_res[HELP ? 4 : 1][HELP ? 32 : 1];
@@ -365,6 +366,7 @@ template <int KIND, int STEPS, bool CHECKED>
 __global__ void __launch_bounds__(128, 8) trace_ww_stack_kernel(SceneView s, const cndl_ray* __restrict__ rays, unsigned R, RayOrder order,
                                                                 cndl_hit* __restrict__ hits, float* __restrict__ any_t,
                                                                 unsigned* __restrict__ work_counter, int park_threshold, int idle_threshold) {
+    R = batch_length(order, R);
     constexpr bool ANY = KIND == Q_ANY;
     const unsigned lane = threadIdx.x & 31u;
     int stack[64];

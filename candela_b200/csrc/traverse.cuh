@@ -34,7 +34,14 @@ struct RayOrder {
     const unsigned* __restrict__ list;
     const unsigned* __restrict__ counts;
     unsigned stride;
+    const unsigned* __restrict__ d_count;  // optional: the batch length in device memory (the launch's R is then its upper bound)
 };
+
+__device__ __forceinline__ unsigned batch_length(const RayOrder& ro, unsigned R) {
+    if (!ro.d_count) return R;
+    const unsigned n = __ldg(ro.d_count);
+    return n < R ? n : R;
+}
 
 __device__ __forceinline__ unsigned ray_of_slot(const RayOrder& ro, unsigned slot) {
     if (!ro.list) return slot;

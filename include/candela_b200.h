@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CNDL_ABI_VERSION 1
+#define CNDL_ABI_VERSION 2
 
 typedef enum cndl_status {
     CNDL_OK = 0,
@@ -152,7 +152,9 @@ int cndl_intersect_closest(cndl_ctx* ctx, const cndl_ray* rays, size_t R, int fl
 /* float IntersectRay(o, d) (any hit; …Stackless.glsl:558-579): t_out[i] = first accepted t or -1. */
 int cndl_intersect_any(cndl_ctx* ctx, const cndl_ray* rays, size_t R, float* t_out);
 /* Same queries on DEVICE buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream)
- * and not synchronised. */
+ * and not synchronised.  Each call takes its own work counter from a ring of 64, so traversal calls in flight on different
+ * streams do not interfere; calls that use the context's ordering / generation scratch (cndl_set_traversal_mode sort_rays != 0,
+ * cndl_generate_rays_device) must be enqueued on ONE stream at a time (or ordered by events). */
 int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, int flags, cndl_hit* d_hits, void* stream);
 int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, float* d_t_out, void* stream);
 
@@ -165,24 +167,25 @@ int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float 
 int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H,
                                   cndl_hit* d_hits, cndl_ray* d_rays_out, void* stream);
 
-/* Wavefront step between bounces (DiffuseTrace.glsl:445-446,:516-517): for every ray whose hit record has
- * t > 0, writes `spp` diffuse rays {origin = P + N*offset, direction = CosWeightedHemisphere(N, xi), tmax}
- * to d_rays_out, compacted in input order (rays that missed emit nothing); N is the geometric normal turned
- * against the incoming ray, xi a counter-based hash of (seed, ray, sample).  d_parent_out (optional) receives
- * the index of the parent ray.  d_rays_out must hold R*spp rays.  *count_out = rays written; synchronises
- * `stream`. */
-int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R, int spp, float offset,
-                                     float tmax, uint32_t seed, cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream);
-
-/* The general form of the wavefront ray generator.  kind:
- *   CNDL_GEN_DIFFUSE   CosWeightedHemisphere(N, xi) about the geometric normal (Include/Sampling.glsl:1-12)
- *   CNDL_GEN_SPECULAR  StochasticReflectionDirection(Incident, N, roughness * 0.9): reflect about a GGX microfacet drawn
- *                      with SampleGGXVNDF, tail control (0.8, 0.7), up to 12 tries (SpecularTrace.glsl:102-135,:513;
- *                      Include/Sampling.glsl:63-83); offset < 0 selects the shader's mix(0.05, 0.1, clamp(roughness*1.4)) (:512)
- *   CNDL_GEN_SHADOW    towards light_dir (unit vector), jittered in a cone of sine light_cone; hits whose normal faces away
- *                      from the light emit nothing.  Meant for cndl_intersect_any_device.
+/* Ray generators: the step in front of the path.  For every input ray whose hit record has t > 0
+ * they write `spp` rays from the hit point P = o + d*t and the geometric normal N of the hit triangle (world space,
+ * turned against the incoming ray; where the shaders read N from a G-buffer texture), compacted in input order (rays that
+ * missed emit nothing).  kind:
+ *   CNDL_GEN_DIFFUSE   origin P + N*offset, direction CosWeightedHemisphere(N, hash2())
+ *                      (DiffuseTrace.glsl:445-446 first bounce, offset 0.05; :516-517 later bounces, 0.02; Include/Sampling.glsl:1-12)
+ *   CNDL_GEN_SPECULAR  direction StochasticReflectionDirection(Incident, N, roughness * 0.9) (SpecularTrace.glsl:102-135,:513;
+ *                      SampleGGXVNDF, Include/Sampling.glsl:63-83); offset < 0 selects the shader's mix(0.05, 0.1, clamp(roughness*1.4)) (:512)
+ *   CNDL_GEN_SHADOW    direction normalize(SampleCone(light_dir, hash2(), sqrt(1 - light_cone^2))) (Include/Sampling.glsl:43-61;
+ *                      light_cone = sine of the cone's half angle); hits whose normal faces away from the light emit nothing.
+ *                      Meant for cndl_intersect_any_device.
+ * Arithmetic contract: the rays are bit-identical to the shader functions evaluated in separately rounded IEEE float
+ * operations over glm 0.9.8.5, with the two things GLSL leaves to the implementation DEFINED: hash2() is a counter stream —
+ * draw n of element e under `seed` is u01(pcg(pcg(seed ^ pcg(e)) + n * 0x9E3779B9)), e = id * spp + sample, id = d_ids_in[i]
+ * or i — and sin / cos / acos / pow are the double-precision formulas of csrc/exact_trig.cuh (within 0.5 ulp).  A CPU
+ * restatement in the test tree reproduces every ray bit for bit, and is pinned against the shader functions compiled from the reference.
  * flags & CNDL_GEN_BUCKET_OCTANTS: the rays are written octant-major (all rays whose direction signs are ---, then +--, ...),
- * each octant in input order; incoherent batches traverse ~8 % faster in that order.  d_parent_out maps back. */
+ * each octant in input order; incoherent batches traverse ~8 % faster in that order.  d_parent_out maps back.
+ * d_rays_out must hold R*spp rays.  *count_out = rays written; the call synchronises `stream`. */
 enum { CNDL_GEN_DIFFUSE = 0, CNDL_GEN_SPECULAR = 1, CNDL_GEN_SHADOW = 2 };
 enum { CNDL_GEN_BUCKET_OCTANTS = 1 };
 typedef struct cndl_raygen_params {
@@ -191,9 +194,22 @@ typedef struct cndl_raygen_params {
     float offset, tmax, roughness;
     float light_dir[3];
     float light_cone;
+    const uint32_t* d_ids_in; /* optional (device): stream id of every input ray; NULL = its index.  Lets a tile-sharded or
+                                 multi-bounce pipeline draw the numbers of pixel p whatever slot p's ray occupies */
+    uint32_t* d_ids_out;      /* optional (device): receives id * spp + sample of every ray written */
 } cndl_raygen_params;
 int cndl_generate_rays_device(cndl_ctx* ctx, const cndl_raygen_params* params, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R,
                               cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream);
+/* CNDL_GEN_DIFFUSE with the remaining parameters at their defaults. */
+int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, const cndl_hit* d_hits, size_t R, int spp, float offset,
+                                     float tmax, uint32_t seed, cndl_ray* d_rays_out, uint32_t* d_parent_out, size_t* count_out, void* stream);
+/* Probe-update rays (UpdateRadianceProbes.glsl:408-427; ProbeGI.cpp:215-217 dispatches PROBE_GRID 48 x 24 x 48, Macros.h:22-24):
+ * probe (x, y, z) of a res[0] x res[1] x res[2] grid -> d_rays_out[(z * res[1] + y) * res[0] + x] with origin
+ * box_origin + (vec3(x, y, z) / res * 2 - 1) * size and direction ImportanceSample() = normalize(LambertBRDF(vec3(hash2(),
+ * hash2().x))) (:351-374; the shader's importance branch is switched off), element = the ray's index, tmax 1e6.  Same
+ * arithmetic contract as above.  Needs no scene; enqueued on `stream`, not synchronised. */
+int cndl_generate_probe_rays_device(cndl_ctx* ctx, const float box_origin[3], const float size[3], const int32_t res[3], uint32_t seed,
+                                    cndl_ray* d_rays_out, void* stream);
 
 /* GetData (…/Include/TraverseBVHStackless.glsl:370-408) without the texture fetch — the step right after
  * the path: for every hit record, the interpolated half-float vertex normal (normalised) and UV and the

@@ -404,3 +404,114 @@ def ref_sample(which: int, normals, xi, roughness: float = 0.0) -> np.ndarray:
     ref_lib().ref_glsl_sample(which, _p(n), _p(x), roughness, len(n), _p(out))
     return out
 
+
+
+# --- ray generators (oracle_raygen.cpp) ----------------------------------------------------------------------------------
+
+GEN_DIFFUSE, GEN_SPECULAR, GEN_SHADOW = 0, 1, 2
+GEN_BUCKET_OCTANTS = 1
+SAMPLE_COS_HEMISPHERE, SAMPLE_GGX_VNDF, SAMPLE_STOCHASTIC_REFLECTION, SAMPLE_CONE, SAMPLE_PROBE = 0, 1, 2, 3, 4
+
+
+class RaygenParams(C.Structure):
+    """orc_raygen_params (same fields as cndl_raygen_params up to `light_cone`)."""
+    _fields_ = [("kind", C.c_int32), ("spp", C.c_int32), ("seed", C.c_uint32), ("flags", C.c_uint32), ("offset", C.c_float), ("tmax", C.c_float),
+                ("roughness", C.c_float), ("light_dir", C.c_float * 3), ("light_cone", C.c_float)]
+
+
+def _raygen_protos():
+    L = lib()
+    if getattr(L, "_raygen_ready", False):
+        return L
+    vp, u64 = C.c_void_p, C.c_uint64
+    for f in ("orc_xsin", "orc_xcos", "orc_xacos"):
+        getattr(L, f).argtypes = [C.c_float]
+        getattr(L, f).restype = C.c_float
+    L.orc_xpow.argtypes = [C.c_float, C.c_float]
+    L.orc_xpow.restype = C.c_float
+    L.orc_xmath_batch.argtypes = [C.c_int, vp, vp, u64, vp]
+    L.orc_sample_directions.argtypes = [C.c_int, vp, vp, vp, vp, C.c_float, u64, vp]
+    L.orc_hash2_stream.argtypes = [C.c_uint32, C.c_uint32, vp]
+    L.orc_stream_key.argtypes = [C.c_uint32, C.c_uint32]
+    L.orc_stream_key.restype = C.c_uint32
+    L.orc_generate_rays.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp]
+    L.orc_generate_rays.restype = u64
+    L.orc_probe_rays.argtypes = [vp, vp, vp, C.c_uint32, vp]
+    L._raygen_ready = True
+    return L
+
+
+def xmath(which: int, x, y=None) -> np.ndarray:
+    """The DEFINED sin (0) / cos (1) / acos (2) / pow (3) of exact_math_ref.h on float32 arrays."""
+    x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+    y = None if y is None else np.ascontiguousarray(y, dtype=np.float32).ravel()
+    out = np.zeros_like(x)
+    _raygen_protos().orc_xmath_batch(which, _p(x), _p(y), len(x), _p(out))
+    return out
+
+
+def stream_keys(seed: int, elements) -> np.ndarray:
+    L = _raygen_protos()
+    return np.array([L.orc_stream_key(seed, int(e)) for e in elements], dtype=np.uint32)
+
+
+def hash2_stream(key: int, m: int) -> np.ndarray:
+    out = np.zeros(m, dtype=np.float32)
+    _raygen_protos().orc_hash2_stream(int(key), m, _p(out))
+    return out
+
+
+def _sample_args(normals, incident, xi, keys):
+    n = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    i = None if incident is None else np.ascontiguousarray(incident, dtype=np.float32).reshape(-1, 3)
+    x = None if xi is None else np.ascontiguousarray(xi, dtype=np.float32).reshape(-1, 2)
+    k = None if keys is None else np.ascontiguousarray(keys, dtype=np.uint32).ravel()
+    count = len(n) if n is not None else len(k)
+    return n, i, x, k, count
+
+
+def sample_directions(which: int, normals=None, incident=None, xi=None, keys=None, roughness: float = 0.0) -> np.ndarray:
+    """The oracle's restatement of the shaders' direction samplers (SAMPLE_*)."""
+    n, i, x, k, count = _sample_args(normals, incident, xi, keys)
+    out = np.zeros((count, 3), dtype=np.float32)
+    _raygen_protos().orc_sample_directions(which, _p(n), _p(i), _p(x), _p(k), roughness, count, _p(out))
+    return out
+
+
+def ref_sample_directions(which: int, normals=None, incident=None, xi=None, keys=None, roughness: float = 0.0) -> np.ndarray:
+    """The shader functions themselves, compiled (oracle/_ref, namespace ref_raygen): hash2() and the implementation-defined
+    built-ins bound to the oracle's definitions, everything else the shader's own text over the reference's glm."""
+    R = ref_lib()
+    R.ref_glsl_sample_directions.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p]
+    n, i, x, k, count = _sample_args(normals, incident, xi, keys)
+    out = np.zeros((count, 3), dtype=np.float32)
+    R.ref_glsl_sample_directions(which, _p(n), _p(i), _p(x), _p(k), roughness, count, _p(out))
+    return out
+
+
+def generate_rays(rays, hits, tris, verts, entities, kind=GEN_DIFFUSE, spp=1, seed=1, offset=0.05, tmax=1.0e6, roughness=0.0,
+                  light_dir=(0.0, 1.0, 0.0), light_cone=0.0, bucket_octants=False, ids=None):
+    """cndl_generate_rays_device restated: returns (rays_out, parent, ids_out)."""
+    L = _raygen_protos()
+    rays = np.ascontiguousarray(rays, dtype=RAY_DT)
+    hits = np.ascontiguousarray(hits, dtype=HIT_DT)
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
+    verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DT)
+    ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+    p = RaygenParams(kind, spp, seed, GEN_BUCKET_OCTANTS if bucket_octants else 0, offset, tmax, roughness, (C.c_float * 3)(*light_dir), light_cone)
+    out = np.zeros(len(rays) * spp, dtype=RAY_DT)
+    parent = np.zeros(len(rays) * spp, dtype=np.uint32)
+    ids_out = np.zeros(len(rays) * spp, dtype=np.uint32)
+    n = int(L.orc_generate_rays(C.byref(p), _p(rays), _p(hits), _p(ids), len(rays), _p(tris), _p(verts), _p(entities), _p(out), _p(parent), _p(ids_out)))
+    return out[:n].copy(), parent[:n].copy(), ids_out[:n].copy()
+
+
+def probe_rays(box_origin, size, res, seed: int) -> np.ndarray:
+    """Probe-update rays (UpdateRadianceProbes.glsl:408-427) for a res[0] x res[1] x res[2] grid."""
+    o = np.ascontiguousarray(box_origin, dtype=np.float32)
+    s = np.ascontiguousarray(size, dtype=np.float32)
+    r = np.ascontiguousarray(res, dtype=np.int32)
+    out = np.zeros(int(r[0]) * int(r[1]) * int(r[2]), dtype=RAY_DT)
+    _raygen_protos().orc_probe_rays(_p(o), _p(s), _p(r), seed, _p(out))
+    return out

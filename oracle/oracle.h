@@ -28,6 +28,15 @@
  *              committed outputs tests/golden/reference_traversal_golden.npz).
  *   GetData  : PINNED the same way (tests/test_get_data.py).
  *   collide  : PINNED against the compiled Physics.cpp (tests/test_collide.py).
+ *   ray generators: PINNED.  CosWeightedHemisphere, SampleGGXVNDF, SampleCone
+ *              (Include/Sampling.glsl), StochasticReflectionDirection
+ *              (SpecularTrace.glsl:102-135) and LambertBRDF / ImportanceSample
+ *              (UpdateRadianceProbes.glsl:351-374) are compiled from the shader
+ *              files with hash2() bound to the counter stream and sin / cos /
+ *              acos / pow bound to exact_math_ref.h (GLSL leaves both to the
+ *              implementation); tests/test_raygen_oracle.py requires identical
+ *              bits, and tests/golden/raygen_golden.npz carries the compiled
+ *              shaders' outputs to the GPU box.
  *
  * Build flags are part of the definition of "the reference result":
  *   g++ -std=c++17 -O2 -ffp-contract=off   (no -march=native, no -ffast-math)
@@ -138,6 +147,23 @@ void orc_get_data(const void* tris, const void* verts, const void* entities, con
  * stackless buffers.  out: n x {collided, mesh, tri, entity} (the first overlapping triangle in walk order). */
 void orc_collide_boxes(const void* nodes, uint64_t n_nodes, const void* tris, const void* verts, const void* entities, int32_t n_entities,
                        const float* boxes, uint64_t n, int32_t* out);
+
+/* ---- ray generators (oracle_raygen.cpp): the step in front of the path.  Bits of sin / cos / acos / pow and the random
+ * stream are DEFINED (exact_math_ref.h, pcg-hash counter stream); everything else follows the shader functions, which
+ * oracle/ref_shim compiles for the pin (tests/test_raygen_oracle.py). */
+typedef struct { int32_t kind, spp; uint32_t seed, flags; float offset, tmax, roughness; float light_dir[3]; float light_cone; } orc_raygen_params;
+float orc_xsin(float x);
+float orc_xcos(float x);
+float orc_xacos(float x);
+float orc_xpow(float x, float y);
+void orc_xmath_batch(int which, const float* x, const float* y, uint64_t n, float* out);
+void orc_sample_directions(int which, const float* normals, const float* incident, const float* xi, const uint32_t* keys, float roughness, uint64_t n,
+                           float* out);
+void orc_hash2_stream(uint32_t key, uint32_t m, float* out);
+uint32_t orc_stream_key(uint32_t seed, uint32_t element);
+uint64_t orc_generate_rays(const void* params, const orc_ray* rays, const orc_hit* hits, const uint32_t* ids_in, uint64_t R, const void* tris,
+                           const void* verts, const void* entities, orc_ray* out_rays, uint32_t* parent_out, uint32_t* ids_out);
+void orc_probe_rays(const float box_origin[3], const float size[3], const int32_t res[3], uint32_t seed, orc_ray* out);
 
 int orc_hardware_threads(void);
 

@@ -13,6 +13,10 @@ Nothing is copied into the repository: the output goes to oracle/_ref/ (git-igno
   * swizzles `.xyz` / `.xy` become `vec3(...)` / `vec2(...)` constructor calls on the same expression
   * the `IntersectRay*` convenience wrappers that pass a swizzle as an `out` argument are dropped (not needed:
     the shim calls IntersectScene* and GetData directly)
+  * `vec3(hash2(), hash2().x)` becomes `vec3{hash2(), hash2().x}`: GLSL evaluates constructor arguments left to
+    right, C++ leaves the order of function arguments unspecified, and brace initialisation restores the GLSL order
+
+`--function NAME` extracts one top-level function; `NAME@k` takes the k-th definition of an overloaded name (1-based).
 """
 import re
 import sys
@@ -97,6 +101,7 @@ def transliterate(text: str) -> str:
         ln = re.sub(r"(?<![\w.])in\s+(?=\w+\s+\w+\s*[,)])", "", ln)
         ln = re.sub(r"(?<![\w.])(\d+\.\d*|\.\d+)(?![\w.])", r"\1f", ln)   # 1.0 -> 1.0f ; 1. -> 1.f ; 1.0f untouched
         ln = rewrite_swizzles(ln)
+        ln = ln.replace("vec3(hash2(), hash2().x)", "vec3{hash2(), hash2().x}")
         out.append(ln)
         i += 1
     return "\n".join(out) + "\n"
@@ -105,8 +110,13 @@ def transliterate(text: str) -> str:
 def extract_function(text: str, name: str) -> str:
     """The definition of one top-level function (from its signature line to the closing brace in column 0)."""
     lines = text.splitlines()
+    name, _, nth = name.partition("@")
+    nth = int(nth or 1)
     for i, ln in enumerate(lines):
         if re.match(r"^\w[\w\s]*\b" + re.escape(name) + r"\s*\(", ln):
+            nth -= 1
+            if nth:
+                continue
             j = i
             while lines[j].rstrip() != "}":
                 j += 1

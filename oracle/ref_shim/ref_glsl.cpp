@@ -4,7 +4,8 @@
 // TraverseBVHStack.glsl) executed on the CPU: oracle/ref_shim/glsl_to_cpp.py rewrites the two include files
 // syntactically (qualifiers, literals, swizzles, SSBO blocks -> pointers) into oracle/_ref/gen/*.inc, and this
 // file compiles them against the reference's own vendored glm 0.9.8.5, whose vector functions follow the GLSL
-// specification (min(x,y) = y<x?y:x, max(x,y) = x<y?y:x, component-wise operators, mat*vec).  Compiled with
+// specification except that glm evaluates min(x,y) as x<y?x:y and max(x,y) as x>y?x:y (func_common.inl:14-27; the two forms
+// differ only for NaN operands, which GLSL leaves undefined).  Compiled with
 // -O2 -ffp-contract=off like the oracle, so every float operation is a separately rounded IEEE operation.
 // This is what pins the oracle's traversal restatement: tests require identical hit records.
 #include <cmath>
@@ -45,6 +46,48 @@ using namespace glm;
 #include "gen/cos_hemisphere.inc"
 #include "gen/ggx_vndf.inc"
 }  // namespace ref_sampling
+
+// The ray generators' direction samplers, compiled from the shader files with the two things GLSL leaves to the
+// implementation bound to ONE definition: hash2() (the shaders' fract(sin()) hash) draws from the counter stream of
+// oracle_raygen.cpp, and sin / cos / acos / pow are the functions of exact_math_ref.h.  Everything else — the order of
+// operations, normalize, cross, reflect, sqrt, mat3 * vec3 — is the shader's own text over the reference's glm.
+//   CosWeightedHemisphere, SampleGGXVNDF, SampleCone x2   Shaders/Include/Sampling.glsl:1-12, :63-83, :43-61
+//   StochasticReflectionDirection                          Shaders/SpecularTrace.glsl:102-135
+//   LambertBRDF, ImportanceSample                          Shaders/UpdateRadianceProbes.glsl:351-362, :365-406
+#include "exact_math_ref.h"
+namespace ref_raygen {
+using namespace glm;
+inline float sin(float x) { return xm::xsin(x); }
+inline float cos(float x) { return xm::xcos(x); }
+inline float acos(float x) { return xm::xacos(x); }
+inline float pow(float x, float y) { return xm::xpow(x, y); }
+static uint32_t g_key = 0, g_calls = 0;
+inline uint32_t pcg_hash(uint32_t v) {
+    const uint32_t s = v * 747796405u + 2891336453u;
+    const uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+    return (w >> 22u) ^ w;
+}
+inline float next_xi() { return (float)(pcg_hash(g_key + (g_calls++) * 0x9E3779B9u) >> 8) * (1.0f / 16777216.0f); }
+inline vec2 hash2() { const float a = next_xi(), b = next_xi(); return vec2(a, b); }
+#define PI 3.14159265359f  /* SpecularTrace.glsl:6 */
+#include "gen/cos_hemisphere.inc"
+#include "gen/ggx_vndf.inc"
+#include "gen/sample_cone_xi.inc"
+#include "gen/sample_cone_dir.inc"
+#include "gen/stochastic_reflection.inc"
+#undef PI
+#define PI 3.1415926535f   /* UpdateRadianceProbes.glsl:4 */
+// ImportanceSample's importance-sampling branch is switched off in the shader (`ShouldImportanceSample = false`); what it
+// names must exist for the text to compile, and is never reached
+struct ProbeMapPixel { vec2 Packed; };
+static const ProbeMapPixel* MapData = nullptr;
+inline int Get1DIdx(ivec2, ivec2) { std::abort(); }
+inline vec3 OctahedronToUnitVector(vec2) { std::abort(); }
+inline vec3 SampleDirectionCone(vec3) { std::abort(); }
+#include "gen/lambert_brdf.inc"
+#include "gen/importance_sample.inc"
+#undef PI
+}  // namespace ref_raygen
 
 namespace {
 struct Hit32 { float t, u, v, w; int32_t mesh, tri, entity, iters; };
@@ -141,6 +184,27 @@ void ref_glsl_sample(int which, const float* normals, const float* xi, float rou
         const glm::vec3 N(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
         const glm::vec2 X(xi[2 * i], xi[2 * i + 1]);
         const glm::vec3 d = which == 0 ? ref_sampling::CosWeightedHemisphere(N, X) : ref_sampling::SampleGGXVNDF(N, roughness, X);
+        out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+    }
+}
+
+// The shader functions of namespace ref_raygen on n inputs (same `which` numbering as orc_sample_directions):
+//   0 CosWeightedHemisphere(N, xi)   1 SampleGGXVNDF(N, roughness, xi)   2 StochasticReflectionDirection(I, N, roughness), hash2() = stream keys[i]
+//   3 SampleCone(N as Direction, xi, CosTheta = roughness argument)      4 ImportanceSample(0) (probe update), hash2() = stream keys[i]
+void ref_glsl_sample_directions(int which, const float* normals, const float* incident, const float* xi, const uint32_t* keys, float roughness, uint64_t n,
+                                float* out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        glm::vec3 N(0.0f), I(0.0f), d;
+        glm::vec2 X(0.0f);
+        if (normals) N = glm::vec3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+        if (incident) I = glm::vec3(incident[3 * i], incident[3 * i + 1], incident[3 * i + 2]);
+        if (xi) X = glm::vec2(xi[2 * i], xi[2 * i + 1]);
+        if (keys) { ref_raygen::g_key = keys[i]; ref_raygen::g_calls = 0; }
+        if (which == 0) d = ref_raygen::CosWeightedHemisphere(N, X);
+        else if (which == 1) d = ref_raygen::SampleGGXVNDF(N, roughness, X);
+        else if (which == 2) d = ref_raygen::StochasticReflectionDirection(I, N, roughness);
+        else if (which == 3) d = ref_raygen::SampleCone(N, X, roughness);
+        else d = ref_raygen::ImportanceSample(0);
         out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
     }
 }

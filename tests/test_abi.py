@@ -40,7 +40,7 @@ def test_record_layouts_match_the_reference():
 
 
 def test_abi_version(lib):
-    assert lib.cndl_abi_version() == 1
+    assert lib.cndl_abi_version() == 2
 
 
 def test_no_gpu_means_no_context(lib):

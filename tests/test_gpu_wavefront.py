@@ -22,141 +22,94 @@ def s260k(cb, ob):
     ri.close()
 
 
-def test_bounce_ray_generation_compacts_and_is_deterministic(cb, ob, s260k):
+def _gen_inputs(ri, W, H, cam=None, knock_out=0):
     import torch
-    from candela_b200 import api, scenes
-    ri = s260k["ri"]
-    W, H, spp = 640, 360, 3
-    iv, ip = scenes.camera((-18.0, 5.0, 0.7), (10.0, 30.0, -0.4), W, H)     # looks partly at the ceiling/out: some misses
+    from candela_b200 import scenes
+    iv, ip = scenes.camera(*cam, W, H) if cam else scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
     hits, rays = ri.IntersectPrimary(iv, ip, W, H, return_rays=True)
     hits = hits.copy()
-    hits["t"][::7] = -1.0                                                     # force misses into the batch
+    if knock_out:
+        hits["t"][::knock_out] = -1.0                                          # force misses into the batch
     d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
     d_hits = torch.from_numpy(hits.view(np.float32).reshape(-1, 8)).cuda()
-    outs = []
-    for _ in range(2):
-        d_out = torch.zeros((W * H * spp, 8), dtype=torch.float32, device="cuda")
-        d_par = torch.zeros(W * H * spp, dtype=torch.int32, device="cuda")
-        n = ri.generate_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), W * H, d_out.data_ptr(), spp=spp, offset=0.05, tmax=2.4, seed=9,
-                                           d_parent_out=d_par.data_ptr())
-        outs.append((n, d_out[:n].cpu().numpy().view(api.RAY_DT).reshape(-1), d_par[:n].cpu().numpy()))
-    n, out, par = outs[0]
+    return rays, hits, d_rays, d_hits
+
+
+def _run_gen(ri, kind, d_rays, d_hits, R, d_ids=None, **kw):
+    import torch
+    from candela_b200 import api
+    spp = kw.get("spp", 1)
+    d_out = torch.zeros((R * spp, 8), dtype=torch.float32, device="cuda")
+    d_par = torch.zeros(R * spp, dtype=torch.int32, device="cuda")
+    d_ido = torch.zeros(R * spp, dtype=torch.int32, device="cuda")
+    n = ri.generate_rays_device(kind, d_rays.data_ptr(), d_hits.data_ptr(), R, d_out.data_ptr(), d_parent_out=d_par.data_ptr(),
+                                d_ids_in=0 if d_ids is None else d_ids.data_ptr(), d_ids_out=d_ido.data_ptr(), **kw)
+    return d_out[:n].cpu().numpy().view(api.RAY_DT).reshape(-1), d_par[:n].cpu().numpy().view(np.uint32), d_ido[:n].cpu().numpy().view(np.uint32)
+
+
+def test_generated_rays_are_bit_identical_to_the_oracle(cb, ob, s260k):
+    """cndl_generate_rays_device == oracle/oracle_raygen.cpp (itself pinned against the compiled shader functions,
+    tests/test_raygen_oracle.py) for every kind, with misses in the batch, several samples per hit, the octant-major
+    order and caller-supplied stream ids: rays, parents and ids, bit for bit."""
+    import torch
+    from candela_b200 import api
+    ri = s260k["ri"]
+    W, H = 640, 360
+    rays, hits, d_rays, d_hits = _gen_inputs(ri, W, H, cam=((-18.0, 5.0, 0.7), (10.0, 30.0, -0.4)), knock_out=7)
+    R = W * H
+    L = np.array([0.3, 0.9, 0.2], np.float32)
+    L /= np.linalg.norm(L)
+    light = tuple(float(x) for x in L)
+    perm_ids = torch.from_numpy(np.random.default_rng(2).permutation(R).astype(np.int32)).cuda()
+    cases = [dict(kind=api.GEN_DIFFUSE, spp=3, offset=0.05, tmax=2.4, seed=9),
+             dict(kind=api.GEN_DIFFUSE, spp=1, offset=0.02, seed=31, bucket_octants=True),
+             dict(kind=api.GEN_DIFFUSE, spp=2, seed=5, ids=True),
+             dict(kind=api.GEN_SPECULAR, roughness=0.0, offset=-1.0, seed=11),
+             dict(kind=api.GEN_SPECULAR, roughness=0.3, offset=-1.0, seed=11),
+             dict(kind=api.GEN_SPECULAR, roughness=0.8, offset=-1.0, seed=12, bucket_octants=True),
+             dict(kind=api.GEN_SHADOW, light_dir=light, light_cone=0.0, tmax=200.0, offset=0.02),
+             dict(kind=api.GEN_SHADOW, light_dir=light, light_cone=0.05, spp=2, seed=4)]
+    for c in cases:
+        c = dict(c)
+        use_ids = c.pop("ids", False)
+        kind = c.pop("kind")
+        got = _run_gen(ri, kind, d_rays, d_hits, R, d_ids=perm_ids if use_ids else None, **c)
+        want = ob.generate_rays(rays, hits, s260k["tris"], s260k["v"], s260k["ents"], kind=kind,
+                                ids=perm_ids.cpu().numpy().view(np.uint32) if use_ids else None, **c)
+        assert len(got[0]) == len(want[0]) > 0, c
+        assert got[0].tobytes() == want[0].tobytes(), c
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), c
+    # compaction in input order; deterministic; the generated rays trace identically on GPU and oracle
+    out, par, _ = _run_gen(ri, api.GEN_DIFFUSE, d_rays, d_hits, R, spp=3, offset=0.05, tmax=2.4, seed=9)
     ok = hits["t"] > 0
-    assert n == spp * int(ok.sum())
-    assert np.array_equal(par, np.repeat(np.nonzero(ok)[0], spp))             # compacted in input order
-    assert outs[1][0] == n and outs[1][1].tobytes() == out.tobytes()          # deterministic
-    assert np.all(out["tmax"] == np.float32(2.4))
-    assert np.allclose(np.linalg.norm(out["d"], axis=1), 1.0, atol=1e-5)
-    # origin = hit point + 0.05 * normal, direction in the normal's hemisphere
-    P = rays["o"][par] + rays["d"][par] * hits["t"][par][:, None]
-    N = (out["o"] - P) / 0.05
-    assert np.allclose(np.linalg.norm(N, axis=1), 1.0, atol=2e-3)
-    assert np.all(np.sum(N * out["d"], axis=1) > -1e-3)
-    assert np.all(np.sum(N * rays["d"][par], axis=1) < 1e-3)                  # turned against the incoming ray
-    # the generated rays trace identically on GPU and oracle
+    assert len(out) == 3 * int(ok.sum()) and np.array_equal(par, np.repeat(np.nonzero(ok)[0], 3))
+    assert _run_gen(ri, api.GEN_DIFFUSE, d_rays, d_hits, R, spp=3, offset=0.05, tmax=2.4, seed=9)[0].tobytes() == out.tobytes()
     want, _ = ob.trace(ob.STACKLESS, ob.ANY, s260k["nodes"], s260k["tris"], s260k["v"], s260k["ents"], out, nthreads=ob.hardware_threads())
     assert ri.IntersectRaysAny(out).tobytes() == want.tobytes()
 
 
-def _pcg(v):
-    v = np.asarray(v, dtype=np.uint64) & np.uint64(0xFFFFFFFF)
-    s = (v * np.uint64(747796405) + np.uint64(2891336453)) & np.uint64(0xFFFFFFFF)
-    w = (((s >> ((s >> np.uint64(28)) + np.uint64(4))) ^ s) * np.uint64(277803737)) & np.uint64(0xFFFFFFFF)
-    return ((w >> np.uint64(22)) ^ w) & np.uint64(0xFFFFFFFF)
-
-
-def _u01(h):
-    return ((h >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)).astype(np.float32)
-
-
-def _specular_reference(I, N, rough_pbr, seed, idx):
-    """StochasticReflectionDirection restated (SpecularTrace.glsl:102-135 + Include/Sampling.glsl:63-83), spp = 1,
-    with the generator's counter-based xi instead of the shader's fract(sin()) hash."""
-    rough = np.float32(rough_pbr) * np.float32(0.9)
-    k = _pcg(np.uint64(seed) ^ _pcg(idx))
-    M = N.copy()
-    if rough >= 0.01:
-        a2 = np.float32(rough * rough) ** 2
-        up = np.where((np.abs(N[:, 2]) < 0.999)[:, None], np.array([0, 0, 1], np.float32), np.array([1, 0, 0], np.float32))
-        T = np.cross(up, N)
-        T /= np.linalg.norm(T, axis=1, keepdims=True)
-        B = np.cross(N, T)
-        found = np.zeros(len(N), bool)
-        for t in range(12):
-            x1 = _u01(_pcg(k + np.uint64((2 * t + 1) * 0x9E3779B9))) * np.float32(0.8)
-            x2 = _u01(_pcg(k + np.uint64((2 * t + 2) * 0x9E3779B9))) * np.float32(0.7)
-            phi = np.float32(2 * np.pi) * x1
-            ct = np.sqrt((1 - x2) / (1 + (a2 - 1) * x2))
-            st = np.sqrt(np.maximum(1 - ct * ct, 0))
-            S = T * (np.cos(phi) * st)[:, None] + B * (np.sin(phi) * st)[:, None] + N * ct[:, None]
-            S /= np.linalg.norm(S, axis=1, keepdims=True)
-            ok = (np.sum(S * N, axis=1) > 0.001) & ~found
-            M[ok] = S[ok]
-            found |= ok
-    D = I - 2 * np.sum(M * I, axis=1, keepdims=True) * M
-    return D / np.linalg.norm(D, axis=1, keepdims=True)
-
-
-def test_specular_shadow_and_bucketed_generation(cb, ob, s260k):
-    """cndl_generate_rays_device: specular rays against a numpy restatement of the reference's sampler, shadow rays,
-    and the octant-major emission order (a stable partition of the plain order)."""
+def test_probe_rays_equal_the_compiled_shader(cb, ob, s260k):
+    """cndl_generate_probe_rays_device for the reference's 48 x 24 x 48 probe grid (Macros.h:22-24): bit-identical to the
+    oracle, and its directions to the outputs of the compiled ImportanceSample (tests/golden/raygen_golden.npz)."""
     import torch
-    from candela_b200 import api, scenes
+    from candela_b200 import api
+    from conftest import GOLDEN
+    from golden.make_raygen_golden import PROBE_RES, PROBE_SEED
     ri = s260k["ri"]
-    W, H = 640, 360
-    iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
-    hits, rays = ri.IntersectPrimary(iv, ip, W, H, return_rays=True)
-    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
-    d_hits = torch.from_numpy(hits.view(np.float32).reshape(-1, 8)).cuda()
-    R = W * H
-    ok = np.nonzero(hits["t"] > 0)[0]
-
-    def run(kind, **kw):
-        spp = kw.get("spp", 1)
-        d_out = torch.zeros((R * spp, 8), dtype=torch.float32, device="cuda")
-        d_par = torch.zeros(R * spp, dtype=torch.int32, device="cuda")
-        n = ri.generate_rays_device(kind, d_rays.data_ptr(), d_hits.data_ptr(), R, d_out.data_ptr(), d_parent_out=d_par.data_ptr(), **kw)
-        return d_out[:n].cpu().numpy().view(api.RAY_DT).reshape(-1), d_par[:n].cpu().numpy()
-
-    # geometric normal and hit point, as the generator defines them
-    tv = s260k["tris"]["v"][hits["tri"][ok]]
-    Pv = s260k["v"]["position"][:, :3]
-    N = np.cross(Pv[tv[:, 1]] - Pv[tv[:, 0]], Pv[tv[:, 2]] - Pv[tv[:, 0]]).astype(np.float32)
-    N /= np.linalg.norm(N, axis=1, keepdims=True)
-    I = rays["d"][ok]
-    flip = np.sum(N * I, axis=1) > 0
-    N[flip] = -N[flip]
-    P = rays["o"][ok] + I * hits["t"][ok][:, None]
-
-    for rough in (0.0, 0.3, 0.8):
-        out, par = run(api.GEN_SPECULAR, roughness=rough, offset=-1.0, seed=11)
-        assert len(out) == len(ok) and np.array_equal(par, ok)
-        want = _specular_reference(I, N, rough, 11, ok.astype(np.uint64))
-        assert np.abs(out["d"] - want).max() < 2e-4, rough
-        off = 0.05 + 0.05 * min(max(rough * 1.4, 0.0), 1.0)
-        assert np.abs(out["o"] - (P + N * np.float32(off))).max() < 1e-4
-    mirror, _ = run(api.GEN_SPECULAR, roughness=0.0, offset=0.05)
-    assert np.abs(np.sum(mirror["d"] * N, axis=1) + np.sum(I * N, axis=1)).max() < 1e-5        # angle out = angle in
-
-    L = np.array([0.3, 0.9, 0.2], np.float32)
-    L /= np.linalg.norm(L)
-    sh, par = run(api.GEN_SHADOW, light_dir=tuple(float(x) for x in L), light_cone=0.0, tmax=200.0, offset=0.02)
-    lit = np.sum(N * L, axis=1) > 0
-    assert np.array_equal(par, ok[lit]) and np.abs(sh["d"] - L).max() < 1e-6 and np.all(sh["tmax"] == np.float32(200.0))
-    soft, _ = run(api.GEN_SHADOW, light_dir=tuple(float(x) for x in L), light_cone=0.05, spp=2, seed=4)
-    cosang = np.sum(soft["d"] * L, axis=1)
-    assert len(soft) == 2 * int(lit.sum()) and cosang.min() > np.cos(np.arcsin(0.05)) - 1e-4 and cosang.std() > 0
-
-    # octant-major emission = stable partition of the plain emission by the direction signs
-    plain, ppar = run(api.GEN_DIFFUSE, spp=3, seed=9)
-    buck, bpar = run(api.GEN_DIFFUSE, spp=3, seed=9, bucket_octants=True)
-    octant = (plain["d"][:, 0] > 0).astype(np.int64) | ((plain["d"][:, 1] > 0).astype(np.int64) << 1) | ((plain["d"][:, 2] > 0).astype(np.int64) << 2)
-    order = np.argsort(octant, kind="stable")
-    assert buck.tobytes() == plain[order].tobytes() and np.array_equal(bpar, ppar[order])
-    # and the traversal of the bucketed batch gives the same records, permuted
-    a = ri.IntersectRays(plain)
-    b = ri.IntersectRays(buck)
-    assert b.tobytes() == a[order].tobytes()
+    n = PROBE_RES[0] * PROBE_RES[1] * PROBE_RES[2]
+    d = torch.zeros((n, 8), dtype=torch.float32, device="cuda")
+    org, size = (0.5, 6.0, -0.25), (24.0, 12.0, 24.0)                         # PROBE_GRID_SIZE, Macros.h:26-29
+    ri.generate_probe_rays_device(org, size, PROBE_RES, PROBE_SEED, d.data_ptr())
+    torch.cuda.synchronize()
+    got = d.cpu().numpy().view(api.RAY_DT).reshape(-1)
+    want = ob.probe_rays(org, size, PROBE_RES, PROBE_SEED)
+    assert got.tobytes() == want.tobytes()
+    gold = np.load(GOLDEN / "raygen_golden.npz")["probe_grid_directions"]
+    assert np.ascontiguousarray(got["d"][::9]).tobytes() == gold.tobytes()
+    # and they trace identically
+    hits = ri.IntersectRays(got)
+    ref, _ = ob.trace(ob.STACKLESS, ob.CLOSEST, s260k["nodes"], s260k["tris"], s260k["v"], s260k["ents"], got, nthreads=ob.hardware_threads())
+    assert hits.tobytes() == ref.tobytes()
 
 
 def test_knobs_and_modes_never_change_results(cb, ob, s260k):
