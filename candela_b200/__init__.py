@@ -6,7 +6,7 @@ CPU implementation of the path and raises if the library is missing.
 """
 from . import api, scenes  # noqa: F401
 from .api import (BUILDER_LBVH, BUILDER_SAH_EXACT, STACK, STACKLESS, SWAP_HASHED, SWAP_NONE, BuildBVH, CandelaError, PinnedBuffer,  # noqa: F401
-                  RayIntersector, make_rays, make_vertices)
+                  MultiRayIntersector, RayIntersector, frame_params, make_rays, make_vertices)
 
-__all__ = ["api", "scenes", "RayIntersector", "BuildBVH", "CandelaError", "PinnedBuffer", "make_rays", "make_vertices", "STACKLESS", "STACK",
+__all__ = ["api", "scenes", "RayIntersector", "MultiRayIntersector", "frame_params", "BuildBVH", "CandelaError", "PinnedBuffer", "make_rays", "make_vertices", "STACKLESS", "STACK",
            "BUILDER_SAH_EXACT", "BUILDER_LBVH", "SWAP_NONE", "SWAP_HASHED"]

@@ -40,6 +40,12 @@ EXPORTS = [
     "cndl_model_load_obj", "cndl_model_load_gltf", "cndl_model_load", "cndl_model_free", "cndl_model_vertex_count", "cndl_model_index_count", "cndl_model_mesh_count", "cndl_model_vertices",
     "cndl_model_indices", "cndl_model_mesh_ids", "cndl_model_mesh_name", "cndl_add_model", "cndl_pack_half2x16", "cndl_save", "cndl_load", "cndl_build_bvh",
     "cndl_generate_probe_rays_device",
+    "cndl_frame_records", "cndl_frame_shard_records", "cndl_frame_record_bytes", "cndl_trace_frame_device", "cndl_frame_submit", "cndl_frame_wait",
+    "cndl_trace_frame", "cndl_frame_rays_traced", "cndl_frame_untile_device",
+    "cndl_multi_create", "cndl_multi_destroy", "cndl_multi_device_count", "cndl_multi_context", "cndl_multi_last_error", "cndl_multi_add_object",
+    "cndl_multi_commit", "cndl_multi_push_entity", "cndl_multi_buffer_entities", "cndl_multi_frame_submit", "cndl_multi_frame_wait",
+    "cndl_multi_trace_frame", "cndl_multi_frame_rays_traced", "cndl_multi_last_replicate_ms", "cndl_clone_scene", "cndl_add_prebuilt_object_device",
+    "cndl_object_device_view", "cndl_multi_set_transport",
 ]
 
 
@@ -58,6 +64,33 @@ class RaygenParams(C.Structure):
     """cndl_raygen_params (include/candela_b200.h)."""
     _fields_ = [("kind", C.c_int32), ("spp", C.c_int32), ("seed", C.c_uint32), ("flags", C.c_uint32), ("offset", C.c_float), ("tmax", C.c_float),
                 ("roughness", C.c_float), ("light_dir", C.c_float * 3), ("light_cone", C.c_float), ("d_ids_in", C.c_void_p), ("d_ids_out", C.c_void_p)]
+
+
+FRAME_OUT_HIT32, FRAME_OUT_HIT16, FRAME_OUT_PIXEL32 = 0, 1, 2
+FRAME_OCTANT_ORDER, FRAME_LOCAL_LAYOUT = 1, 2
+TRANSPORT_PEER_STORES, TRANSPORT_STAGED_COPY = 0, 1
+HIT16_DT = np.dtype([("t", "<f4"), ("tri", "<i4"), ("v", "<f4"), ("w", "<f4")])
+PIXEL_DT = np.dtype([("t", "<f4"), ("tri", "<i4"), ("v", "<f4"), ("w", "<f4"), ("ao", "<f4"), ("t_mean", "<f4"), ("rays", "<i4"), ("escaped", "<i4")])
+FRAME_RECORD_DT = {FRAME_OUT_HIT32: None, FRAME_OUT_HIT16: HIT16_DT, FRAME_OUT_PIXEL32: PIXEL_DT}   # HIT32 -> HIT_DT (defined above)
+
+
+class FrameParams(C.Structure):
+    """cndl_frame_params (include/candela_b200.h)."""
+    _fields_ = [("inv_view", C.c_float * 16), ("inv_proj", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32),
+                ("bounces", C.c_int32), ("seed", C.c_uint32), ("tile", C.c_int32), ("shard_index", C.c_int32), ("shard_count", C.c_int32),
+                ("out_format", C.c_int32), ("flags", C.c_uint32)]
+
+
+def frame_params(inv_view, inv_proj, width: int, height: int, spp: int = 1, bounces: int = 1, seed: int = 1, tile: int = 0, shard_index: int = 0,
+                 shard_count: int = 1, out_format: int = FRAME_OUT_HIT16, octant_order: bool = False, local_layout: bool = False) -> FrameParams:
+    """inv_view / inv_proj: 4x4 (row, column) matrices, as IntersectPrimary takes them."""
+    iv, ip = _colmajor(inv_view), _colmajor(inv_proj)
+    flags = (FRAME_OCTANT_ORDER if octant_order else 0) | (FRAME_LOCAL_LAYOUT if local_layout else 0)
+    return FrameParams((C.c_float * 16)(*iv), (C.c_float * 16)(*ip), width, height, spp, bounces, seed, tile, shard_index, shard_count, out_format, flags)
+
+
+def frame_record_dtype(out_format: int):
+    return HIT_DT if out_format == FRAME_OUT_HIT32 else FRAME_RECORD_DT[out_format]
 
 
 class BuildOpts(C.Structure):
@@ -111,6 +144,42 @@ def load_library() -> C.CDLL:
     L.cndl_get_data_device.argtypes = [vp, vp, sz, vp, vp]
     L.cndl_generate_rays_device.argtypes = [vp, C.POINTER(RaygenParams), vp, vp, sz, vp, vp, C.POINTER(sz), vp]
     L.cndl_generate_probe_rays_device.argtypes = [vp, vp, vp, vp, C.c_uint32, vp, vp]
+    fp = C.POINTER(FrameParams)
+    for f in ("cndl_frame_records", "cndl_frame_shard_records"):
+        getattr(L, f).argtypes = [fp]
+        getattr(L, f).restype = sz
+    L.cndl_frame_record_bytes.argtypes = [C.c_int]
+    L.cndl_frame_record_bytes.restype = sz
+    L.cndl_trace_frame_device.argtypes = [vp, fp, vp, C.c_int, vp]
+    L.cndl_frame_submit.argtypes = [vp, fp, vp, C.c_int]
+    L.cndl_frame_wait.argtypes = [vp, C.c_int]
+    L.cndl_trace_frame.argtypes = [vp, fp, vp]
+    L.cndl_frame_rays_traced.argtypes = [vp, C.c_int]
+    L.cndl_frame_rays_traced.restype = C.c_uint64
+    L.cndl_frame_untile_device.argtypes = [vp, fp, vp, vp, vp]
+    L.cndl_multi_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_int), C.c_int]
+    L.cndl_multi_destroy.argtypes = [vp]
+    L.cndl_multi_destroy.restype = None
+    L.cndl_multi_device_count.argtypes = [vp]
+    L.cndl_multi_context.argtypes = [vp, C.c_int]
+    L.cndl_multi_context.restype = vp
+    L.cndl_multi_last_error.argtypes = [vp]
+    L.cndl_multi_last_error.restype = C.c_char_p
+    L.cndl_multi_add_object.argtypes = [vp, C.c_uint32, vp, sz, vp, sz, vp, C.POINTER(BuildOpts)]
+    L.cndl_multi_commit.argtypes = [vp]
+    L.cndl_multi_push_entity.argtypes = [vp, C.c_uint32, vp, C.c_float, C.c_float]
+    L.cndl_multi_buffer_entities.argtypes = [vp]
+    L.cndl_multi_frame_submit.argtypes = [vp, fp, vp, C.c_int]
+    L.cndl_multi_frame_wait.argtypes = [vp, C.c_int]
+    L.cndl_multi_trace_frame.argtypes = [vp, fp, vp]
+    L.cndl_multi_frame_rays_traced.argtypes = [vp, C.c_int]
+    L.cndl_multi_frame_rays_traced.restype = C.c_uint64
+    L.cndl_multi_last_replicate_ms.argtypes = [vp]
+    L.cndl_multi_last_replicate_ms.restype = C.c_float
+    L.cndl_multi_set_transport.argtypes = [vp, C.c_int]
+    L.cndl_clone_scene.argtypes = [vp, vp]
+    L.cndl_add_prebuilt_object_device.argtypes = [vp, C.c_uint32, vp, sz, vp, sz, vp, sz, C.c_int32, C.c_int32]
+    L.cndl_object_device_view.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
     L.cndl_collide_boxes.argtypes = [vp, vp, sz, vp]
     L.cndl_collide_boxes_device.argtypes = [vp, vp, sz, vp, vp]
     for f in ("cndl_model_load_obj", "cndl_model_load_gltf", "cndl_model_load"):
@@ -262,7 +331,8 @@ class RayIntersector:
     # -- lifetime -------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.cndl_destroy(self._h)
+            if not getattr(self, "_borrowed", False):   # a MultiRayIntersector owns its per-device contexts
+                self._lib.cndl_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -455,8 +525,137 @@ class RayIntersector:
         iv, ip = _colmajor(inv_view), _colmajor(inv_proj)
         self._check(self._lib.cndl_intersect_primary_device(self._h, _p(iv), _p(ip), Width, Height, d_hits, d_rays or None, stream or None))
 
+    # -- frame-level calls (cndl_trace_frame and friends) --------------------------------------------------------------
+    def TraceFrame(self, params: "FrameParams", out=None) -> np.ndarray:
+        """One diffuse-GI frame on the device (camera rays -> hits -> diffuse rays -> hits -> records); returns the records of the
+        layout / format `params` selects.  `out` (optional): a numpy array over pinned memory (PinnedBuffer.array)."""
+        n = self.frame_records(params)
+        if out is None:
+            out = np.zeros(n, dtype=frame_record_dtype(params.out_format))
+        assert out.nbytes >= n * out.dtype.itemsize
+        self._check(self._lib.cndl_trace_frame(self._h, C.byref(params), _p(out)))
+        return out
+
+    def frame_records(self, params: "FrameParams") -> int:
+        f = self._lib.cndl_frame_shard_records if (params.flags & FRAME_LOCAL_LAYOUT) else self._lib.cndl_frame_records
+        return int(f(C.byref(params)))
+
+    def frame_submit(self, params: "FrameParams", out: np.ndarray, slot: int = 0):
+        self._check(self._lib.cndl_frame_submit(self._h, C.byref(params), _p(out), slot))
+
+    def frame_wait(self, slot: int = 0):
+        self._check(self._lib.cndl_frame_wait(self._h, slot))
+
+    def frame_rays_traced(self, slot: int = 0) -> int:
+        return int(self._lib.cndl_frame_rays_traced(self._h, slot))
+
+    def trace_frame_device(self, params: "FrameParams", d_out: int, slot: int = 0, stream: int = 0):
+        self._check(self._lib.cndl_trace_frame_device(self._h, C.byref(params), d_out, slot, stream or None))
+
+    def frame_untile_device(self, params: "FrameParams", d_shard: int, d_frame: int, stream: int = 0):
+        self._check(self._lib.cndl_frame_untile_device(self._h, C.byref(params), d_shard, d_frame, stream or None))
+
+    # -- scene replication ------------------------------------------------------------------------------------------------
+    def CloneSceneFrom(self, other: "RayIntersector"):
+        """Replicates every object of `other` (any device) into this EMPTY intersector, device to device; call BufferData() afterwards."""
+        self._check(self._lib.cndl_clone_scene(self._h, other._h))
+
+    def object_device_view(self, object_id: int) -> dict:
+        vs = [C.c_void_p() for _ in range(3)]
+        ns = [C.c_size_t() for _ in range(3)]
+        self._check(self._lib.cndl_object_device_view(self._h, object_id, C.byref(vs[0]), C.byref(ns[0]), C.byref(vs[1]), C.byref(ns[1]), C.byref(vs[2]), C.byref(ns[2])))
+        return dict(d_nodes=vs[0].value, n_nodes=ns[0].value, d_tris=vs[1].value, n_tris=ns[1].value, d_verts=vs[2].value, n_verts=ns[2].value)
+
+    def AddPrebuiltObjectDevice(self, object_id: int, d_nodes: int, n_nodes: int, d_tris: int, n_tris: int, d_verts: int, n_verts: int,
+                                vertex_index_base: int = 0, leaf_triangle_offset: int = 0):
+        self._check(self._lib.cndl_add_prebuilt_object_device(self._h, object_id, d_nodes, n_nodes, d_tris, n_tris, d_verts, n_verts, vertex_index_base,
+                                                              leaf_triangle_offset))
+
     def get_data_device(self, d_hits: int, n: int, d_out: int, stream: int = 0):
         self._check(self._lib.cndl_get_data_device(self._h, d_hits, n, d_out, stream or None))
 
     def collide_boxes_device(self, d_boxes: int, n: int, d_out: int, stream: int = 0):
         self._check(self._lib.cndl_collide_boxes_device(self._h, d_boxes, n, d_out, stream or None))
+
+
+class MultiRayIntersector:
+    """Several GPUs behind one handle (cndl_multi_*): the BVH replicated per device (built once, copied device to device), screen
+    tiles dealt round-robin, every device's records stored straight into the first device's frame over NVLink peer memory."""
+
+    def __init__(self, node_format: int = STACKLESS, devices=(0,)):
+        self._lib = load_library()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._lib.cndl_multi_create(C.byref(h), node_format, devs, len(devices))
+        if rc != 0:
+            raise CandelaError(rc, "cndl_multi_create failed: a device is missing or not sm_100 (there is no CPU fallback)")
+        self._h = h
+        self.devices = tuple(devices)
+        self.node_format = node_format
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cndl_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CandelaError(rc, self._lib.cndl_multi_last_error(self._h).decode())
+
+    def AddObject(self, object_id: int, verts, indices, mesh_ids=None, builder: int = BUILDER_SAH_EXACT, swap_policy: int = SWAP_NONE, swap_seed: int = 0):
+        verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+        indices = np.ascontiguousarray(indices, dtype=np.uint32).ravel()
+        if mesh_ids is not None:
+            mesh_ids = np.ascontiguousarray(mesh_ids, dtype=np.int32)
+        opts = BuildOpts(builder, swap_policy, swap_seed)
+        self._check(self._lib.cndl_multi_add_object(self._h, object_id, _p(verts), len(verts), _p(indices), len(indices), _p(mesh_ids), C.byref(opts)))
+
+    def BufferData(self, ClearCPUData: bool = True):
+        self._check(self._lib.cndl_multi_commit(self._h))
+
+    def PushEntity(self, object_id: int, model=None, emissive: float = 0.0, translucency: float = 0.0):
+        m = _colmajor(np.eye(4, dtype=np.float32) if model is None else model)
+        self._check(self._lib.cndl_multi_push_entity(self._h, object_id, _p(m), emissive, translucency))
+
+    def BufferEntities(self):
+        self._check(self._lib.cndl_multi_buffer_entities(self._h))
+
+    def context(self, i: int) -> "RayIntersector":
+        """A borrowed view of device i's context (do not close it)."""
+        ri = RayIntersector.__new__(RayIntersector)
+        ri._lib = self._lib
+        ri._borrowed = True
+        ri._h = C.c_void_p(self._lib.cndl_multi_context(self._h, i))
+        ri.node_format = self.node_format
+        ri.node_dtype = NODE_DT if self.node_format == STACKLESS else STACK_NODE_DT
+        return ri
+
+    def TraceFrame(self, params: FrameParams, out=None) -> np.ndarray:
+        n = int(self._lib.cndl_frame_records(C.byref(params)))
+        if out is None:
+            out = np.zeros(n, dtype=frame_record_dtype(params.out_format))
+        self._check(self._lib.cndl_multi_trace_frame(self._h, C.byref(params), _p(out)))
+        return out
+
+    def frame_submit(self, params: FrameParams, out: np.ndarray, slot: int = 0):
+        self._check(self._lib.cndl_multi_frame_submit(self._h, C.byref(params), _p(out), slot))
+
+    def frame_wait(self, slot: int = 0):
+        self._check(self._lib.cndl_multi_frame_wait(self._h, slot))
+
+    def frame_rays_traced(self, slot: int = 0) -> int:
+        return int(self._lib.cndl_multi_frame_rays_traced(self._h, slot))
+
+    def set_transport(self, transport: int):
+        """TRANSPORT_PEER_STORES (default where peer access exists) or TRANSPORT_STAGED_COPY."""
+        self._check(self._lib.cndl_multi_set_transport(self._h, transport))
+
+    @property
+    def last_replicate_ms(self) -> float:
+        return float(self._lib.cndl_multi_last_replicate_ms(self._h))

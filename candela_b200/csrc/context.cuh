@@ -51,6 +51,17 @@ constexpr int kCounterSlots = 64;
 
 struct ObjectData { int tri_offset, vert_offset, node_offset, node_count, tri_count, vert_count; };  // _ObjectData, Intersector.h:51-56 (+ counts)
 
+// Scratch of one frame in flight (frame.cu): two of these per context, so that the device->host copy of one frame overlaps
+// the tracing of the next.
+struct FrameSlot {
+    DeviceBuffer prim_rays, prim_hits, pix_ids, rays[2], hits, rids[2], gen_scratch, acc, out, counts;
+    unsigned* h_counts = nullptr;      // pinned: rays traced per bounce, copied back with the frame
+    int n_counts = 0;
+    cudaEvent_t traced = nullptr, copied = nullptr;
+    bool pending = false;
+    unsigned long long rays_traced = 0;
+};
+
 }  // namespace cndl
 
 struct cndl_ctx {
@@ -93,6 +104,8 @@ struct cndl_ctx {
     size_t build_arena_cap = 0;
     int* build_host_counts = nullptr;
     unsigned counter_next = 0;   // next_counter(): ring of work-counter slots for device calls
+    cndl::FrameSlot frame[2];
+    cudaStream_t frame_stream = nullptr, frame_copy_stream = nullptr;
     int tri_offset_bias = 0;  // cndl_build_bvh: BuildBVH's t_offset for a stand-alone build
 
     int fail(int code, const std::string& msg) { err = msg; return code; }

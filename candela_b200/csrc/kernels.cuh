@@ -49,6 +49,21 @@ void launch_octant_partition(const cndl_ray* rays, size_t R, unsigned* order, in
 void launch_collide_boxes(const SceneView& s, const float4* verts, const cndl_box* boxes, size_t n, cndl_collision* out, cudaStream_t stream,
                           LaunchCounter& lc);
 
+// The camera ray of pixel (x, y): main() of Intersectors/TraverseBVHStack.glsl:414-421 — TexCoords = vec2(Pixel) / u_Dims,
+// rD = normalize(GetRayDirectionAt(TexCoords)) (:133-138), rO = u_InverseView[3].xyz — in glm's operation order.
+struct Mat2 { float iv[16]; float ip[16]; };
+__device__ __forceinline__ void primary_ray(const Mat2& m, int x, int y, int W, int H, float4& o, float4& d) {
+    const float tx = fdiv((float)x, (float)W), ty = fdiv((float)y, (float)H);  // vec2(Pixel) / u_Dims
+    const float cx = fsub(fmul(tx, 2.0f), 1.0f), cy = fsub(fmul(ty, 2.0f), 1.0f);
+    const float* ip = m.ip;
+    const float ex = fadd(fadd(fmul(ip[0], cx), fmul(ip[4], cy)), fadd(fmul(ip[8], -1.0f), fmul(ip[12], 1.0f)));
+    const float ey = fadd(fadd(fmul(ip[1], cx), fmul(ip[5], cy)), fadd(fmul(ip[9], -1.0f), fmul(ip[13], 1.0f)));
+    const V3 dir = xform(m.iv, V3{ex, ey, -1.0f}, 0.0f);
+    const float inv_len = fdiv(1.0f, __fsqrt_rn(vdot(dir, dir)));  // glm::normalize: v * inversesqrt(dot(v,v))
+    o = make_float4(m.iv[12], m.iv[13], m.iv[14], 0.0f);
+    d = make_float4(fmul(dir.x, inv_len), fmul(dir.y, inv_len), fmul(dir.z, inv_len), 1000000.0f);
+}
+
 // Camera rays of the primary kernel (Intersectors/TraverseBVHStack.glsl:133-138,:414-431).
 void launch_primary_rays(const float* inv_view16, const float* inv_proj16, int W, int H, cndl_ray* rays, cudaStream_t stream,
                          LaunchCounter& lc);

@@ -278,21 +278,14 @@ __global__ void collide_boxes_kernel(SceneView s, const float4* __restrict__ ver
     out[q] = res;
 }
 
-struct Mat2 { float iv[16]; float ip[16]; };
-
 __global__ void primary_rays_kernel(Mat2 m, int W, int H, cndl_ray* __restrict__ rays) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
-    const float tx = fdiv((float)x, (float)W), ty = fdiv((float)y, (float)H);  // vec2(Pixel) / u_Dims
-    const float cx = fsub(fmul(tx, 2.0f), 1.0f), cy = fsub(fmul(ty, 2.0f), 1.0f);
-    const float* ip = m.ip;
-    const float ex = fadd(fadd(fmul(ip[0], cx), fmul(ip[4], cy)), fadd(fmul(ip[8], -1.0f), fmul(ip[12], 1.0f)));
-    const float ey = fadd(fadd(fmul(ip[1], cx), fmul(ip[5], cy)), fadd(fmul(ip[9], -1.0f), fmul(ip[13], 1.0f)));
-    const V3 dir = xform(m.iv, V3{ex, ey, -1.0f}, 0.0f);
-    const float inv_len = fdiv(1.0f, __fsqrt_rn(vdot(dir, dir)));  // glm::normalize: v * inversesqrt(dot(v,v))
+    float4 o, d;
+    primary_ray(m, x, y, W, H, o, d);
     float4* p = reinterpret_cast<float4*>(rays + ((size_t)y * (size_t)W + (size_t)x));
-    p[0] = make_float4(m.iv[12], m.iv[13], m.iv[14], 0.0f);
-    p[1] = make_float4(fmul(dir.x, inv_len), fmul(dir.y, inv_len), fmul(dir.z, inv_len), 1000000.0f);
+    p[0] = o;
+    p[1] = d;
 }
 
 template <bool STACK>

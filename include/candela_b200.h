@@ -211,6 +211,109 @@ int cndl_generate_bounce_rays_device(cndl_ctx* ctx, const cndl_ray* d_rays, cons
 int cndl_generate_probe_rays_device(cndl_ctx* ctx, const float box_origin[3], const float size[3], const int32_t res[3], uint32_t seed,
                                     cndl_ray* d_rays_out, void* stream);
 
+/* ---- Frame-level calls: one diffuse-GI frame without any ray ever crossing the host bus ---------------------------------
+ * In the reference the rays of a frame never exist on the host: DiffuseTrace.glsl:437-446 forms them in the shader from the
+ * G-buffer and traces them on the spot.  cndl_trace_frame does the same on the device: camera rays of the frame's pixels
+ * (as cndl_intersect_primary) -> closest hit -> CNDL_GEN_DIFFUSE rays (spp per pixel, offset 0.05, stream id = pixel index)
+ * -> IntersectRayIgnoreTransparent (:484) -> for bounce b = 1 .. bounces-1: one CNDL_GEN_DIFFUSE ray per surviving path
+ * (offset 0.02, seed + b, :516-517) -> IntersectRay (:518) -> one compact record per pixel (sample) written to the output.
+ * Only the 168-byte parameter block goes in and the records come out.
+ *
+ * Sharding: the frame is cut into tile x tile pixel tiles, tile t = ty * tiles_x + tx; a call with
+ * (shard_index, shard_count) traces the tiles with t % shard_count == shard_index and writes ONLY their pixels.  The random
+ * stream of a pixel depends on its index, not on the shard, so the shards of any shard_count assemble to the same frame, bit
+ * for bit.  Output layouts: the whole frame row-major (pixel * spp + sample; default — every shard writes its pixels into the
+ * same buffer, which may live on a peer GPU), or CNDL_FRAME_LOCAL_LAYOUT: this shard's slots only, tile-major
+ * ((local_tile * tile * tile + y_in_tile * tile + x_in_tile) * spp + sample, local_tile = t / shard_count; slots of edge tiles
+ * that fall outside the image hold miss records), for transports that move contiguous shards (cndl_frame_untile_device
+ * scatters one back into the row-major frame). */
+enum { CNDL_FRAME_OUT_HIT32 = 0,   /* cndl_hit of the diffuse ray of every (pixel, sample); bounces must be 1 */
+       CNDL_FRAME_OUT_HIT16 = 1,   /* the same as cndl_hit16 */
+       CNDL_FRAME_OUT_PIXEL32 = 2  /* one resolved cndl_pixel per pixel, any number of bounces */ };
+enum { CNDL_FRAME_OCTANT_ORDER = 1, /* every generated batch is emitted octant-major (CNDL_GEN_BUCKET_OCTANTS); results do not depend on it */
+       CNDL_FRAME_LOCAL_LAYOUT = 2 };
+/* Compact hit: t, tri and the barycentric weights of vertices B and C (cndl_hit.v, .w; u = 1 - v - w in that order of
+ * operations); mesh = triangle[tri].mesh.  Scenes with several entities need the 32-byte form (entity is not carried). */
+typedef struct cndl_hit16 { float t; int32_t tri; float v, w; } cndl_hit16;
+/* Resolved pixel of a multi-bounce frame.  t / tri / v / w: the camera ray's hit (compact form; t = -1: sky).  ao: mean over the
+ * pixel's samples of DiffuseTrace.glsl:494's AO term, t1 > 0 ? pow(clamp(t1 / 2.4, 0, 1), 1.23) : 1, t1 = the first diffuse
+ * ray's hit distance, summed in sample order (1 when the pixel traced nothing).  t_mean: mean of the t1 that hit (-1 if none).
+ * rays: diffuse rays traced for this pixel over all bounces.  escaped: those that reported no hit. */
+typedef struct cndl_pixel { float t; int32_t tri; float v, w; float ao, t_mean; int32_t rays, escaped; } cndl_pixel;
+typedef struct cndl_frame_params {
+    float inv_view[16], inv_proj[16]; /* column-major, as cndl_intersect_primary */
+    int32_t width, height;
+    int32_t spp;                      /* diffuse samples per pixel at the first bounce (>= 1) */
+    int32_t bounces;                  /* diffuse bounces per sample (>= 1; the reference's u_SecondaryBounces + 1) */
+    uint32_t seed;
+    int32_t tile;                     /* tile edge in pixels; 0 = 64 */
+    int32_t shard_index, shard_count; /* shard_count 0 or 1: the whole frame */
+    int32_t out_format;               /* CNDL_FRAME_OUT_* */
+    uint32_t flags;                   /* CNDL_FRAME_* */
+} cndl_frame_params;
+/* Records in the whole row-major frame / in this shard's local layout; bytes per record of the format. */
+size_t cndl_frame_records(const cndl_frame_params* p);
+size_t cndl_frame_shard_records(const cndl_frame_params* p);
+size_t cndl_frame_record_bytes(int out_format);
+/* Enqueues the shard's work on `stream` (not synchronised); d_out is a device pointer (this device's or a peer's with peer
+ * access enabled) in the layout the flags select.  `slot` (0 or 1) names one of two scratch sets, so two frames can be in
+ * flight.  cndl_frame_rays_traced (after the stream has been synchronised) = diffuse rays the last frame of that slot traced. */
+int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_out, int slot, void* stream);
+/* The same with a HOST output buffer (pinned memory makes the copy asynchronous): cndl_frame_submit enqueues frame + copy
+ * on the context's own stream pair and returns; cndl_frame_wait blocks until that slot's records are in host_out.
+ * Submitting slot 1 while slot 0's copy is in flight overlaps the device->host copy of one frame with the tracing of the
+ * next.  cndl_trace_frame = submit + wait on slot 0. */
+int cndl_frame_submit(cndl_ctx* ctx, const cndl_frame_params* p, void* host_out, int slot);
+int cndl_frame_wait(cndl_ctx* ctx, int slot);
+int cndl_trace_frame(cndl_ctx* ctx, const cndl_frame_params* p, void* host_out);
+uint64_t cndl_frame_rays_traced(const cndl_ctx* ctx, int slot);
+/* Scatters one shard in local layout (d_shard, as written with CNDL_FRAME_LOCAL_LAYOUT by the shard p names) into the
+ * row-major frame d_frame.  Enqueued on `stream`. */
+int cndl_frame_untile_device(cndl_ctx* ctx, const cndl_frame_params* p, const void* d_shard, void* d_frame, void* stream);
+
+/* ---- Several GPUs behind one handle: the BVH replicated per device, screen tiles dealt round-robin, hit
+ * records gathered for the final frame only.  One process drives all devices; the C++ mirror's RayIntersector holds one of
+ * these when it is given more than one device.  cndl_multi_add_object builds on the first device and replicates the
+ * reference-layout buffers device to device (cudaMemcpyPeerAsync over NVLink), so the scene is built once.
+ * cndl_multi_trace_frame: every device traces its shard and its resolve kernel stores the records straight into the first
+ * device's frame buffer through peer memory (NVLink; no index payload, no padding, no collective), then one device->host
+ * copy.  Without peer access the shards travel in local layout with cudaMemcpyPeerAsync and are untiled on the first device. */
+typedef struct cndl_multi cndl_multi;
+int cndl_multi_create(cndl_multi** out, int node_format, const int* devices, int n_devices);
+void cndl_multi_destroy(cndl_multi* m);
+int cndl_multi_device_count(const cndl_multi* m);
+cndl_ctx* cndl_multi_context(cndl_multi* m, int i);   /* borrowed; per-device queries go through the ordinary calls */
+const char* cndl_multi_last_error(const cndl_multi* m);
+int cndl_multi_add_object(cndl_multi* m, uint32_t object_id, const cndl_vertex* verts, size_t V, const uint32_t* indices, size_t I,
+                          const int32_t* mesh_id_per_tri, const cndl_build_opts* opts);
+int cndl_multi_commit(cndl_multi* m);
+int cndl_multi_push_entity(cndl_multi* m, uint32_t object_id, const float model[16], float emissive, float translucency);
+int cndl_multi_buffer_entities(cndl_multi* m);
+int cndl_multi_frame_submit(cndl_multi* m, const cndl_frame_params* p, void* host_out, int slot);  /* p's shard fields are ignored */
+int cndl_multi_frame_wait(cndl_multi* m, int slot);
+int cndl_multi_trace_frame(cndl_multi* m, const cndl_frame_params* p, void* host_out);
+uint64_t cndl_multi_frame_rays_traced(const cndl_multi* m, int slot);
+/* How the other devices' records reach the first device's frame: stored by their resolve kernels through peer memory (default
+ * where peer access can be enabled), or written in local layout, copied with cudaMemcpyPeerAsync and untiled on the first device
+ * (the only way without peer access).  Results are identical. */
+enum { CNDL_TRANSPORT_PEER_STORES = 0, CNDL_TRANSPORT_STAGED_COPY = 1 };
+int cndl_multi_set_transport(cndl_multi* m, int transport);
+float cndl_multi_last_replicate_ms(const cndl_multi* m);  /* device-to-device copy time of the last cndl_multi_add_object */
+/* Replicates every object of `src` (any device) into the EMPTY context `dst` device to device; call cndl_commit afterwards. */
+int cndl_clone_scene(cndl_ctx* dst, cndl_ctx* src);
+/* AddObject for reference-layout buffers that already live in device memory (this device's, or a peer's: the copy is a
+ * cudaMemcpyDefault) — e.g. another context's slices (cndl_object_device_view) or buffers received over NCCL.  Vertex indices in
+ * d_tris are relative to vertex_index_base (0 = object-local as BuildBVH leaves them; a view's indices are relative to minus
+ * its vertex_offset, i.e. pass vertex_offset); they are rebased to this context's running vertex count (Intersector.h:190-197).
+ * leaf_triangle_offset is the triangle offset the leaf packs embed (BuildBVH's t_offset): it must equal cndl_triangle_count(ctx),
+ * else CNDL_ERR_INVALID — so replicating a subset or a different order fails loudly instead of returning wrong triangles. */
+int cndl_add_prebuilt_object_device(cndl_ctx* ctx, uint32_t object_id, const void* d_nodes, size_t N, const cndl_triangle* d_tris, size_t T,
+                                    const cndl_vertex* d_verts, size_t V, int32_t vertex_index_base, int32_t leaf_triangle_offset);
+/* Device pointers and sizes of one object's slices of the reference-layout buffers (triangle vertex indices are GLOBAL there,
+ * leaf packs hold global triangle offsets); valid until the next add / commit.  Any out pointer may be NULL. */
+int cndl_object_device_view(cndl_ctx* ctx, uint32_t object_id, const void** d_nodes, size_t* N, const cndl_triangle** d_tris, size_t* T,
+                            const cndl_vertex** d_verts, size_t* V);
+
 /* GetData (…/Include/TraverseBVHStackless.glsl:370-408) without the texture fetch — the step right after
  * the path: for every hit record, the interpolated half-float vertex normal (normalised) and UV and the
  * entity's emissive / alpha floats.  A miss (t < 0 or mesh < 0) gives normal (-1,-1,-1) and zeros. */
