@@ -45,7 +45,7 @@ EXPORTS = [
     "cndl_multi_create", "cndl_multi_destroy", "cndl_multi_device_count", "cndl_multi_context", "cndl_multi_last_error", "cndl_multi_add_object",
     "cndl_multi_commit", "cndl_multi_push_entity", "cndl_multi_buffer_entities", "cndl_multi_frame_submit", "cndl_multi_frame_wait",
     "cndl_multi_trace_frame", "cndl_multi_frame_rays_traced", "cndl_multi_last_replicate_ms", "cndl_clone_scene", "cndl_add_prebuilt_object_device",
-    "cndl_object_device_view", "cndl_multi_set_transport",
+    "cndl_object_device_view", "cndl_multi_set_transport", "cndl_object_count", "cndl_object_ids",
 ]
 
 
@@ -177,6 +177,9 @@ def load_library() -> C.CDLL:
     L.cndl_multi_last_replicate_ms.argtypes = [vp]
     L.cndl_multi_last_replicate_ms.restype = C.c_float
     L.cndl_multi_set_transport.argtypes = [vp, C.c_int]
+    L.cndl_object_count.argtypes = [vp]
+    L.cndl_object_count.restype = sz
+    L.cndl_object_ids.argtypes = [vp, C.POINTER(C.c_uint32), sz]
     L.cndl_clone_scene.argtypes = [vp, vp]
     L.cndl_add_prebuilt_object_device.argtypes = [vp, C.c_uint32, vp, sz, vp, sz, vp, sz, C.c_int32, C.c_int32]
     L.cndl_object_device_view.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
@@ -396,6 +399,13 @@ class RayIntersector:
     def BufferEntities(self):
         """Intersector.h:227-239."""
         self._check(self._lib.cndl_buffer_entities(self._h))
+
+    def object_ids(self):
+        """Ids of the objects added so far."""
+        n = self._lib.cndl_object_count(self._h)
+        ids = (C.c_uint32 * max(n, 1))()
+        self._lib.cndl_object_ids(self._h, ids, n)
+        return [int(ids[k]) for k in range(n)]
 
     def object_data(self, object_id: int) -> dict:
         v = [C.c_int32() for _ in range(4)]

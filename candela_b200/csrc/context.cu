@@ -191,6 +191,19 @@ size_t cndl_entity_count(const cndl_ctx* ctx) { return ctx ? ctx->n_ents : 0; }
 uint64_t cndl_launch_count(const cndl_ctx* ctx) { return ctx ? ctx->launches.n : 0; }
 float cndl_last_build_ms(const cndl_ctx* ctx) { return ctx ? ctx->last_build_ms : 0.0f; }
 
+size_t cndl_object_count(const cndl_ctx* ctx) { return ctx ? ctx->objects.size() : 0; }
+
+size_t cndl_object_ids(const cndl_ctx* ctx, uint32_t* ids_out, size_t capacity) {
+    if (!ctx || !ids_out) return 0;
+    std::vector<std::pair<int, uint32_t>> order;
+    for (const auto& kv : ctx->objects) order.emplace_back(kv.second.node_offset, kv.first);
+    std::sort(order.begin(), order.end());
+    size_t n = 0;
+    for (const auto& o : order)
+        if (n < capacity) ids_out[n++] = o.second;
+    return n;
+}
+
 int cndl_get_object(const cndl_ctx* ctx, uint32_t object_id, int32_t* node_offset, int32_t* node_count, int32_t* triangle_offset,
                     int32_t* vertex_offset) {
     if (!ctx) return CNDL_ERR_INVALID;
@@ -337,15 +350,21 @@ int cndl_commit(cndl_ctx* ctx, int clear_host) try {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->main_stream;
     CK(ctx->tri48.ensure_scratch(ctx->n_tris * 48));
-    launch_make_tri48(static_cast<const int4*>(ctx->tris.p), static_cast<const float4*>(ctx->verts.p), ctx->n_tris,
-                      static_cast<float4*>(ctx->tri48.p), st, ctx->launches);
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));
-    ctx->committed_nodes = ctx->n_nodes;  // m_NodeCountBuffered, Intersector.h:345
-    ctx->committed_tris = ctx->n_tris;
-    ctx->committed = true;
+    ctx->committed = false;
     ctx->hot_ready = false;
     ctx->nodes_valid = false;
+    int* d_tri_flag = static_cast<int*>(ctx->d_counter.p) + 33;
+    int tri_flag = 0;
+    CK(cudaMemsetAsync(d_tri_flag, 0, sizeof(int), st));
+    launch_make_tri48(static_cast<const int4*>(ctx->tris.p), static_cast<const float4*>(ctx->verts.p), ctx->n_tris, ctx->n_verts,
+                      static_cast<float4*>(ctx->tri48.p), d_tri_flag, st, ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&tri_flag, d_tri_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (tri_flag) return ctx->fail(CNDL_ERR_INVALID, "a triangle names a vertex outside the vertex buffer (corrupt cache file or prebuilt buffer)");
+    const char* kBadLeaf = "a leaf names triangles outside the scene (corrupt cache file or prebuilt buffer)";
+    ctx->committed_nodes = ctx->n_nodes;  // m_NodeCountBuffered, Intersector.h:345
+    ctx->committed_tris = ctx->n_tris;
     ctx->h_objects.clear();
     for (const auto& kv : ctx->objects) ctx->h_objects.push_back(make_int2(kv.second.node_offset, kv.second.node_count));
     std::sort(ctx->h_objects.begin(), ctx->h_objects.end(), [](const int2& a, const int2& b) { return a.x < b.x; });
@@ -354,7 +373,9 @@ int cndl_commit(cndl_ctx* ctx, int clear_host) try {
         int invalid = 0;
         CK(validate_stack_nodes(static_cast<const float4*>(ctx->nodes.p), ctx->h_objects.data(), n_obj, ctx->n_tris, static_cast<int*>(ctx->d_counter.p) + 32,
                                 &invalid, st, ctx->launches));
+        if (invalid & 2) return ctx->fail(CNDL_ERR_INVALID, kBadLeaf);
         ctx->nodes_valid = invalid == 0;
+        ctx->committed = true;
         if (ctx->ents_buffered) {
             const int rc = upload_hot_entities(ctx);
             if (rc != CNDL_OK) return rc;
@@ -373,8 +394,10 @@ int cndl_commit(cndl_ctx* ctx, int clear_host) try {
         CK(derive_hot_layout(static_cast<const float4*>(ctx->nodes.p), N, static_cast<const int2*>(ctx->d_objects.p), ctx->h_objects.data(), n_obj,
                              ctx->n_tris, ctx->knobs[CNDL_KNOB_HOT_NODES], static_cast<float4*>(ctx->nodes2.p), static_cast<int*>(ctx->perm.p),
                              static_cast<int*>(ctx->hot_scratch.p), ctx->h_roots.data(), &ctx->n_hot, &invalid, st, ctx->launches));
+        if (invalid & 2) return ctx->fail(CNDL_ERR_INVALID, kBadLeaf);
         ctx->hot_ready = invalid == 0;  // a buffer with out-of-range links keeps the reference-layout kernel and its range checks
         ctx->nodes_valid = ctx->hot_ready;
+        ctx->committed = true;
         if (ctx->ents_buffered) {
             const int rc = upload_hot_entities(ctx);
             if (rc != CNDL_OK) return rc;

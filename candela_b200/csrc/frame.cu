@@ -9,6 +9,8 @@
 #include "context.cuh"
 #include "exact_trig.cuh"
 
+#include <chrono>
+
 using namespace cndl;
 
 namespace {
@@ -68,29 +70,31 @@ __global__ void frame_primary_kernel(Mat2 m, TileMap tm, unsigned P, cndl_ray* _
 }
 
 // Output of the hit formats (bounces == 1): element e = slot * spp + sample holds the record of the diffuse ray the
-// generator wrote at dest[e] (keys[e] < 8), or a miss when that sample emitted no ray.
+// generator wrote at dest[e] (keys[e] < 8), or a miss when that sample emitted no ray.  One thread per 16 bytes of output, so
+// that a warp's stores are contiguous (they may cross NVLink into a peer's frame).
 template <bool COMPACT>
 __global__ void frame_resolve_hits_kernel(unsigned n_elems, int spp, const unsigned* __restrict__ pix_ids, const unsigned char* __restrict__ keys,
-                                          const unsigned* __restrict__ dest, const cndl_hit* __restrict__ hits, void* __restrict__ out, int local_layout) {
-    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+                                          const unsigned* __restrict__ dest, const cndl_hit* __restrict__ hits, float4* __restrict__ out, int local_layout) {
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned e = COMPACT ? q : q >> 1, half = COMPACT ? 0u : q & 1u;
     if (e >= n_elems) return;
     const unsigned slot = e / (unsigned)spp, s = e - slot * (unsigned)spp;
     const unsigned pixel = __ldg(pix_ids + slot);
     if (pixel == 0xFFFFFFFFu && !local_layout) return;
-    float4 h0 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
-    int4 h1 = make_int4(-1, -1, -1, 0);
-    if (keys[e] < 8) {
-        const unsigned k = __ldg(dest + e);
-        h0 = __ldg(reinterpret_cast<const float4*>(hits + k));
-        h1 = __ldg(reinterpret_cast<const int4*>(hits + k) + 1);
-    }
+    const bool has = keys[e] < 8;
+    const unsigned k = has ? __ldg(dest + e) : 0u;
     const size_t idx = local_layout ? (size_t)e : (size_t)pixel * (size_t)spp + s;
     if (COMPACT) {
-        reinterpret_cast<float4*>(out)[idx] = make_float4(h0.x, __int_as_float(h1.y), h0.z, h0.w);
+        float4 r = make_float4(-1.0f, __int_as_float(-1), -1.0f, -1.0f);
+        if (has) {
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(hits + k));
+            r = make_float4(h0.x, __int_as_float(__ldg(&hits[k].tri)), h0.z, h0.w);
+        }
+        out[idx] = r;
     } else {
-        float4* q = reinterpret_cast<float4*>(out) + 2 * idx;
-        q[0] = h0;
-        reinterpret_cast<int4*>(q)[1] = h1;
+        float4 r = half ? make_float4(__int_as_float(-1), __int_as_float(-1), __int_as_float(-1), __int_as_float(0)) : make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+        if (has) r = __ldg(reinterpret_cast<const float4*>(hits + k) + half);
+        out[2 * idx + half] = r;
     }
 }
 
@@ -140,16 +144,15 @@ __global__ void frame_accumulate_kernel(TileMap tm, int spp, unsigned cap, const
     if (!(__ldg(&hits[k].t) > 0.0f)) atomicAdd(&acc[slot].escaped, 1);
 }
 
-__global__ void frame_write_pixels_kernel(unsigned P, const unsigned* __restrict__ pix_ids, const cndl_pixel* __restrict__ acc, cndl_pixel* __restrict__ out,
+// one thread per 16 bytes of output: contiguous stores (possibly into a peer's frame over NVLink)
+__global__ void frame_write_pixels_kernel(unsigned P, const unsigned* __restrict__ pix_ids, const float4* __restrict__ acc, float4* __restrict__ out,
                                           int local_layout) {
-    const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned slot = q >> 1, half = q & 1u;
     if (slot >= P) return;
     const unsigned pixel = __ldg(pix_ids + slot);
     if (pixel == 0xFFFFFFFFu && !local_layout) return;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(acc + slot)), b = __ldg(reinterpret_cast<const float4*>(acc + slot) + 1);
-    float4* q = reinterpret_cast<float4*>(out + (local_layout ? (size_t)slot : (size_t)pixel));
-    q[0] = a;
-    q[1] = b;
+    out[2 * (local_layout ? (size_t)slot : (size_t)pixel) + half] = __ldg(acc + 2 * (size_t)slot + half);
 }
 
 __global__ void frame_count_kernel(const unsigned* __restrict__ src, unsigned cap, unsigned* __restrict__ dst) { *dst = min(*src, cap); }
@@ -295,11 +298,12 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
             if (pixels) {
                 frame_first_bounce_kernel<<<g256, 256, 0, st>>>((unsigned)P, spp, keys, dest, prim_hits, hits, static_cast<cndl_pixel*>(f.acc.p));
             } else {
-                const unsigned ge = (unsigned)((cap + 255) / 256);
                 if (p->out_format == CNDL_FRAME_OUT_HIT16)
-                    frame_resolve_hits_kernel<true><<<ge, 256, 0, st>>>((unsigned)cap, spp, pix_ids, keys, dest, hits, d_out, local);
+                    frame_resolve_hits_kernel<true><<<(unsigned)((cap + 255) / 256), 256, 0, st>>>((unsigned)cap, spp, pix_ids, keys, dest, hits,
+                                                                                                  static_cast<float4*>(d_out), local);
                 else
-                    frame_resolve_hits_kernel<false><<<ge, 256, 0, st>>>((unsigned)cap, spp, pix_ids, keys, dest, hits, d_out, local);
+                    frame_resolve_hits_kernel<false><<<(unsigned)((2 * cap + 255) / 256), 256, 0, st>>>((unsigned)cap, spp, pix_ids, keys, dest, hits,
+                                                                                                       static_cast<float4*>(d_out), local);
             }
             ctx->launches.n++;
         } else {
@@ -313,7 +317,8 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
         src_cap = cap;
     }
     if (pixels) {
-        frame_write_pixels_kernel<<<g256, 256, 0, st>>>((unsigned)P, pix_ids, static_cast<const cndl_pixel*>(f.acc.p), static_cast<cndl_pixel*>(d_out), local);
+        frame_write_pixels_kernel<<<(unsigned)((2 * P + 255) / 256), 256, 0, st>>>((unsigned)P, pix_ids, static_cast<const float4*>(f.acc.p),
+                                                                                  static_cast<float4*>(d_out), local);
         ctx->launches.n++;
     }
     f.n_counts = p->bounces;
@@ -397,6 +402,71 @@ int cndl_frame_untile_device(cndl_ctx* ctx, const cndl_frame_params* p, const vo
 // ---------------------------------------------------------------------------------------------------------------------
 // Scene replication and several devices behind one handle.
 
+// AddObject for buffers in device memory, in three steps so that several destinations can be filled concurrently:
+// reserve (validates, grows the destination buffers; may synchronise), enqueue (asynchronous copies + index rebase on the
+// context's stream), finish (waits for the stream, records the object).
+namespace {
+
+int prebuilt_reserve(cndl_ctx* ctx, const void* d_nodes, size_t N, const cndl_triangle* d_tris, size_t T, const cndl_vertex* d_verts, size_t V,
+                     int32_t leaf_triangle_offset) {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!d_nodes || !d_tris || !d_verts || N == 0 || T == 0 || V == 0) return ctx->fail(CNDL_ERR_INVALID, "null or empty buffer");
+    if ((size_t)leaf_triangle_offset != ctx->n_tris)
+        return ctx->fail(CNDL_ERR_INVALID, "leaf packs embed triangle offset " + std::to_string(leaf_triangle_offset) + " but the context holds " +
+                                               std::to_string(ctx->n_tris) + " triangles: replicate all objects, in insertion order, into an empty context");
+    if (ctx->n_nodes + N > 0x7FFFFFF0ull || ctx->n_tris + T > (1ull << 27) || ctx->n_verts + V > 0x7FFFFFF0ull)
+        return ctx->fail(CNDL_ERR_INVALID, "scene exceeds the leaf-pack limits (2^27 triangles, BVHConstructor.cpp:794)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->main_stream;
+    const size_t ns = ctx->node_size;
+    CK(ctx->nodes.reserve((ctx->n_nodes + N + 1) * ns, st));
+    CK(ctx->tris.reserve((ctx->n_tris + T) * sizeof(cndl_triangle), st));
+    CK(ctx->verts.reserve((ctx->n_verts + V) * sizeof(cndl_vertex), st));
+    return CNDL_OK;
+}
+
+int prebuilt_enqueue(cndl_ctx* ctx, const void* d_nodes, size_t N, const cndl_triangle* d_tris, size_t T, const cndl_vertex* d_verts, size_t V,
+                     int32_t vertex_index_base) {
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->main_stream;
+    const size_t ns = ctx->node_size;
+    char* dn = static_cast<char*>(ctx->nodes.p) + ctx->n_nodes * ns;
+    char* dt = static_cast<char*>(ctx->tris.p) + ctx->n_tris * sizeof(cndl_triangle);
+    char* dv = static_cast<char*>(ctx->verts.p) + ctx->n_verts * sizeof(cndl_vertex);
+    CK(cudaMemcpyAsync(dn, d_nodes, N * ns, cudaMemcpyDefault, st));
+    CK(cudaMemsetAsync(dn + N * ns, 0, ns, st));
+    CK(cudaMemcpyAsync(dt, d_tris, T * sizeof(cndl_triangle), cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(dv, d_verts, V * sizeof(cndl_vertex), cudaMemcpyDefault, st));
+    const int delta = (int)ctx->n_verts - vertex_index_base;
+    if (delta != 0) launch_rebase_triangles(reinterpret_cast<int4*>(dt), T, delta, st, ctx->launches);  // Intersector.h:190-197
+    CK(cudaGetLastError());
+    return CNDL_OK;
+}
+
+int prebuilt_finish(cndl_ctx* ctx, uint32_t object_id, size_t N, size_t T, size_t V) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->main_stream));
+    const size_t ns = ctx->node_size;
+    ObjectData od;
+    od.node_offset = (int)ctx->n_nodes;
+    od.tri_offset = (int)ctx->n_tris;
+    od.vert_offset = (int)ctx->n_verts;
+    od.node_count = (int)N;
+    od.tri_count = (int)T;
+    od.vert_count = (int)V;
+    ctx->objects[object_id] = od;
+    ctx->n_nodes += N;
+    ctx->n_tris += T;
+    ctx->n_verts += V;
+    ctx->nodes.bytes = ctx->n_nodes * ns;
+    ctx->tris.bytes = ctx->n_tris * sizeof(cndl_triangle);
+    ctx->verts.bytes = ctx->n_verts * sizeof(cndl_vertex);
+    ctx->committed = false;
+    return CNDL_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int cndl_object_device_view(cndl_ctx* ctx, uint32_t object_id, const void** d_nodes, size_t* N, const cndl_triangle** d_tris, size_t* T,
@@ -416,46 +486,10 @@ int cndl_object_device_view(cndl_ctx* ctx, uint32_t object_id, const void** d_no
 
 int cndl_add_prebuilt_object_device(cndl_ctx* ctx, uint32_t object_id, const void* d_nodes, size_t N, const cndl_triangle* d_tris, size_t T,
                                     const cndl_vertex* d_verts, size_t V, int32_t vertex_index_base, int32_t leaf_triangle_offset) try {
-    if (!ctx) return CNDL_ERR_INVALID;
-    if (!d_nodes || !d_tris || !d_verts || N == 0 || T == 0 || V == 0) return ctx->fail(CNDL_ERR_INVALID, "null or empty buffer");
-    if ((size_t)leaf_triangle_offset != ctx->n_tris)
-        return ctx->fail(CNDL_ERR_INVALID, "leaf packs embed triangle offset " + std::to_string(leaf_triangle_offset) + " but the context holds " +
-                                               std::to_string(ctx->n_tris) + " triangles: replicate all objects, in insertion order, into an empty context");
-    if (ctx->n_nodes + N > 0x7FFFFFF0ull || ctx->n_tris + T > (1ull << 27) || ctx->n_verts + V > 0x7FFFFFF0ull)
-        return ctx->fail(CNDL_ERR_INVALID, "scene exceeds the leaf-pack limits (2^27 triangles, BVHConstructor.cpp:794)");
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->main_stream;
-    const size_t ns = ctx->node_size;
-    CK(ctx->nodes.reserve((ctx->n_nodes + N + 1) * ns, st));
-    CK(ctx->tris.reserve((ctx->n_tris + T) * sizeof(cndl_triangle), st));
-    CK(ctx->verts.reserve((ctx->n_verts + V) * sizeof(cndl_vertex), st));
-    char* dn = static_cast<char*>(ctx->nodes.p) + ctx->n_nodes * ns;
-    char* dt = static_cast<char*>(ctx->tris.p) + ctx->n_tris * sizeof(cndl_triangle);
-    char* dv = static_cast<char*>(ctx->verts.p) + ctx->n_verts * sizeof(cndl_vertex);
-    CK(cudaMemcpyAsync(dn, d_nodes, N * ns, cudaMemcpyDefault, st));
-    CK(cudaMemsetAsync(dn + N * ns, 0, ns, st));
-    CK(cudaMemcpyAsync(dt, d_tris, T * sizeof(cndl_triangle), cudaMemcpyDefault, st));
-    CK(cudaMemcpyAsync(dv, d_verts, V * sizeof(cndl_vertex), cudaMemcpyDefault, st));
-    const int delta = (int)ctx->n_verts - vertex_index_base;
-    if (delta != 0) launch_rebase_triangles(reinterpret_cast<int4*>(dt), T, delta, st, ctx->launches);  // Intersector.h:190-197
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));
-    ObjectData od;
-    od.node_offset = (int)ctx->n_nodes;
-    od.tri_offset = (int)ctx->n_tris;
-    od.vert_offset = (int)ctx->n_verts;
-    od.node_count = (int)N;
-    od.tri_count = (int)T;
-    od.vert_count = (int)V;
-    ctx->objects[object_id] = od;
-    ctx->n_nodes += N;
-    ctx->n_tris += T;
-    ctx->n_verts += V;
-    ctx->nodes.bytes = ctx->n_nodes * ns;
-    ctx->tris.bytes = ctx->n_tris * sizeof(cndl_triangle);
-    ctx->verts.bytes = ctx->n_verts * sizeof(cndl_vertex);
-    ctx->committed = false;
-    return CNDL_OK;
+    int rc = prebuilt_reserve(ctx, d_nodes, N, d_tris, T, d_verts, V, leaf_triangle_offset);
+    if (rc == CNDL_OK) rc = prebuilt_enqueue(ctx, d_nodes, N, d_tris, T, d_verts, V, vertex_index_base);
+    if (rc == CNDL_OK) rc = prebuilt_finish(ctx, object_id, N, T, V);
+    return rc;
 } CNDL_CATCH
 
 int cndl_clone_scene(cndl_ctx* dst, cndl_ctx* src) try {
@@ -574,25 +608,26 @@ int cndl_multi_add_object(cndl_multi* m, uint32_t object_id, const cndl_vertex* 
     int rc = cndl_add_object(c0, object_id, verts, V, indices, I, mesh_id_per_tri, opts);
     if (rc != CNDL_OK) return m->fail_from(rc, 0);
     const ObjectData o = c0->objects[object_id];
-    // replicate the object's reference-layout slices device to device; timed on the first device around all copies
-    cudaSetDevice(m->devices[0]);
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0, c0->main_stream);
-    cudaStreamSynchronize(c0->main_stream);
+    // replicate the object's reference-layout slices device to device: every destination reserves first, then all copies are in
+    // flight together (one source, NVLink to every peer), then every destination is waited for.  Host wall clock around the copies.
+    const void* sn = static_cast<const char*>(c0->nodes.p) + (size_t)o.node_offset * c0->node_size;
+    const cndl_triangle* stp = static_cast<const cndl_triangle*>(c0->tris.p) + o.tri_offset;
+    const cndl_vertex* sv = static_cast<const cndl_vertex*>(c0->verts.p) + o.vert_offset;
+    const size_t N = (size_t)o.node_count, T = (size_t)o.tri_count, Vn = (size_t)o.vert_count;
     for (size_t i = 1; i < m->ctx.size(); ++i) {
-        rc = cndl_add_prebuilt_object_device(m->ctx[i], object_id, static_cast<const char*>(c0->nodes.p) + (size_t)o.node_offset * c0->node_size,
-                                             (size_t)o.node_count, static_cast<const cndl_triangle*>(c0->tris.p) + o.tri_offset, (size_t)o.tri_count,
-                                             static_cast<const cndl_vertex*>(c0->verts.p) + o.vert_offset, (size_t)o.vert_count, o.vert_offset, o.tri_offset);
-        if (rc != CNDL_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return m->fail_from(rc, (int)i); }
+        rc = prebuilt_reserve(m->ctx[i], sn, N, stp, T, sv, Vn, o.tri_offset);
+        if (rc != CNDL_OK) return m->fail_from(rc, (int)i);
     }
-    cudaSetDevice(m->devices[0]);
-    cudaEventRecord(e1, c0->main_stream);
-    cudaEventSynchronize(e1);
-    cudaEventElapsedTime(&m->replicate_ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (size_t i = 1; i < m->ctx.size(); ++i) {
+        rc = prebuilt_enqueue(m->ctx[i], sn, N, stp, T, sv, Vn, o.vert_offset);
+        if (rc != CNDL_OK) return m->fail_from(rc, (int)i);
+    }
+    for (size_t i = 1; i < m->ctx.size(); ++i) {
+        rc = prebuilt_finish(m->ctx[i], object_id, N, T, Vn);
+        if (rc != CNDL_OK) return m->fail_from(rc, (int)i);
+    }
+    m->replicate_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return CNDL_OK;
 } CNDL_CATCH
 

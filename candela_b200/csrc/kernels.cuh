@@ -18,7 +18,8 @@ inline int current_device_slot() {
 }
 
 // Derives tri48 from the reference-layout triangle and vertex buffers (commit time).
-void launch_make_tri48(const int4* tris, const float4* verts /* 2 float4 per vertex */, size_t T, float4* tri48,
+// *d_invalid |= 4 when a triangle names a vertex outside [0, V).
+void launch_make_tri48(const int4* tris, const float4* verts /* 2 float4 per vertex */, size_t T, size_t V, float4* tri48, int* d_invalid,
                        cudaStream_t stream, LaunchCounter& lc);
 
 // Adds `offset` to the three vertex indices of T triangles (Intersector.h:190-197).
@@ -93,11 +94,11 @@ struct HotView {
 };
 size_t hot_scratch_ints(size_t N, int n_objects);
 // objects: (node_offset, node_count) per object in insertion order, on the device and on the host.
-// h_roots_out[o] = index of object o's root in nodes2; *h_invalid != 0 when a link or leaf range is out of bounds.
+// h_roots_out[o] = index of object o's root in nodes2; *h_invalid: bit 0 a link / first child leaves its object, bit 1 a leaf range leaves the scene.
 cudaError_t derive_hot_layout(const float4* nodes, size_t N, const int2* d_objects, const int2* h_objects, int n_objects, size_t n_tris, int H,
                               float4* nodes2, int* perm, int* scratch, int* h_roots_out, int* h_n_hot, int* h_invalid, cudaStream_t st,
                               LaunchCounter& lc);
-// Stack format: *h_invalid != 0 when a child slot or a leaf range is out of bounds (d_flag: one int of device scratch).
+// Stack format: *h_invalid bit 0: a child slot leaves its object, bit 1: a leaf range leaves the scene (d_flag: one int of device scratch).
 cudaError_t validate_stack_nodes(const float4* nodes, const int2* h_objects, int n_objects, size_t n_tris, int* d_flag, int* h_invalid, cudaStream_t st,
                                  LaunchCounter& lc);
 void launch_trace_hot(const SceneView& s, const HotView& hv, int kind, const cndl_ray* rays, size_t R, const RayOrder& order, cndl_hit* hits,

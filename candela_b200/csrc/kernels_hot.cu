@@ -122,20 +122,22 @@ __global__ void derive_nodes_kernel(const float4* __restrict__ nodes, int start,
     const int i = start + k;
     float4 lo = nodes[2 * (size_t)i], hi = nodes[2 * (size_t)i + 1];
     const int pack = __float_as_int(lo.w), link = __float_as_int(hi.w);
-    bool bad = false;
+    // invalid bit 0: a link or first child leaves the object (the reference-layout kernels with their range checks handle that like
+    // the shader does); bit 1: a leaf names triangles outside the scene (nothing can traverse that: cndl_commit fails)
+    int bad = 0;
     int word = pack, link2 = -1;
     if (pack == -1) {
-        if (k + 1 >= count) { bad = true; word = 0; }  // an inner node needs a first child inside the object
+        if (k + 1 >= count) { bad |= 1; word = 0; }  // an inner node needs a first child inside the object
         else word = ~perm[i + 1];
     } else {
         const int first = pack >> 4, len = pack & 0xF;
-        if (pack < 0 || first + len > n_tris) { bad = true; word = 0; }
+        if (pack < 0 || first + len > n_tris) { bad |= 2; word = 0; }
     }
     if (link >= 0) {
-        if (link >= count) bad = true;
+        if (link >= count) bad |= 1;
         else link2 = perm[start + link];
     }
-    if (bad) atomicExch(invalid, 1);
+    if (bad) atomicOr(invalid, bad);
     lo.w = __int_as_float(word);
     hi.w = __int_as_float(link2);
     const size_t j = (size_t)perm[i];
@@ -147,15 +149,15 @@ __global__ void derive_nodes_kernel(const float4* __restrict__ nodes, int start,
 __global__ void validate_stack_kernel(const float4* __restrict__ nodes, int start, int count, int n_tris, int* __restrict__ invalid) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
-    bool bad = false;
+    int bad = 0;  // bit 0: child slot outside the object; bit 1: leaf range outside the scene (see derive_nodes_kernel)
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
         const float4 mn = nodes[4 * (size_t)(start + k) + 2 * side], mx = nodes[4 * (size_t)(start + k) + 2 * side + 1];
         const int pack = __float_as_int(mn.w), slot = __float_as_int(mx.w);
-        if (pack == -1) bad = bad || slot < 0 || slot >= count;
-        else bad = bad || pack < 0 || (pack >> 4) + (pack & 0xF) > n_tris;
+        if (pack == -1) bad |= (slot < 0 || slot >= count) ? 1 : 0;
+        else bad |= (pack < 0 || (pack >> 4) + (pack & 0xF) > n_tris) ? 2 : 0;
     }
-    if (bad) atomicExch(invalid, 1);
+    if (bad) atomicOr(invalid, bad);
 }
 
 __global__ void gather_kernel(const int* __restrict__ perm, const int2* __restrict__ objects, int n, int* __restrict__ out) {

@@ -185,10 +185,16 @@ __global__ void __launch_bounds__(128, 4) trace_persistent_stackless_kernel(Scen
     }
 }
 
-__global__ void make_tri48_kernel(const int4* __restrict__ tris, const float4* __restrict__ verts, size_t T, float4* __restrict__ tri48) {
+__global__ void make_tri48_kernel(const int4* __restrict__ tris, const float4* __restrict__ verts, size_t T, unsigned V, float4* __restrict__ tri48,
+                                  int* __restrict__ invalid) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     const int4 t = tris[i];
+    if ((unsigned)t.x >= V || (unsigned)t.y >= V || (unsigned)t.z >= V) {  // a vertex index outside the vertex buffer (corrupt cache file / prebuilt buffer)
+        atomicOr(invalid, 4);
+        tri48[3 * i + 0] = tri48[3 * i + 1] = tri48[3 * i + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
     const float4 a = verts[2 * (size_t)t.x], b = verts[2 * (size_t)t.y], c = verts[2 * (size_t)t.z];
     const V3 v0 = {a.x, a.y, a.z};
     const V3 e1 = vsub(V3{b.x, b.y, b.z}, v0);  // v1v0, SL:81
@@ -330,9 +336,9 @@ void launch_trace_persistent(const SceneView& s, bool stack, int kind, const cnd
     lc.n++;
 }
 
-void launch_make_tri48(const int4* tris, const float4* verts, size_t T, float4* tri48, cudaStream_t stream, LaunchCounter& lc) {
+void launch_make_tri48(const int4* tris, const float4* verts, size_t T, size_t V, float4* tri48, int* d_invalid, cudaStream_t stream, LaunchCounter& lc) {
     if (T == 0) return;
-    make_tri48_kernel<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(tris, verts, T, tri48);
+    make_tri48_kernel<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(tris, verts, T, (unsigned)V, tri48, d_invalid);
     lc.n++;
 }
 

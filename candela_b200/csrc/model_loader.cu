@@ -421,7 +421,7 @@ int cndl_model_load_gltf(const char* path, int32_t first_mesh_number, cndl_model
             std::uint32_t len1, type1;
             std::memcpy(&len1, file.data() + at, 4);
             std::memcpy(&type1, file.data() + at + 4, 4);
-            if (type1 == 0x004E4942u && at + 8 + (size_t)len1 <= file.size()) glb_bin.assign(file.data() + at + 8, file.data() + at + 8 + len1);
+            if (type1 == 0x004E4942u && (size_t)len1 <= file.size() - (at + 8)) glb_bin.assign(file.data() + at + 8, file.data() + at + 8 + len1);
         }
     }
     JParser jp{json_begin, json_begin + json_len};
@@ -455,16 +455,21 @@ int cndl_model_load_gltf(const char* path, int32_t first_mesh_number, cndl_model
         const JVal* type = j.find("type");
         a.component = (int)j.integer("componentType", 0);
         a.width = !type ? 0 : type->str == "SCALAR" ? 1 : type->str == "VEC2" ? 2 : type->str == "VEC3" ? 3 : type->str == "VEC4" ? 4 : 0;
-        a.count = (size_t)j.integer("count", 0);
+        const long jcount = j.integer("count", 0);
+        if (jcount < 0) { why = "negative accessor count"; return false; }
+        a.count = (size_t)jcount;
         const JVal* nrm = j.find("normalized");
         a.normalized = nrm && nrm->type == JVal::Bool && nrm->b;
         const int cs = component_size(a.component);
         if (!cs || !a.width) { why = "unsupported accessor type"; return false; }
         const size_t elem = (size_t)cs * a.width;
-        const long bs = v.integer("byteStride", 0);
+        const long bs = v.integer("byteStride", 0), off_v = v.integer("byteOffset", 0), off_a = j.integer("byteOffset", 0);
+        if (bs < 0 || off_v < 0 || off_a < 0) { why = "negative byteStride / byteOffset"; return false; }
         a.stride = bs > 0 ? (size_t)bs : elem;
-        const size_t off = (size_t)v.integer("byteOffset", 0) + (size_t)j.integer("byteOffset", 0);
-        if (a.count && off + (a.count - 1) * a.stride + elem > buffers[buf].size()) { why = "accessor runs past its buffer"; return false; }
+        // overflow-safe range check: off + (count - 1) * stride + elem <= size, without forming a product that can wrap
+        const size_t size = buffers[buf].size(), off = (size_t)off_v + (size_t)off_a;
+        if (off < (size_t)off_v || off > size || elem > size - off) { if (a.count) { why = "accessor runs past its buffer"; return false; } }
+        else if (a.count && a.count - 1 > (size - off - elem) / a.stride) { why = "accessor runs past its buffer"; return false; }
         a.base = buffers[buf].data() + off;
         return true;
     };

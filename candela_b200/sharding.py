@@ -27,34 +27,51 @@ def shard_range(n: int, world: int, rank: int) -> tuple[int, int]:
     return lo, min(n, lo + per)
 
 
-def gather_frame(local_records, pixel_index, n_pixels: int, group=None):
-    """Assembles the final frame on every rank: `local_records` [n_local, K] (torch tensor on the
-    backend's device) belong to pixels `pixel_index` [n_local] (int64 tensor).  Returns [n_pixels, K].
-    One all_gather of padded shards; ranks may own different numbers of pixels."""
+def shard_slots(width: int, height: int, world: int, rank: int, tile: int = 64) -> np.ndarray:
+    """The tile map of the frame-level C calls (cndl_frame_params: tiles t = ty * tiles_x + tx dealt round-robin, shard `rank` owns
+    t % world == rank in ascending order): pixel index of every slot of the shard's LOCAL layout (local_tile * tile^2 +
+    y_in_tile * tile + x_in_tile), -1 for the padding slots of edge tiles.  len() == cndl_frame_shard_records for one record per pixel."""
+    tiles_x, tiles_y = (width + tile - 1) // tile, (height + tile - 1) // tile
+    tiles = np.arange(rank, tiles_x * tiles_y, world, dtype=np.int64)
+    ty, tx = np.divmod(tiles, tiles_x)
+    iy, ix = np.divmod(np.arange(tile * tile, dtype=np.int64), tile)
+    y = (ty[:, None] * tile + iy[None, :]).ravel()
+    x = (tx[:, None] * tile + ix[None, :]).ravel()
+    return np.where((x < width) & (y < height), y * width + x, -1)
+
+
+def gather_frame(local_records, width: int, height: int, tile: int = 64, group=None, untile=None):
+    """Final-frame gather without an index payload: every rank passes its shard in the local tile-major layout
+    ([slots, K] tensor, slots = len(shard_slots(...)), on the backend's device); rank 0 receives the shards (one gather of
+    equal-size buffers: shard 0 is the largest, the others are padded by at most one tile) and scatters them into the row-major
+    frame — the tile map is a pure function of (width, height, tile, world), so no pixel indices travel.  Returns the
+    [width * height, K] frame on rank 0 and None elsewhere.  `untile(shard_tensor, rank, frame_tensor)`: device-side scatter
+    (cndl_frame_untile_device); default: the numpy mapping above (CPU tensors)."""
     import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if world == 1:
-        out = torch.full((n_pixels, local_records.shape[1]), -1, dtype=local_records.dtype, device=local_records.device)
-        out[pixel_index] = local_records
-        return out
-    n_local = torch.tensor([local_records.shape[0]], dtype=torch.int64, device=local_records.device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    n_max = int(max(c.item() for c in counts))
-    pad_r = torch.zeros((n_max, local_records.shape[1]), dtype=local_records.dtype, device=local_records.device)
-    pad_i = torch.full((n_max,), -1, dtype=torch.int64, device=local_records.device)
-    pad_r[: local_records.shape[0]] = local_records
-    pad_i[: local_records.shape[0]] = pixel_index
-    all_r = [torch.empty_like(pad_r) for _ in range(world)]
-    all_i = [torch.empty_like(pad_i) for _ in range(world)]
-    dist.all_gather(all_r, pad_r, group=group)
-    dist.all_gather(all_i, pad_i, group=group)
-    out = torch.full((n_pixels, local_records.shape[1]), -1, dtype=local_records.dtype, device=local_records.device)
-    for r, i, c in zip(all_r, all_i, counts):
-        n = int(c.item())
-        out[i[:n]] = r[:n]
-    return out
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if multi else 1
+    rank = dist.get_rank(group) if multi else 0
+    n_max = len(shard_slots(width, height, world, 0, tile))
+    send = local_records
+    if local_records.shape[0] < n_max:
+        send = torch.zeros((n_max,) + tuple(local_records.shape[1:]), dtype=local_records.dtype, device=local_records.device)
+        send[: local_records.shape[0]] = local_records
+    shards = [send]
+    if multi:
+        shards = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+        dist.gather(send, shards, dst=0, group=group)
+    if rank != 0:
+        return None
+    frame = torch.full((width * height,) + tuple(local_records.shape[1:]), -1, dtype=local_records.dtype, device=local_records.device)
+    for r, sh in enumerate(shards):
+        if untile is not None:
+            untile(sh, r, frame)
+        else:
+            slots = torch.from_numpy(shard_slots(width, height, world, r, tile)).to(frame.device)
+            ok = slots >= 0
+            frame[slots[ok]] = sh[: len(slots)][ok]
+    return frame
 
 
 def reduce_timing(ms_local: float, units_local: float, device="cpu", group=None) -> tuple[float, float]:
@@ -97,34 +114,47 @@ def broadcast_arrays(arrays, src: int = 0, device="cpu", group=None):
     return out
 
 
-def broadcast_scene(ri, object_ids, src: int = 0, device="cuda", group=None):
-    """BVH distribution of SURVEY.md §8e: rank `src` has built (or loaded) the objects `object_ids` in `ri`; every
-    other rank passes an empty intersector of the same node format and receives them as prebuilt objects
-    (reference-layout nodes / triangles / vertices), so the scene is built once and replicated over NVLink.
-    Call BufferData() afterwards on every rank."""
+class _DevicePtr:
+    """A raw device pointer as a torch-importable object (__cuda_array_interface__), so that NCCL can send straight from / into
+    the intersector's own buffers."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def broadcast_scene(ri, object_ids=None, src: int = 0, device="cuda", group=None):
+    """BVH distribution of SURVEY.md §8e, device to device: rank `src` has built (or loaded) its objects in `ri`; every other rank
+    passes an EMPTY intersector of the same node format and receives ALL of them, in insertion order, as prebuilt objects:
+    NCCL broadcasts straight out of rank src's reference-layout buffers (cndl_object_device_view) into device tensors, which
+    cndl_add_prebuilt_object_device appends with a device-to-device copy — nothing crosses the host bus.  Leaf packs embed global
+    triangle offsets, so a subset or a different order cannot be replicated: the receiver checks every object's offset and fails
+    loudly.  `object_ids`, when given, must be the complete list in insertion order (checked).  Call BufferData() afterwards."""
+    import torch
     import torch.distributed as dist
-    from . import api
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     rank = dist.get_rank(group)
-    arrays = None
+    meta = [None]
     if rank == src:
-        nodes, tris, verts = ri.read_buffers()
-        arrays = []
-        for oid in object_ids:
-            o = ri.object_data(oid)
-            ends = sorted(ri.object_data(x)["tri_offset"] for x in object_ids) + [len(tris)]
-            vends = sorted(ri.object_data(x)["vert_offset"] for x in object_ids) + [len(verts)]
-            t1 = min(e for e in ends if e > o["tri_offset"])
-            v1 = min(e for e in vends if e > o["vert_offset"])
-            t = tris[o["tri_offset"]:t1].copy()
-            t["v"] -= o["vert_offset"]          # AddPrebuiltObject takes object-local vertex indices (Intersector.h:190-197 rebases them)
-            arrays += [nodes[o["node_offset"]:o["node_offset"] + o["node_count"]], t, verts[o["vert_offset"]:v1]]
-    arrays = broadcast_arrays(arrays, src, device, group)
-    if rank != src:
-        for k, oid in enumerate(object_ids):
-            n, t, v = arrays[3 * k:3 * k + 3]
-            ri.AddPrebuiltObject(oid, n.view(ri.node_dtype), t.view(api.TRIANGLE_DT), v.view(api.VERTEX_DT))
+        ids = sorted(ri.object_ids(), key=lambda oid: ri.object_data(oid)["node_offset"])
+        if object_ids is not None and list(object_ids) != ids:
+            raise ValueError(f"broadcast_scene replicates the whole scene in insertion order {ids}; got {list(object_ids)}")
+        meta = [[(oid, ri.object_data(oid), {k: v for k, v in ri.object_device_view(oid).items() if k.startswith("n_")}) for oid in ids]]
+    dist.broadcast_object_list(meta, src=src, group=group, device=torch.device(device))
+    node_size = 32 if ri.node_format == 0 else 64
+    for oid, od, view in meta[0]:
+        sizes = (view["n_nodes"] * node_size, view["n_tris"] * 16, view["n_verts"] * 32)
+        if rank == src:
+            v = ri.object_device_view(oid)
+            bufs = [torch.as_tensor(_DevicePtr(p, n), device=device) for p, n in zip((v["d_nodes"], v["d_tris"], v["d_verts"]), sizes)]
+        else:
+            bufs = [torch.empty(n, dtype=torch.uint8, device=device) for n in sizes]
+        for b in bufs:
+            dist.broadcast(b, src, group=group)
+        if rank != src:
+            torch.cuda.synchronize()
+            ri.AddPrebuiltObjectDevice(oid, bufs[0].data_ptr(), view["n_nodes"], bufs[1].data_ptr(), view["n_tris"], bufs[2].data_ptr(), view["n_verts"],
+                                       vertex_index_base=od["vert_offset"], leaf_triangle_offset=od["tri_offset"])
 
 
 def bind_to_gpu_numa_node(gpu_index: int) -> bool:

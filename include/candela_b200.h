@@ -111,6 +111,10 @@ size_t cndl_vertex_count(const cndl_ctx* ctx);
 int cndl_get_object(const cndl_ctx* ctx, uint32_t object_id, int32_t* node_offset, int32_t* node_count,
                     int32_t* triangle_offset, int32_t* vertex_offset);
 
+/* Number of objects added, and their ids in insertion order (ids_out holds `capacity` entries; returns the number written). */
+size_t cndl_object_count(const cndl_ctx* ctx);
+size_t cndl_object_ids(const cndl_ctx* ctx, uint32_t* ids_out, size_t capacity);
+
 /* BVH::BuildBVH (BVHConstructor.h:86-87, BVHConstructor.cpp:951-1108) as a stand-alone call, for callers that want the
  * flattened buffers themselves: builds on GPU `device` and returns host buffers exactly as the reference's function
  * leaves them in FlattenedNodes / FlattenedTris — leaf packs include tri_offset (its `int t_offset`), triangle records

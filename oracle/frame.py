@@ -24,14 +24,19 @@ def _default_tracer(fmt, nodes, tris, verts, ents, threads):
     return trace
 
 
-def diffuse_batches(fmt, nodes, tris, verts, ents, inv_view, inv_proj, W, H, spp=1, bounces=1, seed=1, tracer=None, threads=None):
-    """Yields (bounce, rays, ray ids, hits, kind) for every diffuse batch of the frame, plus the camera pass first as bounce -1."""
+def diffuse_batches(fmt, nodes, tris, verts, ents, inv_view, inv_proj, W, H, spp=1, bounces=1, seed=1, tracer=None, threads=None, pixels=None):
+    """Yields (bounce, rays, ray ids, hits, kind) for every diffuse batch of the frame, plus the camera pass first as bounce -1.
+    `pixels` (optional): only these pixel indices (e.g. one shard of the frame) are traced."""
     threads = threads or ob.hardware_threads()
     trace = tracer or _default_tracer(fmt, nodes, tris, verts, ents, threads)
     prim = ob.primary_rays(inv_view, inv_proj, W, H)
+    pix_ids = np.arange(W * H, dtype=np.uint32)
+    if pixels is not None:
+        pix_ids = np.ascontiguousarray(pixels, dtype=np.uint32)
+        prim = np.ascontiguousarray(prim[pix_ids])
     phits = trace(ob.CLOSEST, prim)
-    yield -1, prim, np.arange(W * H, dtype=np.uint32), phits, ob.CLOSEST
-    src_rays, src_hits, src_ids = prim, phits, np.arange(W * H, dtype=np.uint32)
+    yield -1, prim, pix_ids, phits, ob.CLOSEST
+    src_rays, src_hits, src_ids = prim, phits, pix_ids
     for b in range(bounces):
         rays, _, rids = ob.generate_rays(src_rays, src_hits, tris, verts, ents, kind=ob.GEN_DIFFUSE, spp=spp if b == 0 else 1, seed=(seed + b) & 0xFFFFFFFF,
                                          offset=0.05 if b == 0 else 0.02, tmax=1.0e6, ids=src_ids)
@@ -41,8 +46,10 @@ def diffuse_batches(fmt, nodes, tris, verts, ents, inv_view, inv_proj, W, H, spp
         src_rays, src_hits, src_ids = rays, hits, rids
 
 
-def trace_frame(fmt, nodes, tris, verts, ents, inv_view, inv_proj, W, H, spp=1, bounces=1, seed=1, out_format=OUT_HIT16, tracer=None, threads=None):
-    """Returns (records of the whole row-major frame, diffuse rays traced)."""
+def trace_frame(fmt, nodes, tris, verts, ents, inv_view, inv_proj, W, H, spp=1, bounces=1, seed=1, out_format=OUT_HIT16, tracer=None, threads=None,
+                pixels=None):
+    """Returns (records of the whole row-major frame, diffuse rays traced).  With `pixels`, only those pixels are traced; the rest of
+    the frame keeps miss records / zeroed pixels (compare on `pixels` only)."""
     n_pix = W * H
     traced = 0
     if out_format in (OUT_HIT32, OUT_HIT16):
@@ -53,10 +60,13 @@ def trace_frame(fmt, nodes, tris, verts, ents, inv_view, inv_proj, W, H, spp=1, 
         for f in ("mesh", "tri", "entity"):
             out32[f] = -1
     acc = None
-    for b, rays, rids, hits, _ in diffuse_batches(fmt, nodes, tris, verts, ents, inv_view, inv_proj, W, H, spp, bounces, seed, tracer, threads):
+    for b, rays, rids, hits, _ in diffuse_batches(fmt, nodes, tris, verts, ents, inv_view, inv_proj, W, H, spp, bounces, seed, tracer, threads, pixels):
         if b == -1:
             acc = np.zeros(n_pix, dtype=PIXEL_DT)
-            acc["t"], acc["tri"], acc["v"], acc["w"] = hits["t"], hits["tri"], hits["v"], hits["w"]
+            acc["ao"] = 1.0
+            acc["t_mean"] = -1.0
+            for f in ("t", "tri", "v", "w"):
+                acc[f][rids] = hits[f]
             continue
         traced += len(rays)
         if b == 0:

@@ -40,3 +40,19 @@ def cb():
     from candela_b200 import api
     api.load_library()
     return candela_b200
+
+
+@pytest.fixture(scope="session")
+def s260k(cb, ob):
+    """The ~260k-triangle benchmark scene on the GPU (stackless) with the buffers the oracle needs."""
+    from candela_b200 import scenes
+    v, i, m = scenes.make_s260k()
+    ri = candela = cb.RayIntersector(cb.STACKLESS)
+    ri.AddObject(2, v, i, m)
+    ri.BufferData()
+    ri.PushEntity(2)
+    ri.BufferEntities()
+    nodes, tris, _ = ri.read_buffers()
+    ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(nodes))
+    yield dict(ri=ri, v=v, i=i, m=m, nodes=nodes, tris=tris, ents=ents)
+    candela.close()

@@ -183,6 +183,17 @@ def test_gltf_errors(cb, tmp_path):
                                      '"meshes":[{"primitives":[{"attributes":{"POSITION":0}}]}]}')
     with pytest.raises(cb.CandelaError, match="past its buffer"):
         cb.api.load_model(tmp_path / "c.gltf")
+    # crafted sizes that would wrap a naive `off + (count - 1) * stride + elem` check: negative offsets / counts, a huge count, a huge stride
+    tmpl = ('{"asset":{"version":"2.0"},"buffers":[{"uri":"data:application/octet-stream;base64,' + "A" * 64 + '","byteLength":48}],'
+            '"bufferViews":[{"buffer":0,"byteLength":48%s}],"accessors":[{"bufferView":0,"componentType":5126,"count":%s,"type":"VEC3"%s}],'
+            '"meshes":[{"primitives":[{"attributes":{"POSITION":0}}]}]}')
+    for k, (view_extra, count, acc_extra, msg) in enumerate(((', "byteOffset": -16', "3", "", "negative"), ("", "-1", "", "negative"), ("", "3", ', "byteOffset": -4', "negative"),
+                                                             ("", "1537228672809129302", "", "past its buffer"), (', "byteStride": -12', "3", "", "negative"),
+                                                             (', "byteStride": 4611686018427387904', "5", "", "past its buffer"), ("", "9223372036854775807", "", "past its buffer|negative"))):
+        f = tmp_path / f"crafted{k}.gltf"
+        f.write_text(tmpl % (view_extra, count, acc_extra))
+        with pytest.raises(cb.CandelaError, match=msg):
+            cb.api.load_model(f)
 
 
 @pytest.mark.gpu
@@ -223,6 +234,33 @@ def test_loaded_model_builds_and_cache_round_trips(cb, ob, golden_meshes, tmp_pa
         assert r2.IntersectRays(rays).tobytes() == want.tobytes()
         with pytest.raises(cb.CandelaError, match="empty context"):
             r2.Load(cache)
+        # a corrupt cache file is refused at BufferData instead of being traversed: a vertex index outside the vertex buffer, a leaf range
+        # outside the triangle buffer
+        raw = bytearray(cache.read_bytes())
+        head = 8 + 8 + 4 * 8                                             # magic, version + format, four 64-bit counts
+        n_obj, n_nodes, n_tris, n_verts = np.frombuffer(bytes(raw[16:48]), dtype=np.uint64)
+        node_size = 32 if fmt == cb.STACKLESS else 64
+        tri_at = head + int(n_obj) * 28 + int(n_nodes) * node_size
+        for what, at, value in (("vertex", tri_at + 16 * 7 + 4, int(n_verts) + 5), ("leaf", None, None)):
+            bad = bytearray(raw)
+            if what == "vertex":
+                bad[at:at + 4] = np.int32(value).tobytes()
+            else:
+                nodes_at = head + int(n_obj) * 28
+                nb = np.frombuffer(bytes(bad[nodes_at:nodes_at + int(n_nodes) * node_size]), dtype=np.int32).reshape(-1, node_size // 4).copy()
+                packs = nb[:, 3]                                          # Min.w (stackless) / left child's Min.w (stack)
+                k = int(np.nonzero((packs != -1) & (packs > 0))[0][5])
+                nb[k, 3] = ((int(n_tris) + 100) << 4) | 2
+                bad[nodes_at:nodes_at + int(n_nodes) * node_size] = nb.tobytes()
+            cf = tmp_path / f"corrupt_{what}_{fmt}.cndl"
+            cf.write_bytes(bytes(bad))
+            r3 = cb.RayIntersector(fmt)
+            r3.Load(cf)
+            with pytest.raises(cb.CandelaError, match="outside the"):
+                r3.BufferData()
+            with pytest.raises(cb.CandelaError):
+                r3.IntersectRays(rays[:10])                              # nothing committed: no traversal of the corrupt buffers
+            r3.close()
         other = cb.RayIntersector(cb.STACK if fmt == cb.STACKLESS else cb.STACKLESS)
         with pytest.raises(cb.CandelaError, match="node format"):
             other.Load(cache)

@@ -7,21 +7,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def s260k(cb, ob):
-    from candela_b200 import scenes
-    v, i, m = scenes.make_s260k()
-    ri = cb.RayIntersector(cb.STACKLESS)
-    ri.AddObject(2, v, i, m)
-    ri.BufferData()
-    ri.PushEntity(2)
-    ri.BufferEntities()
-    nodes, tris, _ = ri.read_buffers()
-    ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(nodes))
-    yield dict(ri=ri, v=v, nodes=nodes, tris=tris, ents=ents)
-    ri.close()
-
-
 def _gen_inputs(ri, W, H, cam=None, knock_out=0):
     import torch
     from candela_b200 import scenes

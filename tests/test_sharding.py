@@ -39,16 +39,45 @@ def _free_port():
     return p
 
 
+def test_shard_slots_match_the_c_tile_map():
+    """sharding.shard_slots is the Python statement of frame.cu's TileMap: sizes agree with cndl_frame_shard_records, the shards of any
+    world size partition the pixels, shard 0 is the largest, and the slot order is tile-major / row-major inside a tile."""
+    import ctypes as C
+    import candela_b200 as cb
+    from candela_b200 import api
+    L = api.load_library()
+    for W, H, tile in ((200, 130, 64), (1920, 1080, 64), (97, 33, 16), (64, 64, 64), (5, 300, 7)):
+        for world in (1, 2, 3, 8):
+            seen = []
+            sizes = []
+            for r in range(world):
+                sl = sharding.shard_slots(W, H, world, r, tile)
+                p = cb.frame_params(np.eye(4), np.eye(4), W, H, spp=1, tile=tile, shard_index=r, shard_count=world, out_format=api.FRAME_OUT_PIXEL32, local_layout=True)
+                assert len(sl) == L.cndl_frame_shard_records(C.byref(p))
+                sizes.append(len(sl))
+                pix = sl[sl >= 0]
+                seen.append(pix)
+                tid = sharding.tile_ids(W, H, tile)[pix]
+                assert np.all(tid % world == r) and np.all(np.diff(tid) >= 0)
+            allpix = np.concatenate(seen)
+            assert len(allpix) == W * H and len(np.unique(allpix)) == W * H
+            assert sizes[0] == max(sizes) and max(sizes) - min(sizes) <= tile * tile
+    p = cb.frame_params(np.eye(4), np.eye(4), 3840, 2160, spp=8, out_format=api.FRAME_OUT_HIT16)
+    assert L.cndl_frame_records(C.byref(p)) == 3840 * 2160 * 8 and L.cndl_frame_record_bytes(api.FRAME_OUT_HIT16) == 16
+
+
 def _worker(rank, world, port, W, H, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    pix = sharding.shard_pixels(W, H, world, rank, tile=16)
-    # a stand-in for this rank's hit records: 8 floats per pixel derived from the pixel index
-    rec = torch.from_numpy(np.stack([pix * 1.0 + k for k in range(8)], 1).astype(np.float32))
-    frame = sharding.gather_frame(rec, torch.from_numpy(pix), W * H)
-    t, u = sharding.reduce_timing(10.0 + rank, float(len(pix)))
+    slots = sharding.shard_slots(W, H, world, rank, tile=16)
+    # a stand-in for this rank's records in the local tile-major layout: 8 floats per slot derived from the pixel index (padding: -7)
+    rec = torch.from_numpy(np.stack([np.where(slots >= 0, slots * 1.0 + k, -7.0) for k in range(8)], 1).astype(np.float32))
+    frame = sharding.gather_frame(rec, W, H, tile=16)
+    t, u = sharding.reduce_timing(10.0 + rank, float(np.count_nonzero(slots >= 0)))
     if rank == 0:
         out.put((frame.numpy(), t, u))
+    else:
+        assert frame is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,10 +100,10 @@ def test_gather_frame_and_timing_world2():
 
 
 def test_single_process_gather_is_identity():
-    pix = sharding.shard_pixels(40, 30, 1, 0)
-    rec = torch.arange(len(pix) * 8, dtype=torch.float32).reshape(-1, 8)
-    frame = sharding.gather_frame(rec, torch.from_numpy(pix), 40 * 30)
-    assert torch.equal(frame[torch.from_numpy(pix)], rec)
+    slots = sharding.shard_slots(40, 30, 1, 0, tile=16)
+    rec = torch.from_numpy(np.stack([np.where(slots >= 0, slots * 2.0, -1.0)] * 3, 1).astype(np.float32))
+    frame = sharding.gather_frame(rec, 40, 30, tile=16)
+    assert torch.equal(frame[:, 0], torch.arange(40 * 30, dtype=torch.float32) * 2)
 
 
 def _bcast_worker(rank, world, port, out):
