@@ -31,7 +31,8 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
 
 // sort_rays = 2: order[0..R) = ray indices sorted by (direction octant, Morton code of the origin cell inside lo..hi).
 size_t ray_sort_scratch_ints(size_t R);
-cudaError_t sort_rays_morton(const cndl_ray* rays, size_t R, const float lo[3], const float hi[3], unsigned* order_out, int* scratch, cudaStream_t st,
+// order_out[pos] = original index of the ray sorted to pos; sorted_out (optional, R rays): the rays moved to their sorted places
+cudaError_t sort_rays_morton(const cndl_ray* rays, size_t R, const float lo[3], const float hi[3], unsigned* order_out, cndl_ray* sorted_out, int* scratch, cudaStream_t st,
                              LaunchCounter& lc);
 
 // Morton helper shared by the LBVH builder and the ray ordering

@@ -56,7 +56,7 @@ unsigned* next_counter(cndl_ctx* ctx) {
 // Enqueues one traversal batch on `st`.  scratch: 16 unsigned ints ([0] work counter, [8..15] octant counts);
 // order_region: order_region_ints(R) unsigned ints, used when ray bucketing is on.
 int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, const unsigned* d_R, cndl_hit* d_hits, float* d_any, unsigned* scratch,
-                  unsigned* order_region, cudaStream_t st) {
+                  unsigned* order_region, cndl_ray* sorted_region, cudaStream_t st) {
     if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 rays in one call");
     if (d_R && ctx->mode != 2) return ctx->fail(CNDL_ERR_INVALID, "a device-side batch length needs traversal mode 2");
     const SceneView s = scene_view(ctx);
@@ -64,23 +64,32 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, con
     if (ctx->mode == 0 || (stack && ctx->mode == 1)) launch_trace_simple(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, st, ctx->launches);
     else if (ctx->mode == 1) launch_trace_persistent(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, scratch, ctx->sm_count, st, ctx->launches);
     else {
-        RayOrder order{nullptr, nullptr, 0, d_R};
+        RayOrder order{nullptr, nullptr, 0, d_R, nullptr};
         if (ctx->sort_rays && order_region && R >= 65536 && !d_R) {
-            if (ctx->sort_rays == 2) {
-                cudaError_t se = sort_rays_morton(d_rays, R, ctx->world_lo, ctx->world_hi, order_region, reinterpret_cast<int*>(order_region + R), st,
+            if (ctx->sort_rays >= 2) {
+                // 2: the rays are MOVED into sorted order (sorted_region) and the results scattered back through the index list;
+                // 3: the rays stay and are read through the index list
+                cndl_ray* sorted = ctx->sort_rays == 2 ? sorted_region : nullptr;
+                cudaError_t se = sort_rays_morton(d_rays, R, ctx->world_lo, ctx->world_hi, order_region, sorted, reinterpret_cast<int*>(order_region + R), st,
                                                   ctx->launches);
                 if (se != cudaSuccess) return ctx->cuda_fail(se, "ray sort");
+                if (sorted) {
+                    d_rays = sorted;
+                    order = RayOrder{nullptr, nullptr, 0, nullptr, order_region};
+                } else {
+                    order = RayOrder{order_region, nullptr, 0, nullptr, nullptr};
+                }
             } else {
                 launch_octant_partition(d_rays, R, order_region, reinterpret_cast<int*>(order_region + R), st, ctx->launches);
+                order = RayOrder{order_region, nullptr, 0, nullptr, nullptr};
             }
-            order = RayOrder{order_region, nullptr, 0, nullptr};
         }
         int variant = ctx->knobs[CNDL_KNOB_VARIANT];
         if (variant == 0) {
             // automatic: a scene that fits the 126 MB L2 is served best by the plain kernel; once the node and triangle
             // records spill to DRAM, staging the top of the tree in shared memory wins (10 M triangles: +8.7 %)
             const size_t working_set = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 48;
-            variant = (!stack && working_set > ((size_t)96 << 20)) ? 34 : 18;
+            variant = (!stack && working_set > ((size_t)96 << 20) && order.out_index == nullptr) ? 34 : 18;  // physically sorted rays: L2 hits rise and the plain kernel's higher residency wins (4.85 vs 5.20 ms)
         }
         int steps = variant & 7;
         if (steps < 1 || steps > 4) steps = 2;
@@ -488,7 +497,7 @@ int cndl_buffer_entities(cndl_ctx* ctx) try {
 } CNDL_CATCH
 
 int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays) {
-    if (!ctx || mode < 0 || mode > 2 || sort_rays < 0 || sort_rays > 2) return CNDL_ERR_INVALID;
+    if (!ctx || mode < 0 || mode > 2 || sort_rays < 0 || sort_rays > 3) return CNDL_ERR_INVALID;
     ctx->mode = mode;
     ctx->sort_rays = sort_rays;
     return CNDL_OK;
@@ -509,8 +518,9 @@ int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t 
     CK(cudaSetDevice(ctx->device));
     const int kind = (flags & CNDL_IGNORE_TRANSPARENT) ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST;
     if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
+    if (ctx->sort_rays == 2) CK(ctx->d_sorted.ensure_scratch(R * sizeof(cndl_ray)));
     return enqueue_trace(ctx, kind, d_rays, R, nullptr, d_hits, nullptr, next_counter(ctx), static_cast<unsigned*>(ctx->d_order.p),
-                         static_cast<cudaStream_t>(stream));
+                         static_cast<cndl_ray*>(ctx->d_sorted.p), static_cast<cudaStream_t>(stream));
 } CNDL_CATCH
 
 int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, float* d_t_out, void* stream) try {
@@ -520,8 +530,9 @@ int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, f
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
+    if (ctx->sort_rays == 2) CK(ctx->d_sorted.ensure_scratch(R * sizeof(cndl_ray)));
     return enqueue_trace(ctx, Q_ANY, d_rays, R, nullptr, nullptr, d_t_out, next_counter(ctx), static_cast<unsigned*>(ctx->d_order.p),
-                         static_cast<cudaStream_t>(stream));
+                         static_cast<cndl_ray*>(ctx->d_sorted.p), static_cast<cudaStream_t>(stream));
 } CNDL_CATCH
 
 // Host-buffer queries: the batch is cut into chunks that rotate over three streams, so the
@@ -550,6 +561,7 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
     }
     CK(ctx->d_chunk_counters.ensure_scratch(n_chunks * 64));
     if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch((order_region_ints(chunk) * n_chunks) * sizeof(unsigned)));
+    if (ctx->sort_rays == 2) CK(ctx->d_sorted.ensure_scratch(R * sizeof(cndl_ray)));
     size_t k = 0;
     for (size_t lo = 0; lo < R; lo += chunk, ++k) {
         const size_t n = R - lo < chunk ? R - lo : chunk;
@@ -562,7 +574,8 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
         unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->d_chunk_counters.p) + 64 * k);
         rc = enqueue_trace(ctx, kind, dr, n, nullptr, kind == Q_ANY ? nullptr : reinterpret_cast<cndl_hit*>(dout),
                            kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter,
-                           ctx->sort_rays ? static_cast<unsigned*>(ctx->d_order.p) + order_region_ints(chunk) * k : nullptr, ks);
+                           ctx->sort_rays ? static_cast<unsigned*>(ctx->d_order.p) + order_region_ints(chunk) * k : nullptr,
+                           ctx->sort_rays == 2 ? static_cast<cndl_ray*>(ctx->d_sorted.p) + lo : nullptr, ks);
         if (rc != CNDL_OK) return rc;
         CK(cudaEventRecord(ctx->events[2 * k + 1], ks));
         CK(cudaStreamWaitEvent(ctx->streams[2], ctx->events[2 * k + 1], 0));
@@ -601,7 +614,7 @@ int cndl_intersect_primary_device(cndl_ctx* ctx, const float inv_view[16], const
     }
     launch_primary_rays(inv_view, inv_proj, W, H, dr, st, ctx->launches);
     CK(cudaGetLastError());
-    return enqueue_trace(ctx, Q_CLOSEST, dr, R, nullptr, d_hits, nullptr, next_counter(ctx), nullptr, st);  // camera rays are coherent already
+    return enqueue_trace(ctx, Q_CLOSEST, dr, R, nullptr, d_hits, nullptr, next_counter(ctx), nullptr, nullptr, st);  // camera rays are coherent already
 } CNDL_CATCH
 
 int cndl_intersect_primary(cndl_ctx* ctx, const float inv_view[16], const float inv_proj[16], int W, int H, cndl_hit* hits,

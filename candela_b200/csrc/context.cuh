@@ -83,11 +83,11 @@ struct cndl_ctx {
     bool ents_buffered = false;
 
     // query scratch
-    cndl::DeviceBuffer d_rays, d_hits, d_order, d_keys, d_sort_tmp, d_counter, d_chunk_counters;
+    cndl::DeviceBuffer d_rays, d_hits, d_order, d_keys, d_sort_tmp, d_counter, d_chunk_counters, d_sorted;
     std::vector<cudaEvent_t> events;
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};  // H2D, traversal (even chunks), D2H, traversal (odd chunks)
     cudaStream_t main_stream = nullptr;
-    int mode = 2, sort_rays = 0;   // sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order
+    int mode = 2, sort_rays = 0;   // sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order (rays moved), 3 the same through an index list
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};  // bounds of all entities (for sort_rays = 2)
     int knobs[9] = {8, 14, 10, 0, 0, 12, 4096, 1024, 0};  // CNDL_KNOB_*
     // hot-first derived layout of the stackless nodes (kernels_hot.cu), rebuilt by cndl_commit
@@ -135,7 +135,7 @@ int check_ready(cndl_ctx* ctx);
 // Enqueues one traversal batch on `st`.  scratch: 16 unsigned ints ([0] work counter); order_region: order_region_ints(R)
 // unsigned ints, used when ray ordering is on; d_R (optional): the batch length in device memory, R being its upper bound.
 int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, const unsigned* d_R, cndl_hit* d_hits, float* d_any, unsigned* scratch,
-                  unsigned* order_region, cudaStream_t st);
+                  unsigned* order_region, cndl_ray* sorted_region, cudaStream_t st);
 // One 64-byte work-counter slot from the context's ring: device calls in flight on different streams never share one.
 unsigned* next_counter(cndl_ctx* ctx);
 }  // namespace cndl

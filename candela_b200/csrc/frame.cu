@@ -261,7 +261,7 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
     const unsigned g256 = (unsigned)((P + 255) / 256);
     frame_primary_kernel<<<g256, 256, 0, st>>>(m, tm, (unsigned)P, prim, pix_ids);
     ctx->launches.n++;
-    rc = enqueue_trace(ctx, Q_CLOSEST, prim, P, nullptr, prim_hits, nullptr, next_counter(ctx), nullptr, st);
+    rc = enqueue_trace(ctx, Q_CLOSEST, prim, P, nullptr, prim_hits, nullptr, next_counter(ctx), nullptr, nullptr, st);
     if (rc != CNDL_OK) return rc;
 
     const SceneView sv = scene_view(ctx);
@@ -289,7 +289,7 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
         frame_count_kernel<<<1, 1, 0, st>>>(d_count, (unsigned)cap, counts + b);  // the scratch total is overwritten by the next bounce
         ctx->launches.n++;
         rc = enqueue_trace(ctx, b == 0 ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST, out_rays, cap, counts + b, hits, nullptr, next_counter(ctx), nullptr,
-                           st);                                              // :484 IntersectRayIgnoreTransparent, :518 IntersectRay
+                           nullptr, st);                                              // :484 IntersectRayIgnoreTransparent, :518 IntersectRay
         if (rc != CNDL_OK) return rc;
         if (b == 0) {
             const unsigned char* keys;

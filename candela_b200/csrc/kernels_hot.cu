@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
                     next_entity_hot<KIND>(s, ents2, rays, L, L.ent + 1);  // WALK again, or still DONE: the scene loop is over
                     if (L.state == DONE) {
                         if (ANY) {
-                            any_t[L.rid] = L.closest;
+                            any_t[out_slot(order, L.rid)] = L.closest;
                         } else {
                             // tail of IntersectScene (SL:300-318)
                             float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
                                 t = L.closest;
                                 barycentrics(s.tri48, L.best_tri, p, u, v, w);
                             }
-                            store_hit(hits, L.rid, t, u, v, w, mesh, L.best_tri, L.best_ent, min(L.iters, 1024));
+                            store_hit(hits, out_slot(order, L.rid), t, u, v, w, mesh, L.best_tri, L.best_ent, min(L.iters, 1024));
                         }
                         L.state = EMPTY;
                     }
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(128, MINB) trace_pair_stackless_kernel(SceneVi
                     pair_next_entity<KIND>(s, ents2, rays, T, T.ent + 1);
                     if (T.state == DONE) {
                         if (ANY) {
-                            any_t[T.rid] = T.best_tri >= 0 ? T.tmax : -1.0f;
+                            any_t[out_slot(order, T.rid)] = T.best_tri >= 0 ? T.tmax : -1.0f;
                         } else {
                             // tail of IntersectScene (SL:300-318); TMax == ClosestT once something was accepted
                             float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(128, MINB) trace_pair_stackless_kernel(SceneVi
                                 const V3 p = {fadd(ro.x, fmul(rd.x, t)), fadd(ro.y, fmul(rd.y, t)), fadd(ro.z, fmul(rd.z, t))};
                                 barycentrics(s.tri48, T.best_tri, p, u, v, w);
                             }
-                            store_hit(hits, T.rid, t, u, v, w, mesh, T.best_tri, T.best_ent, T.iters);
+                            store_hit(hits, out_slot(order, T.rid), t, u, v, w, mesh, T.best_tri, T.best_ent, T.iters);
                         }
                         T.state = EMPTY;
                     }

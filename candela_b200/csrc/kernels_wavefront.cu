@@ -46,7 +46,7 @@ __device__ __forceinline__ void store_hit(cndl_hit* __restrict__ hits, size_t i,
 }
 
 // tail of IntersectScene (SL:300-318 / ST:347-365): `closest` is TMax after the last acceptance
-__device__ __forceinline__ void retire_closest(const SceneView& s, const cndl_ray* __restrict__ rays, cndl_hit* __restrict__ hits, unsigned rid,
+__device__ __forceinline__ void retire_closest(const SceneView& s, const cndl_ray* __restrict__ rays, cndl_hit* __restrict__ hits, unsigned rid, unsigned out,
                                                const RayState& cur, int cur_ent, float closest, int best_tri, int best_ent, int iters) {
     float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
     int mesh = -1;
@@ -62,7 +62,7 @@ __device__ __forceinline__ void retire_closest(const SceneView& s, const cndl_ra
         const V3 p = {fadd(r.o.x, fmul(r.d.x, t)), fadd(r.o.y, fmul(r.d.y, t)), fadd(r.o.z, fmul(r.d.z, t))};
         barycentrics(s.tri48, best_tri, p, u, v, w);
     }
-    store_hit(hits, rid, t, u, v, w, mesh, best_tri, best_ent, iters);
+    store_hit(hits, out, t, u, v, w, mesh, best_tri, best_ent, iters);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
                 if (L.state == DONE) {
                     next_entity<KIND>(s, rays, L, L.ent + 1);  // WALK again, or still DONE: the scene loop is over
                     if (L.state == DONE) {
-                        if (ANY) any_t[L.rid] = L.best_tri >= 0 ? L.tmax : -1.0f;
-                        else retire_closest(s, rays, hits, L.rid, L.r, L.ent, L.tmax, L.best_tri, L.best_ent, min(L.iters, 1024));
+                        if (ANY) any_t[out_slot(order, L.rid)] = L.best_tri >= 0 ? L.tmax : -1.0f;
+                        else retire_closest(s, rays, hits, L.rid, out_slot(order, L.rid), L.r, L.ent, L.tmax, L.best_tri, L.best_ent, min(L.iters, 1024));
                         L.state = EMPTY;
                     }
                 }
@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(128, 8) trace_ww_stack_kernel(SceneView s, con
                 if (L.state == DONE) {
                     next_entity_stack<KIND>(s, rays, L, L.ent + 1);
                     if (L.state == DONE) {
-                        if (ANY) any_t[L.rid] = L.best_tri >= 0 ? L.tmax : -1.0f;
-                        else retire_closest(s, rays, hits, L.rid, L.r, L.ent, L.tmax, L.best_tri, L.best_ent, L.iters);
+                        if (ANY) any_t[out_slot(order, L.rid)] = L.best_tri >= 0 ? L.tmax : -1.0f;
+                        else retire_closest(s, rays, hits, L.rid, out_slot(order, L.rid), L.r, L.ent, L.tmax, L.best_tri, L.best_ent, L.iters);
                         L.state = EMPTY;
                     }
                 }

@@ -49,8 +49,9 @@ __global__ void __launch_bounds__(1024) ray_order_scan_kernel(unsigned* __restri
     for (int k = 0; k < 4; ++k) { hist[4 * threadIdx.x + k] = (unsigned)ex; ex += (int)v[k]; }
 }
 
+// order[pos] = original index of the ray sorted to pos; sorted (optional): the rays themselves, moved to their sorted places
 __global__ void __launch_bounds__(kRoBlock) ray_order_scatter_kernel(const cndl_ray* __restrict__ rays, unsigned R, float3 lo, float3 scale,
-                                                                    unsigned* __restrict__ cursor, unsigned* __restrict__ order) {
+                                                                    unsigned* __restrict__ cursor, unsigned* __restrict__ order, cndl_ray* __restrict__ sorted) {
     __shared__ unsigned h[kRoBins];
     for (int b = threadIdx.x; b < kRoBins; b += kRoBlock) h[b] = 0;
     __syncthreads();
@@ -73,15 +74,24 @@ __global__ void __launch_bounds__(kRoBlock) ray_order_scatter_kernel(const cndl_
 #pragma unroll
     for (int j = 0; j < kRoItems; ++j) {
         const unsigned i = first + j * kRoBlock + threadIdx.x;
-        if (key[j] < (unsigned)kRoBins) order[h[key[j]] + rank[j]] = i;
+        if (key[j] < (unsigned)kRoBins) {
+            const unsigned pos = h[key[j]] + rank[j];
+            order[pos] = i;
+            if (sorted) {
+                const float4* src = reinterpret_cast<const float4*>(rays + i);
+                float4* dst = reinterpret_cast<float4*>(sorted + pos);
+                dst[0] = __ldg(src);
+                dst[1] = __ldg(src + 1);
+            }
+        }
     }
 }
 }  // namespace
 
 size_t ray_sort_scratch_ints(size_t) { return kRoBins + 64; }
 
-cudaError_t sort_rays_morton(const cndl_ray* rays, size_t R, const float lo[3], const float hi[3], unsigned* order_out, int* scratch, cudaStream_t st,
-                             LaunchCounter& lc) {
+cudaError_t sort_rays_morton(const cndl_ray* rays, size_t R, const float lo[3], const float hi[3], unsigned* order_out, cndl_ray* sorted_out, int* scratch,
+                             cudaStream_t st, LaunchCounter& lc) {
     if (R == 0) return cudaSuccess;
     unsigned* hist = reinterpret_cast<unsigned*>(scratch);
     float3 l = make_float3(lo[0], lo[1], lo[2]), sc;
@@ -92,7 +102,7 @@ cudaError_t sort_rays_morton(const cndl_ray* rays, size_t R, const float lo[3], 
     cudaMemsetAsync(hist, 0, kRoBins * sizeof(unsigned), st);
     ray_order_hist_kernel<<<blocks, kRoBlock, 0, st>>>(rays, (unsigned)R, l, sc, hist);
     ray_order_scan_kernel<<<1, 1024, 0, st>>>(hist);
-    ray_order_scatter_kernel<<<blocks, kRoBlock, 0, st>>>(rays, (unsigned)R, l, sc, hist, order_out);
+    ray_order_scatter_kernel<<<blocks, kRoBlock, 0, st>>>(rays, (unsigned)R, l, sc, hist, order_out, sorted_out);
     lc.n += 3;
     return cudaGetLastError();
 }

@@ -35,7 +35,10 @@ struct RayOrder {
     const unsigned* __restrict__ counts;
     unsigned stride;
     const unsigned* __restrict__ d_count;  // optional: the batch length in device memory (the launch's R is then its upper bound)
+    const unsigned* __restrict__ out_index;  // optional: the batch was physically reordered; the result of ray slot i belongs at out_index[i]
 };
+
+__device__ __forceinline__ unsigned out_slot(const RayOrder& ro, unsigned rid) { return ro.out_index ? __ldg(ro.out_index + rid) : rid; }
 
 __device__ __forceinline__ unsigned batch_length(const RayOrder& ro, unsigned R) {
     if (!ro.d_count) return R;

@@ -128,7 +128,10 @@ public:
         else if (std::is_same<T, BVH::FlattenedNode>::value) m_Stackless = true;
         else throw "\nTemplate <T> Passed to RayIntersector can only be of type BVH::FlattenedStackNode or BVH::FlattenedNode>!";
     }
-    ~RayIntersector() { if (m_Ctx) cndl_destroy(m_Ctx); }
+    ~RayIntersector() {
+        if (m_Multi) cndl_multi_destroy(m_Multi);  // owns its per-device contexts, m_Ctx among them
+        else if (m_Ctx) cndl_destroy(m_Ctx);
+    }
     RayIntersector(const RayIntersector&) = delete;
     RayIntersector& operator=(const RayIntersector&) = delete;
 
@@ -139,6 +142,18 @@ public:
             throw "candela_b200: no usable sm_100 CUDA device (there is no CPU fallback)";
     }
 
+    // Several GPUs behind the same object: the BVH is built once on Devices[0] and replicated device to device,
+    // TraceFrame deals the screen tiles round-robin and gathers the records into Devices[0]'s frame over NVLink peer memory.
+    // Every other query runs on Devices[0].
+    void Initialize(const std::vector<int>& Devices) {
+        if (m_Ctx) return;
+        if (Devices.size() <= 1) { Initialize(Devices.empty() ? 0 : Devices[0]); return; }
+        if (cndl_multi_create(&m_Multi, m_Stackless ? CNDL_STACKLESS : CNDL_STACK, Devices.data(), (int)Devices.size()) != CNDL_OK)
+            throw "candela_b200: no usable sm_100 CUDA device (there is no CPU fallback)";
+        m_Ctx = cndl_multi_context(m_Multi, 0);
+    }
+    int DeviceCount() const { return m_Multi ? cndl_multi_device_count(m_Multi) : (m_Ctx ? 1 : 0); }
+
     // Intersector.h:170-198.  The mesh concatenation of BuildBVH (BVHConstructor.cpp:981-1002) happens here on
     // the host; the build itself runs on the GPU and is byte-identical to BVH::BuildBVH.
     template <typename ObjectT>
@@ -148,25 +163,67 @@ public:
         std::vector<std::uint32_t> MeshIndices;
         std::vector<std::int32_t> MeshReferences;
         detail::ConcatenateMeshes(object, Vertices, MeshIndices, MeshReferences);
-        Check(cndl_add_object(m_Ctx, static_cast<std::uint32_t>(object.GetID()), reinterpret_cast<const cndl_vertex*>(Vertices.data()),
-                              Vertices.size(), MeshIndices.data(), MeshIndices.size(), MeshReferences.data(), Options));
+        if (m_Multi)
+            CheckMulti(cndl_multi_add_object(m_Multi, static_cast<std::uint32_t>(object.GetID()), reinterpret_cast<const cndl_vertex*>(Vertices.data()),
+                                             Vertices.size(), MeshIndices.data(), MeshIndices.size(), MeshReferences.data(), Options));
+        else
+            Check(cndl_add_object(m_Ctx, static_cast<std::uint32_t>(object.GetID()), reinterpret_cast<const cndl_vertex*>(Vertices.data()),
+                                  Vertices.size(), MeshIndices.data(), MeshIndices.size(), MeshReferences.data(), Options));
     }
 
     // Intersector.h:201-216
     template <typename EntityT>
     void PushEntity(const EntityT& entity) {
         Require();
-        const int rc = cndl_push_entity(m_Ctx, static_cast<std::uint32_t>(entity.m_Object->m_ObjectID), &entity.m_Model[0][0],
-                                        entity.m_EmissiveAmount, entity.m_TranslucencyAmount);
+        const std::uint32_t id = static_cast<std::uint32_t>(entity.m_Object->m_ObjectID);
+        const int rc = m_Multi ? cndl_multi_push_entity(m_Multi, id, &entity.m_Model[0][0], entity.m_EmissiveAmount, entity.m_TranslucencyAmount)
+                               : cndl_push_entity(m_Ctx, id, &entity.m_Model[0][0], entity.m_EmissiveAmount, entity.m_TranslucencyAmount);
         if (rc == CNDL_ERR_UNKNOWN_OBJECT) throw "Trying to push entity whose parent object hasn't been added to global BVH";
-        Check(rc);
+        if (m_Multi) CheckMulti(rc); else Check(rc);
     }
     template <typename EntityT>
     void PushEntities(const std::vector<EntityT*>& Entities) {  // Intersector.h:219-224
         for (const auto& e : Entities) PushEntity(*e);
     }
-    void BufferEntities() { Require(); Check(cndl_buffer_entities(m_Ctx)); }           // Intersector.h:227-239
-    void BufferData(bool ClearCPUData) { Require(); Check(cndl_commit(m_Ctx, ClearCPUData ? 1 : 0)); }  // Intersector.h:322-351
+    void BufferEntities() {  // Intersector.h:227-239
+        Require();
+        if (m_Multi) CheckMulti(cndl_multi_buffer_entities(m_Multi)); else Check(cndl_buffer_entities(m_Ctx));
+    }
+    void BufferData(bool ClearCPUData) {  // Intersector.h:322-351
+        Require();
+        if (m_Multi) CheckMulti(cndl_multi_commit(m_Multi)); else Check(cndl_commit(m_Ctx, ClearCPUData ? 1 : 0));
+    }
+
+    // One diffuse-GI frame on the device(s), the way DiffuseTrace.glsl:437-518 runs it (camera rays stand in for the G-buffer):
+    // camera rays -> closest hits -> SamplesPerPixel cosine-hemisphere rays per pixel -> IntersectRayIgnoreTransparent ->
+    // Bounces - 1 further bounces.  Output: cndl_frame_records(Params) records of Params.out_format, row-major (host memory; pinned
+    // memory keeps the copy asynchronous).  With several devices the tiles are dealt round-robin and gathered over NVLink.
+    void TraceFrame(const cndl_frame_params& Params, void* Output) {
+        Require();
+        if (m_Multi) CheckMulti(cndl_multi_trace_frame(m_Multi, &Params, Output)); else Check(cndl_trace_frame(m_Ctx, &Params, Output));
+    }
+    // Two frames in flight: Submit(slot) returns at once, Wait(slot) blocks until that frame's records are in Output.
+    void SubmitFrame(const cndl_frame_params& Params, void* Output, int Slot) {
+        Require();
+        if (m_Multi) CheckMulti(cndl_multi_frame_submit(m_Multi, &Params, Output, Slot)); else Check(cndl_frame_submit(m_Ctx, &Params, Output, Slot));
+    }
+    void WaitFrame(int Slot) {
+        Require();
+        if (m_Multi) CheckMulti(cndl_multi_frame_wait(m_Multi, Slot)); else Check(cndl_frame_wait(m_Ctx, Slot));
+    }
+    // Same shape as IntersectPrimary (Intersector.h:241-266), one bounce further: the compact hit record {t, tri, v, w} of every
+    // pixel's diffuse ray(s).
+    void IntersectDiffuse(cndl_hit16* Output, int Width, int Height, const float* InverseView, const float* InverseProjection, std::uint32_t Seed,
+                          int SamplesPerPixel = 1) {
+        cndl_frame_params p;
+        std::memset(&p, 0, sizeof(p));
+        std::memcpy(p.inv_view, InverseView, 64);
+        std::memcpy(p.inv_proj, InverseProjection, 64);
+        p.width = Width; p.height = Height; p.spp = SamplesPerPixel; p.bounces = 1; p.seed = Seed;
+        p.out_format = CNDL_FRAME_OUT_HIT16;
+        p.flags = CNDL_FRAME_OCTANT_ORDER;
+        TraceFrame(p, Output);
+    }
 
     // Intersector.h:241-266 with hit records instead of an albedo image. Matrices are glm::mat4-compatible (column-major).
     void IntersectPrimary(RayHit* Output, int Width, int Height, const float* InverseView, const float* InverseProjection) {
@@ -245,7 +302,14 @@ private:
             throw m_LastError.c_str();  // the reference throws C strings (Intersector.h:147,:204)
         }
     }
+    void CheckMulti(int rc) {
+        if (rc != CNDL_OK) {
+            m_LastError = cndl_multi_last_error(m_Multi);
+            throw m_LastError.c_str();
+        }
+    }
     cndl_ctx* m_Ctx = nullptr;
+    cndl_multi* m_Multi = nullptr;
     bool m_Stackless = false;
     std::string m_LastError;
 };

@@ -25,6 +25,13 @@ struct Entity {
     float m_EmissiveAmount = 0.0f, m_TranslucencyAmount = 0.0f;
 };
 
+// the demo links only against libcandela_b200.so: the device count comes from trying to open a context on device 1
+static void cudaGetDeviceCountShim(int* n) {
+    cndl_ctx* c = nullptr;
+    *n = 1;
+    if (cndl_create(&c, CNDL_STACKLESS, 1) == CNDL_OK) { *n = 2; cndl_destroy(c); }
+}
+
 int main() {
     Object obj;
     for (int m = 0; m < 2; ++m) {  // two meshes: a floor grid and a wall grid
@@ -100,6 +107,29 @@ int main() {
             std::vector<Candela::BVH::Triangle> T2;
             Candela::BVH::BuildBVH(obj, StackNodes, V2, T2, 1000);
             std::printf("BUILDBVH same=%d stack_nodes=%zu tris=%zu\n", (int)same, StackNodes.size(), T2.size());
+        }
+        // a diffuse frame (IntersectDiffuse: camera rays -> hits -> cosine-hemisphere rays -> hits, all on the device), and the same
+        // frame from a second intersector that drives two contexts (two GPUs when the box has them, else the same GPU twice):
+        // tiles dealt round-robin, records gathered into the first device's frame — identical bytes
+        {
+            const int W = 160, H = 96;
+            // camera at (6, 5, 6) looking along -y/-z onto the floor and the wall: inverse view = rotation * translation, column-major
+            const float InverseView[16] = {1, 0, 0, 0, 0, 0.70710678f, -0.70710678f, 0, 0, 0.70710678f, 0.70710678f, 0, 6, 5, 6, 1};
+            const float InverseProjection[16] = {1.6666666f, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, -24.99f, 0, 0, -1, 25.01f};
+            std::vector<cndl_hit16> a((size_t)W * H), b((size_t)W * H);
+            Intersector.IntersectDiffuse(a.data(), W, H, InverseView, InverseProjection, 42u);
+            int n_d = 0;
+            for (auto& h : a) n_d += h.t > 0 ? 1 : 0;
+            int n_dev = 0;
+            cudaGetDeviceCountShim(&n_dev);
+            Candela::RayIntersector<Candela::BVH::StacklessTraversalNode> Multi;
+            Multi.Initialize(std::vector<int>{0, n_dev > 1 ? 1 : 0});
+            Multi.AddObject(obj);
+            Multi.BufferData(true);
+            Multi.PushEntities(list);
+            Multi.BufferEntities();
+            Multi.IntersectDiffuse(b.data(), W, H, InverseView, InverseProjection, 42u);
+            std::printf("FRAME hits=%d devices=%d same=%d\n", n_d, Multi.DeviceCount(), (int)(std::memcmp(a.data(), b.data(), a.size() * sizeof(a[0])) == 0));
         }
         // pushing an entity of an unknown object must throw the reference's message
         Object other;

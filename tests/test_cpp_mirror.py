@@ -40,4 +40,6 @@ def test_mirror_runs_the_reference_call_sequence():
     assert extra[1] == f"data={n_hit}" and extra[2] == "collide=101"          # floor point collides, air point does not, box does
     build = [l for l in lines if l.startswith("BUILDBVH ")][0].split()
     assert build[1] == "same=1" and build[3] == "tris=576"                    # BVH::BuildBVH free function: same bytes as AddObject's buffers
+    frame = [l for l in lines if l.startswith("FRAME ")][0].split()
+    assert int(frame[1].split("=")[1]) > 1000 and frame[2] in ("devices=2",) and frame[3] == "same=1"   # multi-device frame == single-device frame
     assert "THROW Trying to push entity whose parent object hasn't been added to global BVH" in p.stdout

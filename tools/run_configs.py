@@ -131,67 +131,49 @@ def cfg_spec_shadow(args, rank, world, local_rank):
 
 
 def cfg_bounce4k(args, rank, world, local_rank):
+    """BASELINE configs[3] through the frame-level call: tiles dealt round-robin to the ranks, every rank's resolved 32-byte pixels
+    gathered into rank 0's row-major frame (sharding.gather_frame: one NCCL gather of the tile-major shards + the untile kernel)."""
+    from oracle import frame as of
     W, H, spp, bounces = args.width or 3840, args.height or 2160, 8, 4
     ri, v, i, m = setup_s260k(local_rank)
     stream = torch.cuda.current_stream().cuda_stream
     iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
-    # this rank's pixels: 64x64 tiles dealt round-robin
-    pix = torch.from_numpy(sharding.shard_pixels(W, H, world, rank, tile=64)).cuda()
-    d_prim_all = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
-    d_hits_all = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
-    ri.intersect_primary_device(iv, ip, W, H, d_hits_all.data_ptr(), d_prim_all.data_ptr(), stream)
-    d_prim, d_phits = d_prim_all[pix].contiguous(), d_hits_all[pix].contiguous()
-    del d_prim_all, d_hits_all
-    n_pix = len(pix)
-    cap = n_pix * spp
-    bufs = [torch.empty((cap, 8), dtype=torch.float32, device="cuda") for _ in range(2)]
-    d_hits = torch.empty((cap, 8), dtype=torch.float32, device="cuda")
-    per_bounce = []
+
+    def params(r, local=True):
+        return cb.frame_params(iv, ip, W, H, spp=spp, bounces=bounces, seed=4000, shard_index=r, shard_count=world, out_format=api.FRAME_OUT_PIXEL32,
+                               octant_order=bool(args.bucket), local_layout=local)
+    shard = torch.zeros((ri.frame_records(params(rank)), 32), dtype=torch.uint8, device="cuda")
+
+    def untile(sh, r, frame):
+        ri.frame_untile_device(params(r), sh.data_ptr(), frame.data_ptr(), stream=stream)
+
+    def step():
+        ri.trace_frame_device(params(rank), shard.data_ptr(), slot=0, stream=stream)
+        return sharding.gather_frame(shard, W, H, 64, untile=untile)
+    for _ in range(2):
+        frame = step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    total_ms, total_rays = 0.0, 0
-    src_rays, src_hits, n_src, s = d_prim, d_phits, n_pix, spp
-    checks = []
-    for b in range(bounces):
-        out = bufs[b % 2]
-        g0, g1, t1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        g0.record()
-        n = ri.generate_rays_device(api.GEN_DIFFUSE, src_rays.data_ptr(), src_hits.data_ptr(), n_src, out.data_ptr(), spp=s, offset=0.05 if b == 0 else 0.02,
-                                    tmax=1.0e6, seed=100 + b, bucket_octants=bool(args.bucket), stream=stream)
-        g1.record()
-        if n == 0:
-            break
-        ri.intersect_closest_device(out.data_ptr(), n, d_hits.data_ptr(), api.IGNORE_TRANSPARENT if b == 0 else 0, stream)
-        t1.record()
-        torch.cuda.synchronize()
-        gen_ms, trace_ms = g0.elapsed_time(g1), g1.elapsed_time(t1)
-        per_bounce.append(dict(bounce=b, rays=n, gen_ms=round(gen_ms, 3), trace_ms=round(trace_ms, 3), mrays_s=round(n / trace_ms / 1e3, 1)))
-        total_ms += trace_ms
-        total_rays += n
-        if rank == 0:  # 1/64 subsample against the oracle
-            idx = torch.arange(0, n, 64, device="cuda")
-            checks.append((b, out[idx].cpu().numpy().view(api.RAY_DT).reshape(-1), d_hits[idx].cpu().numpy().view(api.HIT_DT).reshape(-1)))
-        # next bounce from these hits
-        src_rays, src_hits, n_src, s = out, d_hits.clone(), n, 1
-    t_max, rays_all = sharding.reduce_timing(total_ms, float(total_rays), device="cuda")
-    # final frame: hit records of the last bounce are not per pixel any more; gather the primary hit records instead
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    frame = sharding.gather_frame(d_phits, pix, W * H)
-    g1.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.reps):
+        frame = step()
+    e1.record()
     torch.cuda.synchronize()
-    gather_ms = g0.elapsed_time(g1)
+    ms = e0.elapsed_time(e1) / args.reps
+    t_max, rays_all = sharding.reduce_timing(ms, float(ri.frame_rays_traced(0)), device="cuda")
     if rank != 0:
         return None
+    px = frame.cpu().numpy().view(api.PIXEL_DT).reshape(-1)
+    # one tile row of the frame against the oracle (every pixel of 64 image rows)
     ob, nodes, tris, ents = oracle_scene(ri, v)
-    ok = True
-    for b, r, h in checks:
-        want, _ = ob.trace(ob.STACKLESS, ob.CLOSEST_IGNORE_TRANSPARENT if b == 0 else ob.CLOSEST, nodes, tris, v, ents, r, nthreads=ob.hardware_threads())
-        ok = ok and want.tobytes() == h.tobytes()
-    return dict(config=f"multibounce_{W}x{H}_8spp_tiles", octant_bucketed=bool(args.bucket), n_gpus=world, rays_all_ranks=int(rays_all), trace_ms_max_over_ranks=round(t_max, 3),
-                mrays_s=round(rays_all / t_max / 1e3, 1), per_bounce_rank0=per_bounce, sample_bit_identical_to_oracle=bool(ok),
-                final_frame_gather_ms=round(gather_ms, 3), frame_pixels=int(frame.shape[0]))
+    pixels = np.arange(W * 64 * 8, W * 64 * 9, dtype=np.uint32)
+    want, _ = of.trace_frame(ob.STACKLESS, nodes, tris, v, ents, iv, ip, W, H, spp=spp, bounces=bounces, seed=4000, out_format=of.OUT_PIXEL32, pixels=pixels)
+    return dict(config=f"multibounce_{W}x{H}_8spp_4bounces_tiles", octant_major=bool(args.bucket), n_gpus=world, rays_all_ranks=int(rays_all),
+                ms_max_over_ranks_gather_included=round(t_max, 3), mrays_s=round(rays_all / t_max / 1e3, 1), frame_pixels=int(len(px)),
+                rays_in_frame=int(px["rays"].sum()), sample_pixels_checked=int(len(pixels)),
+                sample_bit_identical_to_oracle=bool(px[pixels].tobytes() == want[pixels].tobytes()))
 
 
 def cfg_soup10m(args, rank, world, local_rank):
