@@ -87,12 +87,22 @@ __device__ __forceinline__ void warp_sah_eval(const int* s_count, const int (*s_
     }
 }
 
+// One level of the tree as the DEVICE knows it: how many of its active nodes fall into each size class and where its nodes
+// sit in the node arrays.  The host launches a level with grid UPPER BOUNDS and never waits for these numbers (it reads them
+// back every few levels to tighten the bounds and to notice the end): every kernel takes its real extent from here.
+struct LevelDesc {
+    int n_class[4];  // split, big, small, tiny
+    int base;        // id of the level's first node
+    int n;           // nodes in the level (2 x the active nodes of the level above)
+    int pad[2];
+};
+enum { CLS_SPLIT = 0, CLS_BIG = 1, CLS_SMALL = 2, CLS_TINY = 3 };
+
 struct LevelArgs {
     BuildArrays a;
     const int* active;     // node ids to split at this level, in level order
     const int* klist;      // positions in `active` handled by this launch (one size class)
-    int n_active;
-    int child_base;        // id of the first node of the next level
+    const LevelDesc* lv;   // this level (device memory)
     int stackless;
     int swap_policy;
     unsigned long long swap_seed;
@@ -104,7 +114,7 @@ struct LevelArgs {
 __device__ __forceinline__ void create_child(const LevelArgs& g, int k, int side, unsigned start, unsigned len, unsigned mid, const int* box_keys,
                                              const int* zero_first, const int* refs) {
     const BuildArrays& a = g.a;
-    const int child = g.child_base + 2 * k;
+    const int child = g.lv->base + g.lv->n + 2 * k;  // the next level starts right after this one
     float bx[6];
     for (int c = 0; c < 6; ++c) {
         bx[c] = key2f(box_keys[c]);
@@ -135,7 +145,7 @@ __device__ __forceinline__ void create_child(const LevelArgs& g, int k, int side
 }
 
 __device__ __forceinline__ void finish_parent(const LevelArgs& g, int k, int id, unsigned start, unsigned len) {
-    g.a.nchild[id] = g.child_base + 2 * k;
+    g.a.nchild[id] = g.lv->base + g.lv->n + 2 * k;
     unsigned char flip = 0;
     if (g.stackless && g.swap_policy == CNDL_SWAP_HASHED)
         flip = (unsigned char)(mix64(g.swap_seed ^ mix64(((unsigned long long)start << 32) | len)) & 1ull);
@@ -144,7 +154,8 @@ __device__ __forceinline__ void finish_parent(const LevelArgs& g, int k, int id,
 
 // One block owns one node for one level: split search, partition, child boxes, leaf emission.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g) {
+__global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g, int cls) {
+    if ((int)blockIdx.x >= g.lv->n_class[cls]) return;  // the grid is an upper bound
     const BuildArrays& a = g.a;
     __shared__ int s_count[3][kBins];
     __shared__ int s_mn[3][3][kBins], s_mx[3][3][kBins];  // [axis][component][bin]
@@ -316,8 +327,9 @@ __global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g) {
 // 64 registers / 4 CTAs per SM: more resident warps (48 or 40 registers, with spills) measured 3-6 % slower.
 constexpr int kTinyWarps = 8;
 constexpr unsigned kDirectLen = 9;  // ranges up to this length search their split without bins (3 x 10 candidates <= 32 lanes)
-__global__ void __launch_bounds__(32 * kTinyWarps, 4) level_step_tiny_kernel(LevelArgs g, int n_nodes) {
+__global__ void __launch_bounds__(32 * kTinyWarps, 4) level_step_tiny_kernel(LevelArgs g) {
     const BuildArrays& a = g.a;
+    const int n_nodes = g.lv->n_class[CLS_TINY];  // the grid is an upper bound
     __shared__ int s_count[kTinyWarps][kBins];
     __shared__ int s_mn[kTinyWarps][3][kBins], s_mx[kTinyWarps][3][kBins];
     __shared__ float s_best_cost[kTinyWarps], s_border[kTinyWarps];
@@ -499,8 +511,7 @@ __global__ void __launch_bounds__(32 * kTinyWarps, 4) level_step_tiny_kernel(Lev
 //                 (rpos gives the run's first position) and a chain costs at most O(sqrt(len)) dependent loads;
 //   split_finish  copies the new order back, reduces the two child boxes and the last CTA creates the children.
 struct SplitArgs {
-    LevelArgs g;         // klist = positions of this level's split nodes in the active list
-    int n_split;
+    LevelArgs g;         // klist = positions of this level's split nodes in the active list; g.lv->n_class[CLS_SPLIT] of them
     int* chunk_base;     // n_split + 1: first chunk of every split node, total
     int* bins;           // n_split x kBinInts
     int* done;           // n_split x 3 arrival counters
@@ -515,9 +526,11 @@ struct SplitArgs {
 struct SplitWhere { int h, chunk, n_chunks, id, k; unsigned start, len; };
 
 __device__ __forceinline__ bool split_locate(const SplitArgs& s, SplitWhere& w) {
-    const int total = s.chunk_base[s.n_split];
+    const int n_split = s.g.lv->n_class[CLS_SPLIT];
+    if (n_split <= 0) return false;
+    const int total = s.chunk_base[n_split];
     if ((int)blockIdx.x >= total) return false;
-    int lo = 0, hi = s.n_split - 1;  // last h with chunk_base[h] <= blockIdx.x
+    int lo = 0, hi = n_split - 1;  // last h with chunk_base[h] <= blockIdx.x
     while (lo < hi) {
         const int m = (lo + hi + 1) >> 1;
         if (s.chunk_base[m] <= (int)blockIdx.x) lo = m; else hi = m - 1;
@@ -546,23 +559,24 @@ __device__ __forceinline__ bool split_arrive_last(const SplitArgs& s, const Spli
 __global__ void __launch_bounds__(1024) split_prep_kernel(SplitArgs s, int chunk_len) {
     __shared__ int s_warp[1024 / 32 + 1];
     const int tid = threadIdx.x;
+    const int n_split = s.g.lv->n_class[CLS_SPLIT];
     int carry = 0;
-    for (int base = 0; base < s.n_split; base += 1024) {
+    for (int base = 0; base < n_split; base += 1024) {
         const int h = base + tid;
         int nch = 0;
-        if (h < s.n_split) nch = (int)((s.g.a.nlen[s.g.active[s.g.klist[h]]] + chunk_len - 1) / chunk_len);
+        if (h < n_split) nch = (int)((s.g.a.nlen[s.g.active[s.g.klist[h]]] + chunk_len - 1) / chunk_len);
         int total;
         const int ex = block_exclusive_scan<1024>(nch, s_warp, total);
-        if (h < s.n_split) s.chunk_base[h] = carry + ex;
+        if (h < n_split) s.chunk_base[h] = carry + ex;
         carry += total;
     }
-    if (tid == 0) s.chunk_base[s.n_split] = carry;
-    for (int i = tid; i < s.n_split * kBinInts; i += 1024) {
+    if (tid == 0) s.chunk_base[n_split] = carry;
+    for (int i = tid; i < n_split * kBinInts; i += 1024) {
         const int j = i % kBinInts;
         s.bins[i] = j < 3 * kBins ? 0 : (j < 12 * kBins ? f2key(kSentinelMax) : f2key(kSentinelMin));
     }
-    for (int i = tid; i < s.n_split * 3; i += 1024) s.done[i] = 0;
-    for (int i = tid; i < s.n_split * 24; i += 1024) {
+    for (int i = tid; i < n_split * 3; i += 1024) s.done[i] = 0;
+    for (int i = tid; i < n_split * 24; i += 1024) {
         const int j = i % 24;
         s.boxes[i] = j >= 12 ? 0x7FFFFFFF : (j % 6 < 3 ? f2key(kSentinelMax) : f2key(kSentinelMin));
     }
@@ -808,13 +822,28 @@ __global__ void __launch_bounds__(kSplitBlock) split_finish_kernel(SplitArgs s) 
     if (tid == 0) finish_parent(s.g, w.k, w.id, start, len);
 }
 
-// classify + scan + compact of a level of at most kSmallLevel nodes in one CTA (one launch instead of five)
-constexpr int kSmallLevel = 4096, kMaxRunLevels = 2048;
-__global__ void __launch_bounds__(1024) level_compact_small_kernel(const unsigned* nlen, int base, int n, unsigned split_node, int* active,
-                                                                   int* klist_split, int* klist_big, int* klist_small, int* klist_tiny,
-                                                                   int* class_counts /* mapped host memory */) {
+// Next level's active list.  Both kernels read where the new level sits from the descriptor of the level above
+// (base' = base + n, n' = 2 x its active nodes), classify + scan + compact its nodes, and write the new level's descriptor to
+// device memory and to its mapped host copy; the host does not wait for it (see build_object).
+//
+// A level of at most kSmallLevel nodes: one CTA (one launch instead of five).
+constexpr int kSmallLevel = 4096, kMaxRunLevels = 2048, kMaxLevels = 1 << 16;
+__device__ __forceinline__ void next_level_extent(const LevelDesc& up, int& base, int& n) {
+    base = up.base + up.n;
+    n = 2 * (up.n_class[0] + up.n_class[1] + up.n_class[2] + up.n_class[3]);
+}
+__device__ __forceinline__ void publish_level(LevelDesc* lv, LevelDesc* host_lv, int level, const int counts[4], int base, int n) {
+    for (int c = 0; c < 4; ++c) { lv[level].n_class[c] = counts[c]; host_lv[level].n_class[c] = counts[c]; }
+    lv[level].base = base; lv[level].n = n;
+    host_lv[level].base = base; host_lv[level].n = n;
+}
+__global__ void __launch_bounds__(1024) level_compact_small_kernel(const unsigned* nlen, LevelDesc* lv, LevelDesc* host_lv /* mapped host memory */, int level,
+                                                                   unsigned split_node, int* active, int* klist_split, int* klist_big, int* klist_small,
+                                                                   int* klist_tiny) {
     __shared__ int s_warp[1024 / 32 + 1];
     const int tid = threadIdx.x;
+    int base, n;
+    next_level_extent(lv[level - 1], base, n);
     int cls[4], c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -826,11 +855,11 @@ __global__ void __launch_bounds__(1024) level_compact_small_kernel(const unsigne
         }
         c0 += cls[j] == 0; c1 += cls[j] == 1; c2 += cls[j] == 2; c3 += cls[j] == 3;
     }
-    int t0, t1, t2, t3;
-    int o0 = block_exclusive_scan<1024>(c0, s_warp, t0);
-    int o1 = block_exclusive_scan<1024>(c1, s_warp, t1);
-    int o2 = block_exclusive_scan<1024>(c2, s_warp, t2);
-    int o3 = block_exclusive_scan<1024>(c3, s_warp, t3);
+    int t[4];
+    int o0 = block_exclusive_scan<1024>(c0, s_warp, t[0]);
+    int o1 = block_exclusive_scan<1024>(c1, s_warp, t[1]);
+    int o2 = block_exclusive_scan<1024>(c2, s_warp, t[2]);
+    int o3 = block_exclusive_scan<1024>(c3, s_warp, t[3]);
     int k = o0 + o1 + o2 + o3;  // active nodes before this thread's first one, in level order
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -842,25 +871,34 @@ __global__ void __launch_bounds__(1024) level_compact_small_kernel(const unsigne
         else klist_tiny[o3++] = k;
         ++k;
     }
-    if (tid == 0) { class_counts[0] = t0; class_counts[1] = t1; class_counts[2] = t2; class_counts[3] = t3; }
+    if (tid == 0) publish_level(lv, host_lv, level, t, base, n);
 }
 
 // The same for larger levels in ONE pass: tiles of 1024 nodes, chained by decoupled look-back over the four class counts
 // (replaces classify + three scan launches + compact, ~25 us of serial launches per level).  Tiles take their index from
-// a ticket, so a tile only ever waits for tiles that are already running.  Tile states carry the level number (epoch)
-// instead of being cleared between levels; the last tile publishes the class sizes and resets the ticket.
+// a ticket (the new level's own: lv[level].pad[0], zero since the build started), so a tile only ever waits for tiles that are
+// already running; the grid is an upper bound, and CTAs whose ticket lies beyond the level leave at once.  Tile states carry the
+// level number (epoch) instead of being cleared between levels; the last tile publishes the descriptor.
 struct TileState { int status; int agg[4]; int incl[4]; };
 constexpr int kCompactTile = 1024;
-__global__ void __launch_bounds__(256) level_compact_chained_kernel(const unsigned* nlen, int base, int n, unsigned split_node, int* active,
-                                                                    int* klist_split, int* klist_big, int* klist_small, int* klist_tiny,
-                                                                    int* class_counts /* mapped host memory */, TileState* tiles, int* ticket,
-                                                                    int epoch) {
+__global__ void __launch_bounds__(256) level_compact_chained_kernel(const unsigned* nlen, LevelDesc* lv, LevelDesc* host_lv /* mapped host memory */, int level,
+                                                                    unsigned split_node, int* active, int* klist_split, int* klist_big, int* klist_small,
+                                                                    int* klist_tiny, TileState* tiles) {
     __shared__ int s_warp[256 / 32 + 1];
     __shared__ int s_tile, s_prefix[4];
     const int tid = threadIdx.x;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1);
+    const int epoch = level;
+    int base, n;
+    next_level_extent(lv[level - 1], base, n);
+    if (tid == 0) s_tile = atomicAdd(&lv[level].pad[0], 1);
     __syncthreads();
     const int tile = s_tile, n_tiles = (n + kCompactTile - 1) / kCompactTile;
+    if (n_tiles == 0) {  // nothing left to split: the (empty) level is published by whoever came first
+        const int zero[4] = {0, 0, 0, 0};
+        if (tile == 0 && tid == 0) publish_level(lv, host_lv, level, zero, base, 0);
+        return;
+    }
+    if (tile >= n_tiles) return;
     int cls[4], c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -899,8 +937,8 @@ __global__ void __launch_bounds__(256) level_compact_chained_kernel(const unsign
         __threadfence();
         *reinterpret_cast<volatile int*>(&tiles[tile].status) = have_incl;
         if (tile == n_tiles - 1) {
-            for (int c = 0; c < 4; ++c) class_counts[c] = pre[c] + t[c];
-            *ticket = 0;  // every tile has taken its ticket by now
+            const int counts[4] = {pre[0] + t[0], pre[1] + t[1], pre[2] + t[2], pre[3] + t[3]};
+            publish_level(lv, host_lv, level, counts, base, n);
         }
     }
     __syncthreads();
@@ -1014,7 +1052,7 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     int32_t* d_mesh = nullptr;
     unsigned char* d_flip = nullptr;
     TileState* d_tiles = nullptr;
-    int* d_ticket = nullptr;
+    LevelDesc* d_lv = nullptr;
     int *d_levels = nullptr, *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr, *d_kl_tiny = nullptr, *d_kl_split = nullptr;
     const size_t scan_n = std::max<size_t>(n_max, 16);  // inner-node flags of the stack flatten (the level compaction scans in its own kernels)
     const unsigned split_node = rq.split_node ? std::max(rq.split_node, kTinyNode) : kSplitNodeDefault;
@@ -1033,7 +1071,7 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
         sc.alloc(&d_block_sums, scan_n / kScanTile + 2); sc.alloc(&d_totals, 4);
         sc.alloc(&d_active, n_max); sc.alloc(&d_active_next, n_max); sc.alloc(&d_kl_big, n_max); sc.alloc(&d_kl_small, n_max); sc.alloc(&d_kl_tiny, n_max);
         sc.alloc(&d_kl_split, n_split_max); sc.alloc(&d_levels, 2 * (size_t)kMaxRunLevels);
-        sc.alloc(&d_tiles, n_max / kCompactTile + 2); sc.alloc(&d_ticket, 1);
+        sc.alloc(&d_tiles, n_max / kCompactTile + 2); sc.alloc(&d_lv, (size_t)kMaxLevels);
         sc.alloc(&sp.chunk_base, n_split_max + 1); sc.alloc(&sp.bins, n_split_max * kBinInts); sc.alloc(&sp.done, n_split_max * 3);
         sc.alloc(&sp.split, n_split_max * 4); sc.alloc(&sp.boxes, n_split_max * 24); sc.alloc(&sp.chunk_l, split_chunks_max);
         sc.alloc(&sp.rankflag, T); sc.alloc(&sp.rpos, T); sc.alloc(&sp.alt, T);
@@ -1051,10 +1089,11 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     sc.base = static_cast<char*>(*rq.arena);
     layout(sc);
 
-    if (!*rq.host_counts) BK(cudaHostAlloc(reinterpret_cast<void**>(rq.host_counts), 4 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
-    volatile int* h_counts = *rq.host_counts;
-    int* d_counts = nullptr;
-    BK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_counts), *rq.host_counts, 0));
+    // the level descriptors' host copy: mapped pinned memory kept by the context, written by the compaction kernels
+    if (!*rq.host_counts) BK(cudaHostAlloc(reinterpret_cast<void**>(rq.host_counts), (size_t)kMaxLevels * sizeof(LevelDesc), cudaHostAllocMapped | cudaHostAllocPortable));
+    volatile LevelDesc* h_lv = reinterpret_cast<volatile LevelDesc*>(*rq.host_counts);
+    LevelDesc* d_host_lv = nullptr;
+    BK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_host_lv), *rq.host_counts, 0));
 
     cudaEvent_t ev0, ev1, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     const bool side_ok = rq.side[0] && rq.side[1];
@@ -1080,7 +1119,7 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     BK(cudaMemcpyAsync(a.root_scratch, h_root_init, sizeof(h_root_init), cudaMemcpyHostToDevice, st));
     BK(cudaMemsetAsync(d_flip, 0, n_max, st));
     BK(cudaMemsetAsync(d_tiles, 0, (n_max / kCompactTile + 2) * sizeof(TileState), st));
-    BK(cudaMemsetAsync(d_ticket, 0, sizeof(int), st));
+    BK(cudaMemsetAsync(d_lv, 0, (size_t)kMaxLevels * sizeof(LevelDesc), st));  // also the per-level tickets of the chained compaction
     tri_precompute_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(a);
     root_finalize_kernel<<<1, 32, 0, st>>>(a);
     lc.n += 2;
@@ -1093,21 +1132,36 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
         single_leaf_kernel<<<1, 32, 0, st>>>(a, stackless ? 1 : 0, out);
         lc.n++;
     } else {
-        // level 0: the root is the only active node
-        int n_split = T > split_node ? 1 : 0, n_big = !n_split && T > kBigNode ? 1 : 0, n_tiny = T <= kTinyNode ? 1 : 0,
-            n_small = 1 - n_split - n_big - n_tiny;
+        // Level-synchronous build WITHOUT a host round trip per level.  The device keeps a descriptor per level (class sizes,
+        // node range); the host launches each level's kernels with grid UPPER BOUNDS derived from the last counts it has seen
+        // (a child is never in a larger size class than its parent, so a class at most doubles per level and is capped by
+        // T / its minimum length) and reads the descriptors back only every kSyncEvery levels, to tighten the bounds and to
+        // notice that nothing is left to split.  Levels enqueued past the end find empty classes and return at once.
+        constexpr int kSyncEvery = 4;
+        LevelDesc l0{};
+        l0.n_class[CLS_SPLIT] = T > split_node ? 1 : 0;
+        l0.n_class[CLS_BIG] = !l0.n_class[CLS_SPLIT] && T > kBigNode ? 1 : 0;
+        l0.n_class[CLS_TINY] = T <= kTinyNode ? 1 : 0;
+        l0.n_class[CLS_SMALL] = 1 - l0.n_class[CLS_SPLIT] - l0.n_class[CLS_BIG] - l0.n_class[CLS_TINY];
+        l0.base = 0;
+        l0.n = 1;
+        BK(cudaMemcpyAsync(d_lv, &l0, sizeof(l0), cudaMemcpyHostToDevice, st));
+        const_cast<LevelDesc&>(h_lv[0]) = l0;
         BK(cudaMemsetAsync(d_active, 0, sizeof(int), st));
         BK(cudaMemsetAsync(d_kl_split, 0, sizeof(int), st));
         BK(cudaMemsetAsync(d_kl_big, 0, sizeof(int), st));
         BK(cudaMemsetAsync(d_kl_small, 0, sizeof(int), st));
         BK(cudaMemsetAsync(d_kl_tiny, 0, sizeof(int), st));
-        while (n_split + n_big + n_small + n_tiny > 0) {
-            const int n_active = n_split + n_big + n_small + n_tiny;
+        const long long cap[4] = {(long long)(T / split_node + 1), (long long)(T / kBigNode + 1), (long long)(T / kTinyNode + 1), (long long)(T / (kMaxLeaf + 1) + 1)};
+        long long ub[4] = {l0.n_class[0], l0.n_class[1], l0.n_class[2], l0.n_class[3]};  // upper bounds of the current level's class sizes
+        int level = 0, known = 0;
+        while (ub[0] + ub[1] + ub[2] + ub[3] > 0) {
+            if (level + 2 >= kMaxLevels) { err = "tree deeper than 65536 levels"; return CNDL_ERR_INVALID; }
+            const int n_split = (int)ub[CLS_SPLIT], n_big = (int)ub[CLS_BIG], n_small = (int)ub[CLS_SMALL], n_tiny = (int)ub[CLS_TINY];
             LevelArgs g;
             g.a = a;
             g.active = d_active;
-            g.n_active = n_active;
-            g.child_base = (int)n_nodes;
+            g.lv = d_lv + level;
             g.stackless = stackless ? 1 : 0;
             g.swap_policy = rq.opts.swap_policy;
             g.swap_seed = rq.opts.swap_seed;
@@ -1115,7 +1169,6 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
             if (n_split) {
                 g.klist = d_kl_split;
                 sp.g = g;
-                sp.n_split = n_split;
                 // every split node is longer than split_node, so its chunks number at most T / chunk + one partial chunk per node
                 const unsigned grid = (unsigned)(T / split_chunk + (size_t)n_split);
                 split_prep_kernel<<<1, 1024, 0, st>>>(sp, split_chunk);
@@ -1144,12 +1197,12 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
                 if (s_big != st) BK(cudaStreamWaitEvent(s_big, ev_fork, 0));
                 if (s_small != st) BK(cudaStreamWaitEvent(s_small, ev_fork, 0));
             }
-            if (n_big) { g.klist = d_kl_big; level_step_kernel<1024><<<n_big, 1024, 0, s_big>>>(g); lc.n++; }
-            if (n_small) { g.klist = d_kl_small; level_step_kernel<128><<<n_small, 128, 0, s_small>>>(g); lc.n++; }
+            if (n_big) { g.klist = d_kl_big; level_step_kernel<1024><<<n_big, 1024, 0, s_big>>>(g, CLS_BIG); lc.n++; }
+            if (n_small) { g.klist = d_kl_small; level_step_kernel<128><<<n_small, 128, 0, s_small>>>(g, CLS_SMALL); lc.n++; }
             if (n_tiny) {
                 g.klist = d_kl_tiny;
                 const unsigned grid = (unsigned)((n_tiny + kTinyWarps - 1) / kTinyWarps);
-                level_step_tiny_kernel<<<grid, 32 * kTinyWarps, 0, st>>>(g, n_tiny);
+                level_step_tiny_kernel<<<grid, 32 * kTinyWarps, 0, st>>>(g);
                 lc.n++;
             }
             BK(cudaGetLastError());
@@ -1157,28 +1210,34 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
                 if (s_big != st) { BK(cudaEventRecord(ev_join[0], s_big)); BK(cudaStreamWaitEvent(st, ev_join[0], 0)); }
                 if (s_small != st) { BK(cudaEventRecord(ev_join[1], s_small)); BK(cudaStreamWaitEvent(st, ev_join[1], 0)); }
             }
-            const int base = (int)n_nodes, n = 2 * n_active;
-            level_base.push_back(base);
-            level_count.push_back(n);
-            n_nodes += (size_t)n;
-            // next level's active list
-            // the four class sizes of the next level land in mapped host memory: one synchronisation per level, no copies
-            if (n <= kSmallLevel) {
-                level_compact_small_kernel<<<1, 1024, 0, st>>>(a.nlen, base, n, split_node, d_active_next, d_kl_split, d_kl_big, d_kl_small, d_kl_tiny,
-                                                               d_counts);
-                lc.n++;
+            // next level's active list and descriptor
+            const long long n_next_ub = 2 * (ub[0] + ub[1] + ub[2] + ub[3]);
+            ++level;
+            if (n_next_ub <= kSmallLevel) {
+                level_compact_small_kernel<<<1, 1024, 0, st>>>(a.nlen, d_lv, d_host_lv, level, split_node, d_active_next, d_kl_split, d_kl_big, d_kl_small,
+                                                               d_kl_tiny);
             } else {
-                level_compact_chained_kernel<<<(n + kCompactTile - 1) / kCompactTile, 256, 0, st>>>(
-                    a.nlen, base, n, split_node, d_active_next, d_kl_split, d_kl_big, d_kl_small, d_kl_tiny, d_counts, d_tiles, d_ticket,
-                    (int)level_base.size());
-                lc.n++;
+                level_compact_chained_kernel<<<(unsigned)((n_next_ub + kCompactTile - 1) / kCompactTile), 256, 0, st>>>(
+                    a.nlen, d_lv, d_host_lv, level, split_node, d_active_next, d_kl_split, d_kl_big, d_kl_small, d_kl_tiny, d_tiles);
             }
-            BK(cudaStreamSynchronize(st));
-            n_split = h_counts[0];
-            n_big = h_counts[1];
-            n_small = h_counts[2];
-            n_tiny = h_counts[3];
+            lc.n++;
             std::swap(d_active, d_active_next);
+            const long long all = ub[0] + ub[1] + ub[2] + ub[3];
+            const long long nb[4] = {2 * ub[0], 2 * (ub[0] + ub[1]), 2 * (ub[0] + ub[1] + ub[2]), 2 * all};
+            for (int c = 0; c < 4; ++c) ub[c] = std::min(nb[c], cap[c]);
+            if (level - known >= kSyncEvery) {
+                BK(cudaStreamSynchronize(st));
+                for (int c = 0; c < 4; ++c) ub[c] = h_lv[level].n_class[c];  // exact
+                known = level;
+            }
+        }
+        BK(cudaStreamSynchronize(st));
+        for (int l = 0; l <= level && l < kMaxLevels; ++l) {
+            const int n_l = h_lv[l].n;
+            if (l > 0 && n_l == 0) break;
+            const int base_l = h_lv[l].base;
+            if (l > 0) { level_base.push_back(base_l); level_count.push_back(n_l); }
+            n_nodes = (size_t)base_l + (size_t)n_l;
         }
         // flatten.  Runs of consecutive levels of at most kSmallLevel nodes (the top and the bottom of the tree) take one
         // single-CTA launch each instead of one launch per level.

@@ -21,7 +21,7 @@ struct BuildRequest {
     size_t n_nodes_out;          // result: LastNodeIndex + 1
     void** arena;                // scratch allocation kept by the context between builds
     size_t* arena_cap;
-    int** host_counts;           // 4 ints of mapped pinned memory kept by the context (per-level class sizes)
+    int** host_counts;           // mapped pinned memory kept by the context: the host copy of the builder's level descriptors (2 MB)
     cudaStream_t side[2] = {nullptr, nullptr};  // SAH builder: streams for the size classes of one level (optional)
     unsigned split_node = 0;     // SAH builder: ranges longer than this are split across CTAs (0 = default)
 };

@@ -2,6 +2,9 @@
 // (Source/Core/BVH/Intersector.h:60-124) held in device memory, plus the query entry points.
 #include "context.cuh"
 
+#include <map>
+#include <mutex>
+
 using namespace cndl;
 
 namespace cndl {
@@ -333,24 +336,37 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     return CNDL_OK;
 } CNDL_CATCH
 
+// BVH::BuildBVH as a free function keeps no state in the reference beyond file-scope statics (BVHConstructor.cpp:58-66); here the
+// state worth keeping between calls is the CUDA side: streams, the build arena, the mapped level descriptors.  One hidden context
+// per (device, node format) is created on first use and reused by later calls (serialised by a mutex; never destroyed: tearing CUDA
+// objects down from a static destructor races the runtime's own shutdown).
 int cndl_build_bvh(int node_format, int device, const cndl_vertex* verts, size_t V, const uint32_t* indices, size_t I,
                    const int32_t* mesh_id_per_tri, int32_t tri_offset, const cndl_build_opts* opts, void* nodes_out, size_t nodes_capacity,
-                   size_t* n_nodes_out, cndl_triangle* tris_out, float* build_ms) {
+                   size_t* n_nodes_out, cndl_triangle* tris_out, float* build_ms) try {
     if (!n_nodes_out || tri_offset < 0) return CNDL_ERR_INVALID;
-    cndl_ctx* ctx = nullptr;
-    int rc = cndl_create(&ctx, node_format, device);
-    if (rc != CNDL_OK) return rc;
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, cndl_ctx*> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    cndl_ctx*& ctx = cache[std::make_pair(device, node_format)];
+    if (!ctx) {
+        const int rc0 = cndl_create(&ctx, node_format, device);
+        if (rc0 != CNDL_OK) { cache.erase(std::make_pair(device, node_format)); return rc0; }
+    }
+    // an empty scene again (the device buffers keep their capacity)
+    ctx->n_nodes = ctx->n_tris = ctx->n_verts = 0;
+    ctx->nodes.bytes = ctx->tris.bytes = ctx->verts.bytes = 0;
+    ctx->objects.clear();
+    ctx->committed = false;
     ctx->tri_offset_bias = tri_offset;
-    rc = cndl_add_object(ctx, 2, verts, V, indices, I, mesh_id_per_tri, opts);
+    int rc = cndl_add_object(ctx, 2, verts, V, indices, I, mesh_id_per_tri, opts);
     if (rc == CNDL_OK) {
         *n_nodes_out = ctx->n_nodes;
         if (build_ms) *build_ms = ctx->last_build_ms;
         if (nodes_out && nodes_capacity < ctx->n_nodes) rc = CNDL_ERR_INVALID;  // 2 * T - 1 always suffices
         else rc = cndl_read_buffers(ctx, nodes_out, tris_out, nullptr);
     }
-    cndl_destroy(ctx);
     return rc;
-}
+} CNDL_CATCH
 
 int cndl_commit(cndl_ctx* ctx, int clear_host) try {
     (void)clear_host;  // the host never keeps a copy: the device buffers are the only ones
