@@ -188,6 +188,13 @@ void cndl_destroy(cndl_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& s : ctx->streams) if (s) cudaStreamDestroy(s);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    for (auto& fs : ctx->frame_stream) if (fs) cudaStreamDestroy(fs);
+    if (ctx->frame_copy_stream) cudaStreamDestroy(ctx->frame_copy_stream);
+    for (auto& f : ctx->frame) {
+        if (f.traced) cudaEventDestroy(f.traced);
+        if (f.copied) cudaEventDestroy(f.copied);
+        if (f.h_counts) cudaFreeHost(f.h_counts);
+    }
     if (ctx->build_arena) cudaFree(ctx->build_arena);
     if (ctx->build_host_counts) cudaFreeHost(ctx->build_host_counts);
     for (auto& e : ctx->events) cudaEventDestroy(e);

@@ -48,6 +48,7 @@ struct DeviceBuffer {
 };
 
 constexpr int kCounterSlots = 64;
+constexpr int kFrameSlots = 4;   // frames in flight per context (cndl_frame_submit's `slot`)
 
 struct ObjectData { int tri_offset, vert_offset, node_offset, node_count, tri_count, vert_count; };  // _ObjectData, Intersector.h:51-56 (+ counts)
 
@@ -104,8 +105,8 @@ struct cndl_ctx {
     size_t build_arena_cap = 0;
     int* build_host_counts = nullptr;
     unsigned counter_next = 0;   // next_counter(): ring of work-counter slots for device calls
-    cndl::FrameSlot frame[2];
-    cudaStream_t frame_stream = nullptr, frame_copy_stream = nullptr;
+    cndl::FrameSlot frame[cndl::kFrameSlots];
+    cudaStream_t frame_stream[cndl::kFrameSlots] = {}, frame_copy_stream = nullptr;  // one compute stream per slot: the kernels of two frames in flight interleave
     int tri_offset_bias = 0;  // cndl_build_bvh: BuildBVH's t_offset for a stand-alone build
 
     int fail(int code, const std::string& msg) { err = msg; return code; }

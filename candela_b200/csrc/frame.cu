@@ -186,7 +186,8 @@ int check_params(cndl_ctx* ctx, const cndl_frame_params* p, TileMap& tm) {
 size_t record_bytes(int fmt) { return fmt == CNDL_FRAME_OUT_HIT16 ? sizeof(cndl_hit16) : 32; }
 
 int ensure_frame_streams(cndl_ctx* ctx) {
-    if (!ctx->frame_stream) CK(cudaStreamCreateWithFlags(&ctx->frame_stream, cudaStreamNonBlocking));
+    for (auto& fs : ctx->frame_stream)
+        if (!fs) CK(cudaStreamCreateWithFlags(&fs, cudaStreamNonBlocking));
     if (!ctx->frame_copy_stream) CK(cudaStreamCreateWithFlags(&ctx->frame_copy_stream, cudaStreamNonBlocking));
     for (auto& f : ctx->frame) {
         if (!f.traced) CK(cudaEventCreateWithFlags(&f.traced, cudaEventDisableTiming));
@@ -220,7 +221,7 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
     TileMap tm;
     int rc = check_params(ctx, p, tm);
     if (rc != CNDL_OK) return rc;
-    if (!d_out || slot < 0 || slot > 1) return ctx->fail(CNDL_ERR_INVALID, "null output or bad slot");
+    if (!d_out || slot < 0 || slot >= kFrameSlots) return ctx->fail(CNDL_ERR_INVALID, "null output or bad slot");
     rc = check_ready(ctx);
     if (rc != CNDL_OK) return rc;
     if (ctx->mode != 2) return ctx->fail(CNDL_ERR_INVALID, "frame-level calls need traversal mode 2");
@@ -328,7 +329,7 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
 } CNDL_CATCH
 
 uint64_t cndl_frame_rays_traced(const cndl_ctx* ctx, int slot) {
-    if (!ctx || slot < 0 || slot > 1) return 0;
+    if (!ctx || slot < 0 || slot >= kFrameSlots) return 0;
     const FrameSlot& f = ctx->frame[slot];
     uint64_t n = 0;
     for (int b = 0; b < f.n_counts; ++b) n += f.h_counts[b];
@@ -340,7 +341,7 @@ int cndl_frame_submit(cndl_ctx* ctx, const cndl_frame_params* p, void* host_out,
     TileMap tm;
     int rc = check_params(ctx, p, tm);
     if (rc != CNDL_OK) return rc;
-    if (!host_out || slot < 0 || slot > 1) return ctx->fail(CNDL_ERR_INVALID, "null output or bad slot");
+    if (!host_out || slot < 0 || slot >= kFrameSlots) return ctx->fail(CNDL_ERR_INVALID, "null output or bad slot");
     CK(cudaSetDevice(ctx->device));
     rc = ensure_frame_streams(ctx);
     if (rc != CNDL_OK) return rc;
@@ -354,10 +355,10 @@ int cndl_frame_submit(cndl_ctx* ctx, const cndl_frame_params* p, void* host_out,
     CK(f.out.ensure_scratch(bytes ? bytes : 16));
     const int shards = p->shard_count > 0 ? p->shard_count : 1;
     if (shards > 1 && !(p->flags & CNDL_FRAME_LOCAL_LAYOUT))  // pixels of other shards are not written: give them a defined value
-        CK(cudaMemsetAsync(f.out.p, 0xFF, bytes, ctx->frame_stream));
-    rc = cndl_trace_frame_device(ctx, p, f.out.p, slot, ctx->frame_stream);
+        CK(cudaMemsetAsync(f.out.p, 0xFF, bytes, ctx->frame_stream[slot]));
+    rc = cndl_trace_frame_device(ctx, p, f.out.p, slot, ctx->frame_stream[slot]);
     if (rc != CNDL_OK) return rc;
-    CK(cudaEventRecord(f.traced, ctx->frame_stream));
+    CK(cudaEventRecord(f.traced, ctx->frame_stream[slot]));
     CK(cudaStreamWaitEvent(ctx->frame_copy_stream, f.traced, 0));
     CK(cudaMemcpyAsync(host_out, f.out.p, bytes, cudaMemcpyDeviceToHost, ctx->frame_copy_stream));
     CK(cudaEventRecord(f.copied, ctx->frame_copy_stream));
@@ -366,7 +367,7 @@ int cndl_frame_submit(cndl_ctx* ctx, const cndl_frame_params* p, void* host_out,
 } CNDL_CATCH
 
 int cndl_frame_wait(cndl_ctx* ctx, int slot) try {
-    if (!ctx || slot < 0 || slot > 1) return CNDL_ERR_INVALID;
+    if (!ctx || slot < 0 || slot >= kFrameSlots) return CNDL_ERR_INVALID;
     FrameSlot& f = ctx->frame[slot];
     if (!f.pending) return CNDL_OK;
     CK(cudaSetDevice(ctx->device));
@@ -517,11 +518,11 @@ struct cndl_multi {
     std::string err;
     bool peer = false;                 // every device can store into the first one's memory
     bool peer_capable = false;
-    std::vector<cudaEvent_t> done[2];  // per slot, per device: its shard's records are in the first device's frame
-    std::vector<cndl::DeviceBuffer*> stage[2];  // without peer access: shard in local layout on its own device / on the first device
+    std::vector<cudaEvent_t> done[kFrameSlots];  // per slot, per device: its shard's records are in the first device's frame
+    std::vector<cndl::DeviceBuffer*> stage[kFrameSlots];  // without peer access: shard in local layout on its own device / on the first device
     float replicate_ms = 0.0f;
-    bool pending[2] = {false, false};
-    unsigned long long rays_traced[2] = {0, 0};
+    bool pending[kFrameSlots] = {};
+    unsigned long long rays_traced[kFrameSlots] = {};
     int fail(int code, const std::string& msg) { err = msg; return code; }
     int fail_from(int code, int i) { err = "device " + std::to_string(devices[(size_t)i]) + ": " + ctx[(size_t)i]->err; return code; }
 };
@@ -558,7 +559,7 @@ int cndl_multi_create(cndl_multi** out, int node_format, const int* devices, int
         cudaGetLastError();
     }
     m->peer_capable = m->peer;
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < kFrameSlots; ++s)
         for (int i = 0; i < n_devices; ++i) {
             cudaSetDevice(devices[i]);
             cudaEvent_t e = nullptr;
@@ -573,7 +574,7 @@ int cndl_multi_create(cndl_multi** out, int node_format, const int* devices, int
 
 void cndl_multi_destroy(cndl_multi* m) {
     if (!m) return;
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kFrameSlots; ++s) {
         for (size_t i = 0; i < m->done[s].size(); ++i) {
             cudaSetDevice(m->devices[i]);
             cudaDeviceSynchronize();
@@ -599,7 +600,7 @@ int cndl_multi_device_count(const cndl_multi* m) { return m ? (int)m->ctx.size()
 cndl_ctx* cndl_multi_context(cndl_multi* m, int i) { return (m && i >= 0 && (size_t)i < m->ctx.size()) ? m->ctx[(size_t)i] : nullptr; }
 const char* cndl_multi_last_error(const cndl_multi* m) { return m ? m->err.c_str() : "null handle"; }
 float cndl_multi_last_replicate_ms(const cndl_multi* m) { return m ? m->replicate_ms : 0.0f; }
-uint64_t cndl_multi_frame_rays_traced(const cndl_multi* m, int slot) { return (m && slot >= 0 && slot < 2) ? m->rays_traced[slot] : 0; }
+uint64_t cndl_multi_frame_rays_traced(const cndl_multi* m, int slot) { return (m && slot >= 0 && slot < kFrameSlots) ? m->rays_traced[slot] : 0; }
 
 int cndl_multi_add_object(cndl_multi* m, uint32_t object_id, const cndl_vertex* verts, size_t V, const uint32_t* indices, size_t I,
                           const int32_t* mesh_id_per_tri, const cndl_build_opts* opts) try {
@@ -659,7 +660,7 @@ int cndl_multi_buffer_entities(cndl_multi* m) {
 }
 
 int cndl_multi_frame_wait(cndl_multi* m, int slot) {
-    if (!m || slot < 0 || slot > 1) return CNDL_ERR_INVALID;
+    if (!m || slot < 0 || slot >= kFrameSlots) return CNDL_ERR_INVALID;
     if (!m->pending[slot]) return CNDL_OK;
     cndl_ctx* c0 = m->ctx[0];
     cudaSetDevice(m->devices[0]);
@@ -677,7 +678,7 @@ int cndl_multi_frame_wait(cndl_multi* m, int slot) {
 }
 
 int cndl_multi_frame_submit(cndl_multi* m, const cndl_frame_params* p, void* host_out, int slot) try {
-    if (!m || !p || !host_out || slot < 0 || slot > 1) return CNDL_ERR_INVALID;
+    if (!m || !p || !host_out || slot < 0 || slot >= kFrameSlots) return CNDL_ERR_INVALID;
     int rc = CNDL_OK;
     if (m->pending[slot]) {
         rc = cndl_multi_frame_wait(m, slot);
@@ -695,12 +696,10 @@ int cndl_multi_frame_submit(cndl_multi* m, const cndl_frame_params* p, void* hos
         cndl_ctx* c = m->ctx[(size_t)i];
         q.shard_index = i;
         cudaSetDevice(m->devices[(size_t)i]);
-        if (!c->frame_stream) {  // created by the first frame call on the context
-            cudaStreamCreateWithFlags(&c->frame_stream, cudaStreamNonBlocking);
-        }
+        if (!c->frame_stream[slot]) cudaStreamCreateWithFlags(&c->frame_stream[slot], cudaStreamNonBlocking);  // else: created by the first frame call on the context
         if (m->peer || i == 0) {
             // the resolve kernel of device i stores its pixels straight into the first device's frame (NVLink peer memory)
-            rc = cndl_trace_frame_device(c, &q, c0->frame[slot].out.p, slot, c->frame_stream);
+            rc = cndl_trace_frame_device(c, &q, c0->frame[slot].out.p, slot, c->frame_stream[slot]);
             if (rc != CNDL_OK) return m->fail_from(rc, i);
         } else {
             // no peer access: shard in local layout on its own device, copied to the first device, untiled there
@@ -710,14 +709,14 @@ int cndl_multi_frame_submit(cndl_multi* m, const cndl_frame_params* p, void* hos
             cndl::DeviceBuffer* own = m->stage[slot][2 * (size_t)i];
             cndl::DeviceBuffer* at0 = m->stage[slot][2 * (size_t)i + 1];
             if (own->ensure_scratch(sb ? sb : 16) != cudaSuccess) return m->fail(CNDL_ERR_OOM, "shard buffer");
-            rc = cndl_trace_frame_device(c, &ql, own->p, slot, c->frame_stream);
+            rc = cndl_trace_frame_device(c, &ql, own->p, slot, c->frame_stream[slot]);
             if (rc != CNDL_OK) return m->fail_from(rc, i);
             cudaSetDevice(m->devices[0]);
             if (at0->ensure_scratch(sb ? sb : 16) != cudaSuccess) return m->fail(CNDL_ERR_OOM, "shard buffer");
             cudaSetDevice(m->devices[(size_t)i]);
-            cudaMemcpyPeerAsync(at0->p, m->devices[0], own->p, m->devices[(size_t)i], sb, c->frame_stream);
+            cudaMemcpyPeerAsync(at0->p, m->devices[0], own->p, m->devices[(size_t)i], sb, c->frame_stream[slot]);
         }
-        cudaEventRecord(m->done[slot][(size_t)i], c->frame_stream);
+        cudaEventRecord(m->done[slot][(size_t)i], c->frame_stream[slot]);
     }
     // first device: wait for every shard, (untile the staged ones,) one copy to the host
     cudaSetDevice(m->devices[0]);

