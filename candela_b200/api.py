@@ -444,8 +444,9 @@ class RayIntersector:
         self._check(self._lib.cndl_read_buffers(self._h, _p(nodes), _p(tris), _p(verts)))
         return nodes, tris, verts
 
-    def set_traversal_mode(self, mode: int, sort_rays: int = 0):
-        """sort_rays: 0 off, 1 (or True) octant buckets, 2 octant + origin Morton order."""
+    def set_traversal_mode(self, mode: int, sort_rays: int = 4):
+        """sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order (rays moved), 3 the same through an index list,
+        4 automatic (3 for large batches on scenes beyond the L2, else off; the library's default)."""
         self._check(self._lib.cndl_set_traversal_mode(self._h, mode, int(sort_rays)))
 
     def set_tuning(self, knob: int, value: int):

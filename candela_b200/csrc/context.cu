@@ -48,6 +48,13 @@ int check_ready(cndl_ctx* ctx) {
     return CNDL_OK;
 }
 
+// sort_rays as it applies to a batch of R rays: 4 = automatic
+int effective_sort(const cndl_ctx* ctx, size_t R) {
+    if (ctx->sort_rays != 4) return ctx->sort_rays;
+    const size_t scene_bytes = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 64;
+    return (scene_bytes > ((size_t)96 << 20) && R >= (1u << 20)) ? 3 : 0;
+}
+
 // 64-byte work-counter slots handed out round-robin: two device calls in flight on different streams never share one
 // (a slot is reused after kCounterSlots further calls on the context).
 unsigned* next_counter(cndl_ctx* ctx) {
@@ -61,6 +68,8 @@ unsigned* next_counter(cndl_ctx* ctx) {
 int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, const unsigned* d_R, cndl_hit* d_hits, float* d_any, unsigned* scratch,
                   unsigned* order_region, cndl_ray* sorted_region, cudaStream_t st) {
     if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 rays in one call");
+    if ((reinterpret_cast<uintptr_t>(d_rays) & 31u) || (reinterpret_cast<uintptr_t>(d_hits) & 31u))
+        return ctx->fail(CNDL_ERR_INVALID, "ray and hit buffers must be 32-byte aligned (the kernels move each record with one 256-bit access)");
     if (d_R && ctx->mode != 2) return ctx->fail(CNDL_ERR_INVALID, "a device-side batch length needs traversal mode 2");
     const SceneView s = scene_view(ctx);
     const bool stack = ctx->format == CNDL_STACK;
@@ -68,11 +77,14 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, con
     else if (ctx->mode == 1) launch_trace_persistent(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, scratch, ctx->sm_count, st, ctx->launches);
     else {
         RayOrder order{nullptr, nullptr, 0, d_R, nullptr};
-        if (ctx->sort_rays && order_region && R >= 65536 && !d_R) {
-            if (ctx->sort_rays >= 2) {
+        // sort_rays 4 (the default) decides by the scene: once nodes + triangle records no longer fit the L2, ordering a large batch by
+        // (octant, origin cell) pays for itself (10 M triangles, 12.5 M random rays: 5.36 -> 4.71 ms with the sort counted)
+        const int sort_mode = effective_sort(ctx, R);
+        if (sort_mode && order_region && R >= 65536 && !d_R) {
+            if (sort_mode >= 2) {
                 // 2: the rays are MOVED into sorted order (sorted_region) and the results scattered back through the index list;
                 // 3: the rays stay and are read through the index list
-                cndl_ray* sorted = ctx->sort_rays == 2 ? sorted_region : nullptr;
+                cndl_ray* sorted = sort_mode == 2 ? sorted_region : nullptr;
                 cudaError_t se = sort_rays_morton(d_rays, R, ctx->world_lo, ctx->world_hi, order_region, sorted, reinterpret_cast<int*>(order_region + R), st,
                                                   ctx->launches);
                 if (se != cudaSuccess) return ctx->cuda_fail(se, "ray sort");
@@ -91,8 +103,10 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, con
         if (variant == 0) {
             // automatic: a scene that fits the 126 MB L2 is served best by the plain kernel; once the node and triangle
             // records spill to DRAM, staging the top of the tree in shared memory wins (10 M triangles: +8.7 %)
-            const size_t working_set = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 48;
-            variant = (!stack && working_set > ((size_t)96 << 20) && order.out_index == nullptr) ? 34 : 18;  // physically sorted rays: L2 hits rise and the plain kernel's higher residency wins (4.85 vs 5.20 ms)
+            const size_t working_set = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 64;
+            // ... unless the batch has just been ordered: neighbouring rays then share nodes, L2 hits rise and the plain kernel's
+            // higher residency wins (10 M triangles: 4.71 vs 5.03 ms)
+            variant = (!stack && working_set > ((size_t)96 << 20) && !(sort_mode >= 2 && order_region && R >= 65536 && !d_R)) ? 34 : 18;
         }
         int steps = variant & 7;
         if (steps < 1 || steps > 4) steps = 2;
@@ -381,7 +395,7 @@ int cndl_commit(cndl_ctx* ctx, int clear_host) try {
     if (ctx->n_tris == 0) return ctx->fail(CNDL_ERR_INVALID, "nothing to commit");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->main_stream;
-    CK(ctx->tri48.ensure_scratch(ctx->n_tris * 48));
+    CK(ctx->tri48.ensure_scratch(ctx->n_tris * 64));  // 64-byte triangle records (traverse.cuh)
     ctx->committed = false;
     ctx->hot_ready = false;
     ctx->nodes_valid = false;
@@ -520,7 +534,7 @@ int cndl_buffer_entities(cndl_ctx* ctx) try {
 } CNDL_CATCH
 
 int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays) {
-    if (!ctx || mode < 0 || mode > 2 || sort_rays < 0 || sort_rays > 3) return CNDL_ERR_INVALID;
+    if (!ctx || mode < 0 || mode > 2 || sort_rays < 0 || sort_rays > 4) return CNDL_ERR_INVALID;
     ctx->mode = mode;
     ctx->sort_rays = sort_rays;
     return CNDL_OK;
@@ -540,8 +554,8 @@ int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t 
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     const int kind = (flags & CNDL_IGNORE_TRANSPARENT) ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST;
-    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
-    if (ctx->sort_rays == 2) CK(ctx->d_sorted.ensure_scratch(R * sizeof(cndl_ray)));
+    if (effective_sort(ctx, R)) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
+    if (effective_sort(ctx, R) == 2) CK(ctx->d_sorted.ensure_scratch(R * sizeof(cndl_ray)));
     return enqueue_trace(ctx, kind, d_rays, R, nullptr, d_hits, nullptr, next_counter(ctx), static_cast<unsigned*>(ctx->d_order.p),
                          static_cast<cndl_ray*>(ctx->d_sorted.p), static_cast<cudaStream_t>(stream));
 } CNDL_CATCH
@@ -552,8 +566,8 @@ int cndl_intersect_any_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, f
     int rc = check_ready(ctx);
     if (rc != CNDL_OK) return rc;
     CK(cudaSetDevice(ctx->device));
-    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
-    if (ctx->sort_rays == 2) CK(ctx->d_sorted.ensure_scratch(R * sizeof(cndl_ray)));
+    if (effective_sort(ctx, R)) CK(ctx->d_order.ensure_scratch(order_region_ints(R) * sizeof(unsigned)));
+    if (effective_sort(ctx, R) == 2) CK(ctx->d_sorted.ensure_scratch(R * sizeof(cndl_ray)));
     return enqueue_trace(ctx, Q_ANY, d_rays, R, nullptr, nullptr, d_t_out, next_counter(ctx), static_cast<unsigned*>(ctx->d_order.p),
                          static_cast<cndl_ray*>(ctx->d_sorted.p), static_cast<cudaStream_t>(stream));
 } CNDL_CATCH
@@ -583,8 +597,9 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
         ctx->events.push_back(e);
     }
     CK(ctx->d_chunk_counters.ensure_scratch(n_chunks * 64));
-    if (ctx->sort_rays) CK(ctx->d_order.ensure_scratch((order_region_ints(chunk) * n_chunks) * sizeof(unsigned)));
-    if (ctx->sort_rays == 2) CK(ctx->d_sorted.ensure_scratch(R * sizeof(cndl_ray)));
+    const int chunk_sort = effective_sort(ctx, chunk);
+    if (chunk_sort) CK(ctx->d_order.ensure_scratch((order_region_ints(chunk) * n_chunks) * sizeof(unsigned)));
+    if (chunk_sort == 2) CK(ctx->d_sorted.ensure_scratch(R * sizeof(cndl_ray)));
     size_t k = 0;
     for (size_t lo = 0; lo < R; lo += chunk, ++k) {
         const size_t n = R - lo < chunk ? R - lo : chunk;
@@ -597,8 +612,8 @@ static int host_query(cndl_ctx* ctx, int kind, const cndl_ray* rays, size_t R, c
         unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->d_chunk_counters.p) + 64 * k);
         rc = enqueue_trace(ctx, kind, dr, n, nullptr, kind == Q_ANY ? nullptr : reinterpret_cast<cndl_hit*>(dout),
                            kind == Q_ANY ? reinterpret_cast<float*>(dout) : nullptr, counter,
-                           ctx->sort_rays ? static_cast<unsigned*>(ctx->d_order.p) + order_region_ints(chunk) * k : nullptr,
-                           ctx->sort_rays == 2 ? static_cast<cndl_ray*>(ctx->d_sorted.p) + lo : nullptr, ks);
+                           chunk_sort ? static_cast<unsigned*>(ctx->d_order.p) + order_region_ints(chunk) * k : nullptr,
+                           chunk_sort == 2 ? static_cast<cndl_ray*>(ctx->d_sorted.p) + lo : nullptr, ks);
         if (rc != CNDL_OK) return rc;
         CK(cudaEventRecord(ctx->events[2 * k + 1], ks));
         CK(cudaStreamWaitEvent(ctx->streams[2], ctx->events[2 * k + 1], 0));

@@ -88,7 +88,7 @@ struct cndl_ctx {
     std::vector<cudaEvent_t> events;
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};  // H2D, traversal (even chunks), D2H, traversal (odd chunks)
     cudaStream_t main_stream = nullptr;
-    int mode = 2, sort_rays = 0;   // sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order (rays moved), 3 the same through an index list
+    int mode = 2, sort_rays = 4;   // sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order (rays moved), 3 the same through an index list, 4 automatic
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};  // bounds of all entities (for sort_rays = 2)
     int knobs[9] = {8, 14, 10, 0, 0, 12, 4096, 1024, 0};  // CNDL_KNOB_*
     // hot-first derived layout of the stackless nodes (kernels_hot.cu), rebuilt by cndl_commit
@@ -132,6 +132,7 @@ struct cndl_ctx {
 namespace cndl {
 SceneView scene_view(const cndl_ctx* ctx);
 size_t order_region_ints(size_t R);
+int effective_sort(const cndl_ctx* ctx, size_t R);
 int check_ready(cndl_ctx* ctx);
 // Enqueues one traversal batch on `st`.  scratch: 16 unsigned ints ([0] work counter); order_region: order_region_ints(R)
 // unsigned ints, used when ray ordering is on; d_R (optional): the batch length in device memory, R being its upper bound.

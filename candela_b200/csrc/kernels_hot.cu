@@ -31,11 +31,6 @@ namespace {
 
 enum LaneState : int { EMPTY = 0, WALK = 1, LEAF = 2, DONE = 3 };
 
-__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "l"(p));
-}
 
 // ---------------------------------------------------------------------------------------------
 // commit-time derivation
@@ -169,9 +164,8 @@ __global__ void gather_kernel(const int* __restrict__ perm, const int2* __restri
 // traversal
 
 __device__ __forceinline__ void store_hit(cndl_hit* __restrict__ hits, size_t i, float t, float u, float v, float w, int mesh, int tri, int ent, int iters) {
-    float4* p = reinterpret_cast<float4*>(hits + i);
-    p[0] = make_float4(t, u, v, w);
-    reinterpret_cast<int4*>(p)[1] = make_int4(mesh, tri, ent, iters);
+    stg256(reinterpret_cast<float4*>(hits + i), make_float4(t, u, v, w),
+           make_float4(__int_as_float(mesh), __int_as_float(tri), __int_as_float(ent), __int_as_float(iters)));  // one 256-bit store
 }
 
 struct HLane {
@@ -194,7 +188,8 @@ __device__ __forceinline__ void next_entity_hot(const SceneView& s, const cndl_e
         const cndl_entity* ent = ents2 + e;
         if (KIND == Q_CLOSEST_IGNORE_TRANSPARENT && __int_as_float(__ldg(&ent->data[1])) < 0.99f) { ++e; continue; }
         const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
-        const float4 a = __ldg(rp), b = __ldg(rp + 1);
+        float4 a, b;
+        ldg256(rp, a, b);  // rays are 32-byte records, 32-byte aligned
         L.r = to_object_space(ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
         L.ptr = __ldg(&ent->node_offset);
         L.iters = 0;
@@ -283,12 +278,13 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
                             // tail of IntersectScene (SL:300-318)
                             float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
                             int mesh = -1;
-                            if (L.best_tri >= 0) mesh = __ldg(&s.tris[L.best_tri]).w;
+                            if (L.best_tri >= 0) mesh = tri_mesh(s.tri48, L.best_tri);
                             if (L.closest > 0.0f && L.best_tri > 0) {
                                 RayState r = L.r;
                                 if (L.best_ent != last_ent) {
                                     const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
-                                    const float4 a = __ldg(rp), b = __ldg(rp + 1);
+                                    float4 a, b;
+        ldg256(rp, a, b);  // rays are 32-byte records, 32-byte aligned
                                     r = to_object_space(ents2 + L.best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
                                 }
                                 const V3 p = {fadd(r.o.x, fmul(r.d.x, L.closest)), fadd(r.o.y, fmul(r.d.y, L.closest)), fadd(r.o.z, fmul(r.d.z, L.closest))};
@@ -399,7 +395,8 @@ __device__ __forceinline__ void pair_next_entity(const SceneView& s, const cndl_
         const cndl_entity* ent = ents2 + e;
         if (KIND == Q_CLOSEST_IGNORE_TRANSPARENT && __int_as_float(__ldg(&ent->data[1])) < 0.99f) { ++e; continue; }
         const float4* rp = reinterpret_cast<const float4*>(rays + S.rid);
-        const float4 a = __ldg(rp), b = __ldg(rp + 1);
+        float4 a, b;
+        ldg256(rp, a, b);  // rays are 32-byte records, 32-byte aligned
         const RayState r = to_object_space(ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
         S.o = r.o; S.d = r.d; S.inv = r.inv;
         S.ptr = __ldg(&ent->node_offset);
@@ -495,12 +492,13 @@ __global__ void __launch_bounds__(128, MINB) trace_pair_stackless_kernel(SceneVi
                             // tail of IntersectScene (SL:300-318); TMax == ClosestT once something was accepted
                             float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
                             int mesh = -1;
-                            if (T.best_tri >= 0) mesh = __ldg(&s.tris[T.best_tri]).w;
+                            if (T.best_tri >= 0) mesh = tri_mesh(s.tri48, T.best_tri);
                             if (T.best_tri > 0) {
                                 V3 ro = T.o, rd = T.d;
                                 if (T.best_ent != last_ent) {
                                     const float4* rp = reinterpret_cast<const float4*>(rays + T.rid);
-                                    const float4 a = __ldg(rp), b = __ldg(rp + 1);
+                                    float4 a, b;
+        ldg256(rp, a, b);  // rays are 32-byte records, 32-byte aligned
                                     const RayState r = to_object_space(ents2 + T.best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
                                     ro = r.o; rd = r.d;
                                 }

@@ -231,7 +231,7 @@ __device__ __forceinline__ HitFrame hit_frame(const cndl_ray* __restrict__ rays,
     const V3 o = {ra.x, ra.y, ra.z}, d = {rb.x, rb.y, rb.z};
     f.p = vadd(o, vscale(d, h0.x));
     f.in = d;
-    const float4 c = __ldg(tri48 + 3 * (size_t)h1.y + 2);  // .yzw = cross(v1 - v0, v2 - v0), object space
+    const float4 c = __ldg(tri48 + kTriStride * (size_t)h1.y + 2);  // .yzw = cross(v1 - v0, v2 - v0), object space
     const float* m = ents[h1.z].model;
     const V3 nw = {fadd(fadd(fmul(__ldg(m + 0), c.y), fmul(__ldg(m + 4), c.z)), fmul(__ldg(m + 8), c.w)),
                    fadd(fadd(fmul(__ldg(m + 1), c.y), fmul(__ldg(m + 5), c.z)), fmul(__ldg(m + 9), c.w)),

@@ -33,16 +33,10 @@ enum LaneState : int { EMPTY = 0, WALK = 1, LEAF = 2, DONE = 3 };
 constexpr int NO_MORE_ENTITIES = 0x3FFFFFFF;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
-__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "l"(p));
-}
 
 __device__ __forceinline__ void store_hit(cndl_hit* __restrict__ hits, size_t i, float t, float u, float v, float w, int mesh, int tri, int ent, int iters) {
-    float4* p = reinterpret_cast<float4*>(hits + i);
-    p[0] = make_float4(t, u, v, w);
-    reinterpret_cast<int4*>(p)[1] = make_int4(mesh, tri, ent, iters);
+    stg256(reinterpret_cast<float4*>(hits + i), make_float4(t, u, v, w),
+           make_float4(__int_as_float(mesh), __int_as_float(tri), __int_as_float(ent), __int_as_float(iters)));  // one 256-bit store
 }
 
 // tail of IntersectScene (SL:300-318 / ST:347-365): `closest` is TMax after the last acceptance
@@ -50,12 +44,13 @@ __device__ __forceinline__ void retire_closest(const SceneView& s, const cndl_ra
                                                const RayState& cur, int cur_ent, float closest, int best_tri, int best_ent, int iters) {
     float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
     int mesh = -1;
-    if (best_tri >= 0) mesh = __ldg(&s.tris[best_tri]).w;
+    if (best_tri >= 0) mesh = tri_mesh(s.tri48, best_tri);
     if (best_tri > 0) {  // ClosestT > 0 && TriangleIdx > 0: global triangle 0 reports as a miss
         RayState r = cur;
         if (best_ent != cur_ent) {
             const float4* rp = reinterpret_cast<const float4*>(rays + rid);
-            const float4 a = __ldg(rp), b = __ldg(rp + 1);
+            float4 a, b;
+        ldg256(rp, a, b);  // rays are 32-byte records, 32-byte aligned
             r = to_object_space(s.ents + best_ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
         }
         t = closest;
@@ -86,7 +81,8 @@ __device__ __forceinline__ void next_entity(const SceneView& s, const cndl_ray* 
         const cndl_entity* ent = s.ents + e;
         if (KIND == Q_CLOSEST_IGNORE_TRANSPARENT && __int_as_float(__ldg(&ent->data[1])) < 0.99f) { ++e; continue; }
         const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
-        const float4 a = __ldg(rp), b = __ldg(rp + 1);
+        float4 a, b;
+        ldg256(rp, a, b);  // rays are 32-byte records, 32-byte aligned
         L.r = to_object_space(ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
         L.start = __ldg(&ent->node_offset);
         // Pointer >= 0 && Pointer >= NodeStart && Pointer <= NodeStart+NodeCount && Pointer <= u_TotalNodes
@@ -309,7 +305,8 @@ __device__ __forceinline__ void next_entity_stack(const SceneView& s, const cndl
         const cndl_entity* ent = s.ents + e;
         if (KIND == Q_CLOSEST_IGNORE_TRANSPARENT && __int_as_float(__ldg(&ent->data[1])) < 0.99f) { ++e; continue; }
         const float4* rp = reinterpret_cast<const float4*>(rays + L.rid);
-        const float4 a = __ldg(rp), b = __ldg(rp + 1);
+        float4 a, b;
+        ldg256(rp, a, b);  // rays are 32-byte records, 32-byte aligned
         L.r = to_object_space(ent, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z});
         L.start = __ldg(&ent->node_offset);
         L.lo = L.start > 0 ? L.start : 0;  // ST:201-205

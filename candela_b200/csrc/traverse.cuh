@@ -63,13 +63,33 @@ struct RayState {
     bool nan_path;  // some operand can make 0*inf: use the literal GLSL min/max
 };
 
+// One 256-bit load (LDG.E.256, read-only path): a 32-byte record costs one L1 wavefront instead of two.
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(float4* p, float4 a, float4 b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z),
+                 "f"(b.w)
+                 : "memory");
+}
+
+// The per-triangle record is 64 bytes, 64-byte aligned: {v0, e1.x | e1.yz, e2.xy | e2.z, n | mesh id, 0, 0, 0} — the 48 bytes of
+// ray-independent sub-expressions of RayTriangle plus the triangle's GlobalMeshNumber — so a triangle test costs two 256-bit loads
+// (two L1 wavefronts; three 128-bit loads of a 48-byte record cost three) and retiring a ray needs no look-up in the triangle buffer.
+constexpr int kTriStride = 4;  // float4s per record
 __device__ __forceinline__ void load_tri48(const float4* __restrict__ tri48, int idx, V3& v0, V3& e1, V3& e2, V3& n) {
-    const float4 a = __ldg(tri48 + 3 * (size_t)idx), b = __ldg(tri48 + 3 * (size_t)idx + 1), c = __ldg(tri48 + 3 * (size_t)idx + 2);
+    float4 a, b, c, d;
+    ldg256(tri48 + kTriStride * (size_t)idx, a, b);
+    ldg256(tri48 + kTriStride * (size_t)idx + 2, c, d);
     v0 = {a.x, a.y, a.z};
     e1 = {a.w, b.x, b.y};
     e2 = {b.z, b.w, c.x};
     n = {c.y, c.z, c.w};
 }
+
+__device__ __forceinline__ int tri_mesh(const float4* __restrict__ tri48, int idx) { return __float_as_int(__ldg(&tri48[kTriStride * (size_t)idx + 3].x)); }
 
 // RayTriangle, SL:79-97 / ST:87-105. Returns t, or -1 when outside.
 __device__ __forceinline__ float ray_triangle(const float4* __restrict__ tri48, int idx, V3 ro, V3 rd) {
@@ -264,7 +284,7 @@ __device__ __forceinline__ cndl_hit scene_closest(const SceneView& s, V3 ro, V3 
             h.entity = i;
         }
     }
-    if (h.tri >= 0) h.mesh = __ldg(&s.tris[h.tri]).w;
+    if (h.tri >= 0) h.mesh = tri_mesh(s.tri48, h.tri);
     if (closest > 0.0f && h.tri > 0) {  // SL:300 — global triangle 0 reports as a miss
         const RayState r = to_object_space(s.ents + h.entity, ro, rd);
         const V3 p = {fadd(r.o.x, fmul(r.d.x, closest)), fadd(r.o.y, fmul(r.d.y, closest)), fadd(r.o.z, fmul(r.d.z, closest))};

@@ -155,8 +155,8 @@ enum { CNDL_IGNORE_TRANSPARENT = 1 /* IntersectSceneIgnoreTransparent, …Stackl
 int cndl_intersect_closest(cndl_ctx* ctx, const cndl_ray* rays, size_t R, int flags, cndl_hit* hits);
 /* float IntersectRay(o, d) (any hit; …Stackless.glsl:558-579): t_out[i] = first accepted t or -1. */
 int cndl_intersect_any(cndl_ctx* ctx, const cndl_ray* rays, size_t R, float* t_out);
-/* Same queries on DEVICE buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream)
- * and not synchronised.  Each call takes its own work counter from a ring of 64, so traversal calls in flight on different
+/* Same queries on DEVICE buffers (32-byte aligned, like anything cudaMalloc returns), enqueued on `stream` (a cudaStream_t;
+ * NULL = default stream) and not synchronised.  Each call takes its own work counter from a ring of 64, so traversal calls in flight on different
  * streams do not interfere; calls that use the context's ordering / generation scratch (cndl_set_traversal_mode sort_rays != 0,
  * cndl_generate_rays_device) must be enqueued on ONE stream at a time (or ordered by events). */
 int cndl_intersect_closest_device(cndl_ctx* ctx, const cndl_ray* d_rays, size_t R, int flags, cndl_hit* d_hits, void* stream);
@@ -372,9 +372,11 @@ void cndl_host_free(void* p);
 
 /* Traversal tuning (never changes results): mode 0 = one thread per ray, 1 = persistent warps with
  * ray re-fetch (stackless format only), 2 = persistent while-while with postponed leaf tests (default);
- * sort_rays reorders the rays inside the call (batches of >= 65536 rays): 1 = stable buckets by direction octant (L2-resident scenes:
- * -8 % traversal time for incoherent batches, about the cost of the partition); 2 = direction octant, then Morton order of the origin
- * cell, 3 bits per axis, by one counting sort (scenes beyond the L2: 10 M triangles, 12.5 M random rays: 5.35 -> 5.11 ms including the sort). */
+ * sort_rays reorders the rays inside the call (batches of >= 65536 rays): 1 = stable buckets by direction octant; 2 = direction octant, then
+ * Morton order of the origin cell (3 bits per axis) by one counting sort, the rays MOVED into that order and the results scattered back;
+ * 3 = the same order through an index list (the rays stay where they are); 4 (default) = automatic: 3 when the scene (nodes + triangle
+ * records) exceeds 96 MB, i.e. no longer fits the L2, and the batch has at least 2^20 rays (10 M triangles, 12.5 M random rays: 5.36 -> 4.71 ms
+ * with the sort counted), else off (L2-resident scenes: ordering inside the call costs what it saves; let the generator emit octant-major). */
 int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays);
 enum { CNDL_KNOB_BLOCKS_PER_SM = 0,   /* persistent CTAs (128 threads) per SM */
        CNDL_KNOB_LEAF_THRESHOLD = 1,  /* mode 2: parked-at-leaf lanes that trigger the leaf phase */

@@ -84,7 +84,7 @@ def test_config4_two_million_triangles_build_and_trace(cb, ob):
     rays = scenes.random_rays(pos.min(0), pos.max(0) + np.array([0, 10, 0], np.float32), 1_000_000, seed=3)
     ents = ob.make_entity(np.eye(4, dtype=np.float32), 0, len(nodes))
     want, _ = ob.trace(ob.STACKLESS, ob.CLOSEST, nodes, tris, v, ents, rays, nthreads=ob.hardware_threads())
-    for sort in (0, 2):
+    for sort in (0, 2, 3, 4):       # no ordering, rays moved into (octant, origin cell) order, index list, automatic (= 3 here: the scene exceeds the L2)
         ri.set_traversal_mode(2, sort)
         assert ri.IntersectRays(rays).tobytes() == want.tobytes(), sort
     assert float((want["t"] > 0).mean()) > 0.2

@@ -125,7 +125,7 @@ def test_knobs_and_modes_never_change_results(cb, ob, s260k):
         ri.set_tuning(k, val)
     # ray bucketing by direction octant inside the call (every kernel family reads its rays through the bucket lists)
     # (sort_rays 1) or sorted by octant + origin Morton code (sort_rays 2)
-    for variant, sort in ((18, 1), (34, 1), (42, 1), (18, 2), (34, 2)):
+    for variant, sort in ((18, 1), (34, 1), (42, 1), (18, 2), (34, 2), (18, 3), (42, 3)):
         ri.set_tuning(3, variant)
         ri.set_traversal_mode(2, sort)
         assert ri.IntersectRays(rays).tobytes() == want.tobytes(), ("reordered", variant, sort)

@@ -274,7 +274,7 @@ def main():
     ap.add_argument("--builder", type=int, default=0)
     ap.add_argument("--presort", type=int, default=0, help="soup10m experiment: host-side Morton sort of each ray chunk, bits per axis")
     ap.add_argument("--presort-mode", type=int, default=0, help="0: origin cell major; 1: direction octant major")
-    ap.add_argument("--sort", type=int, default=0, help="soup10m: cndl_set_traversal_mode sort_rays (0 off, 1 octant buckets, 2 octant + origin Morton order)")
+    ap.add_argument("--sort", type=int, default=4, help="soup10m: cndl_set_traversal_mode sort_rays (0 off, 1 octant buckets, 2 octant + origin Morton order with the rays moved, 3 through an index list, 4 automatic)")
     ap.add_argument("--knobs", default="", help="comma-separated tuning knobs in knob-id order (see dev_bench.py)")
     ap.add_argument("--bvh", default="build", choices=["build", "broadcast"], help="soup10m at N > 1: every rank builds, or rank 0 builds and broadcasts")
     ap.add_argument("--bucket", type=int, default=0, help="1: the generator emits each batch octant-major (CNDL_GEN_BUCKET_OCTANTS)")
