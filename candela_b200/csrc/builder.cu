@@ -1225,7 +1225,11 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
             const long long all = ub[0] + ub[1] + ub[2] + ub[3];
             const long long nb[4] = {2 * ub[0], 2 * (ub[0] + ub[1]), 2 * (ub[0] + ub[1] + ub[2]), 2 * all};
             for (int c = 0; c < 4; ++c) ub[c] = std::min(nb[c], cap[c]);
-            if (level - known >= kSyncEvery) {
+            // Bounds that have drifted far above anything plausible would launch grids of mostly empty CTAs (10 M triangles: the build
+            // doubled): once the bounded grids of the next level exceed a couple of thousand CTAs, read the real counts every level —
+            // a level that large hides the round trip anyway.
+            const long long bounded_ctas = ub[CLS_BIG] + ub[CLS_SMALL] + (ub[CLS_TINY] + kTinyWarps - 1) / kTinyWarps + (ub[CLS_SPLIT] ? (long long)(T / split_chunk) : 0);
+            if (level - known >= kSyncEvery || bounded_ctas > 2048) {
                 BK(cudaStreamSynchronize(st));
                 for (int c = 0; c < 4; ++c) ub[c] = h_lv[level].n_class[c];  // exact
                 known = level;

@@ -51,7 +51,7 @@ int check_ready(cndl_ctx* ctx) {
 // sort_rays as it applies to a batch of R rays: 4 = automatic
 int effective_sort(const cndl_ctx* ctx, size_t R) {
     if (ctx->sort_rays != 4) return ctx->sort_rays;
-    const size_t scene_bytes = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 64;
+    const size_t scene_bytes = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 48;
     return (scene_bytes > ((size_t)96 << 20) && R >= (1u << 20)) ? 3 : 0;
 }
 
@@ -103,7 +103,7 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, con
         if (variant == 0) {
             // automatic: a scene that fits the 126 MB L2 is served best by the plain kernel; once the node and triangle
             // records spill to DRAM, staging the top of the tree in shared memory wins (10 M triangles: +8.7 %)
-            const size_t working_set = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 64;
+            const size_t working_set = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 48;
             // ... unless the batch has just been ordered: neighbouring rays then share nodes, L2 hits rise and the plain kernel's
             // higher residency wins (10 M triangles: 4.71 vs 5.03 ms)
             variant = (!stack && working_set > ((size_t)96 << 20) && !(sort_mode >= 2 && order_region && R >= 65536 && !d_R)) ? 34 : 18;
@@ -395,7 +395,7 @@ int cndl_commit(cndl_ctx* ctx, int clear_host) try {
     if (ctx->n_tris == 0) return ctx->fail(CNDL_ERR_INVALID, "nothing to commit");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->main_stream;
-    CK(ctx->tri48.ensure_scratch(ctx->n_tris * 64));  // 64-byte triangle records (traverse.cuh)
+    CK(ctx->tri48.ensure_scratch(ctx->n_tris * 48));
     ctx->committed = false;
     ctx->hot_ready = false;
     ctx->nodes_valid = false;

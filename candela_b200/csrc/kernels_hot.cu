@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
                             // tail of IntersectScene (SL:300-318)
                             float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
                             int mesh = -1;
-                            if (L.best_tri >= 0) mesh = tri_mesh(s.tri48, L.best_tri);
+                            if (L.best_tri >= 0) mesh = __ldg(&s.tris[L.best_tri]).w;
                             if (L.closest > 0.0f && L.best_tri > 0) {
                                 RayState r = L.r;
                                 if (L.best_ent != last_ent) {
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(128, MINB) trace_pair_stackless_kernel(SceneVi
                             // tail of IntersectScene (SL:300-318); TMax == ClosestT once something was accepted
                             float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
                             int mesh = -1;
-                            if (T.best_tri >= 0) mesh = tri_mesh(s.tri48, T.best_tri);
+                            if (T.best_tri >= 0) mesh = __ldg(&s.tris[T.best_tri]).w;
                             if (T.best_tri > 0) {
                                 V3 ro = T.o, rd = T.d;
                                 if (T.best_ent != last_ent) {

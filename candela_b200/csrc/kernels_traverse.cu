@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128, 4) trace_persistent_stackless_kernel(Scen
                             any_t[L.rid] = -1.0f;
                         } else {
                             cndl_hit h{-1.0f, -1.0f, -1.0f, -1.0f, -1, L.best_tri, L.best_ent, last_iters};
-                            if (L.best_tri >= 0) h.mesh = tri_mesh(s.tri48, L.best_tri);
+                            if (L.best_tri >= 0) h.mesh = __ldg(&s.tris[L.best_tri]).w;
                             if (L.closest > 0.0f && L.best_tri > 0) {
                                 V3 o, d;
                                 float unused;
@@ -192,7 +192,7 @@ __global__ void make_tri48_kernel(const int4* __restrict__ tris, const float4* _
     const int4 t = tris[i];
     if ((unsigned)t.x >= V || (unsigned)t.y >= V || (unsigned)t.z >= V) {  // a vertex index outside the vertex buffer (corrupt cache file / prebuilt buffer)
         atomicOr(invalid, 4);
-        tri48[4 * i + 0] = tri48[4 * i + 1] = tri48[4 * i + 2] = tri48[4 * i + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        tri48[3 * i + 0] = tri48[3 * i + 1] = tri48[3 * i + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         return;
     }
     const float4 a = verts[2 * (size_t)t.x], b = verts[2 * (size_t)t.y], c = verts[2 * (size_t)t.z];
@@ -200,10 +200,9 @@ __global__ void make_tri48_kernel(const int4* __restrict__ tris, const float4* _
     const V3 e1 = vsub(V3{b.x, b.y, b.z}, v0);  // v1v0, SL:81
     const V3 e2 = vsub(V3{c.x, c.y, c.z}, v0);  // v2v0, SL:82
     const V3 n = vcross(e1, e2);                 // SL:85
-    tri48[4 * i + 0] = make_float4(v0.x, v0.y, v0.z, e1.x);
-    tri48[4 * i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
-    tri48[4 * i + 2] = make_float4(e2.z, n.x, n.y, n.z);
-    tri48[4 * i + 3] = make_float4(__int_as_float(t.w), 0.0f, 0.0f, 0.0f);  // GlobalMeshNumber
+    tri48[3 * i + 0] = make_float4(v0.x, v0.y, v0.z, e1.x);
+    tri48[3 * i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    tri48[3 * i + 2] = make_float4(e2.z, n.x, n.y, n.z);
 }
 
 __global__ void rebase_triangles_kernel(int4* __restrict__ tris, size_t T, int offset) {

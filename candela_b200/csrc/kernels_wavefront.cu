@@ -44,7 +44,7 @@ __device__ __forceinline__ void retire_closest(const SceneView& s, const cndl_ra
                                                const RayState& cur, int cur_ent, float closest, int best_tri, int best_ent, int iters) {
     float t = -1.0f, u = -1.0f, v = -1.0f, w = -1.0f;
     int mesh = -1;
-    if (best_tri >= 0) mesh = tri_mesh(s.tri48, best_tri);
+    if (best_tri >= 0) mesh = __ldg(&s.tris[best_tri]).w;
     if (best_tri > 0) {  // ClosestT > 0 && TriangleIdx > 0: global triangle 0 reports as a miss
         RayState r = cur;
         if (best_ent != cur_ent) {

@@ -75,21 +75,17 @@ __device__ __forceinline__ void stg256(float4* p, float4 a, float4 b) {
                  : "memory");
 }
 
-// The per-triangle record is 64 bytes, 64-byte aligned: {v0, e1.x | e1.yz, e2.xy | e2.z, n | mesh id, 0, 0, 0} — the 48 bytes of
-// ray-independent sub-expressions of RayTriangle plus the triangle's GlobalMeshNumber — so a triangle test costs two 256-bit loads
-// (two L1 wavefronts; three 128-bit loads of a 48-byte record cost three) and retiring a ray needs no look-up in the triangle buffer.
-constexpr int kTriStride = 4;  // float4s per record
+// The per-triangle record: 48 bytes = three float4s {v0, e1.x | e1.yz, e2.xy | e2.z, n}.  (A 64-byte record read with two 256-bit
+// loads — two L1 wavefronts instead of three, with the mesh id in the spare lane — was measured: 0.723 vs 0.717 ms on the diffuse
+// batch, the larger footprint costs more L1 hits than the saved wavefronts give back.)
+constexpr int kTriStride = 3;  // float4s per record
 __device__ __forceinline__ void load_tri48(const float4* __restrict__ tri48, int idx, V3& v0, V3& e1, V3& e2, V3& n) {
-    float4 a, b, c, d;
-    ldg256(tri48 + kTriStride * (size_t)idx, a, b);
-    ldg256(tri48 + kTriStride * (size_t)idx + 2, c, d);
+    const float4 a = __ldg(tri48 + kTriStride * (size_t)idx), b = __ldg(tri48 + kTriStride * (size_t)idx + 1), c = __ldg(tri48 + kTriStride * (size_t)idx + 2);
     v0 = {a.x, a.y, a.z};
     e1 = {a.w, b.x, b.y};
     e2 = {b.z, b.w, c.x};
     n = {c.y, c.z, c.w};
 }
-
-__device__ __forceinline__ int tri_mesh(const float4* __restrict__ tri48, int idx) { return __float_as_int(__ldg(&tri48[kTriStride * (size_t)idx + 3].x)); }
 
 // RayTriangle, SL:79-97 / ST:87-105. Returns t, or -1 when outside.
 __device__ __forceinline__ float ray_triangle(const float4* __restrict__ tri48, int idx, V3 ro, V3 rd) {
@@ -284,7 +280,7 @@ __device__ __forceinline__ cndl_hit scene_closest(const SceneView& s, V3 ro, V3 
             h.entity = i;
         }
     }
-    if (h.tri >= 0) h.mesh = tri_mesh(s.tri48, h.tri);
+    if (h.tri >= 0) h.mesh = __ldg(&s.tris[h.tri]).w;
     if (closest > 0.0f && h.tri > 0) {  // SL:300 — global triangle 0 reports as a miss
         const RayState r = to_object_space(s.ents + h.entity, ro, rd);
         const V3 p = {fadd(r.o.x, fmul(r.d.x, closest)), fadd(r.o.y, fmul(r.d.y, closest)), fadd(r.o.z, fmul(r.d.z, closest))};

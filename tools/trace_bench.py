@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--spp", type=int, default=1)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--camera", action="store_true", help="time the camera pass (cndl_intersect_primary_device) instead of the diffuse batch")
     args = ap.parse_args()
     from oracle import binding as ob
     v, i, m = scenes.make_s260k()
@@ -53,6 +54,24 @@ def main():
         d_prim = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
         d_ph = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
         ri.intersect_primary_device(iv, ip, W, H, d_ph.data_ptr(), d_prim.data_ptr(), stream)
+        if args.camera:
+            knob_sets = [None] + [[int(x) for x in k.split(",")] for k in args.knobs.split(";") if k]
+            for ks in knob_sets:
+                if ks:
+                    for kid, val in enumerate(ks):
+                        ri.set_tuning(kid, val)
+                ts = []
+                for _ in range(args.reps + 3):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    ri.intersect_primary_device(iv, ip, W, H, d_ph.data_ptr(), d_prim.data_ptr(), stream)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                print(json.dumps(dict(fmt=fmt_name, camera=True, knobs=ks, ms=round(float(np.median(ts[3:])), 4))), flush=True)
+            ri.close()
+            continue
         want = None
         for octant in [int(x) for x in args.octant.split(",")]:
             d_r = torch.empty((W * H * args.spp, 8), dtype=torch.float32, device="cuda")
