@@ -27,7 +27,7 @@ def to_bytes(value: str, unit: str) -> float:
     return float(value.replace(",", "")) * scale.get(unit, 1.0)
 
 
-def parse(raw_csv: Path, rays: int, out_dir: Path, tag: str, source: str):
+def parse(raw_csv: Path, rays: int, out_dir: Path, tag: str, source: str, write_traffic: bool = True):
     rows = list(csv.reader(open(raw_csv)))
     hdr, units, vals = rows[0], rows[1], rows[-1]
     col = {h: i for i, h in enumerate(hdr)}
@@ -42,7 +42,8 @@ def parse(raw_csv: Path, rays: int, out_dir: Path, tag: str, source: str):
                "l1tex_throughput_pct": float(got["l1tex__throughput.avg.pct_of_peak_sustained_active"][0]),
                "lanes_per_instruction": float(got["smsp__thread_inst_executed_per_inst_executed.ratio"][0]),
                "kernel": kernel, "rays": rays, "source": source}
-    (out_dir / "traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
+    if write_traffic:
+        (out_dir / "traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
     lines = [f"# {source}", f"# kernel: {kernel}", f"# rays per launch: {rays}"]
     lines += [f"{k:90s} {v[0]:>16s} {v[1]}" for k, v in got.items()]
     (out_dir / f"{tag}_ncu_full.txt").write_text("\n".join(lines) + "\n")
@@ -56,14 +57,18 @@ def main():
     ap.add_argument("--rays", type=int, default=0)
     ap.add_argument("--out", default=str(ROOT / "profiles"))
     ap.add_argument("--tag", default="r2_trace_ww")
+    ap.add_argument("--kernel", default="trace_ww_stackless", help="--capture: kernel name regex")
+    ap.add_argument("--skip", type=int, default=6, help="--capture: launches of that kernel to skip first")
+    ap.add_argument("--cmd", default="", help="--capture: command to profile instead of the bench (quoted, run through the current interpreter)")
+    ap.add_argument("--source", default="", help="--parse: description written into the summary")
     args = ap.parse_args()
     go = ROOT / "gpurun_out"
     if args.capture:
         go.mkdir(exist_ok=True)
         rep = go / f"{args.tag}.ncu-rep"
-        cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "--kernel-name", "regex:trace_ww_stackless", "--launch-skip", "6",
-               "--launch-count", "1", "-f", "-o", str(rep.with_suffix("")), sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "3", "--passes", "2",
-               "--no-strong", "--build-reps", "0"]
+        target = args.cmd.split() if args.cmd else [str(ROOT / "bench.py"), "--steps", "1", "--warmup", "3", "--passes", "2", "--no-strong", "--build-reps", "0"]
+        cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "--kernel-name", f"regex:{args.kernel}", "--launch-skip", str(args.skip),
+               "--launch-count", "1", "-f", "-o", str(rep.with_suffix("")), sys.executable] + target
         subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
         raw = go / f"{args.tag}_raw.csv"
         with open(raw, "w") as f:
@@ -71,7 +76,8 @@ def main():
         print("captured", rep, raw)
         return
     parse(Path(args.parse), args.rays, Path(args.out), args.tag,
-          "ncu --set full --clock-control none, one launch of the bench.py diffuse batch (tools/ncu_traffic.py --capture), B200")
+          args.source or "ncu --set full --clock-control none, one launch of the bench.py diffuse batch (tools/ncu_traffic.py --capture), B200",
+          write_traffic=not args.source)
 
 
 if __name__ == "__main__":
