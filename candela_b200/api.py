@@ -29,6 +29,11 @@ HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("w", "<f4"), ("mes
 BOX_DT = np.dtype([("min", "<f4", 3), ("pad0", "<f4"), ("max", "<f4", 3), ("pad1", "<f4")])
 COLLISION_DT = np.dtype([("collided", "<i4"), ("mesh", "<i4"), ("tri", "<i4"), ("entity", "<i4")])
 ATTR_DT = np.dtype([("normal", "<f4", 3), ("uv", "<f4", 2), ("emissivity", "<f4"), ("alpha", "<f4"), ("mesh", "<i4")])
+TEXREF_DT = np.dtype([("model_color", "<f4", 4), ("albedo", "<i4"), ("normal", "<i4"), ("pad", "<i4", 2)])     # cndl_texture_reference
+MESH_MATERIAL_DT = np.dtype([("albedo_handle", "<u8"), ("normal_handle", "<u8"), ("albedo_valid", "<i4"), ("normal_valid", "<i4"),
+                             ("model_color", "<f4", 3), ("pad", "<f4")])                                           # cndl_mesh_material
+MATERIAL_DT = np.dtype([("normal", "<f4", 3), ("uv", "<f4", 2), ("emissivity", "<f4"), ("alpha", "<f4"), ("mesh", "<i4"), ("albedo", "<f4", 3),
+                        ("albedo_ref", "<i4")])                                                                    # cndl_hit_material
 
 EXPORTS = [
     "cndl_abi_version", "cndl_create", "cndl_destroy", "cndl_last_error", "cndl_add_object", "cndl_add_prebuilt_object",
@@ -46,6 +51,8 @@ EXPORTS = [
     "cndl_multi_commit", "cndl_multi_push_entity", "cndl_multi_buffer_entities", "cndl_multi_frame_submit", "cndl_multi_frame_wait",
     "cndl_multi_trace_frame", "cndl_multi_frame_rays_traced", "cndl_multi_last_replicate_ms", "cndl_clone_scene", "cndl_add_prebuilt_object_device",
     "cndl_object_device_view", "cndl_multi_set_transport", "cndl_object_count", "cndl_object_ids",
+    "cndl_generate_texture_references", "cndl_set_texture_references", "cndl_texture_reference_count", "cndl_get_data_material", "cndl_get_data_material_device",
+    "cndl_model_mesh_albedo_path", "cndl_model_mesh_normal_path", "cndl_model_mesh_color",
 ]
 
 
@@ -142,6 +149,12 @@ def load_library() -> C.CDLL:
     L.cndl_generate_bounce_rays_device.argtypes = [vp, vp, vp, sz, C.c_int, C.c_float, C.c_float, C.c_uint32, vp, vp, C.POINTER(sz), vp]
     L.cndl_get_data.argtypes = [vp, vp, sz, vp]
     L.cndl_get_data_device.argtypes = [vp, vp, sz, vp, vp]
+    L.cndl_get_data_material.argtypes = [vp, vp, sz, vp]
+    L.cndl_get_data_material_device.argtypes = [vp, vp, sz, vp, vp]
+    L.cndl_set_texture_references.argtypes = [vp, vp, sz]
+    L.cndl_texture_reference_count.argtypes = [vp]
+    L.cndl_texture_reference_count.restype = sz
+    L.cndl_generate_texture_references.argtypes = [vp, sz, vp, vp, sz, C.POINTER(sz)]
     L.cndl_generate_rays_device.argtypes = [vp, C.POINTER(RaygenParams), vp, vp, sz, vp, vp, C.POINTER(sz), vp]
     L.cndl_generate_probe_rays_device.argtypes = [vp, vp, vp, vp, C.c_uint32, vp, vp]
     fp = C.POINTER(FrameParams)
@@ -197,6 +210,10 @@ def load_library() -> C.CDLL:
         getattr(L, f).restype = vp
     L.cndl_model_mesh_name.argtypes = [vp, sz]
     L.cndl_model_mesh_name.restype = C.c_char_p
+    for f in ("cndl_model_mesh_albedo_path", "cndl_model_mesh_normal_path"):
+        getattr(L, f).argtypes = [vp, sz]
+        getattr(L, f).restype = C.c_char_p
+    L.cndl_model_mesh_color.argtypes = [vp, sz, vp]
     L.cndl_add_model.argtypes = [vp, C.c_uint32, vp, C.POINTER(BuildOpts)]
     L.cndl_pack_half2x16.argtypes = [C.c_float, C.c_float]
     L.cndl_pack_half2x16.restype = C.c_uint32
@@ -266,9 +283,10 @@ def BuildBVH(node_format: int, verts, indices, mesh_ids=None, t_offset: int = 0,
     return nodes[: n.value].copy(), tris, ms.value
 
 
-def load_model(path, first_mesh_number: int = 0):
+def load_model(path, first_mesh_number: int = 0, materials: bool = False):
     """cndl_model_load (.obj / .gltf / .glb) -> (vertices[VERTEX_DT], indices[u32], mesh_ids[i32 per triangle], mesh names): what
-    ModelFileLoader.cpp:101-185 hands to the intersector, without Assimp.  Host only."""
+    ModelFileLoader.cpp:101-185 hands to the intersector, without Assimp.  Host only.  materials=True appends the per-mesh
+    _MeshMaterialData list (ModelFileLoader.h:21-25) as dicts {albedo, normal, color}."""
     L = load_library()
     h = C.c_void_p()
     err = C.create_string_buffer(512)
@@ -281,9 +299,35 @@ def load_model(path, first_mesh_number: int = 0):
         idx = np.frombuffer((C.c_char * (ni * 4)).from_address(L.cndl_model_indices(h)), dtype=np.uint32).copy()
         mids = np.frombuffer((C.c_char * (ni // 3 * 4)).from_address(L.cndl_model_mesh_ids(h)), dtype=np.int32).copy()
         names = [L.cndl_model_mesh_name(h, k).decode() for k in range(nm)]
+        mats = []
+        for k in range(nm):
+            rgb = (C.c_float * 3)()
+            L.cndl_model_mesh_color(h, k, rgb)
+            mats.append({"albedo": L.cndl_model_mesh_albedo_path(h, k).decode(), "normal": L.cndl_model_mesh_normal_path(h, k).decode(),
+                         "color": (rgb[0], rgb[1], rgb[2])})
     finally:
         L.cndl_model_free(h)
-    return verts, idx, mids, names
+    return (verts, idx, mids, names, mats) if materials else (verts, idx, mids, names)
+
+
+def generate_texture_references(materials):
+    """cndl_generate_texture_references = RayIntersector::GenerateMeshTextureReferences (Intersector.h:367-402) as host arithmetic.
+    materials: MESH_MATERIAL_DT records (or (albedo_handle, albedo_valid, normal_handle, normal_valid, (r, g, b)) tuples).
+    Returns (table[TEXREF_DT], handles[u64]) with handles[i] = the handle to bind to Textures[i]."""
+    if not (isinstance(materials, np.ndarray) and materials.dtype == MESH_MATERIAL_DT):
+        rec = np.zeros(len(materials), dtype=MESH_MATERIAL_DT)
+        for i, (a, va, b, vb, color) in enumerate(materials):
+            rec[i] = (a, b, int(bool(va)), int(bool(vb)), tuple(color), 0.0)
+        materials = rec
+    materials = np.ascontiguousarray(materials)
+    L = load_library()
+    out = np.zeros(len(materials), dtype=TEXREF_DT)
+    handles = np.zeros(2 * len(materials), dtype=np.uint64)
+    n = C.c_size_t(0)
+    rc = L.cndl_generate_texture_references(_p(materials), len(materials), _p(out), _p(handles), len(handles), C.byref(n))
+    if rc != 0:
+        raise CandelaError(rc, "cndl_generate_texture_references")
+    return out, handles[: n.value].copy()
 
 
 load_obj = load_model
@@ -481,6 +525,31 @@ class RayIntersector:
         out = np.zeros(len(hits), dtype=ATTR_DT)
         self._check(self._lib.cndl_get_data(self._h, _p(hits), len(hits), _p(out)))
         return out
+
+    def SetTextureReferences(self, refs):
+        """Uploads the BVHTextureReferences table (m_BVHTextureReferencesSSBO, Intersector.h:404-409)."""
+        refs = np.ascontiguousarray(refs, dtype=TEXREF_DT)
+        self._check(self._lib.cndl_set_texture_references(self._h, _p(refs), len(refs)))
+
+    def GenerateMeshTextureReferences(self, materials):
+        """Intersector.h:367-410: builds the table from the per-mesh materials (see generate_texture_references) and uploads it.
+        Returns the handles to bind to Textures[0..] (m_TextureHandleReferenceMap)."""
+        refs, handles = generate_texture_references(materials)
+        self.SetTextureReferences(refs)
+        return handles
+
+    def texture_reference_count(self) -> int:
+        return int(self._lib.cndl_texture_reference_count(self._h))
+
+    def GetDataMaterial(self, hits) -> np.ndarray:
+        """GetData with the Albedo decision (…Stackless.glsl:393-404): MATERIAL_DT records; albedo_ref > -1 = sample Textures[albedo_ref] at uv."""
+        hits = np.ascontiguousarray(hits, dtype=HIT_DT)
+        out = np.zeros(len(hits), dtype=MATERIAL_DT)
+        self._check(self._lib.cndl_get_data_material(self._h, _p(hits), len(hits), _p(out)))
+        return out
+
+    def get_data_material_device(self, d_hits: int, n: int, d_out: int, stream: int = 0):
+        self._check(self._lib.cndl_get_data_material_device(self._h, d_hits, n, d_out, stream or None))
 
     def CollideBoxes(self, mins, maxs) -> np.ndarray:
         """Physics::CollideBox (Physics.cpp:203-228) for a batch of boxes -> records {collided, mesh, tri, entity}."""

@@ -741,6 +741,63 @@ int cndl_get_data(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_attr* 
     return CNDL_OK;
 } CNDL_CATCH
 
+int cndl_set_texture_references(cndl_ctx* ctx, const cndl_texture_reference* refs, size_t n) try {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (n && !refs) return ctx->fail(CNDL_ERR_INVALID, "null texture-reference table");
+    if (n > 0x7FFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^31-16 texture references");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->main_stream));  // a GetData launch may still read the old table
+    ctx->n_tex_refs = 0;
+    if (n) {
+        CK(ctx->tex_refs.ensure_scratch(n * sizeof(cndl_texture_reference)));
+        CK(cudaMemcpyAsync(ctx->tex_refs.p, refs, n * sizeof(cndl_texture_reference), cudaMemcpyHostToDevice, ctx->main_stream));
+        CK(cudaStreamSynchronize(ctx->main_stream));
+        ctx->n_tex_refs = n;
+    }
+    return CNDL_OK;
+} CNDL_CATCH
+
+size_t cndl_texture_reference_count(const cndl_ctx* ctx) { return ctx ? ctx->n_tex_refs : 0; }
+
+int cndl_get_data_material_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_material* d_out, void* stream) try {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (R && (!d_hits || !d_out)) return ctx->fail(CNDL_ERR_INVALID, "null hit or material buffer");
+    if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 records in one call");
+    int rc = check_ready(ctx);
+    if (rc != CNDL_OK) return rc;
+    if (ctx->n_tex_refs == 0) return ctx->fail(CNDL_ERR_INVALID, "no texture-reference table: call cndl_set_texture_references first (GenerateMeshTextureReferences, Intersector.h:367)");
+    CK(cudaSetDevice(ctx->device));
+    launch_get_data_material(scene_view(ctx), static_cast<const float4*>(ctx->verts.p), static_cast<const cndl_texture_reference*>(ctx->tex_refs.p), ctx->n_tex_refs,
+                             d_hits, R, d_out, static_cast<unsigned*>(ctx->d_counter.p) + 34, static_cast<cudaStream_t>(stream), ctx->launches);
+    CK(cudaGetLastError());
+    return CNDL_OK;
+} CNDL_CATCH
+
+int cndl_get_data_material(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_material* out) try {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (R && (!hits || !out)) return ctx->fail(CNDL_ERR_INVALID, "null hit or material buffer");
+    if (R == 0) return check_ready(ctx);
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_hits.ensure_scratch(R * sizeof(cndl_hit)));
+    CK(ctx->d_rays.ensure_scratch(R * sizeof(cndl_hit_material)));
+    cudaStream_t st = ctx->main_stream;
+    unsigned* flag = static_cast<unsigned*>(ctx->d_counter.p) + 34;
+    CK(cudaMemsetAsync(flag, 0, sizeof(unsigned), st));
+    CK(cudaMemcpyAsync(ctx->d_hits.p, hits, R * sizeof(cndl_hit), cudaMemcpyHostToDevice, st));
+    int rc = cndl_get_data_material_device(ctx, static_cast<const cndl_hit*>(ctx->d_hits.p), R, static_cast<cndl_hit_material*>(ctx->d_rays.p), st);
+    if (rc != CNDL_OK) return rc;
+    unsigned bad = 0;
+    CK(cudaMemcpyAsync(out, ctx->d_rays.p, R * sizeof(cndl_hit_material), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&bad, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (bad) {
+        char msg[160];
+        std::snprintf(msg, sizeof(msg), "%u hit records name a mesh outside the texture-reference table of %zu entries", bad, ctx->n_tex_refs);
+        return ctx->fail(CNDL_ERR_INVALID, msg);
+    }
+    return CNDL_OK;
+} CNDL_CATCH
+
 int cndl_collide_boxes_device(cndl_ctx* ctx, const cndl_box* d_boxes, size_t n, cndl_collision* d_out, void* stream) try {
     if (!ctx) return CNDL_ERR_INVALID;
     if (ctx->format != CNDL_STACKLESS) return ctx->fail(CNDL_ERR_INVALID, "the collide query walks FlattenedNode buffers (Physics.h:15): stackless contexts only");

@@ -81,6 +81,8 @@ struct cndl_ctx {
 
     std::vector<cndl_entity> staged;  // m_Entities
     size_t n_ents = 0;                 // m_EntityPushed
+    cndl::DeviceBuffer tex_refs;       // m_BVHTextureReferencesSSBO (Intersector.h:90)
+    size_t n_tex_refs = 0;
     bool ents_buffered = false;
 
     // query scratch

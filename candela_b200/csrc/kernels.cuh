@@ -84,6 +84,8 @@ void launch_probe_rays(const float box_origin[3], const float size[3], const int
 
 // GetData without textures: interpolated normal / uv + entity emissive / alpha per hit record (kernels_raygen.cu).
 void launch_get_data(const SceneView& s, const float4* verts, const cndl_hit* hits, size_t R, cndl_hit_attr* out, cudaStream_t stream, LaunchCounter& lc);
+void launch_get_data_material(const SceneView& s, const float4* verts, const cndl_texture_reference* refs, size_t n_refs, const cndl_hit* hits, size_t R,
+                              cndl_hit_material* out, unsigned* out_of_table, cudaStream_t stream, LaunchCounter& lc);
 
 // Hot-first derived node layout + shared-memory staged traversal (kernels_hot.cu).
 constexpr int kMaxHotNodes = 7168;  // 224 KB of shared memory

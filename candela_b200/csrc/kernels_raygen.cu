@@ -337,15 +337,19 @@ __global__ void probe_rays_kernel(float3 org, float3 size, int3 res, unsigned se
     q[1] = make_float4(d.x, d.y, d.z, 1000000.0f);
 }
 
-// GetData (…/Include/TraverseBVHStackless.glsl:370-408) without the texture fetch.
+// GetData (…/Include/TraverseBVHStackless.glsl:370-408) without the texture fetch.  MATERIAL adds the Albedo decision (:393-404)
+// from the per-mesh BVHTextureReferences table.
+template <bool MATERIAL>
 __global__ void get_data_kernel(const int4* __restrict__ tris, const float4* __restrict__ verts, const cndl_entity* __restrict__ ents,
-                                const cndl_hit* __restrict__ hits, unsigned R, cndl_hit_attr* __restrict__ out) {
+                                const cndl_texture_reference* __restrict__ refs, unsigned n_refs, const cndl_hit* __restrict__ hits, unsigned R,
+                                void* __restrict__ out_, unsigned* __restrict__ out_of_table) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     const float4 h0 = __ldg(reinterpret_cast<const float4*>(hits + i));
     const int4 h1 = __ldg(reinterpret_cast<const int4*>(hits + i) + 1);
     float4 o0 = make_float4(-1.0f, -1.0f, -1.0f, 0.0f);  // Normal = vec3(-1) on a miss (SL:377-382)
     float4 o1 = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(h1.x));
+    float4 o2 = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));  // Albedo = vec3(0), no texture
     if (!(h0.x < 0.0f || h1.x < 0)) {
         const int4 t = __ldg(tris + h1.y);
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(verts + 2 * (size_t)t.x + 1));
@@ -359,18 +363,37 @@ __global__ void get_data_kernel(const int4* __restrict__ tris, const float4* __r
         const float inv_len = fdiv(1.0f, __fsqrt_rn(fadd(fadd(fmul(nx, nx), fmul(ny, ny)), fmul(nz, nz))));
         o0 = make_float4(fmul(nx, inv_len), fmul(ny, inv_len), fmul(nz, inv_len), u);
         o1 = make_float4(v, __int_as_float(__ldg(&ents[h1.z].data[0])), __int_as_float(__ldg(&ents[h1.z].data[1])), __int_as_float(h1.x));
+        if (MATERIAL) {
+            if ((unsigned)h1.x >= n_refs) {  // the shader would read past its SSBO: flagged, never guessed
+                o2.w = __int_as_float(-2);
+                atomicAdd(out_of_table, 1u);
+            } else {
+                const float4 color = __ldg(reinterpret_cast<const float4*>(refs + h1.x));
+                const int ref = __ldg(&refs[h1.x].albedo);
+                // `Ref > -1 && Mesh > -1 && TUVW.x > 0.` (SL:397): t == 0 takes the ModelColor branch
+                if (ref > -1 && h0.x > 0.0f) o2.w = __int_as_float(ref);
+                else o2 = make_float4(color.x, color.y, color.z, __int_as_float(-1));
+            }
+        }
     }
-    float4* p = reinterpret_cast<float4*>(out + i);
+    float4* p = reinterpret_cast<float4*>(out_) + (size_t)i * (MATERIAL ? 3 : 2);
     p[0] = o0;
     p[1] = o1;
+    if (MATERIAL) p[2] = o2;
 }
-
 
 }  // namespace
 
 void launch_get_data(const SceneView& s, const float4* verts, const cndl_hit* hits, size_t R, cndl_hit_attr* out, cudaStream_t stream, LaunchCounter& lc) {
     if (R == 0) return;
-    get_data_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(s.tris, verts, s.ents, hits, (unsigned)R, out);
+    get_data_kernel<false><<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(s.tris, verts, s.ents, nullptr, 0u, hits, (unsigned)R, out, nullptr);
+    lc.n++;
+}
+
+void launch_get_data_material(const SceneView& s, const float4* verts, const cndl_texture_reference* refs, size_t n_refs, const cndl_hit* hits, size_t R,
+                              cndl_hit_material* out, unsigned* out_of_table, cudaStream_t stream, LaunchCounter& lc) {
+    if (R == 0) return;
+    get_data_kernel<true><<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(s.tris, verts, s.ents, refs, (unsigned)n_refs, hits, (unsigned)R, out, out_of_table);
     lc.n++;
 }
 

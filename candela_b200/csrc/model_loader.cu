@@ -7,16 +7,23 @@
 // GenUVCoords | FlipUVs | GenNormals (ModelFileLoader.cpp:243-252).  This reader does the same where the
 // intersector can see it: one mesh per `usemtl` / `o` / `g` run (Assimp: one mesh per material), polygons
 // fan-triangulated, v flipped (uv.y = 1 - uv.y), a flat face normal generated for corners that name no `vn`, and
-// vertices joined per mesh when their position index, UV index and normal agree.  Tangents are left zero
-// (CalcTangentSpace feeds the raster pass only; GetData reads normal and UV).  The ORDER of the joined
-// vertices is not Assimp's — which cannot matter: the builder and the traversal only ever see the arrays
-// this loader returns.
+// vertices joined per mesh when their position index, UV index, normal and tangent agree.  Tangents follow Assimp's
+// CalcTangentsProcess (the step aiProcess_CalcTangentSpace names; Assimp itself is not in the reference tree — only its headers
+// and a Windows import library — so the step is restated from its published algorithm and NOT pinned against a run of it):
+// per face the UV-gradient tangent / bitangent, per corner Gram-Schmidt against the corner's normal, then one average per
+// group of corners that share a position and a normal (dot >= 0.9999) and whose tangents and bitangents lie within 45 degrees.
+// Nothing on the ray path reads them (GetData takes normal and UV; the tangent feeds the raster pass only).  Materials are
+// recorded per mesh the way LoadMaterialTextures does (ModelFileLoader.cpp:31-99): albedo / normal texture path and ModelColor.
+// The ORDER of the joined vertices is not Assimp's — which cannot matter: the builder and the traversal only ever see the
+// arrays this loader returns.
+#include <array>
 #include <cerrno>
 #include <cstdint>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <new>
 #include <string>
@@ -53,6 +60,85 @@ std::uint16_t to_float16(float f) {
     return (std::uint16_t)(s | (e << 10) | (m >> 13));
 }
 
+struct V3 {
+    float x = 0.0f, y = 0.0f, z = 0.0f;
+    V3 operator-(const V3& o) const { return {x - o.x, y - o.y, z - o.z}; }
+    V3 operator+(const V3& o) const { return {x + o.x, y + o.y, z + o.z}; }
+    V3 operator*(float f) const { return {x * f, y * f, z * f}; }
+    float dot(const V3& o) const { return x * o.x + y * o.y + z * o.z; }
+    V3 cross(const V3& o) const { return {y * o.z - z * o.y, z * o.x - x * o.z, x * o.y - y * o.x}; }
+    void normalize_safe() { const float l = std::sqrt(dot(*this)); if (l > 0.0f) { x /= l; y /= l; z /= l; } }
+    void normalize() { const float l = std::sqrt(dot(*this)); x /= l; y /= l; z /= l; }
+    bool special() const { return !std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z); }
+};
+
+// Assimp's CalcTangentsProcess::ProcessMesh restated (see the file header: unpinned).  `faces` holds vertex index triples; a vertex
+// shared by several faces keeps the tangent of the last face that touches it before the smoothing pass, as in the original.
+// Positions are matched bit for bit (the original: within 1e-4 of the mesh's bounding-box diagonal).
+void calc_tangents(const std::vector<V3>& pos, const std::vector<V3>& nrm, const std::vector<std::array<float, 2>>& uv,
+                   const std::vector<std::uint32_t>& faces, std::vector<V3>& tang) {
+    const size_t n = pos.size();
+    std::vector<V3> bitang(n);
+    tang.assign(n, V3{});
+    for (size_t f = 0; f + 2 < faces.size(); f += 3) {
+        const std::uint32_t p0 = faces[f], p1 = faces[f + 1], p2 = faces[f + 2];
+        const V3 v = pos[p1] - pos[p0], w = pos[p2] - pos[p0];
+        float sx = uv[p1][0] - uv[p0][0], sy = uv[p1][1] - uv[p0][1];
+        float tx = uv[p2][0] - uv[p0][0], ty = uv[p2][1] - uv[p0][1];
+        const float dir = (tx * sy - ty * sx) < 0.0f ? -1.0f : 1.0f;
+        if (sx * ty == sy * tx) { sx = 0.0f; sy = 1.0f; tx = 1.0f; ty = 0.0f; }  // degenerate UVs: a default mapping
+        const V3 tangent{(w.x * sy - v.x * ty) * dir, (w.y * sy - v.y * ty) * dir, (w.z * sy - v.z * ty) * dir};
+        const V3 bitangent{(w.x * sx - v.x * tx) * dir, (w.y * sx - v.y * tx) * dir, (w.z * sx - v.z * tx) * dir};
+        for (const std::uint32_t p : {p0, p1, p2}) {
+            V3 lt = tangent - nrm[p] * tangent.dot(nrm[p]);
+            V3 lb = bitangent - nrm[p] * bitangent.dot(nrm[p]) - lt * bitangent.dot(lt);
+            lt.normalize_safe();
+            lb.normalize_safe();
+            const bool bad_t = lt.special(), bad_b = lb.special();
+            if (bad_t != bad_b) {
+                if (bad_t) { lt = nrm[p].cross(lb); lt.normalize_safe(); }
+                else { lb = lt.cross(nrm[p]); lb.normalize_safe(); }
+            }
+            tang[p] = lt;
+            bitang[p] = lb;
+        }
+    }
+    // smoothing: greedy groups seeded in vertex order
+    struct PosKey { std::uint32_t b[3]; bool operator<(const PosKey& o) const { return std::memcmp(b, o.b, sizeof(b)) < 0; } };
+    std::map<PosKey, std::vector<std::uint32_t>> at;
+    auto key_of = [&](const V3& p) {
+        const float c[3] = {p.x + 0.0f, p.y + 0.0f, p.z + 0.0f};  // -0 -> +0
+        PosKey k;
+        std::memcpy(k.b, c, sizeof(c));
+        return k;
+    };
+    for (size_t a = 0; a < n; ++a) at[key_of(pos[a])].push_back((std::uint32_t)a);
+    const float limit = std::cos(45.0f * 3.14159265358979323846f / 180.0f), same_normal = 0.9999f;
+    std::vector<char> done(n, 0);
+    std::vector<std::uint32_t> close;
+    for (size_t a = 0; a < n; ++a) {
+        if (done[a]) continue;
+        close.clear();
+        for (const std::uint32_t b : at[key_of(pos[a])]) {
+            if (done[b]) continue;
+            if (b != a && (nrm[b].dot(nrm[a]) < same_normal || tang[b].dot(tang[a]) < limit || bitang[b].dot(bitang[a]) < limit)) continue;
+            close.push_back(b);
+            done[b] = 1;
+        }
+        if (close.size() < 2) continue;
+        V3 st, sb;
+        for (const std::uint32_t b : close) { st = st + tang[b]; sb = sb + bitang[b]; }
+        st.normalize();
+        sb.normalize();
+        for (const std::uint32_t b : close) { tang[b] = st; bitang[b] = sb; }
+    }
+}
+
+std::string parent_dir(const std::string& path) {  // std::filesystem::path::parent_path as LoadMaterialTextures uses it (:33-35)
+    const size_t slash = path.find_last_of("/\\");
+    return slash == std::string::npos ? std::string() : path.substr(0, slash);
+}
+
 }  // namespace
 
 struct cndl_model {
@@ -61,6 +147,8 @@ struct cndl_model {
     std::vector<std::int32_t> mesh_ids;   // one per triangle
     std::vector<std::uint32_t> mesh_first_vertex, mesh_first_index;
     std::vector<std::string> mesh_names;
+    std::vector<std::string> mesh_albedo, mesh_normal;     // _MeshMaterialData::Albedo / Normal (ModelFileLoader.h:21-25)
+    std::vector<std::array<float, 3>> mesh_color;          // _MeshMaterialData::ModelColor
 };
 
 extern "C" {
@@ -80,47 +168,115 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
     std::unique_ptr<cndl_model> owner(new cndl_model);
     cndl_model* M = owner.get();
 
+    const std::string dir = parent_dir(path);
     std::vector<float> P, N, T;  // v (3), vn (3), vt (2)
-    // n >= 0: index into the file's `vn` list; n == -1: generated face normal, whose value is in g[]
-    struct Key {
+    // One triangle corner as the file names it.  n >= 0: index into the file's `vn` list; n == -1: generated face normal, whose
+    // value is in g[].  Assimp's OBJ importer emits one vertex per corner like this; tangents are computed on them, then they are joined.
+    struct Corner {
         long v, t, n;
         float g[3];
-        bool operator==(const Key& o) const { return v == o.v && t == o.t && n == o.n && std::memcmp(g, o.g, sizeof(g)) == 0; }
+    };
+    struct Key {
+        long v, t, n;
+        std::uint32_t g[3], tan[3];
+        bool operator==(const Key& o) const { return v == o.v && t == o.t && n == o.n && std::memcmp(g, o.g, sizeof(g)) == 0 && std::memcmp(tan, o.tan, sizeof(tan)) == 0; }
     };
     struct KeyHash {
         size_t operator()(const Key& k) const {
-            std::uint32_t b[3];
-            std::memcpy(b, k.g, sizeof(b));
-            return (size_t)k.v * 73856093u ^ (size_t)(k.t + 1) * 19349663u ^ (size_t)(k.n + 1) * 83492791u ^ b[0] ^ (b[1] * 31u) ^ (b[2] * 131u);
+            return (size_t)k.v * 73856093u ^ (size_t)(k.t + 1) * 19349663u ^ (size_t)(k.n + 1) * 83492791u ^ k.g[0] ^ (k.g[1] * 31u) ^ (k.g[2] * 131u) ^
+                   (k.tan[0] * 7u) ^ (k.tan[1] * 977u) ^ (k.tan[2] * 4099u);
         }
     };
-    std::unordered_map<Key, std::uint32_t, KeyHash> seen;  // per mesh
+    // materials of the `mtllib` files: Kd -> AI_MATKEY_COLOR_DIFFUSE, map_Kd -> aiTextureType_DIFFUSE, norm / map_Kn -> aiTextureType_NORMALS
+    // (map_bump / bump are aiTextureType_HEIGHT in Assimp's OBJ importer and therefore NOT what ModelFileLoader.cpp:58 asks for)
+    struct Mtl { float kd[3] = {0.6f, 0.6f, 0.6f}; std::string map_kd, norm; };
+    std::map<std::string, Mtl> materials;
+    auto read_mtl = [&](const std::string& name) {
+        std::FILE* mf = std::fopen((dir.empty() ? name : dir + "/" + name).c_str(), "rb");
+        if (!mf) return;  // Assimp logs and carries on with default materials
+        std::vector<char> ml(1 << 12);
+        Mtl* cur = nullptr;
+        auto rest = [](char* e) {  // last blank-separated token of the statement: texture options (-bm 1.0 ...) precede the file name
+            std::string r(e);
+            while (!r.empty() && (r.back() == '\n' || r.back() == '\r' || r.back() == ' ' || r.back() == '\t')) r.pop_back();
+            const size_t sp = r.find_last_of(" \t");
+            return sp == std::string::npos ? r : r.substr(sp + 1);
+        };
+        while (std::fgets(ml.data(), (int)ml.size(), mf)) {
+            char* q = ml.data();
+            while (*q == ' ' || *q == '\t') ++q;
+            if (std::strncmp(q, "newmtl", 6) == 0) cur = &materials[rest(q + 6)];
+            else if (!cur) continue;
+            else if (q[0] == 'K' && q[1] == 'd' && (q[2] == ' ' || q[2] == '\t')) { char* e = q + 2; for (int k = 0; k < 3; ++k) cur->kd[k] = std::strtof(e, &e); }
+            else if (std::strncmp(q, "map_Kd", 6) == 0 && (q[6] == ' ' || q[6] == '\t')) cur->map_kd = rest(q + 6);
+            else if (std::strncmp(q, "map_Kn", 6) == 0 && (q[6] == ' ' || q[6] == '\t')) cur->norm = rest(q + 6);
+            else if (std::strncmp(q, "norm", 4) == 0 && (q[4] == ' ' || q[4] == '\t')) cur->norm = rest(q + 4);
+        }
+        std::fclose(mf);
+    };
+
     bool mesh_open = false;
-    std::string pending_name = "default";
+    std::string pending_name = "default", current_material, mesh_material;
+    std::vector<Corner> mesh_corners;  // three per triangle of the open mesh
+    auto close_mesh = [&]() {
+        if (!mesh_open) return;
+        mesh_open = false;
+        const size_t nc = mesh_corners.size();
+        std::vector<V3> tang(nc);
+        bool has_uv = false;
+        for (const Corner& c : mesh_corners) has_uv = has_uv || c.t >= 0;
+        auto normal_of = [&](const Corner& c) { return c.n >= 0 ? V3{N[3 * c.n], N[3 * c.n + 1], N[3 * c.n + 2]} : V3{c.g[0], c.g[1], c.g[2]}; };
+        auto uv_of = [&](const Corner& c) { return c.t >= 0 ? std::array<float, 2>{T[2 * c.t], 1.0f - T[2 * c.t + 1]} : std::array<float, 2>{0.0f, 0.0f}; };  // aiProcess_FlipUVs
+        if (has_uv) {  // CalcTangentsProcess needs a UV channel; without one mTangents stays null and the reference packs zeros (:138-143)
+            std::vector<V3> pos(nc), nrm(nc);
+            std::vector<std::array<float, 2>> uv(nc);
+            std::vector<std::uint32_t> faces(nc);
+            for (size_t k = 0; k < nc; ++k) {
+                const Corner& c = mesh_corners[k];
+                pos[k] = V3{P[3 * c.v], P[3 * c.v + 1], P[3 * c.v + 2]};
+                nrm[k] = normal_of(c);
+                uv[k] = uv_of(c);
+                faces[k] = (std::uint32_t)k;
+            }
+            calc_tangents(pos, nrm, uv, faces, tang);
+        }
+        std::unordered_map<Key, std::uint32_t, KeyHash> seen;  // aiProcess_JoinIdenticalVertices, per mesh
+        for (size_t k = 0; k < nc; ++k) {
+            const Corner& c = mesh_corners[k];
+            Key key{c.v, c.t, c.n, {0, 0, 0}, {0, 0, 0}};
+            std::memcpy(key.g, c.g, sizeof(key.g));
+            const float tg[3] = {tang[k].x + 0.0f, tang[k].y + 0.0f, tang[k].z + 0.0f};
+            std::memcpy(key.tan, tg, sizeof(tg));
+            auto it = seen.find(key);
+            if (it != seen.end()) { M->indices.push_back(it->second); continue; }
+            cndl_vertex v;
+            std::memset(&v, 0, sizeof(v));
+            v.position[0] = P[3 * c.v]; v.position[1] = P[3 * c.v + 1]; v.position[2] = P[3 * c.v + 2]; v.position[3] = 1.0f;
+            const V3 nv = normal_of(c);
+            const std::array<float, 2> tuv = uv_of(c);
+            v.normal_tangent[0] = cndl_pack_half2x16(nv.x, nv.y);          // data.x = packHalf2x16(vnormal.xy)         (ModelFileLoader.cpp:150)
+            v.normal_tangent[1] = cndl_pack_half2x16(nv.z, tang[k].x);     // data.y = packHalf2x16(vnormal.z, vtan.x)  (:151)
+            v.normal_tangent[2] = cndl_pack_half2x16(tang[k].y, tang[k].z);  // data.z = packHalf2x16(vtan.yz)           (:152)
+            v.texcoords = cndl_pack_half2x16(tuv[0], tuv[1]);              // :133-136, (0,0) when the mesh has no UVs (:148)
+            const std::uint32_t idx = (std::uint32_t)M->vertices.size();   // object-local = mesh-local + vertices of earlier meshes
+            M->vertices.push_back(v);
+            seen.emplace(key, idx);
+            M->indices.push_back(idx);
+        }
+        mesh_corners.clear();
+        // LoadMaterialTextures (:31-99): texture_path + "/" + name, "" when the material names no texture; ModelColor = diffuse colour
+        const auto mt = materials.find(mesh_material);
+        const Mtl m = mt == materials.end() ? Mtl{} : mt->second;
+        M->mesh_albedo.push_back(m.map_kd.empty() ? std::string() : dir + "/" + m.map_kd);
+        M->mesh_normal.push_back(m.norm.empty() ? std::string() : dir + "/" + m.norm);
+        M->mesh_color.push_back({m.kd[0], m.kd[1], m.kd[2]});
+    };
     auto open_mesh = [&]() {
         M->mesh_first_vertex.push_back((std::uint32_t)M->vertices.size());
         M->mesh_first_index.push_back((std::uint32_t)M->indices.size());
         M->mesh_names.push_back(pending_name);
-        seen.clear();
+        mesh_material = current_material;
         mesh_open = true;
-    };
-    auto vertex_of = [&](Key k) -> std::uint32_t {
-        auto it = seen.find(k);
-        if (it != seen.end()) return it->second;
-        cndl_vertex v;
-        std::memset(&v, 0, sizeof(v));
-        v.position[0] = P[3 * k.v]; v.position[1] = P[3 * k.v + 1]; v.position[2] = P[3 * k.v + 2]; v.position[3] = 1.0f;
-        float nx = k.g[0], ny = k.g[1], nz = k.g[2], tu = 0.0f, tv = 0.0f;
-        if (k.n >= 0) { nx = N[3 * k.n]; ny = N[3 * k.n + 1]; nz = N[3 * k.n + 2]; }
-        if (k.t >= 0) { tu = T[2 * k.t]; tv = 1.0f - T[2 * k.t + 1]; }  // aiProcess_FlipUVs
-        v.normal_tangent[0] = cndl_pack_half2x16(nx, ny);    // data.x = packHalf2x16(vnormal.xy)   (ModelFileLoader.cpp:150)
-        v.normal_tangent[1] = cndl_pack_half2x16(nz, 0.0f);  // data.y = packHalf2x16(vnormal.z, vtan.x); no tangents in an OBJ
-        v.normal_tangent[2] = cndl_pack_half2x16(0.0f, 0.0f);
-        v.texcoords = cndl_pack_half2x16(tu, tv);            // :133-136, (0,0) when the mesh has no UVs (:148)
-        const std::uint32_t idx = (std::uint32_t)M->vertices.size();  // object-local = mesh-local + vertices of earlier meshes
-        M->vertices.push_back(v);
-        seen.emplace(k, idx);
-        return idx;
     };
 
     std::vector<char> line(1 << 16);
@@ -140,13 +296,12 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
             char* e = s + 2;
             for (int k = 0; k < 2; ++k) T.push_back(std::strtof(e, &e));
         } else if (s[0] == 'f' && (s[1] == ' ' || s[1] == '\t')) {
-            if (!mesh_open) open_mesh();
-            std::vector<Key> corners;
+            std::vector<Corner> corners;
             char* e = s + 1;
             while (true) {
                 while (*e == ' ' || *e == '\t') ++e;
                 if (*e == '\0' || *e == '\n' || *e == '\r' || *e == '#') break;
-                Key k{0, -1, -1, {0.0f, 0.0f, 0.0f}};
+                Corner k{0, -1, -1, {0.0f, 0.0f, 0.0f}};
                 long v = std::strtol(e, &e, 10), t = 0, n = 0;
                 bool has_t = false, has_n = false;
                 if (*e == '/') {
@@ -165,7 +320,9 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
                 corners.push_back(k);
             }
             if (!problem.empty()) break;
-            if (corners.size() >= 3) {  // aiProcess_GenNormals: corners without a `vn` get the face's normal
+            if (corners.size() < 3) continue;
+            if (!mesh_open) open_mesh();
+            {  // aiProcess_GenNormals: corners without a `vn` get the face's normal
                 const float* a = &P[3 * corners[0].v];
                 const float* b = &P[3 * corners[1].v];
                 const float* c = &P[3 * corners[2].v];
@@ -174,12 +331,12 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
                 const float len = std::sqrt(fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2]);
                 if (len > 0.0f) { fn[0] /= len; fn[1] /= len; fn[2] /= len; }
                 for (auto& k : corners)
-                    if (k.n < 0) { k.g[0] = fn[0]; k.g[1] = fn[1]; k.g[2] = fn[2]; }
+                    if (k.n < 0) { k.g[0] = fn[0] + 0.0f; k.g[1] = fn[1] + 0.0f; k.g[2] = fn[2] + 0.0f; }
             }
             for (size_t c = 1; c + 1 < corners.size(); ++c) {  // triangle fan, like aiProcess_Triangulate on convex polygons
-                M->indices.push_back(vertex_of(corners[0]));
-                M->indices.push_back(vertex_of(corners[c]));
-                M->indices.push_back(vertex_of(corners[c + 1]));
+                mesh_corners.push_back(corners[0]);
+                mesh_corners.push_back(corners[c]);
+                mesh_corners.push_back(corners[c + 1]);
             }
         } else if (std::strncmp(s, "usemtl", 6) == 0 || ((s[0] == 'o' || s[0] == 'g') && (s[1] == ' ' || s[1] == '\t'))) {
             char* e = s + (s[0] == 'u' ? 6 : 1);
@@ -187,11 +344,17 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
             std::string name(e);
             while (!name.empty() && (name.back() == '\n' || name.back() == '\r' || name.back() == ' ')) name.pop_back();
             pending_name = name.empty() ? "default" : name;
-            // a new mesh starts at the next face; a mesh that has no face yet is simply renamed
-            if (mesh_open && M->indices.size() > M->mesh_first_index.back()) mesh_open = false;
-            else if (mesh_open) M->mesh_names.back() = pending_name;
+            if (s[0] == 'u') current_material = name;
+            close_mesh();  // a new mesh starts at the next face
+        } else if (std::strncmp(s, "mtllib", 6) == 0 && (s[6] == ' ' || s[6] == '\t')) {
+            char* e = s + 6;
+            while (*e == ' ' || *e == '\t') ++e;
+            std::string name(e);
+            while (!name.empty() && (name.back() == '\n' || name.back() == '\r' || name.back() == ' ')) name.pop_back();
+            if (!name.empty()) read_mtl(name);
         }
     }
+    close_mesh();
     if (!problem.empty() || M->indices.empty()) return fail(problem.empty() ? std::string("no faces in ") + path : problem);
     // one GlobalMeshNumber per mesh, consecutive from first_mesh_number; one entry per triangle
     M->mesh_ids.resize(M->indices.size() / 3);
@@ -428,7 +591,20 @@ int cndl_model_load_gltf(const char* path, int32_t first_mesh_number, cndl_model
     const JVal root = jp.value();
     if (!jp.ok || root.type != JVal::Obj) return fail(std::string(path) + ": not valid JSON");
     const JVal *jbuffers = root.find("buffers"), *jviews = root.find("bufferViews"), *jacc = root.find("accessors"), *jmeshes = root.find("meshes"),
-               *jnodes = root.find("nodes"), *jscenes = root.find("scenes");
+               *jnodes = root.find("nodes"), *jscenes = root.find("scenes"), *jmats = root.find("materials"), *jtex = root.find("textures"),
+               *jimages = root.find("images");
+    const std::string texture_dir = parent_dir(spath);
+    // textures[i].source -> images[j].uri; an image held in a bufferView is named "*j", Assimp's name for an embedded texture
+    auto texture_name = [&](const JVal* slot) -> std::string {
+        if (!slot || slot->type != JVal::Obj || !jtex) return std::string();
+        const long t = slot->integer("index", -1);
+        if (t < 0 || (size_t)t >= jtex->arr.size()) return std::string();
+        const long img = jtex->arr[(size_t)t].integer("source", -1);
+        if (!jimages || img < 0 || (size_t)img >= jimages->arr.size()) return std::string();
+        const JVal* uri = jimages->arr[(size_t)img].find("uri");
+        if (uri && uri->type == JVal::Str && uri->str.compare(0, 5, "data:") != 0) return uri->str;
+        return "*" + std::to_string(img);
+    };
     if (!jviews || !jacc || !jmeshes || !jbuffers) return fail(std::string(path) + ": no meshes / accessors / bufferViews / buffers");
 
     std::vector<std::vector<unsigned char>> buffers(jbuffers->arr.size());
@@ -486,12 +662,15 @@ int cndl_model_load_gltf(const char* path, int32_t first_mesh_number, cndl_model
             if (mode < 4 || mode > 6) continue;  // points / lines are not triangles
             const JVal* attrs = prim.find("attributes");
             if (!attrs) continue;
-            Accessor pos, nor, uv, idx;
+            Accessor pos, nor, uv, idx, tan;
             if (!accessor(attrs->integer("POSITION", -1), pos, why) || pos.width != 3) { if (why.empty()) why = "POSITION must be VEC3"; return false; }
             const bool has_n = attrs->find("NORMAL") != nullptr, has_uv = attrs->find("TEXCOORD_0") != nullptr, has_i = prim.find("indices") != nullptr;
             if (has_n && (!accessor(attrs->integer("NORMAL", -1), nor, why) || nor.count < pos.count)) { if (why.empty()) why = "NORMAL shorter than POSITION"; return false; }
             if (has_uv && (!accessor(attrs->integer("TEXCOORD_0", -1), uv, why) || uv.count < pos.count)) { if (why.empty()) why = "TEXCOORD_0 shorter than POSITION"; return false; }
             if (has_i && !accessor(prim.integer("indices", -1), idx, why)) return false;
+            // a TANGENT attribute is imported as it stands (CalcTangentsProcess skips meshes that already carry tangents)
+            const bool has_t = has_n && attrs->find("TANGENT") != nullptr && accessor(attrs->integer("TANGENT", -1), tan, why) && tan.width >= 3 && tan.count >= pos.count;
+            why.clear();
             // corner list in triangle order
             const size_t n_src = has_i ? idx.count : pos.count;
             std::vector<std::uint32_t> corners;
@@ -506,6 +685,23 @@ int cndl_model_load_gltf(const char* path, int32_t first_mesh_number, cndl_model
             M->mesh_first_vertex.push_back(first_vertex);
             M->mesh_first_index.push_back((std::uint32_t)M->indices.size());
             M->mesh_names.push_back(name && name->type == JVal::Str ? name->str : std::string("mesh"));
+            {   // LoadMaterialTextures (ModelFileLoader.cpp:31-99): base colour texture, normal texture, diffuse colour
+                std::string albedo, normal;
+                std::array<float, 3> color{1.0f, 1.0f, 1.0f};  // glTF default baseColorFactor, also Assimp's default glTF material
+                const long mat = prim.integer("material", -1);
+                if (jmats && mat >= 0 && (size_t)mat < jmats->arr.size()) {
+                    const JVal& jm = jmats->arr[(size_t)mat];
+                    if (const JVal* pbr = jm.find("pbrMetallicRoughness")) {
+                        if (const JVal* bc = pbr->find("baseColorFactor"))
+                            for (size_t k = 0; k < 3 && k < bc->arr.size(); ++k) color[k] = (float)bc->arr[k].num;
+                        albedo = texture_name(pbr->find("baseColorTexture"));
+                    }
+                    normal = texture_name(jm.find("normalTexture"));
+                }
+                M->mesh_albedo.push_back(albedo.empty() ? std::string() : texture_dir + "/" + albedo);
+                M->mesh_normal.push_back(normal.empty() ? std::string() : texture_dir + "/" + normal);
+                M->mesh_color.push_back(color);
+            }
             auto make_vertex = [&](std::uint32_t v, const float* n) {
                 cndl_vertex o;
                 std::memset(&o, 0, sizeof(o));
@@ -517,13 +713,46 @@ int cndl_model_load_gltf(const char* path, int32_t first_mesh_number, cndl_model
                 o.texcoords = cndl_pack_half2x16(tu, tv);
                 return o;
             };
+            std::vector<V3> vertex_normals;
+            std::vector<std::array<float, 2>> vertex_uvs;
+            // tangents of the mesh's vertices [first_vertex, end) over faces given as mesh-local index triples (ModelFileLoader.cpp:138-152)
+            auto add_tangents = [&](const std::vector<std::uint32_t>& faces) {
+                if (!has_uv) return;  // no UV channel: mTangents stays null, the reference packs zeros
+                const size_t nv = M->vertices.size() - first_vertex;
+                std::vector<V3> tg(nv);
+                if (has_t) {
+                    for (size_t v = 0; v < nv; ++v) tg[v] = V3{tan.get(v, 0), tan.get(v, 1), tan.get(v, 2)};
+                } else {
+                    std::vector<V3> p(nv), nn(nv);
+                    std::vector<std::array<float, 2>> tuv(nv);
+                    for (size_t v = 0; v < nv; ++v) {
+                        const cndl_vertex& o = M->vertices[first_vertex + v];
+                        p[v] = V3{o.position[0], o.position[1], o.position[2]};
+                        nn[v] = vertex_normals[v];
+                        tuv[v] = vertex_uvs[v];
+                    }
+                    calc_tangents(p, nn, tuv, faces, tg);
+                }
+                for (size_t v = 0; v < nv; ++v) {
+                    cndl_vertex& o = M->vertices[first_vertex + v];
+                    o.normal_tangent[1] = cndl_pack_half2x16(vertex_normals[v].z, tg[v].x);
+                    o.normal_tangent[2] = cndl_pack_half2x16(tg[v].y, tg[v].z);
+                }
+            };
+            auto remember = [&](std::uint32_t v, const float* n) {
+                vertex_normals.push_back(V3{n[0], n[1], n[2]});
+                vertex_uvs.push_back({has_uv ? uv.get(v, 0) : 0.0f, has_uv ? 1.0f - uv.get(v, 1) : 0.0f});
+            };
             if (has_n) {  // indexed as in the file
                 for (std::uint32_t v = 0; v < pos.count; ++v) {
                     const float n[3] = {nor.get(v, 0), nor.get(v, 1), nor.get(v, 2)};
                     M->vertices.push_back(make_vertex(v, n));
+                    remember(v, n);
                 }
                 for (std::uint32_t c : corners) M->indices.push_back(first_vertex + c);
+                add_tangents(corners);
             } else {  // aiProcess_GenNormals: flat shading, one vertex per corner
+                std::vector<std::uint32_t> faces;
                 for (size_t k = 0; k + 2 < corners.size() + 0 && k + 2 < corners.size(); k += 3) {
                     float p[3][3];
                     for (int c = 0; c < 3; ++c)
@@ -533,10 +762,13 @@ int cndl_model_load_gltf(const char* path, int32_t first_mesh_number, cndl_model
                     const float len = std::sqrt(fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2]);
                     if (len > 0.0f) { fn[0] /= len; fn[1] /= len; fn[2] /= len; }
                     for (int c = 0; c < 3; ++c) {
+                        faces.push_back((std::uint32_t)(M->vertices.size() - first_vertex));
                         M->indices.push_back((std::uint32_t)M->vertices.size());
                         M->vertices.push_back(make_vertex(corners[k + c], fn));
+                        remember(corners[k + c], fn);
                     }
                 }
+                add_tangents(faces);
             }
         }
         return true;
@@ -597,6 +829,39 @@ const cndl_vertex* cndl_model_vertices(const cndl_model* m) { return m ? m->vert
 const uint32_t* cndl_model_indices(const cndl_model* m) { return m ? m->indices.data() : nullptr; }
 const int32_t* cndl_model_mesh_ids(const cndl_model* m) { return m ? m->mesh_ids.data() : nullptr; }
 const char* cndl_model_mesh_name(const cndl_model* m, size_t mesh) { return (m && mesh < m->mesh_names.size()) ? m->mesh_names[mesh].c_str() : ""; }
+const char* cndl_model_mesh_albedo_path(const cndl_model* m, size_t mesh) { return (m && mesh < m->mesh_albedo.size()) ? m->mesh_albedo[mesh].c_str() : ""; }
+const char* cndl_model_mesh_normal_path(const cndl_model* m, size_t mesh) { return (m && mesh < m->mesh_normal.size()) ? m->mesh_normal[mesh].c_str() : ""; }
+int cndl_model_mesh_color(const cndl_model* m, size_t mesh, float rgb[3]) {
+    if (!m || !rgb || mesh >= m->mesh_color.size()) return CNDL_ERR_INVALID;
+    for (int k = 0; k < 3; ++k) rgb[k] = m->mesh_color[mesh][(size_t)k];
+    return CNDL_OK;
+}
+
+// RayIntersector::GenerateMeshTextureReferences (Intersector.h:367-402): every handle not seen before takes the next index of the
+// shader's Textures[] array — whether or not its path was found — and the table entry holds that index only for a valid path.
+int cndl_generate_texture_references(const cndl_mesh_material* materials, size_t n, cndl_texture_reference* out, uint64_t* handles, size_t handles_cap,
+                                     size_t* n_handles) try {
+    if ((n && (!materials || !out)) || (handles_cap && !handles)) return CNDL_ERR_INVALID;
+    std::map<std::uint64_t, int> index_of;  // m_TextureHandleReferenceMap
+    int last = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const cndl_mesh_material& mm = materials[i];
+        if (index_of.find(mm.albedo_handle) == index_of.end()) index_of[mm.albedo_handle] = last++;
+        if (index_of.find(mm.normal_handle) == index_of.end()) index_of[mm.normal_handle] = last++;
+        cndl_texture_reference r;
+        std::memset(&r, 0, sizeof(r));
+        r.model_color[0] = mm.model_color[0]; r.model_color[1] = mm.model_color[1]; r.model_color[2] = mm.model_color[2]; r.model_color[3] = 1.0f;
+        r.albedo = mm.albedo_valid ? index_of[mm.albedo_handle] : -1;
+        r.normal = mm.normal_valid ? index_of[mm.normal_handle] : -1;
+        out[i] = r;
+    }
+    for (const auto& kv : index_of)
+        if ((size_t)kv.second < handles_cap) handles[kv.second] = kv.first;
+    if (n_handles) *n_handles = (size_t)last;
+    return CNDL_OK;
+} catch (...) {
+    return CNDL_ERR_OOM;
+}
 
 int cndl_add_model(cndl_ctx* ctx, uint32_t object_id, const cndl_model* m, const cndl_build_opts* opts) {
     if (!ctx || !m) return CNDL_ERR_INVALID;

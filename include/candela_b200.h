@@ -326,6 +326,30 @@ typedef struct cndl_hit_attr { float nx, ny, nz, u, v, emissivity, alpha; int32_
 int cndl_get_data_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_attr* d_out, void* stream);
 int cndl_get_data(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_attr* out);
 
+/* The per-mesh material table GetData indexes by GlobalMeshNumber: BVH::TextureReferences (Source/Core/BVH/Intersector.h:32-37),
+ * 32 bytes, uploaded by RayIntersector::GenerateMeshTextureReferences (:404-409) and bound at SSBO slot 4 (:251). */
+typedef struct cndl_texture_reference { float model_color[4]; int32_t albedo, normal, pad[2]; } cndl_texture_reference;
+/* One entry of FileLoader::GetMeshTexturePaths() (ModelFileLoader.h:21-25) after the texture cache has resolved its two paths
+ * (GLClasses::GetTextureCachedDataForPath, Texture.cpp:168-188: a handle and whether the path was found). */
+typedef struct cndl_mesh_material { uint64_t albedo_handle, normal_handle; int32_t albedo_valid, normal_valid; float model_color[3]; float pad; } cndl_mesh_material;
+/* GenerateMeshTextureReferences (Intersector.h:367-402) as host arithmetic: walks the meshes in order, gives every handle not seen
+ * before the next texture-array index — INVALID handles too, they consume an index like in the reference — and writes
+ * {vec4(ModelColor, 1), valid ? index : -1, valid ? index : -1} per mesh.  handles (optional, capacity handles_cap) receives the
+ * handle bound to Textures[i] (m_TextureHandleReferenceMap inverted, _BindTextures :423-427); *n_handles the number of indices used.
+ * Host only; no GPU needed. */
+int cndl_generate_texture_references(const cndl_mesh_material* materials, size_t n, cndl_texture_reference* out, uint64_t* handles, size_t handles_cap,
+                                     size_t* n_handles);
+/* Uploads the table (replacing the previous one, like the reference's glDeleteBuffers + glGenBuffers); n = 0 removes it. */
+int cndl_set_texture_references(cndl_ctx* ctx, const cndl_texture_reference* refs, size_t n);
+size_t cndl_texture_reference_count(const cndl_ctx* ctx);
+/* GetData in full up to the texture unit: cndl_hit_attr plus the Albedo decision (…Stackless.glsl:393-404).  albedo_ref > -1: the
+ * caller samples Textures[albedo_ref] at (u, v) and albedo[] is (0,0,0), the shader's initial value; albedo_ref == -1: albedo[] is the
+ * mesh's ModelColor.xyz.  A miss gives albedo (0,0,0), albedo_ref -1.  A hit whose mesh number is not in the table (the shader would read
+ * past its SSBO) gives albedo (0,0,0), albedo_ref -2; the host-buffer call turns any such record into CNDL_ERR_INVALID. */
+typedef struct cndl_hit_material { float nx, ny, nz, u, v, emissivity, alpha; int32_t mesh; float albedo[3]; int32_t albedo_ref; } cndl_hit_material;
+int cndl_get_data_material_device(cndl_ctx* ctx, const cndl_hit* d_hits, size_t R, cndl_hit_material* d_out, void* stream);
+int cndl_get_data_material(cndl_ctx* ctx, const cndl_hit* hits, size_t R, cndl_hit_material* out);
+
 /* Physics::CollideBox (Source/Core/Physics.cpp:203-228; declared Physics.h:15) for a batch of axis-aligned boxes: does the
  * box touch any triangle of any entity?  collided = 0/1; mesh / tri / entity identify the first overlapping triangle in the
  * reference's walk order (the reference computes them and returns only the bool).  Physics::CollidePoint is the box
@@ -355,6 +379,13 @@ const cndl_vertex* cndl_model_vertices(const cndl_model* m);
 const uint32_t* cndl_model_indices(const cndl_model* m);
 const int32_t* cndl_model_mesh_ids(const cndl_model* m);
 const char* cndl_model_mesh_name(const cndl_model* m, size_t mesh);
+/* The mesh's material as LoadMaterialTextures records it in FileLoader::GetMeshTexturePaths() (ModelFileLoader.cpp:31-99): texture
+ * path = directory of the model file + "/" + the name the material gives ("" when it names none; OBJ: map_Kd and norm / map_Kn, the
+ * statements Assimp maps to aiTextureType_DIFFUSE / _NORMALS; glTF: baseColorTexture and normalTexture image URIs), ModelColor = the
+ * diffuse colour (OBJ Kd, glTF baseColorFactor; Assimp's defaults 0.6 / 1.0 when the file gives none). */
+const char* cndl_model_mesh_albedo_path(const cndl_model* m, size_t mesh);
+const char* cndl_model_mesh_normal_path(const cndl_model* m, size_t mesh);
+int cndl_model_mesh_color(const cndl_model* m, size_t mesh, float rgb[3]);
 int cndl_add_model(cndl_ctx* ctx, uint32_t object_id, const cndl_model* m, const cndl_build_opts* opts);  /* = cndl_add_object */
 /* glm::packHalf2x16 (glm 0.9.8.5 detail::toFloat16: round to nearest, ties up in magnitude). */
 uint32_t cndl_pack_half2x16(float x, float y);

@@ -113,10 +113,18 @@ struct BVHEntity {  // Intersector.h:43-49
 struct RayHit { float T, U, V, W; int Mesh, TriangleIdx, Entity, Iters; };  // cndl_hit
 struct HitData { float Normal[3]; float UV[2]; float Emissivity; float Alpha; int Mesh; };  // cndl_hit_attr: the outputs of GetData
 struct Ray { float Origin[3]; float TMin; float Direction[3]; float TMax; }; // cndl_ray
+struct HitMaterial { float Normal[3]; float UV[2]; float Emissivity; float Alpha; int Mesh; float Albedo[3]; int AlbedoRef; };  // cndl_hit_material
+namespace BVH {
+struct TextureReferences { float ModelColor[4]; int Albedo; int Normal; int Pad[2]; };  // Intersector.h:32-37
+}
+namespace FileLoader {
+// ModelFileLoader.h:21-25 with the two paths already resolved by the texture cache (Texture.cpp:168-188): a 64-bit handle + found flag.
+struct _MeshMaterialData { std::uint64_t AlbedoHandle, NormalHandle; int AlbedoValid, NormalValid; float ModelColor[3]; float Pad; };  // cndl_mesh_material
+}
 
 static_assert(sizeof(Vertex) == 32 && sizeof(BVH::Triangle) == 16 && sizeof(BVH::FlattenedNode) == 32 &&
                   sizeof(BVH::FlattenedStackNode) == 64 && sizeof(BVHEntity) == 192 && sizeof(RayHit) == 32 && sizeof(Ray) == 32 &&
-                  sizeof(HitData) == 32,
+                  sizeof(HitData) == 32 && sizeof(HitMaterial) == 48 && sizeof(BVH::TextureReferences) == 32 && sizeof(FileLoader::_MeshMaterialData) == 40,
               "record layouts are the contract (SURVEY.md §8a)");
 
 template <typename T>
@@ -249,6 +257,26 @@ public:
         Check(cndl_get_data(m_Ctx, reinterpret_cast<const cndl_hit*>(Hits), Count, reinterpret_cast<cndl_hit_attr*>(Output)));
     }
 
+    // GenerateMeshTextureReferences (Intersector.h:367-410): texture-array indices per mesh + upload of the table GetData reads.
+    // The reference pulls the materials from FileLoader::GetMeshTexturePaths(); here the caller passes them.  m_TextureHandles[i]
+    // is the handle to bind to Textures[i] (m_TextureHandleReferenceMap, :423-427).
+    void GenerateMeshTextureReferences(const std::vector<FileLoader::_MeshMaterialData>& MeshMaterials) {
+        Require();
+        m_MeshTextureReferences.assign(MeshMaterials.size(), BVH::TextureReferences{});
+        m_TextureHandles.assign(2 * MeshMaterials.size(), 0);
+        std::size_t used = 0;
+        Check(cndl_generate_texture_references(reinterpret_cast<const cndl_mesh_material*>(MeshMaterials.data()), MeshMaterials.size(),
+                                               reinterpret_cast<cndl_texture_reference*>(m_MeshTextureReferences.data()), m_TextureHandles.data(),
+                                               m_TextureHandles.size(), &used));
+        m_TextureHandles.resize(used);
+        Check(cndl_set_texture_references(m_Ctx, reinterpret_cast<const cndl_texture_reference*>(m_MeshTextureReferences.data()), m_MeshTextureReferences.size()));
+    }
+    // GetData with the Albedo decision (:393-404): AlbedoRef > -1 = sample Textures[AlbedoRef] at UV, else Albedo = ModelColor.
+    void GetData(const RayHit* Hits, std::size_t Count, HitMaterial* Output) {
+        Require();
+        Check(cndl_get_data_material(m_Ctx, reinterpret_cast<const cndl_hit*>(Hits), Count, reinterpret_cast<cndl_hit_material*>(Output)));
+    }
+
     // Physics::CollideBox / CollidePoint (Physics.cpp:175-228) on the GPU; stackless intersectors only, like Physics.h:15.
     bool CollideBox(const float* Min, const float* Max) {
         Require();
@@ -293,6 +321,8 @@ public:
     std::vector<T> m_BVHNodes;
     std::vector<Vertex> m_BVHVertices;
     std::vector<BVH::Triangle> m_BVHTriangles;
+    std::vector<BVH::TextureReferences> m_MeshTextureReferences;  // Intersector.h:116
+    std::vector<std::uint64_t> m_TextureHandles;
 
 private:
     void Require() { if (!m_Ctx) Initialize(0); }

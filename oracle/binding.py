@@ -29,6 +29,8 @@ NODE64_DT = np.dtype([("lmin", "<f4", 4), ("lmax", "<f4", 4), ("rmin", "<f4", 4)
 ENTITY_DT = np.dtype([("model", "<f4", 16), ("inverse", "<f4", 16), ("node_offset", "<i4"), ("node_count", "<i4"), ("data", "<i4", 14)])
 RAY_DT = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
 ATTR_DT = np.dtype([("normal", "<f4", 3), ("uv", "<f4", 2), ("emissivity", "<f4"), ("alpha", "<f4"), ("mesh", "<i4")])
+TEXREF_DT = np.dtype([("model_color", "<f4", 4), ("albedo", "<i4"), ("normal", "<i4"), ("pad", "<i4", 2)])   # BVH::TextureReferences, Intersector.h:32-37
+MATERIAL_DT = np.dtype([("normal", "<f4", 3), ("uv", "<f4", 2), ("emissivity", "<f4"), ("alpha", "<f4"), ("mesh", "<i4"), ("albedo", "<f4", 3), ("albedo_ref", "<i4")])
 HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("w", "<f4"), ("mesh", "<i4"), ("tri", "<i4"), ("entity", "<i4"), ("iters", "<i4")])
 assert (VERTEX_DT.itemsize, TRIANGLE_DT.itemsize, NODE32_DT.itemsize, NODE64_DT.itemsize, ENTITY_DT.itemsize, RAY_DT.itemsize, HIT_DT.itemsize) == (32, 16, 32, 64, 192, 32, 32)
 
@@ -74,6 +76,7 @@ def lib() -> C.CDLL:
         L.orc_trace.argtypes = [C.c_int, C.c_int, vp, u64, vp, vp, vp, i32, vp, u64, vp, vp, vp, C.c_int]
         L.orc_brute_force.argtypes = [vp, u64, vp, vp, i32, vp, u64, vp, C.c_int]
         L.orc_get_data.argtypes = [vp, vp, vp, vp, u64, vp]
+        L.orc_get_data_material.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp]
         L.orc_collide_boxes.argtypes = [vp, u64, vp, vp, vp, i32, vp, u64, vp]
         L.orc_hardware_threads.restype = C.c_int
         _lib = L
@@ -237,6 +240,42 @@ def get_data(tris, verts, entities, hits):
     return out
 
 
+def get_data_material(tris, verts, entities, refs, hits):
+    """GetData with the BVHTextureReferences table (oracle_trace.cpp: orc_get_data_material)."""
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
+    verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DT)
+    refs = np.ascontiguousarray(refs, dtype=TEXREF_DT)
+    hits = np.ascontiguousarray(hits, dtype=HIT_DT)
+    out = np.zeros(len(hits), dtype=MATERIAL_DT)
+    lib().orc_get_data_material(_p(tris), _p(verts), _p(entities), _p(refs), len(refs), _p(hits), len(hits), _p(out))
+    return out
+
+
+def texture_references(materials):
+    """RayIntersector::GenerateMeshTextureReferences (Intersector.h:367-402) restated.  materials: one
+    (albedo_handle, albedo_valid, normal_handle, normal_valid, (r, g, b)) per mesh, i.e. what GetTextureCachedDataForPath
+    (Texture.cpp:168-188) returns for _MeshMaterialData::Albedo / Normal plus its ModelColor.  Returns (table, handles) where
+    handles[i] is the handle bound to Textures[i] (m_TextureHandleReferenceMap, :423-427)."""
+    data_map = {}                                   # :370-372  DataMap (handle -> index), cleared on every call
+    last = 0                                        # :375
+    out = np.zeros(len(materials), dtype=TEXREF_DT)
+    for i, (a, va, b, vb, color) in enumerate(materials):
+        if a not in data_map:                       # :390-392: an index is taken whether or not the path was valid
+            data_map[a] = last
+            last += 1
+        if b not in data_map:                       # :394-396
+            data_map[b] = last
+            last += 1
+        out[i]["model_color"] = (color[0], color[1], color[2], 1.0)   # :401 glm::vec4(ModelColor, 1.0f)
+        out[i]["albedo"] = data_map[a] if va else -1                  # :398
+        out[i]["normal"] = data_map[b] if vb else -1                  # :399
+    handles = np.zeros(last, dtype=np.uint64)
+    for h, k in data_map.items():
+        handles[k] = h
+    return out, handles
+
+
 BOX_DT = np.dtype([("min", "<f4", 3), ("pad0", "<f4"), ("max", "<f4", 3), ("pad1", "<f4")])
 COLLISION_DT = np.dtype([("collided", "<i4"), ("mesh", "<i4"), ("tri", "<i4"), ("entity", "<i4")])
 
@@ -305,6 +344,7 @@ def ref_lib() -> C.CDLL:
         R.ref_glm_inverse.argtypes = [vp, vp]
         R.ref_glsl_sample.argtypes = [C.c_int, vp, vp, C.c_float, C.c_uint64, vp]
         R.ref_glsl_get_data.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_uint64, vp]
+        R.ref_glsl_get_data_material.argtypes = [vp, vp, vp, C.c_int32, vp, vp, C.c_uint64, vp, vp]
         R.ref_pack_half2x16.argtypes = [C.c_float, C.c_float]
         R.ref_pack_half2x16.restype = C.c_uint32
         R.ref_collide_box.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, vp]
@@ -377,6 +417,21 @@ def ref_glsl_get_data(tris, verts, entities, hits):
     out = np.zeros(len(hits), dtype=ATTR_DT)
     ref_lib().ref_glsl_get_data(_p(tris), _p(verts), _p(entities), len(entities), _p(hits), len(hits), _p(out))
     return out
+
+
+def ref_glsl_get_data_material(tris, verts, entities, refs, hits):
+    """GetData of the compiled reference shader with a BVHTextureReferences table.  Returns (records, tex_uv): `albedo_ref` is the index
+    of the sampler the shader called texture() with (-1: it did not), tex_uv the UV it passed.  Every mesh must be inside the table."""
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DT)
+    verts = np.ascontiguousarray(verts, dtype=VERTEX_DT)
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DT)
+    refs = np.ascontiguousarray(refs, dtype=TEXREF_DT)
+    hits = np.ascontiguousarray(hits, dtype=HIT_DT)
+    assert len(hits) == 0 or int(hits["mesh"].max()) < len(refs)
+    out = np.zeros(len(hits), dtype=MATERIAL_DT)
+    tex_uv = np.zeros((len(hits), 2), dtype=np.float32)
+    ref_lib().ref_glsl_get_data_material(_p(tris), _p(verts), _p(entities), len(entities), _p(refs), _p(hits), len(hits), _p(out), _p(tex_uv))
+    return out, tex_uv
 
 
 def ref_primary_rays(inv_view, inv_proj, W, H) -> np.ndarray:

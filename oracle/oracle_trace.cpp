@@ -462,6 +462,37 @@ extern "C" void orc_get_data(const void* tris_, const void* verts_, const void* 
     }
 }
 
+// GetData with the BVHTextureReferences table (SL:393-404): the Albedo decision without the texture unit.  Record = Attr32 +
+// {albedo[3], albedo_ref}: albedo_ref > -1 means the shader samples Textures[albedo_ref] at (u, v) (albedo stays at its
+// initial vec3(0)); otherwise albedo = ModelColor.xyz.  A mesh outside the table is marked albedo_ref = -2 (the shader has no
+// defined behaviour there).  PINNED by tests/test_materials.py against the compiled reference shader (ref_glsl_get_data_material).
+namespace {
+struct TexRef32 { float color[4]; int32_t albedo, normal, pad[2]; };
+struct Mat48 { Attr32 a; float albedo[3]; int32_t albedo_ref; };
+static_assert(sizeof(TexRef32) == 32 && sizeof(Mat48) == 48, "record layouts");
+}  // namespace
+
+extern "C" void orc_get_data_material(const void* tris_, const void* verts_, const void* entities, const void* refs_, uint64_t n_refs, const orc_hit* hits,
+                                      uint64_t R, void* out_) {
+    const TexRef32* refs = static_cast<const TexRef32*>(refs_);
+    Mat48* out = static_cast<Mat48*>(out_);
+    std::vector<Attr32> attr(R);
+    orc_get_data(tris_, verts_, entities, hits, R, attr.data());
+    for (uint64_t i = 0; i < R; ++i) {
+        const orc_hit& h = hits[i];
+        Mat48 m{attr[i], {0.0f, 0.0f, 0.0f}, -1};
+        if (!(h.t < 0.0f || h.mesh < 0)) {
+            if ((uint64_t)h.mesh >= n_refs) m.albedo_ref = -2;
+            else {
+                const int ref = refs[h.mesh].albedo;                       // SL:393
+                if (ref > -1 && h.mesh > -1 && h.t > 0.0f) m.albedo_ref = ref;  // SL:397-399: texture(Textures[Ref], UV)
+                else { m.albedo[0] = refs[h.mesh].color[0]; m.albedo[1] = refs[h.mesh].color[1]; m.albedo[2] = refs[h.mesh].color[2]; }  // SL:402-404
+            }
+        }
+        out[i] = m;
+    }
+}
+
 // ---- AABB collide query: Physics::CollideBox / CollideBVH (Source/Core/Physics.cpp:21-228), the other consumer of the
 // stackless buffers.  PINNED: the reference's Physics.cpp compiles here (oracle/_ref) and
 // tests/test_collide.py requires identical answers.  Quirks kept: the query box is taken to object space corner by

@@ -19,8 +19,12 @@
 #include <glm/gtc/packing.hpp>
 
 namespace glsl_prelude {
-struct sampler2D {};
-inline glm::vec4 texture(const sampler2D&, const glm::vec2&) { return glm::vec4(0.0f); }  // no texture unit here: the ModelColor branch is the one exercised
+// No texture unit here.  A sampler knows its index in Textures[], and texture() records (index, uv) of the call instead of
+// sampling: that is exactly what the product reports for a textured hit (albedo_ref, u, v), so the Albedo branch is pinned too.
+struct sampler2D { int id = -1; };
+static int g_sampled_id = -1;
+static glm::vec2 g_sampled_uv(0.0f);
+inline glm::vec4 texture(const sampler2D& s, const glm::vec2& uv) { g_sampled_id = s.id; g_sampled_uv = uv; return glm::vec4(0.0f); }
 }  // namespace glsl_prelude
 
 namespace ref_stackless {
@@ -244,6 +248,40 @@ int ref_glsl_get_data(const void* tris, const void* verts, const void* ents, int
             uv = (glm::unpackHalf2x16(A.PackedData.w) * h.u) + (glm::unpackHalf2x16(B.PackedData.w) * h.v) + (glm::unpackHalf2x16(C.PackedData.w) * h.w);
         }
         out[i] = Attr32{normal.x, normal.y, normal.z, uv.x, uv.y, emissivity, alpha, h.mesh};
+    }
+    return 0;
+}
+
+// GetData with a caller-supplied BVHTextureReferences table (Intersector.h:32-37).  Output per record: the cndl_hit_material
+// layout (48 bytes) — Normal, UV, Emissivity, Alpha, Mesh, Albedo, and the index of the sampler texture() was called with
+// (-1: not called); tex_uv receives the UV texture() was called with.  Every Mesh must be inside the table (the caller checks).
+int ref_glsl_get_data_material(const void* tris, const void* verts, const void* ents, int32_t n_ents, const void* refs, const void* hits_, uint64_t R,
+                               void* out_, float* tex_uv) {
+    const void* nodes = nullptr;
+    const uint64_t n_nodes = 0;
+    BIND(ref_stackless)
+    ref_stackless::BVHTextureReferences = static_cast<const ref_stackless::TextureReferences*>(refs);
+    for (int i = 0; i < 512; ++i) ref_stackless::Textures[i].id = i;
+    const Hit32* hits = static_cast<const Hit32*>(hits_);
+    struct Mat48 { float nx, ny, nz, u, v, emissivity, alpha; int32_t mesh; float albedo[3]; int32_t albedo_ref; };
+    static_assert(sizeof(Mat48) == 48, "record layout");
+    Mat48* out = static_cast<Mat48*>(out_);
+    for (uint64_t i = 0; i < R; ++i) {
+        const Hit32& h = hits[i];
+        glm::vec3 normal(0.0f), albedo(0.0f);
+        float emissivity = 0.0f, alpha = 0.0f;
+        glsl_prelude::g_sampled_id = -1;
+        glsl_prelude::g_sampled_uv = glm::vec2(0.0f);
+        ref_stackless::GetData(glm::vec4(h.t, h.u, h.v, h.w), h.mesh, h.tri, h.entity, normal, albedo, emissivity, alpha);
+        const bool miss = h.t < 0.0f || h.mesh < 0;
+        glm::vec2 uv(0.0f);
+        if (!miss) {
+            const auto& T = ref_stackless::BVHTris[h.tri];
+            const auto &A = ref_stackless::BVHVertices[T.PackedData[0]], &B = ref_stackless::BVHVertices[T.PackedData[1]], &C = ref_stackless::BVHVertices[T.PackedData[2]];
+            uv = (glm::unpackHalf2x16(A.PackedData.w) * h.u) + (glm::unpackHalf2x16(B.PackedData.w) * h.v) + (glm::unpackHalf2x16(C.PackedData.w) * h.w);
+        }
+        out[i] = Mat48{normal.x, normal.y, normal.z, uv.x, uv.y, emissivity, alpha, h.mesh, {albedo.x, albedo.y, albedo.z}, glsl_prelude::g_sampled_id};
+        if (tex_uv) { tex_uv[2 * i] = glsl_prelude::g_sampled_uv.x; tex_uv[2 * i + 1] = glsl_prelude::g_sampled_uv.y; }
     }
     return 0;
 }

@@ -92,6 +92,21 @@ int main() {
         const float bmin[3] = {0.5f, -0.2f, 0.5f}, bmax[3] = {0.8f, 0.2f, 0.8f};
         std::printf("EXTRA data=%d collide=%d%d%d\n", n_data, (int)Candela::Physics::CollidePoint(on_floor, Intersector),
                     (int)Candela::Physics::CollidePoint(in_air, Intersector), (int)Candela::Physics::CollideBox(bmin, bmax, Intersector));
+        // GenerateMeshTextureReferences + GetData with the Albedo decision: mesh 5 textured (valid handle), the others plain
+        {
+            std::vector<Candela::FileLoader::_MeshMaterialData> mats(6);
+            for (int m = 0; m < 6; ++m) mats[m] = {0xA0u + m, 0xB0u, m == 5 ? 1 : 0, 0, {0.1f * m, 0.5f, 1.0f}, 0.0f};
+            Intersector.GenerateMeshTextureReferences(mats);
+            std::vector<Candela::HitMaterial> mat(hits.size());
+            Intersector.GetData(hits.data(), hits.size(), mat.data());
+            int n_tex = 0, n_same = 0;
+            for (std::size_t i = 0; i < hits.size(); ++i) {
+                if (hits[i].T > 0 && mat[i].AlbedoRef == Intersector.m_MeshTextureReferences[5].Albedo && mat[i].Albedo[0] == 0.0f) ++n_tex;
+                if (std::memcmp(&mat[i], &data[i], sizeof(data[i])) == 0) ++n_same;
+            }
+            std::printf("MATERIAL tex=%d same=%d handles=%zu ref5=%d ref0=%d\n", n_tex, n_same, Intersector.m_TextureHandles.size(),
+                        Intersector.m_MeshTextureReferences[5].Albedo, Intersector.m_MeshTextureReferences[0].Albedo);
+        }
         // BVH::BuildBVH as a free function (BVHConstructor.h:86-87): same bytes as the intersector's own buffers for its first object
         {
             std::vector<Candela::BVH::FlattenedNode> Nodes;

@@ -80,19 +80,24 @@ def test_obj_loader_reproduces_the_vertex_packing(cb, golden_meshes, tmp_path):
     # indices of a mesh stay inside its own vertex range (per-mesh join, offset applied like BVHConstructor.cpp:981-1002)
     tri_first = idx.reshape(-1, 3).min(1)
     assert tri_first[150] > idx.reshape(-1, 3)[:150].max() and tri_first[151:].min() > idx.reshape(-1, 3)[150].max()
-    # packing: data.x = packHalf2x16(n.xy), data.y = packHalf2x16(n.z, tan.x = 0), data.z = 0, texcoords = packHalf2x16(uv)
+    # packing: data.x = packHalf2x16(n.xy), data.y = packHalf2x16(n.z, tan.x), data.z = packHalf2x16(tan.yz), texcoords = packHalf2x16(uv)
     L = cb.api.load_library()
     src = F.reshape(-1)
+    halves = lambda u: np.array([u & 0xFFFF, u >> 16], dtype=np.uint16).view(np.float16).astype(np.float32)
     for k in rng.integers(0, len(idx), 300):
         v, s = verts[idx[k]], src[k]
         assert v["normal_tangent"][0] == L.cndl_pack_half2x16(float(N[s, 0]), float(N[s, 1]))
-        assert v["normal_tangent"][1] == L.cndl_pack_half2x16(float(N[s, 2]), 0.0) and v["normal_tangent"][2] == 0
+        assert (v["normal_tangent"][1] & 0xFFFF) == (L.cndl_pack_half2x16(float(N[s, 2]), 0.0) & 0xFFFF)
         assert v["texcoords"] == L.cndl_pack_half2x16(float(UV[s, 0]), float(np.float32(1.0) - UV[s, 1]))   # aiProcess_FlipUVs
+        # aiProcess_CalcTangentSpace: a unit tangent orthogonal to the corner's normal (to half precision)
+        t = np.array([halves(int(v["normal_tangent"][1]))[1], *halves(int(v["normal_tangent"][2]))])
+        assert abs(np.linalg.norm(t) - 1.0) < 2e-3 and abs(float(t @ N[s])) < 2e-3
     # quads and negative indices; no normals / UVs -> zeros
     q = tmp_path / "quad.obj"
     q.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nf -5 -4 -3 -2\ng top\nf 1 2 5\n")
     verts, idx, mids, names = cb.api.load_obj(q)
     assert len(idx) == 9 and list(mids) == [0, 0, 1] and names == ["default", "top"] and np.all(verts["texcoords"] == 0)
+    assert np.all(verts["normal_tangent"][:, 2] == 0) and np.all(verts["normal_tangent"][:, 1] >> 16 == 0)   # no UV channel: no tangents (ModelFileLoader.cpp:138-143)
     # aiProcess_GenNormals: no `vn` in the file -> the quad's corners carry its face normal (0, 0, 1), the other face (0, -1, 0);
     # the quad's four corners are joined across its two triangles
     L = cb.api.load_library()
@@ -166,7 +171,11 @@ def test_gltf_loader(cb, tmp_path, kind):
     assert np.array_equal(verts["position"][:4, :3], quad_p) and np.array_equal(verts["position"][4:7, :3], tri_p) and np.array_equal(verts["position"][7:, :3], quad_p)
     for k in range(4):
         assert verts["texcoords"][k] == L.cndl_pack_half2x16(float(quad_uv[k, 0]), float(np.float32(1) - quad_uv[k, 1]))      # FlipUVs
-        assert verts["normal_tangent"][k, 0] == L.cndl_pack_half2x16(0.0, 0.0) and verts["normal_tangent"][k, 1] == L.cndl_pack_half2x16(1.0, 0.0)
+        assert verts["normal_tangent"][k, 0] == L.cndl_pack_half2x16(0.0, 0.0) and (verts["normal_tangent"][k, 1] & 0xFFFF) == L.cndl_pack_half2x16(1.0, 0.0)
+        # aiProcess_CalcTangentSpace: a unit tangent in the quad's plane (normal = +z), pointing along +u = +x for this mapping
+        tan = np.array([int(verts["normal_tangent"][k, 1]) >> 16, int(verts["normal_tangent"][k, 2]) & 0xFFFF, int(verts["normal_tangent"][k, 2]) >> 16],
+                       dtype=np.uint16).view(np.float16).astype(np.float32)
+        assert abs(np.linalg.norm(tan) - 1.0) < 2e-3 and tan[2] == 0.0 and tan[0] > 0.5
     # the bare triangle gets its face normal: cross((0,3,0), (4,0,0)) = (0,0,-12) -> (0,0,-1)
     assert np.all(verts["normal_tangent"][4:7, 1] == L.cndl_pack_half2x16(-1.0, 0.0)) and np.all(verts["texcoords"][4:7] == L.cndl_pack_half2x16(0.0, 0.0))
 

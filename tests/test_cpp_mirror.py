@@ -38,6 +38,9 @@ def test_mirror_runs_the_reference_call_sequence():
     assert n_hit > 90 and abs(total - 3.0 * n_hit) < 1e-3      # floor at y = 0, rays from y = 3 straight down
     extra = [l for l in lines if l.startswith("EXTRA ")][0].split()
     assert extra[1] == f"data={n_hit}" and extra[2] == "collide=101"          # floor point collides, air point does not, box does
+    mat = [l for l in lines if l.startswith("MATERIAL ")][0].split()
+    # GenerateMeshTextureReferences: 6 albedo handles + 1 shared normal handle -> 7 indices, mesh 5 valid (index 6), mesh 0 not (-1)
+    assert mat[1:] == [f"tex={n_hit}", "same=100", "handles=7", "ref5=6", "ref0=-1"]
     build = [l for l in lines if l.startswith("BUILDBVH ")][0].split()
     assert build[1] == "same=1" and build[3] == "tris=576"                    # BVH::BuildBVH free function: same bytes as AddObject's buffers
     frame = [l for l in lines if l.startswith("FRAME ")][0].split()
