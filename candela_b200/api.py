@@ -74,7 +74,7 @@ class RaygenParams(C.Structure):
 
 
 FRAME_OUT_HIT32, FRAME_OUT_HIT16, FRAME_OUT_PIXEL32 = 0, 1, 2
-FRAME_OCTANT_ORDER, FRAME_LOCAL_LAYOUT = 1, 2
+FRAME_OCTANT_ORDER, FRAME_LOCAL_LAYOUT, FRAME_COMPACT_RAYS = 1, 2, 4
 TRANSPORT_PEER_STORES, TRANSPORT_STAGED_COPY = 0, 1
 HIT16_DT = np.dtype([("t", "<f4"), ("tri", "<i4"), ("v", "<f4"), ("w", "<f4")])
 PIXEL_DT = np.dtype([("t", "<f4"), ("tri", "<i4"), ("v", "<f4"), ("w", "<f4"), ("ao", "<f4"), ("t_mean", "<f4"), ("rays", "<i4"), ("escaped", "<i4")])
@@ -89,10 +89,12 @@ class FrameParams(C.Structure):
 
 
 def frame_params(inv_view, inv_proj, width: int, height: int, spp: int = 1, bounces: int = 1, seed: int = 1, tile: int = 0, shard_index: int = 0,
-                 shard_count: int = 1, out_format: int = FRAME_OUT_HIT16, octant_order: bool = False, local_layout: bool = False) -> FrameParams:
-    """inv_view / inv_proj: 4x4 (row, column) matrices, as IntersectPrimary takes them."""
+                 shard_count: int = 1, out_format: int = FRAME_OUT_HIT16, octant_order: bool = False, local_layout: bool = False,
+                 compact_rays: bool = False) -> FrameParams:
+    """inv_view / inv_proj: 4x4 (row, column) matrices, as IntersectPrimary takes them.  compact_rays: the three-pass compacting
+    generator instead of the one-pass segmented one (same results)."""
     iv, ip = _colmajor(inv_view), _colmajor(inv_proj)
-    flags = (FRAME_OCTANT_ORDER if octant_order else 0) | (FRAME_LOCAL_LAYOUT if local_layout else 0)
+    flags = (FRAME_OCTANT_ORDER if octant_order else 0) | (FRAME_LOCAL_LAYOUT if local_layout else 0) | (FRAME_COMPACT_RAYS if compact_rays else 0)
     return FrameParams((C.c_float * 16)(*iv), (C.c_float * 16)(*ip), width, height, spp, bounces, seed, tile, shard_index, shard_count, out_format, flags)
 
 

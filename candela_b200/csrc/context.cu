@@ -66,21 +66,22 @@ unsigned* next_counter(cndl_ctx* ctx) {
 // Enqueues one traversal batch on `st`.  scratch: 16 unsigned ints ([0] work counter, [8..15] octant counts);
 // order_region: order_region_ints(R) unsigned ints, used when ray bucketing is on.
 int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, const unsigned* d_R, cndl_hit* d_hits, float* d_any, unsigned* scratch,
-                  unsigned* order_region, cndl_ray* sorted_region, cudaStream_t st) {
+                  unsigned* order_region, cndl_ray* sorted_region, cudaStream_t st, const RayOrder* preset) {
     if (R > 0xFFFFFFF0ull) return ctx->fail(CNDL_ERR_INVALID, "more than 2^32-16 rays in one call");
     if ((reinterpret_cast<uintptr_t>(d_rays) & 31u) || (reinterpret_cast<uintptr_t>(d_hits) & 31u))
         return ctx->fail(CNDL_ERR_INVALID, "ray and hit buffers must be 32-byte aligned (the kernels move each record with one 256-bit access)");
-    if (d_R && ctx->mode != 2) return ctx->fail(CNDL_ERR_INVALID, "a device-side batch length needs traversal mode 2");
+    if ((d_R || preset) && ctx->mode != 2) return ctx->fail(CNDL_ERR_INVALID, "a device-side batch length needs traversal mode 2");
     const SceneView s = scene_view(ctx);
     const bool stack = ctx->format == CNDL_STACK;
     if (ctx->mode == 0 || (stack && ctx->mode == 1)) launch_trace_simple(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, st, ctx->launches);
     else if (ctx->mode == 1) launch_trace_persistent(s, stack, kind, d_rays, R, nullptr, d_hits, d_any, scratch, ctx->sm_count, st, ctx->launches);
     else {
-        RayOrder order{nullptr, nullptr, 0, d_R, nullptr};
+        RayOrder order{nullptr, nullptr, 0, d_R, nullptr, nullptr};
+        if (preset) order = *preset;
         // sort_rays 4 (the default) decides by the scene: once nodes + triangle records no longer fit the L2, ordering a large batch by
         // (octant, origin cell) pays for itself (10 M triangles, 12.5 M random rays: 5.36 -> 4.71 ms with the sort counted)
         const int sort_mode = effective_sort(ctx, R);
-        if (sort_mode && order_region && R >= 65536 && !d_R) {
+        if (sort_mode && order_region && R >= 65536 && !d_R && !preset) {
             if (sort_mode >= 2) {
                 // 2: the rays are MOVED into sorted order (sorted_region) and the results scattered back through the index list;
                 // 3: the rays stay and are read through the index list
@@ -106,7 +107,7 @@ int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, con
             const size_t working_set = ctx->committed_nodes * ctx->node_size + ctx->committed_tris * 48;
             // ... unless the batch has just been ordered: neighbouring rays then share nodes, L2 hits rise and the plain kernel's
             // higher residency wins (10 M triangles: 4.71 vs 5.03 ms)
-            variant = (!stack && working_set > ((size_t)96 << 20) && !(sort_mode >= 2 && order_region && R >= 65536 && !d_R)) ? 34 : 18;
+            variant = (!stack && working_set > ((size_t)96 << 20) && !(sort_mode >= 2 && order_region && R >= 65536 && !d_R && !preset)) ? 34 : 18;
         }
         int steps = variant & 7;
         if (steps < 1 || steps > 4) steps = 2;

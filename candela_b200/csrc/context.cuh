@@ -55,7 +55,7 @@ struct ObjectData { int tri_offset, vert_offset, node_offset, node_count, tri_co
 // Scratch of one frame in flight (frame.cu): two of these per context, so that the device->host copy of one frame overlaps
 // the tracing of the next.
 struct FrameSlot {
-    DeviceBuffer prim_rays, prim_hits, pix_ids, rays[2], hits, rids[2], gen_scratch, acc, out, counts;
+    DeviceBuffer prim_rays, prim_hits, pix_ids, rays[2], hits, rids[2], gen_scratch, acc, out, counts, oct_list;
     unsigned* h_counts = nullptr;      // pinned: rays traced per bounce, copied back with the frame
     int n_counts = 0;
     cudaEvent_t traced = nullptr, copied = nullptr;
@@ -137,9 +137,11 @@ size_t order_region_ints(size_t R);
 int effective_sort(const cndl_ctx* ctx, size_t R);
 int check_ready(cndl_ctx* ctx);
 // Enqueues one traversal batch on `st`.  scratch: 16 unsigned ints ([0] work counter); order_region: order_region_ints(R)
-// unsigned ints, used when ray ordering is on; d_R (optional): the batch length in device memory, R being its upper bound.
+// unsigned ints, used when ray ordering is on; d_R (optional): the batch length in device memory, R being its upper bound;
+// preset (optional): the caller has already ordered the batch (the frame call's generator writes segmented batches and octant
+// lists): the launch takes this RayOrder as it is and d_R / the in-call ordering are ignored.
 int enqueue_trace(cndl_ctx* ctx, int kind, const cndl_ray* d_rays, size_t R, const unsigned* d_R, cndl_hit* d_hits, float* d_any, unsigned* scratch,
-                  unsigned* order_region, cndl_ray* sorted_region, cudaStream_t st);
+                  unsigned* order_region, cndl_ray* sorted_region, cudaStream_t st, const cndl::RayOrder* preset = nullptr);
 // One 64-byte work-counter slot from the context's ring: device calls in flight on different streams never share one.
 unsigned* next_counter(cndl_ctx* ctx);
 }  // namespace cndl

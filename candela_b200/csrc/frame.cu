@@ -133,12 +133,16 @@ __global__ void frame_first_bounce_kernel(unsigned P, int spp, const unsigned ch
     q[1] = make_float4(px.ao, px.t_mean, __int_as_float(px.rays), __int_as_float(px.escaped));
 }
 
-// PIXEL32, bounce b >= 1: integer counts only (order-independent, so the result does not depend on scheduling).
-__global__ void frame_accumulate_kernel(TileMap tm, int spp, unsigned cap, const unsigned* __restrict__ d_count, const unsigned* __restrict__ rids,
-                                        const cndl_hit* __restrict__ hits, cndl_pixel* __restrict__ acc) {
+// PIXEL32, bounce b >= 1: integer counts only (order-independent, so the result does not depend on scheduling).  The batch is
+// either compact (d_count rays) or segmented (seg_counts).
+__global__ void frame_accumulate_kernel(TileMap tm, int spp, unsigned cap, const unsigned* __restrict__ d_count, const unsigned* __restrict__ seg_counts,
+                                        const unsigned* __restrict__ rids, const cndl_hit* __restrict__ hits, cndl_pixel* __restrict__ acc) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned n = min(cap, __ldg(d_count));
-    if (k >= n) return;
+    if (seg_counts) {
+        if (k >= cap || (k & (unsigned)(kRaySegment - 1)) >= __ldg(seg_counts + (k >> kRaySegmentShift))) return;
+    } else if (k >= min(cap, __ldg(d_count))) {
+        return;
+    }
     const unsigned slot = pixel_to_slot(tm, __ldg(rids + k) / (unsigned)spp);
     atomicAdd(&acc[slot].rays, 1);
     if (!(__ldg(&hits[k].t) > 0.0f)) atomicAdd(&acc[slot].escaped, 1);
@@ -245,7 +249,13 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
     CK(f.hits.ensure_scratch(cap * sizeof(cndl_hit)));
     CK(f.rids[0].ensure_scratch(cap * sizeof(unsigned)));
     CK(f.gen_scratch.ensure_scratch(generate_rays_scratch_ints(P, spp) * sizeof(int)));  // bounce 0: P inputs x spp; later: cap inputs x 1
-    CK(f.counts.ensure_scratch(64));
+    const bool tiled = !(p->flags & CNDL_FRAME_COMPACT_RAYS);
+    const size_t n_seg = (cap + kRaySegment - 1) / kRaySegment;
+    // counts: [0..kMaxBounces) rays per bounce; [16 + 8 b ..) the octant cursors of bounce b; then two arrays of per-segment live counts
+    constexpr size_t kCountHeader = 16 + 8 * kMaxBounces;
+    CK(f.counts.ensure_scratch((kCountHeader + 2 * n_seg) * sizeof(unsigned)));
+    const bool oct_lists = tiled && (p->flags & CNDL_FRAME_OCTANT_ORDER);
+    if (oct_lists) CK(f.oct_list.ensure_scratch(8 * cap * sizeof(unsigned)));
     if (p->bounces > 1) {
         CK(f.rays[1].ensure_scratch(cap * sizeof(cndl_ray)));
         CK(f.rids[1].ensure_scratch(cap * sizeof(unsigned)));
@@ -259,7 +269,9 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
     cndl_hit* prim_hits = static_cast<cndl_hit*>(f.prim_hits.p);
     unsigned* pix_ids = static_cast<unsigned*>(f.pix_ids.p);
     unsigned* counts = static_cast<unsigned*>(f.counts.p);
+    unsigned* seg[2] = {counts + kCountHeader, counts + kCountHeader + n_seg};
     const unsigned g256 = (unsigned)((P + 255) / 256);
+    if (tiled) CK(cudaMemsetAsync(counts, 0, kCountHeader * sizeof(unsigned), st));
     frame_primary_kernel<<<g256, 256, 0, st>>>(m, tm, (unsigned)P, prim, pix_ids);
     ctx->launches.n++;
     rc = enqueue_trace(ctx, Q_CLOSEST, prim, P, nullptr, prim_hits, nullptr, next_counter(ctx), nullptr, nullptr, st);
@@ -284,13 +296,25 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
         g.offset = b == 0 ? 0.05f : 0.02f;                                   // DiffuseTrace.glsl:445, :516
         g.d_ids_in = b == 0 ? pix_ids : static_cast<const unsigned*>(f.rids[(b - 1) & 1].p);
         g.d_ids_out = out_ids;
-        const unsigned* d_count = nullptr;
-        CK(generate_rays(sv, g, src_rays, src_hits, src_cap, src_count, out_rays, nullptr, static_cast<int*>(f.gen_scratch.p), &d_count, nullptr, st,
-                         ctx->launches));
-        frame_count_kernel<<<1, 1, 0, st>>>(d_count, (unsigned)cap, counts + b);  // the scratch total is overwritten by the next bounce
-        ctx->launches.n++;
-        rc = enqueue_trace(ctx, b == 0 ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST, out_rays, cap, counts + b, hits, nullptr, next_counter(ctx), nullptr,
-                           nullptr, st);                                              // :484 IntersectRayIgnoreTransparent, :518 IntersectRay
+        const int kind = b == 0 ? Q_CLOSEST_IGNORE_TRANSPARENT : Q_CLOSEST;         // :484 IntersectRayIgnoreTransparent, :518 IntersectRay
+        if (tiled) {
+            // one pass: rays ordered inside 1024-slot segments, dead slots at each segment's end (counts[b] accumulates the live ones)
+            unsigned* cursor = counts + 16 + 8 * b;
+            unsigned* list = oct_lists ? static_cast<unsigned*>(f.oct_list.p) : nullptr;
+            CK(generate_rays_tiled(sv, g, src_rays, src_hits, src_cap, b == 0 ? nullptr : seg[(b - 1) & 1], out_rays, static_cast<int*>(f.gen_scratch.p),
+                                   seg[b & 1], counts + b, cursor, list, cap, st, ctx->launches));
+            // octant order: the launch walks the eight lists one after the other (all resident warps in one octant at a time); otherwise the
+            // segments in place
+            const RayOrder ro = oct_lists ? RayOrder{list, cursor, (unsigned)cap, counts + b, nullptr, nullptr} : RayOrder{nullptr, nullptr, 0, nullptr, nullptr, seg[b & 1]};
+            rc = enqueue_trace(ctx, kind, out_rays, cap, nullptr, hits, nullptr, next_counter(ctx), nullptr, nullptr, st, &ro);
+        } else {
+            const unsigned* d_count = nullptr;
+            CK(generate_rays(sv, g, src_rays, src_hits, src_cap, src_count, out_rays, nullptr, static_cast<int*>(f.gen_scratch.p), &d_count, nullptr, st,
+                             ctx->launches));
+            frame_count_kernel<<<1, 1, 0, st>>>(d_count, (unsigned)cap, counts + b);  // the scratch total is overwritten by the next bounce
+            ctx->launches.n++;
+            rc = enqueue_trace(ctx, kind, out_rays, cap, counts + b, hits, nullptr, next_counter(ctx), nullptr, nullptr, st);
+        }
         if (rc != CNDL_OK) return rc;
         if (b == 0) {
             const unsigned char* keys;
@@ -308,7 +332,7 @@ int cndl_trace_frame_device(cndl_ctx* ctx, const cndl_frame_params* p, void* d_o
             }
             ctx->launches.n++;
         } else {
-            frame_accumulate_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(tm, spp, (unsigned)cap, counts + b, out_ids, hits,
+            frame_accumulate_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(tm, spp, (unsigned)cap, counts + b, tiled ? seg[b & 1] : nullptr, out_ids, hits,
                                                                                  static_cast<cndl_pixel*>(f.acc.p));
             ctx->launches.n++;
         }

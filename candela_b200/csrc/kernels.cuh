@@ -79,6 +79,9 @@ cudaError_t generate_rays(const SceneView& s, const cndl_raygen_params& prm, con
                           LaunchCounter& lc);
 // element e = i * spp + s of the last generate_rays call on `scratch`: keys[e] < 8 iff it produced a ray, stored at dest[e]
 void generate_rays_maps(int* scratch, size_t R, int spp, const unsigned char** keys, const unsigned** dest);
+cudaError_t generate_rays_tiled(const SceneView& s, const cndl_raygen_params& prm, const cndl_ray* rays, const cndl_hit* hits, size_t R,
+                                const unsigned* in_seg_counts, cndl_ray* out, int* scratch, unsigned* seg_counts, unsigned* total, unsigned* oct_cursor,
+                                unsigned* oct_list, size_t oct_stride, cudaStream_t stream, LaunchCounter& lc);
 // Probe-update rays (UpdateRadianceProbes.glsl:408-427), one per probe of a res[0] x res[1] x res[2] grid.
 void launch_probe_rays(const float box_origin[3], const float size[3], const int res[3], unsigned seed, cndl_ray* out, cudaStream_t stream, LaunchCounter& lc);
 

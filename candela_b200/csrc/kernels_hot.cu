@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) trace_hot_stackless_kerne
                     if (base + (unsigned)n >= R) drained = true;
                     if (L.state == EMPTY) {
                         const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
-                        if (slot < R) {
+                        if (slot_live(order, slot, R)) {
                             L.rid = ray_of_slot(order, slot);
                             L.closest = -1.0f;
                             L.best_tri = -1;
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(128, MINB) trace_pair_stackless_kernel(SceneVi
                     if (base + (unsigned)n >= R) drained = true;
                     if (sel >= 0 && T.state == EMPTY) {
                         const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
-                        if (slot < R) {
+                        if (slot_live(order, slot, R)) {
                             T.rid = ray_of_slot(order, slot);
                             T.best_tri = -1;
                             T.best_ent = -1;

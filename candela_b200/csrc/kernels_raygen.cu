@@ -318,6 +318,94 @@ __global__ void gen_emit_kernel(GenParams g, const cndl_ray* __restrict__ rays, 
     }
 }
 
+// The generator of the frame-level call: one CTA per kRaySegment potential rays (element e = input slot * spp + sample).  Every
+// thread forms its four rays ONCE, the CTA orders them by direction octant (a stable counting sort over nine keys — ballots per
+// warp, one scan of the 9 x 32 partial counts) and writes them into ITS segment of the output, live rays first.  No global scan,
+// no second evaluation of the sample: the traversal learns which slots of a segment are live from seg_counts[segment]
+// (RayOrder::seg_counts), and consecutive slots of a segment hold rays of one octant from neighbouring pixels.
+// in_seg_counts (optional): the input batch is itself such a segmented batch (a further bounce).
+__global__ void __launch_bounds__(256) gen_tile_kernel(GenParams g, const cndl_ray* __restrict__ rays, const cndl_hit* __restrict__ hits,
+                                                       const unsigned* __restrict__ ids, const float4* __restrict__ tri48, const cndl_entity* __restrict__ ents,
+                                                       const unsigned* __restrict__ in_seg_counts, unsigned n_elems, unsigned char* __restrict__ keys,
+                                                       unsigned* __restrict__ dest, cndl_ray* __restrict__ out, unsigned* __restrict__ ids_out,
+                                                       unsigned* __restrict__ seg_counts, unsigned* __restrict__ total, unsigned* __restrict__ oct_cursor,
+                                                       unsigned* __restrict__ oct_list, unsigned oct_stride) {
+    constexpr int ROUNDS = kRaySegment / 256;
+    __shared__ int s_cnt[9 * 8 * ROUNDS];  // [key][round * 8 + warp]
+    __shared__ unsigned s_oct_base[8];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, wp = tid >> 5;
+    const unsigned cta_base = blockIdx.x * (unsigned)kRaySegment;
+    for (unsigned k = tid; k < 9u * 8u * ROUNDS; k += 256) s_cnt[k] = 0;
+    __syncthreads();
+    float4 o[ROUNDS], d[ROUNDS];
+    unsigned key[ROUNDS], rank[ROUNDS], element[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const unsigned e = cta_base + (unsigned)r * 256u + tid;
+        key[r] = 8;
+        element[r] = 0;
+        if (e < n_elems) {
+            const unsigned i = e / (unsigned)g.spp, smp = e - i * (unsigned)g.spp;
+            const bool live = !in_seg_counts || (i & (unsigned)(kRaySegment - 1)) < __ldg(in_seg_counts + (i >> kRaySegmentShift));
+            if (live) {
+                const HitFrame f = hit_frame(rays, hits, tri48, ents, i);
+                const unsigned id = ids ? __ldg(ids + i) : i;
+                element[r] = id * (unsigned)g.spp + smp;
+                if (f.valid && gen_ray(g, f, element[r], o[r], d[r]))
+                    key[r] = g.bucket ? ((d[r].x > 0.0f ? 1u : 0u) | (d[r].y > 0.0f ? 2u : 0u) | (d[r].z > 0.0f ? 4u : 0u)) : 0u;
+            }
+        }
+        const unsigned same = __match_any_sync(0xFFFFFFFFu, key[r]);
+        rank[r] = (unsigned)__popc(same & ((1u << lane) - 1u));
+        if (rank[r] == 0) s_cnt[key[r] * (8 * ROUNDS) + r * 8 + wp] = __popc(same);
+    }
+    __syncthreads();
+    if (wp == 0) {  // exclusive scan of the 9 * 8 * ROUNDS counts in (key, round, warp) order: 9 * ROUNDS / 4 entries per lane
+        constexpr int PER = 9 * 8 * ROUNDS / 32;
+        int v[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { v[k] = s_cnt[lane * PER + k]; sum += v[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int up = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if ((int)lane >= off) incl += up;
+        }
+        int run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { s_cnt[lane * PER + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    const unsigned n_live = (unsigned)s_cnt[8 * (8 * ROUNDS)];  // where key 8 (no ray) begins
+    if (oct_list) {
+        // octant-major over the WHOLE batch without a global scan: the segment's run of octant o is appended to the batch's list of
+        // octant o (one atomic per run; the lists are RayOrder's bucketed form).  Which segment comes first inside an octant depends
+        // on scheduling; results do not.
+        if (tid < 8) {
+            const unsigned n = (unsigned)(s_cnt[(tid + 1) * (8 * ROUNDS)] - s_cnt[tid * (8 * ROUNDS)]);
+            s_oct_base[tid] = n ? atomicAdd(oct_cursor + tid, n) : 0u;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const unsigned e = cta_base + (unsigned)r * 256u + tid;
+        if (e >= n_elems) continue;
+        keys[e] = (unsigned char)key[r];
+        if (key[r] >= 8) continue;
+        const unsigned in_seg = (unsigned)s_cnt[key[r] * (8 * ROUNDS) + r * 8 + wp] + rank[r];
+        const unsigned pos = cta_base + in_seg;
+        dest[e] = pos;
+        if (oct_list) oct_list[(size_t)key[r] * oct_stride + s_oct_base[key[r]] + (in_seg - (unsigned)s_cnt[key[r] * (8 * ROUNDS)])] = pos;
+        stg256(reinterpret_cast<float4*>(out + pos), o[r], d[r]);
+        if (ids_out) ids_out[pos] = element[r];
+    }
+    if (tid == 0) {
+        seg_counts[blockIdx.x] = n_live;
+        if (n_live) atomicAdd(total, n_live);
+    }
+}
+
 // Probe-update rays (UpdateRadianceProbes.glsl:408-427): probe (x, y, z) of a res.x * res.y * res.z grid -> ray index
 // (z * res.y + y) * res.x + x; RayOrigin = u_BoxOrigin + (vec3(Pixel) / u_Resolution * 2 - 1) * u_Size; direction =
 // ImportanceSample() with its importance branch off = normalize(LambertBRDF(vec3(hash2(), hash2().x))) (:365-374).
@@ -447,6 +535,33 @@ cudaError_t generate_rays(const SceneView& s, const cndl_raygen_params& prm, con
         if (e != cudaSuccess) return e;
         *h_count = (size_t)h_total;
     }
+    return cudaGetLastError();
+}
+
+// The segmented variant (gen_tile_kernel): element e's ray lands inside segment e / kRaySegment of `out`; seg_counts[segment] = live
+// rays of the segment, *total += all of them (the caller zeroes it).  keys / dest are left in `scratch` like generate_rays does.
+// oct_list (optional, with CNDL_GEN_BUCKET_OCTANTS): 8 lists of oct_stride entries each; list o receives the positions of the rays of
+// octant o, oct_cursor[o] (zeroed by the caller) their number.
+cudaError_t generate_rays_tiled(const SceneView& s, const cndl_raygen_params& prm, const cndl_ray* rays, const cndl_hit* hits, size_t R,
+                                const unsigned* in_seg_counts, cndl_ray* out, int* scratch, unsigned* seg_counts, unsigned* total, unsigned* oct_cursor,
+                                unsigned* oct_list, size_t oct_stride, cudaStream_t stream, LaunchCounter& lc) {
+    if (R == 0) return cudaSuccess;
+    GenParams g;
+    g.kind = prm.kind;
+    g.spp = prm.spp;
+    g.bucket = (prm.flags & CNDL_GEN_BUCKET_OCTANTS) ? 1 : 0;
+    g.seed = prm.seed;
+    g.offset = prm.offset;
+    g.tmax = prm.tmax;
+    g.roughness = prm.roughness;
+    g.lx = prm.light_dir[0]; g.ly = prm.light_dir[1]; g.lz = prm.light_dir[2];
+    g.cone = prm.light_cone;
+    const size_t n = R * (size_t)prm.spp;
+    unsigned char* keys = reinterpret_cast<unsigned char*>(scratch);
+    unsigned* dest = reinterpret_cast<unsigned*>(scratch + (n + 3) / 4);
+    gen_tile_kernel<<<(unsigned)((n + kRaySegment - 1) / kRaySegment), 256, 0, stream>>>(g, rays, hits, prm.d_ids_in, s.tri48, s.ents, in_seg_counts, (unsigned)n, keys,
+                                                                                       dest, out, prm.d_ids_out, seg_counts, total, oct_cursor, oct_list, (unsigned)oct_stride);
+    lc.n++;
     return cudaGetLastError();
 }
 

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128, MINB) trace_ww_stackless_kernel(SceneView
                     if (base + (unsigned)n >= R) drained = true;
                     if (L.state == EMPTY) {
                         const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
-                        if (slot < R) {
+                        if (slot_live(order, slot, R)) {
                             L.rid = ray_of_slot(order, slot);
                             L.best_tri = -1;
                             L.best_ent = -1;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(128, 8) trace_ww_stack_kernel(SceneView s, con
                     if (base + (unsigned)n >= R) drained = true;
                     if (L.state == EMPTY) {
                         const unsigned slot = base + (unsigned)__popc(want & ((1u << lane) - 1u));
-                        if (slot < R) {
+                        if (slot_live(order, slot, R)) {
                             L.rid = ray_of_slot(order, slot);
                             L.best_tri = -1;
                             L.best_ent = -1;

@@ -36,7 +36,15 @@ struct RayOrder {
     unsigned stride;
     const unsigned* __restrict__ d_count;  // optional: the batch length in device memory (the launch's R is then its upper bound)
     const unsigned* __restrict__ out_index;  // optional: the batch was physically reordered; the result of ray slot i belongs at out_index[i]
+    const unsigned* __restrict__ seg_counts;  // optional: the batch is cut into segments of kRaySegment slots; only the first seg_counts[k] slots of segment k hold rays
 };
+constexpr int kRaySegmentShift = 10, kRaySegment = 1 << kRaySegmentShift;
+
+// Does launch slot `slot` hold a ray?  (R: the batch length; segmented batches keep their dead slots at the end of every segment.)
+__device__ __forceinline__ bool slot_live(const RayOrder& ro, unsigned slot, unsigned R) {
+    if (slot >= R) return false;
+    return !ro.seg_counts || (slot & (unsigned)(kRaySegment - 1)) < __ldg(ro.seg_counts + (slot >> kRaySegmentShift));
+}
 
 __device__ __forceinline__ unsigned out_slot(const RayOrder& ro, unsigned rid) { return ro.out_index ? __ldg(ro.out_index + rid) : rid; }
 

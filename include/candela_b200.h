@@ -234,8 +234,11 @@ int cndl_generate_probe_rays_device(cndl_ctx* ctx, const float box_origin[3], co
 enum { CNDL_FRAME_OUT_HIT32 = 0,   /* cndl_hit of the diffuse ray of every (pixel, sample); bounces must be 1 */
        CNDL_FRAME_OUT_HIT16 = 1,   /* the same as cndl_hit16 */
        CNDL_FRAME_OUT_PIXEL32 = 2  /* one resolved cndl_pixel per pixel, any number of bounces */ };
-enum { CNDL_FRAME_OCTANT_ORDER = 1, /* every generated batch is emitted octant-major (CNDL_GEN_BUCKET_OCTANTS); results do not depend on it */
-       CNDL_FRAME_LOCAL_LAYOUT = 2 };
+enum { CNDL_FRAME_OCTANT_ORDER = 1, /* every generated batch is ordered by direction octant (inside each 1024-ray segment; with
+                                      * CNDL_FRAME_COMPACT_RAYS: over the whole batch); results do not depend on it */
+       CNDL_FRAME_LOCAL_LAYOUT = 2,
+       CNDL_FRAME_COMPACT_RAYS = 4  /* generate through the three-pass compacting generator (cndl_generate_rays_device) instead of the
+                                      * one-pass segmented one; results do not depend on it */ };
 /* Compact hit: t, tri and the barycentric weights of vertices B and C (cndl_hit.v, .w; u = 1 - v - w in that order of
  * operations); mesh = triangle[tri].mesh.  Scenes with several entities need the 32-byte form (entity is not carried). */
 typedef struct cndl_hit16 { float t; int32_t tri; float v, w; } cndl_hit16;

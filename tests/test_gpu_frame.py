@@ -53,10 +53,11 @@ def test_frame_hit_formats_equal_the_oracle(cb, ob, dragon2):
     assert 0.1 * W * H * spp < traced < W * H * spp and np.count_nonzero(want32["entity"] == 1) == 0   # the translucent copy is skipped (:484 IgnoreTransparent)
     for octant in (False, True):
         for tile in (32, 64, 7):
-            p = cb.frame_params(iv, ip, W, H, spp=spp, seed=5, tile=tile, out_format=api.FRAME_OUT_HIT32, octant_order=octant)
-            got = ri.TraceFrame(p)
-            assert got.tobytes() == want32.tobytes(), (octant, tile)
-            assert ri.frame_rays_traced(0) == traced
+            for compact in (False, True):                    # the one-pass segmented generator (default) and the three-pass compacting one
+                p = cb.frame_params(iv, ip, W, H, spp=spp, seed=5, tile=tile, out_format=api.FRAME_OUT_HIT32, octant_order=octant, compact_rays=compact)
+                got = ri.TraceFrame(p)
+                assert got.tobytes() == want32.tobytes(), (octant, tile, compact)
+                assert ri.frame_rays_traced(0) == traced
     want16, _ = _oracle_frame(ob, dragon2, iv, ip, W, H, spp=spp, seed=5, out_format=1)
     got16 = ri.TraceFrame(cb.frame_params(iv, ip, W, H, spp=spp, seed=5, out_format=api.FRAME_OUT_HIT16))
     assert got16.dtype.itemsize == 16 and got16.tobytes() == want16.tobytes()
@@ -72,9 +73,10 @@ def test_frame_pixels_multibounce_equal_the_oracle(cb, ob, dragon2):
     iv, ip = _camera(W, H)
     for spp, bounces, seed in ((3, 3, 11), (1, 1, 2), (8, 4, 77)):
         want, traced = _oracle_frame(ob, dragon2, iv, ip, W, H, spp=spp, bounces=bounces, seed=seed, out_format=2)
-        for octant in (False, True):
-            got = ri.TraceFrame(cb.frame_params(iv, ip, W, H, spp=spp, bounces=bounces, seed=seed, tile=32, out_format=api.FRAME_OUT_PIXEL32, octant_order=octant))
-            assert got.tobytes() == want.tobytes(), (spp, bounces, octant)
+        for octant, compact in ((False, False), (True, False), (False, True), (True, True)):
+            got = ri.TraceFrame(cb.frame_params(iv, ip, W, H, spp=spp, bounces=bounces, seed=seed, tile=32, out_format=api.FRAME_OUT_PIXEL32, octant_order=octant,
+                                                compact_rays=compact))
+            assert got.tobytes() == want.tobytes(), (spp, bounces, octant, compact)
             assert ri.frame_rays_traced(0) == traced == int(got["rays"].sum())
     assert got["ao"].min() >= 0.0 and got["ao"].max() <= 1.0 and np.count_nonzero(got["escaped"]) > 0
 

@@ -77,6 +77,39 @@ def main():
     out["d2h_ms"] = timed(lambda: t.copy_(d_out, non_blocking=True), args.reps)
     out["d2h_GBs"] = round(len(d_out) / out["d2h_ms"] / 1e6, 1)
     print(json.dumps(out))
+    # generator variants: one frame on one stream, and frames pipelined through cndl_frame_submit (3 in flight, records to pinned host memory)
+    import time
+    F = 3
+    pins = [cb.PinnedBuffer(ri.frame_records(p), api.HIT16_DT if args.fmt == api.FRAME_OUT_HIT16 else (api.PIXEL_DT if args.fmt == api.FRAME_OUT_PIXEL32 else api.HIT_DT))
+            for _ in range(F)]
+    for octant in (0, 1):
+        for compact in (0, 1):
+            mk = lambda seed: cb.frame_params(iv, ip, W, H, spp=args.spp, bounces=args.bounces, seed=seed, out_format=args.fmt, octant_order=bool(octant),
+                                              compact_rays=bool(compact))
+            pv = mk(5)
+            for _ in range(3):
+                ri.trace_frame_device(pv, d_out.data_ptr(), 0, stream)
+            torch.cuda.synchronize()
+            one = timed(lambda: ri.trace_frame_device(pv, d_out.data_ptr(), 0, stream), args.reps)
+            n_frames = 600
+            for k in range(2 * F):
+                ri.frame_submit(mk(k), pins[k % F].array, k % F)
+            for sl in range(F):
+                ri.frame_wait(sl)
+            rays = 0
+            t0 = time.perf_counter()
+            for k in range(n_frames):
+                sl = k % F
+                if k >= F:
+                    ri.frame_wait(sl)
+                    rays += ri.frame_rays_traced(sl)
+                ri.frame_submit(mk(100 + k), pins[sl].array, sl)
+            for k in range(n_frames - F, n_frames):
+                ri.frame_wait(k % F)
+                rays += ri.frame_rays_traced(k % F)
+            dt = time.perf_counter() - t0
+            print(json.dumps(dict(octant=octant, compact_rays=compact, frame_ms=round(one, 4), pipelined_ms_per_frame=round(dt / n_frames * 1e3, 4),
+                                  pipelined_mrays_s=round(rays / dt / 1e6, 1))), flush=True)
 
 
 if __name__ == "__main__":
