@@ -51,6 +51,7 @@ EXPORTS = [
     "cndl_multi_commit", "cndl_multi_push_entity", "cndl_multi_buffer_entities", "cndl_multi_frame_submit", "cndl_multi_frame_wait",
     "cndl_multi_trace_frame", "cndl_multi_frame_rays_traced", "cndl_multi_last_replicate_ms", "cndl_clone_scene", "cndl_add_prebuilt_object_device",
     "cndl_object_device_view", "cndl_multi_set_transport", "cndl_object_count", "cndl_object_ids",
+    "cndl_ipc_alloc", "cndl_ipc_open", "cndl_ipc_close", "cndl_ipc_free",
     "cndl_generate_texture_references", "cndl_set_texture_references", "cndl_texture_reference_count", "cndl_get_data_material", "cndl_get_data_material_device",
     "cndl_model_mesh_albedo_path", "cndl_model_mesh_normal_path", "cndl_model_mesh_color",
 ]
@@ -151,6 +152,10 @@ def load_library() -> C.CDLL:
     L.cndl_generate_bounce_rays_device.argtypes = [vp, vp, vp, sz, C.c_int, C.c_float, C.c_float, C.c_uint32, vp, vp, C.POINTER(sz), vp]
     L.cndl_get_data.argtypes = [vp, vp, sz, vp]
     L.cndl_get_data_device.argtypes = [vp, vp, sz, vp, vp]
+    L.cndl_ipc_alloc.argtypes = [vp, sz, C.POINTER(vp), vp]
+    L.cndl_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.cndl_ipc_close.argtypes = [vp, vp]
+    L.cndl_ipc_free.argtypes = [vp, vp]
     L.cndl_get_data_material.argtypes = [vp, vp, sz, vp]
     L.cndl_get_data_material_device.argtypes = [vp, vp, sz, vp, vp]
     L.cndl_set_texture_references.argtypes = [vp, vp, sz]
@@ -527,6 +532,25 @@ class RayIntersector:
         out = np.zeros(len(hits), dtype=ATTR_DT)
         self._check(self._lib.cndl_get_data(self._h, _p(hits), len(hits), _p(out)))
         return out
+
+    def ipc_alloc(self, nbytes: int):
+        """cndl_ipc_alloc -> (device pointer, 64 handle bytes): memory other processes of the node can map (ipc_open) and store into."""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self._check(self._lib.cndl_ipc_alloc(self._h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self._lib.cndl_ipc_open(self._h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self._lib.cndl_ipc_close(self._h, ptr))
+
+    def ipc_free(self, ptr: int):
+        self._check(self._lib.cndl_ipc_free(self._h, ptr))
 
     def SetTextureReferences(self, refs):
         """Uploads the BVHTextureReferences table (m_BVHTextureReferencesSSBO, Intersector.h:404-409)."""

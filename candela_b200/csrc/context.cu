@@ -916,6 +916,57 @@ int cndl_load(cndl_ctx* ctx, const char* path) try {
     return CNDL_OK;
 } CNDL_CATCH
 
+// Peer memory across processes (one process per GPU): a plain cudaMalloc allocation exported with cudaIpcGetMemHandle; another
+// process on the node maps it with cudaIpcOpenMemHandle (peer access is enabled lazily) and its kernels store into it over NVLink.
+int cndl_ipc_alloc(cndl_ctx* ctx, size_t bytes, void** d_ptr, cndl_ipc_handle* handle) try {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!d_ptr || !handle || bytes == 0) return ctx->fail(CNDL_ERR_INVALID, "null output or zero size");
+    *d_ptr = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == sizeof(handle->bytes), "cudaIpcMemHandle_t is 64 bytes");
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return ctx->cuda_fail(e, "cudaIpcGetMemHandle");
+    }
+    std::memcpy(handle->bytes, &h, sizeof(h));
+    *d_ptr = p;
+    return CNDL_OK;
+} CNDL_CATCH
+
+int cndl_ipc_open(cndl_ctx* ctx, const cndl_ipc_handle* handle, void** d_ptr) try {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!d_ptr || !handle) return ctx->fail(CNDL_ERR_INVALID, "null handle or output");
+    *d_ptr = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle->bytes, sizeof(h));
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = p;
+    return CNDL_OK;
+} CNDL_CATCH
+
+int cndl_ipc_close(cndl_ctx* ctx, void* d_ptr) try {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!d_ptr) return CNDL_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(d_ptr));
+    return CNDL_OK;
+} CNDL_CATCH
+
+int cndl_ipc_free(cndl_ctx* ctx, void* d_ptr) try {
+    if (!ctx) return CNDL_ERR_INVALID;
+    if (!d_ptr) return CNDL_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaFree(d_ptr));
+    return CNDL_OK;
+} CNDL_CATCH
+
 void* cndl_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }

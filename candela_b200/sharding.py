@@ -157,6 +157,71 @@ def broadcast_scene(ri, object_ids=None, src: int = 0, device="cuda", group=None
                                        vertex_index_base=od["vert_offset"], leaf_triangle_offset=od["tri_offset"])
 
 
+class PeerFrame:
+    """The final frame of SURVEY.md §8e without a gather: `nbytes` of device memory in rank `dst`'s process that every rank of the
+    group maps (cudaIpc; NVLink peer access) and passes as the output of its frame call in the ROW-MAJOR layout, so each rank's
+    resolve kernel stores its own tiles' records straight into the one frame.  `ptr` is this process's address of the frame.
+    After a frame: complete() = a one-element all-reduce on the current stream — when it has passed on rank dst, every rank's
+    stores have landed.  Needs one process per GPU on one node; raises CandelaError where CUDA IPC is not available."""
+
+    def __init__(self, ri, nbytes: int, dst: int = 0, device="cuda", group=None):
+        import torch
+        import torch.distributed as dist
+        self.ri, self.dst, self.group, self.nbytes = ri, dst, group, nbytes
+        self.multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.rank = dist.get_rank(group) if self.multi else 0
+        self.owner = self.rank == dst
+        box = [None]
+        err = None
+        if self.owner:
+            try:
+                self.ptr, handle = ri.ipc_alloc(nbytes)
+                box = [handle]
+            except Exception as e:  # every rank must learn about it, or the others would wait in the broadcast forever
+                err = e
+                box = [None]
+        if self.multi:
+            dist.broadcast_object_list(box, src=dst, group=group, device=torch.device(device))
+        if box[0] is None:
+            raise err if err is not None else RuntimeError("PeerFrame: the owning rank could not export its frame (CUDA IPC unavailable)")
+        ok = 1
+        if not self.owner:
+            try:
+                self.ptr = ri.ipc_open(box[0])
+            except Exception as e:
+                err, ok, self.ptr = e, 0, 0
+        self._flag = torch.ones(1, dtype=torch.int32, device=device) * ok if self.multi else None
+        if self.multi:
+            dist.all_reduce(self._flag, op=dist.ReduceOp.MIN, group=group)
+            if int(self._flag.item()) == 0:
+                self.close()
+                raise err if err is not None else RuntimeError("PeerFrame: another rank could not map the frame (CUDA IPC unavailable)")
+            self._flag.fill_(1)
+
+    def complete(self):
+        """Enqueue the completion barrier on the current stream."""
+        if self.multi:
+            import torch.distributed as dist
+            dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
+
+    def tensor(self):
+        """The frame as a uint8 tensor (any rank; rank dst reads the assembled frame from it)."""
+        import torch
+        return torch.as_tensor(_DevicePtr(self.ptr, self.nbytes), device="cuda")
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.multi:
+            import torch.distributed as dist
+            if not self.owner and getattr(self, "ptr", 0):
+                self.ri.ipc_close(self.ptr)
+            dist.barrier(group=self.group)       # every peer has unmapped before the owner frees
+        if self.owner and getattr(self, "ptr", 0):
+            self.ri.ipc_free(self.ptr)
+        self.ptr = 0
+
+
 def bind_to_gpu_numa_node(gpu_index: int) -> bool:
     """Restricts this process to the CPU cores NVML reports as local to GPU `gpu_index`, so that pinned host buffers
     allocated afterwards (first touch) and the copy-issuing thread sit on the GPU's own NUMA node.  With one process per

@@ -279,6 +279,17 @@ uint64_t cndl_frame_rays_traced(const cndl_ctx* ctx, int slot);
  * row-major frame d_frame.  Enqueued on `stream`. */
 int cndl_frame_untile_device(cndl_ctx* ctx, const cndl_frame_params* p, const void* d_shard, void* d_frame, void* stream);
 
+/* One process per GPU (torchrun-style hosts): a frame buffer in ONE process's device memory that the other processes of the node
+ * map and pass as d_out of cndl_trace_frame_device — every rank's resolve kernel then stores its tiles' records straight into that
+ * frame over NVLink peer memory (row-major layout; no gather, no untile).  cndl_ipc_alloc = cudaMalloc + cudaIpcGetMemHandle on the
+ * owner; the 64 handle bytes travel by any means (a broadcast); cndl_ipc_open = cudaIpcOpenMemHandle in a peer process (not in the
+ * owner's: CUDA refuses that).  The caller orders the ranks (a barrier or a tiny all-reduce after the frame) before rank 0 reads. */
+typedef struct cndl_ipc_handle { unsigned char bytes[64]; } cndl_ipc_handle;
+int cndl_ipc_alloc(cndl_ctx* ctx, size_t bytes, void** d_ptr, cndl_ipc_handle* handle);
+int cndl_ipc_open(cndl_ctx* ctx, const cndl_ipc_handle* handle, void** d_ptr);
+int cndl_ipc_close(cndl_ctx* ctx, void* d_ptr);   /* in a peer process */
+int cndl_ipc_free(cndl_ctx* ctx, void* d_ptr);    /* in the owner, after every peer has closed */
+
 /* ---- Several GPUs behind one handle: the BVH replicated per device, screen tiles dealt round-robin, hit
  * records gathered for the final frame only.  One process drives all devices; the C++ mirror's RayIntersector holds one of
  * these when it is given more than one device.  cndl_multi_add_object builds on the first device and replicates the

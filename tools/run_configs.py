@@ -147,7 +147,15 @@ def cfg_bounce4k(args, rank, world, local_rank):
     def untile(sh, r, frame):
         ri.frame_untile_device(params(r), sh.data_ptr(), frame.data_ptr(), stream=stream)
 
+    peer = None
+    if world > 1 and args.transport == "peer":   # every rank's resolve kernel stores into rank 0's frame over NVLink (CUDA IPC mapping)
+        peer = sharding.PeerFrame(ri, W * H * 32, dst=0)
+
     def step():
+        if peer is not None:
+            ri.trace_frame_device(params(rank, local=False), peer.ptr, slot=0, stream=stream)
+            peer.complete()
+            return peer.tensor() if rank == 0 else None
         ri.trace_frame_device(params(rank), shard.data_ptr(), slot=0, stream=stream)
         return sharding.gather_frame(shard, W, H, 64, untile=untile)
     for _ in range(2):
@@ -163,14 +171,17 @@ def cfg_bounce4k(args, rank, world, local_rank):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
     t_max, rays_all = sharding.reduce_timing(ms, float(ri.frame_rays_traced(0)), device="cuda")
+    px = frame.cpu().numpy().view(api.PIXEL_DT).reshape(-1) if rank == 0 else None
+    if peer is not None:
+        peer.close()
     if rank != 0:
         return None
-    px = frame.cpu().numpy().view(api.PIXEL_DT).reshape(-1)
     # one tile row of the frame against the oracle (every pixel of 64 image rows)
     ob, nodes, tris, ents = oracle_scene(ri, v)
     pixels = np.arange(W * 64 * 8, W * 64 * 9, dtype=np.uint32)
     want, _ = of.trace_frame(ob.STACKLESS, nodes, tris, v, ents, iv, ip, W, H, spp=spp, bounces=bounces, seed=4000, out_format=of.OUT_PIXEL32, pixels=pixels)
-    return dict(config=f"multibounce_{W}x{H}_8spp_4bounces_tiles", octant_major=bool(args.bucket), n_gpus=world, rays_all_ranks=int(rays_all),
+    return dict(config=f"multibounce_{W}x{H}_8spp_4bounces_tiles", octant_major=bool(args.bucket), n_gpus=world, transport=("peer" if args.transport == "peer" and world > 1 else "gather"),
+                rays_all_ranks=int(rays_all),
                 ms_max_over_ranks_gather_included=round(t_max, 3), mrays_s=round(rays_all / t_max / 1e3, 1), frame_pixels=int(len(px)),
                 rays_in_frame=int(px["rays"].sum()), sample_pixels_checked=int(len(pixels)),
                 sample_bit_identical_to_oracle=bool(px[pixels].tobytes() == want[pixels].tobytes()))
@@ -281,6 +292,8 @@ def main():
     ap.add_argument("--presort-mode", type=int, default=0, help="0: origin cell major; 1: direction octant major")
     ap.add_argument("--sort", type=int, default=4, help="soup10m: cndl_set_traversal_mode sort_rays (0 off, 1 octant buckets, 2 octant + origin Morton order with the rays moved, 3 through an index list, 4 automatic)")
     ap.add_argument("--knobs", default="", help="comma-separated tuning knobs in knob-id order (see dev_bench.py)")
+    ap.add_argument("--transport", default="gather", choices=["gather", "peer"],
+                    help="bounce4k at N > 1: NCCL gather of tile-major shards + untile, or every rank storing into rank 0's frame over NVLink (CUDA IPC)")
     ap.add_argument("--bvh", default="build", choices=["build", "broadcast"], help="soup10m at N > 1: every rank builds, or rank 0 builds and broadcasts")
     ap.add_argument("--bucket", type=int, default=0, help="1: the generator emits each batch octant-major (CNDL_GEN_BUCKET_OCTANTS)")
     ap.add_argument("--check-rays", type=int, default=1_000_000)
