@@ -28,6 +28,7 @@ def main():
     stack = next(t for t in tb if t["fmt"] == "stack" and t["octant"] == 0)
     n1, n8 = b[1], b[8]
     ss = {n: b[n]["strong_scaling"] for n in b}
+    g8 = json.loads((P / "r2_bench_gather_n8.json").read_text())["strong_scaling"]
     eff = {n: ss[1]["ms_per_step"] / (n * ss[n]["ms_per_step"]) for n in b}
     new = f'''## 5. Results
 
@@ -43,8 +44,8 @@ is throughput served from L1/L2 (the measured limiter there is the L1 data pipe 
 | 2, stack node format (`r2_trace_bench.jsonl`) | {stack["mrays_s"]:.0f} Mrays/s ({stack["ms"]:.3f} ms) | {stack["frac"]:.2f} (2382 B/ray) | — | bit-identical, including the 63-entry stack break |
 | 3 — RTAO, 4 spp, tmax 2.4, any hit (`r2_configs_n1.jsonl`) | {rtao["mrays_s"] / 1e3:.2f} Grays/s ({rtao["ms"]:.3f} ms for {rtao["rays"]:,} rays) | {rtao["roofline_frac"]:.2f} (walk served from L1/L2) | {rtao["cpu_mrays_s"]:.1f} Mrays/s (oracle port) | batch and all 8.29 M results bit-identical (also under `pytest -m gpu`) |
 | specular (GGX, roughness 0.3) / shadow batches, 1080p | {spec["mrays_s"] / 1e3:.2f} / {shadow["mrays_s"] / 1e3:.2f} Grays/s | {spec["roofline_frac"]:.2f} / {shadow["roofline_frac"]:.2f} | — | bit-identical |
-| 4 — 3840×2160, 8 spp, 4 bounces = {ss[1]["rays_per_step"] / 1e6:.1f} M rays, tiles dealt round-robin, **final-frame gather inside the timed region** (`strong_scaling` in `r2_bench_n*.json`) | {ss[1]["ms_per_step"]:.1f} / {ss[2]["ms_per_step"]:.1f} / {ss[4]["ms_per_step"]:.1f} / **{ss[8]["ms_per_step"]:.1f} ms** at 1 / 2 / 4 / 8 GPUs = {ss[1]["mrays_s"] / 1e3:.2f} … {ss[8]["mrays_s"] / 1e3:.1f} Grays/s; strong-scaling efficiency {eff[2]:.2f} / {eff[4]:.2f} / **{eff[8]:.2f}**; gather of the 265 MB frame {ss[8]["final_frame_gather_ms"]:.2f} ms at 8 GPUs | — | — | the same pipeline at 480×270 bit-identical to the CPU frame; one shard in sixteen of the 4K frame under `pytest -m gpu` |
-| 4 through one process driving all GPUs (`cndl_multi_*`, `r2_multi_bench_n8.json`) | {m8["frame_ms_staged_copy_pipelined"]:.1f} ms per frame at 8 GPUs including the copy of the frame to the host (single GPU {m8["single_device_frame_ms"]:.1f}); scene replication device to device: {m8["replicate_2M_tris_ms"]:.2f} ms for 2 M triangles to 7 peers | — | — | frame bit-identical to the single-GPU frame |
+| 4 — 3840×2160, 8 spp, 4 bounces = {ss[1]["rays_per_step"] / 1e6:.1f} M rays, tiles dealt round-robin, **the final frame assembled on rank 0 inside the timed region** — every rank's resolve kernel stores its pixels into rank 0's frame over NVLink peer memory (CUDA IPC), then a one-element all-reduce (`strong_scaling` in `r2_bench_n*.json`; with the NCCL gather + untile instead: `r2_bench_gather_n*.json`) | {ss[1]["ms_per_step"]:.1f} / {ss[2]["ms_per_step"]:.1f} / {ss[4]["ms_per_step"]:.1f} / **{ss[8]["ms_per_step"]:.1f} ms** at 1 / 2 / 4 / 8 GPUs = {ss[1]["mrays_s"] / 1e3:.2f} … {ss[8]["mrays_s"] / 1e3:.1f} Grays/s; strong-scaling efficiency {eff[2]:.2f} / {eff[4]:.2f} / **{eff[8]:.2f}**; completion barrier {ss[8]["final_frame_gather_ms"]:.2f} ms at 8 GPUs (NCCL gather + untile of the 265 MB frame: {g8["final_frame_gather_ms"]:.2f} ms, {g8["ms_per_step"]:.1f} ms per frame) | — | — | the same pipeline at 480×270 bit-identical to the CPU frame; one shard in sixteen of the 4K frame under `pytest -m gpu` |
+| 4 through one process driving all GPUs (`cndl_multi_*`, `r2_multi_bench_n8.json`) | {min(m8["frame_ms_staged_copy_pipelined"], m8["frame_ms_peer_stores_pipelined"]):.1f} ms per frame at 8 GPUs (two frames in flight) including the copy of the frame to the host (single GPU {m8["single_device_frame_ms"]:.1f}); scene replication device to device: {m8["replicate_2M_tris_ms"]:.2f} ms for 2 M triangles to 7 peers | — | — | frame bit-identical to the single-GPU frame |
 | 5 — 10 M triangles, 100 M random rays | {soup1["mrays_s"] / 1e3:.2f} Grays/s on 1 GPU ({soup1["trace_ms_max_over_ranks"]:.1f} ms, in-call ray ordering counted), {soup8["mrays_s"] / 1e3:.1f} on 8 | **{soup1["roofline_frac_per_gpu"]:.2f}** per GPU (DRAM roofline, {soup1["bytes_per_ray"]} B/ray; round 1: 0.55) | {soup1["cpu_mrays_s"]:.1f} Mrays/s | 1 M-ray sample bit-identical |
 | BVH build, 262,624 triangles | {n1["build"]["gpu_ms"]:.2f} ms (exact binned SAH, both formats; LBVH 0.31 ms) | per-level latency | reference builder {r[1]["cpu_baseline"]["build_ms_reference_builder_1thread"]:.0f} ms, oracle port {r[1]["cpu_baseline"]["build_ms_port_1thread"]:.0f} ms, one thread | node and triangle buffers byte-identical to the compiled reference builder |
 | BVH build, 10 M triangles | {soup8["gpu_build_ms"]:.1f} ms (LBVH 3.6 ms) | — | {soup1["cpu_build_ms"]:,} ms | byte-identical |

@@ -58,7 +58,7 @@ def main():
     mi.BufferEntities()
     W, H = args.width, args.height
     iv, ip = scenes.camera(**scenes.S260K_CAMERA, width=W, height=H)
-    p = cb.frame_params(iv, ip, W, H, spp=args.spp, bounces=args.bounces, seed=4000, out_format=api.FRAME_OUT_PIXEL32, octant_order=True)
+    p = cb.frame_params(iv, ip, W, H, spp=args.spp, bounces=args.bounces, seed=4000, out_format=api.FRAME_OUT_PIXEL32, octant_order=False)   # 8 spp: pixel order keeps a pixel's samples together (see profiles/r2_experiments.md)
     pins = [cb.PinnedBuffer(W * H, api.PIXEL_DT) for _ in range(2)]
     for transport, label in ((api.TRANSPORT_PEER_STORES, "peer_stores"), (api.TRANSPORT_STAGED_COPY, "staged_copy")):
         if n_dev == 1 and transport == api.TRANSPORT_STAGED_COPY:
@@ -66,6 +66,10 @@ def main():
         mi.set_transport(transport)
         mi.TraceFrame(p, pins[0].array)
         mi.TraceFrame(p, pins[0].array)
+        for k in range(4):   # both slots allocate their scratch (and, for staged copies, their staging) outside the timed loops
+            mi.frame_submit(p, pins[k & 1].array, k & 1)
+        mi.frame_wait(0)
+        mi.frame_wait(1)
         t0 = time.perf_counter()
         for _ in range(args.reps):
             mi.TraceFrame(p, pins[0].array)
