@@ -180,3 +180,27 @@ def test_multi_device_handle(cb, ob, dragon2):
             assert got.tobytes() == want.tobytes(), (fmt, transport)
             assert mi.frame_rays_traced(0) == dragon2["ri"].frame_rays_traced(0)
     mi.close()
+
+
+def test_frame_call_on_a_stack_format_context(cb, ob, dragon2):
+    """The frame pipeline over FlattenedStackNode buffers (the stack-format traversal kernels read the generator's segmented batches and
+    octant lists too): the oracle's frame for the stack format — same hits, different `iters` — in all three output formats."""
+    from candela_b200 import api
+    from oracle import frame as of
+    sc = dragon2
+    ri = cb.RayIntersector(cb.STACK)
+    ri.AddObject(2, sc["V"], sc["F"].ravel(), sc["mids"])
+    ri.BufferData()
+    sc["fill"](ri)
+    nodes, tris, _ = ri.read_buffers()
+    ents = sc["ents"].copy()
+    ents["node_count"] = len(nodes)
+    W, H = 160, 96
+    iv, ip = _camera(W, H)
+    for fmt, kw in ((0, dict(spp=2, seed=5)), (1, dict(spp=2, seed=5)), (2, dict(spp=3, bounces=3, seed=11))):
+        want, traced = of.trace_frame(ob.STACK, nodes, tris, sc["V"], ents, iv, ip, W, H, out_format=fmt, **kw)
+        for octant, compact in ((False, False), (True, False), (True, True)):
+            got = ri.TraceFrame(cb.frame_params(iv, ip, W, H, tile=32, out_format=fmt, octant_order=octant, compact_rays=compact, **kw))
+            assert got.tobytes() == want.tobytes(), (fmt, octant, compact)
+            assert ri.frame_rays_traced(0) == traced
+    ri.close()
