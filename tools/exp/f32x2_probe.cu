@@ -1,3 +1,6 @@
+// Development probe: throughput of the packed add.rn.f32x2 / mul.rn.f32x2 instructions (FADD2 / FMUL2 / FFMA2) against scalar FADD / FMUL.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/exp/f32x2_probe tools/exp/f32x2_probe.cu && ./tools/exp/f32x2_probe
+// Result on a B200: 59 vs 34 G lane-ops/s; note that ptxas contracted the packed mul + add into FFMA2 despite the .rn qualifiers.
 #include <cstdio>
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     unsigned long long ra, rb, rc;
