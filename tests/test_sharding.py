@@ -136,3 +136,20 @@ def test_broadcast_arrays_world2():
             rng.integers(0, 255, size=77).astype(np.uint8)]
     assert got == [a.tobytes() for a in want]
 
+
+
+def test_sub_shards_partition_a_ranks_tiles():
+    """bench.py / INTEGRATION.md §3b: rank r of N cuts its tiles into `split` sub-shards (r + k N, split N) traced by separate frame
+    calls on separate streams.  Tile t belongs to rank t mod N, and t mod (split N) is r + k N for exactly one k: the sub-shards
+    partition the rank's pixels, so the calls store disjoint records into the one frame."""
+    from candela_b200 import sharding
+    for (W, H, tile) in ((200, 120, 32), (1920, 1080, 64), (97, 45, 7)):
+        for world in (1, 2, 3, 8):
+            for split in (2, 3, 4):
+                for rank in range(world):
+                    whole = sharding.shard_slots(W, H, world, rank, tile)
+                    whole = np.sort(whole[whole >= 0])
+                    parts = [sharding.shard_slots(W, H, world * split, rank + k * world, tile) for k in range(split)]
+                    parts = [p[p >= 0] for p in parts]
+                    joined = np.sort(np.concatenate(parts))
+                    assert np.array_equal(joined, whole) and len(np.unique(joined)) == len(joined)
