@@ -324,24 +324,25 @@ __global__ void gen_emit_kernel(GenParams g, const cndl_ray* __restrict__ rays, 
 // no second evaluation of the sample: the traversal learns which slots of a segment are live from seg_counts[segment]
 // (RayOrder::seg_counts), and consecutive slots of a segment hold rays of one octant from neighbouring pixels.
 // in_seg_counts (optional): the input batch is itself such a segmented batch (a further bounce).
-__global__ void __launch_bounds__(256) gen_tile_kernel(GenParams g, const cndl_ray* __restrict__ rays, const cndl_hit* __restrict__ hits,
+template <int TPB>
+__global__ void __launch_bounds__(TPB) gen_tile_kernel(GenParams g, const cndl_ray* __restrict__ rays, const cndl_hit* __restrict__ hits,
                                                        const unsigned* __restrict__ ids, const float4* __restrict__ tri48, const cndl_entity* __restrict__ ents,
                                                        const unsigned* __restrict__ in_seg_counts, unsigned n_elems, unsigned char* __restrict__ keys,
                                                        unsigned* __restrict__ dest, cndl_ray* __restrict__ out, unsigned* __restrict__ ids_out,
                                                        unsigned* __restrict__ seg_counts, unsigned* __restrict__ total, unsigned* __restrict__ oct_cursor,
                                                        unsigned* __restrict__ oct_list, unsigned oct_stride) {
-    constexpr int ROUNDS = kRaySegment / 256;
-    __shared__ int s_cnt[9 * 8 * ROUNDS];  // [key][round * 8 + warp]
+    constexpr int ROUNDS = kRaySegment / TPB, WARPS = TPB / 32, PER_KEY = ROUNDS * WARPS;  // PER_KEY = kRaySegment / 32
+    __shared__ int s_cnt[9 * PER_KEY];  // [key][round * WARPS + warp]
     __shared__ unsigned s_oct_base[8];
     const unsigned tid = threadIdx.x, lane = tid & 31u, wp = tid >> 5;
     const unsigned cta_base = blockIdx.x * (unsigned)kRaySegment;
-    for (unsigned k = tid; k < 9u * 8u * ROUNDS; k += 256) s_cnt[k] = 0;
+    for (unsigned k = tid; k < 9u * PER_KEY; k += TPB) s_cnt[k] = 0;
     __syncthreads();
     float4 o[ROUNDS], d[ROUNDS];
     unsigned key[ROUNDS], rank[ROUNDS], element[ROUNDS];
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        const unsigned e = cta_base + (unsigned)r * 256u + tid;
+        const unsigned e = cta_base + (unsigned)r * (unsigned)TPB + tid;
         key[r] = 8;
         element[r] = 0;
         if (e < n_elems) {
@@ -357,11 +358,11 @@ __global__ void __launch_bounds__(256) gen_tile_kernel(GenParams g, const cndl_r
         }
         const unsigned same = __match_any_sync(0xFFFFFFFFu, key[r]);
         rank[r] = (unsigned)__popc(same & ((1u << lane) - 1u));
-        if (rank[r] == 0) s_cnt[key[r] * (8 * ROUNDS) + r * 8 + wp] = __popc(same);
+        if (rank[r] == 0) s_cnt[key[r] * PER_KEY + r * WARPS + wp] = __popc(same);
     }
     __syncthreads();
-    if (wp == 0) {  // exclusive scan of the 9 * 8 * ROUNDS counts in (key, round, warp) order: 9 * ROUNDS / 4 entries per lane
-        constexpr int PER = 9 * 8 * ROUNDS / 32;
+    if (wp == 0) {  // exclusive scan of the 9 * PER_KEY counts in (key, round, warp) order
+        constexpr int PER = 9 * PER_KEY / 32;
         int v[PER], sum = 0;
 #pragma unroll
         for (int k = 0; k < PER; ++k) { v[k] = s_cnt[lane * PER + k]; sum += v[k]; }
@@ -376,27 +377,27 @@ __global__ void __launch_bounds__(256) gen_tile_kernel(GenParams g, const cndl_r
         for (int k = 0; k < PER; ++k) { s_cnt[lane * PER + k] = run; run += v[k]; }
     }
     __syncthreads();
-    const unsigned n_live = (unsigned)s_cnt[8 * (8 * ROUNDS)];  // where key 8 (no ray) begins
+    const unsigned n_live = (unsigned)s_cnt[8 * PER_KEY];  // where key 8 (no ray) begins
     if (oct_list) {
         // octant-major over the WHOLE batch without a global scan: the segment's run of octant o is appended to the batch's list of
         // octant o (one atomic per run; the lists are RayOrder's bucketed form).  Which segment comes first inside an octant depends
         // on scheduling; results do not.
         if (tid < 8) {
-            const unsigned n = (unsigned)(s_cnt[(tid + 1) * (8 * ROUNDS)] - s_cnt[tid * (8 * ROUNDS)]);
+            const unsigned n = (unsigned)(s_cnt[(tid + 1) * PER_KEY] - s_cnt[tid * PER_KEY]);
             s_oct_base[tid] = n ? atomicAdd(oct_cursor + tid, n) : 0u;
         }
         __syncthreads();
     }
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        const unsigned e = cta_base + (unsigned)r * 256u + tid;
+        const unsigned e = cta_base + (unsigned)r * (unsigned)TPB + tid;
         if (e >= n_elems) continue;
         keys[e] = (unsigned char)key[r];
         if (key[r] >= 8) continue;
-        const unsigned in_seg = (unsigned)s_cnt[key[r] * (8 * ROUNDS) + r * 8 + wp] + rank[r];
+        const unsigned in_seg = (unsigned)s_cnt[key[r] * PER_KEY + r * WARPS + wp] + rank[r];
         const unsigned pos = cta_base + in_seg;
         dest[e] = pos;
-        if (oct_list) oct_list[(size_t)key[r] * oct_stride + s_oct_base[key[r]] + (in_seg - (unsigned)s_cnt[key[r] * (8 * ROUNDS)])] = pos;
+        if (oct_list) oct_list[(size_t)key[r] * oct_stride + s_oct_base[key[r]] + (in_seg - (unsigned)s_cnt[key[r] * PER_KEY])] = pos;
         stg256(reinterpret_cast<float4*>(out + pos), o[r], d[r]);
         if (ids_out) ids_out[pos] = element[r];
     }
@@ -559,8 +560,11 @@ cudaError_t generate_rays_tiled(const SceneView& s, const cndl_raygen_params& pr
     const size_t n = R * (size_t)prm.spp;
     unsigned char* keys = reinterpret_cast<unsigned char*>(scratch);
     unsigned* dest = reinterpret_cast<unsigned*>(scratch + (n + 3) / 4);
-    gen_tile_kernel<<<(unsigned)((n + kRaySegment - 1) / kRaySegment), 256, 0, stream>>>(g, rays, hits, prm.d_ids_in, s.tri48, s.ents, in_seg_counts, (unsigned)n, keys,
-                                                                                       dest, out, prm.d_ids_out, seg_counts, total, oct_cursor, oct_list, (unsigned)oct_stride);
+    const unsigned grid = (unsigned)((n + kRaySegment - 1) / kRaySegment);
+    // 512 threads x 2 rays: 54 registers, 32 resident warps per SM (256 x 4: 68 registers, 24 warps; 1024 x 1: 38 registers, one CTA per
+    // SM, slower) — 1.222 / 1.226 / 1.244 ms per 1080p frame
+    gen_tile_kernel<512><<<grid, 512, 0, stream>>>(g, rays, hits, prm.d_ids_in, s.tri48, s.ents, in_seg_counts, (unsigned)n, keys, dest, out, prm.d_ids_out, seg_counts,
+                                                   total, oct_cursor, oct_list, (unsigned)oct_stride);
     lc.n++;
     return cudaGetLastError();
 }
