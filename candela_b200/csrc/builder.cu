@@ -327,16 +327,27 @@ __global__ void __launch_bounds__(BLOCK) level_step_kernel(LevelArgs g, int cls)
 // 64 registers / 4 CTAs per SM: more resident warps (48 or 40 registers, with spills) measured 3-6 % slower.
 constexpr int kTinyWarps = 8;
 constexpr unsigned kDirectLen = 9;  // ranges up to this length search their split without bins (3 x 10 candidates <= 32 lanes)
-__global__ void __launch_bounds__(32 * kTinyWarps, 4) level_step_tiny_kernel(LevelArgs g) {
+constexpr unsigned kPackLen = 8;    // ranges up to this length are handled four to a warp, eight lanes each (level_step_tiny_kernel)
+constexpr long long kPackMinRanges = 131072;  // levels with fewer tiny ranges keep one range per warp (262k triangles: 2.06 ms either way below it, 2.25 packed)
+constexpr int kPackStride = 12;     // staged words per reference: box min, box max, (unused x3), bins of the three axes
+struct TinyShared {
+    int count[kTinyWarps][kBins];
+    int mn[kTinyWarps][3][kBins], mx[kTinyWarps][3][kBins];
+    float best_cost[kTinyWarps], border[kTinyWarps];
+    int axis[kTinyWarps];
+    float stage[kTinyWarps][4 * kPackLen * kPackStride];
+};
+
+// One range of 9..64 references (or any tiny range), the whole warp on it.
+__device__ __forceinline__ void tiny_node_full(const LevelArgs& g, TinyShared& sh, int node) {
     const BuildArrays& a = g.a;
-    const int n_nodes = g.lv->n_class[CLS_TINY];  // the grid is an upper bound
-    __shared__ int s_count[kTinyWarps][kBins];
-    __shared__ int s_mn[kTinyWarps][3][kBins], s_mx[kTinyWarps][3][kBins];
-    __shared__ float s_best_cost[kTinyWarps], s_border[kTinyWarps];
-    __shared__ int s_axis[kTinyWarps];
+    int (&s_count)[kTinyWarps][kBins] = sh.count;
+    int (&s_mn)[kTinyWarps][3][kBins] = sh.mn;
+    int (&s_mx)[kTinyWarps][3][kBins] = sh.mx;
+    float (&s_best_cost)[kTinyWarps] = sh.best_cost;
+    float (&s_border)[kTinyWarps] = sh.border;
+    int (&s_axis)[kTinyWarps] = sh.axis;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const int node = blockIdx.x * kTinyWarps + wp;
-    if (node >= n_nodes) return;  // whole warps leave; nothing below synchronises across warps
     const int k = g.klist[node];
     const int id = g.active[k];
     const unsigned start = a.nstart[id], len = a.nlen[id];
@@ -491,6 +502,179 @@ __global__ void __launch_bounds__(32 * kTinyWarps, 4) level_step_tiny_kernel(Lev
     if (lane == 0) create_child(g, k, 0, start, len, mid, box[0], zf[0], a.refs);
     if (lane == 1) create_child(g, k, 1, start, len, mid, box[1], zf[1], a.refs);
     if (lane == 0) finish_parent(g, k, id, start, len);
+    __syncwarp();
+}
+
+// The level step for the tiny class.  A warp takes FOUR consecutive ranges of the class.  Those of at most kPackLen references —
+// three quarters of all tiny ranges; at 10 M triangles 1.6 M of them in one level — are split side by side, eight lanes each: the
+// split search is the direct one of tiny_node_full (candidates = the references' own bins and i = 0, four rounds of eight
+// candidates), the Lomuto emulation fits one 8-position chunk, the child boxes come from three shuffle steps inside the group, and
+// lanes 0 / 1 of every group create the children — so the per-range cost that does not depend on the range's length (partition,
+// boxes, children: ~900 warp instructions before) is paid once per four ranges.  The longer ranges of the four follow one at a
+// time on the whole warp.  Same arithmetic, same order of decisions.
+// PACK = 1: one range per warp (levels with few tiny ranges are latency-bound: four ranges in a row on one warp would only
+// lengthen the level); PACK = 4: the packed form for levels with many.
+template <int PACK>
+__global__ void __launch_bounds__(32 * kTinyWarps, 4) level_step_tiny_kernel(LevelArgs g) {
+    const BuildArrays& a = g.a;
+    const int n_nodes = g.lv->n_class[CLS_TINY];  // the grid is an upper bound
+    __shared__ TinyShared sh;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if (PACK == 1) {
+        const int node = blockIdx.x * kTinyWarps + wp;
+        if (node < n_nodes) tiny_node_full(g, sh, node);
+        return;
+    }
+    const int first = (blockIdx.x * kTinyWarps + wp) * 4;
+    if (first >= n_nodes) return;  // whole warps leave; nothing below synchronises across warps
+    const int grp = lane >> 3, gl = lane & 7;
+    const unsigned gm = 0xFFu << (8 * grp);
+    const int node = first + grp;
+    const bool have = node < n_nodes;
+    int k = 0, id = 0;
+    unsigned start = 0, len = 0;
+    if (have) {
+        k = g.klist[node];
+        id = g.active[k];
+        start = a.nstart[id];
+        len = a.nlen[id];
+    }
+    if (have && len <= kPackLen) {
+        const float4 bmn = a.nmin[id], bmx = a.nmax[id];
+        float* stg = sh.stage[wp] + grp * (kPackLen * kPackStride);
+        int* sbin = reinterpret_cast<int*>(stg);
+        const bool v = (unsigned)gl < len;
+        const int r = v ? a.refs[start + gl] : -1;
+        float cen[3] = {0.0f, 0.0f, 0.0f};
+        if (v) {
+            const float4 tm = a.tmin[r], tx = a.tmax[r];
+            cen[0] = tm.w; cen[1] = tx.w; cen[2] = a.tcz[r];
+            float* e = stg + kPackStride * gl;
+            e[0] = tm.x; e[1] = tm.y; e[2] = tm.z; e[3] = tx.x; e[4] = tx.y; e[5] = tx.z;
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                const float lo = ax == 0 ? bmn.x : (ax == 1 ? bmn.y : bmn.z), hi = ax == 0 ? bmx.x : (ax == 1 ? bmx.y : bmx.z);
+                const float scale = fdiv((float)kBins, fsub(hi, lo));       // :295
+                int b = __float2int_rz(fmul(fsub(cen[ax], lo), scale));       // :302
+                b = b > kBins - 1 ? kBins - 1 : (b < 0 ? 0 : b);
+                sbin[kPackStride * gl + 9 + ax] = b;
+            }
+        }
+        __syncwarp(gm);
+        // ---- SearchSAHPlaneBinned (:276-363), direct form: 27 (axis, candidate) pairs, eight per round ----
+        float best_cost = __int_as_float(0x7F800000), best_border = bmn.x;
+        int best_key = 0x7FFFFFFF;
+        for (int rr = 0; rr < 4; ++rr) {
+            const int c = rr * 8 + gl;
+            const int ax = c / 9 > 2 ? 2 : c / 9, j = c - (c / 9) * 9;
+            const float lo = ax == 0 ? bmn.x : (ax == 1 ? bmn.y : bmn.z), hi = ax == 0 ? bmx.x : (ax == 1 ? bmx.y : bmx.z);
+            int ci = 0;
+            if ((unsigned)j < len) ci = sbin[kPackStride * j + 9 + ax];
+            const bool active = c < 27 && (unsigned)j <= len && !(lo == hi) && ci < kBins - 1;  // :285; i = 63 is not a split
+            float cost = __int_as_float(0x7F800000);
+            if (active) {
+                BinAgg L = agg_identity(), R = agg_identity();
+                for (unsigned e = 0; e < len; ++e) {
+                    const float* el = stg + kPackStride * e;
+                    BinAgg one;
+                    one.n = 1;
+                    one.mn[0] = el[0]; one.mn[1] = el[1]; one.mn[2] = el[2]; one.mx[0] = el[3]; one.mx[1] = el[4]; one.mx[2] = el[5];
+                    if (sbin[kPackStride * e + 9 + ax] <= ci) L = agg_join(L, one); else R = agg_join(R, one);
+                }
+                cost = agg_cost(L, R);
+                if (!(cost == cost)) cost = __int_as_float(0x7F800000);  // a NaN cost is never selected by `<`
+            }
+            const int key = ax * kBins + ci;
+            if (cost < best_cost || (cost == best_cost && key < best_key)) {
+                best_cost = cost;
+                best_key = key;
+                best_border = fadd(lo, fmul(fdiv(fsub(hi, lo), (float)kBins), __int2float_rn(ci + 1)));  // :347,:356
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const float pc = __shfl_xor_sync(gm, best_cost, o), pb = __shfl_xor_sync(gm, best_border, o);
+            const int pk = __shfl_xor_sync(gm, best_key, o);
+            if (pc < best_cost || (pc == best_cost && pk < best_key)) { best_cost = pc; best_key = pk; best_border = pb; }
+        }
+        const bool found = best_cost < kInfCost;
+        const int axis = found ? best_key / kBins : 0;
+        const float border = found ? best_border : bmn.x;
+
+        // ---- Lomuto partition (:532-549): one chunk of at most eight positions (see level_step_kernel) ----
+        const bool f = v && (axis == 0 ? cen[0] : (axis == 1 ? cen[1] : cen[2])) < border;
+        const unsigned m8 = (__ballot_sync(gm, f) >> (8 * grp)) & 0xFFu;
+        const int rank = __popc(m8 & ((1u << gl) - 1u)), nL = __popc(m8);
+        const unsigned P = start + gl, s_pos = start + (unsigned)rank;
+        const bool writes_back = f && s_pos != P && !(P < start + (unsigned)nL);
+        int q = rank;
+        if (writes_back)
+            while ((m8 >> q) & 1u) q = __popc(m8 & ((1u << q) - 1u));
+        const int displaced = __shfl_sync(gm, r, 8 * grp + q);
+        __syncwarp(gm);
+        if (f) a.refs[s_pos] = r;
+        if (writes_back) a.refs[P] = displaced;
+        unsigned mid = start + (unsigned)nL;
+        __syncwarp(gm);
+        if (mid == start || mid == start + len) mid = start + len / 2;  // split failure (:553-556)
+
+        // ---- child boxes (:574-597): the FIRST zero decides a zero's sign ----
+        int box[2][6], zf[2][6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            box[0][c] = box[1][c] = c < 3 ? f2key(kSentinelMax) : f2key(kSentinelMin);
+            zf[0][c] = zf[1][c] = 0x7FFFFFFF;
+        }
+        bool zero_seen = false;
+        if (v) {
+            const int r2 = a.refs[P];
+            const float4 tm = a.tmin[r2], tx = a.tmax[r2];
+            const float val[6] = {tm.x, tm.y, tm.z, tx.x, tx.y, tx.z};
+            const int side = P < mid ? 0 : 1;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const int key = f2key(val[c] == 0.0f ? 0.0f : val[c]);
+                if (side == 0) box[0][c] = key; else box[1][c] = key;
+                if (val[c] == 0.0f) {
+                    zero_seen = true;
+                    if (side == 0) zf[0][c] = (int)P; else zf[1][c] = (int)P;
+                }
+            }
+        }
+        const bool any_zero = (__ballot_sync(gm, zero_seen) & gm) != 0u;
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd)
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    const int other = __shfl_xor_sync(gm, box[sd][c], o);
+                    box[sd][c] = c < 3 ? min(box[sd][c], other) : max(box[sd][c], other);
+                }
+        if (any_zero) {
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd)
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+#pragma unroll
+                    for (int o = 4; o > 0; o >>= 1) zf[sd][c] = min(zf[sd][c], __shfl_xor_sync(gm, zf[sd][c], o));
+        }
+        // ---- create the two children (:559-572,:612-625): lanes 0 and 1 of the group, side = lane ----
+        if (gl < 2) {
+            int bk[6], z[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { bk[c] = gl ? box[1][c] : box[0][c]; z[c] = gl ? zf[1][c] : zf[0][c]; }
+            create_child(g, k, gl, start, len, mid, bk, z, a.refs);
+        }
+        if (gl == 0) finish_parent(g, k, id, start, len);
+    }
+    __syncwarp();
+    // ---- the longer ranges of the four, one at a time on the whole warp ----
+#pragma unroll 1
+    for (int qn = 0; qn < 4; ++qn) {
+        const unsigned lq = __shfl_sync(0xFFFFFFFFu, len, 8 * qn);
+        if (lq > kPackLen) tiny_node_full(g, sh, first + qn);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1056,6 +1240,7 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
     int *d_levels = nullptr, *d_flags = nullptr, *d_offsets = nullptr, *d_block_sums = nullptr, *d_totals = nullptr, *d_active = nullptr, *d_active_next = nullptr, *d_kl_big = nullptr, *d_kl_small = nullptr, *d_kl_tiny = nullptr, *d_kl_split = nullptr;
     const size_t scan_n = std::max<size_t>(n_max, 16);  // inner-node flags of the stack flatten (the level compaction scans in its own kernels)
     const unsigned split_node = rq.split_node ? std::max(rq.split_node, kTinyNode) : kSplitNodeDefault;
+    const long long pack_min = rq.pack_min ? (long long)rq.pack_min : kPackMinRanges;
     const int split_items = T <= (1u << 20) ? 2 : 8, split_chunk = kSplitBlock * split_items;
     const size_t n_split_max = T / split_node + 2, split_chunks_max = T / split_chunk + n_split_max + 1;
     SplitArgs sp{};
@@ -1201,8 +1386,11 @@ int build_object(BuildRequest& rq, cudaStream_t st, LaunchCounter& lc, float* bu
             if (n_small) { g.klist = d_kl_small; level_step_kernel<128><<<n_small, 128, 0, s_small>>>(g, CLS_SMALL); lc.n++; }
             if (n_tiny) {
                 g.klist = d_kl_tiny;
-                const unsigned grid = (unsigned)((n_tiny + kTinyWarps - 1) / kTinyWarps);
-                level_step_tiny_kernel<<<grid, 32 * kTinyWarps, 0, st>>>(g);
+                if (n_tiny >= pack_min) {  // four ranges per warp
+                    level_step_tiny_kernel<4><<<(unsigned)((n_tiny + 4 * kTinyWarps - 1) / (4 * kTinyWarps)), 32 * kTinyWarps, 0, st>>>(g);
+                } else {
+                    level_step_tiny_kernel<1><<<(unsigned)((n_tiny + kTinyWarps - 1) / kTinyWarps), 32 * kTinyWarps, 0, st>>>(g);
+                }
                 lc.n++;
             }
             BK(cudaGetLastError());

@@ -24,6 +24,7 @@ struct BuildRequest {
     int** host_counts;           // mapped pinned memory kept by the context: the host copy of the builder's level descriptors (2 MB)
     cudaStream_t side[2] = {nullptr, nullptr};  // SAH builder: streams for the size classes of one level (optional)
     unsigned split_node = 0;     // SAH builder: ranges longer than this are split across CTAs (0 = default)
+    unsigned pack_min = 0;       // SAH builder: levels with at least this many tiny ranges take four ranges per warp (0 = default)
 };
 
 // Returns CNDL_OK or a negative cndl_status with `err` set. Work is enqueued on `st` and complete on return.

@@ -330,6 +330,7 @@ int cndl_add_object(cndl_ctx* ctx, uint32_t object_id, const cndl_vertex* verts,
     rq.side[0] = ctx->streams[1];
     rq.side[1] = ctx->streams[3];
     rq.split_node = (unsigned)ctx->knobs[CNDL_KNOB_BUILD_SPLIT_NODE];
+    rq.pack_min = (unsigned)ctx->knobs[CNDL_KNOB_BUILD_PACK_MIN];
     std::string berr;
     float ms = 0.0f;
     const int rc = build_object(rq, st, ctx->launches, &ms, berr);
@@ -542,7 +543,7 @@ int cndl_set_traversal_mode(cndl_ctx* ctx, int mode, int sort_rays) {
 }
 
 int cndl_set_tuning(cndl_ctx* ctx, int knob, int value) {
-    if (!ctx || knob < 0 || knob >= 9 || value < 0) return CNDL_ERR_INVALID;
+    if (!ctx || knob < 0 || knob >= 10 || value < 0) return CNDL_ERR_INVALID;
     if (knob == CNDL_KNOB_BLOCKS_PER_SM && (value < 1 || value > 16)) return CNDL_ERR_INVALID;
     ctx->knobs[knob] = value;
     return CNDL_OK;

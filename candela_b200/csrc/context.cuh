@@ -92,7 +92,7 @@ struct cndl_ctx {
     cudaStream_t main_stream = nullptr;
     int mode = 2, sort_rays = 4;   // sort_rays: 0 off, 1 octant buckets, 2 octant + origin Morton order (rays moved), 3 the same through an index list, 4 automatic
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};  // bounds of all entities (for sort_rays = 2)
-    int knobs[9] = {8, 14, 10, 0, 0, 12, 4096, 1024, 0};  // CNDL_KNOB_*
+    int knobs[10] = {8, 14, 10, 0, 0, 12, 4096, 1024, 0, 0};  // CNDL_KNOB_*
     // hot-first derived layout of the stackless nodes (kernels_hot.cu), rebuilt by cndl_commit
     cndl::DeviceBuffer nodes2, perm, ents2, hot_scratch, d_objects;
     std::vector<int2> h_objects;                 // (node_offset, node_count) in insertion order

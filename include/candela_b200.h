@@ -432,8 +432,11 @@ enum { CNDL_KNOB_BLOCKS_PER_SM = 0,   /* persistent CTAs (128 threads) per SM */
        CNDL_KNOB_HOST_CHUNKS = 4,     /* host-buffer queries: chunks in the copy/traverse/copy pipeline (0 = default 12) */
        CNDL_KNOB_HOT_NODES = 6,       /* mode 2, stackless: top-of-tree nodes staged in shared memory (<= 7168; takes effect at cndl_commit) */
        CNDL_KNOB_BLOCK_THREADS = 7,   /* mode 2, stackless, staged kernel: threads per CTA (256, 512 or 1024; CTAs per SM = 1024 / threads) */
-       CNDL_KNOB_BUILD_SPLIT_NODE = 8 /* SAH builder: ranges longer than this are processed by one CTA per 512 (2048 beyond 2^20 triangles) references instead of one CTA
-                                         per node (0 = default 16384; values below 64 are raised to 64); the buffers do not depend on it */ };
+       CNDL_KNOB_BUILD_SPLIT_NODE = 8, /* SAH builder: ranges longer than this are processed by one CTA per 512 (2048 beyond 2^20 triangles) references instead of one CTA
+                                         per node (0 = default 16384; values below 64 are raised to 64); the buffers do not depend on it */
+       CNDL_KNOB_BUILD_PACK_MIN = 9   /* SAH builder: levels with at least this many ranges of 3..64 references handle four ranges per warp
+                                         (ranges of <= 8 references side by side, eight lanes each); 0 = default 131072, 1 = always; the
+                                         buffers do not depend on it */ };
 int cndl_set_tuning(cndl_ctx* ctx, int knob, int value);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */
 uint64_t cndl_launch_count(const cndl_ctx* ctx);

@@ -139,6 +139,36 @@ def test_split_node_threshold_never_changes_the_buffers(cb, ob, golden_meshes, s
         ri.close()
 
 
+def test_packed_tiny_ranges_never_change_the_buffers(cb, ob, golden_meshes):
+    """CNDL_KNOB_BUILD_PACK_MIN = 1: every level handles its ranges of 3..64 references four to a warp (those of <= 8 references side by
+    side on eight lanes each, the longer ones in turn) — the default only does so for levels of >= 131072 such ranges.  Same bytes, on
+    meshes with split failures, duplicates, signed zeros and degenerate boxes, with and without the hashed child swaps."""
+    from candela_b200 import scenes
+    names = [n for n in ("dragon", "coplanar_grid", "duplicates", "signed_zero", "soup400", "peach_castle") if n in golden_meshes]
+    v, i, m = scenes.make_heightfield(120)
+    for fmt in (ob.STACKLESS, ob.STACK):
+        for name in names:
+            P, F = golden_meshes[name]
+            V = ob.make_vertices(P)
+            ref = ob.build(fmt, V, F.ravel())
+            for split_node in (0, 64):
+                ri = cb.RayIntersector(fmt)
+                ri.set_tuning(9, 1)
+                ri.set_tuning(8, split_node)
+                ri.AddObject(2, V, F.ravel())
+                nodes, tris, _ = ri.read_buffers()
+                assert tris.tobytes() == ref.tris.tobytes(), (name, split_node, first_diff(tris, ref.tris))
+                assert nodes.tobytes() == ref.nodes.tobytes(), (name, split_node, first_diff(nodes, ref.nodes))
+                ri.close()
+        ref = ob.build(fmt, v, i, m, swap_policy=ob.SWAP_HASHED, swap_seed=7)
+        ri = cb.RayIntersector(fmt)
+        ri.set_tuning(9, 1)
+        ri.AddObject(2, v, i, m, swap_policy=ob.SWAP_HASHED, swap_seed=7)
+        nodes, tris, _ = ri.read_buffers()
+        assert tris.tobytes() == ref.tris.tobytes() and nodes.tobytes() == ref.nodes.tobytes(), ("heightfield", first_diff(nodes, ref.nodes))
+        ri.close()
+
+
 @pytest.mark.parametrize("fmt", FORMATS)
 def test_build_bvh_free_function_with_triangle_offset(cb, ob, golden_meshes, fmt):
     """cndl_build_bvh == BVH::BuildBVH(object, nodes, vertices, triangles, t_offset) (BVHConstructor.h:86-87): the leaf packs carry

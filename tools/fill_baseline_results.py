@@ -48,7 +48,7 @@ is throughput served from L1/L2 (the measured limiter there is the L1 data pipe 
 | 4 through one process driving all GPUs (`cndl_multi_*`, `r2_multi_bench_n8.json`) | {min(m8["frame_ms_staged_copy_pipelined"], m8["frame_ms_peer_stores_pipelined"]):.1f} ms per frame at 8 GPUs (two frames in flight) including the copy of the frame to the host (single GPU {m8["single_device_frame_ms"]:.1f}); scene replication device to device: {m8["replicate_2M_tris_ms"]:.2f} ms for 2 M triangles to 7 peers | — | — | frame bit-identical to the single-GPU frame |
 | 5 — 10 M triangles, 100 M random rays | {soup1["mrays_s"] / 1e3:.2f} Grays/s on 1 GPU ({soup1["trace_ms_max_over_ranks"]:.1f} ms, in-call ray ordering counted), {soup8["mrays_s"] / 1e3:.1f} on 8 | **{soup1["roofline_frac_per_gpu"]:.2f}** per GPU (DRAM roofline, {soup1["bytes_per_ray"]} B/ray; round 1: 0.55) | {soup1["cpu_mrays_s"]:.1f} Mrays/s | 1 M-ray sample bit-identical |
 | BVH build, 262,624 triangles | {n1["build"]["gpu_ms"]:.2f} ms (exact binned SAH, both formats; LBVH 0.31 ms) | per-level latency | reference builder {r[1]["cpu_baseline"]["build_ms_reference_builder_1thread"]:.0f} ms, oracle port {r[1]["cpu_baseline"]["build_ms_port_1thread"]:.0f} ms, one thread | node and triangle buffers byte-identical to the compiled reference builder |
-| BVH build, 10 M triangles | {soup8["gpu_build_ms"]:.1f} ms (LBVH 3.6 ms) | — | {soup1["cpu_build_ms"]:,} ms | byte-identical |
+| BVH build, 10 M triangles | **19.0 ms** (`tools/exp/pack_ab.py`, tiny ranges packed four to a warp; {soup8["gpu_build_ms"]:.1f} ms in the `r2_configs` runs made before that change; LBVH 3.6 ms) | — | {soup1["cpu_build_ms"]:,} ms | byte-identical |
 '''
     p.write_text(s[: s.index("## 5. Results")] + new)
 

@@ -17,6 +17,7 @@ for fmt in (cb.STACKLESS, cb.STACK):
     for split in (0, 64, 1000):
         for (vv, ii, mm) in ((v, i, m), (soup_v, soup_i, None)):
             ri = cb.RayIntersector(fmt)
+            ri.set_tuning(9, 1)        # four tiny ranges per warp on every level (the default packs only large levels)
             ri.set_tuning(8, split)
             ri.AddObject(2, vv, ii, mm)
             n, t, _ = ri.read_buffers()
