@@ -132,3 +132,80 @@ def build_cases(ob, golden_meshes, fmt):
         lo, hi = Pd.min(0) - 1, Pd.max(0) + 1
         add(nm, s, rays_in_box(lo, hi, 3000, 4))
     return cases
+
+
+def random_mesh(kind, T, seed):
+    """Seeded meshes whose character stresses a different rule of the builder each: ties in the binning, zero-extent axes,
+    split failures, long thin boxes, clustered centroids."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-10, 10, size=(T, 1, 3))
+    if kind == "soup":
+        P = c + rng.normal(scale=0.3, size=(T, 3, 3))
+    elif kind == "quantised":          # coordinates on a coarse lattice: many equal centroids and bin-edge ties
+        P = np.round(c + rng.normal(scale=1.0, size=(T, 3, 3)))
+    elif kind == "flat":               # zero extent on y: the axis is skipped (BVHConstructor.cpp:285)
+        P = c + rng.normal(scale=0.5, size=(T, 3, 3))
+        P[..., 1] = 2.5
+    elif kind == "slivers":            # long thin triangles: boxes far larger than the centroid spread
+        P = c + rng.normal(scale=0.05, size=(T, 3, 3))
+        P[:, 2, :] += rng.normal(scale=8.0, size=(T, 3))
+    elif kind == "clusters":           # a few tight clusters far apart: most bins empty
+        k = rng.integers(0, 5, size=T)
+        P = (np.array([[-9, 0, 0], [9, 0, 0], [0, 9, 0], [0, 0, -9], [4, 4, 4]], np.float64)[k])[:, None, :] + rng.normal(scale=0.02, size=(T, 3, 3))
+    elif kind == "repeats":            # every triangle four times: split failures down the tree
+        base = c[: (T + 3) // 4] + rng.normal(scale=0.3, size=((T + 3) // 4, 3, 3))
+        P = np.repeat(base, 4, axis=0)[:T]
+    else:
+        raise ValueError(kind)
+    P = P.reshape(-1, 3).astype(np.float32)
+    F = np.arange(3 * T, dtype=np.uint32).reshape(-1, 3)
+    return P, F
+
+
+RANDOM_MESH_KINDS = ["soup", "quantised", "flat", "slivers", "clusters", "repeats"]
+
+
+def random_model(rng):
+    """A random affine instance matrix: rotation about a random axis, non-uniform scale (a factor may be negative: a mirrored
+    instance), shear now and then, translation."""
+    a = rng.normal(size=3)
+    a /= np.linalg.norm(a)
+    th = rng.uniform(0, 2 * np.pi)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+    S = np.diag(rng.uniform(0.3, 3.0, size=3) * rng.choice([1.0, 1.0, 1.0, -1.0], size=3))
+    if rng.random() < 0.3:
+        S[0, 1] = rng.uniform(-0.5, 0.5)
+    m = np.eye(4, dtype=np.float32)
+    m[:3, :3] = (R @ S).astype(np.float32)
+    m[:3, 3] = rng.uniform(-4, 4, size=3).astype(np.float32)
+    return m
+
+
+def random_scene(ob, fmt, seed):
+    """(scene, rays): 1-3 objects of random_mesh kinds (hashed child flips on some), 1-5 entities with random_model matrices,
+    translucency and emissive flags; 3000 rays from inside the scene's neighbourhood + 1000 aimed at it from far outside, every
+    seventh direction scaled by 2.5 (the shaders never renormalise, …Stackless.glsl:177-178)."""
+    from helpers import rays_in_box
+    rng = np.random.default_rng(100 + seed)
+    sc = ob.Scene(fmt)
+    n_obj = 1 + seed % 3
+    for k in range(n_obj):
+        P, F = random_mesh(RANDOM_MESH_KINDS[(seed + k) % len(RANDOM_MESH_KINDS)], int(rng.integers(100, 1500)), 31 * seed + k)
+        sc.add_object(2 + k, ob.make_vertices(P * np.float32(0.3)), F.ravel(), np.full(len(F), k + 1, np.int32),
+                      swap_policy=ob.SWAP_HASHED if (seed + k) % 2 else ob.SWAP_NONE, swap_seed=seed)
+    for e in range(1 + 2 * (seed % 3)):
+        sc.push_entity(2 + int(rng.integers(0, n_obj)), model=random_model(rng) if e or seed % 2 else None,
+                       emissive=float(rng.random() < 0.3) * 2.0, translucency=float(rng.choice([0.0, 0.0, 0.005, 0.5])))
+    rays = rays_in_box((-6, -6, -6), (6, 6, 6), 3000, 50 + seed)
+    far = rays_in_box((-40, -40, -40), (40, 40, 40), 1000, 70 + seed)
+    far["d"] = -far["o"] / np.linalg.norm(far["o"], axis=1, keepdims=True) + rng.normal(scale=0.1, size=(1000, 3)).astype(np.float32)
+    rays = np.concatenate([rays, far])
+    rays["d"][::7] *= np.float32(2.5)
+    return sc, np.ascontiguousarray(rays)
+
+
+def random_scene_queries(ob, seed):
+    """(kind, tmax) pairs of the sweep; the short any-hit range varies with the seed."""
+    t = float(np.random.default_rng(seed).uniform(0.5, 5.0))
+    return ((ob.CLOSEST, 0.0), (ob.CLOSEST_IGNORE_TRANSPARENT, 0.0), (ob.ANY, 0.0), (ob.ANY, t))

@@ -38,6 +38,26 @@ def test_gpu_build_is_byte_identical(cb, ob, golden_meshes, name, fmt):
     ri.close()
 
 
+@pytest.mark.parametrize("kind", ["soup", "quantised", "flat", "slivers", "clusters", "repeats"])
+def test_gpu_build_random_mesh_sweep(cb, ob, kind):
+    """Seeded random meshes (tests/cases.py: bin-edge ties, a zero-extent axis, repeated triangles, slivers, clusters) at sizes
+    either side of the builder's size classes (64 / 512 / 16384 references per range): both formats byte-identical to the oracle,
+    which tests/test_oracle_builder.py pins to the compiled reference builder on the same meshes."""
+    import cases
+    for n, T in enumerate([100, 513, 2049, 4500, 17000, 40000]):
+        P, F = cases.random_mesh(kind, T, 1000 * n + 7)
+        V = ob.make_vertices(P)
+        mids = (np.arange(T) % 3).astype(np.int32)
+        for fmt in FORMATS:
+            ref = ob.build(fmt_id(ob, fmt), V, F.ravel(), mids)
+            ri = cb.RayIntersector(fmt_id(ob, fmt))
+            ri.AddObject(2, V, F.ravel(), mids)
+            nodes, tris, _ = ri.read_buffers()
+            assert tris.tobytes() == ref.tris.tobytes(), (kind, T, fmt, first_diff(tris, ref.tris))
+            assert nodes.tobytes() == ref.nodes.tobytes(), (kind, T, fmt, first_diff(nodes, ref.nodes))
+            ri.close()
+
+
 @pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 7, 50, 129])
 def test_tiny_meshes(cb, ob, T, fmt):

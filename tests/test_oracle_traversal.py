@@ -217,3 +217,27 @@ def test_direction_samplers_vs_compiled_reference(ob):
     assert np.abs(ob.sample_directions(ob.SAMPLE_COS_HEMISPHERE, normals=N, xi=xi) - libm).max() < 5e-7
     for rough in (0.27, 0.72):
         assert np.abs(ob.sample_directions(ob.SAMPLE_GGX_VNDF, normals=N, xi=xi, roughness=rough) - ob.ref_sample(1, N, xi, rough)).max() < 5e-7
+
+
+
+def test_oracle_vs_compiled_reference_glsl_random_scene_sweep(ob):
+    """The pin of the traversal restatement on scenes nobody looked at (cases.random_scene: seeded random meshes, several
+    objects, random affine instances incl. mirrored and sheared ones, translucent and emissive entities, rays from inside and
+    outside the scene, unnormalised directions): all four query kinds, both node formats, against the compiled reference GLSL."""
+    if not ob.REFERENCE_ROOT.exists():
+        pytest.skip("/root/reference is not present (GPU box): the committed fixture covers this")
+    import cases
+    n = n_hit = 0
+    for seed in range(6):
+        for fmt in (ob.STACKLESS, ob.STACK):
+            sc, rays = cases.random_scene(ob, fmt, seed)
+            for kind, tmax in cases.random_scene_queries(ob, seed):
+                r = rays.copy()
+                r["tmax"] = tmax
+                mine, _ = sc.trace(kind, r, nthreads=ob.hardware_threads())
+                ref = ob.ref_glsl_trace(fmt, kind, sc.nodes, sc.tris, sc.verts, sc.entities, r, nthreads=ob.hardware_threads())
+                assert mine.tobytes() == ref.tobytes(), (seed, fmt, kind, tmax)
+                n += len(r)
+            hits, _ = sc.trace(ob.CLOSEST, rays)
+            n_hit += int(np.count_nonzero(hits["t"] > 0))
+    assert n >= 6 * 2 * 4 * 4000 and n_hit > 5000, "the sweep must actually hit things"
