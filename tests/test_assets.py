@@ -1,8 +1,12 @@
 """Scene ingest (OBJ -> Vertex packing of ModelFileLoader.cpp:101-185) and the flat-buffer BVH cache —
 SURVEY.md §8f ranks 3 and 4a.  The half-float packing is PINNED against glm::packHalf2x16 of the reference's
 vendored glm, compiled into oracle/_ref."""
+from pathlib import Path
+
 import numpy as np
 import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
 
 
 def _glm_like_pack(x):
@@ -274,3 +278,23 @@ def test_loaded_model_builds_and_cache_round_trips(cb, ob, golden_meshes, tmp_pa
         with pytest.raises(cb.CandelaError, match="node format"):
             other.Load(cache)
         other.close(); r2.close(); ri.close()
+
+
+def test_loader_survives_fuzzing_under_asan(tmp_path):
+    """The host-side readers under AddressSanitizer + UBSan (tools/fuzz/): byte-level mutations of valid OBJ / glTF / GLB seeds and
+    syntactically valid glTF documents whose fields lie (counts, offsets, strides, indices, node cycles, deep chains, container
+    lengths).  Every case must load or be refused with an error string — any sanitizer report fails the run.  (Short run; the
+    tools run hundreds of thousands of cases.)"""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    probe = subprocess.run(["g++", "-fsanitize=address,undefined", "-x", "c++", "-", "-o", str(tmp_path / "probe")], input="int main(){return 0;}", text=True,
+                           capture_output=True)
+    if probe.returncode != 0:
+        pytest.skip("g++ has no sanitizer runtime here")
+    r = subprocess.run(["bash", str(ROOT / "tools" / "fuzz" / "run_fuzz_loader.sh"), "400", "5", str(tmp_path / "mut")], capture_output=True, text=True)
+    assert r.returncode == 0 and "no sanitizer report" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "fuzz" / "craft_gltf.py"), "250", "5", str(tmp_path / "craft")], capture_output=True, text=True)
+    assert r.returncode == 0 and "no sanitizer report" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
