@@ -131,6 +131,27 @@ def build_cases(ob, golden_meshes, fmt):
         s.push_entity(2)
         lo, hi = Pd.min(0) - 1, Pd.max(0) + 1
         add(nm, s, rays_in_box(lo, hi, 3000, 4))
+    # ties (SURVEY.md §8c "tie on a shared edge"): the 12 x 12 integer grid in the plane z = 0, rays through its vertices (shared by up
+    # to six triangles), edge midpoints and diagonal midpoints.  Every coordinate is a small integer or a half, so every product is
+    # exact: two to six triangles report the SAME t with u, v of exactly 0, 0.5 or 1, RayTriangle accepts all of them (its test is
+    # u < 0 || v < 0 || u + v > 1) and the strict t < TMax keeps the first one the walk meets.
+    Pg, Fg = golden_meshes["coplanar_grid"]
+    sg = ob.Scene(fmt)
+    sg.add_object(2, ob.make_vertices(Pg), Fg.ravel(), (np.arange(len(Fg)) % 4).astype(np.int32))
+    sg.push_entity(2)
+    k = np.arange(13, dtype=np.float32)
+    h = np.arange(12, dtype=np.float32) + np.float32(0.5)
+    pts = np.concatenate([np.stack(np.meshgrid(a, b, indexing="ij"), -1).reshape(-1, 2) for a, b in ((k, k), (h, k), (k, h), (h, h))]).astype(np.float32)
+    tr = np.zeros(3 * len(pts), dtype=ob.RAY_DT)
+    n = len(pts)
+    tr["o"][:n] = np.concatenate([pts, np.full((n, 1), 3, np.float32)], 1)                 # straight down
+    tr["d"][:n] = (0, 0, -1)
+    tr["o"][n:2 * n] = np.concatenate([pts, np.full((n, 1), -2, np.float32)], 1)           # straight up, from below
+    tr["d"][n:2 * n] = (0, 0, 1)
+    tr["o"][2 * n:] = np.concatenate([pts - np.float32([1.5, 0.5]), np.full((n, 1), 1, np.float32)], 1)   # oblique, unnormalised, still exact: lands on pts
+    tr["d"][2 * n:] = (1.5, 0.5, -1)
+    tr["tmax"] = 1.0e6
+    add("shared_edges", sg, tr)
     return cases
 
 

@@ -5,7 +5,7 @@ import numpy as np
 
 import cases
 
-LIMIT = {"dragon_random": 4096, "dragon_axis_parallel": 1536, "multi_entity": 3072}
+LIMIT = {"dragon_random": 4096, "dragon_axis_parallel": 1536, "multi_entity": 3072, "shared_edges": 4096}
 KINDS = (("closest", 0, 0.0), ("ignore_transparent", 1, 0.0), ("any", 2, 0.0), ("any_tmax", 2, 2.4))
 
 
