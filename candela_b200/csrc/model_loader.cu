@@ -60,6 +60,19 @@ std::uint16_t to_float16(float f) {
     return (std::uint16_t)(s | (e << 10) | (m >> 13));
 }
 
+// One whole text line of any length (fgets into a buffer that grows): a statement is never cut in two — a polygon with thousands
+// of corners, or a long comment whose tail would otherwise be read as a statement of its own.
+bool read_line(std::FILE* f, std::vector<char>& buf) {
+    size_t have = 0;
+    for (;;) {
+        if (!std::fgets(buf.data() + have, (int)(buf.size() - have), f)) return have > 0;
+        have += std::strlen(buf.data() + have);
+        if (have && buf[have - 1] == '\n') return true;
+        if (have + 1 < buf.size()) return true;          // end of file without a newline (or an embedded NUL: the rest of the line is dropped)
+        buf.resize(buf.size() * 2);
+    }
+}
+
 struct V3 {
     float x = 0.0f, y = 0.0f, z = 0.0f;
     V3 operator-(const V3& o) const { return {x - o.x, y - o.y, z - o.z}; }
@@ -202,7 +215,7 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
             const size_t sp = r.find_last_of(" \t");
             return sp == std::string::npos ? r : r.substr(sp + 1);
         };
-        while (std::fgets(ml.data(), (int)ml.size(), mf)) {
+        while (read_line(mf, ml)) {
             char* q = ml.data();
             while (*q == ' ' || *q == '\t') ++q;
             if (std::strncmp(q, "newmtl", 6) == 0) cur = &materials[rest(q + 6)];
@@ -282,7 +295,7 @@ int cndl_model_load_obj(const char* path, int32_t first_mesh_number, cndl_model*
     std::vector<char> line(1 << 16);
     long lineno = 0;
     std::string problem;
-    while (std::fgets(line.data(), (int)line.size(), f)) {
+    while (read_line(f, line)) {
         ++lineno;
         char* s = line.data();
         while (*s == ' ' || *s == '\t') ++s;

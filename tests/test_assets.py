@@ -298,3 +298,19 @@ def test_loader_survives_fuzzing_under_asan(tmp_path):
     assert r.returncode == 0 and "no sanitizer report" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
     r = subprocess.run([sys.executable, str(ROOT / "tools" / "fuzz" / "craft_gltf.py"), "250", "5", str(tmp_path / "craft")], capture_output=True, text=True)
     assert r.returncode == 0 and "no sanitizer report" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_obj_lines_of_any_length(cb, tmp_path):
+    """A statement is never cut in two: a 70,000-character comment whose tail looks like a vertex statement adds no vertex, and a
+    polygon whose `f` line is longer than any fixed buffer is fan-triangulated whole."""
+    n = 20000
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    lines = ["# " + "x" * 65533 + "v 9 9 9 and more comment"]           # the tail starts exactly where a 64 KiB buffer would have ended
+    lines += [f"v {np.cos(a):.7f} {np.sin(a):.7f} 0" for a in ang]
+    lines.append("f " + " ".join(str(k + 1) for k in range(n)))           # one convex polygon, ~129 KB of text
+    p = tmp_path / "long.obj"
+    p.write_text("\n".join(lines))                                         # no newline at the end of the file either
+    verts, idx, mids, names = cb.api.load_obj(p)
+    assert len(idx) == 3 * (n - 2) and len(mids) == n - 2
+    assert len(verts) == n
+    assert float(np.abs(verts["position"][:, :3]).max()) <= 1.0 + 1e-6      # the comment's "v 9 9 9" never became a vertex
