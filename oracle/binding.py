@@ -37,10 +37,10 @@ assert (VERTEX_DT.itemsize, TRIANGLE_DT.itemsize, NODE32_DT.itemsize, NODE64_DT.
 
 def build_library(force: bool = False) -> Path:
     """Compiles oracle/liboracle.so (and oracle/_ref when /root/reference exists)."""
-    srcs = [HERE / "oracle_build.cpp", HERE / "oracle_trace.cpp", HERE / "oracle.h"]
+    srcs = [HERE / "oracle_build.cpp", HERE / "oracle_trace.cpp", HERE / "oracle_raygen.cpp", HERE / "oracle.h", HERE / "exact_math_ref.h"]
     stale = force or not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
     if stale:
-        subprocess.run(["make", "-C", str(HERE), "all"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", str(HERE), "all"] + (["-B"] if force else []), check=True, capture_output=True)
     if REFERENCE_ROOT.exists():  # make decides whether oracle/_ref is stale (it depends on the shim sources)
         subprocess.run(["make", "-C", str(HERE), "ref"] + (["-B"] if force else []), check=True, capture_output=True)
     return LIB_PATH
